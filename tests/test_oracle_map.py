@@ -1,0 +1,137 @@
+"""Pins the oracle's map_read on every known answer and property the reference's own tests
+hold for the path, then cross-checks it against an independent pure-Python restatement."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import orc
+import pyref
+import util
+
+EX1 = "GGCTGTCAACCAGTCCATAGGCAGGGCCATCAGGCACCAAAGGGATTCTGCCAGCATAGT"         # ref src/build_index.rs:429-431
+SINGLE_SNP = "GGCTGTCAACCAGTCCATAGGCGGGGCCATCAGGCACCAAAGGGATTCTGCCAGCATAGT"  # :436-438
+TWO_SNPS = "GGCTGTCAACCAGTCCATAGGCGGGGCCATCAGGCACCAAAGGGATTCTGCCAGCGTAGT"    # :443-445 (no asserted answer upstream)
+
+
+def test_alignment_known_answers(orc_index_for):
+    """test_alignment, ref src/build_index.rs:423-451 (dead code upstream, answers verified
+    by brute force in SURVEY.md section 4)."""
+    ix = orc_index_for(20)
+    assert ix.map_read(EX1) == ([1, 30], 60)
+    assert ix.map_read(SINGLE_SNP) == ([1, 30], 60)
+    # upstream re-queries single_snp for the third case (:446); both stated for completeness
+    assert ix.map_read(SINGLE_SNP)[1] == len(TWO_SNPS)
+    assert ix.map_read(TWO_SNPS) == ([1, 30], 60)
+
+
+# ---- intersect: ref src/pseudoaligner.rs:542-586
+INTERSECT_VECS = [
+    [1, 2, 3, 4, 5, 6, 7, 8, 9], [1, 2, 3], [1, 4, 5], [7, 8, 9], [9], [], [1, 2, 3, 6, 7, 8, 9],
+    [1, 7, 8, 9, 10], [10, 15, 20], [21, 22, 23], [0], [0, 1000, 5000], [0, 1000, 1000001], [5],
+    [100000000], [1, 23, 45, 1000001, 100000000],
+]
+
+
+def test_intersect_vectors():
+    for a in INTERSECT_VECS:
+        for b in INTERSECT_VECS:
+            want = sorted(set(a) & set(b))
+            assert orc.intersect(a, b) == want
+            assert orc.intersect(b, a) == want
+            assert pyref.intersect(list(a), b) == want
+
+
+@settings(max_examples=1000, deadline=None)
+@given(st.lists(st.integers(0, 99), max_size=5000), st.lists(st.integers(0, 99), max_size=5000))
+def test_intersect_property(v1, v2):
+    v1 = sorted(set(v1)); v2 = sorted(set(v2))
+    want = sorted(set(v1) & set(v2))
+    assert orc.intersect(v1, v2) == want
+    assert orc.intersect(v2, v1) == want
+
+
+# ---- test/small.fq: no golden output upstream (parity unpinned); derivable properties only
+def test_small_fq_properties(orc_index_for, fixture_fasta, fixture_fastq):
+    ix = orc_index_for(20)
+    seqs = [s.decode() for s in fixture_fasta[1]]
+    words, off, lens = orc.pack_reads([s for _, s in fixture_fastq])
+    hits, tx, counts, ev = ix.map_batch(words, off, lens, counts=True)
+    res = orc.hits_to_tuples(hits, tx)
+    n_exact = n_rev_none = n_rev = 0
+    for (rid, s), (aligned, flag, eq, cov) in zip(fixture_fastq, res):
+        if rid.endswith("_rev"):
+            n_rev += 1
+            n_rev_none += (not aligned)
+        elif "_err" not in rid:
+            assert aligned and cov == 60
+            # the read is an exact 60-base FASTA line: every transcript in eq contains it
+            assert eq and all(s in seqs[t] for t in eq)
+            n_exact += 1
+        assert flag == (aligned and cov >= 32 and len(eq) == 0)   # QUIRK-4
+    assert n_exact == 3103 and n_rev == 3103
+    assert n_rev_none > 2900
+    assert ev["reads"] == 9309 and int(counts.sum()) == 9309
+
+
+def test_small_fq_oracle_vs_pyref(orc_index_for, fixture_fastq):
+    ix = orc_index_for(20)
+    pix = pyref.PyIndex(ix.flat())
+    for rid, s in fixture_fastq[::7]:
+        assert ix.map_read(s) == _t(pyref.map_read(pix, s)), rid
+
+
+def _t(r):
+    return None if r is None else (r[0], r[1])
+
+
+# ---- C oracle vs pure-Python restatement on mixed / adversarial reads
+@pytest.mark.parametrize("k,length", [(20, 150), (20, 60), (24, 91), (64, 150)])
+def test_oracle_vs_pyref_fixture(orc_index_for, fixture_fasta, k, length):
+    ix = orc_index_for(k)
+    pix = pyref.PyIndex(ix.flat())
+    rng = np.random.default_rng(k * 1000 + length)
+    reads = util.sample_reads(rng, fixture_fasta[1], 1500, length, p_sub=0.005)
+    reads += util.sample_reads(rng, fixture_fasta[1], 1500, length, p_sub=0.04, mix=(0.8, 0.2, 0.0))
+    reads += util.sample_reads(rng, fixture_fasta[1], 300, length, p_sub=0.01, n_rate=0.01)
+    n_some = 0
+    for r in reads:
+        got = ix.map_read(r)
+        assert got == _t(pyref.map_read(pix, r)), r
+        n_some += got is not None
+    assert n_some > (2500 if k < 64 else 1800)
+
+
+@pytest.mark.parametrize("k", [5, 19, 31, 32, 33, 47, 64])
+def test_oracle_vs_pyref_random_transcriptomes(k):
+    rng = np.random.default_rng(k)
+    for rep in range(2):
+        seqs = util.random_transcriptome(rng, n_genes=8, k=k)
+        ix = orc.OrcIndex.build(seqs, k)
+        pix = pyref.PyIndex(ix.flat())
+        for length in (k, k + 1, 2 * k + 3, 150):
+            reads = util.sample_reads(rng, seqs, 250, length, p_sub=0.03, mix=(0.7, 0.25, 0.05)) \
+                if any(len(s) >= length for s in seqs) else []
+            reads += ["A" * length, "ACG" * (length // 3 + 1), "T" * length]
+            for r in reads:
+                r = r[:length]
+                assert ix.map_read(r) == _t(pyref.map_read(pix, r)), (k, length, r)
+        assert ix.map_read("ACGT"[:k - 1] if k <= 4 else "A" * (k - 1)) is None     # L < k -> None (:82-84)
+
+
+def test_batch_equals_single(orc_index_for, fixture_fasta):
+    ix = orc_index_for(20)
+    rng = np.random.default_rng(5)
+    reads = util.sample_reads(rng, fixture_fasta[1], 400, 150, p_sub=0.02)
+    reads += ["", "ACGT", "A" * 19, "A" * 20]                       # empty / shorter than k / == k
+    words, off, lens = orc.pack_reads(reads)
+    hits, tx, counts, ev = ix.map_batch(words, off, lens, counts=True)
+    res = orc.hits_to_tuples(hits, tx)
+    for r, (aligned, flag, eq, cov) in zip(reads, res):
+        single = ix.map_read(r)
+        if single is None:
+            assert not aligned and eq == () and cov == 0 and not flag
+        else:
+            assert aligned and list(eq) == single[0] and cov == single[1]
+    assert ev["reads"] == len(reads) and ev["aligned"] == sum(1 for x in res if x[0])
+    assert int(counts.sum()) == len(reads)
+    assert int(counts[-1]) == sum(1 for x in res if not x[0])
