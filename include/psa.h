@@ -1,0 +1,233 @@
+/*
+ * psa.h -- C ABI of the B200-native pseudoalignment hot path.
+ *
+ * This is the drop-in boundary for ONE path of 10XGenomics/rust-pseudoaligner (crate
+ * debruijn_mapping 0.6.0, commit 9d9cab8): Pseudoaligner::map_read and the process_reads
+ * inner loop.  The reference has no FFI of its own (everything is generic Rust), so every
+ * entry point below names the reference item it replaces; "ref" = /root/reference.
+ * INTEGRATION.md shows the Rust `extern "C"` block and the patch to process_reads that
+ * binds them.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; 0 = success, negative = error
+ * (psa_strerror); no exceptions or aborts cross the ABI; the caller owns every host buffer,
+ * the library owns every device buffer; nothing here ever falls back to the CPU -- without a
+ * CUDA device the calls that need one return PSA_ERR_CUDA.
+ */
+#ifndef PSA_H
+#define PSA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSA_ABI_VERSION 1
+
+/* ---- status codes ---- */
+#define PSA_OK 0
+#define PSA_ERR_ARG (-1)      /* bad argument                                              */
+#define PSA_ERR_CUDA (-2)     /* CUDA runtime error (psa_last_error has the text)          */
+#define PSA_ERR_NOMEM (-3)    /* host allocation failed                                    */
+#define PSA_ERR_CAPACITY (-4) /* tx_buf too small; *tx_used holds the size needed          */
+#define PSA_ERR_INDEX (-5)    /* graph is not a valid index: duplicate k-mer, ext bit whose
+                                 neighbour is missing ("missing link" in debruijn), eq id
+                                 out of range                                              */
+#define PSA_ERR_NCCL (-6)     /* NCCL error or libnccl not loadable                        */
+#define PSA_ERR_IO (-7)       /* file could not be read / parsed                           */
+
+const char* psa_strerror(int code);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* psa_last_error(void);
+int psa_abi_version(void);
+
+/* ---- constants of the path (ref src/config.rs:16-18, stride literal src/pseudoaligner.rs:110) */
+#define PSA_READ_COVERAGE_THRESHOLD 32u
+#define PSA_DEFAULT_ALLOWED_MISMATCHES 2u
+#define PSA_SEED_STRIDE 3u
+#define PSA_EQ_NONE 0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------------------------
+ * The index.  Replaces the read-only use of `Pseudoaligner<K>` (ref src/pseudoaligner.rs:26-33)
+ * at map time.  The caller flattens `dbg` and `eq_classes` through debruijn's public accessors
+ * (dbg.len(), get_node(i).sequence()/exts()/data()); `dbg_index` (boomphf's private
+ * bit-vectors) is NOT passed: psa_index_create rebuilds a minimal perfect hash of every
+ * k-mer -> (node, offset) on the GPU (what make_dbg_index does, ref src/build_index.rs:182-221)
+ * together with the successor/predecessor tables that Node::r_edges()/l_edges() compute on
+ * the fly.  That is legal because every MPHF answer is verified against the unitig
+ * (ref src/pseudoaligner.rs:99-107), so only dictionary membership reaches the output.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct psa_index psa_index; /* opaque, immutable after create, shareable across threads */
+
+typedef struct psa_index_desc { /* all pointers host memory, borrowed for the call only */
+    uint32_t k;                 /* K::k(), 2..64.  k <= 32 runs the 64-bit k-mer kernels,
+                                   k <= 64 the 128-bit ones (Kmer64 of the CLI)             */
+    uint32_t reserved;
+    uint64_t n_nodes;           /* dbg.len()                                                */
+    const uint64_t* seq_words;  /* all node sequences concatenated, debruijn DnaString
+                                   packing: base i in word i/32 at bits 62-2*(i%32),
+                                   A0 C1 G2 T3                                              */
+    uint64_t n_seq_words;
+    const uint64_t* node_start; /* first base of node i in the concatenation                */
+    const uint32_t* node_len;   /* node.sequence().len(), >= k                              */
+    const uint8_t* node_exts;   /* bit b = right extension with base b, bit 4+b = left
+                                   extension with base b (debruijn Exts{val})               */
+    const uint32_t* node_eq;    /* *node.data(): equivalence-class id                       */
+    uint64_t n_eq;              /* eq_classes.len()                                         */
+    const uint64_t* eq_offsets; /* n_eq+1, CSR over eq_members                              */
+    const uint32_t* eq_members; /* eq_classes[c]: ascending, unique transcript ids
+                                   (ref src/equiv_classes.rs:78-79)                         */
+} psa_index_desc;
+
+typedef struct psa_index_info {
+    uint32_t k;
+    uint32_t mphf_levels;
+    uint64_t n_nodes, n_kmers, n_eq, n_eq_members, n_seq_words;
+    uint64_t mphf_bytes, values_bytes, node_bytes, seq_bytes, eq_bytes; /* device residency */
+    uint32_t node_bits, off_bits, fp_bits; /* packing of one `values` entry               */
+    uint32_t max_class_len;
+    double gamma;
+    double build_ms; /* device time of the MPHF/edge build                                  */
+} psa_index_info;
+
+/* gamma <= 0 selects the reference's 1.7 (ref src/build_index.rs:197). */
+int psa_index_create(const psa_index_desc* desc, int device, double gamma, psa_index** out);
+void psa_index_destroy(psa_index*);
+int psa_index_get_info(const psa_index*, psa_index_info* out);
+/* dbg_index.get(kmer) + verification (ref src/pseudoaligner.rs:96-107) for n k-mers given
+ * as packed words (k bases from base 0; 1 word per k-mer if k<=32 else 2).  found[i] = 1 and
+ * node/off filled when the k-mer is in the graph.  Diagnostic / test entry. */
+int psa_index_lookup(psa_index*, const uint64_t* kmer_words, uint64_t n, uint8_t* found,
+                     uint32_t* node, uint32_t* off);
+
+/* ------------------------------------------------------------------------------------------
+ * Reads and results
+ * ---------------------------------------------------------------------------------------- */
+#define PSA_READS_ASCII 0u  /* record.seq() bytes; packed on the GPU exactly as
+                               DnaString::from_dna_string does at ref src/pseudoaligner.rs:449-450:
+                               A/a 0, C/c 1, G/g 2, T/t 3, anything else 0                  */
+#define PSA_READS_PACKED 1u /* DnaString storage words, read i starting at word read_off[i] */
+#define PSA_MEM_HOST 0u
+#define PSA_MEM_DEVICE 1u
+
+typedef struct psa_read_batch {
+    uint32_t format;          /* PSA_READS_*                                                */
+    uint32_t location;        /* PSA_MEM_*: where data/read_off/read_len live               */
+    const void* data;         /* bytes (ASCII) or uint64 words (PACKED)                     */
+    uint64_t data_len;        /* in bytes / words                                           */
+    const uint64_t* read_off; /* n_reads offsets into data (bytes / words); NULL: read i
+                                 starts at i*stride                                          */
+    const uint32_t* read_len; /* n_reads lengths in bases; NULL: every read has fixed_len    */
+    uint64_t stride;          /* used when read_off == NULL                                 */
+    uint32_t fixed_len;       /* used when read_len == NULL                                 */
+    uint32_t reserved;
+    uint64_t n_reads;
+} psa_read_batch;
+
+#define PSA_FLAG_ALIGNED 1u /* map_read returned Some(..)                                    */
+#define PSA_FLAG_MAPPED 2u  /* the bool process_reads prints: coverage >= 32 &&
+                               eq_class.is_empty() (sic, ref src/pseudoaligner.rs:455)       */
+
+typedef struct psa_hit {    /* one per read, input order                                    */
+    uint32_t coverage;      /* read_coverage; 0 for None                                    */
+    uint32_t n_tx;          /* eq_class.len()                                               */
+    uint64_t tx_off;        /* eq_class = tx_buf[tx_off .. tx_off+n_tx), ascending          */
+    uint32_t eq_id;         /* id of the index class equal to eq_class when one of the
+                               visited nodes carries it (smallest such id), else PSA_EQ_NONE */
+    uint32_t flags;         /* PSA_FLAG_*                                                   */
+} psa_hit;
+
+typedef struct psa_result_batch {
+    uint32_t location; /* PSA_MEM_*: where hits / tx_buf live                                */
+    uint32_t reserved;
+    psa_hit* hits;     /* n_reads                                                            */
+    uint32_t* tx_buf;  /* members of every eq_class back to back in read order; NULL = skip  */
+    uint64_t tx_cap;   /* capacity of tx_buf in entries                                      */
+    uint64_t tx_used;  /* out: entries written (or needed, with PSA_ERR_CAPACITY)            */
+} psa_result_batch;
+
+/* ------------------------------------------------------------------------------------------
+ * The mapper: mutable per-caller state (device staging, per-class counts).  One per host
+ * thread or pipeline; many mappers may share one index.  Replaces the worker-thread body of
+ * process_reads (ref src/pseudoaligner.rs:440-472) for a whole batch of records at once.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct psa_mapper psa_mapper;
+
+/* chunk_reads: reads per internal pipeline chunk for host-resident batches (0 = default). */
+int psa_mapper_create(psa_index*, uint64_t chunk_reads, psa_mapper** out);
+void psa_mapper_destroy(psa_mapper*);
+/* ref src/pseudoaligner.rs:382: DEFAULT_ALLOWED_MISMATCHES; map_read_with_mismatch (:361) takes any. */
+int psa_mapper_set_allowed_mismatches(psa_mapper*, uint32_t allowed);
+
+/* Pseudoalign a batch.  For every read i: hits[i] and its members in tx_buf are exactly
+ * what `index.map_read(&DnaString::from_dna_string(seq_i))` returns (ref :381-384, :449-462).
+ * Host batches are cut into chunks and pipelined (H2D | kernels | D2H on separate streams);
+ * device batches run in place on the mapper's stream.  Synchronous: results are complete
+ * on return.  Per-class counts accumulate across calls until psa_mapper_counts_reset. */
+int psa_mapper_map(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results);
+
+/* Device-resident batch, asynchronous on the mapper's stream, fixed shape helpers for
+ * benchmarking: same as psa_mapper_map with location == PSA_MEM_DEVICE but does not
+ * synchronise; results->tx_used is valid after psa_mapper_sync. */
+int psa_mapper_map_async(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results);
+int psa_mapper_sync(psa_mapper*);
+void* psa_mapper_stream(psa_mapper*); /* cudaStream_t */
+
+/* Pseudoaligner::map_read for one read (ref src/pseudoaligner.rs:381): returns 1 = Some,
+ * 0 = None, <0 error.  Convenience over psa_mapper_map; one launch per call. */
+int psa_mapper_map_read(psa_mapper*, const uint64_t* read_words, uint32_t read_len,
+                        uint32_t* tx_out, uint64_t tx_cap, uint32_t* n_tx, uint32_t* coverage);
+
+/* counts[c] for c < n_eq: reads whose eq_class equals index class c; counts[n_eq]: aligned
+ * reads whose set is no visited class (incl. the empty set); counts[n_eq+1]: None.
+ * The array has n_eq+2 entries. */
+int psa_mapper_counts_get(psa_mapper*, uint64_t* counts_host);
+int psa_mapper_counts_reset(psa_mapper*);
+void* psa_mapper_counts_device(psa_mapper*); /* uint64[n_eq+2] in HBM */
+
+/* Work actually done by the mapper's kernels since the last reset, in the units of the
+ * algorithmic-bytes model of DESIGN.md (sequential-equivalent events: speculative probes
+ * of the warp-wide seed scan are not counted). Filled only by psa_mapper_map_events. */
+typedef struct psa_events {
+    uint64_t reads, read_bases;
+    uint64_t kmer_lookups;   /* P: the reference's own counter (src/pseudoaligner.rs:95)     */
+    uint64_t mphf_levels;    /* bit-vector blocks probed                                     */
+    uint64_t mphf_hits;      /* probes that reached `values`                                 */
+    uint64_t verifications;  /* unitig k-mer fetched and compared                            */
+    uint64_t node_visits;    /* nodes.push                                                   */
+    uint64_t bases_compared; /* base compares of both extension loops                        */
+    uint64_t edge_jumps;
+    uint64_t class_members;  /* members of visited distinct classes read by the intersection */
+    uint64_t out_members;    /* sum |eq_class|                                               */
+    uint64_t aligned;
+} psa_events;
+/* Same as psa_mapper_map on a device batch, with event counting compiled in (slower). */
+int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results,
+                          psa_events* out);
+
+/* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
+uint64_t psa_mapper_launch_count(const psa_mapper*);
+
+/* ---- multi-GPU: reads shard across ranks, one all-reduce of the per-class counts ---- */
+typedef struct psa_comm psa_comm;
+#define PSA_NCCL_UNIQUE_ID_BYTES 128
+int psa_comm_unique_id(uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES]); /* rank 0; ship to the others */
+int psa_comm_create(const uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES], int world, int rank, int device,
+                    psa_comm** out);
+void psa_comm_destroy(psa_comm*);
+/* ncclAllReduce(sum, uint64, n_eq+2) in place on the mapper's counts, on its stream. */
+int psa_mapper_counts_allreduce(psa_mapper*, psa_comm*);
+
+/* ---- pinned host memory for the batch buffers (pageable memory works, slower) ---- */
+int psa_host_alloc(void** out, uint64_t bytes);
+void psa_host_free(void*);
+/* ---- raw device memory, for callers that keep batches resident in HBM ---- */
+int psa_device_alloc(void** out, uint64_t bytes);
+void psa_device_free(void*);
+int psa_memcpy_h2d(void* dst_dev, const void* src_host, uint64_t bytes);
+int psa_memcpy_d2h(void* dst_host, const void* src_dev, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSA_H */

@@ -1,0 +1,1036 @@
+// psa_api.cu -- the C ABI of include/psa.h: index upload + on-device MPHF/edge construction,
+// the mapper (batch pipeline around k_map), counts, NCCL all-reduce of the counts.
+// There is no CPU implementation of any of this: without a CUDA device every compute entry
+// returns PSA_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+#include <string>
+#include <vector>
+
+#include "../../include/psa.h"
+#include "psa_kernels.cuh"
+
+using namespace psa;
+
+static_assert(sizeof(HitRec) == sizeof(psa_hit), "HitRec must mirror psa_hit");
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            return fail(PSA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                          \
+    } while (0)
+
+extern "C" const char* psa_strerror(int code) {
+    switch (code) {
+        case PSA_OK: return "ok";
+        case PSA_ERR_ARG: return "bad argument";
+        case PSA_ERR_CUDA: return "CUDA error";
+        case PSA_ERR_NOMEM: return "out of host memory";
+        case PSA_ERR_CAPACITY: return "output buffer too small";
+        case PSA_ERR_INDEX: return "invalid index graph";
+        case PSA_ERR_NCCL: return "NCCL error";
+        case PSA_ERR_IO: return "I/O error";
+        default: return "unknown error";
+    }
+}
+extern "C" const char* psa_last_error(void) { return g_err.c_str(); }
+extern "C" int psa_abi_version(void) { return PSA_ABI_VERSION; }
+
+static inline unsigned nblocks(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---------------------------------------------------------------------------------------------
+// small device buffer
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {  // contents are NOT preserved on growth
+        if (bytes <= cap) return PSA_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return PSA_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// index
+// ---------------------------------------------------------------------------------------------
+struct psa_index {
+    int device = 0;
+    DevIndex d{};
+    DevBuf blocks, values, nodes, seq, eq_off, eq_mem;
+    psa_index_info info{};
+    int kw = 1;
+};
+
+static uint32_t bits_for(uint64_t max_value) {  // bits needed to store 0..max_value
+    uint32_t b = 1;
+    while (b < 64 && (max_value >> b)) b++;
+    return b;
+}
+
+template <int KW>
+static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma, DevBuf& node_start,
+                           const std::vector<uint64_t>& koff_host, uint64_t n_kmers) {
+    const uint32_t k = d->k;
+    cudaStream_t st = 0;
+    DevBuf koff, key_lo[3], key_hi[3], val[3], coll, cursor, err, cnt, rank, tmp;
+    auto cleanup = [&]() {
+        koff.release(); coll.release(); cursor.release(); err.release(); cnt.release(); rank.release(); tmp.release();
+        for (int i = 0; i < 3; i++) { key_lo[i].release(); key_hi[i].release(); val[i].release(); }
+    };
+#define CUB_(call)                                                                                 \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            cleanup();                                                                             \
+            return fail(PSA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+        }                                                                                          \
+    } while (0)
+#define RC_(call)                      \
+    do {                               \
+        int rc_ = (call);              \
+        if (rc_ != PSA_OK) {           \
+            cleanup();                 \
+            return rc_;                \
+        }                              \
+    } while (0)
+
+    RC_(koff.ensure((d->n_nodes + 1) * 8));
+    CUB_(cudaMemcpy(koff.p, koff_host.data(), (d->n_nodes + 1) * 8, cudaMemcpyHostToDevice));
+    RC_(err.ensure(4));
+    CUB_(cudaMemset(err.p, 0, 4));
+    RC_(cursor.ensure(8));
+
+    // 1. every k-mer of every node
+    RC_(key_lo[0].ensure(n_kmers * 8 + 8));
+    if (KW == 2) RC_(key_hi[0].ensure(n_kmers * 8 + 8));
+    RC_(val[0].ensure(n_kmers * 8 + 8));
+    if (n_kmers)
+        k_enumerate_keys<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(
+            ix->seq.as<uint64_t>(), node_start.as<uint64_t>(), koff.as<uint64_t>(), d->n_nodes, n_kmers, k,
+            key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(), val[0].as<uint64_t>());
+    CUB_(cudaGetLastError());
+
+    // 2. cascade of bit-vector levels (boomphf's construction, on the device)
+    std::vector<uint64_t> lvl_nblk, lvl_base;
+    uint64_t total_blk = 0;
+    {
+        // level sizes depend on the survivors of the level before; allocate for the geometric bound
+        // (each level keeps < 50% of its keys at gamma >= 1.45; 4x level 0 is a safe cap) and grow if needed
+        uint64_t nblk0 = std::max<uint64_t>(1, (uint64_t)(gamma * (double)n_kmers / kBlockBits) + 1);
+        uint64_t cap_blk = 4 * nblk0 + 4 * kMaxLevels;
+        RC_(ix->blocks.ensure(cap_blk * 32));
+        CUB_(cudaMemsetAsync(ix->blocks.p, 0, ix->blocks.cap, st));
+        RC_(coll.ensure(nblk0 * 32));
+        CUB_(cudaMemsetAsync(coll.p, 0, coll.cap, st));
+        uint64_t rem = n_kmers;
+        int src = 0;  // buffer holding the remaining keys (0 = the full list, kept for step 4)
+        while (rem > 0) {
+            if ((int)lvl_nblk.size() >= kMaxLevels) {
+                cleanup();
+                return fail(PSA_ERR_INDEX, "MPHF did not converge: duplicate k-mer in the graph");
+            }
+            uint64_t nblk = std::max<uint64_t>(1, (uint64_t)(gamma * (double)rem / kBlockBits) + 1);
+            if (total_blk + nblk > cap_blk) {
+                cleanup();
+                return fail(PSA_ERR_INDEX, "MPHF block budget exceeded (gamma too small?)");
+            }
+            uint32_t lvl = (uint32_t)lvl_nblk.size();
+            int dst = src == 1 ? 2 : 1;
+            RC_(key_lo[dst].ensure(rem * 8 + 8));
+            if (KW == 2) RC_(key_hi[dst].ensure(rem * 8 + 8));
+            RC_(val[dst].ensure(rem * 8 + 8));
+            CUB_(cudaMemsetAsync(cursor.p, 0, 8, st));
+            k_mphf_set<KW><<<nblocks(rem, 256), 256, 0, st>>>(
+                key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(), rem, lvl, nblk, total_blk,
+                ix->blocks.as<unsigned long long>(), coll.as<unsigned long long>());
+            k_mphf_filter<KW><<<nblocks(rem, 256), 256, 0, st>>>(
+                key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(), val[src].as<uint64_t>(), rem, lvl, nblk,
+                coll.as<unsigned long long>(), key_lo[dst].as<uint64_t>(), key_hi[dst].as<uint64_t>(),
+                val[dst].as<uint64_t>(), cursor.as<unsigned long long>());
+            k_mphf_finalize<<<nblocks(4 * nblk, 256), 256, 0, st>>>(ix->blocks.as<unsigned long long>(),
+                                                                   coll.as<unsigned long long>(), total_blk, nblk);
+            CUB_(cudaGetLastError());
+            unsigned long long next = 0;
+            CUB_(cudaMemcpyAsync(&next, cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            CUB_(cudaStreamSynchronize(st));
+            lvl_nblk.push_back(nblk);
+            lvl_base.push_back(total_blk);
+            total_blk += nblk;
+            rem = next;
+            src = dst;
+        }
+    }
+    // 3. rank headers
+    if (total_blk) {
+        RC_(cnt.ensure(total_blk * 4));
+        RC_(rank.ensure(total_blk * 8));
+        k_block_counts<<<nblocks(total_blk, 256), 256, 0, st>>>(ix->blocks.as<uint64_t>(), total_blk, cnt.as<uint32_t>());
+        size_t tb = 0;
+        auto in = cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*>(cnt.as<uint32_t>(), CastU64());
+        CUB_(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, rank.as<uint64_t>(), total_blk, st));
+        RC_(tmp.ensure(tb));
+        CUB_(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, rank.as<uint64_t>(), total_blk, st));
+        k_block_headers<<<nblocks(total_blk, 256), 256, 0, st>>>(ix->blocks.as<uint64_t>(), total_blk, rank.as<uint64_t>());
+        CUB_(cudaGetLastError());
+    }
+    ix->d.mphf.blocks = ix->blocks.as<uint64_t>();
+    ix->d.mphf.n_levels = (uint32_t)lvl_nblk.size();
+    for (size_t i = 0; i < lvl_nblk.size(); i++) {
+        ix->d.mphf.level_nblk[i] = lvl_nblk[i];
+        ix->d.mphf.level_base[i] = lvl_base[i];
+    }
+    ix->info.mphf_levels = (uint32_t)lvl_nblk.size();
+    ix->info.mphf_bytes = total_blk * 32;
+
+    // 4. values[mphf(kmer)] = (node, offset, fingerprint)
+    RC_(ix->values.ensure(n_kmers * 8 + 8));
+    ix->d.values = ix->values.as<uint64_t>();
+    if (n_kmers)
+        k_fill_values<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(),
+                                                                 val[0].as<uint64_t>(), n_kmers, ix->d,
+                                                                 ix->values.as<uint64_t>(), err.as<uint32_t>());
+    // 5. successor / predecessor tables
+    if (d->n_nodes)
+        k_build_edges<KW><<<nblocks(d->n_nodes, 128), 128, 0, st>>>(ix->d, ix->nodes.as<NodeRec>(), err.as<uint32_t>());
+    CUB_(cudaGetLastError());
+    uint32_t e = 0;
+    CUB_(cudaMemcpyAsync(&e, err.p, 4, cudaMemcpyDeviceToHost, st));
+    CUB_(cudaStreamSynchronize(st));
+    cleanup();
+    if (e & 2u) return fail(PSA_ERR_INDEX, "MPHF self-check failed (internal)");
+    if (e & 4u) return fail(PSA_ERR_INDEX, "missing link: an extension bit has no neighbouring node");
+    return PSA_OK;
+#undef CUB_
+#undef RC_
+}
+
+extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamma, psa_index** out) {
+    if (!d || !out) return fail(PSA_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (d->k < 2 || d->k > 64) return fail(PSA_ERR_ARG, "k must be in 2..64");
+    if (d->n_nodes >= 0xFFFFFFFFull) return fail(PSA_ERR_ARG, "too many nodes (node ids are u32)");
+    if (d->n_nodes && (!d->seq_words || !d->node_start || !d->node_len || !d->node_exts || !d->node_eq))
+        return fail(PSA_ERR_ARG, "null node array");
+    if (!d->eq_offsets || (d->n_eq && d->eq_offsets[d->n_eq] && !d->eq_members)) return fail(PSA_ERR_ARG, "null eq array");
+    if (gamma <= 0) gamma = 1.7;  // ref src/build_index.rs:197
+    if (gamma < 1.0) return fail(PSA_ERR_ARG, "gamma must be >= 1");
+    CU(cudaSetDevice(device));
+
+    // host-side pass over the node table: k-mer counts, value packing widths, validation
+    std::vector<uint64_t> koff(d->n_nodes + 1);
+    uint64_t n_kmers = 0, max_off = 0;
+    for (uint64_t i = 0; i < d->n_nodes; i++) {
+        koff[i] = n_kmers;
+        if (d->node_len[i] < d->k) return fail(PSA_ERR_INDEX, "node shorter than k");
+        if (d->node_eq[i] >= d->n_eq) return fail(PSA_ERR_INDEX, "node eq id out of range");
+        if ((d->node_start[i] + d->node_len[i] + 31) / 32 > d->n_seq_words)
+            return fail(PSA_ERR_INDEX, "node sequence outside seq_words");
+        uint64_t nk = (uint64_t)d->node_len[i] - d->k + 1;
+        max_off = std::max(max_off, nk - 1);
+        n_kmers += nk;
+    }
+    koff[d->n_nodes] = n_kmers;
+    uint32_t max_class = 0;
+    for (uint64_t c = 0; c < d->n_eq; c++) {
+        if (d->eq_offsets[c + 1] < d->eq_offsets[c]) return fail(PSA_ERR_INDEX, "eq_offsets not monotone");
+        uint64_t l = d->eq_offsets[c + 1] - d->eq_offsets[c];
+        if (l > 0xFFFFFFFFull) return fail(PSA_ERR_INDEX, "class too large");
+        max_class = std::max<uint32_t>(max_class, (uint32_t)l);
+    }
+
+    psa_index* ix = new (std::nothrow) psa_index();
+    if (!ix) return fail(PSA_ERR_NOMEM, "out of memory");
+    ix->device = device;
+    ix->kw = d->k <= 32 ? 1 : 2;
+    auto bail = [&](int rc) {
+        psa_index_destroy(ix);
+        return rc;
+    };
+    int rc;
+    const uint64_t n_mem = d->n_eq ? d->eq_offsets[d->n_eq] : 0;
+    DevBuf node_start, node_len, node_exts, node_eq, err;
+    auto rel = [&]() { node_start.release(); node_len.release(); node_exts.release(); node_eq.release(); err.release(); };
+#define RCI(call)            \
+    do {                     \
+        rc = (call);         \
+        if (rc != PSA_OK) {  \
+            rel();           \
+            return bail(rc); \
+        }                    \
+    } while (0)
+#define CUI(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            (void)cudaGetLastError();                                                                      \
+            rel();                                                                                         \
+            return bail(fail(PSA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));           \
+        }                                                                                                  \
+    } while (0)
+    RCI(ix->seq.ensure((d->n_seq_words + 2) * 8));
+    CUI(cudaMemset(ix->seq.p, 0, (d->n_seq_words + 2) * 8));
+    if (d->n_seq_words) CUI(cudaMemcpy(ix->seq.p, d->seq_words, d->n_seq_words * 8, cudaMemcpyHostToDevice));
+    RCI(ix->eq_off.ensure((d->n_eq + 1) * 8));
+    CUI(cudaMemcpy(ix->eq_off.p, d->eq_offsets, (d->n_eq + 1) * 8, cudaMemcpyHostToDevice));
+    RCI(ix->eq_mem.ensure(n_mem * 4 + 4));
+    if (n_mem) CUI(cudaMemcpy(ix->eq_mem.p, d->eq_members, n_mem * 4, cudaMemcpyHostToDevice));
+    RCI(ix->nodes.ensure((d->n_nodes + 1) * sizeof(NodeRec)));
+    RCI(node_start.ensure(d->n_nodes * 8 + 8));
+    RCI(node_len.ensure(d->n_nodes * 4 + 4));
+    RCI(node_exts.ensure(d->n_nodes + 4));
+    RCI(node_eq.ensure(d->n_nodes * 4 + 4));
+    RCI(err.ensure(4));
+    CUI(cudaMemset(err.p, 0, 4));
+    if (d->n_nodes) {
+        CUI(cudaMemcpy(node_start.p, d->node_start, d->n_nodes * 8, cudaMemcpyHostToDevice));
+        CUI(cudaMemcpy(node_len.p, d->node_len, d->n_nodes * 4, cudaMemcpyHostToDevice));
+        CUI(cudaMemcpy(node_exts.p, d->node_exts, d->n_nodes, cudaMemcpyHostToDevice));
+        CUI(cudaMemcpy(node_eq.p, d->node_eq, d->n_nodes * 4, cudaMemcpyHostToDevice));
+    }
+
+    DevIndex& D = ix->d;
+    D.k = d->k;
+    D.node_bits = bits_for(d->n_nodes ? d->n_nodes - 1 : 0);
+    D.off_bits = bits_for(max_off);
+    int fp = 64 - (int)D.node_bits - (int)D.off_bits;
+    D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
+    D.n_nodes = d->n_nodes;
+    D.n_kmers = n_kmers;
+    D.n_eq = d->n_eq;
+    D.nodes = ix->nodes.as<NodeRec>();
+    D.seq = ix->seq.as<uint64_t>();
+    D.eq_off = ix->eq_off.as<uint64_t>();
+    D.eq_mem = ix->eq_mem.as<uint32_t>();
+
+    cudaEvent_t e0, e1;
+    CUI(cudaEventCreate(&e0));
+    CUI(cudaEventCreate(&e1));
+    CUI(cudaEventRecord(e0, 0));
+    if (d->n_nodes)
+        k_node_basics<<<nblocks(d->n_nodes, 256), 256>>>(ix->nodes.as<NodeRec>(), d->n_nodes, node_start.as<uint64_t>(),
+                                                         node_len.as<uint32_t>(), node_exts.as<uint8_t>(),
+                                                         node_eq.as<uint32_t>(), ix->eq_off.as<uint64_t>(), d->n_eq,
+                                                         d->k, err.as<uint32_t>());
+    CUI(cudaGetLastError());
+    if (ix->kw == 1) RCI(build_on_device<1>(ix, d, gamma, node_start, koff, n_kmers));
+    else RCI(build_on_device<2>(ix, d, gamma, node_start, koff, n_kmers));
+    CUI(cudaEventRecord(e1, 0));
+    CUI(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    rel();
+#undef RCI
+#undef CUI
+
+    psa_index_info& I = ix->info;
+    I.k = d->k;
+    I.n_nodes = d->n_nodes;
+    I.n_kmers = n_kmers;
+    I.n_eq = d->n_eq;
+    I.n_eq_members = n_mem;
+    I.n_seq_words = d->n_seq_words;
+    I.values_bytes = n_kmers * 8;
+    I.node_bytes = d->n_nodes * sizeof(NodeRec);
+    I.seq_bytes = d->n_seq_words * 8;
+    I.eq_bytes = (d->n_eq + 1) * 8 + n_mem * 4;
+    I.node_bits = D.node_bits;
+    I.off_bits = D.off_bits;
+    I.fp_bits = D.fp_bits;
+    I.max_class_len = max_class;
+    I.gamma = gamma;
+    I.build_ms = ms;
+    *out = ix;
+    return PSA_OK;
+}
+
+extern "C" void psa_index_destroy(psa_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    ix->blocks.release(); ix->values.release(); ix->nodes.release();
+    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release();
+    delete ix;
+}
+
+extern "C" int psa_index_get_info(const psa_index* ix, psa_index_info* out) {
+    if (!ix || !out) return fail(PSA_ERR_ARG, "null argument");
+    *out = ix->info;
+    return PSA_OK;
+}
+
+extern "C" int psa_index_lookup(psa_index* ix, const uint64_t* kmer_words, uint64_t n, uint8_t* found,
+                                uint32_t* node, uint32_t* off) {
+    if (!ix || (n && (!kmer_words || !found || !node || !off))) return fail(PSA_ERR_ARG, "null argument");
+    if (!n) return PSA_OK;
+    CU(cudaSetDevice(ix->device));
+    DevBuf w, f, nn, oo;
+    int rc = PSA_OK;
+    auto rel = [&]() { w.release(); f.release(); nn.release(); oo.release(); };
+    if ((rc = w.ensure(n * 8 * ix->kw + 8)) || (rc = f.ensure(n)) || (rc = nn.ensure(n * 4)) || (rc = oo.ensure(n * 4))) {
+        rel();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpy(w.p, kmer_words, n * 8 * ix->kw, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (ix->kw == 1) k_lookup<1><<<nblocks(n, 128), 128>>>(ix->d, w.as<uint64_t>(), n, f.as<uint8_t>(), nn.as<uint32_t>(), oo.as<uint32_t>());
+        else k_lookup<2><<<nblocks(n, 128), 128>>>(ix->d, w.as<uint64_t>(), n, f.as<uint8_t>(), nn.as<uint32_t>(), oo.as<uint32_t>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(found, f.p, n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(node, nn.p, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(off, oo.p, n * 4, cudaMemcpyDeviceToHost);
+    rel();
+    if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mapper
+// ---------------------------------------------------------------------------------------------
+struct Slot {  // staging of one pipeline chunk
+    DevBuf in_data, in_off, in_len;     // host batch copied as is
+    DevBuf hits, tx, meta_dev;          // results of the chunk; meta_dev = {running total, status}
+    cudaEvent_t in_ready = nullptr, in_free = nullptr, comp_done = nullptr, meta_done = nullptr, out_free = nullptr;
+    bool in_free_rec = false, out_free_rec = false;
+    unsigned long long* meta_host = nullptr;  // pinned: [0] running tx total after the chunk, [1] status
+};
+
+struct psa_mapper {
+    psa_index* ix = nullptr;
+    uint64_t chunk_reads = 0;
+    uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
+    cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
+    DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, running;
+    DevBuf words, woff, nwords, dst_off, scan_tmp, meta;
+    uint64_t novel_cap = 0;
+    uint32_t spill_cap = 1024;
+    int grid = 0;
+    Slot slot[2];
+    uint64_t launches = 0;
+    // pending async call
+    psa_result_batch* pending = nullptr;
+    unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
+};
+
+static int mapper_grid(psa_mapper* m) {
+    if (m->grid) return m->grid;
+    int sms = 148, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->ix->device);
+    if (m->ix->kw == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<1, false>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<2, false>, 256, 0);
+    if (per_sm < 1) per_sm = 1;
+    m->grid = sms * per_sm;
+    return m->grid;
+}
+
+extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper** out) {
+    if (!ix || !out) return fail(PSA_ERR_ARG, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(ix->device));
+    psa_mapper* m = new (std::nothrow) psa_mapper();
+    if (!m) return fail(PSA_ERR_NOMEM, "out of memory");
+    m->ix = ix;
+    m->chunk_reads = chunk_reads ? chunk_reads : (1ull << 20);
+    int rc = PSA_OK;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_d2h, cudaStreamNonBlocking);
+    for (int s = 0; s < 2 && e == cudaSuccess; s++) {
+        Slot& S = m->slot[s];
+        cudaEvent_t* evs[5] = {&S.in_ready, &S.in_free, &S.comp_done, &S.meta_done, &S.out_free};
+        for (auto ev : evs)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&S.meta_host, 64, cudaHostAllocDefault);
+    }
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&m->pin, 64, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        psa_mapper_destroy(m);
+        return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    }
+    const uint64_t nc = ix->d.n_eq + 2;
+    if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
+        (rc = m->novel_cursor.ensure(8)) || (rc = m->events.ensure(12 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
+        (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16))) {
+        psa_mapper_destroy(m);
+        return rc;
+    }
+    cudaMemset(m->counts.p, 0, nc * 8);
+    cudaMemset(m->events.p, 0, 12 * 8);
+    const int grid = mapper_grid(m);
+    if ((rc = m->spill.ensure((size_t)grid * 8 * m->spill_cap * sizeof(uint2)))) {
+        psa_mapper_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return PSA_OK;
+}
+
+extern "C" void psa_mapper_destroy(psa_mapper* m) {
+    if (!m) return;
+    cudaSetDevice(m->ix->device);
+    if (m->st) cudaStreamSynchronize(m->st);
+    if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
+    if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
+    DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill,
+                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta};
+    for (auto b : bufs) b->release();
+    for (int s = 0; s < 2; s++) {
+        Slot& S = m->slot[s];
+        S.in_data.release(); S.in_off.release(); S.in_len.release(); S.hits.release(); S.tx.release(); S.meta_dev.release();
+        cudaEvent_t evs[5] = {S.in_ready, S.in_free, S.comp_done, S.meta_done, S.out_free};
+        for (auto ev : evs)
+            if (ev) cudaEventDestroy(ev);
+        if (S.meta_host) cudaFreeHost(S.meta_host);
+    }
+    if (m->pin) cudaFreeHost(m->pin);
+    if (m->st) cudaStreamDestroy(m->st);
+    if (m->st_h2d) cudaStreamDestroy(m->st_h2d);
+    if (m->st_d2h) cudaStreamDestroy(m->st_d2h);
+    delete m;
+}
+
+extern "C" int psa_mapper_set_allowed_mismatches(psa_mapper* m, uint32_t allowed) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    m->allowed = allowed;
+    return PSA_OK;
+}
+extern "C" void* psa_mapper_stream(psa_mapper* m) { return m ? (void*)m->st : nullptr; }
+extern "C" void* psa_mapper_counts_device(psa_mapper* m) { return m ? m->counts.p : nullptr; }
+extern "C" uint64_t psa_mapper_launch_count(const psa_mapper* m) { return m ? m->launches : 0; }
+
+// Enqueue the kernels for one device-resident batch on m->st.
+//   reads: device pointers.  hits/tx_buf: device.  tx_base_dev: device u64 holding the offset at
+//   which this batch's members start in tx_buf (nullptr = 0); it is advanced by the batch total.
+//   total_dev: device u64[2] receiving {running total after the batch, status}.
+struct DeviceBatch {
+    const psa_read_batch* reads;
+    HitRec* hits;
+    uint32_t* tx_buf;
+    uint64_t tx_cap;
+    uint64_t* meta_out;    // device u64[2]: {running total after the batch, status}
+    uint64_t total_words;  // ragged ASCII only: sum of ceil(len/32) if the caller knows it, else 0
+};
+
+template <bool EV>
+static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_counts) {
+    const psa_read_batch* r = b.reads;
+    const uint64_t n = r->n_reads;
+    psa_index* ix = m->ix;
+    cudaStream_t st = m->st;
+    ReadsView rv{};
+    rv.n = n;
+    rv.len = r->read_len;
+    rv.fixed_len = r->fixed_len;
+    int rc;
+    if (r->format == PSA_READS_PACKED) {
+        rv.words = (const uint64_t*)r->data;
+        rv.woff = r->read_off;
+        rv.wstride = r->stride;
+    } else {
+        // ASCII -> DnaString words (ref src/pseudoaligner.rs:449-450), in HBM
+        if (r->read_len) {
+            if ((rc = m->nwords.ensure((n + 2) * 8)) || (rc = m->woff.ensure((n + 2) * 8))) return rc;
+            k_words_per_read<<<nblocks(n + 1, 256), 256, 0, st>>>(r->read_len, n, m->nwords.as<uint64_t>());
+            m->launches++;
+            size_t tb = 0;
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, m->nwords.as<uint64_t>(), m->woff.as<uint64_t>(), n + 1, st));
+            if ((rc = m->scan_tmp.ensure(tb))) return rc;
+            CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb, m->nwords.as<uint64_t>(), m->woff.as<uint64_t>(), n + 1, st));
+            uint64_t total_words = b.total_words;
+            if (!total_words) {  // unknown: read it back (one small sync per ragged ASCII device batch)
+                CU(cudaMemcpyAsync(m->pin + 2, m->woff.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                total_words = m->pin[2];
+            }
+            if ((rc = m->words.ensure(total_words * 8 + 16))) return rc;
+            rv.woff = m->woff.as<uint64_t>();
+        } else {
+            rv.woff = nullptr;
+            rv.wstride = ((uint64_t)r->fixed_len + 31) / 32;
+            if ((rc = m->words.ensure(n * rv.wstride * 8 + 16))) return rc;
+        }
+        k_pack_ascii<<<std::min<uint64_t>(nblocks(n * 32, 256), 148 * 64), 256, 0, st>>>(
+            (const uint8_t*)r->data, r->read_off, r->stride, r->read_len, r->fixed_len, rv.woff, rv.wstride, n,
+            m->words.as<uint64_t>());
+        m->launches++;
+        CU(cudaGetLastError());
+        rv.words = m->words.as<uint64_t>();
+    }
+    if (b.tx_buf && !m->novel_cap) {
+        m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
+        if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
+    }
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 8, st));
+    CU(cudaMemsetAsync(m->status.p, 0, 4, st));
+
+    MapParams p{};
+    p.reads = rv;
+    p.hits = b.hits;
+    p.counts = want_counts ? m->counts.as<unsigned long long>() : nullptr;
+    p.novel = b.tx_buf ? m->novel.as<uint32_t>() : nullptr;
+    p.novel_cap = m->novel_cap;
+    p.novel_cursor = m->novel_cursor.as<unsigned long long>();
+    p.spill = m->spill.as<uint2>();
+    p.spill_cap = m->spill_cap;
+    p.allowed_mismatches = m->allowed;
+    p.status = m->status.as<uint32_t>();
+    p.events = EV ? m->events.as<unsigned long long>() : nullptr;
+    const int grid = mapper_grid(m);
+    if (n) {
+        if (ix->kw == 1) k_map<1, EV><<<grid, 256, 0, st>>>(ix->d, p);
+        else k_map<2, EV><<<grid, 256, 0, st>>>(ix->d, p);
+        m->launches++;
+        CU(cudaGetLastError());
+    }
+    // exclusive scan of n_tx (n+1 items: the last one is the batch total), seeded by the running total
+    if ((rc = m->dst_off.ensure((n + 2) * 8))) return rc;
+    {
+        cub::CountingInputIterator<uint64_t> cnt(0);
+        TxLenN f{b.hits, n};
+        cub::TransformInputIterator<uint64_t, TxLenN, cub::CountingInputIterator<uint64_t>> in(cnt, f);
+        size_t tb = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
+        if ((rc = m->scan_tmp.ensure(tb))) return rc;
+        CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
+    }
+    if (n)
+        k_expand<<<nblocks(n * 8, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
+                                                      ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
+    k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
+                                m->status.as<uint32_t>(), b.meta_out);
+    m->launches++;
+    m->launches++;
+    CU(cudaGetLastError());
+    return PSA_OK;
+}
+
+static int check_batch_args(const psa_read_batch* r, const psa_result_batch* o) {
+    if (!r || !o) return fail(PSA_ERR_ARG, "null argument");
+    if (r->format != PSA_READS_ASCII && r->format != PSA_READS_PACKED) return fail(PSA_ERR_ARG, "unknown read format");
+    if (r->n_reads && (!r->data || !o->hits)) return fail(PSA_ERR_ARG, "null data / hits");
+    if (!r->read_len && r->n_reads && r->read_off == nullptr && r->stride == 0 && r->fixed_len != 0)
+        return fail(PSA_ERR_ARG, "stride required when read_off is NULL");
+    if (o->tx_cap && !o->tx_buf) return fail(PSA_ERR_ARG, "tx_cap without tx_buf");
+    return PSA_OK;
+}
+
+// grow the novel-set buffer after an overflow
+static int grow_novel(psa_mapper* m) {
+    m->novel_cap *= 4;
+    return m->novel.ensure(m->novel_cap * 4);
+}
+
+template <bool EV>
+static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o) {
+    const uint64_t nc = m->ix->d.n_eq + 2;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+        CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
+        DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
+        int rc = enqueue_device_batch<EV>(m, b, true);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(m->pin, m->meta.p, 16, cudaMemcpyDeviceToHost, m->st));
+        CU(cudaStreamSynchronize(m->st));
+        uint32_t status = (uint32_t)m->pin[1];
+        o->tx_used = m->pin[0];
+        if (status & 2u) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
+        if (status & 1u) {  // novel-set buffer overflow: undo the counts and retry with a larger buffer
+            CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+            if ((rc = grow_novel(m))) return rc;
+            continue;
+        }
+        if (o->tx_buf && o->tx_used > o->tx_cap) {  // the caller resubmits: leave the counts as they were
+            CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+            CU(cudaStreamSynchronize(m->st));
+            return fail(PSA_ERR_CAPACITY, "tx_buf too small");
+        }
+        return PSA_OK;
+    }
+    return fail(PSA_ERR_CAPACITY, "novel-set buffer kept overflowing");
+}
+
+extern "C" int psa_mapper_map_async(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    int rc = check_batch_args(r, o);
+    if (rc) return rc;
+    if (r->location != PSA_MEM_DEVICE || o->location != PSA_MEM_DEVICE)
+        return fail(PSA_ERR_ARG, "psa_mapper_map_async needs device-resident batches");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
+    DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
+    if ((rc = enqueue_device_batch<false>(m, b, true))) return rc;
+    CU(cudaMemcpyAsync(m->pin, m->meta.p, 16, cudaMemcpyDeviceToHost, m->st));
+    m->pending = o;
+    return PSA_OK;
+}
+
+extern "C" int psa_mapper_sync(psa_mapper* m) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaStreamSynchronize(m->st));
+    if (m->pending) {
+        psa_result_batch* o = m->pending;
+        m->pending = nullptr;
+        o->tx_used = m->pin[0];
+        uint32_t status = (uint32_t)m->pin[1];
+        if (status & 2u) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
+        if (status & 1u) {
+            int rc = grow_novel(m);
+            if (rc) return rc;
+            return fail(PSA_ERR_CAPACITY, "novel-set buffer overflow (buffer grown: resubmit the batch)");
+        }
+        if (o->tx_buf && o->tx_used > o->tx_cap) return fail(PSA_ERR_CAPACITY, "tx_buf too small");
+    }
+    return PSA_OK;
+}
+
+// Host-resident batch: chunks pipelined over three streams (H2D | kernels | D2H).
+static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o) {
+    const uint64_t n = r->n_reads;
+    const uint64_t nc = m->ix->d.n_eq + 2;
+    const bool ascii = r->format == PSA_READS_ASCII;
+    const uint64_t unit = ascii ? 1 : 8;  // bytes per data element
+    const uint64_t C = m->chunk_reads;
+    const uint64_t nchunks = (n + C - 1) / C;
+    o->tx_used = 0;
+    if (!n) return PSA_OK;
+
+    struct ChunkPlan { uint64_t r0, nr, d0, dn, words; };  // reads [r0, r0+nr), data elements [d0, d0+dn)
+    std::vector<ChunkPlan> plan(nchunks);
+    uint64_t max_dn = 0;
+    for (uint64_t c = 0; c < nchunks; c++) {
+        ChunkPlan& P = plan[c];
+        P.r0 = c * C;
+        P.nr = std::min(C, n - P.r0);
+        P.words = 0;
+        uint64_t lo = ~0ull, hi = 0, max_span = 0;
+        if (r->read_off || r->read_len) {
+            for (uint64_t i = P.r0; i < P.r0 + P.nr; i++) {
+                uint64_t L = r->read_len ? r->read_len[i] : r->fixed_len;
+                uint64_t span = ascii ? L : (L + 31) / 32;
+                P.words += (L + 31) / 32;
+                max_span = std::max(max_span, span);
+                if (r->read_off) {
+                    lo = std::min(lo, r->read_off[i]);
+                    hi = std::max(hi, r->read_off[i] + span);
+                }
+            }
+        } else {
+            max_span = ascii ? r->fixed_len : ((uint64_t)r->fixed_len + 31) / 32;
+        }
+        if (r->read_off) {
+            P.d0 = lo;
+            P.dn = hi - lo;
+        } else {
+            P.d0 = P.r0 * r->stride;
+            P.dn = (P.nr - 1) * r->stride + max_span;
+        }
+        if (P.d0 + P.dn > r->data_len) return fail(PSA_ERR_ARG, "read extends past data_len");
+        max_dn = std::max(max_dn, P.dn);
+    }
+
+    for (int attempt = 0; attempt < 6; attempt++) {
+        int rc;
+        CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+        CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
+        for (int s = 0; s < 2; s++) {
+            Slot& S = m->slot[s];
+            if ((rc = S.in_data.ensure(max_dn * unit + 64)) || (rc = S.hits.ensure(C * sizeof(HitRec)))) return rc;
+            if (r->read_off && (rc = S.in_off.ensure(C * 8))) return rc;
+            if (r->read_len && (rc = S.in_len.ensure(C * 4))) return rc;
+            if (o->tx_buf && (rc = S.tx.ensure(std::max<uint64_t>(S.tx.cap, std::min(C, n) * 16 * 4)))) return rc;
+            S.in_free_rec = S.out_free_rec = false;
+        }
+        bool novel_overflow = false, spill_overflow = false, stage_overflow = false;
+        uint64_t stage_need = 0;
+        uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
+
+        auto finish = [&](uint64_t c) -> int {  // host side of chunk c: totals, members D2H
+            Slot& S = m->slot[c & 1];
+            CU(cudaEventSynchronize(S.meta_done));
+            uint64_t total = S.meta_host[0];
+            uint32_t status = (uint32_t)S.meta_host[1];
+            if (status & 1u) novel_overflow = true;
+            if (status & 2u) spill_overflow = true;
+            uint64_t cnt = total - tx_prev_total;
+            if (status & 4u) {  // the chunk produced more members than its staging buffer holds
+                stage_overflow = true;
+                stage_need = std::max(stage_need, cnt);
+            } else if (o->tx_buf && cnt && total <= o->tx_cap) {
+                CU(cudaMemcpyAsync(o->tx_buf + tx_prev_total, S.tx.p, cnt * 4, cudaMemcpyDeviceToHost, m->st_d2h));
+            }
+            CU(cudaEventRecord(S.out_free, m->st_d2h));
+            S.out_free_rec = true;
+            tx_prev_total = total;
+            return PSA_OK;
+        };
+
+        for (uint64_t c = 0; c < nchunks; c++) {
+            const ChunkPlan& P = plan[c];
+            Slot& S = m->slot[c & 1];
+            // H2D
+            if (S.in_free_rec) CU(cudaStreamWaitEvent(m->st_h2d, S.in_free, 0));
+            CU(cudaMemcpyAsync(S.in_data.p, (const uint8_t*)r->data + P.d0 * unit, P.dn * unit, cudaMemcpyHostToDevice, m->st_h2d));
+            if (r->read_off) CU(cudaMemcpyAsync(S.in_off.p, r->read_off + P.r0, P.nr * 8, cudaMemcpyHostToDevice, m->st_h2d));
+            if (r->read_len) CU(cudaMemcpyAsync(S.in_len.p, r->read_len + P.r0, P.nr * 4, cudaMemcpyHostToDevice, m->st_h2d));
+            CU(cudaEventRecord(S.in_ready, m->st_h2d));
+            // kernels
+            CU(cudaStreamWaitEvent(m->st, S.in_ready, 0));
+            if (S.out_free_rec) CU(cudaStreamWaitEvent(m->st, S.out_free, 0));
+            psa_read_batch rb = *r;
+            rb.location = PSA_MEM_DEVICE;
+            rb.n_reads = P.nr;
+            rb.data_len = P.dn;
+            if (r->read_off) {  // offsets stay absolute: bias the base pointer by the chunk's first element
+                rb.data = (const uint8_t*)S.in_data.p - P.d0 * unit;
+                rb.read_off = S.in_off.as<uint64_t>();
+            } else {
+                rb.data = S.in_data.p;
+                rb.read_off = nullptr;
+            }
+            rb.read_len = r->read_len ? S.in_len.as<uint32_t>() : nullptr;
+            DeviceBatch b{&rb, S.hits.as<HitRec>(), o->tx_buf ? S.tx.as<uint32_t>() : nullptr,
+                          o->tx_buf ? (uint64_t)(S.tx.cap / 4) : 0, S.meta_dev.as<uint64_t>(), P.words};
+            if ((rc = enqueue_device_batch<false>(m, b, true))) return rc;
+            CU(cudaEventRecord(S.comp_done, m->st));
+            CU(cudaEventRecord(S.in_free, m->st));
+            S.in_free_rec = true;
+            // D2H: the two meta words first (the host waits on them), then the hits
+            CU(cudaStreamWaitEvent(m->st_d2h, S.comp_done, 0));
+            CU(cudaMemcpyAsync(S.meta_host, S.meta_dev.p, 16, cudaMemcpyDeviceToHost, m->st_d2h));
+            CU(cudaEventRecord(S.meta_done, m->st_d2h));
+            CU(cudaMemcpyAsync(o->hits + P.r0, S.hits.p, P.nr * sizeof(HitRec), cudaMemcpyDeviceToHost, m->st_d2h));
+            if (c >= 1 && (rc = finish(c - 1))) return rc;
+        }
+        if ((rc = finish(nchunks - 1))) return rc;
+        CU(cudaStreamSynchronize(m->st_d2h));
+        CU(cudaStreamSynchronize(m->st));
+        o->tx_used = tx_prev_total;
+        if (spill_overflow) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
+        if (novel_overflow || stage_overflow) {
+            CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+            if (novel_overflow && m->novel_cap && (rc = grow_novel(m))) return rc;
+            if (stage_overflow)
+                for (int s = 0; s < 2; s++)
+                    if ((rc = m->slot[s].tx.ensure(stage_need * 4 + 4096))) return rc;
+            continue;
+        }
+        if (o->tx_buf && o->tx_used > o->tx_cap) {  // the caller resubmits: leave the counts as they were
+            CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+            CU(cudaStreamSynchronize(m->st));
+            return fail(PSA_ERR_CAPACITY, "tx_buf too small");
+        }
+        return PSA_OK;
+    }
+    return fail(PSA_ERR_CAPACITY, "staging buffers kept overflowing");
+}
+
+extern "C" int psa_mapper_map(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    int rc = check_batch_args(r, o);
+    if (rc) return rc;
+    if (r->location != o->location) return fail(PSA_ERR_ARG, "reads and results must live on the same side");
+    CU(cudaSetDevice(m->ix->device));
+    if (r->location == PSA_MEM_DEVICE) return map_device_sync<false>(m, r, o);
+    return map_host(m, r, o);
+}
+
+extern "C" int psa_mapper_map_events(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o, psa_events* out) {
+    if (!m || !out) return fail(PSA_ERR_ARG, "null argument");
+    int rc = check_batch_args(r, o);
+    if (rc) return rc;
+    if (r->location != PSA_MEM_DEVICE || o->location != PSA_MEM_DEVICE)
+        return fail(PSA_ERR_ARG, "psa_mapper_map_events needs device-resident batches");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaMemsetAsync(m->events.p, 0, 12 * 8, m->st));
+    if ((rc = map_device_sync<true>(m, r, o))) return rc;
+    static_assert(sizeof(psa_events) == 12 * 8, "psa_events layout");
+    CU(cudaMemcpy(out, m->events.p, sizeof(psa_events), cudaMemcpyDeviceToHost));
+    return PSA_OK;
+}
+
+extern "C" int psa_mapper_map_read(psa_mapper* m, const uint64_t* read_words, uint32_t read_len, uint32_t* tx_out,
+                                   uint64_t tx_cap, uint32_t* n_tx, uint32_t* coverage) {
+    if (!m || !n_tx || !coverage || (read_len && !read_words)) return fail(PSA_ERR_ARG, "null argument");
+    uint64_t dummy = 0;
+    uint32_t len = read_len;
+    uint64_t off = 0;
+    psa_read_batch r{};
+    r.format = PSA_READS_PACKED;
+    r.location = PSA_MEM_HOST;
+    r.data = read_len ? (const void*)read_words : (const void*)&dummy;
+    r.data_len = ((uint64_t)read_len + 31) / 32;
+    r.read_off = &off;
+    r.read_len = &len;
+    r.n_reads = 1;
+    psa_hit h{};
+    psa_result_batch o{};
+    o.location = PSA_MEM_HOST;
+    o.hits = &h;
+    o.tx_buf = tx_out;
+    o.tx_cap = tx_out ? tx_cap : 0;
+    int rc = psa_mapper_map(m, &r, &o);
+    *n_tx = h.n_tx;
+    *coverage = h.coverage;
+    if (rc) return rc;
+    return (h.flags & PSA_FLAG_ALIGNED) ? 1 : 0;
+}
+
+extern "C" int psa_mapper_counts_get(psa_mapper* m, uint64_t* counts_host) {
+    if (!m || !counts_host) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaStreamSynchronize(m->st));
+    CU(cudaMemcpy(counts_host, m->counts.p, (m->ix->d.n_eq + 2) * 8, cudaMemcpyDeviceToHost));
+    return PSA_OK;
+}
+extern "C" int psa_mapper_counts_reset(psa_mapper* m) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaMemsetAsync(m->counts.p, 0, (m->ix->d.n_eq + 2) * 8, m->st));
+    CU(cudaStreamSynchronize(m->st));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL: resolved at run time so that the library loads on machines without libnccl and uses
+// whichever libnccl.so.2 the process already holds (torch's, when called from bench.py).
+// ---------------------------------------------------------------------------------------------
+struct Id128 {
+    char b[128];
+};
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return PSA_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (auto nm : names)
+        if ((h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(PSA_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(PSA_ERR_NCCL, "libnccl lacks a required symbol");
+    g_nccl.h = h;
+    return PSA_OK;
+}
+static int nccl_fail(const char* what, int code) {
+    return fail(PSA_ERR_NCCL, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(code) : "?"));
+}
+struct psa_comm {
+    void* comm = nullptr;
+    int world = 1, rank = 0, device = 0;
+};
+extern "C" int psa_comm_unique_id(uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES]) {
+    if (!id) return fail(PSA_ERR_ARG, "null argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    int e = g_nccl.GetUniqueId(id);
+    if (e) return nccl_fail("ncclGetUniqueId", e);
+    return PSA_OK;
+}
+extern "C" int psa_comm_create(const uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES], int world, int rank, int device,
+                               psa_comm** out) {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(PSA_ERR_ARG, "bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    psa_comm* c = new (std::nothrow) psa_comm();
+    if (!c) return fail(PSA_ERR_NOMEM, "out of memory");
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    int e = g_nccl.CommInitRank(&c->comm, world, uid, rank);
+    if (e) {
+        delete c;
+        return nccl_fail("ncclCommInitRank", e);
+    }
+    c->world = world; c->rank = rank; c->device = device;
+    *out = c;
+    return PSA_OK;
+}
+extern "C" void psa_comm_destroy(psa_comm* c) {
+    if (!c) return;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+extern "C" int psa_mapper_counts_allreduce(psa_mapper* m, psa_comm* c) {
+    if (!m || !c) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    // ncclUint64 = 5, ncclSum = 0
+    int e = g_nccl.AllReduce(m->counts.p, m->counts.p, m->ix->d.n_eq + 2, 5, 0, c->comm, m->st);
+    if (e) return nccl_fail("ncclAllReduce", e);
+    CU(cudaStreamSynchronize(m->st));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// memory helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int psa_host_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return PSA_OK;
+}
+extern "C" void psa_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+extern "C" int psa_device_alloc(void** out, uint64_t bytes) {
+    if (!out) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return PSA_OK;
+}
+extern "C" void psa_device_free(void* p) {
+    if (p) cudaFree(p);
+}
+extern "C" int psa_memcpy_h2d(void* dst, const void* src, uint64_t bytes) {
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return PSA_OK;
+}
+extern "C" int psa_memcpy_d2h(void* dst, const void* src, uint64_t bytes) {
+    CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return PSA_OK;
+}

@@ -1,0 +1,601 @@
+// psa_kernels.cuh -- the sm_100a kernels: index construction on the device (k-mer enumeration,
+// cascaded-bit-vector MPHF, `values` scatter, successor/predecessor tables), ASCII -> 2-bit
+// packing, the one-warp-per-read map kernel, and the result expansion.
+//
+// Reference items replaced (10XGenomics/rust-pseudoaligner @ 9d9cab8):
+//   k_map            Pseudoaligner::map_read + the per-record body of process_reads
+//                    (src/pseudoaligner.rs:64-384, :449-462)
+//   k_pack_ascii     DnaString::from_dna_string at src/pseudoaligner.rs:449-450
+//   k_mphf_* / k_fill_values   make_dbg_index (src/build_index.rs:182-221)
+//   k_build_edges    what Node::r_edges()/l_edges() compute per call (src/pseudoaligner.rs:191,275)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "psa_core.cuh"
+
+namespace psa {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// index construction
+// ---------------------------------------------------------------------------------------------
+// first pass over the nodes: record everything that does not need the dictionary
+__global__ void k_node_basics(NodeRec* nodes, uint64_t n_nodes, const uint64_t* node_start,
+                              const uint32_t* node_len, const uint8_t* node_exts, const uint32_t* node_eq,
+                              const uint64_t* eq_off, uint64_t n_eq, uint32_t k, uint32_t* err) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    NodeRec r;
+    r.start = node_start[i];
+    r.len = node_len[i];
+    r.eq = node_eq[i];
+    r.exts = node_exts[i];
+    r.pad[0] = r.pad[1] = 0;
+    if (r.eq >= n_eq || r.len < k) {
+        atomicOr(err, 1u);
+        r.class_len = 0;
+    } else {
+        r.class_len = (uint32_t)(eq_off[r.eq + 1] - eq_off[r.eq]);
+    }
+    for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
+    nodes[i] = r;
+}
+
+// every k-mer of every node: key and its (node, offset); koff = exclusive scan of (len-k+1)
+template <int KW>
+__global__ void k_enumerate_keys(const uint64_t* seq, const uint64_t* node_start, const uint64_t* koff,
+                                 uint64_t n_nodes, uint64_t n_kmers, uint32_t k, uint64_t* key_lo,
+                                 uint64_t* key_hi, uint64_t* val) {
+    uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (g >= n_kmers) return;
+    uint64_t lo = 0, hi = n_nodes;  // last node with koff[node] <= g
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (koff[mid] <= g) lo = mid;
+        else hi = mid;
+    }
+    uint64_t off = g - koff[lo];
+    Kmer<KW> key = KmerOps<KW>::get(GLoad{seq}, node_start[lo] + off, k);
+    key_lo[g] = key.lo;
+    if constexpr (KW == 2) key_hi[g] = key.hi;
+    val[g] = (lo << 32) | off;
+}
+
+template <int KW>
+__device__ __forceinline__ uint64_t key_hash_at(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t i) {
+    if (KW == 1) {
+        Kmer<1> x; x.lo = key_lo[i];
+        return KmerOps<1>::hash(x);
+    } else {
+        Kmer<2> x; x.lo = key_lo[i]; x.hi = key_hi[i];
+        return KmerOps<2>::hash(x);
+    }
+}
+
+// one cascade level, step 1: every remaining key sets its bit; a second arrival marks a collision
+template <int KW>
+__global__ void k_mphf_set(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t n, uint32_t lvl,
+                           uint64_t nblk, uint64_t base, unsigned long long* blocks,
+                           unsigned long long* coll) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t blk; uint32_t bit;
+    level_pos(level_hash(key_hash_at<KW>(key_lo, key_hi, i), lvl), nblk, blk, bit);
+    uint64_t w = 4 * (base + blk) + 1 + (bit >> 6);
+    unsigned long long m = 1ULL << (bit & 63);
+    unsigned long long old = atomicOr(blocks + w, m);
+    if (old & m) atomicOr(coll + 4 * blk + 1 + (bit >> 6), m);
+}
+// step 2: keys on collided bits move on to the next level
+template <int KW>
+__global__ void k_mphf_filter(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n,
+                              uint32_t lvl, uint64_t nblk, const unsigned long long* coll, uint64_t* out_lo,
+                              uint64_t* out_hi, uint64_t* out_val, unsigned long long* cursor) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < n) {
+        uint64_t blk; uint32_t bit;
+        level_pos(level_hash(key_hash_at<KW>(key_lo, key_hi, i), lvl), nblk, blk, bit);
+        keep = (coll[4 * blk + 1 + (bit >> 6)] >> (bit & 63)) & 1;
+    }
+    unsigned b = __ballot_sync(kFull, keep);
+    if (!b) return;
+    unsigned lane = threadIdx.x & 31;
+    unsigned long long basepos = 0;
+    if (lane == 0) basepos = atomicAdd(cursor, (unsigned long long)__popc(b));
+    basepos = __shfl_sync(kFull, basepos, 0);
+    if (keep) {
+        uint64_t o = basepos + __popc(b & ((1u << lane) - 1));
+        out_lo[o] = key_lo[i];
+        if (KW == 2) out_hi[o] = key_hi[i];
+        out_val[o] = val[i];
+    }
+}
+// step 3: collided bits are cleared from the level, the scratch is zeroed for the next level
+__global__ void k_mphf_finalize(unsigned long long* blocks, unsigned long long* coll, uint64_t base,
+                                uint64_t nblk) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= 4 * nblk) return;
+    unsigned long long c = coll[i];
+    if (c) {
+        blocks[4 * base + i] &= ~c;
+        coll[i] = 0;
+    }
+}
+__global__ void k_block_counts(const uint64_t* blocks, uint64_t nblk, uint32_t* cnt) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nblk) return;
+    cnt[i] = __popcll(blocks[4 * i + 1]) + __popcll(blocks[4 * i + 2]) + __popcll(blocks[4 * i + 3]);
+}
+__global__ void k_block_headers(uint64_t* blocks, uint64_t nblk, const uint64_t* rank_excl) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nblk) return;
+    uint32_t c1 = __popcll(blocks[4 * i + 1]);
+    uint32_t c2 = c1 + __popcll(blocks[4 * i + 2]);
+    blocks[4 * i] = make_header(rank_excl[i], c1, c2);
+}
+
+// values[mphf(kmer)] = (node, offset) -- ref src/build_index.rs:200-220
+template <int KW>
+__global__ void k_fill_values(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n,
+                              DevIndex ix, uint64_t* values, uint32_t* err) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t hk = key_hash_at<KW>(key_lo, key_hi, i);
+    uint64_t slot; uint32_t levels;
+    if (!mphf_lookup(ix.mphf, hk, slot, levels) || slot >= ix.n_kmers) {
+        atomicOr(err, 2u);
+        return;
+    }
+    uint64_t v = val[i];
+    values[slot] = pack_value(ix, (uint32_t)(v >> 32), (uint32_t)v, hk);
+}
+
+// succ[b] / pred[b]: the node whose first k-mer is last(k-1)+b, resp. whose last k-mer is
+// b+first(k-1).  debruijn's find_link expects every ext bit to resolve ("missing link").
+template <int KW>
+__global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= ix.n_nodes) return;
+    const NodeRec r = nodes[i];
+    if (r.len < ix.k) return;
+    Kmer<KW> first = KmerOps<KW>::get(GLoad{ix.seq}, r.start, ix.k);
+    Kmer<KW> last = KmerOps<KW>::get(GLoad{ix.seq}, r.start + r.len - ix.k, ix.k);
+    for (uint32_t b = 0; b < 4; b++) {
+        uint32_t n, o;
+        if ((r.exts >> b) & 1) {
+            if (dict_get<KW>(ix, KmerOps<KW>::extend_right(last, b, ix.k), n, o, nullptr) && o == 0)
+                nodes[i].succ[b] = n;
+            else
+                atomicOr(err, 4u);
+        }
+        if ((r.exts >> (4 + b)) & 1) {
+            if (dict_get<KW>(ix, KmerOps<KW>::extend_left(first, b, ix.k), n, o, nullptr) &&
+                o == nodes[n].len - ix.k)
+                nodes[i].pred[b] = n;
+            else
+                atomicOr(err, 4u);
+        }
+    }
+}
+
+template <int KW>
+__global__ void k_lookup(DevIndex ix, const uint64_t* kmer_words, uint64_t n, uint8_t* found, uint32_t* node,
+                         uint32_t* off) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer<KW> key = KmerOps<KW>::get(PLoad{kmer_words + (uint64_t)KW * i}, 0, ix.k);
+    uint32_t nn = 0, oo = 0;
+    bool f = dict_get<KW>(ix, key, nn, oo, nullptr);
+    found[i] = f;
+    node[i] = nn;
+    off[i] = oo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reads: ASCII -> DnaString words.  One thread per output word.
+// ---------------------------------------------------------------------------------------------
+struct ReadsView {          // device-resident batch
+    const uint64_t* words;  // packed
+    const uint64_t* woff;   // word offset of read i; nullptr: i * wstride
+    const uint32_t* len;    // nullptr: fixed_len
+    uint64_t wstride;
+    uint32_t fixed_len;
+    uint64_t n;
+};
+
+__global__ void k_words_per_read(const uint32_t* len, uint64_t n, uint64_t* nw) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) nw[i] = ((uint64_t)len[i] + 31) >> 5;
+}
+
+// ragged: warp per read, lane-strided over its words
+__global__ void k_pack_ascii(const uint8_t* ascii, const uint64_t* aoff, uint64_t astride, const uint32_t* len,
+                             uint32_t fixed_len, const uint64_t* woff, uint64_t wstride, uint64_t n,
+                             uint64_t* words) {
+    uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    uint64_t nwarps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
+    for (uint64_t r = warp; r < n; r += nwarps) {
+        const uint8_t* s = ascii + (aoff ? aoff[r] : r * astride);
+        uint32_t L = len ? len[r] : fixed_len;
+        uint64_t* w = words + (woff ? woff[r] : r * wstride);
+        uint32_t nw = (L + 31) >> 5;
+        for (uint32_t j = lane; j < nw; j += 32) {
+            uint32_t nb = min(32u, L - 32 * j);
+            uint64_t v = 0;
+            for (uint32_t t = 0; t < nb; t++) v |= (uint64_t)base_code(s[32 * j + t]) << (62 - 2 * t);
+            w[j] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the map kernel
+// ---------------------------------------------------------------------------------------------
+struct HitRec {  // == psa_hit
+    uint32_t coverage, n_tx;
+    uint64_t tx_off;
+    uint32_t eq_id, flags;
+};
+constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
+
+struct MapParams {
+    ReadsView reads;
+    HitRec* hits;
+    unsigned long long* counts;   // n_eq + 2, or nullptr
+    uint32_t* novel;              // members of sets that are no index class
+    unsigned long long novel_cap;
+    unsigned long long* novel_cursor;
+    uint2* spill;                 // per-warp overflow of the visited-class list
+    uint32_t spill_cap;           // entries per warp
+    uint32_t allowed_mismatches;
+    uint32_t* status;             // bit0: novel buffer overflow, bit1: spill overflow
+    unsigned long long* events;   // psa_events layout, or nullptr
+};
+
+struct LaneEvents {
+    uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
+};
+
+template <int KW, bool EV>
+struct WarpCtx {
+    const DevIndex& ix;
+    PLoad rd;
+    uint32_t lane;
+    uint32_t k;
+    // visited distinct classes: entry j < 32 lives in lane j, further ones in `spill`
+    uint32_t my_eq, my_len, n_list;
+    uint2* spill;
+    uint32_t spill_cap;
+    bool spill_overflow;
+    LaneEvents ev;
+
+    __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint2* spill_, uint32_t cap)
+        : ix(ix_), rd{read_words}, lane(threadIdx.x & 31), k(ix_.k), my_eq(kNone), my_len(0), n_list(0),
+          spill(spill_), spill_cap(cap), spill_overflow(false), ev{} {}
+
+    __device__ __forceinline__ uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
+
+    // find_kmer_match, ref src/pseudoaligner.rs:91-114.  The first position is probed by the
+    // whole warp on one address (the common case: it hits); after a miss, 32 stride-3
+    // positions are probed at once, one per lane, and the lowest hitting lane wins -- the
+    // same answer as the sequential scan.
+    __device__ __forceinline__ bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
+        if (kmer_pos > last) return false;
+        ProbeStats st;
+        {
+            Kmer<KW> key = KmerOps<KW>::get(rd, kmer_pos, k);
+            bool hit = dict_get<KW>(ix, key, node, off, EV ? &st : nullptr);
+            if (EV && lane == 0) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
+            if (hit) return true;
+        }
+        const uint64_t start = kmer_pos;
+        for (uint64_t cur = start + kSeedStride; cur <= last; cur += 32 * kSeedStride) {
+            uint64_t p = cur + (uint64_t)kSeedStride * lane;
+            bool h = false;
+            uint32_t n = 0, o = 0;
+            st.levels = st.hit = st.verified = 0;
+            if (p <= last) {
+                Kmer<KW> key = KmerOps<KW>::get(rd, p, k);
+                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
+            }
+            unsigned b = __ballot_sync(kFull, h);
+            int j = b ? (__ffs(b) - 1) : 32;
+            if (EV && p <= last && (int)lane <= j) {
+                ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified;
+            }
+            if (b) {
+                node = __shfl_sync(kFull, n, j);
+                off = __shfl_sync(kFull, o, j);
+                kmer_pos = cur + (uint64_t)kSeedStride * j;
+                return true;
+            }
+        }
+        kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
+        return false;
+    }
+
+    __device__ __forceinline__ NodeView node(uint32_t id) const {
+        const NodeRec* r = ix.nodes + id;
+        uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
+        uint2 b = __ldg(reinterpret_cast<const uint2*>(r) + 2);
+        NodeView v;
+        v.start = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        v.len = a.z;
+        v.eq = a.w;
+        v.class_len = b.x;
+        v.exts = b.y;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t succ(uint32_t id, uint32_t b) {
+        if (EV && lane == 0) ev.jumps++;
+        return __ldg(&ix.nodes[id].succ[b]);
+    }
+    __device__ __forceinline__ uint32_t pred(uint32_t id, uint32_t b) {
+        if (EV && lane == 0) ev.jumps++;
+        return __ldg(&ix.nodes[id].pred[b]);
+    }
+
+    // shared tail of the two compare loops: lane `lane` holds the mismatch mask of bases
+    // [base+32*lane, base+32*lane+n); find the (A+1)-th mismatch in scan order.
+    __device__ __forceinline__ bool locate_break(uint64_t mask, uint32_t& snp, uint32_t A, uint32_t& t_out, int& j_out) {
+        uint32_t c = (uint32_t)popc64(mask);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(kFull, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        unsigned b = __ballot_sync(kFull, snp + incl > A);
+        if (b) {
+            int j = __ffs(b) - 1;
+            uint32_t t = 0;
+            if ((int)lane == j) t = nth_mismatch(mask, A + 1 - (snp + incl - c));
+            t_out = __shfl_sync(kFull, t, j);
+            j_out = j;
+            return true;
+        }
+        snp += __shfl_sync(kFull, incl, 31);
+        return false;
+    }
+
+    // ref src/pseudoaligner.rs:234-255
+    __device__ __forceinline__ uint64_t cmp_fwd(uint64_t rpos, uint64_t spos, uint64_t m, uint32_t A, bool& premature) {
+        uint32_t snp = 0;
+        for (uint64_t base = 0; base < m; base += 1024) {
+            uint64_t my = base + 32 * lane;
+            uint32_t n = my < m ? (uint32_t)min((uint64_t)32, m - my) : 0;
+            uint64_t mask = n ? mismatch_fwd(rd, rpos + my, GLoad{ix.seq}, spos + my, n) : 0;
+            if (!__any_sync(kFull, mask != 0)) continue;
+            uint32_t t; int j;
+            if (locate_break(mask, snp, A, t, j)) {
+                premature = true;
+                uint64_t matched = base + 32 * (uint64_t)j + t;
+                if (EV && lane == 0) ev.bases += (uint32_t)matched + 1;
+                return matched;
+            }
+        }
+        if (EV && lane == 0) ev.bases += (uint32_t)m;
+        return m;
+    }
+    // ref src/pseudoaligner.rs:149-170
+    __device__ __forceinline__ uint64_t cmp_bwd(uint64_t rend, uint64_t send, uint64_t m, uint32_t A, bool& premature) {
+        uint32_t snp = 0;
+        for (uint64_t base = 0; base < m; base += 1024) {
+            uint64_t my = base + 32 * lane;
+            uint32_t n = my < m ? (uint32_t)min((uint64_t)32, m - my) : 0;
+            uint64_t mask = n ? mismatch_bwd(rd, rend - my, GLoad{ix.seq}, send - my, n) : 0;
+            if (!__any_sync(kFull, mask != 0)) continue;
+            uint32_t t; int j;
+            if (locate_break(mask, snp, A, t, j)) {
+                premature = true;
+                uint64_t matched = base + 32 * (uint64_t)j + t;
+                if (EV && lane == 0) ev.bases += (uint32_t)matched + 1;
+                return matched;
+            }
+        }
+        if (EV && lane == 0) ev.bases += (uint32_t)m;
+        return m;
+    }
+
+    // nodes.push (ref :199, :219), keeping only what nodes_to_eq_class needs: the distinct
+    // classes of the visited nodes (intersection is idempotent, ref :352-355).
+    __device__ __forceinline__ void push(uint32_t /*node_id*/, const NodeView& nv) {
+        if (EV && lane == 0) ev.visits++;
+        if (__ballot_sync(kFull, lane < n_list && my_eq == nv.eq)) return;
+        if (n_list < 32) {
+            if (lane == n_list) { my_eq = nv.eq; my_len = nv.class_len; }
+            n_list++;
+            return;
+        }
+        // rare: more than 32 distinct classes
+        uint32_t ns = n_list - 32;
+        bool dup = false;
+        for (uint32_t j = lane; j < ns; j += 32) dup |= (spill[j].x == nv.eq);
+        if (__any_sync(kFull, dup)) return;
+        if (ns >= spill_cap) { spill_overflow = true; return; }
+        if (lane == 0) spill[ns] = make_uint2(nv.eq, nv.class_len);
+        __syncwarp();
+        n_list++;
+    }
+    __device__ __forceinline__ void entry(uint32_t j, uint32_t& eq, uint32_t& len) const {  // uniform j
+        if (j < 32) {
+            eq = __shfl_sync(kFull, my_eq, j);
+            len = __shfl_sync(kFull, my_len, j);
+        } else {
+            uint2 e = spill[j - 32];
+            eq = e.x;
+            len = e.y;
+        }
+    }
+};
+
+// nodes_to_eq_class, ref src/pseudoaligner.rs:323-356, on the distinct visited classes.
+// The result is the ascending intersection (intersect keeps v1's order, :406); the sort by
+// length (:331-334) only picks the smallest class as v1.  Lane l tests member c0+l of the
+// smallest class against every other class by binary search (the reference's own search,
+// :404).  pass == 0 counts, pass == 1 writes the survivors to out[].
+template <int KW, bool EV>
+__device__ __forceinline__ uint32_t intersect_pass(WarpCtx<KW, EV>& w, uint32_t s_eq, uint32_t s_len, uint32_t* out) {
+    const DevIndex& ix = w.ix;
+    const uint64_t s_off = __ldg(ix.eq_off + s_eq);
+    uint32_t count = 0;
+    for (uint32_t c0 = 0; c0 < s_len; c0 += 32) {
+        bool alive = c0 + w.lane < s_len;
+        uint32_t mem = alive ? __ldg(ix.eq_mem + s_off + c0 + w.lane) : 0;
+        for (uint32_t j = 0; j < w.n_list; j++) {
+            uint32_t e, l;
+            w.entry(j, e, l);
+            if (e == s_eq) continue;
+            const uint64_t o = __ldg(ix.eq_off + e);
+            if (alive) alive = contains_sorted(ix.eq_mem + o, (uint64_t)l, mem);
+            if (!__any_sync(kFull, alive)) break;
+        }
+        unsigned b = __ballot_sync(kFull, alive);
+        if (out && alive) out[count + __popc(b & ((1u << w.lane) - 1))] = mem;
+        count += __popc(b);
+    }
+    return count;
+}
+
+template <int KW, bool EV>
+__global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix, const __grid_constant__ MapParams p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
+    LaneEvents tot{};
+    uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
+
+    for (uint64_t r = warp; r < p.reads.n; r += nwarps) {
+        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+        const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+        WarpCtx<KW, EV> w(ix, p.reads.words + wo, p.spill + warp * p.spill_cap, p.spill_cap);
+        uint32_t coverage = 0;
+        bool some = map_read_nodes(w, ix.k, (uint64_t)L, p.allowed_mismatches, coverage);
+
+        HitRec h;
+        h.coverage = 0; h.n_tx = 0; h.tx_off = 0; h.eq_id = kNone; h.flags = 0;
+        uint64_t count_slot = ix.n_eq + 1;  // None
+        if (some) {
+            // smallest class first (ref :331-334); ties broken by id so every lane agrees
+            uint64_t key = lane < w.n_list ? (((uint64_t)w.my_len << 32) | w.my_eq) : ~0ULL;
+            for (uint32_t j = 32 + lane; j < w.n_list; j += 32) {
+                uint2 e = w.spill[j - 32];
+                uint64_t kk = ((uint64_t)e.y << 32) | e.x;
+                key = kk < key ? kk : key;
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                uint64_t o = __shfl_xor_sync(kFull, key, d);
+                key = o < key ? o : key;
+            }
+            const uint32_t s_len = (uint32_t)(key >> 32), s_eq = (uint32_t)key;
+            uint32_t count, eq_id;
+            if (w.n_list == 1) {
+                count = s_len;
+                eq_id = s_eq;
+                if (EV && lane == 0) w.ev.members += s_len;
+            } else {
+                count = intersect_pass(w, s_eq, s_len, nullptr);
+                // the result equals a visited class iff that class has `count` members
+                uint32_t cand = (lane < w.n_list && w.my_len == count) ? w.my_eq : kNone;
+                for (uint32_t j = 32 + lane; j < w.n_list; j += 32) {
+                    uint2 e = w.spill[j - 32];
+                    if (e.y == count && e.x < cand) cand = e.x;
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, d));
+                eq_id = cand;
+                if (EV) {
+                    for (uint32_t j = 0; j < w.n_list; j++) {
+                        uint32_t e, l;
+                        w.entry(j, e, l);
+                        if (lane == 0) w.ev.members += l;
+                    }
+                }
+            }
+            h.coverage = coverage;
+            h.n_tx = count;
+            h.eq_id = eq_id;
+            h.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
+            if (eq_id != kNone) {
+                h.tx_off = __ldg(ix.eq_off + eq_id);  // members are read from the index by k_expand
+                count_slot = eq_id;
+            } else {
+                count_slot = ix.n_eq;
+                if (count && p.novel) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(p.novel_cursor, (unsigned long long)count);
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base + count <= p.novel_cap) intersect_pass(w, s_eq, s_len, p.novel + base);
+                    else if (lane == 0) atomicOr(p.status, 1u);
+                    h.tx_off = base;
+                }
+            }
+            if (w.spill_overflow && lane == 0) atomicOr(p.status, 2u);
+        }
+        if (lane == 0) {
+            p.hits[r] = h;
+            if (p.counts) atomicAdd(p.counts + count_slot, 1ULL);
+        }
+        if (EV) {
+            tot.lookups += w.ev.lookups; tot.levels += w.ev.levels; tot.hits += w.ev.hits; tot.verifs += w.ev.verifs;
+            tot.visits += w.ev.visits; tot.bases += w.ev.bases; tot.jumps += w.ev.jumps; tot.members += w.ev.members;
+            if (lane == 0) { ev_reads++; ev_bases += L; ev_out += h.n_tx; ev_aligned += some; }
+        }
+    }
+    if (EV && p.events) {
+        unsigned long long v[12] = {ev_reads, ev_bases, tot.lookups, tot.levels, tot.hits, tot.verifs,
+                                    tot.visits, tot.bases, tot.jumps, tot.members, ev_out, ev_aligned};
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            unsigned long long x = v[i];
+            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+            if (lane == 0 && x) atomicAdd(p.events + i, x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// result expansion: hits[i].tx_off (a source offset) -> members copied to tx_buf in read order
+// ---------------------------------------------------------------------------------------------
+struct TxLenN {  // iterator adaptor for the scan of n_tx; item n is a zero so that out[n] = total
+    const HitRec* h;
+    uint64_t n;
+    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)h[i].n_tx : 0; }
+};
+struct CastU64 {
+    __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }
+};
+
+// rel_off[i] = offset of read i's members inside this batch's tx_buf; running[0] = members
+// emitted by the batches before this one (so that tx_off is global across a chunked call).
+__global__ void k_expand(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
+                         const uint32_t* eq_mem, const uint32_t* novel, uint32_t* tx_buf, uint64_t tx_cap) {
+    const uint32_t sub = threadIdx.x & 7;
+    uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 3;
+    if (i >= n) return;
+    HitRec h = hits[i];
+    uint64_t rel = rel_off[i];
+    if (tx_buf && rel + h.n_tx <= tx_cap) {
+        const uint32_t* src = (h.eq_id != kNone ? eq_mem : novel) + h.tx_off;
+        for (uint32_t j = sub; j < h.n_tx; j += 8) tx_buf[rel + j] = src[j];
+    }
+    if (sub == 0) hits[i].tx_off = running[0] + rel;
+}
+// after k_expand: advance the running total, publish {running, status} for the host
+__global__ void k_advance(uint64_t* running, const uint64_t* batch_total, uint64_t tx_cap, int has_tx,
+                          const uint32_t* status, uint64_t* meta_out) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint64_t t = *batch_total;
+    uint32_t st = *status;
+    if (has_tx && t > tx_cap) st |= 4u;
+    running[0] += t;
+    meta_out[0] = running[0];
+    meta_out[1] = st;
+}
+
+}  // namespace psa

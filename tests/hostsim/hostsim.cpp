@@ -1,0 +1,271 @@
+// hostsim.cpp -- UNIT-TEST HARNESS, not product code.
+//
+// Compiles rust-pseudoaligner_b200/csrc/psa_core.cuh (the __host__ __device__ arithmetic the
+// CUDA kernels are made of: 2-bit access, k-mer hash, sector-block MPHF probe, value packing,
+// fingerprint + verification, per-word mismatch masks, the map_read state machine) with g++
+// and a serial "warp" policy, so that the tests that run without a GPU can compare that text
+// against the oracle.  It is built into tests/hostsim/libhostsim.so, loaded only by
+// tests/test_hostsim.py, and never linked into libpsa_b200.so -- the product has no CPU path.
+// The MPHF here is built serially on the host with the same layout rules the device builder
+// uses (level size = floor(gamma*n/192)+1 blocks, bits cleared on collision, cumulative rank
+// header), so the probe code sees a structure of identical shape.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../rust-pseudoaligner_b200/csrc/psa_core.cuh"
+
+using namespace psa;
+
+struct HsIndex {
+    DevIndex d{};
+    std::vector<uint64_t> blocks, values, seq, eq_off;
+    std::vector<NodeRec> nodes;
+    std::vector<uint32_t> eq_mem;
+    int kw = 1;
+    int error = 0;
+};
+
+struct HsHit {  // == psa_hit
+    uint32_t coverage, n_tx;
+    uint64_t tx_off;
+    uint32_t eq_id, flags;
+};
+
+template <int KW>
+static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* node_start, const uint32_t* node_len,
+                  const uint8_t* node_exts, const uint32_t* node_eq, double gamma) {
+    DevIndex& D = ix->d;
+    std::vector<Kmer<KW>> keys;
+    std::vector<uint64_t> vals;
+    uint64_t max_off = 0;
+    for (uint64_t i = 0; i < n_nodes; i++) {
+        uint64_t nk = node_len[i] - k + 1;
+        max_off = std::max(max_off, nk - 1);
+        for (uint64_t o = 0; o < nk; o++) {
+            keys.push_back(KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i] + o, k));
+            vals.push_back((i << 32) | o);
+        }
+    }
+    const uint64_t n_kmers = keys.size();
+    auto bits_for = [](uint64_t v) { uint32_t b = 1; while (b < 64 && (v >> b)) b++; return b; };
+    D.k = k;
+    D.node_bits = bits_for(n_nodes ? n_nodes - 1 : 0);
+    D.off_bits = bits_for(max_off);
+    int fp = 64 - (int)D.node_bits - (int)D.off_bits;
+    D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
+    D.n_nodes = n_nodes;
+    D.n_kmers = n_kmers;
+
+    // cascade
+    std::vector<uint64_t> rem_h(n_kmers);
+    for (uint64_t i = 0; i < n_kmers; i++) rem_h[i] = KmerOps<KW>::hash(keys[i]);
+    std::vector<uint64_t> cur = rem_h;
+    uint64_t total_blk = 0;
+    uint32_t lvl = 0;
+    while (!cur.empty()) {
+        if (lvl >= (uint32_t)kMaxLevels) { ix->error = 1; return; }
+        uint64_t nblk = std::max<uint64_t>(1, (uint64_t)(gamma * (double)cur.size() / kBlockBits) + 1);
+        ix->blocks.resize(4 * (total_blk + nblk), 0);
+        std::vector<uint64_t> coll(4 * nblk, 0);
+        for (uint64_t h : cur) {
+            uint64_t blk; uint32_t bit;
+            level_pos(level_hash(h, lvl), nblk, blk, bit);
+            uint64_t& w = ix->blocks[4 * (total_blk + blk) + 1 + (bit >> 6)];
+            uint64_t m = 1ULL << (bit & 63);
+            if (w & m) coll[4 * blk + 1 + (bit >> 6)] |= m;
+            w |= m;
+        }
+        std::vector<uint64_t> next;
+        for (uint64_t h : cur) {
+            uint64_t blk; uint32_t bit;
+            level_pos(level_hash(h, lvl), nblk, blk, bit);
+            if ((coll[4 * blk + 1 + (bit >> 6)] >> (bit & 63)) & 1) next.push_back(h);
+        }
+        for (uint64_t i = 0; i < 4 * nblk; i++) ix->blocks[4 * total_blk + i] &= ~coll[i];
+        D.mphf.level_nblk[lvl] = nblk;
+        D.mphf.level_base[lvl] = total_blk;
+        total_blk += nblk;
+        lvl++;
+        cur.swap(next);
+    }
+    D.mphf.n_levels = lvl;
+    uint64_t rank = 0;
+    for (uint64_t b = 0; b < total_blk; b++) {
+        uint32_t c1 = popc64(ix->blocks[4 * b + 1]), c2 = c1 + popc64(ix->blocks[4 * b + 2]);
+        ix->blocks[4 * b] = make_header(rank, c1, c2);
+        rank += c2 + popc64(ix->blocks[4 * b + 3]);
+    }
+    if (rank != n_kmers) { ix->error = 2; return; }
+    D.mphf.blocks = ix->blocks.data();
+    ix->values.assign(n_kmers + 1, 0);
+    D.values = ix->values.data();
+    std::vector<uint8_t> seen(n_kmers, 0);
+    for (uint64_t i = 0; i < n_kmers; i++) {
+        uint64_t slot; uint32_t levels;
+        if (!mphf_lookup(D.mphf, rem_h[i], slot, levels) || slot >= n_kmers || seen[slot]) { ix->error = 3; return; }
+        seen[slot] = 1;
+        ix->values[slot] = pack_value(D, (uint32_t)(vals[i] >> 32), (uint32_t)vals[i], rem_h[i]);
+    }
+    // nodes + edges
+    ix->nodes.resize(n_nodes + 1);
+    for (uint64_t i = 0; i < n_nodes; i++) {
+        NodeRec& r = ix->nodes[i];
+        r.start = node_start[i]; r.len = node_len[i]; r.eq = node_eq[i]; r.exts = node_exts[i];
+        r.class_len = (uint32_t)(ix->eq_off[r.eq + 1] - ix->eq_off[r.eq]);
+        r.pad[0] = r.pad[1] = 0;
+        for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
+    }
+    D.nodes = ix->nodes.data();
+    for (uint64_t i = 0; i < n_nodes; i++) {
+        NodeRec& r = ix->nodes[i];
+        Kmer<KW> first = KmerOps<KW>::get(PLoad{ix->seq.data()}, r.start, k);
+        Kmer<KW> last = KmerOps<KW>::get(PLoad{ix->seq.data()}, r.start + r.len - k, k);
+        for (uint32_t b = 0; b < 4; b++) {
+            uint32_t n, o;
+            if ((r.exts >> b) & 1) {
+                if (dict_get<KW>(D, KmerOps<KW>::extend_right(last, b, k), n, o, nullptr) && o == 0) r.succ[b] = n;
+                else ix->error = 4;
+            }
+            if ((r.exts >> (4 + b)) & 1) {
+                if (dict_get<KW>(D, KmerOps<KW>::extend_left(first, b, k), n, o, nullptr) && o == ix->nodes[n].len - k) r.pred[b] = n;
+                else ix->error = 4;
+            }
+        }
+    }
+}
+
+// serial stand-in for the warp-cooperative steps: same per-lane functions, lanes looped
+template <int KW>
+struct SerialWarp {
+    const DevIndex& ix;
+    PLoad rd;
+    uint32_t k;
+    std::vector<uint32_t> eqs, lens;  // distinct visited classes
+    uint64_t lookups = 0;
+
+    bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
+        if (kmer_pos > last) return false;
+        const uint64_t start = kmer_pos;
+        // lane order == position order, so the first hitting lane is the sequential first hit
+        for (uint64_t p = start; p <= last; p += kSeedStride) {
+            lookups++;
+            if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr)) { kmer_pos = p; return true; }
+        }
+        kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);
+        return false;
+    }
+    uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
+    NodeView node(uint32_t id) const {
+        const NodeRec& r = ix.nodes[id];
+        return NodeView{r.start, r.len, r.eq, r.class_len, r.exts};
+    }
+    uint32_t succ(uint32_t id, uint32_t b) { return ix.nodes[id].succ[b]; }
+    uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes[id].pred[b]; }
+    // the two compare loops, chunked by 32 bases exactly as the kernel lanes are
+    template <bool FWD>
+    uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
+        uint32_t snp = 0;
+        for (uint64_t my = 0; my < m; my += 32) {
+            uint32_t n = (uint32_t)std::min<uint64_t>(32, m - my);
+            uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
+                                : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
+            uint32_t c = (uint32_t)popc64(mask);
+            if (snp + c > A) {
+                premature = true;
+                return my + nth_mismatch(mask, A + 1 - snp);
+            }
+            snp += c;
+        }
+        return m;
+    }
+    uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
+    void push(uint32_t, const NodeView& nv) {
+        if (std::find(eqs.begin(), eqs.end(), nv.eq) != eqs.end()) return;
+        eqs.push_back(nv.eq);
+        lens.push_back(nv.class_len);
+    }
+};
+
+template <int KW>
+static void map_one(const HsIndex* ix, const uint64_t* words, uint32_t L, uint32_t allowed, HsHit& h,
+                    std::vector<uint32_t>& tx) {
+    SerialWarp<KW> w{ix->d, PLoad{words}, ix->d.k, {}, {}};
+    uint32_t cov = 0;
+    h.coverage = 0; h.n_tx = 0; h.tx_off = tx.size(); h.eq_id = kNone; h.flags = 0;
+    if (!map_read_nodes(w, ix->d.k, (uint64_t)L, allowed, cov)) return;
+    // smallest class, then keep its members found in every other class
+    size_t s = 0;
+    for (size_t j = 1; j < w.eqs.size(); j++)
+        if (w.lens[j] < w.lens[s] || (w.lens[j] == w.lens[s] && w.eqs[j] < w.eqs[s])) s = j;
+    const uint32_t* sm = ix->eq_mem.data() + ix->eq_off[w.eqs[s]];
+    uint32_t count = 0;
+    for (uint32_t i = 0; i < w.lens[s]; i++) {
+        bool alive = true;
+        for (size_t j = 0; j < w.eqs.size() && alive; j++)
+            if (j != s) alive = contains_sorted(ix->eq_mem.data() + ix->eq_off[w.eqs[j]], (uint64_t)w.lens[j], sm[i]);
+        if (alive) { tx.push_back(sm[i]); count++; }
+    }
+    uint32_t eq_id = kNone;
+    for (size_t j = 0; j < w.eqs.size(); j++)
+        if (w.lens[j] == count && w.eqs[j] < eq_id) eq_id = w.eqs[j];
+    h.coverage = cov; h.n_tx = count; h.eq_id = eq_id;
+    h.flags = 1u | ((cov >= kCoverageThreshold && count == 0) ? 2u : 0u);
+}
+
+extern "C" {
+
+HsIndex* hs_index_create(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words, uint64_t n_seq_words,
+                         const uint64_t* node_start, const uint32_t* node_len, const uint8_t* node_exts,
+                         const uint32_t* node_eq, uint64_t n_eq, const uint64_t* eq_offsets,
+                         const uint32_t* eq_members, double gamma) {
+    HsIndex* ix = new HsIndex();
+    ix->seq.assign(seq_words, seq_words + n_seq_words);
+    ix->seq.push_back(0); ix->seq.push_back(0);
+    ix->eq_off.assign(eq_offsets, eq_offsets + n_eq + 1);
+    ix->eq_mem.assign(eq_members, eq_members + eq_offsets[n_eq]);
+    ix->d.seq = ix->seq.data();
+    ix->d.eq_off = ix->eq_off.data();
+    ix->d.eq_mem = ix->eq_mem.data();
+    ix->d.n_eq = n_eq;
+    ix->kw = k <= 32 ? 1 : 2;
+    if (gamma <= 0) gamma = 1.7;
+    if (ix->kw == 1) build<1>(ix, k, n_nodes, node_start, node_len, node_exts, node_eq, gamma);
+    else build<2>(ix, k, n_nodes, node_start, node_len, node_exts, node_eq, gamma);
+    return ix;
+}
+int hs_index_error(const HsIndex* ix) { return ix->error; }
+uint32_t hs_index_levels(const HsIndex* ix) { return ix->d.mphf.n_levels; }
+uint32_t hs_index_fp_bits(const HsIndex* ix) { return ix->d.fp_bits; }
+void hs_index_destroy(HsIndex* ix) { delete ix; }
+
+int hs_lookup(const HsIndex* ix, const uint64_t* kmer_words, uint32_t* node, uint32_t* off) {
+    if (ix->kw == 1) return dict_get<1>(ix->d, KmerOps<1>::get(PLoad{kmer_words}, 0, ix->d.k), *node, *off, nullptr);
+    return dict_get<2>(ix->d, KmerOps<2>::get(PLoad{kmer_words}, 0, ix->d.k), *node, *off, nullptr);
+}
+
+// returns the number of tx entries needed; fills up to tx_cap
+uint64_t hs_map_batch(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off, const uint32_t* read_len,
+                      uint64_t n, uint32_t allowed, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap) {
+    std::vector<uint32_t> tx;
+    for (uint64_t i = 0; i < n; i++) {
+        if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+        else map_one<2>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+    }
+    memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
+    return tx.size();
+}
+
+// ASCII -> DnaString words with the product's base_code()
+void hs_pack_ascii(const uint8_t* s, uint64_t len, uint64_t* words) {
+    for (uint64_t j = 0; j < (len + 31) / 32; j++) {
+        uint64_t v = 0;
+        for (uint64_t t = 0; t < 32 && 32 * j + t < len; t++) v |= (uint64_t)base_code(s[32 * j + t]) << (62 - 2 * t);
+        words[j] = v;
+    }
+}
+}

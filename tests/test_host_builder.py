@@ -1,0 +1,95 @@
+"""The product's host graph builder (libpsa_host.so) against the oracle's naive builder and
+against the transcripts themselves (validate_dbg (a), ref src/build_index.rs:263-298)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import orc
+import util
+
+host = importlib.import_module("rust-pseudoaligner_b200.host")
+
+
+def _codes(seqs):
+    return host.encode_transcripts(seqs)
+
+
+@pytest.mark.parametrize("k", [20, 24, 64])
+def test_builder_matches_oracle_on_fixture(fixture_fasta, orc_index_for, k):
+    codes, off = _codes(fixture_fasta[1])
+    flat, stats = host.build_graph(codes, off, k, threads=4)
+    ox = orc_index_for(k)
+    assert stats["n_kmers"] == ox.n_kmers and stats["n_nodes"] == ox.n_nodes and stats["n_eq"] == ox.n_eq
+    assert util.canonical_nodes(flat) == util.canonical_nodes(ox.flat())
+    # class ids follow the same first-appearance rule in both builders
+    of = ox.flat()
+    assert np.array_equal(flat["eq_offsets"], of["eq_offsets"]) and np.array_equal(flat["eq_members"], of["eq_members"])
+    # and the oracle accepts the product-built graph as a valid index (every ext resolves)
+    orc.OrcIndex.from_flat(flat).close()
+
+
+def test_builder_validate_dbg_a(fixture_fasta):
+    codes, off = _codes(fixture_fasta[1])
+    flat, _ = host.build_graph(codes, off, 20, threads=3)
+    seqs_codes = [codes[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+    util.check_index_against_transcripts(flat, seqs_codes)
+
+
+@pytest.mark.parametrize("k", [2, 5, 19, 31, 32, 33, 47, 64])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_builder_random_transcriptomes(k, threads):
+    rng = np.random.default_rng(k)
+    for _ in range(3):
+        seqs = util.random_transcriptome(rng, n_genes=10, k=max(k, 3))
+        codes, off = _codes(seqs)
+        flat, stats = host.build_graph(codes, off, k, threads=threads)
+        if k >= 5:
+            ox = orc.OrcIndex.build(seqs, k)
+            assert util.canonical_nodes(flat) == util.canonical_nodes(ox.flat())
+            assert k < 19 or stats["n_cycles"] >= 1          # the ACG tandem repeat
+        else:
+            orc.OrcIndex.from_flat(flat).close()
+
+
+def test_builder_thread_count_invariant():
+    rng = np.random.default_rng(0)
+    seqs = util.random_transcriptome(rng, n_genes=30, k=21)
+    codes, off = _codes(seqs)
+    a, _ = host.build_graph(codes, off, 21, threads=1)
+    b, _ = host.build_graph(codes, off, 21, threads=7)
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+
+
+def test_synth_is_deterministic_and_shaped():
+    t1 = host.Transcriptome.synth(2, 40, threads=1)
+    t2 = host.Transcriptome.synth(2, 40, threads=6)
+    assert t1.n_tx == t2.n_tx and np.array_equal(t1.codes(), t2.codes()) and np.array_equal(t1.tx_off(), t2.tx_off())
+    assert 100 < t1.n_tx < 2000 and t1.codes().max() <= 3
+    r1, k1 = t1.reads(3, 0, 5000, 150, kinds=True, threads=1)
+    r2 = t2.reads(3, 1000, 100, 150, threads=3)
+    assert np.array_equal(r1[1000 * 150:1100 * 150], r2[:100 * 150])      # counter-based: any slice regenerates
+    assert set(np.unique(r1[:-1]).tolist()) <= set(b"ACGT")
+    frac = np.bincount(k1, minlength=3) / 5000.0
+    assert abs(frac[0] - 0.90) < 0.03 and abs(frac[1] - 0.05) < 0.02 and abs(frac[2] - 0.05) < 0.02
+    # transcript reads are substrings of the transcriptome up to substitutions
+    codes = t1.codes()
+    text = np.frombuffer(b"ACGT", np.uint8)[codes].tobytes()
+    exact = sum(1 for i in np.flatnonzero(k1 == 0)[:300] if r1[i * 150:(i + 1) * 150].tobytes() in text)
+    assert exact > 100
+
+
+def test_fasta_fastq_readers(tmp_path, fixture_fasta, fixture_fastq):
+    import gzip, os
+    from conftest import GOLDEN
+    fa = tmp_path / "t.fa"
+    fa.write_bytes(gzip.open(os.path.join(GOLDEN, "gencode_small.fa.gz")).read())
+    names, data, off = host.read_fasta(fa)
+    assert names == fixture_fasta[0]
+    assert all(data[int(off[i]):int(off[i + 1])].tobytes() == fixture_fasta[1][i] for i in range(0, len(names), 37))
+    fq = tmp_path / "t.fq"
+    fq.write_bytes(gzip.open(os.path.join(GOLDEN, "small.fq.gz")).read())
+    ids, data, off = host.read_fastq(fq)
+    assert ids == [r[0] for r in fixture_fastq]
+    assert all(data[int(off[i]):int(off[i + 1])].tobytes().decode() == fixture_fastq[i][1] for i in range(0, len(ids), 101))

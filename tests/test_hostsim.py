@@ -1,0 +1,146 @@
+"""CPU checks of the code the CUDA kernels are built from.
+
+tests/hostsim/ compiles rust-pseudoaligner_b200/csrc/psa_core.cuh with g++ and a serial warp
+policy; here its results are compared with the oracle read by read.  This pins, without a
+GPU: the MPHF block layout + rank + fingerprint + verification, the successor/predecessor
+tables, the 32-base mismatch masks of both extension loops, the map_read state machine as the
+kernel runs it, and ASCII packing.  (The warp-shuffle glue itself is covered by the
+`-m gpu` parity tests.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+import orc
+import util
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["make", "-C", _DIR, "libhostsim.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(_DIR, "libhostsim.so"))
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    L.hs_index_create.restype = vp
+    L.hs_index_create.argtypes = [u32, u64, vp, u64, vp, vp, vp, vp, u64, vp, vp, C.c_double]
+    L.hs_index_error.restype, L.hs_index_error.argtypes = C.c_int, [vp]
+    L.hs_index_levels.restype, L.hs_index_levels.argtypes = u32, [vp]
+    L.hs_index_fp_bits.restype, L.hs_index_fp_bits.argtypes = u32, [vp]
+    L.hs_index_destroy.argtypes = [vp]
+    L.hs_lookup.restype, L.hs_lookup.argtypes = C.c_int, [vp, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.hs_map_batch.restype = u64
+    L.hs_map_batch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64]
+    L.hs_pack_ascii.argtypes = [C.c_char_p, u64, vp]
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HsIndex:
+    def __init__(self, L, flat, gamma=0.0):
+        self.L = L
+        f = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in flat.items()}
+        self.keep = f
+        self.h = L.hs_index_create(int(f["k"]), len(f["node_len"]), _p(f["seq_words"]), len(f["seq_words"]),
+                                   _p(f["node_start"]), _p(f["node_len"]), _p(f["node_exts"]), _p(f["node_eq"]),
+                                   len(f["eq_offsets"]) - 1, _p(f["eq_offsets"]), _p(f["eq_members"]), gamma)
+        assert L.hs_index_error(self.h) == 0, "hostsim index error %d" % L.hs_index_error(self.h)
+
+    def map_batch(self, words, off, lens, allowed=2):
+        n = len(lens)
+        hits = np.zeros(n, dtype=orc.HIT_DTYPE)
+        cap = max(64 * n, 4096)
+        while True:
+            tx = np.zeros(cap, np.uint32)
+            need = self.L.hs_map_batch(self.h, _p(words), _p(off), _p(lens), n, allowed, _p(hits), _p(tx), cap)
+            if need <= cap:
+                return hits, tx[:need]
+            cap = int(need)
+
+    def close(self):
+        self.L.hs_index_destroy(self.h)
+
+
+def _compare(ix_orc, ix_hs, reads):
+    words, off, lens = orc.pack_reads(reads)
+    h1, t1, _, _ = ix_orc.map_batch(words, off, lens)
+    h2, t2 = ix_hs.map_batch(words, off, lens)
+    a, b = orc.hits_to_tuples(h1, t1), orc.hits_to_tuples(h2, t2)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x == y, (i, reads[i], x, y)
+    assert np.array_equal(h1["eq_id"], h2["eq_id"])
+    return a
+
+
+@pytest.mark.parametrize("k,length", [(20, 150), (20, 60), (24, 91), (64, 150)])
+def test_hostsim_vs_oracle_fixture(hs, orc_index_for, fixture_fasta, fixture_fastq, k, length):
+    ix = orc_index_for(k)
+    hx = HsIndex(hs, ix.flat())
+    assert hs.hs_index_fp_bits(hx.h) >= 16
+    rng = np.random.default_rng(77 * k + length)
+    n_left = 0
+    for name, reads in cases.read_sets(rng, fixture_fasta[1], length, k).items():
+        res = _compare(ix, hx, reads)
+        if name == "left_ext":
+            n_left = sum(1 for r in res if r[0])
+    assert n_left > 100
+    if k == 20 and length == 60:
+        _compare(ix, hx, [s for _, s in fixture_fastq])
+    hx.close()
+
+
+def test_hostsim_lookup_every_kmer(hs, orc_index_for):
+    """validate_dbg (a)-style: every k-mer of every node resolves to its (node, offset); k-mers
+    that are not in the graph resolve to nothing (ref src/build_index.rs:263-298, :99-107)."""
+    ix = orc_index_for(20)
+    flat = ix.flat()
+    hx = HsIndex(hs, flat)
+    nt = util.node_kmer_table(flat)
+    rng = np.random.default_rng(3)
+    pick = rng.choice(len(nt["lo"]), 20000, replace=False)
+    n, o = C.c_uint32(), C.c_uint32()
+    for i in pick.tolist():
+        w = np.array([int(nt["lo"][i]) << (64 - 40), 0], dtype=np.uint64)
+        assert hs.hs_lookup(hx.h, _p(w), C.byref(n), C.byref(o)) == 1
+        assert (n.value, o.value) == (int(nt["node"][i]), int(nt["off"][i]))
+    present = set(nt["lo"].tolist())
+    miss = 0
+    for v in rng.integers(0, 1 << 40, 20000).tolist():
+        if v in present:
+            continue
+        w = np.array([v << 24, 0], dtype=np.uint64)
+        assert hs.hs_lookup(hx.h, _p(w), C.byref(n), C.byref(o)) == 0
+        miss += 1
+    assert miss > 19000
+    hx.close()
+
+
+@pytest.mark.parametrize("k", [5, 19, 31, 32, 33, 47, 64])
+def test_hostsim_vs_oracle_random_transcriptomes(hs, k):
+    rng = np.random.default_rng(100 + k)
+    seqs = util.random_transcriptome(rng, n_genes=8, k=k)
+    ix = orc.OrcIndex.build(seqs, k)
+    for gamma in (0.0, 1.0, 3.0):
+        hx = HsIndex(hs, ix.flat(), gamma)
+        for length in (k, k + 1, 2 * k + 3, 150, 1100):
+            for name, reads in cases.read_sets(rng, seqs, length, k, scale=0.1).items():
+                _compare(ix, hx, [r[:length] if name != "edge" else r for r in reads])
+        hx.close()
+
+
+def test_hostsim_pack_ascii_matches_oracle(hs):
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        n = int(rng.integers(0, 200))
+        s = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        a = np.zeros((n + 31) // 32 + 1, np.uint64)
+        b = np.zeros((n + 31) // 32 + 1, np.uint64)
+        hs.hs_pack_ascii(s, n, _p(a))
+        orc.lib().orc_pack_ascii(s, n, _p(b))
+        assert np.array_equal(a, b), s
