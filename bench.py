@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s pseudoaligned (150 bp) on N B200s, with roofline and CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step is one pass of the hot path (ASCII -> 2-bit pack, map kernel, result scan + expansion,
+per-class counting) over one batch of synthetic 150 bp reads.  The default workload is BASELINE
+config 3: reads sampled from a synthetic GENCODE-scale transcriptome (20 000 genes, ~200 k
+transcripts, k = 24).  `value` times K steps with the batch resident in HBM; `e2e` times the
+same K batches through the public C ABI call (psa_mapper_map) from pinned HOST buffers, H2D and
+D2H inside the timed region.  The reference arm times the CPU oracle (C restatement of the
+reference's map_read; the Rust crate cannot be built in this image) on all host threads.
+"""
+import argparse
+import gzip
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+PKG = "rust-pseudoaligner_b200"
+METRIC = "reads/sec pseudoaligned (150 bp)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gencode_synth", choices=["gencode_synth", "gencode_small"])
+    ap.add_argument("--genes", type=int, default=20000, help="synthetic transcriptome size (20000 ~ 200k transcripts)")
+    ap.add_argument("--k", type=int, default=0, help="k-mer length (default: 24 synthetic, 20 gencode_small)")
+    ap.add_argument("--read-len", type=int, default=150)
+    ap.add_argument("--reads-per-step", type=int, default=1 << 23)
+    ap.add_argument("--distinct-batches", type=int, default=3, help="distinct read batches rotated over the steps")
+    ap.add_argument("--gamma", type=float, default=0.0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cache-dir", default="/dev/shm")
+    ap.add_argument("--host-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ workload
+def workload_name(a):
+    if a.workload == "gencode_small":
+        return "config2: synthetic %d bp reads vs test/gencode_small.fa index, k=%d" % (a.read_len, a.k)
+    return "config3: synthetic %d bp reads vs synthetic GENCODE-scale transcriptome (%d genes), k=%d" % (
+        a.read_len, a.genes, a.k)
+
+
+def load_transcriptome(a, host, threads):
+    if a.workload == "gencode_small":
+        names, seqs, cur = [], [], []
+        with gzip.open(os.path.join(ROOT, "tests", "golden", "gencode_small.fa.gz"), "rt") as f:
+            for line in f:
+                line = line.rstrip("\r\n")
+                if line.startswith(">"):
+                    if names:
+                        seqs.append("".join(cur).encode())
+                    names.append(line[1:])
+                    cur = []
+                elif line:
+                    cur.append(line)
+        seqs.append("".join(cur).encode())
+        codes, off = host.encode_transcripts(seqs)
+        return host.Transcriptome.from_codes(codes, off)
+    return host.Transcriptome.synth(2, a.genes, threads=threads)
+
+
+FLAT_KEYS = ("seq_words", "node_start", "node_len", "node_exts", "node_eq", "eq_offsets", "eq_members")
+
+
+def load_index(a, host, tr, rank, world, barrier, threads):
+    """Host graph build (rank 0), shared with the other ranks through cache_dir."""
+    tag = "psa_%s_g%d_k%d" % (a.workload, a.genes if a.workload == "gencode_synth" else 0, a.k)
+    d = os.path.join(a.cache_dir, tag)
+    done = os.path.join(d, "done")
+    t0 = time.time()
+    if rank == 0 and not os.path.exists(done):
+        flat, stats = host.build_graph(tr.codes(), tr.tx_off(), a.k, threads=threads)
+        try:
+            os.makedirs(d, exist_ok=True)
+            for key in FLAT_KEYS:
+                np.save(os.path.join(d, key + ".npy"), flat[key])
+            open(done, "w").write(json.dumps(stats))
+        except OSError:
+            if world > 1:
+                raise
+        build_s = time.time() - t0
+        if world == 1:
+            return flat, build_s
+    barrier()
+    flat = {"k": a.k}
+    for key in FLAT_KEYS:
+        flat[key] = np.load(os.path.join(d, key + ".npy"), mmap_mode="r")
+        flat[key] = np.ascontiguousarray(flat[key])
+    return flat, time.time() - t0
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# ------------------------------------------------------------------------------------ algorithmic bytes
+def algorithmic_bytes(ev, k, hit_bytes=24):
+    """Bytes the algorithm needs per DESIGN.md section 'Algorithmic bytes' (sequential-equivalent
+    events; speculative probes, sector padding and re-reads are NOT counted)."""
+    kb = (2 * k + 7) // 8
+    b = 0.0
+    b += ev["read_bases"] / 4.0                       # packed read, 2 bit/base
+    b += 8.0 * ev["mphf_levels"]                      # one bit-vector word per level probed
+    b += 16.0 * ev["mphf_hits"]                       # rank header + values entry
+    b += (8.0 + kb) * ev["verifications"]             # node start + unitig k-mer
+    b += 24.0 * ev["node_visits"]                     # start, len, eq, class_len, exts
+    b += 0.25 * ev["bases_compared"]                  # unitig side of the compares
+    b += 4.0 * ev["edge_jumps"]                       # one successor / predecessor entry
+    b += 4.0 * ev["class_members"]                    # class members read by the intersection
+    b += hit_bytes * ev["reads"] + 4.0 * ev["out_members"]   # psa_hit + members written
+    return b
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads):
+    """Times the oracle (oracle/psa_oracle.c, the C restatement of the reference's map_read) on
+    `threads` host threads over bounded samples of the workload.  Returns (reads/s, info)."""
+    import orc
+    t0 = time.time()
+    ox = orc.OrcIndex.from_flat(flat)
+    index_s = time.time() - t0
+    L = a.read_len
+    nw = (L + 31) // 32
+
+    shifts = (62 - 2 * np.arange(32, dtype=np.uint64)).astype(np.uint64)
+    lut = np.zeros(256, np.uint64)
+    for ch, v in ((b"C", 1), (b"G", 2), (b"T", 3), (b"c", 1), (b"g", 2), (b"t", 3)):
+        lut[ch[0]] = v
+
+    def make_sample(first, n):
+        data = tr.reads(3, first, n, L, threads=threads)
+        words = np.zeros(n * nw + 1, np.uint64)
+        for c0 in range(0, n, 65536):           # ASCII -> DnaString words, untimed
+            c1 = min(n, c0 + 65536)
+            codes = np.zeros((c1 - c0, nw * 32), np.uint64)
+            codes[:, :L] = lut[data[c0 * L:c1 * L].reshape(c1 - c0, L)]
+            words[c0 * nw:c1 * nw] = np.bitwise_or.reduce(codes.reshape(c1 - c0, nw, 32) << shifts, axis=2).reshape(-1)
+        off = (np.arange(n, dtype=np.uint64) * np.uint64(nw))
+        lens = np.full(n, L, np.uint32)
+        return words, off, lens
+
+    def run(words, off, lens, n):
+        bounds = [n * t // threads for t in range(threads + 1)]
+        res = [None] * threads
+
+        def work(t):
+            res[t] = ox.map_batch(words, off, lens, start=bounds[t], stop=bounds[t + 1])[0]["flags"].sum()
+        th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        t1 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t1
+
+    # calibrate on a small sample, then size the steps to the budget
+    n0 = 2000 * threads
+    w, o, l = make_sample(10 ** 9, n0)
+    dt = run(w, o, l, n0)
+    rate = n0 / dt
+    total_steps = max(1, steps + warmup)
+    n = int(max(2000 * threads, min(4e6, rate * budget_s / total_steps)))
+    w, o, l = make_sample(0, n)
+    for _ in range(warmup):
+        run(w, o, l, n)
+    t_sum = 0.0
+    for _ in range(steps):
+        t_sum += run(w, o, l, n)
+    value = steps * n / t_sum
+    ox.close()
+    return value, {"sample": "%d steps x %d reads (first reads of the workload's stream), %d threads" % (steps, n, threads),
+                   "reads_per_step": n, "ms_per_step": 1e3 * t_sum / steps, "oracle_index_s": index_s}
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    a = parse_args()
+    if a.k == 0:
+        a.k = 24 if a.workload == "gencode_synth" else 20
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+    host_threads = a.host_threads or max(1, ncores // max(1, world))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        host = importlib.import_module(PKG + ".host")
+        tr = load_transcriptome(a, host, ncores)
+        flat, _ = load_index(a, host, tr, 0, 1, lambda: None, ncores)
+        threads = a.host_threads or ncores
+        value, info = cpu_arm(a, tr, flat, a.steps, a.warmup, max(a.cpu_seconds, 20.0), threads)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_step": info["reads_per_step"], "read_len": a.read_len,
+                       "k": a.k, "note": "C restatement of the reference's map_read (oracle/psa_oracle.c): the Rust "
+                                         "crate and its debruijn/boomphf dependencies cannot be built in this image"},
+            "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    pkg = importlib.import_module(PKG)
+    host = importlib.import_module(PKG + ".host")
+    psa = pkg.pseudoaligner
+
+    t_setup = time.time()
+    tr = load_transcriptome(a, host, host_threads)
+    flat, build_s = load_index(a, host, tr, rank, world, barrier, ncores if rank == 0 else host_threads)
+    index = pkg.Index(flat, device=local_rank, gamma=a.gamma)
+    info = index.info()
+    mapper = pkg.Mapper(index)
+    stream = torch.cuda.ExternalStream(mapper.stream(), device=local_rank)
+
+    R, L, G = a.reads_per_step, a.read_len, max(1, a.distinct_batches)
+    tx_cap = 24 * R
+    # distinct batches of this rank's share of the read stream: host (pinned) and device copies
+    host_batches, dev_batches = [], []
+    for g in range(G):
+        pin = psa.PinnedArray(R * L + 64, np.uint8)
+        tr.reads(3, (rank * G + g) * R, R, L, out=pin.array, threads=host_threads)
+        host_batches.append(pin)
+        dev_batches.append(pkg.DeviceBatch(psa.READS_ASCII, pin.array, R, stride=L, fixed_len=L, tx_cap=tx_cap))
+    pin_hits = psa.PinnedArray(R, pkg.HIT_DTYPE)
+    pin_tx = psa.PinnedArray(tx_cap, np.uint32)
+    setup_s = time.time() - t_setup
+
+    # events of one batch (untimed): the algorithmic work the roofline is computed from
+    ev = mapper.map_device_events(dev_batches[0])
+    mapper.counts_reset()
+    a_bytes_per_read = algorithmic_bytes(ev, a.k) / ev["reads"]
+
+    comm = None
+    if world > 1:
+        uid = [pkg.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = pkg.Comm(uid[0], world, rank, local_rank)
+
+    # ---------------- kernel-resident arm: `value`
+    for s in range(a.warmup):
+        mapper.map_device_async(dev_batches[s % G])
+        mapper.sync()
+    mapper.counts_reset()
+    launches0 = mapper.launch_count()
+    mapper.profile_enable(True)
+    mapper.profile_read()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(a.steps):
+        mapper.map_device_async(dev_batches[s % G])
+    if comm is not None:
+        mapper.sync()
+        mapper.counts_allreduce(comm)      # the path's one collective: per-class counts summed over NVLink
+    e1.record(stream)
+    mapper.sync()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    map_ms, map_launches = mapper.profile_read()
+    mapper.profile_enable(False)
+    launches = mapper.launch_count() - launches0
+    counts = mapper.counts()
+    total_reads_counted = int(counts.sum())
+    expect = a.steps * R * (world if comm is not None else 1)
+    assert total_reads_counted == expect, "per-class counts sum to %d, expected %d" % (total_reads_counted, expect)
+    ms_t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = world * a.steps * R / (ms_max / 1e3)
+
+    # ---------------- end-to-end arm through the public call, host buffers
+    e2e = None
+    if not a.no_e2e:
+        def e2e_step(g):
+            return mapper._map_host(psa.READS_ASCII, host_batches[g].array, R, None, None, L, L, True,
+                                    tx_cap=tx_cap, hits=pin_hits.array, tx=pin_tx.array)
+        e2e_step(0)
+        e2e_step(1 % G)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        used = 0
+        for s in range(a.steps):
+            h, tx = e2e_step(s % G)
+            used += len(tx)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        e2e = {"value": world * a.steps * R / dt, "unit": "reads/s", "h2d_bytes_per_step": R * L,
+               "d2h_bytes_per_step": R * pkg.HIT_DTYPE.itemsize + 4 * used // a.steps + 16 * ((R + (1 << 20) - 1) >> 20),
+               "ms_per_step": 1e3 * dt / a.steps, "api": "psa_mapper_map (host ASCII batch -> psa_hit[] + tx_buf)"}
+
+    # ---------------- roofline of the dominant kernel (k_map)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    map_ms_per_launch = map_ms / max(1, map_launches)
+    achieved = a_bytes_per_read * R / (map_ms_per_launch / 1e3) / 1e9 if map_launches else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_map", "kernel_ms_per_launch": map_ms_per_launch,
+                "kernel_share_of_step": map_ms / ms if ms else None,
+                "algorithmic_bytes_per_read": a_bytes_per_read, "peak_source": peak_src,
+                "note": "latency-bound dependent random gathers: see DESIGN.md for the sector-rate view"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = a.host_threads or ncores
+        v, ci = cpu_arm(a, tr, flat, 3, 1, a.cpu_seconds, threads)
+        cpu = {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": ci["sample"],
+               "note": "oracle/psa_oracle.c, the C restatement of the reference's map_read (Rust toolchain absent)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reads_per_step_per_gpu": R, "read_len": L, "k": a.k,
+                       "input": "ASCII reads resident in HBM; each step packs, maps, scans and expands one batch",
+                       "l2": "inputs larger than L2 (%.0f MB per batch, %d distinct batches rotated; index %.0f MB)" % (
+                           R * L / 1e6, G, (info["mphf_bytes"] + info["values_bytes"] + info["node_bytes"]
+                                            + info["seq_bytes"] + info["eq_bytes"]) / 1e6),
+                       "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
+                                                                  "mphf_levels", "fp_bits", "max_class_len")},
+                       "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",
+                       "host_cores": ncores, "index_build_s": build_s, "setup_s": setup_s},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "events_per_read": {key: ev[key] / ev["reads"] for key in ev if key != "reads"},
+        }
+        print(json.dumps(line))
+    if comm is not None:
+        comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -207,6 +207,11 @@ int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_b
 
 /* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
 uint64_t psa_mapper_launch_count(const psa_mapper*);
+/* Device timing of the map kernel alone: when enabled, every k_map launch is bracketed by
+ * CUDA events on the mapper's stream.  psa_mapper_profile_read synchronises, returns the
+ * summed kernel time and launch count since the last read, and resets them. */
+int psa_mapper_profile_enable(psa_mapper*, int on);
+int psa_mapper_profile_read(psa_mapper*, double* map_kernel_ms, uint64_t* map_launches);
 
 /* ---- multi-GPU: reads shard across ranks, one all-reduce of the per-class counts ---- */
 typedef struct psa_comm psa_comm;

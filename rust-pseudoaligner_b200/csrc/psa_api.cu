@@ -13,6 +13,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/psa.h"
@@ -441,6 +442,9 @@ struct psa_mapper {
     int grid = 0;
     Slot slot[2];
     uint64_t launches = 0;
+    // map-kernel timing (psa_mapper_profile_*)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     // pending async call
     psa_result_batch* pending = nullptr;
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
@@ -611,8 +615,18 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     p.events = EV ? m->events.as<unsigned long long>() : nullptr;
     const int grid = mapper_grid(m);
     if (n) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (m->profiling) {
+            CU(cudaEventCreate(&e0));
+            CU(cudaEventCreate(&e1));
+            CU(cudaEventRecord(e0, st));
+        }
         if (ix->kw == 1) k_map<1, EV><<<grid, 256, 0, st>>>(ix->d, p);
         else k_map<2, EV><<<grid, 256, 0, st>>>(ix->d, p);
+        if (m->profiling) {
+            CU(cudaEventRecord(e1, st));
+            m->prof_events.emplace_back(e0, e1);
+        }
         m->launches++;
         CU(cudaGetLastError());
     }
@@ -908,6 +922,29 @@ extern "C" int psa_mapper_map_read(psa_mapper* m, const uint64_t* read_words, ui
     *coverage = h.coverage;
     if (rc) return rc;
     return (h.flags & PSA_FLAG_ALIGNED) ? 1 : 0;
+}
+
+extern "C" int psa_mapper_profile_enable(psa_mapper* m, int on) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    m->profiling = on != 0;
+    return PSA_OK;
+}
+extern "C" int psa_mapper_profile_read(psa_mapper* m, double* map_kernel_ms, uint64_t* map_launches) {
+    if (!m || !map_kernel_ms || !map_launches) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaStreamSynchronize(m->st));
+    double ms = 0;
+    for (auto& pr : m->prof_events) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *map_kernel_ms = ms;
+    *map_launches = m->prof_events.size();
+    m->prof_events.clear();
+    return PSA_OK;
 }
 
 extern "C" int psa_mapper_counts_get(psa_mapper* m, uint64_t* counts_host) {

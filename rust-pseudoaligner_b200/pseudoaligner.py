@@ -74,6 +74,7 @@ EXPORTS = (
     "psa_mapper_map", "psa_mapper_map_async", "psa_mapper_sync", "psa_mapper_stream",
     "psa_mapper_map_read", "psa_mapper_counts_get", "psa_mapper_counts_reset",
     "psa_mapper_counts_device", "psa_mapper_map_events", "psa_mapper_launch_count",
+    "psa_mapper_profile_enable", "psa_mapper_profile_read",
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
     "psa_memcpy_h2d", "psa_memcpy_d2h",
@@ -123,6 +124,9 @@ def lib():
     L.psa_mapper_counts_reset.restype, L.psa_mapper_counts_reset.argtypes = i32, [vp]
     L.psa_mapper_counts_device.restype, L.psa_mapper_counts_device.argtypes = vp, [vp]
     L.psa_mapper_launch_count.restype, L.psa_mapper_launch_count.argtypes = u64, [vp]
+    L.psa_mapper_profile_enable.restype, L.psa_mapper_profile_enable.argtypes = i32, [vp, i32]
+    L.psa_mapper_profile_read.restype = i32
+    L.psa_mapper_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     L.psa_comm_unique_id.restype, L.psa_comm_unique_id.argtypes = i32, [vp]
     L.psa_comm_create.restype, L.psa_comm_create.argtypes = i32, [vp, i32, i32, i32, C.POINTER(vp)]
     L.psa_comm_destroy.restype, L.psa_comm_destroy.argtypes = None, [vp]
@@ -417,6 +421,15 @@ class Mapper:
 
     def launch_count(self):
         return int(lib().psa_mapper_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        _check(lib().psa_mapper_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """-> (summed k_map device ms, k_map launches) since the last read."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().psa_mapper_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -1,0 +1,246 @@
+"""GPU parity: the CUDA path through the C ABI (libpsa_b200.so) against the oracle, read by
+read, bit-exact on (aligned?, flag, sorted transcript set, coverage) and on eq_id.
+
+Covers the reference's own pins for the path (validate_dbg (b), test_alignment known answers,
+test/small.fq properties -- ref src/build_index.rs:300-367, :429-441) and every branch of
+map_read the reference never tests (left extension, re-seed, >2 mismatches per unitig, N,
+short reads), at k = 20 / 24 / 64 and read lengths 60 / 91 / 150 / 1100."""
+import importlib
+
+import numpy as np
+import pytest
+
+import cases
+import orc
+import util
+
+pytestmark = pytest.mark.gpu
+
+pkg = importlib.import_module("rust-pseudoaligner_b200")
+host = importlib.import_module("rust-pseudoaligner_b200.host")
+
+_PA = {}
+
+
+@pytest.fixture(scope="module")
+def pa_for(orc_index_for):
+    def get(k):
+        if k not in _PA:
+            _PA[k] = pkg.Pseudoaligner(orc_index_for(k).flat(), device=0)
+        return _PA[k]
+    yield get
+    for p in _PA.values():
+        p.close()
+    _PA.clear()
+
+
+def _oracle(ix, reads):
+    words, off, lens = orc.pack_reads(reads)
+    hits, tx, counts, ev = ix.map_batch(words, off, lens, counts=True)
+    return hits, tx, counts, ev
+
+
+def _assert_same(reads, got_hits, got_tx, want_hits, want_tx):
+    a, b = orc.hits_to_tuples(got_hits, got_tx), orc.hits_to_tuples(want_hits, want_tx)
+    bad = [i for i in range(len(reads)) if a[i] != b[i]]
+    assert not bad, "%d/%d reads differ; first: read %d %r\n gpu    %r\n oracle %r" % (
+        len(bad), len(reads), bad[0], reads[bad[0]], a[bad[0]], b[bad[0]])
+    assert np.array_equal(got_hits["eq_id"], want_hits["eq_id"])
+    # deterministic layout: members back to back in read order
+    assert np.array_equal(got_hits["tx_off"], want_hits["tx_off"])
+    assert np.array_equal(got_tx, want_tx)
+
+
+def test_known_answers(pa_for):
+    """test_alignment, ref src/build_index.rs:423-451."""
+    pa = pa_for(20)
+    ex1 = "GGCTGTCAACCAGTCCATAGGCAGGGCCATCAGGCACCAAAGGGATTCTGCCAGCATAGT"
+    snp = "GGCTGTCAACCAGTCCATAGGCGGGGCCATCAGGCACCAAAGGGATTCTGCCAGCATAGT"
+    assert pa.map_read(ex1) == ([1, 30], 60)
+    assert pa.map_read(snp) == ([1, 30], 60)
+    assert pa.map_read("ACGT") is None
+    assert pa.map_reads([ex1, snp, "ACGT", ""]) == [([1, 30], 60), ([1, 30], 60), None, None]
+
+
+@pytest.mark.parametrize("k", [20, 64])
+def test_validate_dbg_part_b(pa_for, orc_index_for, fixture_fasta, k):
+    """ref src/build_index.rs:300-367: every transcript maps to itself with coverage == len;
+    singleton class == [i]; otherwise i is a member.  (Reads up to 16 355 bases.)"""
+    pa = pa_for(k)
+    seqs = [s for s in fixture_fasta[1]]
+    res = pa.map_reads(seqs)
+    for i, (s, r) in enumerate(zip(seqs, res)):
+        if len(s) < k:
+            assert r is None
+            continue
+        eq, cov = r
+        assert cov == len(s), i
+        assert i in eq
+    hits, tx, _, _ = _oracle(orc_index_for(k), [s.decode() for s in seqs])
+    want = [None if not a else (list(e), c) for a, _, e, c in orc.hits_to_tuples(hits, tx)]
+    assert res == want
+
+
+@pytest.mark.parametrize("k,length", [(20, 150), (20, 60), (24, 91), (64, 150)])
+def test_parity_fixture_read_sets(pa_for, orc_index_for, fixture_fasta, k, length):
+    ix, pa = orc_index_for(k), pa_for(k)
+    rng = np.random.default_rng(31 * k + length)
+    for name, reads in cases.read_sets(rng, fixture_fasta[1], length, k, scale=2.0).items():
+        want_hits, want_tx, _, _ = _oracle(ix, reads)
+        got_hits, got_tx = pa.mapper.map_ascii(reads)
+        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+
+
+def test_small_fq(pa_for, orc_index_for, fixture_fastq):
+    """test/small.fq (BASELINE config 1): no golden output upstream; oracle parity + properties."""
+    ix, pa = orc_index_for(20), pa_for(20)
+    reads = [s for _, s in fixture_fastq]
+    want_hits, want_tx, _, _ = _oracle(ix, reads)
+    got_hits, got_tx = pa.mapper.map_ascii(reads)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    exact = [i for i, (rid, _) in enumerate(fixture_fastq) if "_err" not in rid and not rid.endswith("_rev")]
+    assert len(exact) == 3103 and (got_hits["coverage"][exact] == 60).all()
+
+
+def test_long_reads_and_chunking(orc_index_for, fixture_fasta):
+    """Reads of 1100 bases (35 words: the compare loop's second round), a pipeline cut into
+    many small chunks, packed input, counts across calls."""
+    ix = orc_index_for(20)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0, chunk_reads=257)
+    rng = np.random.default_rng(5)
+    reads = util.sample_reads(rng, fixture_fasta[1], 1500, 1100, p_sub=0.004, mix=(0.8, 0.15, 0.05))
+    reads += util.sample_reads(rng, fixture_fasta[1], 700, 150, p_sub=0.01) + ["", "ACGT"]
+    rng.shuffle(reads)
+    want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
+    got_hits, got_tx = pa.mapper.map_ascii(reads)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    assert np.array_equal(pa.mapper.counts(), want_counts)
+    # packed input, same answer; counts accumulate
+    words, off, lens = orc.pack_reads(reads)
+    got_hits, got_tx = pa.mapper.map_packed(words, off, lens)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    assert np.array_equal(pa.mapper.counts(), 2 * want_counts)
+    pa.mapper.counts_reset()
+    assert int(pa.mapper.counts().sum()) == 0
+    # hits only (no member buffer)
+    h2, t2 = pa.mapper.map_ascii(reads, want_tx=False)
+    assert np.array_equal(h2["n_tx"], want_hits["n_tx"]) and np.array_equal(h2["coverage"], want_hits["coverage"])
+    assert len(t2) == 0
+    pa.close()
+
+
+def test_device_batch_and_events(orc_index_for, fixture_fasta):
+    """Device-resident fixed-stride ASCII batch (the bench's kernel-only arm), async entry,
+    and the event counters against the oracle's (hash-independent ones must agree exactly)."""
+    ix = orc_index_for(20)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0)
+    rng = np.random.default_rng(8)
+    L, n = 150, 6000
+    reads = util.sample_reads(rng, fixture_fasta[1], n, L, p_sub=0.01)
+    data = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    want_hits, want_tx, want_counts, want_ev = _oracle(ix, reads)
+    b = pkg.DeviceBatch(pkg.pseudoaligner.READS_ASCII, data, n, stride=L, fixed_len=L, tx_cap=64 * n)
+    pa.mapper.map_device(b)
+    got_hits, got_tx = b.download()
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    pa.mapper.counts_reset()
+    pa.mapper.map_device_async(b)
+    pa.mapper.sync()
+    got_hits, got_tx = b.download()
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    assert np.array_equal(pa.mapper.counts(), want_counts)
+    ev = pa.mapper.map_device_events(b)
+    for key_gpu, key_orc in (("reads", "reads"), ("read_bases", "read_bases"), ("kmer_lookups", "kmer_lookups"),
+                             ("node_visits", "node_visits"), ("bases_compared", "bases_compared"),
+                             ("edge_jumps", "edge_jumps"), ("out_members", "out_members"), ("aligned", "aligned")):
+        assert ev[key_gpu] == want_ev[key_orc], (key_gpu, ev, want_ev)
+    assert ev["verifications"] >= want_ev["dict_hits"] and ev["mphf_levels"] >= ev["kmer_lookups"]
+    # packed device batch
+    words, off, lens = orc.pack_reads(reads)
+    b2 = pkg.DeviceBatch(pkg.pseudoaligner.READS_PACKED, words, n, read_off=off, read_len=lens, tx_cap=64 * n)
+    pa.mapper.map_device(b2)
+    got_hits, got_tx = b2.download()
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    # tx_buf too small is reported, not truncated silently, and does not disturb the counts
+    before = pa.mapper.counts()
+    b3 = pkg.DeviceBatch(pkg.pseudoaligner.READS_ASCII, data, n, stride=L, fixed_len=L, tx_cap=10)
+    with pytest.raises(pkg.PsaError) as e:
+        pa.mapper.map_device(b3)
+    assert e.value.code == -4 and b3.ob.tx_used == len(want_tx)
+    assert np.array_equal(pa.mapper.counts(), before)
+    for x in (b, b2, b3):
+        x.free()
+    pa.close()
+
+
+def test_lookup_every_kmer(pa_for, orc_index_for):
+    """dbg_index.get + verification over the whole dictionary and over absent k-mers."""
+    ix, pa = orc_index_for(20), pa_for(20)
+    nt = util.node_kmer_table(ix.flat())
+    found, node, off = pa.index.lookup(nt["lo"] << np.uint64(24))
+    assert found.all() and np.array_equal(node, nt["node"]) and np.array_equal(off, nt["off"])
+    rng = np.random.default_rng(2)
+    q = rng.integers(0, 1 << 40, 200000).astype(np.uint64)
+    absent = ~np.isin(q, nt["lo"])
+    found, _, _ = pa.index.lookup(q << np.uint64(24))
+    assert not found[absent].any() and found[~absent].all()
+    info = pa.index.info()
+    assert info["n_kmers"] == len(nt["lo"]) and info["fp_bits"] >= 16 and 10 <= info["mphf_levels"] <= 48
+
+
+@pytest.mark.parametrize("k", [5, 19, 31, 32, 33, 47, 64])
+def test_parity_random_transcriptomes(k):
+    """Small adversarial transcriptomes (shared exons, repeats, poly-A self loop, tandem cycle)
+    built by the PRODUCT host builder, every k-mer width edge, several MPHF gammas."""
+    rng = np.random.default_rng(200 + k)
+    seqs = util.random_transcriptome(rng, n_genes=8, k=k)
+    codes, off = host.encode_transcripts(seqs)
+    flat, _ = host.build_graph(codes, off, k)
+    ix = orc.OrcIndex.from_flat(flat)
+    for gamma in (0.0, 1.0, 4.0):
+        pa = pkg.Pseudoaligner(flat, device=0, gamma=gamma)
+        reads = []
+        for length in (k, k + 1, 2 * k + 3, 150, 1100):
+            for name, rs in cases.read_sets(rng, seqs, length, k, scale=0.1).items():
+                reads += [r[:length] if name != "edge" else r for r in rs]
+        want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
+        got_hits, got_tx = pa.mapper.map_ascii(reads)
+        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+        assert np.array_equal(pa.mapper.counts(), want_counts)
+        pa.close()
+
+
+def test_allowed_mismatches_and_invalid_index(orc_index_for, fixture_fasta):
+    ix = orc_index_for(20)
+    flat = ix.flat()
+    bad = dict(flat)
+    bad["node_exts"] = flat["node_exts"].copy()
+    # claim a right extension that no node provides -> "missing link"
+    i = int(np.flatnonzero((flat["node_exts"] & 0x0F) == 0)[0])
+    bad["node_exts"][i] |= 1
+    with pytest.raises(pkg.PsaError) as e:
+        pkg.Index(bad)
+    assert e.value.code == -5
+    dup = dict(flat)
+    dup["node_eq"] = flat["node_eq"].copy()
+    dup["node_eq"][0] = len(flat["eq_offsets"]) + 5
+    with pytest.raises(pkg.PsaError):
+        pkg.Index(dup)
+
+
+def test_synthetic_scale_checksum():
+    """A mid-size synthetic GENCODE-shaped index (BASELINE config 3 in miniature) built by the
+    product builder: 200 k reads, full per-read equality and equal per-class counts."""
+    t = host.Transcriptome.synth(2, 300)
+    flat, stats = host.build_graph(t.codes(), t.tx_off(), 24)
+    n, L = 200000, 150
+    data = t.reads(3, 0, n, L)
+    pa = pkg.Pseudoaligner(flat, device=0, chunk_reads=1 << 16)
+    got_hits, got_tx = pa.mapper.map_ascii_fixed(data, n, L)
+    ox = orc.OrcIndex.from_flat(flat)
+    reads = [data[i * L:(i + 1) * L].tobytes().decode() for i in range(n)]
+    want_hits, want_tx, want_counts, _ = _oracle(ox, reads)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    assert np.array_equal(pa.mapper.counts(), want_counts)
+    assert int((got_hits["flags"] & 1).sum()) > 0.9 * n
+    pa.close()
