@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--reads-per-step", type=int, default=1 << 23)
     ap.add_argument("--distinct-batches", type=int, default=3, help="distinct read batches rotated over the steps")
     ap.add_argument("--gamma", type=float, default=0.0)
+    ap.add_argument("--group-width", type=int, default=0, help="lanes per read (8/16/32; 0 = library default)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -299,6 +300,8 @@ def main():
     index = pkg.Index(flat, device=local_rank, gamma=a.gamma)
     info = index.info()
     mapper = pkg.Mapper(index)
+    if a.group_width:
+        mapper.set_group_width(a.group_width)
     stream = torch.cuda.ExternalStream(mapper.stream(), device=local_rank)
 
     R, L, G = a.reads_per_step, a.read_len, max(1, a.distinct_batches)

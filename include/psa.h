@@ -158,6 +158,9 @@ int psa_mapper_create(psa_index*, uint64_t chunk_reads, psa_mapper** out);
 void psa_mapper_destroy(psa_mapper*);
 /* ref src/pseudoaligner.rs:382: DEFAULT_ALLOWED_MISMATCHES; map_read_with_mismatch (:361) takes any. */
 int psa_mapper_set_allowed_mismatches(psa_mapper*, uint32_t allowed);
+/* Tuning: lanes of a warp that cooperate on one read (8, 16 or 32; default 8, or the
+ * PSA_GROUP_WIDTH environment variable).  Results do not depend on it. */
+int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
 
 /* Pseudoalign a batch.  For every read i: hits[i] and its members in tx_buf are exactly
  * what `index.map_read(&DnaString::from_dna_string(seq_i))` returns (ref :381-384, :449-462).

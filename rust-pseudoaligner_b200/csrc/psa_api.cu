@@ -438,7 +438,8 @@ struct psa_mapper {
     DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, running;
     DevBuf words, woff, nwords, dst_off, scan_tmp, meta;
     uint64_t novel_cap = 0;
-    uint32_t spill_cap = 1024;
+    uint32_t spill_cap = 256;
+    uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     int grid = 0;
     Slot slot[2];
     uint64_t launches = 0;
@@ -450,15 +451,45 @@ struct psa_mapper {
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
 
+template <bool EV>
+static void launch_map(psa_mapper* m, int grid, cudaStream_t st, const MapParams& p) {
+    const DevIndex& d = m->ix->d;
+#define PSA_LAUNCH(KW, G) k_map<KW, EV, G><<<grid, 256, 0, st>>>(d, p)
+    if (m->ix->kw == 1) {
+        if (m->group == 8) PSA_LAUNCH(1, 8);
+        else if (m->group == 16) PSA_LAUNCH(1, 16);
+        else PSA_LAUNCH(1, 32);
+    } else {
+        if (m->group == 8) PSA_LAUNCH(2, 8);
+        else if (m->group == 16) PSA_LAUNCH(2, 16);
+        else PSA_LAUNCH(2, 32);
+    }
+#undef PSA_LAUNCH
+}
+
 static int mapper_grid(psa_mapper* m) {
     if (m->grid) return m->grid;
     int sms = 148, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->ix->device);
-    if (m->ix->kw == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<1, false>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<2, false>, 256, 0);
+#define PSA_OCC(KW, G) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_map<KW, false, G>, 256, 0)
+    if (m->ix->kw == 1) {
+        if (m->group == 8) PSA_OCC(1, 8);
+        else if (m->group == 16) PSA_OCC(1, 16);
+        else PSA_OCC(1, 32);
+    } else {
+        if (m->group == 8) PSA_OCC(2, 8);
+        else if (m->group == 16) PSA_OCC(2, 16);
+        else PSA_OCC(2, 32);
+    }
+#undef PSA_OCC
     if (per_sm < 1) per_sm = 1;
     m->grid = sms * per_sm;
     return m->grid;
+}
+
+static int mapper_alloc_spill(psa_mapper* m) {
+    const int grid = mapper_grid(m);
+    return m->spill.ensure((size_t)grid * (256 / m->group) * m->spill_cap * sizeof(uint4));
 }
 
 extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper** out) {
@@ -494,8 +525,11 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     cudaMemset(m->counts.p, 0, nc * 8);
     cudaMemset(m->events.p, 0, 12 * 8);
-    const int grid = mapper_grid(m);
-    if ((rc = m->spill.ensure((size_t)grid * 8 * m->spill_cap * sizeof(uint2)))) {
+    if (const char* e = getenv("PSA_GROUP_WIDTH")) {
+        int g = atoi(e);
+        if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
+    }
+    if ((rc = mapper_alloc_spill(m))) {
         psa_mapper_destroy(m);
         return rc;
     }
@@ -531,6 +565,14 @@ extern "C" int psa_mapper_set_allowed_mismatches(psa_mapper* m, uint32_t allowed
     if (!m) return fail(PSA_ERR_ARG, "null argument");
     m->allowed = allowed;
     return PSA_OK;
+}
+extern "C" int psa_mapper_set_group_width(psa_mapper* m, uint32_t lanes) {
+    if (!m || (lanes != 8 && lanes != 16 && lanes != 32)) return fail(PSA_ERR_ARG, "group width must be 8, 16 or 32");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaStreamSynchronize(m->st));
+    m->group = lanes;
+    m->grid = 0;
+    return mapper_alloc_spill(m);
 }
 extern "C" void* psa_mapper_stream(psa_mapper* m) { return m ? (void*)m->st : nullptr; }
 extern "C" void* psa_mapper_counts_device(psa_mapper* m) { return m ? m->counts.p : nullptr; }
@@ -587,9 +629,13 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             rv.wstride = ((uint64_t)r->fixed_len + 31) / 32;
             if ((rc = m->words.ensure(n * rv.wstride * 8 + 16))) return rc;
         }
-        k_pack_ascii<<<std::min<uint64_t>(nblocks(n * 32, 256), 148 * 64), 256, 0, st>>>(
-            (const uint8_t*)r->data, r->read_off, r->stride, r->read_len, r->fixed_len, rv.woff, rv.wstride, n,
-            m->words.as<uint64_t>());
+        if (!r->read_len && !r->read_off)
+            k_pack_ascii_fixed<<<(unsigned)std::min<uint64_t>(nblocks(n * rv.wstride, 256), 148 * 32), 256, 0, st>>>(
+                (const uint8_t*)r->data, r->stride, r->fixed_len, n, m->words.as<uint64_t>());
+        else
+            k_pack_ascii<<<(unsigned)std::min<uint64_t>(nblocks(n * 32, 256), 148 * 64), 256, 0, st>>>(
+                (const uint8_t*)r->data, r->read_off, r->stride, r->read_len, r->fixed_len, rv.woff, rv.wstride, n,
+                m->words.as<uint64_t>());
         m->launches++;
         CU(cudaGetLastError());
         rv.words = m->words.as<uint64_t>();
@@ -608,7 +654,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     p.novel = b.tx_buf ? m->novel.as<uint32_t>() : nullptr;
     p.novel_cap = m->novel_cap;
     p.novel_cursor = m->novel_cursor.as<unsigned long long>();
-    p.spill = m->spill.as<uint2>();
+    p.spill = m->spill.as<uint4>();
     p.spill_cap = m->spill_cap;
     p.allowed_mismatches = m->allowed;
     p.status = m->status.as<uint32_t>();
@@ -621,8 +667,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             CU(cudaEventCreate(&e1));
             CU(cudaEventRecord(e0, st));
         }
-        if (ix->kw == 1) k_map<1, EV><<<grid, 256, 0, st>>>(ix->d, p);
-        else k_map<2, EV><<<grid, 256, 0, st>>>(ix->d, p);
+        launch_map<EV>(m, grid, st, p);
         if (m->profiling) {
             CU(cudaEventRecord(e1, st));
             m->prof_events.emplace_back(e0, e1);

@@ -148,7 +148,7 @@ template <>
 struct KmerOps<1> {
     template <class L>
     static PSA_HD Kmer<1> get(L ld, uint64_t pos, uint32_t k) { return get_kmer1(ld, pos, k); }
-    static PSA_HD uint64_t hash(Kmer<1> x) { return x.lo; }
+    static PSA_HD uint64_t fold(Kmer<1> x) { return x.lo; }
     // successor / predecessor k-mers for the edge tables (debruijn Kmer::extend_right/left)
     static PSA_HD Kmer<1> extend_right(Kmer<1> x, uint32_t b, uint32_t k) {
         Kmer<1> r;
@@ -166,7 +166,7 @@ template <>
 struct KmerOps<2> {
     template <class L>
     static PSA_HD Kmer<2> get(L ld, uint64_t pos, uint32_t k) { return get_kmer2(ld, pos, k); }
-    static PSA_HD uint64_t hash(Kmer<2> x) { return x.lo ^ mix64(x.hi + 0x9e3779b97f4a7c15ULL); }
+    static PSA_HD uint64_t fold(Kmer<2> x) { return x.lo ^ mix64(x.hi + 0x9e3779b97f4a7c15ULL); }
     static PSA_HD Kmer<2> extend_right(Kmer<2> x, uint32_t b, uint32_t k) {
         Kmer<2> r;
         r.hi = (x.hi << 2) | (x.lo >> 62);
@@ -198,7 +198,7 @@ struct NodeRec {        // 64 bytes, 64-byte aligned: one L2 line per node visit
     uint32_t eq;        // equivalence-class id (*node.data())
     uint32_t class_len; // |eq_classes[eq]|
     uint32_t exts;      // debruijn Exts byte
-    uint32_t pad[2];
+    uint64_t class_off; // eq_classes[eq] starts at eq_mem[class_off]
     uint32_t succ[4];   // node reached by right extension b (kNone if the ext bit is clear)
     uint32_t pred[4];   // node reached by left extension b
 };
@@ -224,14 +224,23 @@ struct DevIndex {
     Mphf mphf;
 };
 
-PSA_HD uint64_t level_hash(uint64_t hk, uint32_t lvl) {
-    return mix64(hk + (uint64_t)(lvl + 1) * 0x9E3779B97F4A7C15ULL);
+// Two 64-bit hashes per k-mer, computed once; level l probes h1 + l*h2 (double hashing, as
+// in BBHash), the fingerprint is the top bits of h2.
+struct KeyHash {
+    uint64_t h1, h2;
+};
+PSA_HD KeyHash make_hash(uint64_t folded) {
+    KeyHash kh;
+    kh.h1 = mix64(folded + 0x9E3779B97F4A7C15ULL);
+    kh.h2 = mix64(folded ^ 0xD6E8FEB86659FD93ULL) | 1ULL;
+    return kh;
 }
-PSA_HD uint64_t fp_hash(uint64_t hk) { return mix64(hk ^ 0xD6E8FEB86659FD93ULL); }
+PSA_HD uint64_t level_hash(KeyHash kh, uint32_t lvl) { return kh.h1 + (uint64_t)lvl * kh.h2; }
+PSA_HD uint64_t fp_of(KeyHash kh, uint32_t fp_bits) { return kh.h2 >> (64 - fp_bits); }
 
-// position of a key at a level: (block within level, bit 0..191 within block)
+// position of a key at a level: (block within level, bit 0..191 within block); nblk < 2^32
 PSA_HD void level_pos(uint64_t h, uint64_t nblk, uint64_t& blk, uint32_t& bit) {
-    blk = mulhi64(h, nblk);
+    blk = ((h >> 32) * (uint64_t)(uint32_t)nblk) >> 32;
     bit = (uint32_t)(((h & 0xffffffffULL) * kBlockBits) >> 32);
 }
 
@@ -241,9 +250,10 @@ struct Block {
 PSA_HD Block load_block(const uint64_t* blocks, uint64_t b) {
     Block r;
 #ifdef __CUDA_ARCH__
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(blocks + 4 * b);
-    ulonglong2 a = __ldg(p), c = __ldg(p + 1);
-    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = c.x; r.w[3] = c.y;
+    // one 32-byte sector per probe: header + 3 bit-vector words (LDG.E.256)
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+        : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3])
+        : "l"(blocks + 4 * b));
 #else
     for (int i = 0; i < 4; i++) r.w[i] = blocks[4 * b + i];
 #endif
@@ -269,7 +279,7 @@ struct ProbeStats {  // sequential-equivalent event counts of one dictionary pro
 };
 
 // Mphf::try_hash: cascade of bit-vectors; the first level whose bit is set gives the slot.
-PSA_HD bool mphf_lookup(const Mphf& m, uint64_t hk, uint64_t& slot, uint32_t& levels) {
+PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& levels) {
     levels = 0;
     for (uint32_t lvl = 0; lvl < m.n_levels; lvl++) {
         uint64_t blk;
@@ -285,9 +295,9 @@ PSA_HD bool mphf_lookup(const Mphf& m, uint64_t hk, uint64_t& slot, uint32_t& le
     return false;
 }
 
-PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, uint64_t hk) {
+PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, KeyHash hk) {
     uint64_t v = (uint64_t)node | ((uint64_t)off << ix.node_bits);
-    if (ix.fp_bits) v |= (fp_hash(hk) >> (64 - ix.fp_bits)) << (ix.node_bits + ix.off_bits);
+    if (ix.fp_bits) v |= fp_of(hk, ix.fp_bits) << (ix.node_bits + ix.off_bits);
     return v;
 }
 
@@ -296,7 +306,7 @@ PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, uint
 // fetch cannot change the outcome of the reference's `read_kmer == ref_kmer` test.
 template <int KW>
 PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st) {
-    uint64_t hk = KmerOps<KW>::hash(key);
+    KeyHash hk = make_hash(KmerOps<KW>::fold(key));
     uint64_t slot;
     uint32_t levels;
     bool in = mphf_lookup(ix.mphf, hk, slot, levels);
@@ -308,7 +318,7 @@ PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t&
     uint64_t v = ix.values[slot];
 #endif
     if (ix.fp_bits) {
-        if ((v >> (ix.node_bits + ix.off_bits)) != (fp_hash(hk) >> (64 - ix.fp_bits))) return false;
+        if ((v >> (ix.node_bits + ix.off_bits)) != fp_of(hk, ix.fp_bits)) return false;
     }
     uint32_t n = (uint32_t)(v & ((1ULL << ix.node_bits) - 1));
     uint32_t o = (uint32_t)((v >> ix.node_bits) & ((1ULL << ix.off_bits) - 1));
@@ -378,6 +388,7 @@ PSA_HD uint32_t nth_mismatch(uint64_t m, uint32_t j) {
 struct NodeView {
     uint64_t start;
     uint32_t len, eq, class_len, exts;
+    uint64_t class_off;
 };
 
 #ifdef __CUDACC__

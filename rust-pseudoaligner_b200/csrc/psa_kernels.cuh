@@ -32,12 +32,13 @@ __global__ void k_node_basics(NodeRec* nodes, uint64_t n_nodes, const uint64_t* 
     r.len = node_len[i];
     r.eq = node_eq[i];
     r.exts = node_exts[i];
-    r.pad[0] = r.pad[1] = 0;
     if (r.eq >= n_eq || r.len < k) {
         atomicOr(err, 1u);
         r.class_len = 0;
+        r.class_off = 0;
     } else {
-        r.class_len = (uint32_t)(eq_off[r.eq + 1] - eq_off[r.eq]);
+        r.class_off = eq_off[r.eq];
+        r.class_len = (uint32_t)(eq_off[r.eq + 1] - r.class_off);
     }
     for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
     nodes[i] = r;
@@ -64,13 +65,13 @@ __global__ void k_enumerate_keys(const uint64_t* seq, const uint64_t* node_start
 }
 
 template <int KW>
-__device__ __forceinline__ uint64_t key_hash_at(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t i) {
+__device__ __forceinline__ KeyHash key_hash_at(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t i) {
     if (KW == 1) {
         Kmer<1> x; x.lo = key_lo[i];
-        return KmerOps<1>::hash(x);
+        return make_hash(KmerOps<1>::fold(x));
     } else {
         Kmer<2> x; x.lo = key_lo[i]; x.hi = key_hi[i];
-        return KmerOps<2>::hash(x);
+        return make_hash(KmerOps<2>::fold(x));
     }
 }
 
@@ -143,7 +144,7 @@ __global__ void k_fill_values(const uint64_t* key_lo, const uint64_t* key_hi, co
                               DevIndex ix, uint64_t* values, uint32_t* err) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t hk = key_hash_at<KW>(key_lo, key_hi, i);
+    KeyHash hk = key_hash_at<KW>(key_lo, key_hi, i);
     uint64_t slot; uint32_t levels;
     if (!mphf_lookup(ix.mphf, hk, slot, levels) || slot >= ix.n_kmers) {
         atomicOr(err, 2u);
@@ -195,7 +196,7 @@ __global__ void k_lookup(DevIndex ix, const uint64_t* kmer_words, uint64_t n, ui
 }
 
 // ---------------------------------------------------------------------------------------------
-// reads: ASCII -> DnaString words.  One thread per output word.
+// reads: ASCII -> DnaString words (DnaString::from_dna_string, ref src/pseudoaligner.rs:449-450)
 // ---------------------------------------------------------------------------------------------
 struct ReadsView {          // device-resident batch
     const uint64_t* words;  // packed
@@ -211,6 +212,45 @@ __global__ void k_words_per_read(const uint32_t* len, uint64_t n, uint64_t* nw) 
     if (i < n) nw[i] = ((uint64_t)len[i] + 31) >> 5;
 }
 
+// 4 ASCII bytes (first base in the low byte) -> 8 bits of 2-bit codes, first base in bits 7:6.
+// A/a 0, C/c 1, G/g 2, T/t 3, any other byte 0 -- bytewise SIMD, no table.
+__device__ __forceinline__ uint32_t codes4(uint32_t w) {
+    uint32_t u = w & 0xDFDFDFDFu;  // fold case
+    uint32_t valid = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
+                     __vcmpeq4(u, 0x54545454u);
+    uint32_t x = (w >> 1) & 0x03030303u;  // A0 C1 G3 T2
+    x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3
+    x &= valid;
+    return (x * 0x40100401u) >> 24;       // gather the four 2-bit fields (no carries between them)
+}
+// nb (1..32) bases at s -> one DnaString word.  Reads only the aligned 32-bit words that hold
+// at least one of the nb bytes.
+__device__ __forceinline__ uint64_t pack32(const uint8_t* s, uint32_t nb) {
+    const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(s - mis);
+    const uint32_t nwords = (mis + nb + 3) >> 2;  // <= 9
+    uint32_t w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = (uint32_t)i < nwords ? __ldg(a + i) : 0u;
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t c = __funnelshift_r(w[i], w[i + 1], 8 * mis);
+        v |= (uint64_t)codes4(c) << (56 - 8 * i);
+    }
+    if (nb < 32) v &= ~0ULL << (64 - 2 * nb);
+    return v;
+}
+// fixed read length: one thread per output word
+__global__ void k_pack_ascii_fixed(const uint8_t* ascii, uint64_t astride, uint32_t len, uint64_t n, uint64_t* words) {
+    const uint32_t nw = (len + 31) >> 5;
+    const uint64_t total = n * nw;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += gridDim.x * (uint64_t)blockDim.x) {
+        uint64_t r = i / nw;
+        uint32_t j = (uint32_t)(i - r * nw);
+        words[i] = pack32(ascii + r * astride + 32 * j, min(32u, len - 32 * j));
+    }
+}
 // ragged: warp per read, lane-strided over its words
 __global__ void k_pack_ascii(const uint8_t* ascii, const uint64_t* aoff, uint64_t astride, const uint32_t* len,
                              uint32_t fixed_len, const uint64_t* woff, uint64_t wstride, uint64_t n,
@@ -223,17 +263,12 @@ __global__ void k_pack_ascii(const uint8_t* ascii, const uint64_t* aoff, uint64_
         uint32_t L = len ? len[r] : fixed_len;
         uint64_t* w = words + (woff ? woff[r] : r * wstride);
         uint32_t nw = (L + 31) >> 5;
-        for (uint32_t j = lane; j < nw; j += 32) {
-            uint32_t nb = min(32u, L - 32 * j);
-            uint64_t v = 0;
-            for (uint32_t t = 0; t < nb; t++) v |= (uint64_t)base_code(s[32 * j + t]) << (62 - 2 * t);
-            w[j] = v;
-        }
+        for (uint32_t j = lane; j < nw; j += 32) w[j] = pack32(s + 32 * j, min(32u, L - 32 * j));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// the map kernel
+// the map kernel: G lanes (a power-of-two slice of a warp) cooperate on one read
 // ---------------------------------------------------------------------------------------------
 struct HitRec {  // == psa_hit
     uint32_t coverage, n_tx;
@@ -249,8 +284,8 @@ struct MapParams {
     uint32_t* novel;              // members of sets that are no index class
     unsigned long long novel_cap;
     unsigned long long* novel_cursor;
-    uint2* spill;                 // per-warp overflow of the visited-class list
-    uint32_t spill_cap;           // entries per warp
+    uint4* spill;                 // per-group overflow of the visited-class list
+    uint32_t spill_cap;           // entries per group
     uint32_t allowed_mismatches;
     uint32_t* status;             // bit0: novel buffer overflow, bit1: spill overflow
     unsigned long long* events;   // psa_events layout, or nullptr
@@ -260,27 +295,49 @@ struct LaneEvents {
     uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
 };
 
-template <int KW, bool EV>
+// the lanes of one read: a G-wide slice of the warp (cooperative-groups tile, hand-rolled)
+template <int G>
+struct Grp {
+    uint32_t lane, shift;
+    unsigned mask;
+    static constexpr unsigned kLow = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+    __device__ __forceinline__ Grp() {
+        uint32_t wl = threadIdx.x & 31;
+        lane = wl & (G - 1);
+        shift = wl & ~(uint32_t)(G - 1);
+        mask = kLow << shift;
+    }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> shift) & kLow; }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, G); }
+    template <class T> __device__ __forceinline__ T shfl_up(T v, int d) const { return __shfl_up_sync(mask, v, d, G); }
+    template <class T> __device__ __forceinline__ T shfl_xor(T v, int d) const { return __shfl_xor_sync(mask, v, d, G); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+template <int KW, bool EV, int G>
 struct WarpCtx {
     const DevIndex& ix;
     PLoad rd;
+    Grp<G> g;
     uint32_t lane;
     uint32_t k;
-    // visited distinct classes: entry j < 32 lives in lane j, further ones in `spill`
+    // visited distinct classes: entry j < G lives in lane j, further ones in `spill`
     uint32_t my_eq, my_len, n_list;
-    uint2* spill;
+    uint64_t my_off;
+    uint4* spill;
     uint32_t spill_cap;
     bool spill_overflow;
     LaneEvents ev;
 
-    __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint2* spill_, uint32_t cap)
-        : ix(ix_), rd{read_words}, lane(threadIdx.x & 31), k(ix_.k), my_eq(kNone), my_len(0), n_list(0),
+    __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint4* spill_, uint32_t cap)
+        : ix(ix_), rd{read_words}, g(), lane(g.lane), k(ix_.k), my_eq(kNone), my_len(0), n_list(0), my_off(0),
           spill(spill_), spill_cap(cap), spill_overflow(false), ev{} {}
 
     __device__ __forceinline__ uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
 
     // find_kmer_match, ref src/pseudoaligner.rs:91-114.  The first position is probed by the
-    // whole warp on one address (the common case: it hits); after a miss, 32 stride-3
+    // whole group on one address (the common case: it hits); after a miss, G stride-3
     // positions are probed at once, one per lane, and the lowest hitting lane wins -- the
     // same answer as the sequential scan.
     __device__ __forceinline__ bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
@@ -293,7 +350,7 @@ struct WarpCtx {
             if (hit) return true;
         }
         const uint64_t start = kmer_pos;
-        for (uint64_t cur = start + kSeedStride; cur <= last; cur += 32 * kSeedStride) {
+        for (uint64_t cur = start + kSeedStride; cur <= last; cur += G * kSeedStride) {
             uint64_t p = cur + (uint64_t)kSeedStride * lane;
             bool h = false;
             uint32_t n = 0, o = 0;
@@ -302,14 +359,14 @@ struct WarpCtx {
                 Kmer<KW> key = KmerOps<KW>::get(rd, p, k);
                 h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
             }
-            unsigned b = __ballot_sync(kFull, h);
-            int j = b ? (__ffs(b) - 1) : 32;
+            unsigned b = g.ballot(h);
+            int j = b ? (__ffs(b) - 1) : G;
             if (EV && p <= last && (int)lane <= j) {
                 ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified;
             }
             if (b) {
-                node = __shfl_sync(kFull, n, j);
-                off = __shfl_sync(kFull, o, j);
+                node = g.shfl(n, j);
+                off = g.shfl(o, j);
                 kmer_pos = cur + (uint64_t)kSeedStride * j;
                 return true;
             }
@@ -321,13 +378,14 @@ struct WarpCtx {
     __device__ __forceinline__ NodeView node(uint32_t id) const {
         const NodeRec* r = ix.nodes + id;
         uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
-        uint2 b = __ldg(reinterpret_cast<const uint2*>(r) + 2);
+        uint4 b = __ldg(reinterpret_cast<const uint4*>(r) + 1);
         NodeView v;
         v.start = (uint64_t)a.x | ((uint64_t)a.y << 32);
         v.len = a.z;
         v.eq = a.w;
         v.class_len = b.x;
         v.exts = b.y;
+        v.class_off = (uint64_t)b.z | ((uint64_t)b.w << 32);
         return v;
     }
     __device__ __forceinline__ uint32_t succ(uint32_t id, uint32_t b) {
@@ -345,31 +403,34 @@ struct WarpCtx {
         uint32_t c = (uint32_t)popc64(mask);
         uint32_t incl = c;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(kFull, incl, d);
+        for (int d = 1; d < G; d <<= 1) {
+            uint32_t t = g.shfl_up(incl, d);
             if ((int)lane >= d) incl += t;
         }
-        unsigned b = __ballot_sync(kFull, snp + incl > A);
+        unsigned b = g.ballot(snp + incl > A);
         if (b) {
             int j = __ffs(b) - 1;
             uint32_t t = 0;
             if ((int)lane == j) t = nth_mismatch(mask, A + 1 - (snp + incl - c));
-            t_out = __shfl_sync(kFull, t, j);
+            t_out = g.shfl(t, j);
             j_out = j;
             return true;
         }
-        snp += __shfl_sync(kFull, incl, 31);
+        snp += g.shfl(incl, G - 1);
         return false;
     }
 
-    // ref src/pseudoaligner.rs:234-255
-    __device__ __forceinline__ uint64_t cmp_fwd(uint64_t rpos, uint64_t spos, uint64_t m, uint32_t A, bool& premature) {
+    // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward)
+    template <bool FWD>
+    __device__ __forceinline__ uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
-        for (uint64_t base = 0; base < m; base += 1024) {
+        for (uint64_t base = 0; base < m; base += 32 * G) {
             uint64_t my = base + 32 * lane;
             uint32_t n = my < m ? (uint32_t)min((uint64_t)32, m - my) : 0;
-            uint64_t mask = n ? mismatch_fwd(rd, rpos + my, GLoad{ix.seq}, spos + my, n) : 0;
-            if (!__any_sync(kFull, mask != 0)) continue;
+            uint64_t mask = 0;
+            if (n) mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
+                              : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
+            if (!g.any(mask != 0)) continue;
             uint32_t t; int j;
             if (locate_break(mask, snp, A, t, j)) {
                 premature = true;
@@ -381,54 +442,39 @@ struct WarpCtx {
         if (EV && lane == 0) ev.bases += (uint32_t)m;
         return m;
     }
-    // ref src/pseudoaligner.rs:149-170
-    __device__ __forceinline__ uint64_t cmp_bwd(uint64_t rend, uint64_t send, uint64_t m, uint32_t A, bool& premature) {
-        uint32_t snp = 0;
-        for (uint64_t base = 0; base < m; base += 1024) {
-            uint64_t my = base + 32 * lane;
-            uint32_t n = my < m ? (uint32_t)min((uint64_t)32, m - my) : 0;
-            uint64_t mask = n ? mismatch_bwd(rd, rend - my, GLoad{ix.seq}, send - my, n) : 0;
-            if (!__any_sync(kFull, mask != 0)) continue;
-            uint32_t t; int j;
-            if (locate_break(mask, snp, A, t, j)) {
-                premature = true;
-                uint64_t matched = base + 32 * (uint64_t)j + t;
-                if (EV && lane == 0) ev.bases += (uint32_t)matched + 1;
-                return matched;
-            }
-        }
-        if (EV && lane == 0) ev.bases += (uint32_t)m;
-        return m;
-    }
+    __device__ __forceinline__ uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    __device__ __forceinline__ uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
 
     // nodes.push (ref :199, :219), keeping only what nodes_to_eq_class needs: the distinct
     // classes of the visited nodes (intersection is idempotent, ref :352-355).
     __device__ __forceinline__ void push(uint32_t /*node_id*/, const NodeView& nv) {
         if (EV && lane == 0) ev.visits++;
-        if (__ballot_sync(kFull, lane < n_list && my_eq == nv.eq)) return;
-        if (n_list < 32) {
-            if (lane == n_list) { my_eq = nv.eq; my_len = nv.class_len; }
+        if (g.ballot(lane < n_list && my_eq == nv.eq)) return;
+        if (n_list < G) {
+            if (lane == n_list) { my_eq = nv.eq; my_len = nv.class_len; my_off = nv.class_off; }
             n_list++;
             return;
         }
-        // rare: more than 32 distinct classes
-        uint32_t ns = n_list - 32;
+        // rare: more than G distinct classes
+        uint32_t ns = n_list - G;
         bool dup = false;
-        for (uint32_t j = lane; j < ns; j += 32) dup |= (spill[j].x == nv.eq);
-        if (__any_sync(kFull, dup)) return;
+        for (uint32_t j = lane; j < ns; j += G) dup |= (spill[j].x == nv.eq);
+        if (g.any(dup)) return;
         if (ns >= spill_cap) { spill_overflow = true; return; }
-        if (lane == 0) spill[ns] = make_uint2(nv.eq, nv.class_len);
-        __syncwarp();
+        if (lane == 0) spill[ns] = make_uint4(nv.eq, nv.class_len, (uint32_t)nv.class_off, (uint32_t)(nv.class_off >> 32));
+        g.sync();
         n_list++;
     }
-    __device__ __forceinline__ void entry(uint32_t j, uint32_t& eq, uint32_t& len) const {  // uniform j
-        if (j < 32) {
-            eq = __shfl_sync(kFull, my_eq, j);
-            len = __shfl_sync(kFull, my_len, j);
+    __device__ __forceinline__ void entry(uint32_t j, uint32_t& eq, uint32_t& len, uint64_t& off) const {  // uniform j
+        if (j < G) {
+            eq = g.shfl(my_eq, j);
+            len = g.shfl(my_len, j);
+            off = g.shfl(my_off, j);
         } else {
-            uint2 e = spill[j - 32];
+            uint4 e = spill[j - G];
             eq = e.x;
             len = e.y;
+            off = (uint64_t)e.z | ((uint64_t)e.w << 32);
         }
     }
 };
@@ -437,42 +483,42 @@ struct WarpCtx {
 // The result is the ascending intersection (intersect keeps v1's order, :406); the sort by
 // length (:331-334) only picks the smallest class as v1.  Lane l tests member c0+l of the
 // smallest class against every other class by binary search (the reference's own search,
-// :404).  pass == 0 counts, pass == 1 writes the survivors to out[].
-template <int KW, bool EV>
-__device__ __forceinline__ uint32_t intersect_pass(WarpCtx<KW, EV>& w, uint32_t s_eq, uint32_t s_len, uint32_t* out) {
+// :404).  out == nullptr counts, otherwise the survivors are written to out[].
+template <int KW, bool EV, int G>
+__device__ __forceinline__ uint32_t intersect_pass(WarpCtx<KW, EV, G>& w, uint32_t s_eq, uint32_t s_len, uint64_t s_off,
+                                                   uint32_t* out) {
     const DevIndex& ix = w.ix;
-    const uint64_t s_off = __ldg(ix.eq_off + s_eq);
     uint32_t count = 0;
-    for (uint32_t c0 = 0; c0 < s_len; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < s_len; c0 += G) {
         bool alive = c0 + w.lane < s_len;
         uint32_t mem = alive ? __ldg(ix.eq_mem + s_off + c0 + w.lane) : 0;
         for (uint32_t j = 0; j < w.n_list; j++) {
             uint32_t e, l;
-            w.entry(j, e, l);
+            uint64_t o;
+            w.entry(j, e, l, o);
             if (e == s_eq) continue;
-            const uint64_t o = __ldg(ix.eq_off + e);
             if (alive) alive = contains_sorted(ix.eq_mem + o, (uint64_t)l, mem);
-            if (!__any_sync(kFull, alive)) break;
+            if (!w.g.any(alive)) break;
         }
-        unsigned b = __ballot_sync(kFull, alive);
+        unsigned b = w.g.ballot(alive);
         if (out && alive) out[count + __popc(b & ((1u << w.lane) - 1))] = mem;
         count += __popc(b);
     }
     return count;
 }
 
-template <int KW, bool EV>
+template <int KW, bool EV, int G>
 __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix, const __grid_constant__ MapParams p) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = (gridDim.x * (uint64_t)blockDim.x) >> 5;
+    const uint64_t gid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) / G;
+    const uint64_t ngroups = (gridDim.x * (uint64_t)blockDim.x) / G;
     LaneEvents tot{};
     uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
 
-    for (uint64_t r = warp; r < p.reads.n; r += nwarps) {
+    for (uint64_t r = gid; r < p.reads.n; r += ngroups) {
         const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-        WarpCtx<KW, EV> w(ix, p.reads.words + wo, p.spill + warp * p.spill_cap, p.spill_cap);
+        WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, p.spill + gid * p.spill_cap, p.spill_cap);
+        const uint32_t lane = w.lane;
         uint32_t coverage = 0;
         bool some = map_read_nodes(w, ix.k, (uint64_t)L, p.allowed_mismatches, coverage);
 
@@ -482,37 +528,41 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
         if (some) {
             // smallest class first (ref :331-334); ties broken by id so every lane agrees
             uint64_t key = lane < w.n_list ? (((uint64_t)w.my_len << 32) | w.my_eq) : ~0ULL;
-            for (uint32_t j = 32 + lane; j < w.n_list; j += 32) {
-                uint2 e = w.spill[j - 32];
+            uint64_t koff = w.my_off;
+            for (uint32_t j = G + lane; j < w.n_list; j += G) {
+                uint4 e = w.spill[j - G];
                 uint64_t kk = ((uint64_t)e.y << 32) | e.x;
-                key = kk < key ? kk : key;
+                if (kk < key) { key = kk; koff = (uint64_t)e.z | ((uint64_t)e.w << 32); }
             }
 #pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                uint64_t o = __shfl_xor_sync(kFull, key, d);
-                key = o < key ? o : key;
+            for (int d = G / 2; d; d >>= 1) {
+                uint64_t o = w.g.shfl_xor(key, d);
+                uint64_t oo = w.g.shfl_xor(koff, d);
+                if (o < key) { key = o; koff = oo; }
             }
             const uint32_t s_len = (uint32_t)(key >> 32), s_eq = (uint32_t)key;
+            const uint64_t s_off = koff;
             uint32_t count, eq_id;
             if (w.n_list == 1) {
                 count = s_len;
                 eq_id = s_eq;
                 if (EV && lane == 0) w.ev.members += s_len;
             } else {
-                count = intersect_pass(w, s_eq, s_len, nullptr);
+                count = intersect_pass(w, s_eq, s_len, s_off, nullptr);
                 // the result equals a visited class iff that class has `count` members
                 uint32_t cand = (lane < w.n_list && w.my_len == count) ? w.my_eq : kNone;
-                for (uint32_t j = 32 + lane; j < w.n_list; j += 32) {
-                    uint2 e = w.spill[j - 32];
+                for (uint32_t j = G + lane; j < w.n_list; j += G) {
+                    uint4 e = w.spill[j - G];
                     if (e.y == count && e.x < cand) cand = e.x;
                 }
 #pragma unroll
-                for (int d = 16; d; d >>= 1) cand = min(cand, __shfl_xor_sync(kFull, cand, d));
+                for (int d = G / 2; d; d >>= 1) cand = min(cand, w.g.shfl_xor(cand, d));
                 eq_id = cand;
                 if (EV) {
                     for (uint32_t j = 0; j < w.n_list; j++) {
                         uint32_t e, l;
-                        w.entry(j, e, l);
+                        uint64_t o;
+                        w.entry(j, e, l, o);
                         if (lane == 0) w.ev.members += l;
                     }
                 }
@@ -522,15 +572,23 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
             h.eq_id = eq_id;
             h.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
             if (eq_id != kNone) {
-                h.tx_off = __ldg(ix.eq_off + eq_id);  // members are read from the index by k_expand
+                // members are read from the index by k_expand; eq_id is one of the visited classes
+                uint64_t off = (lane < w.n_list && w.my_eq == eq_id) ? w.my_off : 0;
+                for (uint32_t j = G + lane; j < w.n_list; j += G) {
+                    uint4 e = w.spill[j - G];
+                    if (e.x == eq_id) off = (uint64_t)e.z | ((uint64_t)e.w << 32);
+                }
+#pragma unroll
+                for (int d = G / 2; d; d >>= 1) off |= w.g.shfl_xor(off, d);
+                h.tx_off = off;
                 count_slot = eq_id;
             } else {
                 count_slot = ix.n_eq;
                 if (count && p.novel) {
                     unsigned long long base = 0;
                     if (lane == 0) base = atomicAdd(p.novel_cursor, (unsigned long long)count);
-                    base = __shfl_sync(kFull, base, 0);
-                    if (base + count <= p.novel_cap) intersect_pass(w, s_eq, s_len, p.novel + base);
+                    base = w.g.shfl(base, 0);
+                    if (base + count <= p.novel_cap) intersect_pass(w, s_eq, s_len, s_off, p.novel + base);
                     else if (lane == 0) atomicOr(p.status, 1u);
                     h.tx_off = base;
                 }
@@ -541,21 +599,18 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
             p.hits[r] = h;
             if (p.counts) atomicAdd(p.counts + count_slot, 1ULL);
         }
-        if (EV) {
+        if (EV && lane == 0) {
             tot.lookups += w.ev.lookups; tot.levels += w.ev.levels; tot.hits += w.ev.hits; tot.verifs += w.ev.verifs;
             tot.visits += w.ev.visits; tot.bases += w.ev.bases; tot.jumps += w.ev.jumps; tot.members += w.ev.members;
-            if (lane == 0) { ev_reads++; ev_bases += L; ev_out += h.n_tx; ev_aligned += some; }
+            ev_reads++; ev_bases += L; ev_out += h.n_tx; ev_aligned += some;
         }
     }
-    if (EV && p.events) {
+    if (EV && p.events && (threadIdx.x & (G - 1)) == 0) {
         unsigned long long v[12] = {ev_reads, ev_bases, tot.lookups, tot.levels, tot.hits, tot.verifs,
                                     tot.visits, tot.bases, tot.jumps, tot.members, ev_out, ev_aligned};
 #pragma unroll
-        for (int i = 0; i < 12; i++) {
-            unsigned long long x = v[i];
-            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
-            if (lane == 0 && x) atomicAdd(p.events + i, x);
-        }
+        for (int i = 0; i < 12; i++)
+            if (v[i]) atomicAdd(p.events + i, v[i]);
     }
 }
 

@@ -70,7 +70,7 @@ class _Events(C.Structure):
 EXPORTS = (
     "psa_strerror", "psa_last_error", "psa_abi_version",
     "psa_index_create", "psa_index_destroy", "psa_index_get_info", "psa_index_lookup",
-    "psa_mapper_create", "psa_mapper_destroy", "psa_mapper_set_allowed_mismatches",
+    "psa_mapper_create", "psa_mapper_destroy", "psa_mapper_set_allowed_mismatches", "psa_mapper_set_group_width",
     "psa_mapper_map", "psa_mapper_map_async", "psa_mapper_sync", "psa_mapper_stream",
     "psa_mapper_map_read", "psa_mapper_counts_get", "psa_mapper_counts_reset",
     "psa_mapper_counts_device", "psa_mapper_map_events", "psa_mapper_launch_count",
@@ -111,6 +111,7 @@ def lib():
     L.psa_mapper_destroy.restype, L.psa_mapper_destroy.argtypes = None, [vp]
     L.psa_mapper_set_allowed_mismatches.restype = i32
     L.psa_mapper_set_allowed_mismatches.argtypes = [vp, u32]
+    L.psa_mapper_set_group_width.restype, L.psa_mapper_set_group_width.argtypes = i32, [vp, u32]
     for name in ("psa_mapper_map", "psa_mapper_map_async"):
         f = getattr(L, name)
         f.restype, f.argtypes = i32, [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch)]
@@ -330,6 +331,9 @@ class Mapper:
 
     def set_allowed_mismatches(self, a):
         _check(lib().psa_mapper_set_allowed_mismatches(self.h, int(a)))
+
+    def set_group_width(self, lanes):
+        _check(lib().psa_mapper_set_group_width(self.h, int(lanes)))
 
     # ---- host batches -------------------------------------------------------------------
     def _map_host(self, fmt, data, n, read_off, read_len, stride, fixed_len, want_tx=True, tx_cap=None,

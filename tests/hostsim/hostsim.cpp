@@ -61,9 +61,9 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     D.n_kmers = n_kmers;
 
     // cascade
-    std::vector<uint64_t> rem_h(n_kmers);
-    for (uint64_t i = 0; i < n_kmers; i++) rem_h[i] = KmerOps<KW>::hash(keys[i]);
-    std::vector<uint64_t> cur = rem_h;
+    std::vector<KeyHash> rem_h(n_kmers);
+    for (uint64_t i = 0; i < n_kmers; i++) rem_h[i] = make_hash(KmerOps<KW>::fold(keys[i]));
+    std::vector<KeyHash> cur = rem_h;
     uint64_t total_blk = 0;
     uint32_t lvl = 0;
     while (!cur.empty()) {
@@ -71,7 +71,7 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
         uint64_t nblk = std::max<uint64_t>(1, (uint64_t)(gamma * (double)cur.size() / kBlockBits) + 1);
         ix->blocks.resize(4 * (total_blk + nblk), 0);
         std::vector<uint64_t> coll(4 * nblk, 0);
-        for (uint64_t h : cur) {
+        for (KeyHash h : cur) {
             uint64_t blk; uint32_t bit;
             level_pos(level_hash(h, lvl), nblk, blk, bit);
             uint64_t& w = ix->blocks[4 * (total_blk + blk) + 1 + (bit >> 6)];
@@ -79,8 +79,8 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
             if (w & m) coll[4 * blk + 1 + (bit >> 6)] |= m;
             w |= m;
         }
-        std::vector<uint64_t> next;
-        for (uint64_t h : cur) {
+        std::vector<KeyHash> next;
+        for (KeyHash h : cur) {
             uint64_t blk; uint32_t bit;
             level_pos(level_hash(h, lvl), nblk, blk, bit);
             if ((coll[4 * blk + 1 + (bit >> 6)] >> (bit & 63)) & 1) next.push_back(h);
@@ -116,7 +116,7 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
         NodeRec& r = ix->nodes[i];
         r.start = node_start[i]; r.len = node_len[i]; r.eq = node_eq[i]; r.exts = node_exts[i];
         r.class_len = (uint32_t)(ix->eq_off[r.eq + 1] - ix->eq_off[r.eq]);
-        r.pad[0] = r.pad[1] = 0;
+        r.class_off = ix->eq_off[r.eq];
         for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
     }
     D.nodes = ix->nodes.data();
@@ -161,7 +161,7 @@ struct SerialWarp {
     uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
     NodeView node(uint32_t id) const {
         const NodeRec& r = ix.nodes[id];
-        return NodeView{r.start, r.len, r.eq, r.class_len, r.exts};
+        return NodeView{r.start, r.len, r.eq, r.class_len, r.exts, r.class_off};
     }
     uint32_t succ(uint32_t id, uint32_t b) { return ix.nodes[id].succ[b]; }
     uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes[id].pred[b]; }

@@ -87,8 +87,11 @@ def test_parity_fixture_read_sets(pa_for, orc_index_for, fixture_fasta, k, lengt
     rng = np.random.default_rng(31 * k + length)
     for name, reads in cases.read_sets(rng, fixture_fasta[1], length, k, scale=2.0).items():
         want_hits, want_tx, _, _ = _oracle(ix, reads)
-        got_hits, got_tx = pa.mapper.map_ascii(reads)
-        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+        for lanes in (8, 16, 32):          # lanes per read: a tuning knob that must not change results
+            pa.mapper.set_group_width(lanes)
+            got_hits, got_tx = pa.mapper.map_ascii(reads)
+            _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    pa.mapper.set_group_width(8)
 
 
 def test_small_fq(pa_for, orc_index_for, fixture_fastq):
@@ -197,8 +200,9 @@ def test_parity_random_transcriptomes(k):
     codes, off = host.encode_transcripts(seqs)
     flat, _ = host.build_graph(codes, off, k)
     ix = orc.OrcIndex.from_flat(flat)
-    for gamma in (0.0, 1.0, 4.0):
+    for gamma, lanes in ((0.0, 8), (1.0, 16), (4.0, 32)):
         pa = pkg.Pseudoaligner(flat, device=0, gamma=gamma)
+        pa.mapper.set_group_width(lanes)
         reads = []
         for length in (k, k + 1, 2 * k + 3, 150, 1100):
             for name, rs in cases.read_sets(rng, seqs, length, k, scale=0.1).items():
