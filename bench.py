@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument("--reads-per-step", type=int, default=1 << 23)
     ap.add_argument("--distinct-batches", type=int, default=3, help="distinct read batches rotated over the steps")
     ap.add_argument("--gamma", type=float, default=0.0)
-    ap.add_argument("--group-width", type=int, default=0, help="lanes per read (8/16/32; 0 = library default)")
+    ap.add_argument("--group-width", type=int, default=0, help="lanes per read in the cooperative kernel (8/16/32; 0 = library default)")
+    ap.add_argument("--fast-probes", type=int, default=-1, help="seed positions one thread tries before handing the read over (0: no thread-per-read kernel; -1: library default)")
+    ap.add_argument("--fast-max-small", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -302,6 +304,8 @@ def main():
     mapper = pkg.Mapper(index)
     if a.group_width:
         mapper.set_group_width(a.group_width)
+    if a.fast_probes >= 0:
+        mapper.set_fast_path(a.fast_probes, a.fast_max_small)
     stream = torch.cuda.ExternalStream(mapper.stream(), device=local_rank)
 
     R, L, G = a.reads_per_step, a.read_len, max(1, a.distinct_batches)
@@ -318,7 +322,8 @@ def main():
     setup_s = time.time() - t_setup
 
     # events of one batch (untimed): the algorithmic work the roofline is computed from
-    ev = mapper.map_device_events(dev_batches[0])
+    ev_split = mapper.map_device_events(dev_batches[0], split=True)
+    ev = {key: ev_split[0][key] + ev_split[1][key] for key in ev_split[0]}
     mapper.counts_reset()
     a_bytes_per_read = algorithmic_bytes(ev, a.k) / ev["reads"]
 
@@ -353,7 +358,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    map_ms, map_launches = mapper.profile_read()
+    prof = mapper.profile_read()
     mapper.profile_enable(False)
     launches = mapper.launch_count() - launches0
     counts = mapper.counts()
@@ -397,13 +402,31 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    map_ms_per_launch = map_ms / max(1, map_launches)
-    achieved = a_bytes_per_read * R / (map_ms_per_launch / 1e3) / 1e9 if map_launches else 0.0
+    # the map step is two kernels: k_map_thread (one thread per read) and k_map (cooperative, the reads
+    # k_map_thread handed over); each is charged the algorithmic bytes of the reads it completed
+    kernels = {}
+    for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1])):
+        k_ms, k_n = prof[name]
+        if not k_n:
+            continue
+        per_launch_ms = k_ms / k_n
+        a_bytes = algorithmic_bytes(part, a.k)          # of one batch = one launch
+        kernels[name] = {"ms_per_launch": per_launch_ms, "share_of_step": k_ms / ms if ms else None,
+                         "reads_per_launch": part["reads"], "algorithmic_bytes_per_launch": a_bytes,
+                         "achieved_gbs": a_bytes / (per_launch_ms / 1e3) / 1e9}
+    dom = max(kernels, key=lambda kname: kernels[kname]["ms_per_launch"])
+    achieved = kernels[dom]["achieved_gbs"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("%s:%s" % (a.workload, dom))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_map", "kernel_ms_per_launch": map_ms_per_launch,
-                "kernel_share_of_step": map_ms / ms if ms else None,
-                "algorithmic_bytes_per_read": a_bytes_per_read, "peak_source": peak_src,
-                "note": "latency-bound dependent random gathers: see DESIGN.md for the sector-rate view"}
+                "traffic": traffic, "kernel": dom, "kernel_ms_per_launch": kernels[dom]["ms_per_launch"],
+                "kernel_share_of_step": kernels[dom]["share_of_step"], "kernels": kernels,
+                "algorithmic_bytes_per_read": a_bytes_per_read,
+                "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_launch"] for v in kernels.values()) / 1e3) / 1e9,
+                "peak_source": peak_src,
+                "note": "dependent random 32-byte-sector gathers: see DESIGN.md for the sector-rate view"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

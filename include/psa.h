@@ -161,6 +161,13 @@ int psa_mapper_set_allowed_mismatches(psa_mapper*, uint32_t allowed);
 /* Tuning: lanes of a warp that cooperate on one read (8, 16 or 32; default 8, or the
  * PSA_GROUP_WIDTH environment variable).  Results do not depend on it. */
 int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
+/* Tuning: the map step is two kernels.  k_map_thread gives every read one thread and hands a
+ * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
+ * needs more than max_probes positions, it visits more than 4 distinct classes, or its
+ * smallest class has more than max_small members.  max_probes = 0 sends every read to the
+ * cooperative kernel.  Defaults 3 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
+ * not depend on it. */
+int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
 
 /* Pseudoalign a batch.  For every read i: hits[i] and its members in tx_buf are exactly
  * what `index.map_read(&DnaString::from_dna_string(seq_i))` returns (ref :381-384, :449-462).
@@ -204,17 +211,19 @@ typedef struct psa_events {
     uint64_t out_members;    /* sum |eq_class|                                               */
     uint64_t aligned;
 } psa_events;
-/* Same as psa_mapper_map on a device batch, with event counting compiled in (slower). */
+/* Same as psa_mapper_map on a device batch, with event counting compiled in (slower).
+ * out[0]: the reads completed by k_map_thread, out[1]: the reads completed by k_map. */
 int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results,
-                          psa_events* out);
+                          psa_events out[2]);
 
 /* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
 uint64_t psa_mapper_launch_count(const psa_mapper*);
-/* Device timing of the map kernel alone: when enabled, every k_map launch is bracketed by
+/* Device timing of the two map kernels alone: when enabled, every launch is bracketed by
  * CUDA events on the mapper's stream.  psa_mapper_profile_read synchronises, returns the
- * summed kernel time and launch count since the last read, and resets them. */
+ * summed kernel time and launch count since the last read ([0] k_map_thread, [1] k_map), and
+ * resets them. */
 int psa_mapper_profile_enable(psa_mapper*, int on);
-int psa_mapper_profile_read(psa_mapper*, double* map_kernel_ms, uint64_t* map_launches);
+int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[2], uint64_t map_launches[2]);
 
 /* ---- multi-GPU: reads shard across ranks, one all-reduce of the per-class counts ---- */
 typedef struct psa_comm psa_comm;

@@ -435,21 +435,31 @@ struct psa_mapper {
     uint64_t chunk_reads = 0;
     uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
     cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
-    DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, running;
-    DevBuf words, woff, nwords, dst_off, scan_tmp, meta;
+    DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, pool, running;
+    DevBuf words, woff, nwords, dst_off, scan_tmp, meta, deferred;
     uint64_t novel_cap = 0;
-    uint32_t spill_cap = 256;
+    uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
+    uint64_t pool_cap = 1ull << 18;   // entries (uint4) of the shared overflow pool; grows on demand
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
+    uint32_t fast_probes = 3;   // 0: every read goes to the cooperative kernel
+    uint32_t fast_max_small = 32;
     int grid = 0;
     Slot slot[2];
     uint64_t launches = 0;
     // map-kernel timing (psa_mapper_profile_*)
     bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];  // [0] k_map_thread, [1] k_map
     // pending async call
     psa_result_batch* pending = nullptr;
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
+
+template <bool EV>
+static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p) {
+    const unsigned grid = nblocks(p.reads.n, kThreadBlock);
+    if (m->ix->kw == 1) k_map_thread<1, EV><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    else k_map_thread<2, EV><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+}
 
 template <bool EV>
 static void launch_map(psa_mapper* m, int grid, cudaStream_t st, const MapParams& p) {
@@ -489,7 +499,9 @@ static int mapper_grid(psa_mapper* m) {
 
 static int mapper_alloc_spill(psa_mapper* m) {
     const int grid = mapper_grid(m);
-    return m->spill.ensure((size_t)grid * (256 / m->group) * m->spill_cap * sizeof(uint4));
+    int rc = m->spill.ensure((size_t)grid * (256 / m->group) * m->spill_cap * sizeof(uint4));
+    if (rc) return rc;
+    return m->pool.ensure(m->pool_cap * sizeof(uint4));
 }
 
 extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper** out) {
@@ -518,17 +530,19 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     const uint64_t nc = ix->d.n_eq + 2;
     if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
-        (rc = m->novel_cursor.ensure(8)) || (rc = m->events.ensure(12 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
+        (rc = m->novel_cursor.ensure(32)) || (rc = m->events.ensure(24 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
         (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16))) {
         psa_mapper_destroy(m);
         return rc;
     }
     cudaMemset(m->counts.p, 0, nc * 8);
-    cudaMemset(m->events.p, 0, 12 * 8);
+    cudaMemset(m->events.p, 0, 24 * 8);
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
     }
+    if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
     if ((rc = mapper_alloc_spill(m))) {
         psa_mapper_destroy(m);
         return rc;
@@ -543,8 +557,8 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st) cudaStreamSynchronize(m->st);
     if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
     if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
-    DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill,
-                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta};
+    DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
+                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred};
     for (auto b : bufs) b->release();
     for (int s = 0; s < 2; s++) {
         Slot& S = m->slot[s];
@@ -573,6 +587,12 @@ extern "C" int psa_mapper_set_group_width(psa_mapper* m, uint32_t lanes) {
     m->group = lanes;
     m->grid = 0;
     return mapper_alloc_spill(m);
+}
+extern "C" int psa_mapper_set_fast_path(psa_mapper* m, uint32_t max_probes, uint32_t max_small) {
+    if (!m) return fail(PSA_ERR_ARG, "null argument");
+    m->fast_probes = max_probes;
+    m->fast_max_small = max_small;
+    return PSA_OK;
 }
 extern "C" void* psa_mapper_stream(psa_mapper* m) { return m ? (void*)m->st : nullptr; }
 extern "C" void* psa_mapper_counts_device(psa_mapper* m) { return m ? m->counts.p : nullptr; }
@@ -644,7 +664,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 8, st));
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 32, st));  // [0] novel cursor, [1] pool cursor, [2] deferred reads
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -656,24 +676,40 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     p.novel_cursor = m->novel_cursor.as<unsigned long long>();
     p.spill = m->spill.as<uint4>();
     p.spill_cap = m->spill_cap;
+    p.pool = m->pool.as<uint4>();
+    p.pool_cap = m->pool_cap;
+    p.pool_cursor = m->novel_cursor.as<unsigned long long>() + 1;
     p.allowed_mismatches = m->allowed;
     p.status = m->status.as<uint32_t>();
     p.events = EV ? m->events.as<unsigned long long>() : nullptr;
     const int grid = mapper_grid(m);
-    if (n) {
+    auto timed = [&](int which, auto&& launch) -> int {
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (m->profiling) {
             CU(cudaEventCreate(&e0));
             CU(cudaEventCreate(&e1));
             CU(cudaEventRecord(e0, st));
         }
-        launch_map<EV>(m, grid, st, p);
+        launch();
         if (m->profiling) {
             CU(cudaEventRecord(e1, st));
-            m->prof_events.emplace_back(e0, e1);
+            m->prof_events[which].emplace_back(e0, e1);
         }
         m->launches++;
         CU(cudaGetLastError());
+        return PSA_OK;
+    };
+    if (n) {
+        // fast kernel: one thread per read; the reads it gives up go to the cooperative kernel
+        if (m->fast_probes && n < 0xFFFFFFFFull) {
+            if ((rc = m->deferred.ensure(n * 4))) return rc;
+            p.list = m->deferred.as<uint32_t>();
+            p.list_count = m->novel_cursor.as<unsigned long long>() + 2;
+            p.max_probes = m->fast_probes;
+            p.max_small = m->fast_max_small;
+            if ((rc = timed(0, [&]() { launch_map_thread<EV>(m, st, p); }))) return rc;
+        }
+        if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, st, p); }))) return rc;
     }
     // exclusive scan of n_tx (n+1 items: the last one is the batch total), seeded by the running total
     if ((rc = m->dst_off.ensure((n + 2) * 8))) return rc;
@@ -707,10 +743,14 @@ static int check_batch_args(const psa_read_batch* r, const psa_result_batch* o) 
     return PSA_OK;
 }
 
-// grow the novel-set buffer after an overflow
+// grow the novel-set buffer / the class-list pool after an overflow
 static int grow_novel(psa_mapper* m) {
     m->novel_cap *= 4;
     return m->novel.ensure(m->novel_cap * 4);
+}
+static int grow_pool(psa_mapper* m) {
+    m->pool_cap *= 8;
+    return m->pool.ensure(m->pool_cap * sizeof(uint4));
 }
 
 template <bool EV>
@@ -726,10 +766,11 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
         CU(cudaStreamSynchronize(m->st));
         uint32_t status = (uint32_t)m->pin[1];
         o->tx_used = m->pin[0];
-        if (status & 2u) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
-        if (status & 1u) {  // novel-set buffer overflow: undo the counts and retry with a larger buffer
+        if (status & 3u) {  // novel-set buffer / class-list pool overflow: undo the counts, retry with larger buffers
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
-            if ((rc = grow_novel(m))) return rc;
+            CU(cudaStreamSynchronize(m->st));
+            if ((status & 1u) && (rc = grow_novel(m))) return rc;
+            if ((status & 2u) && (rc = grow_pool(m))) return rc;
             continue;
         }
         if (o->tx_buf && o->tx_used > o->tx_cap) {  // the caller resubmits: leave the counts as they were
@@ -739,7 +780,7 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
         }
         return PSA_OK;
     }
-    return fail(PSA_ERR_CAPACITY, "novel-set buffer kept overflowing");
+    return fail(PSA_ERR_CAPACITY, "novel-set buffer / class-list pool kept overflowing");
 }
 
 extern "C" int psa_mapper_map_async(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o) {
@@ -766,11 +807,11 @@ extern "C" int psa_mapper_sync(psa_mapper* m) {
         m->pending = nullptr;
         o->tx_used = m->pin[0];
         uint32_t status = (uint32_t)m->pin[1];
-        if (status & 2u) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
-        if (status & 1u) {
-            int rc = grow_novel(m);
-            if (rc) return rc;
-            return fail(PSA_ERR_CAPACITY, "novel-set buffer overflow (buffer grown: resubmit the batch)");
+        if (status & 3u) {
+            int rc = PSA_OK;
+            if ((status & 1u) && (rc = grow_novel(m))) return rc;
+            if ((status & 2u) && (rc = grow_pool(m))) return rc;
+            return fail(PSA_ERR_CAPACITY, "novel-set buffer / class-list pool overflow (buffers grown: reset the counts and resubmit the batch)");
         }
         if (o->tx_buf && o->tx_used > o->tx_cap) return fail(PSA_ERR_CAPACITY, "tx_buf too small");
     }
@@ -899,10 +940,11 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         CU(cudaStreamSynchronize(m->st_d2h));
         CU(cudaStreamSynchronize(m->st));
         o->tx_used = tx_prev_total;
-        if (spill_overflow) return fail(PSA_ERR_CAPACITY, "a read visited more distinct classes than the spill list holds");
-        if (novel_overflow || stage_overflow) {
+        if (novel_overflow || stage_overflow || spill_overflow) {
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+            CU(cudaStreamSynchronize(m->st));
             if (novel_overflow && m->novel_cap && (rc = grow_novel(m))) return rc;
+            if (spill_overflow && (rc = grow_pool(m))) return rc;
             if (stage_overflow)
                 for (int s = 0; s < 2; s++)
                     if ((rc = m->slot[s].tx.ensure(stage_need * 4 + 4096))) return rc;
@@ -935,10 +977,10 @@ extern "C" int psa_mapper_map_events(psa_mapper* m, const psa_read_batch* r, psa
     if (r->location != PSA_MEM_DEVICE || o->location != PSA_MEM_DEVICE)
         return fail(PSA_ERR_ARG, "psa_mapper_map_events needs device-resident batches");
     CU(cudaSetDevice(m->ix->device));
-    CU(cudaMemsetAsync(m->events.p, 0, 12 * 8, m->st));
+    CU(cudaMemsetAsync(m->events.p, 0, 24 * 8, m->st));
     if ((rc = map_device_sync<true>(m, r, o))) return rc;
     static_assert(sizeof(psa_events) == 12 * 8, "psa_events layout");
-    CU(cudaMemcpy(out, m->events.p, sizeof(psa_events), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, m->events.p, 2 * sizeof(psa_events), cudaMemcpyDeviceToHost));
     return PSA_OK;
 }
 
@@ -974,21 +1016,23 @@ extern "C" int psa_mapper_profile_enable(psa_mapper* m, int on) {
     m->profiling = on != 0;
     return PSA_OK;
 }
-extern "C" int psa_mapper_profile_read(psa_mapper* m, double* map_kernel_ms, uint64_t* map_launches) {
+extern "C" int psa_mapper_profile_read(psa_mapper* m, double map_kernel_ms[2], uint64_t map_launches[2]) {
     if (!m || !map_kernel_ms || !map_launches) return fail(PSA_ERR_ARG, "null argument");
     CU(cudaSetDevice(m->ix->device));
     CU(cudaStreamSynchronize(m->st));
-    double ms = 0;
-    for (auto& pr : m->prof_events) {
-        float t = 0;
-        CU(cudaEventElapsedTime(&t, pr.first, pr.second));
-        ms += t;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+    for (int w = 0; w < 2; w++) {
+        double ms = 0;
+        for (auto& pr : m->prof_events[w]) {
+            float t = 0;
+            CU(cudaEventElapsedTime(&t, pr.first, pr.second));
+            ms += t;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        map_kernel_ms[w] = ms;
+        map_launches[w] = m->prof_events[w].size();
+        m->prof_events[w].clear();
     }
-    *map_kernel_ms = ms;
-    *map_launches = m->prof_events.size();
-    m->prof_events.clear();
     return PSA_OK;
 }
 

@@ -25,6 +25,11 @@
 #else
 #define PSA_HD inline
 #endif
+#if defined(__CUDA_ARCH__)
+#define PSA_UNROLL _Pragma("unroll")
+#else
+#define PSA_UNROLL
+#endif
 
 namespace psa {
 
@@ -383,6 +388,8 @@ PSA_HD uint32_t nth_mismatch(uint64_t m, uint32_t j) {
 //   W::cmp_bwd(rend, send, m, A, premature)      :151-170 -> matched_bases
 //   W::succ(id, b) / W::pred(id, b)              r_edges()[..].0 / l_edges()[..].0
 //   W::push(node)                                nodes.push
+//   W::abort()                                   true once the policy has given the read up (never for
+//                                                the cooperative policies; see ThreadCtx)
 // Returns false for None.  read_coverage is returned through `coverage`.
 // ---------------------------------------------------------------------------------------------
 struct NodeView {
@@ -433,6 +440,7 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
                 prev_kmer_offset = pv.len - kmer_length;                        // :196
                 w.push(prev_node_id, pv);                                       // :199
                 n_pushed++;
+                if (w.abort()) return false;  // policy gave the read up (it is redone by another kernel)
             } else {
                 break;                                                          // :201
             }
@@ -447,6 +455,7 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
             read_coverage += kmer_length;                                       // :216
             w.push(node_id, nv);                                                // :219
             n_pushed++;
+            if (w.abort()) return false;
             uint64_t remaining_read = read_length - kmer_pos;                   // :222
             uint64_t ref_length = nv.len;                                       // :226
             uint64_t ref_offset = kmer_offset + kmer_length;                    // :227
@@ -496,6 +505,269 @@ PSA_HD bool contains_sorted(const T* v, uint64_t n, T x) {
 #else
     return v[lo] == x;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// One thread = one read: the policy of the fast kernel (k_map_thread).  It runs the same
+// map_read_nodes text with every step done serially by the calling thread, and gives a read
+// up ("defer") as soon as it needs something a single thread does badly: a seed scan longer
+// than max_probes positions, more than kThreadClasses distinct classes, or a smallest class
+// with more than max_small members.  Deferred reads are redone from scratch by the
+// cooperative kernel (k_map over the deferred list), so the split never changes a result.
+// ---------------------------------------------------------------------------------------------
+constexpr int kThreadClasses = 4;
+constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
+
+struct HitRec {  // == psa_hit
+    uint32_t coverage, n_tx;
+    uint64_t tx_off;
+    uint32_t eq_id, flags;
+};
+
+struct ThreadEvents {
+    uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
+};
+
+template <int KW, bool EV>
+struct ThreadCtx {
+    const DevIndex& ix;
+    PLoad rd;
+    uint32_t k, max_probes;
+    uint32_t eq[kThreadClasses], len[kThreadClasses];
+    uint64_t off[kThreadClasses];
+    uint32_t n_list;
+    bool defer;
+    ThreadEvents ev;
+
+    PSA_HD ThreadCtx(const DevIndex& ix_, const uint64_t* words, uint32_t max_probes_)
+        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), ev{} {
+    PSA_UNROLL
+        for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; off[j] = 0; }
+    }
+    PSA_HD bool abort() const { return defer; }
+    PSA_HD uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
+
+    // find_kmer_match, ref src/pseudoaligner.rs:91-114, at most max_probes positions
+    PSA_HD bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& o) {
+        if (kmer_pos > last) return false;
+        const uint64_t start = kmer_pos;
+        uint64_t p = start;
+        for (uint32_t probes = 0;; probes++, p += kSeedStride) {
+            if (p > last) {
+                kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
+                return false;
+            }
+            if (probes >= max_probes) {
+                defer = true;
+                kmer_pos = last + 1;  // keeps map_read_nodes out of the forward loop
+                return false;
+            }
+            ProbeStats st;
+            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr);
+            if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
+            if (hit) {
+                kmer_pos = p;
+                return true;
+            }
+        }
+    }
+    PSA_HD NodeView node(uint32_t id) const {
+        NodeView v;
+#ifdef __CUDA_ARCH__
+        const uint4* r = reinterpret_cast<const uint4*>(ix.nodes + id);
+        uint4 a = __ldg(r), b = __ldg(r + 1);
+        v.start = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        v.len = a.z; v.eq = a.w; v.class_len = b.x; v.exts = b.y;
+        v.class_off = (uint64_t)b.z | ((uint64_t)b.w << 32);
+#else
+        const NodeRec& r = ix.nodes[id];
+        v.start = r.start; v.len = r.len; v.eq = r.eq; v.class_len = r.class_len; v.exts = r.exts; v.class_off = r.class_off;
+#endif
+        return v;
+    }
+    PSA_HD uint32_t succ(uint32_t id, uint32_t b) {
+        if (EV) ev.jumps++;
+#ifdef __CUDA_ARCH__
+        return __ldg(&ix.nodes[id].succ[b]);
+#else
+        return ix.nodes[id].succ[b];
+#endif
+    }
+    PSA_HD uint32_t pred(uint32_t id, uint32_t b) {
+        if (EV) ev.jumps++;
+#ifdef __CUDA_ARCH__
+        return __ldg(&ix.nodes[id].pred[b]);
+#else
+        return ix.nodes[id].pred[b];
+#endif
+    }
+    // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step
+    template <bool FWD>
+    PSA_HD uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
+        uint32_t snp = 0;
+        for (uint64_t my = 0; my < m; my += 32) {
+            uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
+            uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
+                                : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
+            uint32_t c = (uint32_t)popc64(mask);
+            if (snp + c > A) {
+                premature = true;
+                uint64_t matched = my + nth_mismatch(mask, A + 1 - snp);
+                if (EV) ev.bases += (uint32_t)matched + 1;
+                return matched;
+            }
+            snp += c;
+        }
+        if (EV) ev.bases += (uint32_t)m;
+        return m;
+    }
+    PSA_HD uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    PSA_HD uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
+    // nodes.push: only the distinct classes matter (intersection is idempotent, ref :352-355)
+    PSA_HD void push(uint32_t /*node_id*/, const NodeView& nv) {
+        if (EV) ev.visits++;
+        bool dup = false;
+    PSA_UNROLL
+        for (int j = 0; j < kThreadClasses; j++) dup |= (j < (int)n_list && eq[j] == nv.eq);
+        if (dup) return;
+        if (n_list >= (uint32_t)kThreadClasses) {
+            defer = true;
+            return;
+        }
+    PSA_UNROLL
+        for (int j = 0; j < kThreadClasses; j++)
+            if (j == (int)n_list) { eq[j] = nv.eq; len[j] = nv.class_len; off[j] = nv.class_off; }
+        n_list++;
+    }
+};
+
+PSA_HD uint32_t ld_mem(const uint32_t* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// nodes_to_eq_class (ref src/pseudoaligner.rs:323-356) by one thread: members of the smallest
+// class (index s) that every other listed class contains, ascending.  Each other class is
+// searched only in the suffix after its previous match -- the reference's own scheme (:399-404).
+// out == nullptr counts.
+template <int KW, bool EV>
+PSA_HD uint32_t thread_intersect(const ThreadCtx<KW, EV>& w, int s, uint32_t* out) {
+    const uint32_t* mem = w.ix.eq_mem;
+    uint32_t cur[kThreadClasses];
+    PSA_UNROLL
+    for (int j = 0; j < kThreadClasses; j++) cur[j] = 0;
+    uint32_t s_len = 0;
+    uint64_t s_off = 0;
+    PSA_UNROLL
+    for (int j = 0; j < kThreadClasses; j++)
+        if (j == s) { s_len = w.len[j]; s_off = w.off[j]; }
+    uint32_t count = 0;
+    for (uint32_t i = 0; i < s_len; i++) {
+        const uint32_t x = ld_mem(mem + s_off + i);
+        bool alive = true;
+    PSA_UNROLL
+        for (int j = 0; j < kThreadClasses; j++) {
+            if (j == s || j >= (int)w.n_list || !alive) continue;
+            const uint32_t* v = mem + w.off[j];
+            uint32_t lo = cur[j], hi = w.len[j];
+            while (lo < hi) {
+                uint32_t mid = lo + ((hi - lo) >> 1);
+                if (ld_mem(v + mid) < x) lo = mid + 1;
+                else hi = mid;
+            }
+            cur[j] = lo;
+            alive = lo < w.len[j] && ld_mem(v + lo) == x;
+        }
+        if (alive) {
+            if (out) out[count] = x;
+            count++;
+        }
+    }
+    return count;
+}
+
+// Result of map_read for one read as the kernels store it (flag = ref :453-462).
+struct ThreadResult {
+    HitRec hit;
+    uint64_t count_slot;  // index into counts[]: eq id, n_eq (no visited class), n_eq + 1 (None)
+    bool deferred;
+    bool novel_overflow;
+};
+
+// map_read + the process_reads flag for one read, by one thread.  NovelAlloc::operator()(count,
+// off_out) returns room for `count` members of a set that is no visited class (nullptr: no
+// room / members not wanted).
+template <int KW, bool EV, class NovelAlloc>
+PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, uint32_t L, uint32_t allowed,
+                                    uint32_t max_probes, uint32_t max_small, NovelAlloc& novel, bool want_members,
+                                    ThreadEvents* ev_out) {
+    ThreadResult res;
+    res.hit.coverage = 0; res.hit.n_tx = 0; res.hit.tx_off = 0; res.hit.eq_id = kNone; res.hit.flags = 0;
+    res.count_slot = ix.n_eq + 1;
+    res.deferred = false;
+    res.novel_overflow = false;
+    ThreadCtx<KW, EV> w(ix, words, max_probes);
+    uint32_t coverage = 0;
+    bool some = map_read_nodes(w, ix.k, (uint64_t)L, allowed, coverage);
+    if (w.defer) {
+        res.deferred = true;
+        return res;
+    }
+    if (some) {
+        // smallest class first (ref :331-334); ties broken by id
+        int s = 0;
+        uint32_t s_len = w.len[0], s_eq = w.eq[0];
+    PSA_UNROLL
+        for (int j = 1; j < kThreadClasses; j++)
+            if (j < (int)w.n_list && (w.len[j] < s_len || (w.len[j] == s_len && w.eq[j] < s_eq))) {
+                s = j; s_len = w.len[j]; s_eq = w.eq[j];
+            }
+        uint32_t count, eq_id;
+        if (w.n_list == 1) {
+            count = s_len;
+            eq_id = s_eq;
+            if (EV) w.ev.members += s_len;
+        } else {
+            if (s_len > max_small) {  // long lists are the cooperative kernel's job
+                res.deferred = true;
+                return res;
+            }
+            count = thread_intersect(w, s, (uint32_t*)nullptr);
+            eq_id = kNone;  // the result equals a visited class iff that class has `count` members
+    PSA_UNROLL
+            for (int j = 0; j < kThreadClasses; j++)
+                if (j < (int)w.n_list && w.len[j] == count && w.eq[j] < eq_id) eq_id = w.eq[j];
+            if (EV)
+                for (int j = 0; j < kThreadClasses; j++)
+                    if (j < (int)w.n_list) w.ev.members += w.len[j];
+        }
+        res.hit.coverage = coverage;
+        res.hit.n_tx = count;
+        res.hit.eq_id = eq_id;
+        res.hit.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
+        if (eq_id != kNone) {
+            uint64_t o = 0;
+    PSA_UNROLL
+            for (int j = 0; j < kThreadClasses; j++)
+                if (j < (int)w.n_list && w.eq[j] == eq_id) o = w.off[j];
+            res.hit.tx_off = o;  // members are read from the index by k_expand
+            res.count_slot = eq_id;
+        } else {
+            res.count_slot = ix.n_eq;
+            if (count && want_members) {
+                uint64_t o = 0;
+                uint32_t* dst = novel(count, o);
+                if (dst) thread_intersect(w, s, dst);
+                else res.novel_overflow = true;
+                res.hit.tx_off = o;
+            }
+        }
+    }
+    if (EV && ev_out) *ev_out = w.ev;
+    return res;
 }
 
 // ASCII -> 2-bit code, DnaString::from_dna_string (call site ref src/pseudoaligner.rs:450):

@@ -270,12 +270,6 @@ __global__ void k_pack_ascii(const uint8_t* ascii, const uint64_t* aoff, uint64_
 // ---------------------------------------------------------------------------------------------
 // the map kernel: G lanes (a power-of-two slice of a warp) cooperate on one read
 // ---------------------------------------------------------------------------------------------
-struct HitRec {  // == psa_hit
-    uint32_t coverage, n_tx;
-    uint64_t tx_off;
-    uint32_t eq_id, flags;
-};
-constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
 struct MapParams {
     ReadsView reads;
@@ -286,9 +280,17 @@ struct MapParams {
     unsigned long long* novel_cursor;
     uint4* spill;                 // per-group overflow of the visited-class list
     uint32_t spill_cap;           // entries per group
+    uint4* pool;                  // bump-allocated overflow of `spill` (very long reads)
+    unsigned long long pool_cap;  // entries
+    unsigned long long* pool_cursor;
     uint32_t allowed_mismatches;
-    uint32_t* status;             // bit0: novel buffer overflow, bit1: spill overflow
-    unsigned long long* events;   // psa_events layout, or nullptr
+    // deferred reads: written by k_map_thread, consumed by k_map (list != nullptr: map list[0..*list_count))
+    uint32_t* list;
+    unsigned long long* list_count;
+    uint32_t max_probes;          // k_map_thread: seed positions one thread tries per search
+    uint32_t max_small;           // k_map_thread: largest smallest-class one thread intersects
+    uint32_t* status;             // bit0: novel buffer overflow, bit1: spill pool overflow
+    unsigned long long* events;   // 2 x psa_events layout ([0] k_map_thread, [1] k_map), or nullptr
 };
 
 struct LaneEvents {
@@ -328,13 +330,21 @@ struct WarpCtx {
     uint4* spill;
     uint32_t spill_cap;
     bool spill_overflow;
+    // a read can push at most read_len+1 nodes, so one pool allocation of that size always suffices
+    uint4* pool;
+    unsigned long long pool_cap;
+    unsigned long long* pool_cursor;
+    uint32_t read_len;
     LaneEvents ev;
 
-    __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint4* spill_, uint32_t cap)
+    __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint32_t read_len_,
+                                       const MapParams& p, uint64_t group_id)
         : ix(ix_), rd{read_words}, g(), lane(g.lane), k(ix_.k), my_eq(kNone), my_len(0), n_list(0), my_off(0),
-          spill(spill_), spill_cap(cap), spill_overflow(false), ev{} {}
+          spill(p.spill + group_id * p.spill_cap), spill_cap(p.spill_cap), spill_overflow(false), pool(p.pool),
+          pool_cap(p.pool_cap), pool_cursor(p.pool_cursor), read_len(read_len_), ev{} {}
 
     __device__ __forceinline__ uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
+    __device__ __forceinline__ bool abort() const { return false; }
 
     // find_kmer_match, ref src/pseudoaligner.rs:91-114.  The first position is probed by the
     // whole group on one address (the common case: it hits); after a miss, G stride-3
@@ -361,8 +371,14 @@ struct WarpCtx {
             }
             unsigned b = g.ballot(h);
             int j = b ? (__ffs(b) - 1) : G;
-            if (EV && p <= last && (int)lane <= j) {
-                ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified;
+            if (EV) {  // sequential-equivalent events: the probes up to and including the first hit
+                const bool counted = p <= last && (int)lane <= j;
+                uint32_t c0 = counted, c1 = counted ? st.levels : 0, c2 = counted ? st.hit : 0, c3 = counted ? st.verified : 0;
+#pragma unroll
+                for (int d = G / 2; d; d >>= 1) {
+                    c0 += g.shfl_xor(c0, d); c1 += g.shfl_xor(c1, d); c2 += g.shfl_xor(c2, d); c3 += g.shfl_xor(c3, d);
+                }
+                if (lane == 0) { ev.lookups += c0; ev.levels += c1; ev.hits += c2; ev.verifs += c3; }
             }
             if (b) {
                 node = g.shfl(n, j);
@@ -460,10 +476,25 @@ struct WarpCtx {
         bool dup = false;
         for (uint32_t j = lane; j < ns; j += G) dup |= (spill[j].x == nv.eq);
         if (g.any(dup)) return;
-        if (ns >= spill_cap) { spill_overflow = true; return; }
+        if (ns >= spill_cap && !grow_spill(ns)) { spill_overflow = true; return; }
         if (lane == 0) spill[ns] = make_uint4(nv.eq, nv.class_len, (uint32_t)nv.class_off, (uint32_t)(nv.class_off >> 32));
         g.sync();
         n_list++;
+    }
+    // the per-group spill is full: move the list to a pool allocation sized for this read
+    __device__ __noinline__ bool grow_spill(uint32_t ns) {
+        const unsigned long long need = (unsigned long long)read_len + 2;
+        if (need <= spill_cap) return false;  // already grown: cannot happen (pushes <= read_len + 1)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(pool_cursor, need);
+        base = g.shfl(base, 0);
+        if (base + need > pool_cap) return false;
+        uint4* dst = pool + base;
+        for (uint32_t j = lane; j < ns; j += G) dst[j] = spill[j];
+        g.sync();
+        spill = dst;
+        spill_cap = (uint32_t)need;
+        return true;
     }
     __device__ __forceinline__ void entry(uint32_t j, uint32_t& eq, uint32_t& len, uint64_t& off) const {  // uniform j
         if (j < G) {
@@ -514,10 +545,12 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     LaneEvents tot{};
     uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
 
-    for (uint64_t r = gid; r < p.reads.n; r += ngroups) {
+    const uint64_t n_todo = p.list ? (uint64_t)*p.list_count : p.reads.n;
+    for (uint64_t it = gid; it < n_todo; it += ngroups) {
+        const uint64_t r = p.list ? (uint64_t)p.list[it] : it;
         const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-        WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, p.spill + gid * p.spill_cap, p.spill_cap);
+        WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
         const uint32_t lane = w.lane;
         uint32_t coverage = 0;
         bool some = map_read_nodes(w, ix.k, (uint64_t)L, p.allowed_mismatches, coverage);
@@ -610,7 +643,74 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
                                     tot.visits, tot.bases, tot.jumps, tot.members, ev_out, ev_aligned};
 #pragma unroll
         for (int i = 0; i < 12; i++)
-            if (v[i]) atomicAdd(p.events + i, v[i]);
+            if (v[i]) atomicAdd(p.events + 12 + i, v[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fast map kernel: one thread per read (psa_core.cuh ThreadCtx / map_read_thread).  Reads
+// it gives up are appended to p.list for k_map.
+// ---------------------------------------------------------------------------------------------
+struct DevNovel {
+    uint32_t* buf;
+    unsigned long long cap;
+    unsigned long long* cursor;
+    __device__ __forceinline__ uint32_t* operator()(uint32_t count, uint64_t& off) {
+        unsigned long long base = atomicAdd(cursor, (unsigned long long)count);
+        off = base;
+        return base + count <= cap ? buf + base : nullptr;
+    }
+};
+
+constexpr int kThreadBlock = 128;
+
+template <int KW, bool EV>
+__global__ void __launch_bounds__(kThreadBlock) k_map_thread(const __grid_constant__ DevIndex ix,
+                                                             const __grid_constant__ MapParams p) {
+    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const bool live = r < p.reads.n;
+    bool defer = false;
+    ThreadEvents ev{};
+    uint32_t L = 0, n_tx = 0, aligned = 0;
+    if (live) {
+        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+        L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+        DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
+        ThreadResult res = map_read_thread<KW, EV>(ix, p.reads.words + wo, L, p.allowed_mismatches, p.max_probes,
+                                                   p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr);
+        defer = res.deferred;
+        if (!defer) {
+            // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
+            uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
+            out[0] = (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32);
+            out[1] = res.hit.tx_off;
+            out[2] = (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32);
+            if (p.counts) atomicAdd(p.counts + res.count_slot, 1ULL);
+            if (res.novel_overflow) atomicOr(p.status, 1u);
+            n_tx = res.hit.n_tx;
+            aligned = res.hit.flags & kFlagAligned;
+        }
+    }
+    // hand the given-up reads to the cooperative kernel (one atomic per warp)
+    const unsigned b = __ballot_sync(kFull, defer);
+    if (b) {
+        const unsigned lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(p.list_count, (unsigned long long)__popc(b));
+        base = __shfl_sync(kFull, base, __ffs(b) - 1);
+        if (defer) p.list[base + __popc(b & ((1u << lane) - 1))] = (uint32_t)r;
+    }
+    if (EV && p.events) {
+        const bool cnt = live && !defer;
+        unsigned long long v[12] = {cnt ? 1ull : 0ull, cnt ? L : 0ull, ev.lookups, ev.levels, ev.hits, ev.verifs,
+                                    ev.visits, ev.bases, ev.jumps, ev.members, n_tx, aligned};
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            unsigned long long x = cnt ? v[i] : 0ull;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+            if ((threadIdx.x & 31) == 0 && x) atomicAdd(p.events + i, x);
+        }
     }
 }
 

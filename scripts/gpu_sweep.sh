@@ -1,17 +1,21 @@
 #!/bin/bash
 # parity tests + a sweep over tuning knobs (kernel-resident arm only)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
 : > gpurun_out/sweep.jsonl
-for g in 8 16 32; do
-  timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --group-width $g $SWEEP_ARGS >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err
+SWEEP=${SWEEP:-0:8 1:8 2:8 3:8 4:8 8:8 3:16 3:32}
+for cfg in $SWEEP; do
+  p=${cfg%%:*}; g=${cfg##*:}
+  timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --fast-probes $p --group-width $g $SWEEP_ARGS >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err
 done
 python - <<'PY'
 import json
 for l in open('gpurun_out/sweep.jsonl'):
     d=json.loads(l); r=d['roofline']
-    print("reads/s %.1fM  ms/step %.2f  k_map ms %.2f share %.2f" % (d['value']/1e6, d['ms_per_step'], r['kernel_ms_per_launch'], r['kernel_share_of_step']))
+    ks=r.get('kernels',{})
+    print("reads/s %.1fM  ms/step %.2f | " % (d['value']/1e6, d['ms_per_step']) +
+          "  ".join("%s %.2f ms (%d reads, %.0f GB/s)" % (k, v['ms_per_launch'], v['reads_per_launch'], v['achieved_gbs']) for k, v in ks.items()))
 PY
 tail -3 gpurun_out/sweep.err

@@ -159,6 +159,7 @@ struct SerialWarp {
         return false;
     }
     uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
+    bool abort() const { return false; }
     NodeView node(uint32_t id) const {
         const NodeRec& r = ix.nodes[id];
         return NodeView{r.start, r.len, r.eq, r.class_len, r.exts, r.class_off};
@@ -256,6 +257,45 @@ uint64_t hs_map_batch(const HsIndex* ix, const uint64_t* words, const uint64_t* 
         if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
         else map_one<2>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
     }
+    memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
+    return tx.size();
+}
+
+// The fast kernel's one-thread-per-read policy (psa_core.cuh ThreadCtx / map_read_thread), with
+// deferred reads redone by the serial stand-in of the cooperative kernel -- the same split the
+// product makes between k_map_thread and k_map.  *n_deferred receives the number of deferrals.
+struct HostNovel {
+    std::vector<uint32_t> buf;
+    uint32_t* operator()(uint32_t count, uint64_t& off) {
+        off = 0;
+        buf.assign(count, 0);
+        return buf.data();
+    }
+};
+
+uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,
+                             const uint32_t* read_len, uint64_t n, uint32_t allowed, uint32_t max_probes,
+                             uint32_t max_small, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap, uint64_t* n_deferred) {
+    std::vector<uint32_t> tx;
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        HostNovel novel;
+        ThreadResult r;
+        if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, words + read_off[i], read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+        else r = map_read_thread<2, false>(ix->d, words + read_off[i], read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+        if (r.deferred) {
+            nd++;
+            if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+            else map_one<2>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+            continue;
+        }
+        HsHit& h = hits[i];
+        h.coverage = r.hit.coverage; h.n_tx = r.hit.n_tx; h.eq_id = r.hit.eq_id; h.flags = r.hit.flags;
+        h.tx_off = tx.size();
+        const uint32_t* src = r.hit.eq_id != kNone ? ix->eq_mem.data() + r.hit.tx_off : novel.buf.data();
+        tx.insert(tx.end(), src, src + r.hit.n_tx);
+    }
+    if (n_deferred) *n_deferred = nd;
     memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
     return tx.size();
 }

@@ -87,11 +87,15 @@ def test_parity_fixture_read_sets(pa_for, orc_index_for, fixture_fasta, k, lengt
     rng = np.random.default_rng(31 * k + length)
     for name, reads in cases.read_sets(rng, fixture_fasta[1], length, k, scale=2.0).items():
         want_hits, want_tx, _, _ = _oracle(ix, reads)
-        for lanes in (8, 16, 32):          # lanes per read: a tuning knob that must not change results
+        # tuning knobs that must not change results: lanes per read of the cooperative kernel,
+        # and how much the thread-per-read kernel keeps for itself (0 probes = it is skipped)
+        for lanes, probes, max_small in ((8, 0, 0), (16, 1, 4), (32, 3, 32), (8, 64, 1 << 30)):
             pa.mapper.set_group_width(lanes)
+            pa.mapper.set_fast_path(probes, max_small)
             got_hits, got_tx = pa.mapper.map_ascii(reads)
             _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     pa.mapper.set_group_width(8)
+    pa.mapper.set_fast_path(3, 32)
 
 
 def test_small_fq(pa_for, orc_index_for, fixture_fastq):
@@ -132,6 +136,14 @@ def test_long_reads_and_chunking(orc_index_for, fixture_fasta):
     pa.close()
 
 
+def _check_events(ev, want_ev):
+    for key_gpu, key_orc in (("reads", "reads"), ("read_bases", "read_bases"), ("kmer_lookups", "kmer_lookups"),
+                             ("node_visits", "node_visits"), ("bases_compared", "bases_compared"),
+                             ("edge_jumps", "edge_jumps"), ("out_members", "out_members"), ("aligned", "aligned")):
+        assert ev[key_gpu] == want_ev[key_orc], (key_gpu, ev, want_ev)
+    assert ev["verifications"] >= want_ev["dict_hits"] and ev["mphf_levels"] >= ev["kmer_lookups"]
+
+
 def test_device_batch_and_events(orc_index_for, fixture_fasta):
     """Device-resident fixed-stride ASCII batch (the bench's kernel-only arm), async entry,
     and the event counters against the oracle's (hash-independent ones must agree exactly)."""
@@ -152,12 +164,15 @@ def test_device_batch_and_events(orc_index_for, fixture_fasta):
     got_hits, got_tx = b.download()
     _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     assert np.array_equal(pa.mapper.counts(), want_counts)
+    for probes in (0, 1, 3, 64):
+        pa.mapper.set_fast_path(probes, 32)
+        parts = pa.mapper.map_device_events(b, split=True)
+        ev = {key: parts[0][key] + parts[1][key] for key in parts[0]}
+        assert (parts[0]["reads"] == 0) == (probes == 0) and parts[1]["reads"] > 0
+        _check_events(ev, want_ev)
+    pa.mapper.set_fast_path(3, 32)
     ev = pa.mapper.map_device_events(b)
-    for key_gpu, key_orc in (("reads", "reads"), ("read_bases", "read_bases"), ("kmer_lookups", "kmer_lookups"),
-                             ("node_visits", "node_visits"), ("bases_compared", "bases_compared"),
-                             ("edge_jumps", "edge_jumps"), ("out_members", "out_members"), ("aligned", "aligned")):
-        assert ev[key_gpu] == want_ev[key_orc], (key_gpu, ev, want_ev)
-    assert ev["verifications"] >= want_ev["dict_hits"] and ev["mphf_levels"] >= ev["kmer_lookups"]
+    _check_events(ev, want_ev)
     # packed device batch
     words, off, lens = orc.pack_reads(reads)
     b2 = pkg.DeviceBatch(pkg.pseudoaligner.READS_PACKED, words, n, read_off=off, read_len=lens, tx_cap=64 * n)
@@ -200,9 +215,10 @@ def test_parity_random_transcriptomes(k):
     codes, off = host.encode_transcripts(seqs)
     flat, _ = host.build_graph(codes, off, k)
     ix = orc.OrcIndex.from_flat(flat)
-    for gamma, lanes in ((0.0, 8), (1.0, 16), (4.0, 32)):
+    for gamma, lanes, probes in ((0.0, 8, 3), (1.0, 16, 0), (4.0, 32, 1)):
         pa = pkg.Pseudoaligner(flat, device=0, gamma=gamma)
         pa.mapper.set_group_width(lanes)
+        pa.mapper.set_fast_path(probes, 8)
         reads = []
         for length in (k, k + 1, 2 * k + 3, 150, 1100):
             for name, rs in cases.read_sets(rng, seqs, length, k, scale=0.1).items():

@@ -34,6 +34,8 @@ def hs():
     L.hs_lookup.restype, L.hs_lookup.argtypes = C.c_int, [vp, vp, C.POINTER(u32), C.POINTER(u32)]
     L.hs_map_batch.restype = u64
     L.hs_map_batch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64]
+    L.hs_map_batch_thread.restype = u64
+    L.hs_map_batch_thread.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, vp, vp, u64, C.POINTER(u64)]
     L.hs_pack_ascii.argtypes = [C.c_char_p, u64, vp]
     return L
 
@@ -63,11 +65,25 @@ class HsIndex:
                 return hits, tx[:need]
             cap = int(need)
 
+    def map_batch_thread(self, words, off, lens, max_probes, max_small, allowed=2):
+        """The fast kernel's one-thread-per-read policy, deferrals redone by the serial policy."""
+        n = len(lens)
+        hits = np.zeros(n, dtype=orc.HIT_DTYPE)
+        cap = max(64 * n, 4096)
+        nd = C.c_uint64()
+        while True:
+            tx = np.zeros(cap, np.uint32)
+            need = self.L.hs_map_batch_thread(self.h, _p(words), _p(off), _p(lens), n, allowed, max_probes, max_small,
+                                              _p(hits), _p(tx), cap, C.byref(nd))
+            if need <= cap:
+                return hits, tx[:need], int(nd.value)
+            cap = int(need)
+
     def close(self):
         self.L.hs_index_destroy(self.h)
 
 
-def _compare(ix_orc, ix_hs, reads):
+def _compare(ix_orc, ix_hs, reads, thread_cfgs=((1, 4), (3, 64), (64, 1 << 30))):
     words, off, lens = orc.pack_reads(reads)
     h1, t1, _, _ = ix_orc.map_batch(words, off, lens)
     h2, t2 = ix_hs.map_batch(words, off, lens)
@@ -75,7 +91,34 @@ def _compare(ix_orc, ix_hs, reads):
     for i, (x, y) in enumerate(zip(a, b)):
         assert x == y, (i, reads[i], x, y)
     assert np.array_equal(h1["eq_id"], h2["eq_id"])
+    # the thread-per-read policy with its deferrals: same results whatever the split
+    for max_probes, max_small in thread_cfgs:
+        h3, t3, nd = ix_hs.map_batch_thread(words, off, lens, max_probes, max_small)
+        c = orc.hits_to_tuples(h3, t3)
+        for i, (x, y) in enumerate(zip(a, c)):
+            assert x == y, ("thread", max_probes, max_small, i, reads[i], x, y)
+        assert np.array_equal(h1["eq_id"], h3["eq_id"])
+        assert np.array_equal(t1, t3)
+        _DEFER[(max_probes, max_small)] = _DEFER.get((max_probes, max_small), 0) + nd
+        _DEFER["reads"] = _DEFER.get("reads", 0) + len(reads)
     return a
+
+
+_DEFER = {}
+
+
+def test_thread_policy_defers_some_but_not_all(hs, orc_index_for, fixture_fasta):
+    """With one probe per seed search the fast policy must hand the noisy reads over and keep
+    the clean ones; with unbounded probes only class-list overflows are handed over."""
+    ix = orc_index_for(20)
+    hx = HsIndex(hs, ix.flat())
+    rng = np.random.default_rng(5)
+    reads = util.sample_reads(rng, fixture_fasta[1], 3000, 150, p_sub=0.005)
+    words, off, lens = orc.pack_reads(reads)
+    _, _, nd1 = hx.map_batch_thread(words, off, lens, 1, 64)
+    _, _, nd64 = hx.map_batch_thread(words, off, lens, 64, 1 << 30)
+    assert 0 < nd64 <= nd1 < len(reads) // 2, (nd1, nd64)
+    hx.close()
 
 
 @pytest.mark.parametrize("k,length", [(20, 150), (20, 60), (24, 91), (64, 150)])
