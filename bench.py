@@ -324,6 +324,7 @@ def main():
     # events of one batch (untimed): the algorithmic work the roofline is computed from
     ev_split = mapper.map_device_events(dev_batches[0], split=True)
     ev = {key: ev_split[0][key] + ev_split[1][key] for key in ev_split[0]}
+    deferred_by = mapper.defer_reasons()
     mapper.counts_reset()
     a_bytes_per_read = algorithmic_bytes(ev, a.k) / ev["reads"]
 
@@ -425,7 +426,7 @@ def main():
                 "kernel_share_of_step": kernels[dom]["share_of_step"], "kernels": kernels,
                 "algorithmic_bytes_per_read": a_bytes_per_read,
                 "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_launch"] for v in kernels.values()) / 1e3) / 1e9,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "handed_over_by_k_map_thread": deferred_by,
                 "note": "dependent random 32-byte-sector gathers: see DESIGN.md for the sector-rate view"}
 
     cpu = None

@@ -216,6 +216,11 @@ typedef struct psa_events {
 int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results,
                           psa_events out[2]);
 
+/* After psa_mapper_map_events: why k_map_thread handed reads over -- [0] first seed search
+ * longer than max_probes, [1] re-seed search longer than max_probes, [2] more than 4
+ * distinct classes, [3] smallest class longer than max_small.  Diagnostic. */
+int psa_mapper_defer_reasons(psa_mapper*, uint64_t out[4]);
+
 /* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
 uint64_t psa_mapper_launch_count(const psa_mapper*);
 /* Device timing of the two map kernels alone: when enabled, every launch is bracketed by

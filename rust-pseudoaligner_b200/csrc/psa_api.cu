@@ -89,7 +89,7 @@ struct DevBuf {
 struct psa_index {
     int device = 0;
     DevIndex d{};
-    DevBuf blocks, values, nodes, seq, eq_off, eq_mem;
+    DevBuf blocks, values, nodes, seq, eq_off, eq_mem, class_win;
     psa_index_info info{};
     int kw = 1;
 };
@@ -308,6 +308,7 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     CUI(cudaMemcpy(ix->eq_off.p, d->eq_offsets, (d->n_eq + 1) * 8, cudaMemcpyHostToDevice));
     RCI(ix->eq_mem.ensure(n_mem * 4 + 4));
     if (n_mem) CUI(cudaMemcpy(ix->eq_mem.p, d->eq_members, n_mem * 4, cudaMemcpyHostToDevice));
+    RCI(ix->class_win.ensure((d->n_eq + 1) * sizeof(ClassWin)));
     RCI(ix->nodes.ensure((d->n_nodes + 1) * sizeof(NodeRec)));
     RCI(node_start.ensure(d->n_nodes * 8 + 8));
     RCI(node_len.ensure(d->n_nodes * 4 + 4));
@@ -335,6 +336,7 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     D.seq = ix->seq.as<uint64_t>();
     D.eq_off = ix->eq_off.as<uint64_t>();
     D.eq_mem = ix->eq_mem.as<uint32_t>();
+    D.class_win = ix->class_win.as<ClassWin>();
 
     cudaEvent_t e0, e1;
     CUI(cudaEventCreate(&e0));
@@ -345,6 +347,9 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
                                                          node_len.as<uint32_t>(), node_exts.as<uint8_t>(),
                                                          node_eq.as<uint32_t>(), ix->eq_off.as<uint64_t>(), d->n_eq,
                                                          d->k, err.as<uint32_t>());
+    if (d->n_eq)
+        k_build_class_win<<<nblocks(d->n_eq, 256), 256>>>(ix->eq_off.as<uint64_t>(), ix->eq_mem.as<uint32_t>(), d->n_eq,
+                                                          ix->class_win.as<ClassWin>());
     CUI(cudaGetLastError());
     if (ix->kw == 1) RCI(build_on_device<1>(ix, d, gamma, node_start, koff, n_kmers));
     else RCI(build_on_device<2>(ix, d, gamma, node_start, koff, n_kmers));
@@ -368,7 +373,7 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     I.values_bytes = n_kmers * 8;
     I.node_bytes = d->n_nodes * sizeof(NodeRec);
     I.seq_bytes = d->n_seq_words * 8;
-    I.eq_bytes = (d->n_eq + 1) * 8 + n_mem * 4;
+    I.eq_bytes = (d->n_eq + 1) * 8 + n_mem * 4 + d->n_eq * sizeof(ClassWin);
     I.node_bits = D.node_bits;
     I.off_bits = D.off_bits;
     I.fp_bits = D.fp_bits;
@@ -383,7 +388,7 @@ extern "C" void psa_index_destroy(psa_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     ix->blocks.release(); ix->values.release(); ix->nodes.release();
-    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release();
+    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
     delete ix;
 }
 
@@ -530,13 +535,13 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     const uint64_t nc = ix->d.n_eq + 2;
     if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
-        (rc = m->novel_cursor.ensure(32)) || (rc = m->events.ensure(24 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
+        (rc = m->novel_cursor.ensure(32)) || (rc = m->events.ensure(28 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
         (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16))) {
         psa_mapper_destroy(m);
         return rc;
     }
     cudaMemset(m->counts.p, 0, nc * 8);
-    cudaMemset(m->events.p, 0, 24 * 8);
+    cudaMemset(m->events.p, 0, 28 * 8);
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
@@ -977,10 +982,17 @@ extern "C" int psa_mapper_map_events(psa_mapper* m, const psa_read_batch* r, psa
     if (r->location != PSA_MEM_DEVICE || o->location != PSA_MEM_DEVICE)
         return fail(PSA_ERR_ARG, "psa_mapper_map_events needs device-resident batches");
     CU(cudaSetDevice(m->ix->device));
-    CU(cudaMemsetAsync(m->events.p, 0, 24 * 8, m->st));
+    CU(cudaMemsetAsync(m->events.p, 0, 28 * 8, m->st));
     if ((rc = map_device_sync<true>(m, r, o))) return rc;
     static_assert(sizeof(psa_events) == 12 * 8, "psa_events layout");
     CU(cudaMemcpy(out, m->events.p, 2 * sizeof(psa_events), cudaMemcpyDeviceToHost));
+    return PSA_OK;
+}
+
+extern "C" int psa_mapper_defer_reasons(psa_mapper* m, uint64_t out[4]) {
+    if (!m || !out) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaMemcpy(out, m->events.as<uint64_t>() + 24, 4 * 8, cudaMemcpyDeviceToHost));
     return PSA_OK;
 }
 

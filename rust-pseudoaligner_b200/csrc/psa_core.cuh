@@ -226,6 +226,7 @@ struct DevIndex {
     const uint64_t* seq;
     const uint64_t* eq_off;
     const uint32_t* eq_mem;
+    const struct ClassWin* class_win;  // one 32-byte window per class (see below)
     Mphf mphf;
 };
 
@@ -508,6 +509,157 @@ PSA_HD bool contains_sorted(const T* v, uint64_t n, T x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Class windows: nodes_to_eq_class (ref src/pseudoaligner.rs:323-356) as bit-parallel ANDs.
+//
+// An equivalence class is an ascending list of transcript ids (ref src/equiv_classes.rs:78-79).
+// Transcripts of one gene are neighbours in the FASTA, so most classes span a narrow id range.
+// Every class whose max - min < 192 also gets a 32-byte window {min, 192-bit membership map};
+// the intersection of such classes is the AND of their windows aligned to a common base -- one
+// sector per class and a few shifts instead of a binary search per member per class.  Classes
+// that do not fit ("wide") keep the reference's list search (:399-404) against the candidates
+// that survive the windows, so the result is exact in every case.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kWinBits = 192;
+constexpr uint32_t kWinWide = 0xFFFFFFFFu;
+struct ClassWin {      // 32 bytes, 32-byte aligned
+    uint32_t lo;       // smallest member
+    uint32_t len;      // |class|, or kWinWide (bits unused)
+    uint64_t bits[3];  // bit t of the 192-bit map set iff lo + t is a member
+};
+static_assert(sizeof(ClassWin) == 32, "ClassWin must be one 32-byte sector");
+
+struct Win {
+    uint64_t w0, w1, w2;
+};
+PSA_HD Win win_and(Win a, Win b) { return Win{a.w0 & b.w0, a.w1 & b.w1, a.w2 & b.w2}; }
+PSA_HD uint32_t win_popc(Win a) { return (uint32_t)(popc64(a.w0) + popc64(a.w1) + popc64(a.w2)); }
+PSA_HD bool win_empty(Win a) { return (a.w0 | a.w1 | a.w2) == 0; }
+// logical shift right of the 192-bit map by d (any d; >= 192 gives 0)
+PSA_HD Win win_shr(Win a, uint32_t d) {
+    if (d >= kWinBits) return Win{0, 0, 0};
+    const uint32_t ws = d >> 6, bs = d & 63;
+    uint64_t x0 = ws == 0 ? a.w0 : ws == 1 ? a.w1 : a.w2;
+    uint64_t x1 = ws == 0 ? a.w1 : ws == 1 ? a.w2 : 0;
+    uint64_t x2 = ws == 0 ? a.w2 : 0;
+    if (bs) {
+        x0 = (x0 >> bs) | (x1 << (64 - bs));
+        x1 = (x1 >> bs) | (x2 << (64 - bs));
+        x2 >>= bs;
+    }
+    return Win{x0, x1, x2};
+}
+// the window of one class (index construction; members ascending, unique)
+PSA_HD ClassWin make_class_win(const uint32_t* members, uint64_t len) {
+    ClassWin c;
+    c.lo = len ? members[0] : 0;
+    c.len = (uint32_t)len;
+    c.bits[0] = c.bits[1] = c.bits[2] = 0;
+    if (len && members[len - 1] - members[0] >= kWinBits) {
+        c.len = kWinWide;
+        return c;
+    }
+    for (uint64_t i = 0; i < len; i++) {
+        uint32_t t = members[i] - c.lo;
+        c.bits[t >> 6] |= 1ULL << (t & 63);
+    }
+    return c;
+}
+PSA_HD ClassWin load_class_win(const ClassWin* p) {
+    ClassWin c;
+#ifdef __CUDA_ARCH__
+    uint64_t a, b0, b1, b2;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b0), "=l"(b1), "=l"(b2) : "l"(p));
+    c.lo = (uint32_t)a;
+    c.len = (uint32_t)(a >> 32);
+    c.bits[0] = b0; c.bits[1] = b1; c.bits[2] = b2;
+#else
+    c = *p;
+#endif
+    return c;
+}
+// Running intersection of narrow classes: {base, map} means the set {base + t : bit t set}.
+struct WinAcc {
+    uint32_t base;
+    Win map;
+    bool have;
+};
+PSA_HD void winacc_merge(WinAcc& a, const WinAcc& b) {
+    if (!b.have) return;
+    if (!a.have) {
+        a = b;
+    } else if (b.base >= a.base) {
+        a.map = win_and(win_shr(a.map, b.base - a.base), b.map);
+        a.base = b.base;
+    } else {
+        a.map = win_and(a.map, win_shr(b.map, a.base - b.base));
+    }
+}
+PSA_HD void winacc_and(WinAcc& a, const ClassWin& c) {  // c narrow
+    WinAcc b;
+    b.base = c.lo;
+    b.map = Win{c.bits[0], c.bits[1], c.bits[2]};
+    b.have = true;
+    winacc_merge(a, b);
+}
+// members of the accumulated set, ascending
+PSA_HD uint32_t win_write(const WinAcc& a, uint32_t* out) {
+    uint32_t n = 0;
+    uint64_t w = a.map.w0;
+    while (w) { out[n++] = a.base + (uint32_t)ctz64(w); w &= w - 1; }
+    w = a.map.w1;
+    while (w) { out[n++] = a.base + 64 + (uint32_t)ctz64(w); w &= w - 1; }
+    w = a.map.w2;
+    while (w) { out[n++] = a.base + 128 + (uint32_t)ctz64(w); w &= w - 1; }
+    return n;
+}
+PSA_HD uint32_t ld_mem(const uint32_t* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+PSA_HD uint64_t ld_off(const uint64_t* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// Bits of `map` (a set over `base`) whose member the ascending list v[0..n) lacks; only the
+// candidates with rank % stride == phase are examined (the lanes of a group split them).
+PSA_HD Win win_absent_in_list(Win map, uint32_t base, const uint32_t* v, uint32_t n, uint32_t phase, uint32_t stride) {
+    Win kill{0, 0, 0};
+    uint32_t lo = 0, rank = 0;
+    for (int wi = 0; wi < 3; wi++) {
+        uint64_t w = wi == 0 ? map.w0 : wi == 1 ? map.w1 : map.w2;
+        uint64_t k = 0;
+        while (w) {
+            const uint32_t t = (uint32_t)ctz64(w);
+            w &= w - 1;
+            if (rank++ % stride != phase) continue;
+            const uint32_t x = base + 64 * wi + t;
+            uint32_t hi = n;  // search the suffix after the previous match (ref :399-404)
+            while (lo < hi) {
+                uint32_t mid = lo + ((hi - lo) >> 1);
+                if (ld_mem(v + mid) < x) lo = mid + 1;
+                else hi = mid;
+            }
+            if (!(lo < n && ld_mem(v + lo) == x)) k |= 1ULL << t;
+        }
+        if (wi == 0) kill.w0 = k;
+        else if (wi == 1) kill.w1 = k;
+        else kill.w2 = k;
+    }
+    return kill;
+}
+// drop from the accumulated set every member the (wide) class list v[0..n) lacks
+PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
+    Win kill = win_absent_in_list(a.map, a.base, v, n, 0, 1);
+    a.map = Win{a.map.w0 & ~kill.w0, a.map.w1 & ~kill.w1, a.map.w2 & ~kill.w2};
+}
+
+// ---------------------------------------------------------------------------------------------
 // One thread = one read: the policy of the fast kernel (k_map_thread).  It runs the same
 // map_read_nodes text with every step done serially by the calling thread, and gives a read
 // up ("defer") as soon as it needs something a single thread does badly: a seed scan longer
@@ -515,7 +667,7 @@ PSA_HD bool contains_sorted(const T* v, uint64_t n, T x) {
 // with more than max_small members.  Deferred reads are redone from scratch by the
 // cooperative kernel (k_map over the deferred list), so the split never changes a result.
 // ---------------------------------------------------------------------------------------------
-constexpr int kThreadClasses = 4;
+constexpr int kThreadClasses = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
 struct HitRec {  // == psa_hit
@@ -533,16 +685,17 @@ struct ThreadCtx {
     const DevIndex& ix;
     PLoad rd;
     uint32_t k, max_probes;
-    uint32_t eq[kThreadClasses], len[kThreadClasses];
-    uint64_t off[kThreadClasses];
+    uint32_t eq[kThreadClasses], len[kThreadClasses];  // offsets are re-read from eq_off when needed
     uint32_t n_list;
     bool defer;
+    uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
+    bool seeded;
     ThreadEvents ev;
 
     PSA_HD ThreadCtx(const DevIndex& ix_, const uint64_t* words, uint32_t max_probes_)
-        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), ev{} {
+        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false), ev{} {
     PSA_UNROLL
-        for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; off[j] = 0; }
+        for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; }
     }
     PSA_HD bool abort() const { return defer; }
     PSA_HD uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
@@ -559,6 +712,7 @@ struct ThreadCtx {
             }
             if (probes >= max_probes) {
                 defer = true;
+                why = seeded ? 1 : 0;
                 kmer_pos = last + 1;  // keeps map_read_nodes out of the forward loop
                 return false;
             }
@@ -567,6 +721,7 @@ struct ThreadCtx {
             if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) {
                 kmer_pos = p;
+                seeded = true;
                 return true;
             }
         }
@@ -632,38 +787,31 @@ struct ThreadCtx {
         if (dup) return;
         if (n_list >= (uint32_t)kThreadClasses) {
             defer = true;
+            why = 2;
             return;
         }
     PSA_UNROLL
         for (int j = 0; j < kThreadClasses; j++)
-            if (j == (int)n_list) { eq[j] = nv.eq; len[j] = nv.class_len; off[j] = nv.class_off; }
+            if (j == (int)n_list) { eq[j] = nv.eq; len[j] = nv.class_len; }
         n_list++;
     }
 };
 
-PSA_HD uint32_t ld_mem(const uint32_t* p) {
-#ifdef __CUDA_ARCH__
-    return __ldg(p);
-#else
-    return *p;
-#endif
-}
-
-// nodes_to_eq_class (ref src/pseudoaligner.rs:323-356) by one thread: members of the smallest
-// class (index s) that every other listed class contains, ascending.  Each other class is
-// searched only in the suffix after its previous match -- the reference's own scheme (:399-404).
+// All visited classes are wide: the reference's list scheme by one thread.  Members of the
+// smallest class (index s) that every other listed class contains, ascending; each other
+// class is searched only in the suffix after its previous match (ref :399-404).
 // out == nullptr counts.
 template <int KW, bool EV>
-PSA_HD uint32_t thread_intersect(const ThreadCtx<KW, EV>& w, int s, uint32_t* out) {
+PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV>& w, int s, uint32_t* out) {
     const uint32_t* mem = w.ix.eq_mem;
     uint32_t cur[kThreadClasses];
     PSA_UNROLL
     for (int j = 0; j < kThreadClasses; j++) cur[j] = 0;
-    uint32_t s_len = 0;
-    uint64_t s_off = 0;
+    uint32_t s_len = 0, s_eq = 0;
     PSA_UNROLL
     for (int j = 0; j < kThreadClasses; j++)
-        if (j == s) { s_len = w.len[j]; s_off = w.off[j]; }
+        if (j == s) { s_len = w.len[j]; s_eq = w.eq[j]; }
+    const uint64_t s_off = ld_off(w.ix.eq_off + s_eq);
     uint32_t count = 0;
     for (uint32_t i = 0; i < s_len; i++) {
         const uint32_t x = ld_mem(mem + s_off + i);
@@ -671,7 +819,7 @@ PSA_HD uint32_t thread_intersect(const ThreadCtx<KW, EV>& w, int s, uint32_t* ou
     PSA_UNROLL
         for (int j = 0; j < kThreadClasses; j++) {
             if (j == s || j >= (int)w.n_list || !alive) continue;
-            const uint32_t* v = mem + w.off[j];
+            const uint32_t* v = mem + ld_off(w.ix.eq_off + w.eq[j]);
             uint32_t lo = cur[j], hi = w.len[j];
             while (lo < hi) {
                 uint32_t mid = lo + ((hi - lo) >> 1);
@@ -695,6 +843,7 @@ struct ThreadResult {
     uint64_t count_slot;  // index into counts[]: eq id, n_eq (no visited class), n_eq + 1 (None)
     bool deferred;
     bool novel_overflow;
+    uint32_t why;  // ThreadCtx::why when deferred
 };
 
 // map_read + the process_reads flag for one read, by one thread.  NovelAlloc::operator()(count,
@@ -712,6 +861,7 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, u
     ThreadCtx<KW, EV> w(ix, words, max_probes);
     uint32_t coverage = 0;
     bool some = map_read_nodes(w, ix.k, (uint64_t)L, allowed, coverage);
+    res.why = w.why;
     if (w.defer) {
         res.deferred = true;
         return res;
@@ -726,16 +876,40 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, u
                 s = j; s_len = w.len[j]; s_eq = w.eq[j];
             }
         uint32_t count, eq_id;
+        WinAcc acc;
+        acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
         if (w.n_list == 1) {
             count = s_len;
             eq_id = s_eq;
             if (EV) w.ev.members += s_len;
         } else {
-            if (s_len > max_small) {  // long lists are the cooperative kernel's job
-                res.deferred = true;
-                return res;
+            // narrow classes: AND of their windows; wide ones filter what survives
+            uint32_t n_wide = 0;
+    PSA_UNROLL
+            for (int j = 0; j < kThreadClasses; j++) {
+                if (j >= (int)w.n_list) continue;
+                ClassWin c = load_class_win(ix.class_win + w.eq[j]);
+                if (c.len == kWinWide) n_wide++;
+                else winacc_and(acc, c);
             }
-            count = thread_intersect(w, s, (uint32_t*)nullptr);
+            if (acc.have) {
+                if (n_wide) {
+    PSA_UNROLL
+                    for (int j = 0; j < kThreadClasses; j++) {
+                        if (j >= (int)w.n_list || win_empty(acc.map)) continue;
+                        if (load_class_win(ix.class_win + w.eq[j]).len != kWinWide) continue;
+                        winacc_filter_list(acc, ix.eq_mem + ld_off(ix.eq_off + w.eq[j]), w.len[j]);
+                    }
+                }
+                count = win_popc(acc.map);
+            } else {
+                if (s_len > max_small) {  // long lists are the cooperative kernel's job
+                    res.why = 3;
+                    res.deferred = true;
+                    return res;
+                }
+                count = thread_intersect_lists(w, s, (uint32_t*)nullptr);
+            }
             eq_id = kNone;  // the result equals a visited class iff that class has `count` members
     PSA_UNROLL
             for (int j = 0; j < kThreadClasses; j++)
@@ -749,19 +923,16 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, u
         res.hit.eq_id = eq_id;
         res.hit.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
         if (eq_id != kNone) {
-            uint64_t o = 0;
-    PSA_UNROLL
-            for (int j = 0; j < kThreadClasses; j++)
-                if (j < (int)w.n_list && w.eq[j] == eq_id) o = w.off[j];
-            res.hit.tx_off = o;  // members are read from the index by k_expand
+            res.hit.tx_off = ld_off(ix.eq_off + eq_id);  // members are read from the index by k_expand
             res.count_slot = eq_id;
         } else {
             res.count_slot = ix.n_eq;
             if (count && want_members) {
                 uint64_t o = 0;
                 uint32_t* dst = novel(count, o);
-                if (dst) thread_intersect(w, s, dst);
-                else res.novel_overflow = true;
+                if (!dst) res.novel_overflow = true;
+                else if (acc.have) win_write(acc, dst);
+                else thread_intersect_lists(w, s, dst);
                 res.hit.tx_off = o;
             }
         }

@@ -182,6 +182,14 @@ __global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
     }
 }
 
+// one 32-byte window per class (psa_core.cuh "Class windows")
+__global__ void k_build_class_win(const uint64_t* eq_off, const uint32_t* eq_mem, uint64_t n_eq, ClassWin* out) {
+    uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c >= n_eq) return;
+    const uint64_t o = eq_off[c];
+    out[c] = make_class_win(eq_mem + o, eq_off[c + 1] - o);
+}
+
 template <int KW>
 __global__ void k_lookup(DevIndex ix, const uint64_t* kmer_words, uint64_t n, uint8_t* found, uint32_t* node,
                          uint32_t* off) {
@@ -576,12 +584,57 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
             const uint32_t s_len = (uint32_t)(key >> 32), s_eq = (uint32_t)key;
             const uint64_t s_off = koff;
             uint32_t count, eq_id;
+            WinAcc acc;
+            acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
             if (w.n_list == 1) {
                 count = s_len;
                 eq_id = s_eq;
                 if (EV && lane == 0) w.ev.members += s_len;
             } else {
-                count = intersect_pass(w, s_eq, s_len, s_off, nullptr);
+                // windows of this lane's entries, then a butterfly over the group (psa_core.cuh "Class windows")
+                uint32_t n_wide = 0;
+                if (lane < w.n_list) {
+                    ClassWin c = load_class_win(ix.class_win + w.my_eq);
+                    if (c.len == kWinWide) n_wide++;
+                    else winacc_and(acc, c);
+                }
+                for (uint32_t j = G + lane; j < w.n_list; j += G) {
+                    ClassWin c = load_class_win(ix.class_win + w.spill[j - G].x);
+                    if (c.len == kWinWide) n_wide++;
+                    else winacc_and(acc, c);
+                }
+#pragma unroll
+                for (int d = G / 2; d; d >>= 1) {
+                    WinAcc o;
+                    o.base = w.g.shfl_xor(acc.base, d);
+                    o.map.w0 = w.g.shfl_xor(acc.map.w0, d);
+                    o.map.w1 = w.g.shfl_xor(acc.map.w1, d);
+                    o.map.w2 = w.g.shfl_xor(acc.map.w2, d);
+                    o.have = w.g.shfl_xor((int)acc.have, d) != 0;
+                    winacc_merge(acc, o);
+                    n_wide += w.g.shfl_xor(n_wide, d);
+                }
+                if (acc.have) {
+                    if (n_wide) {  // wide classes filter the surviving candidates, the lanes sharing the searches
+                        for (uint32_t j = 0; j < w.n_list && !win_empty(acc.map); j++) {
+                            uint32_t e, l;
+                            uint64_t o;
+                            w.entry(j, e, l, o);
+                            if (__ldg(&ix.class_win[e].len) != kWinWide) continue;
+                            Win kill = win_absent_in_list(acc.map, acc.base, ix.eq_mem + o, l, lane, G);
+#pragma unroll
+                            for (int d = G / 2; d; d >>= 1) {
+                                kill.w0 |= w.g.shfl_xor(kill.w0, d);
+                                kill.w1 |= w.g.shfl_xor(kill.w1, d);
+                                kill.w2 |= w.g.shfl_xor(kill.w2, d);
+                            }
+                            acc.map = Win{acc.map.w0 & ~kill.w0, acc.map.w1 & ~kill.w1, acc.map.w2 & ~kill.w2};
+                        }
+                    }
+                    count = win_popc(acc.map);
+                } else {
+                    count = intersect_pass(w, s_eq, s_len, s_off, nullptr);  // every class is wide: the list scheme
+                }
                 // the result equals a visited class iff that class has `count` members
                 uint32_t cand = (lane < w.n_list && w.my_len == count) ? w.my_eq : kNone;
                 for (uint32_t j = G + lane; j < w.n_list; j += G) {
@@ -606,14 +659,7 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
             h.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
             if (eq_id != kNone) {
                 // members are read from the index by k_expand; eq_id is one of the visited classes
-                uint64_t off = (lane < w.n_list && w.my_eq == eq_id) ? w.my_off : 0;
-                for (uint32_t j = G + lane; j < w.n_list; j += G) {
-                    uint4 e = w.spill[j - G];
-                    if (e.x == eq_id) off = (uint64_t)e.z | ((uint64_t)e.w << 32);
-                }
-#pragma unroll
-                for (int d = G / 2; d; d >>= 1) off |= w.g.shfl_xor(off, d);
-                h.tx_off = off;
+                h.tx_off = __ldg(ix.eq_off + eq_id);
                 count_slot = eq_id;
             } else {
                 count_slot = ix.n_eq;
@@ -621,8 +667,13 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
                     unsigned long long base = 0;
                     if (lane == 0) base = atomicAdd(p.novel_cursor, (unsigned long long)count);
                     base = w.g.shfl(base, 0);
-                    if (base + count <= p.novel_cap) intersect_pass(w, s_eq, s_len, s_off, p.novel + base);
-                    else if (lane == 0) atomicOr(p.status, 1u);
+                    if (base + count > p.novel_cap) {
+                        if (lane == 0) atomicOr(p.status, 1u);
+                    } else if (acc.have) {
+                        if (lane == 0) win_write(acc, p.novel + base);
+                    } else {
+                        intersect_pass(w, s_eq, s_len, s_off, p.novel + base);
+                    }
                     h.tx_off = base;
                 }
             }
@@ -679,6 +730,7 @@ __global__ void __launch_bounds__(kThreadBlock) k_map_thread(const __grid_consta
         ThreadResult res = map_read_thread<KW, EV>(ix, p.reads.words + wo, L, p.allowed_mismatches, p.max_probes,
                                                    p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr);
         defer = res.deferred;
+        if (EV && defer && p.events) atomicAdd(p.events + 24 + res.why, 1ULL);
         if (!defer) {
             // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
             uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);

@@ -74,7 +74,7 @@ EXPORTS = (
     "psa_mapper_set_fast_path",
     "psa_mapper_map", "psa_mapper_map_async", "psa_mapper_sync", "psa_mapper_stream",
     "psa_mapper_map_read", "psa_mapper_counts_get", "psa_mapper_counts_reset",
-    "psa_mapper_counts_device", "psa_mapper_map_events", "psa_mapper_launch_count",
+    "psa_mapper_counts_device", "psa_mapper_map_events", "psa_mapper_defer_reasons", "psa_mapper_launch_count",
     "psa_mapper_profile_enable", "psa_mapper_profile_read",
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
@@ -119,6 +119,7 @@ def lib():
         f.restype, f.argtypes = i32, [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch)]
     L.psa_mapper_map_events.restype = i32
     L.psa_mapper_map_events.argtypes = [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch), C.POINTER(_Events * 2)]
+    L.psa_mapper_defer_reasons.restype, L.psa_mapper_defer_reasons.argtypes = i32, [vp, C.POINTER(u64 * 4)]
     L.psa_mapper_sync.restype, L.psa_mapper_sync.argtypes = i32, [vp]
     L.psa_mapper_stream.restype, L.psa_mapper_stream.argtypes = vp, [vp]
     L.psa_mapper_map_read.restype = i32
@@ -396,6 +397,11 @@ class Mapper:
         if split:
             return parts
         return {f: parts[0][f] + parts[1][f] for f in EVENT_FIELDS}
+
+    def defer_reasons(self):
+        out = (C.c_uint64 * 4)()
+        _check(lib().psa_mapper_defer_reasons(self.h, C.byref(out)))
+        return dict(zip(("first_seed_search", "reseed_search", "class_list_full", "smallest_class_long"), map(int, out)))
 
     def stream(self):
         return lib().psa_mapper_stream(self.h)

@@ -25,6 +25,7 @@ struct HsIndex {
     std::vector<uint64_t> blocks, values, seq, eq_off;
     std::vector<NodeRec> nodes;
     std::vector<uint32_t> eq_mem;
+    std::vector<ClassWin> class_win;
     int kw = 1;
     int error = 0;
 };
@@ -233,6 +234,10 @@ HsIndex* hs_index_create(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words
     ix->d.eq_off = ix->eq_off.data();
     ix->d.eq_mem = ix->eq_mem.data();
     ix->d.n_eq = n_eq;
+    ix->class_win.resize(n_eq + 1);
+    for (uint64_t c = 0; c < n_eq; c++)
+        ix->class_win[c] = make_class_win(ix->eq_mem.data() + eq_offsets[c], eq_offsets[c + 1] - eq_offsets[c]);
+    ix->d.class_win = ix->class_win.data();
     ix->kw = k <= 32 ? 1 : 2;
     if (gamma <= 0) gamma = 1.7;
     if (ix->kw == 1) build<1>(ix, k, n_nodes, node_start, node_len, node_exts, node_eq, gamma);

@@ -264,3 +264,21 @@ def test_synthetic_scale_checksum():
     assert np.array_equal(pa.mapper.counts(), want_counts)
     assert int((got_hits["flags"] & 1).sum()) > 0.9 * n
     pa.close()
+
+
+def test_wide_classes(fixture_fasta):
+    """Shuffled transcript order: most multi-member classes are too wide for a window, so the
+    list path runs next to the windows in both kernels (and alone when every class is wide)."""
+    rng = np.random.default_rng(12)
+    seqs = list(fixture_fasta[1][:700])
+    rng.shuffle(seqs)
+    ix = orc.OrcIndex.build(seqs, 20)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0)
+    for name, reads in cases.read_sets(rng, seqs, 150, 20, scale=1.0).items():
+        want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
+        for lanes, probes, max_small in ((8, 0, 0), (16, 3, 2), (32, 64, 1 << 30)):
+            pa.mapper.set_group_width(lanes)
+            pa.mapper.set_fast_path(probes, max_small)
+            got_hits, got_tx = pa.mapper.map_ascii(reads)
+            _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    pa.close()

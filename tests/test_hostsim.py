@@ -187,3 +187,20 @@ def test_hostsim_pack_ascii_matches_oracle(hs):
         hs.hs_pack_ascii(s, n, _p(a))
         orc.lib().orc_pack_ascii(s, n, _p(b))
         assert np.array_equal(a, b), s
+
+
+def test_hostsim_wide_classes(hs, fixture_fasta):
+    """Transcripts in shuffled order: isoforms of a gene are no longer neighbours, so most
+    multi-member classes span >= 192 ids and take the list path next to the windows."""
+    rng = np.random.default_rng(12)
+    seqs = list(fixture_fasta[1][:700])
+    rng.shuffle(seqs)
+    ix = orc.OrcIndex.build(seqs, 20)
+    flat = ix.flat()
+    eo, em = flat["eq_offsets"], flat["eq_members"]
+    wide = sum(1 for c in range(len(eo) - 1) if eo[c + 1] > eo[c] and int(em[eo[c + 1] - 1]) - int(em[eo[c]]) >= 192)
+    assert wide > 200
+    hx = HsIndex(hs, flat)
+    for name, reads in cases.read_sets(rng, seqs, 150, 20, scale=0.5).items():
+        _compare(ix, hx, reads)
+    hx.close()
