@@ -250,21 +250,22 @@ PSA_HD void level_pos(uint64_t h, uint64_t nblk, uint64_t& blk, uint32_t& bit) {
     bit = (uint32_t)(((h & 0xffffffffULL) * kBlockBits) >> 32);
 }
 
-struct Block {
-    uint64_t w[4];
+struct Block {  // named words, never indexed dynamically: the block must stay in registers
+    uint64_t hdr, w1, w2, w3;
 };
 PSA_HD Block load_block(const uint64_t* blocks, uint64_t b) {
     Block r;
 #ifdef __CUDA_ARCH__
     // one 32-byte sector per probe: header + 3 bit-vector words (LDG.E.256)
     asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-        : "=l"(r.w[0]), "=l"(r.w[1]), "=l"(r.w[2]), "=l"(r.w[3])
+        : "=l"(r.hdr), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3)
         : "l"(blocks + 4 * b));
 #else
-    for (int i = 0; i < 4; i++) r.w[i] = blocks[4 * b + i];
+    r.hdr = blocks[4 * b]; r.w1 = blocks[4 * b + 1]; r.w2 = blocks[4 * b + 2]; r.w3 = blocks[4 * b + 3];
 #endif
     return r;
 }
+PSA_HD uint64_t block_word(const Block& b, uint32_t wi) { return wi == 0 ? b.w1 : wi == 1 ? b.w2 : b.w3; }
 constexpr uint64_t kRankMask = (1ULL << 48) - 1;
 PSA_HD uint64_t make_header(uint64_t rank, uint32_t c1, uint32_t c2) {
     return rank | ((uint64_t)c1 << 48) | ((uint64_t)c2 << 55);
@@ -272,11 +273,10 @@ PSA_HD uint64_t make_header(uint64_t rank, uint32_t c1, uint32_t c2) {
 // rank of bit `bit` of a block whose bit is set = number of set bits before it in the cascade
 PSA_HD uint64_t block_rank(const Block& b, uint32_t bit) {
     uint32_t wi = bit >> 6, bi = bit & 63;
-    uint64_t hdr = b.w[0];
+    uint64_t hdr = b.hdr;
     uint64_t r = hdr & kRankMask;
-    if (wi == 1) r += (hdr >> 48) & 0x7f;
-    else if (wi == 2) r += (hdr >> 55) & 0xff;
-    r += (uint64_t)popc64(b.w[1 + wi] & ((1ULL << bi) - 1));
+    r += wi == 0 ? 0 : wi == 1 ? ((hdr >> 48) & 0x7f) : ((hdr >> 55) & 0xff);
+    r += (uint64_t)popc64(block_word(b, wi) & ((1ULL << bi) - 1));
     return r;
 }
 
@@ -293,7 +293,7 @@ PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& lev
         level_pos(level_hash(hk, lvl), m.level_nblk[lvl], blk, bit);
         Block b = load_block(m.blocks, m.level_base[lvl] + blk);
         levels++;
-        if ((b.w[1 + (bit >> 6)] >> (bit & 63)) & 1) {
+        if ((block_word(b, bit >> 6) >> (bit & 63)) & 1) {
             slot = block_rank(b, bit);
             return true;
         }

@@ -490,7 +490,7 @@ struct WarpCtx {
         n_list++;
     }
     // the per-group spill is full: move the list to a pool allocation sized for this read
-    __device__ __noinline__ bool grow_spill(uint32_t ns) {
+    __device__ __forceinline__ bool grow_spill(uint32_t ns) {
         const unsigned long long need = (unsigned long long)read_len + 2;
         if (need <= spill_cap) return false;  // already grown: cannot happen (pushes <= read_len + 1)
         unsigned long long base = 0;
@@ -714,9 +714,12 @@ struct DevNovel {
 };
 
 constexpr int kThreadBlock = 128;
+#ifndef PSA_THREAD_MIN_BLOCKS
+#define PSA_THREAD_MIN_BLOCKS 8
+#endif
 
 template <int KW, bool EV>
-__global__ void __launch_bounds__(kThreadBlock) k_map_thread(const __grid_constant__ DevIndex ix,
+__global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
                                                              const __grid_constant__ MapParams p) {
     const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     const bool live = r < p.reads.n;

@@ -83,7 +83,8 @@ EXPORTS = (
 
 
 def lib_path():
-    return os.path.join(_HERE, "libpsa_b200.so")
+    # PSA_LIB_PATH: an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("PSA_LIB_PATH") or os.path.join(_HERE, "libpsa_b200.so")
 
 
 _lib = None
