@@ -311,10 +311,13 @@ def main():
     R, L, G = a.reads_per_step, a.read_len, max(1, a.distinct_batches)
     tx_cap = 24 * R
     # distinct batches of this rank's share of the read stream: host (pinned) and device copies
+    shard = importlib.import_module(PKG + ".shard")
+    shard_lo, shard_hi = shard.shard_range(world * G * R, world, rank)   # weak scaling: G*R reads per rank
+    assert shard_hi - shard_lo == G * R
     host_batches, dev_batches = [], []
     for g in range(G):
         pin = psa.PinnedArray(R * L + 64, np.uint8)
-        tr.reads(3, (rank * G + g) * R, R, L, out=pin.array, threads=host_threads)
+        tr.reads(3, shard_lo + g * R, R, L, out=pin.array, threads=host_threads)
         host_batches.append(pin)
         dev_batches.append(pkg.DeviceBatch(psa.READS_ASCII, pin.array, R, stride=L, fixed_len=L, tx_cap=tx_cap))
     pin_hits = psa.PinnedArray(R, pkg.HIT_DTYPE)

@@ -230,6 +230,24 @@ uint64_t psa_mapper_launch_count(const psa_mapper*);
 int psa_mapper_profile_enable(psa_mapper*, int on);
 int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[2], uint64_t map_launches[2]);
 
+/* ------------------------------------------------------------------------------------------
+ * process_reads (ref src/pseudoaligner.rs:420-514): FASTQ file (plain or gzip) in, one line per
+ * read out -- `(flag, "id", [tx, ...], coverage)`, the `{:?}` of the tuple the reference
+ * println!s at :490 -- in input order.  out_path NULL or "-" = stdout.  num_threads = host
+ * threads that format the lines (the reference's num_threads are its mapping workers; mapping
+ * is on the GPU here).  batch_reads 0 = 1 Mi reads per batch.  progress != 0 prints the
+ * reference's stderr tick every 1 000 000 reads (:497-504).  A malformed FASTQ record returns
+ * PSA_ERR_IO after the records before it were processed (the reference panics, :446).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct psa_process_stats {
+    uint64_t reads;   /* read_counter, :476                                                  */
+    uint64_t mapped;  /* mapped_read_counter, :477 (the flag of :455, sic)                   */
+    uint64_t aligned; /* reads for which map_read returned Some                              */
+    double seconds;   /* wall time of the call                                               */
+} psa_process_stats;
+int psa_process_reads(psa_index*, const char* fastq_path, const char* out_path, uint32_t num_threads,
+                      uint64_t batch_reads, int progress, psa_process_stats* stats);
+
 /* ---- multi-GPU: reads shard across ranks, one all-reduce of the per-class counts ---- */
 typedef struct psa_comm psa_comm;
 #define PSA_NCCL_UNIQUE_ID_BYTES 128

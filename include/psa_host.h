@@ -10,8 +10,7 @@
  *   - psa_synth_*      the counter-based synthetic transcriptome / read generators of
  *                      BASELINE.md section 4
  *   - psa_fasta_* / psa_fastq_*   minimal readers (ref src/utils.rs:61-97, bio::io::fastq)
- *   - psa_process_reads  the batch driver around psa_mapper_map that prints the reference's
- *                      per-read tuple (ref src/pseudoaligner.rs:420-514)
+ * (The map driver, psa_process_reads, is part of libpsa_b200.so: include/psa.h.)
  * None of this is on the GPU hot path and none of it is a CPU implementation of map_read.
  */
 #ifndef PSA_HOST_H

@@ -11,5 +11,5 @@ table can be checked), every compute call needs the CUDA library and a device.
 """
 from .pseudoaligner import (  # noqa: F401
     EQ_NONE, FLAG_ALIGNED, FLAG_MAPPED, HIT_DTYPE, Index, Mapper, Pseudoaligner, PsaError,
-    Comm, format_read_data, lib, lib_path, process_reads, DeviceBatch,
+    Comm, format_read_data, lib, lib_path, process_reads, process_reads_file, DeviceBatch,
 )

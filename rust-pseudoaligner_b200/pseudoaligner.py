@@ -63,6 +63,10 @@ class _ResultBatch(C.Structure):
                 ("tx_buf", C.c_void_p), ("tx_cap", C.c_uint64), ("tx_used", C.c_uint64)]
 
 
+class _ProcessStats(C.Structure):
+    _fields_ = [("reads", C.c_uint64), ("mapped", C.c_uint64), ("aligned", C.c_uint64), ("seconds", C.c_double)]
+
+
 class _Events(C.Structure):
     _fields_ = [(f, C.c_uint64) for f in EVENT_FIELDS]
 
@@ -78,7 +82,7 @@ EXPORTS = (
     "psa_mapper_profile_enable", "psa_mapper_profile_read",
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
-    "psa_memcpy_h2d", "psa_memcpy_d2h",
+    "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads",
 )
 
 
@@ -142,6 +146,8 @@ def lib():
     L.psa_device_free.restype, L.psa_device_free.argtypes = None, [vp]
     L.psa_memcpy_h2d.restype, L.psa_memcpy_h2d.argtypes = i32, [vp, vp, u64]
     L.psa_memcpy_d2h.restype, L.psa_memcpy_d2h.argtypes = i32, [vp, vp, u64]
+    L.psa_process_reads.restype = i32
+    L.psa_process_reads.argtypes = [vp, C.c_char_p, C.c_char_p, u32, u64, i32, C.POINTER(_ProcessStats)]
     _lib = L
     return L
 
@@ -524,6 +530,16 @@ def format_read_data(flag, read_id, eq_class, coverage):
     esc = read_id.replace("\\", "\\\\").replace('"', '\\"')
     return "(%s, \"%s\", [%s], %d)" % ("true" if flag else "false", esc, ", ".join(str(int(t)) for t in eq_class),
                                       coverage)
+
+
+def process_reads_file(fastq_path, index, out_path=None, num_threads=2, batch_reads=0, progress=False):
+    """psa_process_reads: the native (C++) map driver, FASTQ file -> lines in `out_path` (stdout when
+    None).  `index` is a Pseudoaligner or an Index.  Returns {reads, mapped, aligned, seconds}."""
+    ix = index.index if isinstance(index, Pseudoaligner) else index
+    st = _ProcessStats()
+    _check(lib().psa_process_reads(ix.h, os.fsencode(fastq_path), os.fsencode(out_path) if out_path else None,
+                                   int(num_threads), int(batch_reads), 1 if progress else 0, C.byref(st)))
+    return {"reads": int(st.reads), "mapped": int(st.mapped), "aligned": int(st.aligned), "seconds": float(st.seconds)}
 
 
 def process_reads(records, index, outdir=None, num_threads=1, out=None, batch_reads=1 << 20):

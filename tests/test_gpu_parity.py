@@ -6,6 +6,7 @@ test/small.fq properties -- ref src/build_index.rs:300-367, :429-441) and every 
 map_read the reference never tests (left extension, re-seed, >2 mismatches per unitig, N,
 short reads), at k = 20 / 24 / 64 and read lengths 60 / 91 / 150 / 1100."""
 import importlib
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,7 @@ import pytest
 import cases
 import orc
 import util
+from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -282,3 +284,36 @@ def test_wide_classes(fixture_fasta):
             got_hits, got_tx = pa.mapper.map_ascii(reads)
             _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     pa.close()
+
+
+def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
+    """psa_process_reads (C++ mirror of ref src/pseudoaligner.rs:420-514) on test/small.fq: the
+    printed tuples equal the oracle's, line by line in input order; plain and gzip input, small
+    batches (pipeline wrap-around), a truncated file is an error after the good records."""
+    import gzip
+    ix, pa = orc_index_for(20), pa_for(20)
+    want_hits, want_tx, _, _ = _oracle(ix, [s for _, s in fixture_fastq])
+    want = []
+    for (rid, _), (al, flag, eq, cov) in zip(fixture_fastq, orc.hits_to_tuples(want_hits, want_tx)):
+        want.append(pkg.format_read_data(flag, rid, eq, cov))
+    fq = tmp_path / "small.fq"
+    with gzip.open(os.path.join(GOLDEN, "small.fq.gz"), "rb") as f:
+        raw = f.read()
+    fq.write_bytes(raw)
+    out = tmp_path / "out.txt"
+    st = pkg.process_reads_file(str(fq), pa, str(out), num_threads=3, batch_reads=1000)
+    assert out.read_text().splitlines() == want
+    assert st["reads"] == len(want) and st["mapped"] == sum(1 for l in want if l.startswith("(true"))
+    st = pkg.process_reads_file(os.path.join(GOLDEN, "small.fq.gz"), pa, str(out), num_threads=1)
+    assert out.read_text().splitlines() == want and st["reads"] == len(want)
+    # the Python driver prints the same lines
+    import io
+    buf = io.StringIO()
+    pkg.process_reads(fixture_fastq, pa, out=buf)
+    assert buf.getvalue().splitlines() == want
+    # truncated record
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(raw[:raw.index(b"\n", len(raw) // 2) + 1] + b"@broken\nACGT\n")
+    with pytest.raises(pkg.PsaError) as e:
+        pkg.process_reads_file(str(bad), pa, str(out))
+    assert e.value.code == -7
