@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--group-width", type=int, default=0, help="lanes per read in the cooperative kernel (8/16/32; 0 = library default)")
     ap.add_argument("--fast-probes", type=int, default=-1, help="seed positions one thread tries before handing the read over (0: no thread-per-read kernel; -1: library default)")
     ap.add_argument("--fast-max-small", type=int, default=32)
+    ap.add_argument("--scan-width", type=int, default=-1, help="lanes per read of the seed-scan kernel (0: off; -1: library default)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -306,6 +307,8 @@ def main():
         mapper.set_group_width(a.group_width)
     if a.fast_probes >= 0:
         mapper.set_fast_path(a.fast_probes, a.fast_max_small)
+    if a.scan_width >= 0:
+        mapper.set_scan_width(a.scan_width)
     stream = torch.cuda.ExternalStream(mapper.stream(), device=local_rank)
 
     R, L, G = a.reads_per_step, a.read_len, max(1, a.distinct_batches)
@@ -326,7 +329,7 @@ def main():
 
     # events of one batch (untimed): the algorithmic work the roofline is computed from
     ev_split = mapper.map_device_events(dev_batches[0], split=True)
-    ev = {key: ev_split[0][key] + ev_split[1][key] for key in ev_split[0]}
+    ev = {key: sum(part[key] for part in ev_split) for key in ev_split[0]}
     deferred_by = mapper.defer_reasons()
     mapper.counts_reset()
     a_bytes_per_read = algorithmic_bytes(ev, a.k) / ev["reads"]
@@ -409,15 +412,16 @@ def main():
     # the map step is two kernels: k_map_thread (one thread per read) and k_map (cooperative, the reads
     # k_map_thread handed over); each is charged the algorithmic bytes of the reads it completed
     kernels = {}
-    for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1])):
+    for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
         k_ms, k_n = prof[name]
         if not k_n:
             continue
-        per_launch_ms = k_ms / k_n
-        a_bytes = algorithmic_bytes(part, a.k)          # of one batch = one launch
-        kernels[name] = {"ms_per_launch": per_launch_ms, "share_of_step": k_ms / ms if ms else None,
+        per_step_ms = k_ms / a.steps                     # k_map_thread runs twice per step (second pass: seeded reads)
+        a_bytes = algorithmic_bytes(part, a.k)          # of one batch = one step
+        kernels[name] = {"ms_per_launch": per_step_ms, "launches_per_step": k_n / a.steps,
+                         "share_of_step": k_ms / ms if ms else None,
                          "reads_per_launch": part["reads"], "algorithmic_bytes_per_launch": a_bytes,
-                         "achieved_gbs": a_bytes / (per_launch_ms / 1e3) / 1e9}
+                         "achieved_gbs": a_bytes / (per_step_ms / 1e3) / 1e9}
     dom = max(kernels, key=lambda kname: kernels[kname]["ms_per_launch"])
     achieved = kernels[dom]["achieved_gbs"]
     traffic = None

@@ -168,6 +168,12 @@ int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
  * cooperative kernel.  Defaults 3 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
  * not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
+/* Tuning: reads whose FIRST seed search is too long for one thread go to k_seed_scan, where
+ * `lanes` lanes (8, 16 or 32; default 16, PSA_SCAN_WIDTH) probe as many stride-3 positions at
+ * once; a read without any seed ends there, a seeded one returns to the thread-per-read kernel
+ * with the answer.  0: such reads go to the cooperative kernel instead.  Results do not depend
+ * on it. */
+int psa_mapper_set_scan_width(psa_mapper*, uint32_t lanes);
 
 /* Pseudoalign a batch.  For every read i: hits[i] and its members in tx_buf are exactly
  * what `index.map_read(&DnaString::from_dna_string(seq_i))` returns (ref :381-384, :449-462).
@@ -212,9 +218,10 @@ typedef struct psa_events {
     uint64_t aligned;
 } psa_events;
 /* Same as psa_mapper_map on a device batch, with event counting compiled in (slower).
- * out[0]: the reads completed by k_map_thread, out[1]: the reads completed by k_map. */
+ * out[0]: the reads completed by k_map_thread, out[1]: by k_map, out[2]: by k_seed_scan (reads
+ * without a seed) plus the first seed searches it made for reads k_map_thread completed. */
 int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results,
-                          psa_events out[2]);
+                          psa_events out[3]);
 
 /* After psa_mapper_map_events: why k_map_thread handed reads over -- [0] first seed search
  * longer than max_probes, [1] re-seed search longer than max_probes, [2] more than 4
@@ -223,12 +230,12 @@ int psa_mapper_defer_reasons(psa_mapper*, uint64_t out[4]);
 
 /* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
 uint64_t psa_mapper_launch_count(const psa_mapper*);
-/* Device timing of the two map kernels alone: when enabled, every launch is bracketed by
- * CUDA events on the mapper's stream.  psa_mapper_profile_read synchronises, returns the
- * summed kernel time and launch count since the last read ([0] k_map_thread, [1] k_map), and
- * resets them. */
+/* Device timing of the map kernels alone: when enabled, every launch is bracketed by CUDA
+ * events on the mapper's stream.  psa_mapper_profile_read synchronises, returns the summed
+ * kernel time and launch count since the last read ([0] k_map_thread, both passes; [1] k_map;
+ * [2] k_seed_scan), and resets them. */
 int psa_mapper_profile_enable(psa_mapper*, int on);
-int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[2], uint64_t map_launches[2]);
+int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[3], uint64_t map_launches[3]);
 
 /* ------------------------------------------------------------------------------------------
  * process_reads (ref src/pseudoaligner.rs:420-514): FASTQ file (plain or gzip) in, one line per

@@ -441,19 +441,20 @@ struct psa_mapper {
     uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
     cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
     DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, pool, running;
-    DevBuf words, woff, nwords, dst_off, scan_tmp, meta, deferred;
+    DevBuf words, woff, nwords, dst_off, scan_tmp, meta, deferred, scan_list, seeded, seeded_ev;
     uint64_t novel_cap = 0;
     uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
     uint64_t pool_cap = 1ull << 18;   // entries (uint4) of the shared overflow pool; grows on demand
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 3;   // 0: every read goes to the cooperative kernel
     uint32_t fast_max_small = 32;
+    uint32_t scan_width = 16;   // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[2];
     uint64_t launches = 0;
     // map-kernel timing (psa_mapper_profile_*)
     bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];  // [0] k_map_thread, [1] k_map
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];  // [0] k_map_thread, [1] k_map, [2] k_seed_scan
     // pending async call
     psa_result_batch* pending = nullptr;
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
@@ -462,8 +463,31 @@ struct psa_mapper {
 template <bool EV>
 static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p) {
     const unsigned grid = nblocks(p.reads.n, kThreadBlock);
-    if (m->ix->kw == 1) k_map_thread<1, EV><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
-    else k_map_thread<2, EV><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    if (m->ix->kw == 1) k_map_thread<1, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    else k_map_thread<2, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+}
+// second pass over the reads k_seed_scan seeded: persistent warps, the list length is on the device
+template <bool EV>
+static void launch_map_thread_seeded(psa_mapper* m, cudaStream_t st, const MapParams& p) {
+    const unsigned grid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n, kThreadBlock), 148 * PSA_THREAD_MIN_BLOCKS);
+    if (m->ix->kw == 1) k_map_thread<1, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    else k_map_thread<2, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+}
+template <bool EV>
+static void launch_seed_scan(psa_mapper* m, cudaStream_t st, const MapParams& p) {
+    const DevIndex& d = m->ix->d;
+    const unsigned grid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n * m->scan_width, 256), 148 * 4);
+#define PSA_SCAN(KW, G) k_seed_scan<KW, EV, G><<<grid, 256, 0, st>>>(d, p)
+    if (m->ix->kw == 1) {
+        if (m->scan_width == 8) PSA_SCAN(1, 8);
+        else if (m->scan_width == 16) PSA_SCAN(1, 16);
+        else PSA_SCAN(1, 32);
+    } else {
+        if (m->scan_width == 8) PSA_SCAN(2, 8);
+        else if (m->scan_width == 16) PSA_SCAN(2, 16);
+        else PSA_SCAN(2, 32);
+    }
+#undef PSA_SCAN
 }
 
 template <bool EV>
@@ -535,19 +559,23 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     const uint64_t nc = ix->d.n_eq + 2;
     if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
-        (rc = m->novel_cursor.ensure(32)) || (rc = m->events.ensure(28 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
+        (rc = m->novel_cursor.ensure(64)) || (rc = m->events.ensure(40 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
         (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16))) {
         psa_mapper_destroy(m);
         return rc;
     }
     cudaMemset(m->counts.p, 0, nc * 8);
-    cudaMemset(m->events.p, 0, 28 * 8);
+    cudaMemset(m->events.p, 0, 40 * 8);
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
     }
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("PSA_SCAN_WIDTH")) {
+        int g = atoi(e);
+        if (g == 0 || g == 8 || g == 16 || g == 32) m->scan_width = (uint32_t)g;
+    }
     if ((rc = mapper_alloc_spill(m))) {
         psa_mapper_destroy(m);
         return rc;
@@ -563,7 +591,7 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
     if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
     DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
-                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred};
+                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
     for (auto b : bufs) b->release();
     for (int s = 0; s < 2; s++) {
         Slot& S = m->slot[s];
@@ -597,6 +625,12 @@ extern "C" int psa_mapper_set_fast_path(psa_mapper* m, uint32_t max_probes, uint
     if (!m) return fail(PSA_ERR_ARG, "null argument");
     m->fast_probes = max_probes;
     m->fast_max_small = max_small;
+    return PSA_OK;
+}
+extern "C" int psa_mapper_set_scan_width(psa_mapper* m, uint32_t lanes) {
+    if (!m || (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32))
+        return fail(PSA_ERR_ARG, "scan width must be 0, 8, 16 or 32");
+    m->scan_width = lanes;
     return PSA_OK;
 }
 extern "C" void* psa_mapper_stream(psa_mapper* m) { return m ? (void*)m->st : nullptr; }
@@ -669,7 +703,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 32, st));  // [0] novel cursor, [1] pool cursor, [2] deferred reads
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -712,7 +746,20 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             p.list_count = m->novel_cursor.as<unsigned long long>() + 2;
             p.max_probes = m->fast_probes;
             p.max_small = m->fast_max_small;
+            if (m->scan_width) {
+                if ((rc = m->scan_list.ensure(n * 4)) || (rc = m->seeded.ensure(n * sizeof(uint4)))) return rc;
+                if (EV && (rc = m->seeded_ev.ensure(n * sizeof(uint4)))) return rc;
+                p.scan_list = m->scan_list.as<uint32_t>();
+                p.scan_count = m->novel_cursor.as<unsigned long long>() + 3;
+                p.seeded = m->seeded.as<uint4>();
+                p.seeded_count = m->novel_cursor.as<unsigned long long>() + 4;
+                p.seeded_ev = EV ? m->seeded_ev.as<uint4>() : nullptr;
+            }
             if ((rc = timed(0, [&]() { launch_map_thread<EV>(m, st, p); }))) return rc;
+            if (m->scan_width) {
+                if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
+                if ((rc = timed(0, [&]() { launch_map_thread_seeded<EV>(m, st, p); }))) return rc;
+            }
         }
         if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, st, p); }))) return rc;
     }
@@ -982,17 +1029,17 @@ extern "C" int psa_mapper_map_events(psa_mapper* m, const psa_read_batch* r, psa
     if (r->location != PSA_MEM_DEVICE || o->location != PSA_MEM_DEVICE)
         return fail(PSA_ERR_ARG, "psa_mapper_map_events needs device-resident batches");
     CU(cudaSetDevice(m->ix->device));
-    CU(cudaMemsetAsync(m->events.p, 0, 28 * 8, m->st));
+    CU(cudaMemsetAsync(m->events.p, 0, 40 * 8, m->st));
     if ((rc = map_device_sync<true>(m, r, o))) return rc;
     static_assert(sizeof(psa_events) == 12 * 8, "psa_events layout");
-    CU(cudaMemcpy(out, m->events.p, 2 * sizeof(psa_events), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, m->events.p, 3 * sizeof(psa_events), cudaMemcpyDeviceToHost));
     return PSA_OK;
 }
 
 extern "C" int psa_mapper_defer_reasons(psa_mapper* m, uint64_t out[4]) {
     if (!m || !out) return fail(PSA_ERR_ARG, "null argument");
     CU(cudaSetDevice(m->ix->device));
-    CU(cudaMemcpy(out, m->events.as<uint64_t>() + 24, 4 * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, m->events.as<uint64_t>() + 36, 4 * 8, cudaMemcpyDeviceToHost));
     return PSA_OK;
 }
 
@@ -1028,11 +1075,11 @@ extern "C" int psa_mapper_profile_enable(psa_mapper* m, int on) {
     m->profiling = on != 0;
     return PSA_OK;
 }
-extern "C" int psa_mapper_profile_read(psa_mapper* m, double map_kernel_ms[2], uint64_t map_launches[2]) {
+extern "C" int psa_mapper_profile_read(psa_mapper* m, double map_kernel_ms[3], uint64_t map_launches[3]) {
     if (!m || !map_kernel_ms || !map_launches) return fail(PSA_ERR_ARG, "null argument");
     CU(cudaSetDevice(m->ix->device));
     CU(cudaStreamSynchronize(m->st));
-    for (int w = 0; w < 2; w++) {
+    for (int w = 0; w < 3; w++) {
         double ms = 0;
         for (auto& pr : m->prof_events[w]) {
             float t = 0;

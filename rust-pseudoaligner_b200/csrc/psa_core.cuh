@@ -690,10 +690,14 @@ struct ThreadCtx {
     bool defer;
     uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
     bool seeded;
+    // answer of the read's first seed search when k_seed_scan has already made it
+    bool has_hint;
+    uint32_t hint_pos, hint_node, hint_off;
     ThreadEvents ev;
 
     PSA_HD ThreadCtx(const DevIndex& ix_, const uint64_t* words, uint32_t max_probes_)
-        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false), ev{} {
+        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false),
+          has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
     PSA_UNROLL
         for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; }
     }
@@ -703,6 +707,14 @@ struct ThreadCtx {
     // find_kmer_match, ref src/pseudoaligner.rs:91-114, at most max_probes positions
     PSA_HD bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& o) {
         if (kmer_pos > last) return false;
+        if (has_hint) {  // the first search of the read (it starts at 0), done by k_seed_scan
+            has_hint = false;
+            kmer_pos = hint_pos;
+            node = hint_node;
+            o = hint_off;
+            seeded = true;
+            return true;
+        }
         const uint64_t start = kmer_pos;
         uint64_t p = start;
         for (uint32_t probes = 0;; probes++, p += kSeedStride) {
@@ -852,13 +864,17 @@ struct ThreadResult {
 template <int KW, bool EV, class NovelAlloc>
 PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, uint32_t L, uint32_t allowed,
                                     uint32_t max_probes, uint32_t max_small, NovelAlloc& novel, bool want_members,
-                                    ThreadEvents* ev_out) {
+                                    ThreadEvents* ev_out, const uint32_t* hint = nullptr /* pos, node, off */) {
     ThreadResult res;
     res.hit.coverage = 0; res.hit.n_tx = 0; res.hit.tx_off = 0; res.hit.eq_id = kNone; res.hit.flags = 0;
     res.count_slot = ix.n_eq + 1;
     res.deferred = false;
     res.novel_overflow = false;
     ThreadCtx<KW, EV> w(ix, words, max_probes);
+    if (hint) {
+        w.has_hint = true;
+        w.hint_pos = hint[0]; w.hint_node = hint[1]; w.hint_off = hint[2];
+    }
     uint32_t coverage = 0;
     bool some = map_read_nodes(w, ix.k, (uint64_t)L, allowed, coverage);
     res.why = w.why;

@@ -295,10 +295,17 @@ struct MapParams {
     // deferred reads: written by k_map_thread, consumed by k_map (list != nullptr: map list[0..*list_count))
     uint32_t* list;
     unsigned long long* list_count;
+    // reads whose FIRST seed search was too long for one thread: k_map_thread -> k_seed_scan
+    uint32_t* scan_list;
+    unsigned long long* scan_count;
+    // reads k_seed_scan found a seed for: {read, pos, node, off} -> second pass of k_map_thread
+    uint4* seeded;
+    unsigned long long* seeded_count;
+    uint4* seeded_ev;             // event counting only: {lookups, levels, hits, verifs} of that search
     uint32_t max_probes;          // k_map_thread: seed positions one thread tries per search
     uint32_t max_small;           // k_map_thread: largest smallest-class one thread intersects
     uint32_t* status;             // bit0: novel buffer overflow, bit1: spill pool overflow
-    unsigned long long* events;   // 2 x psa_events layout ([0] k_map_thread, [1] k_map), or nullptr
+    unsigned long long* events;   // 3 x psa_events layout ([0] k_map_thread, [1] k_map, [2] k_seed_scan), or nullptr
 };
 
 struct LaneEvents {
@@ -718,53 +725,127 @@ constexpr int kThreadBlock = 128;
 #define PSA_THREAD_MIN_BLOCKS 8
 #endif
 
-template <int KW, bool EV>
+// HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
+// first seed search was made by k_seed_scan), persistent warps striding over that list.
+template <int KW, bool EV, bool HINT>
 __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
-                                                             const __grid_constant__ MapParams p) {
-    const uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const bool live = r < p.reads.n;
-    bool defer = false;
-    ThreadEvents ev{};
-    uint32_t L = 0, n_tx = 0, aligned = 0;
-    if (live) {
-        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
-        L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-        DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
-        ThreadResult res = map_read_thread<KW, EV>(ix, p.reads.words + wo, L, p.allowed_mismatches, p.max_probes,
-                                                   p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr);
-        defer = res.deferred;
-        if (EV && defer && p.events) atomicAdd(p.events + 24 + res.why, 1ULL);
-        if (!defer) {
-            // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
-            uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
-            out[0] = (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32);
-            out[1] = res.hit.tx_off;
-            out[2] = (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32);
-            if (p.counts) atomicAdd(p.counts + res.count_slot, 1ULL);
-            if (res.novel_overflow) atomicOr(p.status, 1u);
-            n_tx = res.hit.n_tx;
-            aligned = res.hit.flags & kFlagAligned;
+                                                                                     const __grid_constant__ MapParams p) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
+    const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
+    // warp-uniform trip count: the hand-over below uses full-warp votes
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); base < n_todo; base += stride) {
+        const uint64_t it = base + lane;
+        const bool live = it < n_todo;
+        bool defer = false;
+        uint32_t why = 0;
+        uint64_t r = it;
+        ThreadEvents ev{};
+        uint4 sev = make_uint4(0, 0, 0, 0);
+        uint32_t L = 0, n_tx = 0, aligned = 0;
+        if (live) {
+            uint32_t hint[3];
+            if (HINT) {
+                const uint4 e = p.seeded[it];
+                r = e.x;
+                hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
+                if (EV) sev = p.seeded_ev[it];
+            }
+            const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+            L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+            DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
+            ThreadResult res = map_read_thread<KW, EV>(ix, p.reads.words + wo, L, p.allowed_mismatches, p.max_probes,
+                                                       p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
+                                                       HINT ? hint : nullptr);
+            defer = res.deferred;
+            why = res.why;
+            if (EV && defer && p.events) atomicAdd(p.events + 36 + res.why, 1ULL);
+            if (!defer) {
+                // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
+                uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
+                out[0] = (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32);
+                out[1] = res.hit.tx_off;
+                out[2] = (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32);
+                if (p.counts) atomicAdd(p.counts + res.count_slot, 1ULL);
+                if (res.novel_overflow) atomicOr(p.status, 1u);
+                n_tx = res.hit.n_tx;
+                aligned = res.hit.flags & kFlagAligned;
+            } else if (EV && HINT && p.events) {
+                // k_map redoes this read from scratch and counts its first search again
+                atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
+                atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
+            }
+        }
+        // hand the given-up reads over (one atomic per warp and list): a too long FIRST seed search
+        // goes to k_seed_scan, everything else to the cooperative kernel
+        const bool to_scan = defer && !HINT && why == 0 && p.scan_list != nullptr;
+        const unsigned bs = __ballot_sync(kFull, to_scan);
+        if (bs) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(bs) - 1)) at = atomicAdd(p.scan_count, (unsigned long long)__popc(bs));
+            at = __shfl_sync(kFull, at, __ffs(bs) - 1);
+            if (to_scan) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = (uint32_t)r;
+        }
+        const bool to_coop = defer && !to_scan;
+        const unsigned bc = __ballot_sync(kFull, to_coop);
+        if (bc) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(bc) - 1)) at = atomicAdd(p.list_count, (unsigned long long)__popc(bc));
+            at = __shfl_sync(kFull, at, __ffs(bc) - 1);
+            if (to_coop) p.list[at + __popc(bc & ((1u << lane) - 1))] = (uint32_t)r;
+        }
+        if (EV && p.events) {
+            const bool cnt = live && !defer;
+            unsigned long long v[12] = {cnt ? 1ull : 0ull, cnt ? L : 0ull, ev.lookups, ev.levels, ev.hits, ev.verifs,
+                                        ev.visits, ev.bases, ev.jumps, ev.members, n_tx, aligned};
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                unsigned long long x = cnt ? v[i] : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+                if (lane == 0 && x) atomicAdd(p.events + i, x);
+            }
         }
     }
-    // hand the given-up reads to the cooperative kernel (one atomic per warp)
-    const unsigned b = __ballot_sync(kFull, defer);
-    if (b) {
-        const unsigned lane = threadIdx.x & 31;
-        unsigned long long base = 0;
-        if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(p.list_count, (unsigned long long)__popc(b));
-        base = __shfl_sync(kFull, base, __ffs(b) - 1);
-        if (defer) p.list[base + __popc(b & ((1u << lane) - 1))] = (uint32_t)r;
-    }
-    if (EV && p.events) {
-        const bool cnt = live && !defer;
-        unsigned long long v[12] = {cnt ? 1ull : 0ull, cnt ? L : 0ull, ev.lookups, ev.levels, ev.hits, ev.verifs,
-                                    ev.visits, ev.bases, ev.jumps, ev.members, n_tx, aligned};
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            unsigned long long x = cnt ? v[i] : 0ull;
-#pragma unroll
-            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
-            if ((threadIdx.x & 31) == 0 && x) atomicAdd(p.events + i, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seed_scan: the first seed search (find_kmer_match from position 0, ref :91-114) of the reads
+// whose search was too long for one thread, G lanes probing G stride-3 positions at once.  A read
+// with no seed at all is finished here (map_read = None); a seeded one goes back to the
+// thread-per-read kernel with the answer.
+// ---------------------------------------------------------------------------------------------
+template <int KW, bool EV, int G>
+__global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIndex ix, const __grid_constant__ MapParams p) {
+    const uint64_t gid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) / G;
+    const uint64_t ngroups = (gridDim.x * (uint64_t)blockDim.x) / G;
+    const uint64_t n_todo = (uint64_t)*p.scan_count;
+    for (uint64_t it = gid; it < n_todo; it += ngroups) {
+        const uint64_t r = p.scan_list[it];
+        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+        const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;  // >= k: shorter reads never search
+        WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
+        uint64_t kmer_pos = 0;
+        uint32_t node = 0, off = 0;
+        const bool found = w.find_seed(kmer_pos, (uint64_t)L - ix.k, node, off);
+        if (w.lane == 0) {
+            if (found) {
+                const unsigned long long at = atomicAdd(p.seeded_count, 1ULL);
+                p.seeded[at] = make_uint4((uint32_t)r, (uint32_t)kmer_pos, node, off);
+                if (EV) p.seeded_ev[at] = make_uint4(w.ev.lookups, w.ev.levels, w.ev.hits, w.ev.verifs);
+            } else {
+                uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
+                out[0] = 0;
+                out[1] = 0;
+                out[2] = (uint64_t)kNone;  // eq_id = none, flags = 0
+                if (p.counts) atomicAdd(p.counts + ix.n_eq + 1, 1ULL);
+            }
+            if (EV && p.events) {
+                unsigned long long* e = p.events + 24;
+                if (!found) { atomicAdd(e + 0, 1ULL); atomicAdd(e + 1, (unsigned long long)L); }
+                atomicAdd(e + 2, (unsigned long long)w.ev.lookups); atomicAdd(e + 3, (unsigned long long)w.ev.levels);
+                atomicAdd(e + 4, (unsigned long long)w.ev.hits); atomicAdd(e + 5, (unsigned long long)w.ev.verifs);
+            }
         }
     }
 }

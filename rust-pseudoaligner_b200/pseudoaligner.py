@@ -75,7 +75,7 @@ EXPORTS = (
     "psa_strerror", "psa_last_error", "psa_abi_version",
     "psa_index_create", "psa_index_destroy", "psa_index_get_info", "psa_index_lookup",
     "psa_mapper_create", "psa_mapper_destroy", "psa_mapper_set_allowed_mismatches", "psa_mapper_set_group_width",
-    "psa_mapper_set_fast_path",
+    "psa_mapper_set_fast_path", "psa_mapper_set_scan_width",
     "psa_mapper_map", "psa_mapper_map_async", "psa_mapper_sync", "psa_mapper_stream",
     "psa_mapper_map_read", "psa_mapper_counts_get", "psa_mapper_counts_reset",
     "psa_mapper_counts_device", "psa_mapper_map_events", "psa_mapper_defer_reasons", "psa_mapper_launch_count",
@@ -119,11 +119,12 @@ def lib():
     L.psa_mapper_set_allowed_mismatches.argtypes = [vp, u32]
     L.psa_mapper_set_group_width.restype, L.psa_mapper_set_group_width.argtypes = i32, [vp, u32]
     L.psa_mapper_set_fast_path.restype, L.psa_mapper_set_fast_path.argtypes = i32, [vp, u32, u32]
+    L.psa_mapper_set_scan_width.restype, L.psa_mapper_set_scan_width.argtypes = i32, [vp, u32]
     for name in ("psa_mapper_map", "psa_mapper_map_async"):
         f = getattr(L, name)
         f.restype, f.argtypes = i32, [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch)]
     L.psa_mapper_map_events.restype = i32
-    L.psa_mapper_map_events.argtypes = [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch), C.POINTER(_Events * 2)]
+    L.psa_mapper_map_events.argtypes = [vp, C.POINTER(_ReadBatch), C.POINTER(_ResultBatch), C.POINTER(_Events * 3)]
     L.psa_mapper_defer_reasons.restype, L.psa_mapper_defer_reasons.argtypes = i32, [vp, C.POINTER(u64 * 4)]
     L.psa_mapper_sync.restype, L.psa_mapper_sync.argtypes = i32, [vp]
     L.psa_mapper_stream.restype, L.psa_mapper_stream.argtypes = vp, [vp]
@@ -135,7 +136,7 @@ def lib():
     L.psa_mapper_launch_count.restype, L.psa_mapper_launch_count.argtypes = u64, [vp]
     L.psa_mapper_profile_enable.restype, L.psa_mapper_profile_enable.argtypes = i32, [vp, i32]
     L.psa_mapper_profile_read.restype = i32
-    L.psa_mapper_profile_read.argtypes = [vp, C.POINTER(C.c_double * 2), C.POINTER(u64 * 2)]
+    L.psa_mapper_profile_read.argtypes = [vp, C.POINTER(C.c_double * 3), C.POINTER(u64 * 3)]
     L.psa_comm_unique_id.restype, L.psa_comm_unique_id.argtypes = i32, [vp]
     L.psa_comm_create.restype, L.psa_comm_create.argtypes = i32, [vp, i32, i32, i32, C.POINTER(vp)]
     L.psa_comm_destroy.restype, L.psa_comm_destroy.argtypes = None, [vp]
@@ -397,13 +398,13 @@ class Mapper:
         _check(lib().psa_mapper_sync(self.h))
 
     def map_device_events(self, batch, split=False):
-        """Event counts of one batch; split=True -> (k_map_thread's reads, k_map's reads)."""
-        ev = (_Events * 2)()
+        """Event counts of one batch; split=True -> per kernel (k_map_thread, k_map, k_seed_scan)."""
+        ev = (_Events * 3)()
         _check(lib().psa_mapper_map_events(self.h, C.byref(batch.rb), C.byref(batch.ob), C.byref(ev)))
         parts = [{f: int(getattr(e, f)) for f in EVENT_FIELDS} for e in ev]
         if split:
             return parts
-        return {f: parts[0][f] + parts[1][f] for f in EVENT_FIELDS}
+        return {f: sum(p[f] for p in parts) for f in EVENT_FIELDS}
 
     def defer_reasons(self):
         out = (C.c_uint64 * 4)()
@@ -451,11 +452,15 @@ class Mapper:
     def set_fast_path(self, max_probes, max_small=32):
         _check(lib().psa_mapper_set_fast_path(self.h, int(max_probes), int(max_small)))
 
+    def set_scan_width(self, lanes):
+        _check(lib().psa_mapper_set_scan_width(self.h, int(lanes)))
+
     def profile_read(self):
         """-> {kernel: (summed device ms, launches)} since the last read."""
-        ms, n = (C.c_double * 2)(), (C.c_uint64 * 2)()
+        ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
         _check(lib().psa_mapper_profile_read(self.h, C.byref(ms), C.byref(n)))
-        return {"k_map_thread": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1]))}
+        return {"k_map_thread": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1])),
+                "k_seed_scan": (float(ms[2]), int(n[2]))}
 
     def close(self):
         if getattr(self, "h", None):

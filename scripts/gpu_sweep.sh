@@ -5,10 +5,10 @@ timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
 : > gpurun_out/sweep.jsonl
-SWEEP=${SWEEP:-0:8 1:8 2:8 3:8 4:8 8:8 3:16 3:32}
+SWEEP=${SWEEP:-0:8:16 1:8:16 2:8:16 3:8:16 3:8:0 1:8:32 2:8:32 1:8:8}
 for cfg in $SWEEP; do
-  p=${cfg%%:*}; g=${cfg##*:}
-  timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --fast-probes $p --group-width $g $SWEEP_ARGS >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err
+  IFS=: read p g sw <<< "$cfg"
+  timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --fast-probes $p --group-width $g --scan-width ${sw:-16} $SWEEP_ARGS >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err
 done
 python - <<'PY'
 import json

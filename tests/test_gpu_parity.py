@@ -91,13 +91,17 @@ def test_parity_fixture_read_sets(pa_for, orc_index_for, fixture_fasta, k, lengt
         want_hits, want_tx, _, _ = _oracle(ix, reads)
         # tuning knobs that must not change results: lanes per read of the cooperative kernel,
         # and how much the thread-per-read kernel keeps for itself (0 probes = it is skipped)
-        for lanes, probes, max_small in ((8, 0, 0), (16, 1, 4), (32, 3, 32), (8, 64, 1 << 30)):
+        # and the lanes of the seed-scan kernel (0 = long first searches go to the cooperative kernel)
+        for lanes, probes, max_small, scan in ((8, 0, 0, 16), (16, 1, 4, 8), (32, 3, 32, 0), (8, 64, 1 << 30, 32),
+                                               (8, 1, 32, 32), (8, 2, 32, 16)):
             pa.mapper.set_group_width(lanes)
             pa.mapper.set_fast_path(probes, max_small)
+            pa.mapper.set_scan_width(scan)
             got_hits, got_tx = pa.mapper.map_ascii(reads)
             _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     pa.mapper.set_group_width(8)
     pa.mapper.set_fast_path(3, 32)
+    pa.mapper.set_scan_width(16)
 
 
 def test_small_fq(pa_for, orc_index_for, fixture_fastq):
@@ -166,13 +170,16 @@ def test_device_batch_and_events(orc_index_for, fixture_fasta):
     got_hits, got_tx = b.download()
     _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     assert np.array_equal(pa.mapper.counts(), want_counts)
-    for probes in (0, 1, 3, 64):
+    for probes, scan in ((0, 16), (1, 0), (1, 8), (3, 16), (3, 32), (64, 16)):
         pa.mapper.set_fast_path(probes, 32)
+        pa.mapper.set_scan_width(scan)
         parts = pa.mapper.map_device_events(b, split=True)
-        ev = {key: parts[0][key] + parts[1][key] for key in parts[0]}
+        ev = {key: sum(p[key] for p in parts) for key in parts[0]}
         assert (parts[0]["reads"] == 0) == (probes == 0) and parts[1]["reads"] > 0
+        assert (parts[2]["kmer_lookups"] > 0) == (scan > 0 and 0 < probes < 64)
         _check_events(ev, want_ev)
     pa.mapper.set_fast_path(3, 32)
+    pa.mapper.set_scan_width(16)
     ev = pa.mapper.map_device_events(b)
     _check_events(ev, want_ev)
     # packed device batch
@@ -278,9 +285,10 @@ def test_wide_classes(fixture_fasta):
     pa = pkg.Pseudoaligner(ix.flat(), device=0)
     for name, reads in cases.read_sets(rng, seqs, 150, 20, scale=1.0).items():
         want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
-        for lanes, probes, max_small in ((8, 0, 0), (16, 3, 2), (32, 64, 1 << 30)):
+        for lanes, probes, max_small, scan in ((8, 0, 0, 16), (16, 3, 2, 0), (32, 64, 1 << 30, 8), (8, 1, 32, 32)):
             pa.mapper.set_group_width(lanes)
             pa.mapper.set_fast_path(probes, max_small)
+            pa.mapper.set_scan_width(scan)
             got_hits, got_tx = pa.mapper.map_ascii(reads)
             _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
     pa.close()
