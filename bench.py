@@ -452,7 +452,7 @@ def main():
                        "input": "ASCII reads resident in HBM; each step packs, maps, scans and expands one batch",
                        "l2": "inputs larger than L2 (%.0f MB per batch, %d distinct batches rotated; index %.0f MB)" % (
                            R * L / 1e6, G, (info["mphf_bytes"] + info["values_bytes"] + info["node_bytes"]
-                                            + info["seq_bytes"] + info["eq_bytes"]) / 1e6),
+                                            + info["seq_bytes"] + info["eq_bytes"] + info["bloom_bytes"]) / 1e6),
                        "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
                                                                   "mphf_levels", "fp_bits", "max_class_len")},
                        "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",

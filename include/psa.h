@@ -83,7 +83,7 @@ typedef struct psa_index_info {
     uint32_t k;
     uint32_t mphf_levels;
     uint64_t n_nodes, n_kmers, n_eq, n_eq_members, n_seq_words;
-    uint64_t mphf_bytes, values_bytes, node_bytes, seq_bytes, eq_bytes; /* device residency */
+    uint64_t mphf_bytes, values_bytes, node_bytes, seq_bytes, eq_bytes, bloom_bytes; /* device residency */
     uint32_t node_bits, off_bits, fp_bits; /* packing of one `values` entry               */
     uint32_t max_class_len;
     double gamma;
@@ -165,11 +165,11 @@ int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
  * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
  * needs more than max_probes positions, it visits more than 4 distinct classes, or its
  * smallest class has more than max_small members.  max_probes = 0 sends every read to the
- * cooperative kernel.  Defaults 3 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
+ * cooperative kernel.  Defaults 2 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
  * not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
 /* Tuning: reads whose FIRST seed search is too long for one thread go to k_seed_scan, where
- * `lanes` lanes (8, 16 or 32; default 16, PSA_SCAN_WIDTH) probe as many stride-3 positions at
+ * `lanes` lanes (8, 16 or 32; default 8, PSA_SCAN_WIDTH) probe as many stride-3 positions at
  * once; a read without any seed ends there, a seeded one returns to the thread-per-read kernel
  * with the answer.  0: such reads go to the cooperative kernel instead.  Results do not depend
  * on it. */

@@ -89,7 +89,7 @@ struct DevBuf {
 struct psa_index {
     int device = 0;
     DevIndex d{};
-    DevBuf blocks, values, nodes, seq, eq_off, eq_mem, class_win;
+    DevBuf blocks, values, nodes, seq, eq_off, eq_mem, class_win, bloom;
     psa_index_info info{};
     int kw = 1;
 };
@@ -144,6 +144,19 @@ static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma,
             key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(), val[0].as<uint64_t>());
     CUB_(cudaGetLastError());
 
+    // 1b. absent-key prefilter
+    {
+        const uint64_t nb = std::max<uint64_t>(1, (n_kmers * kBloomBitsPerKey + 255) / 256);
+        RC_(ix->bloom.ensure(nb * 32));
+        CUB_(cudaMemsetAsync(ix->bloom.p, 0, nb * 32, st));
+        Bloom b{ix->bloom.as<uint32_t>(), nb};
+        if (n_kmers)
+            k_bloom_set<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(),
+                                                                    n_kmers, b, ix->bloom.as<uint32_t>());
+        CUB_(cudaGetLastError());
+        ix->d.bloom = b;
+        ix->info.bloom_bytes = nb * 32;
+    }
     // 2. cascade of bit-vector levels (boomphf's construction, on the device)
     std::vector<uint64_t> lvl_nblk, lvl_base;
     uint64_t total_blk = 0;
@@ -388,7 +401,7 @@ extern "C" void psa_index_destroy(psa_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     ix->blocks.release(); ix->values.release(); ix->nodes.release();
-    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
+    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release(); ix->bloom.release();
     delete ix;
 }
 
@@ -446,9 +459,9 @@ struct psa_mapper {
     uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
     uint64_t pool_cap = 1ull << 18;   // entries (uint4) of the shared overflow pool; grows on demand
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
-    uint32_t fast_probes = 3;   // 0: every read goes to the cooperative kernel
+    uint32_t fast_probes = 2;   // 0: every read goes to the cooperative kernel
     uint32_t fast_max_small = 32;
-    uint32_t scan_width = 16;   // lanes per read of k_seed_scan (0: long first searches go to k_map)
+    uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[2];
     uint64_t launches = 0;

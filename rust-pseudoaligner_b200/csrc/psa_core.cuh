@@ -217,6 +217,17 @@ struct Mphf {
     uint64_t level_base[kMaxLevels];  // first block of the level
 };
 
+// Absent-key prefilter: a split-block Bloom filter over every k-mer of the graph.  One 32-byte
+// block per key, one bit in each of its eight 32-bit words.  No false negatives, so consulting it
+// before the MPHF never changes dict_get's answer; it lets a seed scan drop an absent k-mer after
+// one sector instead of ~3 MPHF levels + the `values` sector.  (Not part of the reference: boomphf
+// has nothing comparable; it pays off because unmappable reads probe 43 absent k-mers each.)
+struct Bloom {
+    const uint32_t* words;  // 8 per block; nullptr = no filter
+    uint64_t n_blocks;
+};
+constexpr uint32_t kBloomBitsPerKey = 12;
+
 struct DevIndex {
     uint32_t k;
     uint32_t node_bits, off_bits, fp_bits;  // `values` entry = node | off << node_bits | fp << (node_bits+off_bits)
@@ -227,6 +238,7 @@ struct DevIndex {
     const uint64_t* eq_off;
     const uint32_t* eq_mem;
     const struct ClassWin* class_win;  // one 32-byte window per class (see below)
+    Bloom bloom;
     Mphf mphf;
 };
 
@@ -243,6 +255,29 @@ PSA_HD KeyHash make_hash(uint64_t folded) {
 }
 PSA_HD uint64_t level_hash(KeyHash kh, uint32_t lvl) { return kh.h1 + (uint64_t)lvl * kh.h2; }
 PSA_HD uint64_t fp_of(KeyHash kh, uint32_t fp_bits) { return kh.h2 >> (64 - fp_bits); }
+
+// Bloom position of a key: block, and eight 5-bit in-word positions packed in `bits`
+PSA_HD void bloom_pos(KeyHash kh, uint64_t n_blocks, uint64_t& blk, uint64_t& bits) {
+    const uint64_t g = kh.h1 * 0x9E3779B97F4A7C15ULL + kh.h2;
+    blk = mulhi64(g, n_blocks);
+    bits = g * 0xD6E8FEB86659FD93ULL >> 24;  // 40 bits
+}
+PSA_HD bool bloom_maybe(const Bloom& b, KeyHash kh) {
+    uint64_t blk, bits;
+    bloom_pos(kh, b.n_blocks, blk, bits);
+    uint32_t w[8];
+#ifdef __CUDA_ARCH__
+    const uint4* p = reinterpret_cast<const uint4*>(b.words + 8 * blk);
+    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = b.words[8 * blk + i];
+#endif
+    uint32_t all = 1;
+    PSA_UNROLL
+    for (int i = 0; i < 8; i++) all &= w[i] >> ((bits >> (5 * i)) & 31);
+    return all & 1;
+}
 
 // position of a key at a level: (block within level, bit 0..191 within block); nblk < 2^32
 PSA_HD void level_pos(uint64_t h, uint64_t nblk, uint64_t& blk, uint32_t& bit) {
@@ -310,9 +345,12 @@ PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, KeyH
 // dbg_index.get(kmer) followed by the reference's verification (src/pseudoaligner.rs:96-107).
 // A fingerprint mismatch proves the slot's key differs from `key`, so skipping the unitig
 // fetch cannot change the outcome of the reference's `read_kmer == ref_kmer` test.
+// prefilter: ask the Bloom filter first (callers do when the key is likely absent).
 template <int KW>
-PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st) {
+PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st,
+                     bool prefilter = false) {
     KeyHash hk = make_hash(KmerOps<KW>::fold(key));
+    if (prefilter && ix.bloom.words && !bloom_maybe(ix.bloom, hk)) return false;
     uint64_t slot;
     uint32_t levels;
     bool in = mphf_lookup(ix.mphf, hk, slot, levels);
@@ -729,7 +767,9 @@ struct ThreadCtx {
                 return false;
             }
             ProbeStats st;
-            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr);
+            // after a miss the next positions are likely absent too: Bloom first (never when counting
+            // events, which are defined on the MPHF path)
+            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr, !EV && probes > 0);
             if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) {
                 kmer_pos = p;

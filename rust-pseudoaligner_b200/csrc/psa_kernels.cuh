@@ -138,6 +138,17 @@ __global__ void k_block_headers(uint64_t* blocks, uint64_t nblk, const uint64_t*
     blocks[4 * i] = make_header(rank_excl[i], c1, c2);
 }
 
+// absent-key prefilter (psa_core.cuh Bloom): every key sets one bit in each word of its block
+template <int KW>
+__global__ void k_bloom_set(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t n, Bloom b, uint32_t* words) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t blk, bits;
+    bloom_pos(key_hash_at<KW>(key_lo, key_hi, i), b.n_blocks, blk, bits);
+#pragma unroll
+    for (int w = 0; w < 8; w++) atomicOr(words + 8 * blk + w, 1u << ((bits >> (5 * w)) & 31));
+}
+
 // values[mphf(kmer)] = (node, offset) -- ref src/build_index.rs:200-220
 template <int KW>
 __global__ void k_fill_values(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n,
@@ -350,13 +361,14 @@ struct WarpCtx {
     unsigned long long pool_cap;
     unsigned long long* pool_cursor;
     uint32_t read_len;
+    bool scan_mode;
     LaneEvents ev;
 
     __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint32_t read_len_,
                                        const MapParams& p, uint64_t group_id)
         : ix(ix_), rd{read_words}, g(), lane(g.lane), k(ix_.k), my_eq(kNone), my_len(0), n_list(0), my_off(0),
           spill(p.spill + group_id * p.spill_cap), spill_cap(p.spill_cap), spill_overflow(false), pool(p.pool),
-          pool_cap(p.pool_cap), pool_cursor(p.pool_cursor), read_len(read_len_), ev{} {}
+          pool_cap(p.pool_cap), pool_cursor(p.pool_cursor), read_len(read_len_), scan_mode(false), ev{} {}
 
     __device__ __forceinline__ uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
     __device__ __forceinline__ bool abort() const { return false; }
@@ -368,21 +380,23 @@ struct WarpCtx {
     __device__ __forceinline__ bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
         if (kmer_pos > last) return false;
         ProbeStats st;
-        {
+        const uint64_t start = kmer_pos;
+        uint64_t first = start;
+        if (!scan_mode) {  // (k_seed_scan's reads have already missed here: all lanes speculate from `start`)
             Kmer<KW> key = KmerOps<KW>::get(rd, kmer_pos, k);
             bool hit = dict_get<KW>(ix, key, node, off, EV ? &st : nullptr);
             if (EV && lane == 0) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) return true;
+            first = start + kSeedStride;
         }
-        const uint64_t start = kmer_pos;
-        for (uint64_t cur = start + kSeedStride; cur <= last; cur += G * kSeedStride) {
+        for (uint64_t cur = first; cur <= last; cur += G * kSeedStride) {
             uint64_t p = cur + (uint64_t)kSeedStride * lane;
             bool h = false;
             uint32_t n = 0, o = 0;
             st.levels = st.hit = st.verified = 0;
             if (p <= last) {
                 Kmer<KW> key = KmerOps<KW>::get(rd, p, k);
-                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
+                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr, !EV);  // speculative positions: Bloom first
             }
             unsigned b = g.ballot(h);
             int j = b ? (__ffs(b) - 1) : G;
@@ -825,6 +839,7 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
         const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;  // >= k: shorter reads never search
         WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
+        w.scan_mode = true;
         uint64_t kmer_pos = 0;
         uint32_t node = 0, off = 0;
         const bool found = w.find_seed(kmer_pos, (uint64_t)L - ix.k, node, off);

@@ -46,7 +46,7 @@ class _IndexInfo(C.Structure):
                 ("n_nodes", C.c_uint64), ("n_kmers", C.c_uint64), ("n_eq", C.c_uint64),
                 ("n_eq_members", C.c_uint64), ("n_seq_words", C.c_uint64),
                 ("mphf_bytes", C.c_uint64), ("values_bytes", C.c_uint64), ("node_bytes", C.c_uint64),
-                ("seq_bytes", C.c_uint64), ("eq_bytes", C.c_uint64),
+                ("seq_bytes", C.c_uint64), ("eq_bytes", C.c_uint64), ("bloom_bytes", C.c_uint64),
                 ("node_bits", C.c_uint32), ("off_bits", C.c_uint32), ("fp_bits", C.c_uint32),
                 ("max_class_len", C.c_uint32), ("gamma", C.c_double), ("build_ms", C.c_double)]
 

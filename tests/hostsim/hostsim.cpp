@@ -26,6 +26,7 @@ struct HsIndex {
     std::vector<NodeRec> nodes;
     std::vector<uint32_t> eq_mem;
     std::vector<ClassWin> class_win;
+    std::vector<uint32_t> bloom;
     int kw = 1;
     int error = 0;
 };
@@ -64,6 +65,17 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     // cascade
     std::vector<KeyHash> rem_h(n_kmers);
     for (uint64_t i = 0; i < n_kmers; i++) rem_h[i] = make_hash(KmerOps<KW>::fold(keys[i]));
+    // absent-key prefilter, same layout rule as the device builder
+    {
+        const uint64_t nb = std::max<uint64_t>(1, (n_kmers * kBloomBitsPerKey + 255) / 256);
+        ix->bloom.assign(8 * nb, 0);
+        for (uint64_t i = 0; i < n_kmers; i++) {
+            uint64_t blk, bits;
+            bloom_pos(rem_h[i], nb, blk, bits);
+            for (int w = 0; w < 8; w++) ix->bloom[8 * blk + w] |= 1u << ((bits >> (5 * w)) & 31);
+        }
+        D.bloom = Bloom{ix->bloom.data(), nb};
+    }
     std::vector<KeyHash> cur = rem_h;
     uint64_t total_blk = 0;
     uint32_t lvl = 0;
@@ -154,7 +166,7 @@ struct SerialWarp {
         // lane order == position order, so the first hitting lane is the sequential first hit
         for (uint64_t p = start; p <= last; p += kSeedStride) {
             lookups++;
-            if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr)) { kmer_pos = p; return true; }
+            if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr, p != start)) { kmer_pos = p; return true; }
         }
         kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);
         return false;
