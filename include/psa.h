@@ -84,7 +84,7 @@ typedef struct psa_index_info {
     uint32_t mphf_levels;
     uint64_t n_nodes, n_kmers, n_eq, n_eq_members, n_seq_words;
     uint64_t mphf_bytes, values_bytes, node_bytes, seq_bytes, eq_bytes, bloom_bytes; /* device residency */
-    uint32_t node_bits, off_bits, fp_bits; /* packing of one `values` entry               */
+    uint32_t node_bits, pos_bits, fp_bits; /* packing of one `values` entry               */
     uint32_t max_class_len;
     double gamma;
     double build_ms; /* device time of the MPHF/edge build                                  */
@@ -264,6 +264,12 @@ int psa_comm_create(const uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES], int world, int r
 void psa_comm_destroy(psa_comm*);
 /* ncclAllReduce(sum, uint64, n_eq+2) in place on the mapper's counts, on its stream. */
 int psa_mapper_counts_allreduce(psa_mapper*, psa_comm*);
+
+/* ---- measurement aid: GB/s of independent random gathers of chunk_bytes-sized (32, 64 or 128)
+ * aligned chunks from a table_bytes table in HBM, one chunk per thread -- the access pattern of
+ * the index lookups without their dependencies; the practical ceiling the map kernels are
+ * compared with.  chunk_bytes = 0: one random 128-byte line per warp (4 bytes per lane). ---- */
+int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s);
 
 /* ---- pinned host memory for the batch buffers (pageable memory works, slower) ---- */
 int psa_host_alloc(void** out, uint64_t bytes);

@@ -265,15 +265,18 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
 
     // host-side pass over the node table: k-mer counts, value packing widths, validation
     std::vector<uint64_t> koff(d->n_nodes + 1);
-    uint64_t n_kmers = 0, max_off = 0;
+    uint64_t n_kmers = 0, max_off = 0, max_pos = 0;
     for (uint64_t i = 0; i < d->n_nodes; i++) {
         koff[i] = n_kmers;
         if (d->node_len[i] < d->k) return fail(PSA_ERR_INDEX, "node shorter than k");
+        if (d->node_len[i] > kMaxNodeLen) return fail(PSA_ERR_INDEX, "node longer than 2^24 - 1 bases");
+        if (d->node_start[i] > kStartMask) return fail(PSA_ERR_INDEX, "sequence longer than 2^40 bases");
         if (d->node_eq[i] >= d->n_eq) return fail(PSA_ERR_INDEX, "node eq id out of range");
         if ((d->node_start[i] + d->node_len[i] + 31) / 32 > d->n_seq_words)
             return fail(PSA_ERR_INDEX, "node sequence outside seq_words");
         uint64_t nk = (uint64_t)d->node_len[i] - d->k + 1;
         max_off = std::max(max_off, nk - 1);
+        max_pos = std::max(max_pos, d->node_start[i] + nk - 1);
         n_kmers += nk;
     }
     koff[d->n_nodes] = n_kmers;
@@ -339,8 +342,8 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     DevIndex& D = ix->d;
     D.k = d->k;
     D.node_bits = bits_for(d->n_nodes ? d->n_nodes - 1 : 0);
-    D.off_bits = bits_for(max_off);
-    int fp = 64 - (int)D.node_bits - (int)D.off_bits;
+    D.pos_bits = bits_for(max_pos);
+    int fp = 64 - (int)D.node_bits - (int)D.pos_bits;
     D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
     D.n_nodes = d->n_nodes;
     D.n_kmers = n_kmers;
@@ -388,7 +391,7 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     I.seq_bytes = d->n_seq_words * 8;
     I.eq_bytes = (d->n_eq + 1) * 8 + n_mem * 4 + d->n_eq * sizeof(ClassWin);
     I.node_bits = D.node_bits;
-    I.off_bits = D.off_bits;
+    I.pos_bits = D.pos_bits;
     I.fp_bits = D.fp_bits;
     I.max_class_len = max_class;
     I.gamma = gamma;
@@ -1202,6 +1205,51 @@ extern "C" int psa_mapper_counts_allreduce(psa_mapper* m, psa_comm* c) {
     int e = g_nccl.AllReduce(m->counts.p, m->counts.p, m->ix->d.n_eq + 2, 5, 0, c->comm, m->st);
     if (e) return nccl_fail("ncclAllReduce", e);
     CU(cudaStreamSynchronize(m->st));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// measurement aid
+// ---------------------------------------------------------------------------------------------
+extern "C" int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s) {
+    if (!gbytes_per_s || (chunk_bytes != 0 && chunk_bytes != 32 && chunk_bytes != 64 && chunk_bytes != 128) ||
+        table_bytes < (1u << 20) || !iters)
+        return fail(PSA_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(device));
+    DevBuf table, sink;
+    int rc;
+    if ((rc = table.ensure(table_bytes)) || (rc = sink.ensure(8))) {
+        table.release();
+        return rc;
+    }
+    cudaMemset(table.p, 1, table_bytes);
+    const uint64_t n_chunks = table_bytes / (chunk_bytes ? chunk_bytes : 128);
+    const unsigned grid = 148 * 16, block = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        if (chunk_bytes == 0) k_gather_probe<0><<<grid, block>>>(table.as<uint64_t>(), n_chunks, iters, 17 + rep, sink.as<uint64_t>());
+        else if (chunk_bytes == 32) k_gather_probe<32><<<grid, block>>>(table.as<uint64_t>(), n_chunks, iters, 17 + rep, sink.as<uint64_t>());
+        else if (chunk_bytes == 64) k_gather_probe<64><<<grid, block>>>(table.as<uint64_t>(), n_chunks, iters, 17 + rep, sink.as<uint64_t>());
+        else k_gather_probe<128><<<grid, block>>>(table.as<uint64_t>(), n_chunks, iters, 17 + rep, sink.as<uint64_t>());
+        cudaEventRecord(e1, 0);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            table.release(); sink.release();
+            return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    table.release();
+    sink.release();
+    *gbytes_per_s = (double)grid * block * iters * (chunk_bytes ? chunk_bytes : 4) / (best / 1e3) / 1e9;
     return PSA_OK;
 }
 

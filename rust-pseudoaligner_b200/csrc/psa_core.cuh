@@ -25,6 +25,9 @@
 #else
 #define PSA_HD inline
 #endif
+#ifndef PSA_TWO_AHEAD
+#define PSA_TWO_AHEAD 0
+#endif
 #if defined(__CUDA_ARCH__)
 #define PSA_UNROLL _Pragma("unroll")
 #else
@@ -197,17 +200,23 @@ struct KmerOps<2> {
 // ---------------------------------------------------------------------------------------------
 // The index as the kernels see it (all pointers device memory, immutable)
 // ---------------------------------------------------------------------------------------------
-struct NodeRec {        // 64 bytes, 64-byte aligned: one L2 line per node visit
-    uint64_t start;     // first base in the concatenated sequence
-    uint32_t len;       // bases
-    uint32_t eq;        // equivalence-class id (*node.data())
-    uint32_t class_len; // |eq_classes[eq]|
-    uint32_t exts;      // debruijn Exts byte
-    uint64_t class_off; // eq_classes[eq] starts at eq_mem[class_off]
-    uint32_t succ[4];   // node reached by right extension b (kNone if the ext bit is clear)
-    uint32_t pred[4];   // node reached by left extension b
+// 64 bytes in two 32-byte sectors.  Sector 0 is all the forward walk needs (one LDG.E.256 per
+// node visit: sequence, class, successors); sector 1 is read only by the left extension, the
+// cooperative kernel's class list and the index self-checks.
+struct NodeRec {
+    uint64_t start_len;  // first base in the concatenated sequence (low 40 bits) | bases << 40
+    uint32_t eq;         // equivalence-class id (*node.data())
+    uint32_t class_len;  // |eq_classes[eq]|
+    uint32_t succ[4];    // node reached by right extension b (kNone if the ext bit is clear)
+    uint32_t pred[4];    // node reached by left extension b
+    uint32_t exts;       // debruijn Exts byte
+    uint32_t pad;
+    uint64_t class_off;  // eq_classes[eq] starts at eq_mem[class_off]
 };
 static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte line");
+constexpr uint64_t kStartMask = (1ULL << 40) - 1;
+constexpr uint32_t kMaxNodeLen = (1u << 24) - 1;
+PSA_HD uint64_t pack_start_len(uint64_t start, uint32_t len) { return start | ((uint64_t)len << 40); }
 
 struct Mphf {
     const uint64_t* blocks;  // 4 words per block: [rank:48 | c1:7 | c2:8] w1 w2 w3
@@ -230,7 +239,8 @@ constexpr uint32_t kBloomBitsPerKey = 12;
 
 struct DevIndex {
     uint32_t k;
-    uint32_t node_bits, off_bits, fp_bits;  // `values` entry = node | off << node_bits | fp << (node_bits+off_bits)
+    uint32_t node_bits, pos_bits, fp_bits;  // `values` entry = node | pos << node_bits | fp << (node_bits+pos_bits),
+                                            // pos = absolute base position of the k-mer in `seq`
     uint64_t n_nodes, n_kmers, n_eq;
     const uint64_t* values;
     const NodeRec* nodes;
@@ -249,8 +259,9 @@ struct KeyHash {
 };
 PSA_HD KeyHash make_hash(uint64_t folded) {
     KeyHash kh;
-    kh.h1 = mix64(folded + 0x9E3779B97F4A7C15ULL);
-    kh.h2 = mix64(folded ^ 0xD6E8FEB86659FD93ULL) | 1ULL;
+    kh.h1 = mix64(folded + 0x9E3779B97F4A7C15ULL);  // a bijection of the key
+    uint64_t t = kh.h1 * 0xD6E8FEB86659FD93ULL;     // second hash derived from the first: distinct keys have
+    kh.h2 = (t ^ (t >> 32)) | 1ULL;                 // distinct h1, hence (pseudo-)independent h2
     return kh;
 }
 PSA_HD uint64_t level_hash(KeyHash kh, uint32_t lvl) { return kh.h1 + (uint64_t)lvl * kh.h2; }
@@ -320,9 +331,35 @@ struct ProbeStats {  // sequential-equivalent event counts of one dictionary pro
 };
 
 // Mphf::try_hash: cascade of bit-vectors; the first level whose bit is set gives the slot.
-PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& levels) {
+// two_ahead: fetch the blocks of levels 0 and 1 together (a likely-present key resolves at level
+// 0 with p ~ 0.55 and at level 1 with p ~ 0.25: one round trip instead of two for the latter, at
+// the price of one extra sector for the former).  `levels` stays the sequential count.
+// Measured on B200 (config 3): k_map_thread 3.74 ms with it, 3.40 ms without -- the kernel is
+// bound by the random-sector rate of HBM, not by the length of the dependent chain, so the extra
+// sector costs more than the saved round trip.  Kept for reference, off (PSA_TWO_AHEAD=0).
+PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& levels, bool two_ahead = false) {
     levels = 0;
-    for (uint32_t lvl = 0; lvl < m.n_levels; lvl++) {
+    uint32_t lvl = 0;
+    if (two_ahead && m.n_levels >= 2) {
+        uint64_t blk0, blk1;
+        uint32_t bit0, bit1;
+        level_pos(level_hash(hk, 0), m.level_nblk[0], blk0, bit0);
+        level_pos(level_hash(hk, 1), m.level_nblk[1], blk1, bit1);
+        const Block b0 = load_block(m.blocks, m.level_base[0] + blk0);
+        const Block b1 = load_block(m.blocks, m.level_base[1] + blk1);
+        levels = 1;
+        if ((block_word(b0, bit0 >> 6) >> (bit0 & 63)) & 1) {
+            slot = block_rank(b0, bit0);
+            return true;
+        }
+        levels = 2;
+        if ((block_word(b1, bit1 >> 6) >> (bit1 & 63)) & 1) {
+            slot = block_rank(b1, bit1);
+            return true;
+        }
+        lvl = 2;
+    }
+    for (; lvl < m.n_levels; lvl++) {
         uint64_t blk;
         uint32_t bit;
         level_pos(level_hash(hk, lvl), m.level_nblk[lvl], blk, bit);
@@ -336,9 +373,9 @@ PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& lev
     return false;
 }
 
-PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, KeyHash hk) {
-    uint64_t v = (uint64_t)node | ((uint64_t)off << ix.node_bits);
-    if (ix.fp_bits) v |= fp_of(hk, ix.fp_bits) << (ix.node_bits + ix.off_bits);
+PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint64_t pos, KeyHash hk) {
+    uint64_t v = (uint64_t)node | (pos << ix.node_bits);
+    if (ix.fp_bits) v |= fp_of(hk, ix.fp_bits) << (ix.node_bits + ix.pos_bits);
     return v;
 }
 
@@ -348,12 +385,12 @@ PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint32_t off, KeyH
 // prefilter: ask the Bloom filter first (callers do when the key is likely absent).
 template <int KW>
 PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st,
-                     bool prefilter = false) {
+                     bool prefilter = false, bool two_ahead = false) {
     KeyHash hk = make_hash(KmerOps<KW>::fold(key));
     if (prefilter && ix.bloom.words && !bloom_maybe(ix.bloom, hk)) return false;
     uint64_t slot;
     uint32_t levels;
-    bool in = mphf_lookup(ix.mphf, hk, slot, levels);
+    bool in = mphf_lookup(ix.mphf, hk, slot, levels, two_ahead);
     if (st) { st->levels = levels; st->hit = in; st->verified = 0; }
     if (!in) return false;
 #ifdef __CUDA_ARCH__
@@ -362,20 +399,21 @@ PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t&
     uint64_t v = ix.values[slot];
 #endif
     if (ix.fp_bits) {
-        if ((v >> (ix.node_bits + ix.off_bits)) != fp_of(hk, ix.fp_bits)) return false;
+        if ((v >> (ix.node_bits + ix.pos_bits)) != fp_of(hk, ix.fp_bits)) return false;
     }
     uint32_t n = (uint32_t)(v & ((1ULL << ix.node_bits) - 1));
-    uint32_t o = (uint32_t)((v >> ix.node_bits) & ((1ULL << ix.off_bits) - 1));
+    uint64_t pos = (v >> ix.node_bits) & ((1ULL << ix.pos_bits) - 1);
     if (st) st->verified = 1;
+    // the unitig k-mer and the node's start are independent loads: both addresses come from `v`
 #ifdef __CUDA_ARCH__
-    uint64_t start = __ldg(&ix.nodes[n].start);
+    uint64_t start = __ldg(&ix.nodes[n].start_len) & kStartMask;
 #else
-    uint64_t start = ix.nodes[n].start;
+    uint64_t start = ix.nodes[n].start_len & kStartMask;
 #endif
-    Kmer<KW> ref = KmerOps<KW>::get(GLoad{ix.seq}, start + o, ix.k);
+    Kmer<KW> ref = KmerOps<KW>::get(GLoad{ix.seq}, pos, ix.k);
     if (!(ref == key)) return false;
     node = n;
-    off = o;
+    off = (uint32_t)(pos - start);
     return true;
 }
 
@@ -425,7 +463,8 @@ PSA_HD uint32_t nth_mismatch(uint64_t m, uint32_t j) {
 //   W::node(id)                                  get_node: NodeRec fields
 //   W::cmp_fwd(rpos, spos, m, A, premature)      :236-255 -> matched_bases
 //   W::cmp_bwd(rend, send, m, A, premature)      :151-170 -> matched_bases
-//   W::succ(id, b) / W::pred(id, b)              r_edges()[..].0 / l_edges()[..].0
+//   view_succ(node view, b) / W::pred(id, b)     r_edges()[..].0 / l_edges()[..].0; kNone when the node has no
+//                                                such extension (Exts::has_ext, :183 / :267); W::jumped() counts
 //   W::push(node)                                nodes.push
 //   W::abort()                                   true once the policy has given the read up (never for
 //                                                the cooperative policies; see ThreadCtx)
@@ -433,9 +472,30 @@ PSA_HD uint32_t nth_mismatch(uint64_t m, uint32_t j) {
 // ---------------------------------------------------------------------------------------------
 struct NodeView {
     uint64_t start;
-    uint32_t len, eq, class_len, exts;
-    uint64_t class_off;
+    uint32_t len, eq, class_len;
+    uint32_t succ[4];  // never indexed dynamically (view_succ)
 };
+// sector 0 of a node record
+PSA_HD NodeView load_node_view(const NodeRec* r) {
+    NodeView v;
+#ifdef __CUDA_ARCH__
+    uint64_t a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(r));
+    v.start = a & kStartMask;
+    v.len = (uint32_t)(a >> 40);
+    v.eq = (uint32_t)b;
+    v.class_len = (uint32_t)(b >> 32);
+    v.succ[0] = (uint32_t)c; v.succ[1] = (uint32_t)(c >> 32); v.succ[2] = (uint32_t)d; v.succ[3] = (uint32_t)(d >> 32);
+#else
+    v.start = r->start_len & kStartMask;
+    v.len = (uint32_t)(r->start_len >> 40);
+    v.eq = r->eq;
+    v.class_len = r->class_len;
+    for (int i = 0; i < 4; i++) v.succ[i] = r->succ[i];
+#endif
+    return v;
+}
+PSA_HD uint32_t view_succ(const NodeView& v, uint32_t b) { return b == 0 ? v.succ[0] : b == 1 ? v.succ[1] : b == 2 ? v.succ[2] : v.succ[3]; }
 
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
@@ -473,8 +533,9 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
             if (last_pos + 1 - matched_bases == 0 || premature_break) break;    // :173-175
             last_pos -= matched_bases;                                          // :178
             uint32_t next_base = w.read_base(last_pos);                         // :182
-            if ((nv.exts >> (4 + next_base)) & 1) {                             // :183
-                prev_node_id = w.pred(prev_node_id, next_base);                 // :185-194
+            const uint32_t pred_id = w.pred(prev_node_id, next_base);          // kNone <=> no such left ext
+            if (pred_id != kNone) {                                             // :183
+                prev_node_id = pred_id;                                         // :185-194
                 NodeView pv = w.node(prev_node_id);                             // :195
                 prev_kmer_offset = pv.len - kmer_length;                        // :196
                 w.push(prev_node_id, pv);                                       // :199
@@ -508,8 +569,10 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
             kmer_pos += matched_bases;                                          // :257
             if (kmer_pos >= read_length) break;                                 // :259-261
             uint32_t next_base = w.read_base(kmer_pos);                         // :265
-            if (!premature_break && ((nv.exts >> next_base) & 1)) {             // :267
-                node_id = w.succ(node_id, next_base);                           // :269-278
+            const uint32_t succ_id = view_succ(nv, next_base);                  // kNone <=> no such right ext
+            if (!premature_break && succ_id != kNone) {                         // :267
+                w.jumped();
+                node_id = succ_id;                                              // :269-278
                 kmer_offset = 0;                                                // :279
                 kmer_pos -= kmer_length - 1;                                    // :282
                 read_coverage -= kmer_length - 1;                               // :283
@@ -769,7 +832,8 @@ struct ThreadCtx {
             ProbeStats st;
             // after a miss the next positions are likely absent too: Bloom first (never when counting
             // events, which are defined on the MPHF path)
-            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr, !EV && probes > 0);
+            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr, !EV && probes > 0,
+                                    PSA_TWO_AHEAD && probes == 0);
             if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) {
                 kmer_pos = p;
@@ -778,35 +842,18 @@ struct ThreadCtx {
             }
         }
     }
-    PSA_HD NodeView node(uint32_t id) const {
-        NodeView v;
-#ifdef __CUDA_ARCH__
-        const uint4* r = reinterpret_cast<const uint4*>(ix.nodes + id);
-        uint4 a = __ldg(r), b = __ldg(r + 1);
-        v.start = (uint64_t)a.x | ((uint64_t)a.y << 32);
-        v.len = a.z; v.eq = a.w; v.class_len = b.x; v.exts = b.y;
-        v.class_off = (uint64_t)b.z | ((uint64_t)b.w << 32);
-#else
-        const NodeRec& r = ix.nodes[id];
-        v.start = r.start; v.len = r.len; v.eq = r.eq; v.class_len = r.class_len; v.exts = r.exts; v.class_off = r.class_off;
-#endif
-        return v;
-    }
-    PSA_HD uint32_t succ(uint32_t id, uint32_t b) {
+    PSA_HD NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
+    PSA_HD void jumped() {
         if (EV) ev.jumps++;
-#ifdef __CUDA_ARCH__
-        return __ldg(&ix.nodes[id].succ[b]);
-#else
-        return ix.nodes[id].succ[b];
-#endif
     }
     PSA_HD uint32_t pred(uint32_t id, uint32_t b) {
-        if (EV) ev.jumps++;
 #ifdef __CUDA_ARCH__
-        return __ldg(&ix.nodes[id].pred[b]);
+        const uint32_t p = __ldg(&ix.nodes[id].pred[b]);
 #else
-        return ix.nodes[id].pred[b];
+        const uint32_t p = ix.nodes[id].pred[b];
 #endif
+        if (EV && p != kNone) ev.jumps++;
+        return p;
     }
     // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step
     template <bool FWD>

@@ -28,11 +28,12 @@ __global__ void k_node_basics(NodeRec* nodes, uint64_t n_nodes, const uint64_t* 
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     NodeRec r;
-    r.start = node_start[i];
-    r.len = node_len[i];
+    const uint32_t len = node_len[i];
+    r.start_len = pack_start_len(node_start[i], len);
     r.eq = node_eq[i];
     r.exts = node_exts[i];
-    if (r.eq >= n_eq || r.len < k) {
+    r.pad = 0;
+    if (r.eq >= n_eq || len < k || len > kMaxNodeLen || node_start[i] > kStartMask) {
         atomicOr(err, 1u);
         r.class_len = 0;
         r.class_off = 0;
@@ -162,7 +163,8 @@ __global__ void k_fill_values(const uint64_t* key_lo, const uint64_t* key_hi, co
         return;
     }
     uint64_t v = val[i];
-    values[slot] = pack_value(ix, (uint32_t)(v >> 32), (uint32_t)v, hk);
+    const uint32_t node = (uint32_t)(v >> 32);
+    values[slot] = pack_value(ix, node, (ix.nodes[node].start_len & kStartMask) + (uint32_t)v, hk);
 }
 
 // succ[b] / pred[b]: the node whose first k-mer is last(k-1)+b, resp. whose last k-mer is
@@ -172,9 +174,11 @@ __global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= ix.n_nodes) return;
     const NodeRec r = nodes[i];
-    if (r.len < ix.k) return;
-    Kmer<KW> first = KmerOps<KW>::get(GLoad{ix.seq}, r.start, ix.k);
-    Kmer<KW> last = KmerOps<KW>::get(GLoad{ix.seq}, r.start + r.len - ix.k, ix.k);
+    const uint64_t r_start = r.start_len & kStartMask;
+    const uint32_t r_len = (uint32_t)(r.start_len >> 40);
+    if (r_len < ix.k) return;
+    Kmer<KW> first = KmerOps<KW>::get(GLoad{ix.seq}, r_start, ix.k);
+    Kmer<KW> last = KmerOps<KW>::get(GLoad{ix.seq}, r_start + r_len - ix.k, ix.k);
     for (uint32_t b = 0; b < 4; b++) {
         uint32_t n, o;
         if ((r.exts >> b) & 1) {
@@ -185,7 +189,7 @@ __global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
         }
         if ((r.exts >> (4 + b)) & 1) {
             if (dict_get<KW>(ix, KmerOps<KW>::extend_left(first, b, ix.k), n, o, nullptr) &&
-                o == nodes[n].len - ix.k)
+                o == (uint32_t)(nodes[n].start_len >> 40) - ix.k)
                 nodes[i].pred[b] = n;
             else
                 atomicOr(err, 4u);
@@ -420,26 +424,14 @@ struct WarpCtx {
         return false;
     }
 
-    __device__ __forceinline__ NodeView node(uint32_t id) const {
-        const NodeRec* r = ix.nodes + id;
-        uint4 a = __ldg(reinterpret_cast<const uint4*>(r));
-        uint4 b = __ldg(reinterpret_cast<const uint4*>(r) + 1);
-        NodeView v;
-        v.start = (uint64_t)a.x | ((uint64_t)a.y << 32);
-        v.len = a.z;
-        v.eq = a.w;
-        v.class_len = b.x;
-        v.exts = b.y;
-        v.class_off = (uint64_t)b.z | ((uint64_t)b.w << 32);
-        return v;
-    }
-    __device__ __forceinline__ uint32_t succ(uint32_t id, uint32_t b) {
+    __device__ __forceinline__ NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
+    __device__ __forceinline__ void jumped() {
         if (EV && lane == 0) ev.jumps++;
-        return __ldg(&ix.nodes[id].succ[b]);
     }
     __device__ __forceinline__ uint32_t pred(uint32_t id, uint32_t b) {
-        if (EV && lane == 0) ev.jumps++;
-        return __ldg(&ix.nodes[id].pred[b]);
+        const uint32_t p = __ldg(&ix.nodes[id].pred[b]);
+        if (EV && lane == 0 && p != kNone) ev.jumps++;
+        return p;
     }
 
     // shared tail of the two compare loops: lane `lane` holds the mismatch mask of bases
@@ -496,7 +488,7 @@ struct WarpCtx {
         if (EV && lane == 0) ev.visits++;
         if (g.ballot(lane < n_list && my_eq == nv.eq)) return;
         if (n_list < G) {
-            if (lane == n_list) { my_eq = nv.eq; my_len = nv.class_len; my_off = nv.class_off; }
+            if (lane == n_list) { my_eq = nv.eq; my_len = nv.class_len; my_off = __ldg(ix.eq_off + nv.eq); }
             n_list++;
             return;
         }
@@ -506,7 +498,10 @@ struct WarpCtx {
         for (uint32_t j = lane; j < ns; j += G) dup |= (spill[j].x == nv.eq);
         if (g.any(dup)) return;
         if (ns >= spill_cap && !grow_spill(ns)) { spill_overflow = true; return; }
-        if (lane == 0) spill[ns] = make_uint4(nv.eq, nv.class_len, (uint32_t)nv.class_off, (uint32_t)(nv.class_off >> 32));
+        if (lane == 0) {
+            const uint64_t coff = __ldg(ix.eq_off + nv.eq);
+            spill[ns] = make_uint4(nv.eq, nv.class_len, (uint32_t)coff, (uint32_t)(coff >> 32));
+        }
         g.sync();
         n_list++;
     }
@@ -863,6 +858,37 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Measurement aid: independent random gathers of `bytes`-sized aligned chunks from a table, the
+// access pattern of the index lookups without their dependencies.  Its rate is the practical
+// ceiling ("random-sector roofline") the map kernels are compared with in DESIGN.md.
+// ---------------------------------------------------------------------------------------------
+// BYTES = 32/64/128: every thread gathers its own chunk (32-byte LDG.E.256 pieces, as the index
+// lookups do).  BYTES = 0: every warp gathers one 128-byte line, 4 bytes per lane (the rate at
+// which HBM serves random lines, without divergent addresses inside a load instruction).
+template <int BYTES>
+__global__ void k_gather_probe(const uint64_t* table, uint64_t n_chunks, uint32_t iters, uint64_t seed, uint64_t* sink) {
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    uint64_t x = mix64(seed + (BYTES ? tid : tid >> 5) * 0x9E3779B97F4A7C15ULL);
+    for (uint32_t i = 0; i < iters; i++) {
+        x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+        const uint64_t c = mulhi64(x, n_chunks);
+        if (BYTES == 0) {
+            acc += __ldg(reinterpret_cast<const uint32_t*>(table + c * 16) + (threadIdx.x & 31));
+        } else {
+#pragma unroll
+            for (int j = 0; j < BYTES / 32; j++) {
+                uint64_t a, b2, c2, d;
+                asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b2), "=l"(c2), "=l"(d)
+                             : "l"(table + c * (BYTES / 8) + 4 * j));
+                acc += a ^ b2 ^ c2 ^ d;
+            }
+        }
+    }
+    if (acc == seed) sink[0] = acc;  // keeps the loads alive
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -47,7 +47,7 @@ class _IndexInfo(C.Structure):
                 ("n_eq_members", C.c_uint64), ("n_seq_words", C.c_uint64),
                 ("mphf_bytes", C.c_uint64), ("values_bytes", C.c_uint64), ("node_bytes", C.c_uint64),
                 ("seq_bytes", C.c_uint64), ("eq_bytes", C.c_uint64), ("bloom_bytes", C.c_uint64),
-                ("node_bits", C.c_uint32), ("off_bits", C.c_uint32), ("fp_bits", C.c_uint32),
+                ("node_bits", C.c_uint32), ("pos_bits", C.c_uint32), ("fp_bits", C.c_uint32),
                 ("max_class_len", C.c_uint32), ("gamma", C.c_double), ("build_ms", C.c_double)]
 
 
@@ -82,7 +82,7 @@ EXPORTS = (
     "psa_mapper_profile_enable", "psa_mapper_profile_read",
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
-    "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads",
+    "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe",
 )
 
 
@@ -147,10 +147,19 @@ def lib():
     L.psa_device_free.restype, L.psa_device_free.argtypes = None, [vp]
     L.psa_memcpy_h2d.restype, L.psa_memcpy_h2d.argtypes = i32, [vp, vp, u64]
     L.psa_memcpy_d2h.restype, L.psa_memcpy_d2h.argtypes = i32, [vp, vp, u64]
+    L.psa_gather_probe.restype = i32
+    L.psa_gather_probe.argtypes = [i32, u64, u32, u32, C.POINTER(C.c_double)]
     L.psa_process_reads.restype = i32
     L.psa_process_reads.argtypes = [vp, C.c_char_p, C.c_char_p, u32, u64, i32, C.POINTER(_ProcessStats)]
     _lib = L
     return L
+
+
+def gather_probe(device=0, table_bytes=1 << 30, chunk_bytes=32, iters=64):
+    """GB/s of independent random chunk gathers from HBM (psa_gather_probe)."""
+    out = C.c_double()
+    _check(lib().psa_gather_probe(int(device), int(table_bytes), int(chunk_bytes), int(iters), C.byref(out)))
+    return float(out.value)
 
 
 def _check(rc):

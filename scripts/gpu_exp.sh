@@ -1,7 +1,9 @@
+# A/B of alternative builds of the library (PSA_LIB_PATH) on the kernel-resident arm
 mkdir -p gpurun_out; : > gpurun_out/exp.jsonl
-for lib in "" gpurun_exp_mb8.so gpurun_exp_mb10.so; do
-  for p in 3 8; do
-    PSA_LIB_PATH=${lib:+$PWD/$lib} timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --fast-probes $p >> gpurun_out/exp.jsonl 2>> gpurun_out/exp.err
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5
+for lib in "" $EXP_LIBS; do
+  for args in "" $EXP_ARGS; do
+    PSA_LIB_PATH=${lib:+$PWD/$lib} timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e ${args//,/ } >> gpurun_out/exp.jsonl 2>> gpurun_out/exp.err
   done
 done
 python - <<'PY'

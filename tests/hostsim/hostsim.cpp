@@ -43,10 +43,10 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     DevIndex& D = ix->d;
     std::vector<Kmer<KW>> keys;
     std::vector<uint64_t> vals;
-    uint64_t max_off = 0;
+    uint64_t max_pos = 0;
     for (uint64_t i = 0; i < n_nodes; i++) {
         uint64_t nk = node_len[i] - k + 1;
-        max_off = std::max(max_off, nk - 1);
+        max_pos = std::max(max_pos, node_start[i] + nk - 1);
         for (uint64_t o = 0; o < nk; o++) {
             keys.push_back(KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i] + o, k));
             vals.push_back((i << 32) | o);
@@ -56,8 +56,8 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     auto bits_for = [](uint64_t v) { uint32_t b = 1; while (b < 64 && (v >> b)) b++; return b; };
     D.k = k;
     D.node_bits = bits_for(n_nodes ? n_nodes - 1 : 0);
-    D.off_bits = bits_for(max_off);
-    int fp = 64 - (int)D.node_bits - (int)D.off_bits;
+    D.pos_bits = bits_for(max_pos);
+    int fp = 64 - (int)D.node_bits - (int)D.pos_bits;
     D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
     D.n_nodes = n_nodes;
     D.n_kmers = n_kmers;
@@ -121,13 +121,13 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
         uint64_t slot; uint32_t levels;
         if (!mphf_lookup(D.mphf, rem_h[i], slot, levels) || slot >= n_kmers || seen[slot]) { ix->error = 3; return; }
         seen[slot] = 1;
-        ix->values[slot] = pack_value(D, (uint32_t)(vals[i] >> 32), (uint32_t)vals[i], rem_h[i]);
+        ix->values[slot] = pack_value(D, (uint32_t)(vals[i] >> 32), node_start[vals[i] >> 32] + (uint32_t)vals[i], rem_h[i]);
     }
     // nodes + edges
     ix->nodes.resize(n_nodes + 1);
     for (uint64_t i = 0; i < n_nodes; i++) {
         NodeRec& r = ix->nodes[i];
-        r.start = node_start[i]; r.len = node_len[i]; r.eq = node_eq[i]; r.exts = node_exts[i];
+        r.start_len = pack_start_len(node_start[i], node_len[i]); r.eq = node_eq[i]; r.exts = node_exts[i]; r.pad = 0;
         r.class_len = (uint32_t)(ix->eq_off[r.eq + 1] - ix->eq_off[r.eq]);
         r.class_off = ix->eq_off[r.eq];
         for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
@@ -135,8 +135,8 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     D.nodes = ix->nodes.data();
     for (uint64_t i = 0; i < n_nodes; i++) {
         NodeRec& r = ix->nodes[i];
-        Kmer<KW> first = KmerOps<KW>::get(PLoad{ix->seq.data()}, r.start, k);
-        Kmer<KW> last = KmerOps<KW>::get(PLoad{ix->seq.data()}, r.start + r.len - k, k);
+        Kmer<KW> first = KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i], k);
+        Kmer<KW> last = KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i] + node_len[i] - k, k);
         for (uint32_t b = 0; b < 4; b++) {
             uint32_t n, o;
             if ((r.exts >> b) & 1) {
@@ -144,7 +144,7 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
                 else ix->error = 4;
             }
             if ((r.exts >> (4 + b)) & 1) {
-                if (dict_get<KW>(D, KmerOps<KW>::extend_left(first, b, k), n, o, nullptr) && o == ix->nodes[n].len - k) r.pred[b] = n;
+                if (dict_get<KW>(D, KmerOps<KW>::extend_left(first, b, k), n, o, nullptr) && o == node_len[n] - k) r.pred[b] = n;
                 else ix->error = 4;
             }
         }
@@ -173,11 +173,8 @@ struct SerialWarp {
     }
     uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
     bool abort() const { return false; }
-    NodeView node(uint32_t id) const {
-        const NodeRec& r = ix.nodes[id];
-        return NodeView{r.start, r.len, r.eq, r.class_len, r.exts, r.class_off};
-    }
-    uint32_t succ(uint32_t id, uint32_t b) { return ix.nodes[id].succ[b]; }
+    NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
+    void jumped() {}
     uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes[id].pred[b]; }
     // the two compare loops, chunked by 32 bases exactly as the kernel lanes are
     template <bool FWD>
