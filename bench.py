@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunk-reads", type=int, default=0, help="reads per pipeline chunk of host batches (0 = library default)")
     ap.add_argument("--cache-dir", default="/dev/shm")
     ap.add_argument("--host-threads", type=int, default=0)
     return ap.parse_args()
@@ -118,7 +119,9 @@ def load_index(a, host, tr, rank, world, barrier, threads):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 20 ms from before the warm-up (it takes a while to start); the
+    samples that fall inside the timed windows are the ones reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -126,19 +129,25 @@ class ClockSampler:
         self.gpu = gpu_index
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.windows = []
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -146,16 +155,21 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
+        sm, mx, reasons, power, n_all = [], [], set(), [], 0
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                vals = (float(c[2]), float(c[3]), float(c[4]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+            n_all += 1
+            if self.windows and not any(t0 - 0.02 <= ts <= t1 + 0.02 for t0, t1 in self.windows):
+                continue
+            sm.append(vals[0]); mx.append(vals[1]); power.append(vals[2])
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         try:
@@ -164,7 +178,8 @@ class ClockSampler:
             pass
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+                       samples=len(sm), samples_total=n_all, power_w_max=float(max(power)),
+                       windows="kernel-resident and end-to-end timed regions")
         return out
 
 
@@ -302,7 +317,7 @@ def main():
     flat, build_s = load_index(a, host, tr, rank, world, barrier, ncores if rank == 0 else host_threads)
     index = pkg.Index(flat, device=local_rank, gamma=a.gamma)
     info = index.info()
-    mapper = pkg.Mapper(index)
+    mapper = pkg.Mapper(index, a.chunk_reads)
     if a.group_width:
         mapper.set_group_width(a.group_width)
     if a.fast_probes >= 0:
@@ -341,6 +356,8 @@ def main():
         comm = pkg.Comm(uid[0], world, rank, local_rank)
 
     # ---------------- kernel-resident arm: `value`
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for s in range(a.warmup):
         mapper.map_device_async(dev_batches[s % G])
         mapper.sync()
@@ -348,11 +365,10 @@ def main():
     launches0 = mapper.launch_count()
     mapper.profile_enable(True)
     mapper.profile_read()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_w0 = time.time()
     e0.record(stream)
     for s in range(a.steps):
         mapper.map_device_async(dev_batches[s % G])
@@ -362,9 +378,9 @@ def main():
     e1.record(stream)
     mapper.sync()
     torch.cuda.synchronize()
+    sampler.window(t_w0, time.time())
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
     prof = mapper.profile_read()
     mapper.profile_enable(False)
     launches = mapper.launch_count() - launches0
@@ -388,6 +404,7 @@ def main():
         e2e_step(1 % G)
         barrier()
         torch.cuda.synchronize()
+        t_w0 = time.time()
         t0 = time.perf_counter()
         used = 0
         for s in range(a.steps):
@@ -395,6 +412,7 @@ def main():
             used += len(tx)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        sampler.window(t_w0, time.time())
         dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
@@ -403,7 +421,9 @@ def main():
                "d2h_bytes_per_step": R * pkg.HIT_DTYPE.itemsize + 4 * used // a.steps + 16 * ((R + (1 << 20) - 1) >> 20),
                "ms_per_step": 1e3 * dt / a.steps, "api": "psa_mapper_map (host ASCII batch -> psa_hit[] + tx_buf)"}
 
-    # ---------------- roofline of the dominant kernel (k_map)
+    clocks = sampler.stop()
+
+    # ---------------- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"

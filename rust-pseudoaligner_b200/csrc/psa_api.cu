@@ -556,7 +556,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     psa_mapper* m = new (std::nothrow) psa_mapper();
     if (!m) return fail(PSA_ERR_NOMEM, "out of memory");
     m->ix = ix;
-    m->chunk_reads = chunk_reads ? chunk_reads : (1ull << 20);
+    m->chunk_reads = chunk_reads ? chunk_reads : (1ull << 19);  // 512 Ki: best H2D|kernel|D2H overlap measured on B200
     int rc = PSA_OK;
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking);

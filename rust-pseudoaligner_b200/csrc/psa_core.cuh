@@ -769,6 +769,7 @@ PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
 // cooperative kernel (k_map over the deferred list), so the split never changes a result.
 // ---------------------------------------------------------------------------------------------
 constexpr int kThreadClasses = 8;
+constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
 struct HitRec {  // == psa_hit
@@ -823,7 +824,8 @@ struct ThreadCtx {
                 kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
                 return false;
             }
-            if (probes >= max_probes) {
+            // re-seed searches (ref :293) are short as a rule and have no scan kernel of their own: allow them more
+            if (probes >= (seeded ? (max_probes > kReseedProbes ? max_probes : kReseedProbes) : max_probes)) {
                 defer = true;
                 why = seeded ? 1 : 0;
                 kmer_pos = last + 1;  // keeps map_read_nodes out of the forward loop
