@@ -264,6 +264,10 @@ def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads):
 
 # ------------------------------------------------------------------------------------ main
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version) write to fd 1 too, so
+    # everything but the final line is sent to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     a = parse_args()
     if a.k == 0:
         a.k = 24 if a.workload == "gencode_synth" else 20
@@ -292,13 +296,14 @@ def main():
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
         return 0
 
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}))
+        real_stdout.write(json.dumps({"error": "no CUDA device: the hot path has no CPU fallback"}) + "\n")
         return 2
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -361,6 +366,8 @@ def main():
     for s in range(a.warmup):
         mapper.map_device_async(dev_batches[s % G])
         mapper.sync()
+    if comm is not None:
+        mapper.counts_allreduce(comm)      # warm-up of the collective too (NCCL connects lazily on first use)
     mapper.counts_reset()
     launches0 = mapper.launch_count()
     mapper.profile_enable(True)
@@ -480,7 +487,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "events_per_read": {key: ev[key] / ev["reads"] for key in ev if key != "reads"},
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if comm is not None:
         comm.close()
     if world > 1:
