@@ -98,6 +98,10 @@ struct PLoad {  // plain pointer (shared memory tile or global read buffer)
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const { return p[i]; }
 };
+struct RegLoad6 {  // a read of at most 192 bases held in registers (selected, never indexed)
+    uint64_t w0, w1, w2, w3, w4, w5;
+    PSA_HD uint64_t operator()(uint64_t i) const { return i == 0 ? w0 : i == 1 ? w1 : i == 2 ? w2 : i == 3 ? w3 : i == 4 ? w4 : w5; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // 2-bit sequences: debruijn DnaString packing, base i in word i/32 at bits 62-2*(i%32)
@@ -782,10 +786,10 @@ struct ThreadEvents {
     uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
 };
 
-template <int KW, bool EV>
+template <int KW, bool EV, class RD = PLoad>
 struct ThreadCtx {
     const DevIndex& ix;
-    PLoad rd;
+    RD rd;
     uint32_t k, max_probes;
     uint32_t eq[kThreadClasses], len[kThreadClasses];  // offsets are re-read from eq_off when needed
     uint32_t n_list;
@@ -797,8 +801,8 @@ struct ThreadCtx {
     uint32_t hint_pos, hint_node, hint_off;
     ThreadEvents ev;
 
-    PSA_HD ThreadCtx(const DevIndex& ix_, const uint64_t* words, uint32_t max_probes_)
-        : ix(ix_), rd{words}, k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false),
+    PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
+        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
     PSA_UNROLL
         for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; }
@@ -902,8 +906,8 @@ struct ThreadCtx {
 // smallest class (index s) that every other listed class contains, ascending; each other
 // class is searched only in the suffix after its previous match (ref :399-404).
 // out == nullptr counts.
-template <int KW, bool EV>
-PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV>& w, int s, uint32_t* out) {
+template <int KW, bool EV, class RD>
+PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, uint32_t* out) {
     const uint32_t* mem = w.ix.eq_mem;
     uint32_t cur[kThreadClasses];
     PSA_UNROLL
@@ -950,8 +954,8 @@ struct ThreadResult {
 // map_read + the process_reads flag for one read, by one thread.  NovelAlloc::operator()(count,
 // off_out) returns room for `count` members of a set that is no visited class (nullptr: no
 // room / members not wanted).
-template <int KW, bool EV, class NovelAlloc>
-PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, uint32_t L, uint32_t allowed,
+template <int KW, bool EV, class NovelAlloc, class RD>
+PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, uint32_t allowed,
                                     uint32_t max_probes, uint32_t max_small, NovelAlloc& novel, bool want_members,
                                     ThreadEvents* ev_out, const uint32_t* hint = nullptr /* pos, node, off */) {
     ThreadResult res;
@@ -959,7 +963,7 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, const uint64_t* words, u
     res.count_slot = ix.n_eq + 1;
     res.deferred = false;
     res.novel_overflow = false;
-    ThreadCtx<KW, EV> w(ix, words, max_probes);
+    ThreadCtx<KW, EV, RD> w(ix, words, max_probes);
     if (hint) {
         w.has_hint = true;
         w.hint_pos = hint[0]; w.hint_node = hint[1]; w.hint_off = hint[2];

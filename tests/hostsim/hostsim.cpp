@@ -295,8 +295,14 @@ uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uin
     for (uint64_t i = 0; i < n; i++) {
         HostNovel novel;
         ThreadResult r;
-        if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, words + read_off[i], read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
-        else r = map_read_thread<2, false>(ix->d, words + read_off[i], read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+        if (read_len[i] <= 192) {  // the register-resident reader of the fixed-length kernel variant
+            const uint64_t* q = words + read_off[i];
+            const uint32_t nw = (read_len[i] + 31) / 32;
+            RegLoad6 rr{nw > 0 ? q[0] : 0, nw > 1 ? q[1] : 0, nw > 2 ? q[2] : 0, nw > 3 ? q[3] : 0, nw > 4 ? q[4] : 0, nw > 5 ? q[5] : 0};
+            if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, rr, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+            else r = map_read_thread<2, false>(ix->d, rr, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+        } else if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, PLoad{words + read_off[i]}, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
+        else r = map_read_thread<2, false>(ix->d, PLoad{words + read_off[i]}, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
         if (r.deferred) {
             nd++;
             if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
