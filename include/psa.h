@@ -251,6 +251,8 @@ typedef struct psa_process_stats {
     uint64_t mapped;  /* mapped_read_counter, :477 (the flag of :455, sic)                   */
     uint64_t aligned; /* reads for which map_read returned Some                              */
     double seconds;   /* wall time of the call                                               */
+    double reader_seconds, mapper_seconds, writer_seconds; /* busy time of the three pipeline
+                         stages (FASTQ parse | psa_mapper_map | format + write)              */
 } psa_process_stats;
 int psa_process_reads(psa_index*, const char* fastq_path, const char* out_path, uint32_t num_threads,
                       uint64_t batch_reads, int progress, psa_process_stats* stats);

@@ -3,11 +3,13 @@
 //
 // The reference pulls one FASTQ record per mutex acquisition (src/utils.rs:152-157), maps it on a
 // worker thread, sends the tuple through a bounded channel and println!s it on the main thread
-// (:480-507).  Here the same work is a three-stage pipeline over batches: a reader thread parses
-// FASTQ text into pinned batch buffers, the calling thread runs psa_mapper_map (GPU), formatter
-// threads turn psa_hit[] + tx_buf into the reference's `{:?}` lines and the writer emits them in
-// INPUT order (a legal instance of the reference's "arrival order").  Nothing here maps reads on
-// the CPU.
+// (:480-507).  Here the same work is a three-stage pipeline over batches: a reader thread fills a
+// pinned block with raw FASTQ text and indexes its lines (newline scan split over num_threads
+// threads); the records are NOT copied -- the sequences are handed to psa_mapper_map as offsets
+// into the text block (PSA_READS_ASCII with read_off), ids are formatted straight from it; the
+// calling thread runs psa_mapper_map (GPU); formatter threads turn psa_hit[] + tx_buf into the
+// reference's `{:?}` lines and the writer emits them in INPUT order (a legal instance of the
+// reference's "arrival order").  Nothing here maps reads on the CPU.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,68 +50,88 @@ struct Pinned {  // growable cudaHostAlloc buffer (contents preserved on growth)
 };
 
 struct Batch {
-    Pinned seq, hits, tx;
-    uint64_t seq_len = 0;
-    std::vector<uint64_t> off;
-    std::vector<uint32_t> len;
-    std::string ids;  // ids back to back
-    std::vector<uint64_t> id_off;
+    Pinned text, hits, tx;       // text: raw FASTQ bytes of this batch (records start at byte 0)
+    uint64_t text_len = 0;       // bytes of complete records
+    std::vector<uint64_t> off;   // sequence start (byte offset into text) per read
+    std::vector<uint32_t> len;   // sequence length per read
+    std::vector<uint64_t> id_off;  // id start per read
+    std::vector<uint32_t> id_len;
     uint64_t n = 0, tx_used = 0;
     int state = 0;  // 0 free, 1 filled, 2 mapped
     bool last = false;
-    void clear() {
-        seq_len = 0; off.clear(); len.clear(); ids.clear(); id_off.clear(); n = 0; tx_used = 0; last = false;
+};
+
+// raw byte source: plain files through read(2)-style fread, gzip through zlib
+struct ByteSource {
+    gzFile gz = nullptr;
+    FILE* fp = nullptr;
+    bool open(const char* path) {
+        fp = fopen(path, "rb");
+        if (!fp) return false;
+        unsigned char magic[2] = {0, 0};
+        size_t got = fread(magic, 1, 2, fp);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            fclose(fp);
+            fp = nullptr;
+            gz = gzopen(path, "rb");
+            if (!gz) return false;
+            gzbuffer(gz, 1 << 20);
+        } else {
+            rewind(fp);
+            setvbuf(fp, nullptr, _IONBF, 0);
+        }
+        return true;
+    }
+    // fills up to n bytes; returns bytes read (0 at end of file)
+    size_t read(uint8_t* dst, size_t n) {
+        size_t total = 0;
+        while (total < n) {
+            size_t got;
+            if (gz) {
+                int g = gzread(gz, dst + total, (unsigned)std::min<size_t>(n - total, 1u << 30));
+                got = g > 0 ? (size_t)g : 0;
+            } else {
+                got = fread(dst + total, 1, n - total, fp);
+            }
+            if (!got) break;
+            total += got;
+        }
+        return total;
+    }
+    void close() {
+        if (gz) gzclose(gz);
+        if (fp) fclose(fp);
+        gz = nullptr;
+        fp = nullptr;
     }
 };
 
-// buffered line reader over zlib (reads plain and gzip files alike)
-struct LineReader {
-    gzFile f = nullptr;
-    std::vector<char> buf;
-    size_t pos = 0, end = 0;
-    bool eof = false;
-    bool open(const char* path) {
-        f = gzopen(path, "rb");
-        if (!f) return false;
-        gzbuffer(f, 1 << 20);
-        buf.resize(1 << 22);
-        return true;
-    }
-    void close() {
-        if (f) gzclose(f);
-        f = nullptr;
-    }
-    // returns false at end of file; line excludes the terminator (\n or \r\n)
-    bool next(const char*& s, size_t& n) {
-        for (;;) {
-            char* nl = (char*)memchr(buf.data() + pos, '\n', end - pos);
-            if (nl) {
-                s = buf.data() + pos;
-                n = (size_t)(nl - s);
-                pos += n + 1;
-                if (n && s[n - 1] == '\r') n--;
-                return true;
+// positions of every '\n' in text[0, n), found by `threads` threads over equal slices
+void index_newlines(const uint8_t* text, uint64_t n, uint32_t threads, std::vector<uint64_t>& nl) {
+    std::vector<std::vector<uint64_t>> part(threads);
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < threads; t++) {
+        th.emplace_back([&, t]() {
+            const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+            std::vector<uint64_t>& v = part[t];
+            v.reserve((hi - lo) / 64 + 16);
+            const uint8_t* p = text + lo;
+            const uint8_t* end = text + hi;
+            while (p < end) {
+                const uint8_t* q = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+                if (!q) break;
+                v.push_back((uint64_t)(q - text));
+                p = q + 1;
             }
-            if (eof) {
-                if (pos == end) return false;
-                s = buf.data() + pos;
-                n = end - pos;
-                pos = end;
-                if (n && s[n - 1] == '\r') n--;
-                return true;
-            }
-            if (pos > 0) {  // keep the partial line, refill
-                memmove(buf.data(), buf.data() + pos, end - pos);
-                end -= pos;
-                pos = 0;
-            }
-            if (end == buf.size()) buf.resize(buf.size() * 2);
-            int got = gzread(f, buf.data() + end, (unsigned)std::min<size_t>(buf.size() - end, 1u << 30));
-            if (got <= 0) eof = true;
-            else end += (size_t)got;
-        }
+        });
     }
-};
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& v : part) total += v.size();
+    nl.clear();
+    nl.reserve(total);
+    for (auto& v : part) nl.insert(nl.end(), v.begin(), v.end());
+}
 
 // Rust's `{:?}` of a String: quotes, with \" \\ \n \r \t \0 and \u{..} for other control chars
 void debug_str(std::string& out, const char* s, size_t n) {
@@ -154,7 +176,7 @@ void format_range(const Batch& b, uint64_t r0, uint64_t r1, std::string& out, ui
         const bool flag = (h.flags & PSA_FLAG_MAPPED) != 0;
         mapped += flag;
         out += flag ? "(true, " : "(false, ";
-        debug_str(out, b.ids.data() + b.id_off[i], (size_t)(b.id_off[i + 1] - b.id_off[i]));
+        debug_str(out, (const char*)b.text.p + b.id_off[i], b.id_len[i]);
         out += ", [";
         for (uint32_t j = 0; j < h.n_tx; j++) {
             if (j) out += ", ";
@@ -175,7 +197,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     if (!batch_reads) batch_reads = 1ull << 20;
     const auto t0 = std::chrono::steady_clock::now();
 
-    LineReader in;
+    ByteSource in;
     if (!in.open(fastq_path)) return PSA_ERR_IO;
     FILE* out = stdout;
     const bool own_out = out_path && strcmp(out_path, "-") != 0;
@@ -200,12 +222,21 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     std::condition_variable cv;
     int reader_rc = PSA_OK;
     bool abort_all = false;
+    double busy_reader = 0, busy_mapper = 0, busy_writer = 0;  // seconds spent working (not waiting) per stage
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+    };
 
-    // stage 1: FASTQ text -> batch buffers (four-line records; id = header up to the first blank,
-    // as bio::io::fastq::Record::id)
+    // stage 1: raw FASTQ text -> pinned block + record table (four-line records; id = header up to the
+    // first blank, as bio::io::fastq::Record::id).  Bytes after the last complete record of a block are
+    // carried over to the next one.
+    const uint64_t block_bytes = std::max<uint64_t>(batch_reads * 400, 1ull << 22);
     std::thread reader([&]() {
         int s = 0;
-        bool done = false;
+        bool done = false, eof = false;
+        std::vector<uint8_t> carry;
+        std::vector<uint64_t> nl;
         while (!done) {
             Batch& b = slot[s];
             {
@@ -213,34 +244,87 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 cv.wait(lk, [&]() { return b.state == 0 || abort_all; });
                 if (abort_all) return;
             }
-            b.clear();
-            b.id_off.push_back(0);
+            const auto tr0 = now();
             int err = PSA_OK;
-            while (b.n < batch_reads) {
-                const char* l;
-                size_t n;
-                if (!in.next(l, n)) { done = true; break; }
-                if (n == 0) continue;  // blank line between records
-                if (l[0] != '@') { err = PSA_ERR_IO; break; }
-                size_t e = 1;
-                while (e < n && l[e] != ' ' && l[e] != '\t') e++;
-                b.ids.append(l + 1, e - 1);
-                b.id_off.push_back(b.ids.size());
-                if (!in.next(l, n)) { err = PSA_ERR_IO; break; }
-                if ((err = b.seq.reserve(b.seq_len + n + 64, b.seq_len))) break;
-                memcpy(b.seq.p + b.seq_len, l, n);
-                b.off.push_back(b.seq_len);
-                b.len.push_back((uint32_t)n);
-                b.seq_len += n;
-                const char* q;
-                size_t qn;
-                if (!in.next(q, qn) || qn == 0 || q[0] != '+') { err = PSA_ERR_IO; break; }
-                if (!in.next(q, qn)) { err = PSA_ERR_IO; break; }
-                b.n++;
+            b.n = 0; b.tx_used = 0; b.last = false; b.text_len = 0;
+            uint64_t have = 0;
+            for (;;) {
+                const uint64_t want = std::max<uint64_t>(block_bytes, carry.size() + (1u << 20));
+                if ((err = b.text.reserve(want + 64, have))) break;
+                if (!have && !carry.empty()) {
+                    memcpy(b.text.p, carry.data(), carry.size());
+                    have = carry.size();
+                    carry.clear();
+                }
+                if (!eof) {
+                    const uint64_t room = b.text.cap - 64 - have;
+                    const size_t got = in.read(b.text.p + have, room);
+                    have += got;
+                    if (got < room) eof = true;
+                }
+                if (eof && have && b.text.p[have - 1] != '\n') b.text.p[have++] = '\n';  // unterminated last line
+                index_newlines(b.text.p, have, num_threads, nl);
+                if (nl.size() >= 4 || eof) break;
+                // one record larger than the block: grow and read more
+                if ((err = b.text.reserve(2 * b.text.cap, have))) break;
             }
+            if (!err) {
+                // trailing blank lines at the end of the file are not records
+                uint64_t n_lines = nl.size();
+                auto blank = [&](uint64_t i) {
+                    const uint64_t start = i ? nl[i - 1] + 1 : 0;
+                    return nl[i] == start || (nl[i] == start + 1 && b.text.p[start] == '\r');
+                };
+                if (eof)
+                    while (n_lines && blank(n_lines - 1)) n_lines--;
+                uint64_t n_rec = std::min<uint64_t>(n_lines / 4, batch_reads);
+                if (eof && n_rec == n_lines / 4 && (n_lines & 3)) err = PSA_ERR_IO;  // truncated last record
+                b.off.resize(n_rec); b.len.resize(n_rec); b.id_off.resize(n_rec); b.id_len.resize(n_rec);
+                std::vector<int> bad(num_threads, 0);
+                std::vector<std::thread> th;
+                for (uint32_t t = 0; t < num_threads; t++) {
+                    th.emplace_back([&, t]() {
+                        const uint8_t* x = b.text.p;
+                        for (uint64_t r = n_rec * t / num_threads; r < n_rec * (t + 1) / num_threads; r++) {
+                            const uint64_t l0 = r ? nl[4 * r - 1] + 1 : 0, e0 = nl[4 * r];
+                            const uint64_t l1 = e0 + 1;
+                            uint64_t e1 = nl[4 * r + 1];
+                            const uint64_t l2 = e1 + 1;
+                            if (x[l0] != '@' || x[l2] != '+') {
+                                if (!bad[t]) bad[t] = 1 + (int)std::min<uint64_t>(r, 0x7ffffffe);
+                                continue;
+                            }
+                            if (e1 > l1 && x[e1 - 1] == '\r') e1--;
+                            uint64_t ie = l0 + 1;
+                            while (ie < e0 && x[ie] != ' ' && x[ie] != '\t' && x[ie] != '\r') ie++;
+                            b.id_off[r] = l0 + 1;
+                            b.id_len[r] = (uint32_t)(ie - l0 - 1);
+                            b.off[r] = l1;
+                            b.len[r] = (uint32_t)(e1 - l1);
+                        }
+                    });
+                }
+                for (auto& x : th) x.join();
+                uint64_t first_bad = n_rec;
+                for (uint32_t t = 0; t < num_threads; t++)
+                    if (bad[t]) first_bad = std::min<uint64_t>(first_bad, (uint64_t)bad[t] - 1);
+                if (first_bad < n_rec) {  // the complete records before the bad one are still processed
+                    n_rec = first_bad;
+                    err = PSA_ERR_IO;
+                }
+                b.n = n_rec;
+                b.text_len = n_rec ? nl[4 * n_rec - 1] + 1 : 0;
+                if (!err) {
+                    carry.assign(b.text.p + b.text_len, b.text.p + have);
+                    // only blank lines may remain at the end of the file
+                    if (eof && n_rec == n_lines / 4) carry.clear();
+                    if (eof && carry.empty()) done = true;
+                }
+            }
+            busy_reader += secs(tr0, now());
             std::unique_lock<std::mutex> lk(mu);
             if (err) {
-                reader_rc = err;  // the complete records before the bad one are still processed
+                reader_rc = err;
                 done = true;
             }
             b.last = done;
@@ -264,6 +348,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 cv.wait(lk, [&]() { return b.state == 2 || abort_all; });
                 if (abort_all) return;
             }
+            const auto tw0 = now();
             if (b.n) {
                 std::vector<std::thread> th;
                 for (uint32_t t = 0; t < num_threads; t++) {
@@ -286,6 +371,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                     next_tick = (n_reads / 1000000 + 1) * 1000000;
                 }
             }
+            busy_writer += secs(tw0, now());
             const bool last = b.last;
             {
                 std::unique_lock<std::mutex> lk(mu);
@@ -305,14 +391,15 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&]() { return b.state == 1; });
         }
+        const auto tm0 = now();
         if (b.n) {
             map_rc = b.hits.reserve(b.n * sizeof(psa_hit), 0);
             if (!map_rc) map_rc = b.tx.reserve(std::max<uint64_t>(b.n * 16 * 4, 4096), 0);
             psa_read_batch r{};
             r.format = PSA_READS_ASCII;
             r.location = PSA_MEM_HOST;
-            r.data = b.seq.p;
-            r.data_len = b.seq_len;
+            r.data = b.text.p;
+            r.data_len = b.text_len;
             r.read_off = b.off.data();
             r.read_len = b.len.data();
             r.n_reads = b.n;
@@ -330,6 +417,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             }
             b.tx_used = o.tx_used;
         }
+        busy_mapper += secs(tm0, now());
         const bool last = b.last;
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -349,12 +437,15 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     if (own_out) fclose(out);
     in.close();
     psa_mapper_destroy(mapper);
-    for (auto& b : slot) { b.seq.release(); b.hits.release(); b.tx.release(); }
+    for (auto& b : slot) { b.text.release(); b.hits.release(); b.tx.release(); }
     if (stats) {
         stats->reads = n_reads;
         stats->mapped = n_mapped;
         stats->aligned = n_aligned;
         stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        stats->reader_seconds = busy_reader;
+        stats->mapper_seconds = busy_mapper;
+        stats->writer_seconds = busy_writer;
     }
     if (map_rc) return map_rc;
     if (reader_rc) return reader_rc;  // the reference panics on a malformed record (:446)

@@ -64,7 +64,8 @@ class _ResultBatch(C.Structure):
 
 
 class _ProcessStats(C.Structure):
-    _fields_ = [("reads", C.c_uint64), ("mapped", C.c_uint64), ("aligned", C.c_uint64), ("seconds", C.c_double)]
+    _fields_ = [("reads", C.c_uint64), ("mapped", C.c_uint64), ("aligned", C.c_uint64), ("seconds", C.c_double),
+                ("reader_seconds", C.c_double), ("mapper_seconds", C.c_double), ("writer_seconds", C.c_double)]
 
 
 class _Events(C.Structure):
@@ -553,7 +554,9 @@ def process_reads_file(fastq_path, index, out_path=None, num_threads=2, batch_re
     st = _ProcessStats()
     _check(lib().psa_process_reads(ix.h, os.fsencode(fastq_path), os.fsencode(out_path) if out_path else None,
                                    int(num_threads), int(batch_reads), 1 if progress else 0, C.byref(st)))
-    return {"reads": int(st.reads), "mapped": int(st.mapped), "aligned": int(st.aligned), "seconds": float(st.seconds)}
+    return {"reads": int(st.reads), "mapped": int(st.mapped), "aligned": int(st.aligned), "seconds": float(st.seconds),
+            "reader_seconds": float(st.reader_seconds), "mapper_seconds": float(st.mapper_seconds),
+            "writer_seconds": float(st.writer_seconds)}
 
 
 def process_reads(records, index, outdir=None, num_threads=1, out=None, batch_reads=1 << 20):

@@ -314,6 +314,15 @@ def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
     assert st["reads"] == len(want) and st["mapped"] == sum(1 for l in want if l.startswith("(true"))
     st = pkg.process_reads_file(os.path.join(GOLDEN, "small.fq.gz"), pa, str(out), num_threads=1)
     assert out.read_text().splitlines() == want and st["reads"] == len(want)
+    # CRLF line ends, trailing blank lines, a batch size that does not divide the file
+    crlf = tmp_path / "crlf.fq"
+    crlf.write_bytes(raw.replace(b"\n", b"\r\n") + b"\r\n\r\n")
+    st = pkg.process_reads_file(str(crlf), pa, str(out), num_threads=2, batch_reads=777)
+    assert out.read_text().splitlines() == want and st["reads"] == len(want)
+    empty = tmp_path / "empty.fq"
+    empty.write_bytes(b"")
+    st = pkg.process_reads_file(str(empty), pa, str(out))
+    assert st["reads"] == 0 and out.read_text() == ""
     # the Python driver prints the same lines
     import io
     buf = io.StringIO()
@@ -325,3 +334,5 @@ def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
     with pytest.raises(pkg.PsaError) as e:
         pkg.process_reads_file(str(bad), pa, str(out))
     assert e.value.code == -7
+    n_good = raw[:raw.index(b"\n", len(raw) // 2) + 1].count(b"\n") // 4
+    assert out.read_text().splitlines() == want[:n_good]      # the records before the bad one were processed
