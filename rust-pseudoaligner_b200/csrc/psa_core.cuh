@@ -84,11 +84,50 @@ PSA_HD uint64_t mix64(uint64_t x) {  // murmur3 finaliser (a bijection on 64 bit
 // ---------------------------------------------------------------------------------------------
 // word loaders: the same text reads the index through the read-only path on the device
 // ---------------------------------------------------------------------------------------------
-struct GLoad {  // immutable index memory (global, ld.global.nc)
+// L2 residency hints (PSA_L2_HINTS): the big single-use table (`values`, 8 bytes used per 32-byte
+// sector, no reuse) is loaded evict-first so that it does not push the small hot tables (node
+// records, unitig sequence, class windows) out of the 126 MB L2; those are loaded evict-last.
+#ifndef PSA_L2_HINTS
+#define PSA_L2_HINTS 1
+#endif
+#if defined(__CUDA_ARCH__) && PSA_L2_HINTS
+__device__ __forceinline__ uint64_t l2_policy_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t ld_u64_first(const uint64_t* a) {
+    uint64_t v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(l2_policy_first()));
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_u64_last(const uint64_t* a) {
+    uint64_t v;
+    asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(l2_policy_last()));
+    return v;
+}
+__device__ __forceinline__ void ld_v4_last(const void* a, uint64_t& x, uint64_t& y, uint64_t& z, uint64_t& w) {
+    asm("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(a), "l"(l2_policy_last()));
+}
+#elif defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint64_t ld_u64_first(const uint64_t* a) { return __ldg(a); }
+__device__ __forceinline__ uint64_t ld_u64_last(const uint64_t* a) { return __ldg(a); }
+__device__ __forceinline__ void ld_v4_last(const void* a, uint64_t& x, uint64_t& y, uint64_t& z, uint64_t& w) {
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(a));
+}
+#endif
+
+struct GLoad {  // immutable index memory (global, ld.global.nc): the unitig sequence
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const {
 #ifdef __CUDA_ARCH__
-        return __ldg(p + i);
+        return ld_u64_last(p + i);
 #else
         return p[i];
 #endif
@@ -398,7 +437,7 @@ PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t&
     if (st) { st->levels = levels; st->hit = in; st->verified = 0; }
     if (!in) return false;
 #ifdef __CUDA_ARCH__
-    uint64_t v = __ldg(ix.values + slot);
+    uint64_t v = ld_u64_first(ix.values + slot);
 #else
     uint64_t v = ix.values[slot];
 #endif
@@ -410,7 +449,7 @@ PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t&
     if (st) st->verified = 1;
     // the unitig k-mer and the node's start are independent loads: both addresses come from `v`
 #ifdef __CUDA_ARCH__
-    uint64_t start = __ldg(&ix.nodes[n].start_len) & kStartMask;
+    uint64_t start = ld_u64_last(&ix.nodes[n].start_len) & kStartMask;
 #else
     uint64_t start = ix.nodes[n].start_len & kStartMask;
 #endif
@@ -484,7 +523,7 @@ PSA_HD NodeView load_node_view(const NodeRec* r) {
     NodeView v;
 #ifdef __CUDA_ARCH__
     uint64_t a, b, c, d;
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(r));
+    ld_v4_last(r, a, b, c, d);
     v.start = a & kStartMask;
     v.len = (uint32_t)(a >> 40);
     v.eq = (uint32_t)b;
@@ -673,7 +712,7 @@ PSA_HD ClassWin load_class_win(const ClassWin* p) {
     ClassWin c;
 #ifdef __CUDA_ARCH__
     uint64_t a, b0, b1, b2;
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b0), "=l"(b1), "=l"(b2) : "l"(p));
+    ld_v4_last(p, a, b0, b1, b2);
     c.lo = (uint32_t)a;
     c.len = (uint32_t)(a >> 32);
     c.bits[0] = b0; c.bits[1] = b1; c.bits[2] = b2;
