@@ -464,6 +464,8 @@ struct psa_mapper {
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 2;   // 0: every read goes to the cooperative kernel
     uint32_t fast_max_small = 32;
+    bool tile_reads = false;    // PSA_TILE=1: k_map_thread stages the packed reads of fixed-stride batches in shared
+                                // memory with one bulk copy (TMA) per CTA; measured 2 % slower than reading them through L1
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[2];
@@ -476,11 +478,22 @@ struct psa_mapper {
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
 
+// shared memory of the TILE variant (packed words of 128 reads + the mbarrier), 0 = not eligible
+static uint32_t tile_smem_bytes(const ReadsView& rv) {
+    if (rv.woff || rv.len || !rv.wstride) return 0;
+    const uint64_t total = 16 + (uint64_t)kThreadBlock * rv.wstride * 8;
+    return total > 12 * 1024 ? 0 : (uint32_t)total;  // longer reads keep the L1 for the index instead
+}
 template <bool EV>
-static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p) {
+static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p, uint32_t smem) {
     const unsigned grid = nblocks(p.reads.n, kThreadBlock);
-    if (m->ix->kw == 1) k_map_thread<1, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
-    else k_map_thread<2, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    if (smem) {
+        if (m->ix->kw == 1) k_map_thread<1, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
+    } else {
+        if (m->ix->kw == 1) k_map_thread<1, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+    }
 }
 // second pass over the reads k_seed_scan seeded: persistent warps, the list length is on the device
 template <bool EV>
@@ -588,6 +601,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("PSA_TILE")) m->tile_reads = atoi(e) != 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
         int g = atoi(e);
         if (g == 0 || g == 8 || g == 16 || g == 32) m->scan_width = (uint32_t)g;
@@ -704,9 +718,15 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             rv.wstride = ((uint64_t)r->fixed_len + 31) / 32;
             if ((rc = m->words.ensure(n * rv.wstride * 8 + 16))) return rc;
         }
-        if (!r->read_len && !r->read_off)
-            k_pack_ascii_fixed<<<(unsigned)std::min<uint64_t>(nblocks(n * rv.wstride, 256), 148 * 32), 256, 0, st>>>(
-                (const uint8_t*)r->data, r->stride, r->fixed_len, n, m->words.as<uint64_t>());
+        if (!r->read_len && !r->read_off) {
+            // 32-bit word indices inside the kernel: slices of at most 2^31 words
+            const uint64_t per = std::max<uint64_t>(1, (1ull << 31) / rv.wstride);
+            for (uint64_t r0 = 0; r0 < n; r0 += per) {
+                const uint64_t nr = std::min(per, n - r0);
+                k_pack_ascii_fixed<<<(unsigned)std::min<uint64_t>(nblocks(nr * rv.wstride, 256), 148 * 32), 256, 0, st>>>(
+                    (const uint8_t*)r->data + r0 * r->stride, r->stride, r->fixed_len, nr, m->words.as<uint64_t>() + r0 * rv.wstride);
+            }
+        }
         else
             k_pack_ascii<<<(unsigned)std::min<uint64_t>(nblocks(n * 32, 256), 148 * 64), 256, 0, st>>>(
                 (const uint8_t*)r->data, r->read_off, r->stride, r->read_len, r->fixed_len, rv.woff, rv.wstride, n,
@@ -771,7 +791,8 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 p.seeded_count = m->novel_cursor.as<unsigned long long>() + 4;
                 p.seeded_ev = EV ? m->seeded_ev.as<uint4>() : nullptr;
             }
-            if ((rc = timed(0, [&]() { launch_map_thread<EV>(m, st, p); }))) return rc;
+            const uint32_t tile_smem = m->tile_reads ? tile_smem_bytes(rv) : 0;
+            if ((rc = timed(0, [&]() { launch_map_thread<EV>(m, st, p, tile_smem); }))) return rc;
             if (m->scan_width) {
                 if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
                 if ((rc = timed(0, [&]() { launch_map_thread_seeded<EV>(m, st, p); }))) return rc;

@@ -264,13 +264,13 @@ __device__ __forceinline__ uint64_t pack32(const uint8_t* s, uint32_t nb) {
     if (nb < 32) v &= ~0ULL << (64 - 2 * nb);
     return v;
 }
-// fixed read length: one thread per output word
+// fixed read length: one thread per output word (32-bit index arithmetic: the host splits larger batches)
 __global__ void k_pack_ascii_fixed(const uint8_t* ascii, uint64_t astride, uint32_t len, uint64_t n, uint64_t* words) {
     const uint32_t nw = (len + 31) >> 5;
-    const uint64_t total = n * nw;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += gridDim.x * (uint64_t)blockDim.x) {
-        uint64_t r = i / nw;
-        uint32_t j = (uint32_t)(i - r * nw);
+    const uint32_t total = (uint32_t)(n * nw);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t r = i / nw;
+        const uint32_t j = i - r * nw;
         words[i] = pack32(ascii + r * astride + 32 * j, min(32u, len - 32 * j));
     }
 }
@@ -734,14 +734,64 @@ constexpr int kThreadBlock = 128;
 #define PSA_THREAD_MIN_BLOCKS 8
 #endif
 
+// ---- bulk asynchronous copy (TMA, non-tensor form) + mbarrier, for the read tiles ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
 // HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
 // first seed search was made by k_seed_scan), persistent warps striding over that list.
+// TILE (first pass, fixed word stride): the packed words of the CTA's 128 reads arrive in shared
+// memory as one bulk asynchronous copy (cp.async.bulk + mbarrier: TMA) and every thread maps its
+// read from there -- the read's words are touched ~10 times along the path, and through L1 they
+// kept being evicted by the index gathers.  (Fusing the ASCII packing in as well was measured:
+// the 19 KB ASCII tile per CTA shrinks L1 so much that the kernel loses 1 ms.)
 // (Holding a <= 192-base read in six registers instead of re-reading its words through L1 was
 // measured: 3.93 ms vs 3.48 ms -- the extra registers spill at the 64-register cap.  Not used.)
-template <int KW, bool EV, bool HINT>
+template <int KW, bool EV, bool HINT, bool TILE = false>
 __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
                                                                                      const __grid_constant__ MapParams p) {
     const unsigned lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint64_t* my_words = nullptr;
+    if (TILE) {
+        // layout: [mbarrier (16 B slot) | packed words of the CTA's reads]
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+        uint64_t* pw = reinterpret_cast<uint64_t*>(smem + 16);
+        const uint64_t r0 = blockIdx.x * (uint64_t)kThreadBlock;
+        const uint32_t nr = (uint32_t)min((uint64_t)kThreadBlock, p.reads.n - r0);
+        const uint32_t nw = (uint32_t)p.reads.wstride;
+        const uint64_t* src = p.reads.words + r0 * nw;
+        const uint32_t bytes = nr * nw * 8;
+        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            if (threadIdx.x == 0) {
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(pw, src, bytes, bar);
+            }
+            __syncthreads();  // the barrier is initialised before anyone polls it
+            mbar_wait(bar, 0);
+        } else {  // odd-sized last tile: plain loads
+            for (uint32_t i = threadIdx.x; i < nr * nw; i += kThreadBlock) pw[i] = src[i];
+            __syncthreads();
+        }
+        my_words = pw + threadIdx.x * nw;
+    }
     const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
     const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
     // warp-uniform trip count: the hand-over below uses full-warp votes
@@ -765,7 +815,7 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
             const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
             L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
             DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
-            ThreadResult res = map_read_thread<KW, EV>(ix, PLoad{p.reads.words + wo}, L, p.allowed_mismatches, p.max_probes,
+            ThreadResult res = map_read_thread<KW, EV>(ix, PLoad{TILE ? my_words : p.reads.words + wo}, L, p.allowed_mismatches, p.max_probes,
                                                        p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
                                                        HINT ? hint : nullptr);
             defer = res.deferred;

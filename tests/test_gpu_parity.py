@@ -336,3 +336,20 @@ def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
     assert e.value.code == -7
     n_good = raw[:raw.index(b"\n", len(raw) // 2) + 1].count(b"\n") // 4
     assert out.read_text().splitlines() == want[:n_good]      # the records before the bad one were processed
+
+
+def test_tma_read_tiles(orc_index_for, fixture_fasta, monkeypatch):
+    """PSA_TILE=1: the thread-per-read kernel stages the packed reads of a fixed-stride batch in shared
+    memory with one bulk asynchronous copy per CTA (an option, off by default: measured slower).
+    Same results, including a batch whose last tile is partial and odd-sized."""
+    monkeypatch.setenv("PSA_TILE", "1")
+    ix = orc_index_for(20)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0)
+    rng = np.random.default_rng(21)
+    for L, n in ((150, 128 * 37 + 61), (91, 1000), (60, 127), (33, 3)):
+        reads = util.sample_reads(rng, fixture_fasta[1], n, L, p_sub=0.01, mix=(0.85, 0.1, 0.05))
+        data = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+        want_hits, want_tx, _, _ = _oracle(ix, reads)
+        got_hits, got_tx = pa.mapper.map_ascii_fixed(data, n, L)
+        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    pa.close()
