@@ -165,7 +165,7 @@ int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
  * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
  * needs more than max_probes positions, it visits more than 4 distinct classes, or its
  * smallest class has more than max_small members.  max_probes = 0 sends every read to the
- * cooperative kernel.  Defaults 2 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
+ * cooperative kernel.  Defaults ceil(k/3)+2 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
  * not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
 /* Tuning: reads whose FIRST seed search is too long for one thread go to k_seed_scan, where

@@ -462,7 +462,7 @@ struct psa_mapper {
     uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
     uint64_t pool_cap = 1ull << 18;   // entries (uint4) of the shared overflow pool; grows on demand
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
-    uint32_t fast_probes = 2;   // 0: every read goes to the cooperative kernel
+    uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
     bool tile_reads = false;    // PSA_TILE=1: k_map_thread stages the packed reads of fixed-stride batches in shared
                                 // memory with one bulk copy (TMA) per CTA; measured 2 % slower than reading them through L1
@@ -599,6 +599,9 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
     }
+    // one substitution knocks out the seeds at positions (e-k, e]: ceil(k/3) stride-3 positions; two more and a
+    // read with a single error in its head is seeded by its own thread (measured best on B200)
+    m->fast_probes = (ix->d.k + 2) / 3 + 2;
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE")) m->tile_reads = atoi(e) != 0;
