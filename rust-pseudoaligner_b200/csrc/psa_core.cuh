@@ -807,11 +807,18 @@ PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
 // One thread = one read: the policy of the fast kernel (k_map_thread).  It runs the same
 // map_read_nodes text with every step done serially by the calling thread, and gives a read
 // up ("defer") as soon as it needs something a single thread does badly: a seed scan longer
-// than max_probes positions, more than kThreadClasses distinct classes, or a smallest class
-// with more than max_small members.  Deferred reads are redone from scratch by the
-// cooperative kernel (k_map over the deferred list), so the split never changes a result.
+// than max_probes positions, more than kThreadWide distinct WIDE classes, or only wide classes
+// with a smallest one of more than max_small members.  Deferred reads are redone from scratch
+// by the cooperative kernel (k_map over the deferred list), so the split never changes a result.
+//
+// Classes are intersected ONLINE: the window of every newly visited class is ANDed into one
+// accumulator as the walk goes (any number of narrow classes in constant registers, and the
+// window load overlaps the next compare); only wide classes are listed, for the final filter.
+// eq_id needs no list either: the result equals a visited class iff its size equals the smallest
+// visited class length, and then it is the smallest-id class of that length.
 // ---------------------------------------------------------------------------------------------
-constexpr int kThreadClasses = 8;
+constexpr int kThreadWide = 3;
+constexpr int kThreadRecent = 4;
 constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
@@ -830,8 +837,13 @@ struct ThreadCtx {
     const DevIndex& ix;
     RD rd;
     uint32_t k, max_probes;
-    uint32_t eq[kThreadClasses], len[kThreadClasses];  // offsets are re-read from eq_off when needed
-    uint32_t n_list;
+    // online class state
+    uint32_t first_eq, first_len;  // the first class visited; its window is fetched only when a second class shows up
+    bool multi;                    // more than one distinct class visited
+    uint32_t min_len, min_eq;      // smallest class length seen, and the smallest id among the classes of that length
+    WinAcc acc;                    // AND of the narrow classes' windows
+    uint32_t wide_eq[kThreadWide], wide_len[kThreadWide], n_wide;
+    uint32_t recent[kThreadRecent];  // last few class ids (skips most repeated window loads; repeats are harmless)
     bool defer;
     uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
     bool seeded;
@@ -841,10 +853,14 @@ struct ThreadCtx {
     ThreadEvents ev;
 
     PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
-        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), n_list(0), defer(false), why(0), seeded(false),
+        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), first_eq(kNone), first_len(0), multi(false),
+          min_len(kNone), min_eq(kNone), n_wide(0), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
+        acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
     PSA_UNROLL
-        for (int j = 0; j < kThreadClasses; j++) { eq[j] = kNone; len[j] = 0; }
+        for (int j = 0; j < kThreadWide; j++) { wide_eq[j] = kNone; wide_len[j] = 0; }
+    PSA_UNROLL
+        for (int j = 0; j < kThreadRecent; j++) recent[j] = kNone;
     }
     PSA_HD bool abort() const { return defer; }
     PSA_HD uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
@@ -922,56 +938,87 @@ struct ThreadCtx {
     }
     PSA_HD uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
     PSA_HD uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
-    // nodes.push: only the distinct classes matter (intersection is idempotent, ref :352-355)
-    PSA_HD void push(uint32_t /*node_id*/, const NodeView& nv) {
-        if (EV) ev.visits++;
+    // AND one class into the running intersection (narrow), or list it (wide)
+    PSA_HD void and_class(uint32_t e, uint32_t l) {
+        const ClassWin c = load_class_win(ix.class_win + e);
+        if (c.len != kWinWide) {
+            winacc_and(acc, c);
+            return;
+        }
         bool dup = false;
     PSA_UNROLL
-        for (int j = 0; j < kThreadClasses; j++) dup |= (j < (int)n_list && eq[j] == nv.eq);
+        for (int j = 0; j < kThreadWide; j++) dup |= (j < (int)n_wide && wide_eq[j] == e);
         if (dup) return;
-        if (n_list >= (uint32_t)kThreadClasses) {
+        if (n_wide >= (uint32_t)kThreadWide) {
             defer = true;
             why = 2;
             return;
         }
     PSA_UNROLL
-        for (int j = 0; j < kThreadClasses; j++)
-            if (j == (int)n_list) { eq[j] = nv.eq; len[j] = nv.class_len; }
-        n_list++;
+        for (int j = 0; j < kThreadWide; j++)
+            if (j == (int)n_wide) { wide_eq[j] = e; wide_len[j] = l; }
+        n_wide++;
+    }
+    // nodes.push: only the classes matter, and the intersection is idempotent (ref :352-355)
+    PSA_HD void push(uint32_t /*node_id*/, const NodeView& nv) {
+        if (EV) ev.visits++;
+        bool dup = false;
+    PSA_UNROLL
+        for (int j = 0; j < kThreadRecent; j++) dup |= (recent[j] == nv.eq);
+        if (dup) return;
+    PSA_UNROLL
+        for (int j = kThreadRecent - 1; j > 0; j--) recent[j] = recent[j - 1];
+        recent[0] = nv.eq;
+        if (EV) ev.members += nv.class_len;  // (a class revisited after kThreadRecent others is counted again)
+        if (nv.class_len < min_len || (nv.class_len == min_len && nv.eq < min_eq)) {
+            min_len = nv.class_len;
+            min_eq = nv.eq;
+        }
+        if (first_eq == kNone) {
+            first_eq = nv.eq;
+            first_len = nv.class_len;
+            return;
+        }
+        if (!multi) {
+            if (nv.eq == first_eq) return;
+            multi = true;
+            and_class(first_eq, first_len);
+        }
+        and_class(nv.eq, nv.class_len);
     }
 };
 
 // All visited classes are wide: the reference's list scheme by one thread.  Members of the
-// smallest class (index s) that every other listed class contains, ascending; each other
+// smallest listed class (index s) that every other listed class contains, ascending; each other
 // class is searched only in the suffix after its previous match (ref :399-404).
 // out == nullptr counts.
 template <int KW, bool EV, class RD>
 PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, uint32_t* out) {
     const uint32_t* mem = w.ix.eq_mem;
-    uint32_t cur[kThreadClasses];
+    uint32_t cur[kThreadWide];
     PSA_UNROLL
-    for (int j = 0; j < kThreadClasses; j++) cur[j] = 0;
+    for (int j = 0; j < kThreadWide; j++) cur[j] = 0;
     uint32_t s_len = 0, s_eq = 0;
     PSA_UNROLL
-    for (int j = 0; j < kThreadClasses; j++)
-        if (j == s) { s_len = w.len[j]; s_eq = w.eq[j]; }
+    for (int j = 0; j < kThreadWide; j++)
+        if (j == s) { s_len = w.wide_len[j]; s_eq = w.wide_eq[j]; }
     const uint64_t s_off = ld_off(w.ix.eq_off + s_eq);
     uint32_t count = 0;
     for (uint32_t i = 0; i < s_len; i++) {
         const uint32_t x = ld_mem(mem + s_off + i);
         bool alive = true;
     PSA_UNROLL
-        for (int j = 0; j < kThreadClasses; j++) {
-            if (j == s || j >= (int)w.n_list || !alive) continue;
-            const uint32_t* v = mem + ld_off(w.ix.eq_off + w.eq[j]);
-            uint32_t lo = cur[j], hi = w.len[j];
+        for (int j = 0; j < kThreadWide; j++) {
+            if (j == s || j >= (int)w.n_wide || !alive) continue;
+            const uint32_t* v = mem + ld_off(w.ix.eq_off + w.wide_eq[j]);
+            uint32_t lo = cur[j], hi = w.wide_len[j];
             while (lo < hi) {
                 uint32_t mid = lo + ((hi - lo) >> 1);
                 if (ld_mem(v + mid) < x) lo = mid + 1;
                 else hi = mid;
             }
             cur[j] = lo;
-            alive = lo < w.len[j] && ld_mem(v + lo) == x;
+            alive = lo < w.wide_len[j] && ld_mem(v + lo) == x;
         }
         if (alive) {
             if (out) out[count] = x;
@@ -1015,42 +1062,27 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, ui
         return res;
     }
     if (some) {
-        // smallest class first (ref :331-334); ties broken by id
-        int s = 0;
-        uint32_t s_len = w.len[0], s_eq = w.eq[0];
-    PSA_UNROLL
-        for (int j = 1; j < kThreadClasses; j++)
-            if (j < (int)w.n_list && (w.len[j] < s_len || (w.len[j] == s_len && w.eq[j] < s_eq))) {
-                s = j; s_len = w.len[j]; s_eq = w.eq[j];
-            }
         uint32_t count, eq_id;
-        WinAcc acc;
-        acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
-        if (w.n_list == 1) {
-            count = s_len;
-            eq_id = s_eq;
-            if (EV) w.ev.members += s_len;
+        int s = 0;  // smallest wide class (only used when every class is wide)
+        if (!w.multi) {
+            count = w.first_len;
+            eq_id = w.first_eq;
         } else {
-            // narrow classes: AND of their windows; wide ones filter what survives
-            uint32_t n_wide = 0;
+            if (w.acc.have) {
+                // wide classes filter what survived the windows (ref :399-404 on the candidates)
     PSA_UNROLL
-            for (int j = 0; j < kThreadClasses; j++) {
-                if (j >= (int)w.n_list) continue;
-                ClassWin c = load_class_win(ix.class_win + w.eq[j]);
-                if (c.len == kWinWide) n_wide++;
-                else winacc_and(acc, c);
-            }
-            if (acc.have) {
-                if (n_wide) {
-    PSA_UNROLL
-                    for (int j = 0; j < kThreadClasses; j++) {
-                        if (j >= (int)w.n_list || win_empty(acc.map)) continue;
-                        if (load_class_win(ix.class_win + w.eq[j]).len != kWinWide) continue;
-                        winacc_filter_list(acc, ix.eq_mem + ld_off(ix.eq_off + w.eq[j]), w.len[j]);
-                    }
+                for (int j = 0; j < kThreadWide; j++) {
+                    if (j >= (int)w.n_wide || win_empty(w.acc.map)) continue;
+                    winacc_filter_list(w.acc, ix.eq_mem + ld_off(ix.eq_off + w.wide_eq[j]), w.wide_len[j]);
                 }
-                count = win_popc(acc.map);
+                count = win_popc(w.acc.map);
             } else {
+                uint32_t s_len = w.wide_len[0], s_eq = w.wide_eq[0];  // smallest class first (ref :331-334)
+    PSA_UNROLL
+                for (int j = 1; j < kThreadWide; j++)
+                    if (j < (int)w.n_wide && (w.wide_len[j] < s_len || (w.wide_len[j] == s_len && w.wide_eq[j] < s_eq))) {
+                        s = j; s_len = w.wide_len[j]; s_eq = w.wide_eq[j];
+                    }
                 if (s_len > max_small) {  // long lists are the cooperative kernel's job
                     res.why = 3;
                     res.deferred = true;
@@ -1058,13 +1090,8 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, ui
                 }
                 count = thread_intersect_lists(w, s, (uint32_t*)nullptr);
             }
-            eq_id = kNone;  // the result equals a visited class iff that class has `count` members
-    PSA_UNROLL
-            for (int j = 0; j < kThreadClasses; j++)
-                if (j < (int)w.n_list && w.len[j] == count && w.eq[j] < eq_id) eq_id = w.eq[j];
-            if (EV)
-                for (int j = 0; j < kThreadClasses; j++)
-                    if (j < (int)w.n_list) w.ev.members += w.len[j];
+            // the result equals a visited class iff it has as many members as the smallest visited class
+            eq_id = count == w.min_len ? w.min_eq : kNone;
         }
         res.hit.coverage = coverage;
         res.hit.n_tx = count;
@@ -1079,7 +1106,7 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, ui
                 uint64_t o = 0;
                 uint32_t* dst = novel(count, o);
                 if (!dst) res.novel_overflow = true;
-                else if (acc.have) win_write(acc, dst);
+                else if (w.acc.have) win_write(w.acc, dst);
                 else thread_intersect_lists(w, s, dst);
                 res.hit.tx_off = o;
             }
