@@ -770,37 +770,32 @@ PSA_HD uint64_t ld_off(const uint64_t* p) {
     return *p;
 #endif
 }
-// Bits of `map` (a set over `base`) whose member the ascending list v[0..n) lacks; only the
-// candidates with rank % stride == phase are examined (the lanes of a group split them).
-PSA_HD Win win_absent_in_list(Win map, uint32_t base, const uint32_t* v, uint32_t n, uint32_t phase, uint32_t stride) {
-    Win kill{0, 0, 0};
-    uint32_t lo = 0, rank = 0;
-    for (int wi = 0; wi < 3; wi++) {
-        uint64_t w = wi == 0 ? map.w0 : wi == 1 ? map.w1 : map.w2;
-        uint64_t k = 0;
-        while (w) {
-            const uint32_t t = (uint32_t)ctz64(w);
-            w &= w - 1;
-            if (rank++ % stride != phase) continue;
-            const uint32_t x = base + 64 * wi + t;
-            uint32_t hi = n;  // search the suffix after the previous match (ref :399-404)
-            while (lo < hi) {
-                uint32_t mid = lo + ((hi - lo) >> 1);
-                if (ld_mem(v + mid) < x) lo = mid + 1;
-                else hi = mid;
-            }
-            if (!(lo < n && ld_mem(v + lo) == x)) k |= 1ULL << t;
-        }
-        if (wi == 0) kill.w0 = k;
-        else if (wi == 1) kill.w1 = k;
-        else kill.w2 = k;
+// The members of the ascending list v[0..n) that fall in [base, base + 192), as a window map over
+// `base`: one binary search for the first such member (the reference's own search, ref :404), then
+// the few that follow.  This is how a wide class is applied to the candidates the narrow classes'
+// windows have left: exact, and one search per class instead of one per candidate.
+PSA_HD Win win_of_list_range(const uint32_t* v, uint32_t n, uint32_t base) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (ld_mem(v + mid) < base) lo = mid + 1;
+        else hi = mid;
     }
-    return kill;
+    Win m{0, 0, 0};
+    for (; lo < n; lo++) {
+        const uint32_t x = ld_mem(v + lo);
+        if (x - base >= kWinBits) break;  // (x >= base here)
+        const uint32_t t = x - base;
+        const uint64_t bit = 1ULL << (t & 63);
+        if (t < 64) m.w0 |= bit;
+        else if (t < 128) m.w1 |= bit;
+        else m.w2 |= bit;
+    }
+    return m;
 }
 // drop from the accumulated set every member the (wide) class list v[0..n) lacks
 PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
-    Win kill = win_absent_in_list(a.map, a.base, v, n, 0, 1);
-    a.map = Win{a.map.w0 & ~kill.w0, a.map.w1 & ~kill.w1, a.map.w2 & ~kill.w2};
+    a.map = win_and(a.map, win_of_list_range(v, n, a.base));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -818,6 +813,10 @@ PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
 // visited class length, and then it is the smallest-id class of that length.
 // ---------------------------------------------------------------------------------------------
 constexpr int kThreadWide = 3;
+#ifndef PSA_WIDE_INLINE
+#define PSA_WIDE_INLINE 2
+#endif
+constexpr uint32_t kThreadWideInline = PSA_WIDE_INLINE;  // further wide classes applied on arrival before giving up
 constexpr int kThreadRecent = 4;
 constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
@@ -842,7 +841,7 @@ struct ThreadCtx {
     bool multi;                    // more than one distinct class visited
     uint32_t min_len, min_eq;      // smallest class length seen, and the smallest id among the classes of that length
     WinAcc acc;                    // AND of the narrow classes' windows
-    uint32_t wide_eq[kThreadWide], wide_len[kThreadWide], n_wide;
+    uint32_t wide_eq[kThreadWide], wide_len[kThreadWide], n_wide, n_inline;
     uint32_t recent[kThreadRecent];  // last few class ids (skips most repeated window loads; repeats are harmless)
     bool defer;
     uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
@@ -854,7 +853,7 @@ struct ThreadCtx {
 
     PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
         : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), first_eq(kNone), first_len(0), multi(false),
-          min_len(kNone), min_eq(kNone), n_wide(0), defer(false), why(0), seeded(false),
+          min_len(kNone), min_eq(kNone), n_wide(0), n_inline(0), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
         acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
     PSA_UNROLL
@@ -950,6 +949,13 @@ struct ThreadCtx {
         for (int j = 0; j < kThreadWide; j++) dup |= (j < (int)n_wide && wide_eq[j] == e);
         if (dup) return;
         if (n_wide >= (uint32_t)kThreadWide) {
+            // no room to remember it: apply it now to the candidates the windows have left (the filter
+            // is idempotent and commutes with the ANDs still to come); without any window yet, give up
+            if (acc.have && n_inline < kThreadWideInline) {
+                n_inline++;
+                winacc_filter_list(acc, ix.eq_mem + ld_off(ix.eq_off + e), l);
+                return;
+            }
             defer = true;
             why = 2;
             return;

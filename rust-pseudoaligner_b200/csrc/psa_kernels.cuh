@@ -631,20 +631,13 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
                     n_wide += w.g.shfl_xor(n_wide, d);
                 }
                 if (acc.have) {
-                    if (n_wide) {  // wide classes filter the surviving candidates, the lanes sharing the searches
+                    if (n_wide) {  // wide classes filter the surviving candidates (one range lookup per class)
                         for (uint32_t j = 0; j < w.n_list && !win_empty(acc.map); j++) {
                             uint32_t e, l;
                             uint64_t o;
                             w.entry(j, e, l, o);
                             if (__ldg(&ix.class_win[e].len) != kWinWide) continue;
-                            Win kill = win_absent_in_list(acc.map, acc.base, ix.eq_mem + o, l, lane, G);
-#pragma unroll
-                            for (int d = G / 2; d; d >>= 1) {
-                                kill.w0 |= w.g.shfl_xor(kill.w0, d);
-                                kill.w1 |= w.g.shfl_xor(kill.w1, d);
-                                kill.w2 |= w.g.shfl_xor(kill.w2, d);
-                            }
-                            acc.map = Win{acc.map.w0 & ~kill.w0, acc.map.w1 & ~kill.w1, acc.map.w2 & ~kill.w2};
+                            winacc_filter_list(acc, ix.eq_mem + o, l);  // uniform across the group
                         }
                     }
                     count = win_popc(acc.map);
