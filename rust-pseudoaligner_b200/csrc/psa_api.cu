@@ -451,6 +451,11 @@ struct Slot {  // staging of one pipeline chunk
     unsigned long long* meta_host = nullptr;  // pinned: [0] running tx total after the chunk, [1] status
 };
 
+// Host batches: chunk c uses slot c % kSlots; its host-side completion (reading its totals, enqueueing
+// the D2H of its members) happens kSlots - 1 chunks later, so that the host thread keeps submitting
+// ahead of the GPU instead of waiting for each chunk in turn.
+constexpr int kSlots = 4;
+
 struct psa_mapper {
     psa_index* ix = nullptr;
     uint64_t chunk_reads = 0;
@@ -468,7 +473,7 @@ struct psa_mapper {
                                 // memory with one bulk copy (TMA) per CTA; measured 2 % slower than reading them through L1
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
-    Slot slot[2];
+    Slot slot[kSlots];
     uint64_t launches = 0;
     // map-kernel timing (psa_mapper_profile_*)
     bool profiling = false;
@@ -574,7 +579,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_d2h, cudaStreamNonBlocking);
-    for (int s = 0; s < 2 && e == cudaSuccess; s++) {
+    for (int s = 0; s < kSlots && e == cudaSuccess; s++) {
         Slot& S = m->slot[s];
         cudaEvent_t* evs[5] = {&S.in_ready, &S.in_free, &S.comp_done, &S.meta_done, &S.out_free};
         for (auto ev : evs)
@@ -589,7 +594,8 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     const uint64_t nc = ix->d.n_eq + 2;
     if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
         (rc = m->novel_cursor.ensure(64)) || (rc = m->events.ensure(40 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
-        (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16))) {
+        (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16)) ||
+        (rc = m->slot[2].meta_dev.ensure(16)) || (rc = m->slot[3].meta_dev.ensure(16))) {
         psa_mapper_destroy(m);
         return rc;
     }
@@ -626,7 +632,7 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
                       &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
     for (auto b : bufs) b->release();
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < kSlots; s++) {
         Slot& S = m->slot[s];
         S.in_data.release(); S.in_off.release(); S.in_len.release(); S.hits.release(); S.tx.release(); S.meta_dev.release();
         cudaEvent_t evs[5] = {S.in_ready, S.in_free, S.comp_done, S.meta_done, S.out_free};
@@ -959,7 +965,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         int rc;
         CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
         CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < kSlots; s++) {
             Slot& S = m->slot[s];
             if ((rc = S.in_data.ensure(max_dn * unit + 64)) || (rc = S.hits.ensure(C * sizeof(HitRec)))) return rc;
             if (r->read_off && (rc = S.in_off.ensure(C * 8))) return rc;
@@ -972,7 +978,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
 
         auto finish = [&](uint64_t c) -> int {  // host side of chunk c: totals, members D2H
-            Slot& S = m->slot[c & 1];
+            Slot& S = m->slot[c % kSlots];
             CU(cudaEventSynchronize(S.meta_done));
             uint64_t total = S.meta_host[0];
             uint32_t status = (uint32_t)S.meta_host[1];
@@ -993,7 +999,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
 
         for (uint64_t c = 0; c < nchunks; c++) {
             const ChunkPlan& P = plan[c];
-            Slot& S = m->slot[c & 1];
+            Slot& S = m->slot[c % kSlots];
             // H2D
             if (S.in_free_rec) CU(cudaStreamWaitEvent(m->st_h2d, S.in_free, 0));
             CU(cudaMemcpyAsync(S.in_data.p, (const uint8_t*)r->data + P.d0 * unit, P.dn * unit, cudaMemcpyHostToDevice, m->st_h2d));
@@ -1026,9 +1032,10 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             CU(cudaMemcpyAsync(S.meta_host, S.meta_dev.p, 16, cudaMemcpyDeviceToHost, m->st_d2h));
             CU(cudaEventRecord(S.meta_done, m->st_d2h));
             CU(cudaMemcpyAsync(o->hits + P.r0, S.hits.p, P.nr * sizeof(HitRec), cudaMemcpyDeviceToHost, m->st_d2h));
-            if (c >= 1 && (rc = finish(c - 1))) return rc;
+            if (c >= (uint64_t)(kSlots - 1) && (rc = finish(c - (kSlots - 1)))) return rc;
         }
-        if ((rc = finish(nchunks - 1))) return rc;
+        for (uint64_t c = nchunks > (uint64_t)(kSlots - 1) ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
+            if ((rc = finish(c))) return rc;
         CU(cudaStreamSynchronize(m->st_d2h));
         CU(cudaStreamSynchronize(m->st));
         o->tx_used = tx_prev_total;
@@ -1038,7 +1045,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             if (novel_overflow && m->novel_cap && (rc = grow_novel(m))) return rc;
             if (spill_overflow && (rc = grow_pool(m))) return rc;
             if (stage_overflow)
-                for (int s = 0; s < 2; s++)
+                for (int s = 0; s < kSlots; s++)
                     if ((rc = m->slot[s].tx.ensure(stage_need * 4 + 4096))) return rc;
             continue;
         }
