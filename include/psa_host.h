@@ -46,6 +46,16 @@ const uint32_t* psa_graph_node_eq(const psa_graph*);
 const uint64_t* psa_graph_eq_offsets(const psa_graph*);
 const uint32_t* psa_graph_eq_members(const psa_graph*);
 
+/* ---- the flat index on disk (stands where the reference's bincode blob does, ref src/utils.rs:22-43):
+ * exactly the arrays of psa_index_desc, raw and 64-byte aligned behind a versioned header with a
+ * checksum.  psa_graph_load returns NULL on a missing, foreign, truncated or corrupt file. ---- */
+psa_graph* psa_graph_from_arrays(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words, uint64_t n_seq_words,
+                                 const uint64_t* node_start, const uint32_t* node_len, const uint8_t* node_exts,
+                                 const uint32_t* node_eq, uint64_t n_eq, const uint64_t* eq_offsets,
+                                 const uint32_t* eq_members);
+int psa_graph_save(const psa_graph*, const char* path); /* 0, or < 0 (psa_host_last_error) */
+psa_graph* psa_graph_load(const char* path);
+
 /* ---- synthetic data; everything is a pure function of the seed ---- */
 typedef struct psa_transcriptome psa_transcriptome;
 /* GENCODE-shaped transcriptome: n_genes genes of 4..24 exons (log-normal lengths, median 140,

@@ -1,0 +1,157 @@
+// index_file.cpp -- the flat index on disk.
+//
+// The reference persists `Pseudoaligner<K>` as one bincode blob (ref src/utils.rs:22-43, used by the CLI
+// at src/bin/pseudoaligner.rs:114,135).  That layout belongs to debruijn/boomphf internals that are not
+// available here, and this project's index is rebuilt on the GPU from the graph anyway (include/psa.h),
+// so what is stored is exactly the input of psa_index_create: the arrays of psa_index_desc, raw and
+// 64-byte aligned behind a small versioned header, with a checksum.  Loading is one read per array.
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/psa_host.h"
+
+struct psa_graph {  // same definition as in build_graph.cpp
+    uint32_t k = 0;
+    uint64_t n_kmers = 0, n_cycles = 0;
+    std::vector<uint64_t> seq_words, node_start, eq_offsets;
+    std::vector<uint32_t> node_len, node_eq, eq_members;
+    std::vector<uint8_t> node_exts;
+};
+
+extern thread_local std::string g_host_err;
+
+namespace {
+
+constexpr char kMagic[8] = {'P', 'S', 'A', 'I', 'D', 'X', '1', 0};
+constexpr uint32_t kVersion = 1;
+
+struct Header {
+    char magic[8];
+    uint32_t version, k;
+    uint64_t n_nodes, n_seq_words, n_eq, n_eq_members, n_kmers, n_cycles;
+    uint64_t checksum;
+    uint64_t reserved[7];
+};
+static_assert(sizeof(Header) == 128, "header is two 64-byte lines");
+
+uint64_t fold(uint64_t h, const void* p, size_t bytes) {  // order-sensitive 64-bit checksum
+    const uint8_t* b = (const uint8_t*)p;
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t x;
+        memcpy(&x, b + i, 8);
+        h = (h ^ x) * 0x9E3779B97F4A7C15ULL;
+        h ^= h >> 29;
+    }
+    uint64_t x = 0;
+    if (i < bytes) memcpy(&x, b + i, bytes - i);
+    h = (h ^ x ^ bytes) * 0xD6E8FEB86659FD93ULL;
+    return h ^ (h >> 32);
+}
+uint64_t checksum_of(const psa_graph& g) {
+    uint64_t h = 0x243F6A8885A308D3ULL ^ g.k;
+    h = fold(h, g.seq_words.data(), g.seq_words.size() * 8);
+    h = fold(h, g.node_start.data(), g.node_start.size() * 8);
+    h = fold(h, g.node_len.data(), g.node_len.size() * 4);
+    h = fold(h, g.node_exts.data(), g.node_exts.size());
+    h = fold(h, g.node_eq.data(), g.node_eq.size() * 4);
+    h = fold(h, g.eq_offsets.data(), g.eq_offsets.size() * 8);
+    h = fold(h, g.eq_members.data(), g.eq_members.size() * 4);
+    return h;
+}
+bool put(FILE* f, const void* p, size_t bytes) {
+    static const char zeros[64] = {0};
+    if (bytes && fwrite(p, 1, bytes, f) != bytes) return false;
+    const size_t pad = (64 - bytes % 64) % 64;
+    return !pad || fwrite(zeros, 1, pad, f) == pad;
+}
+template <class T>
+bool get(FILE* f, std::vector<T>& v, uint64_t n) {
+    v.resize(n);
+    const size_t bytes = n * sizeof(T);
+    if (bytes && fread(v.data(), 1, bytes, f) != bytes) return false;
+    const size_t pad = (64 - bytes % 64) % 64;
+    return !pad || fseek(f, (long)pad, SEEK_CUR) == 0;
+}
+
+}  // namespace
+
+extern "C" psa_graph* psa_graph_from_arrays(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words, uint64_t n_seq_words,
+                                            const uint64_t* node_start, const uint32_t* node_len, const uint8_t* node_exts,
+                                            const uint32_t* node_eq, uint64_t n_eq, const uint64_t* eq_offsets,
+                                            const uint32_t* eq_members) {
+    if (!eq_offsets || (n_nodes && (!seq_words || !node_start || !node_len || !node_exts || !node_eq))) {
+        g_host_err = "psa_graph_from_arrays: null array";
+        return nullptr;
+    }
+    psa_graph* g = new psa_graph();
+    g->k = k;
+    g->seq_words.assign(seq_words, seq_words + n_seq_words);
+    g->node_start.assign(node_start, node_start + n_nodes);
+    g->node_len.assign(node_len, node_len + n_nodes);
+    g->node_exts.assign(node_exts, node_exts + n_nodes);
+    g->node_eq.assign(node_eq, node_eq + n_nodes);
+    g->eq_offsets.assign(eq_offsets, eq_offsets + n_eq + 1);
+    g->eq_members.assign(eq_members, eq_members + eq_offsets[n_eq]);
+    for (uint64_t i = 0; i < n_nodes; i++) g->n_kmers += node_len[i] >= k ? node_len[i] - k + 1 : 0;
+    return g;
+}
+
+extern "C" int psa_graph_save(const psa_graph* g, const char* path) {
+    if (!g || !path) { g_host_err = "psa_graph_save: null argument"; return -1; }
+    FILE* f = fopen(path, "wb");
+    if (!f) { g_host_err = std::string("cannot create ") + path; return -7; }
+    Header h{};
+    memcpy(h.magic, kMagic, 8);
+    h.version = kVersion;
+    h.k = g->k;
+    h.n_nodes = g->node_len.size();
+    h.n_seq_words = g->seq_words.size();
+    h.n_eq = g->eq_offsets.size() - 1;
+    h.n_eq_members = g->eq_members.size();
+    h.n_kmers = g->n_kmers;
+    h.n_cycles = g->n_cycles;
+    h.checksum = checksum_of(*g);
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && put(f, g->seq_words.data(), g->seq_words.size() * 8) &&
+              put(f, g->node_start.data(), g->node_start.size() * 8) && put(f, g->node_len.data(), g->node_len.size() * 4) &&
+              put(f, g->node_exts.data(), g->node_exts.size()) && put(f, g->node_eq.data(), g->node_eq.size() * 4) &&
+              put(f, g->eq_offsets.data(), g->eq_offsets.size() * 8) && put(f, g->eq_members.data(), g->eq_members.size() * 4);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { g_host_err = std::string("write error on ") + path; return -7; }
+    return 0;
+}
+
+extern "C" psa_graph* psa_graph_load(const char* path) {
+    if (!path) { g_host_err = "psa_graph_load: null path"; return nullptr; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { g_host_err = std::string("cannot open ") + path; return nullptr; }
+    Header h{};
+    psa_graph* g = nullptr;
+    const char* why = nullptr;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0) why = "not a psa index file";
+    else if (h.version != kVersion) why = "unsupported index file version";
+    else if (h.k < 2 || h.k > 64) why = "corrupt header";
+    else {
+        g = new psa_graph();
+        g->k = h.k;
+        g->n_kmers = h.n_kmers;
+        g->n_cycles = h.n_cycles;
+        if (!get(f, g->seq_words, h.n_seq_words) || !get(f, g->node_start, h.n_nodes) || !get(f, g->node_len, h.n_nodes) ||
+            !get(f, g->node_exts, h.n_nodes) || !get(f, g->node_eq, h.n_nodes) || !get(f, g->eq_offsets, h.n_eq + 1) ||
+            !get(f, g->eq_members, h.n_eq_members))
+            why = "truncated index file";
+        else if (g->eq_offsets[h.n_eq] != h.n_eq_members || checksum_of(*g) != h.checksum)
+            why = "index file checksum mismatch";
+    }
+    fclose(f);
+    if (why) {
+        delete g;
+        g_host_err = std::string(why) + ": " + path;
+        return nullptr;
+    }
+    return g;
+}

@@ -33,6 +33,10 @@ def lib():
     for n in ("seq_words", "node_start", "node_len", "node_exts", "node_eq", "eq_offsets", "eq_members"):
         f = getattr(L, "psa_graph_" + n)
         f.restype, f.argtypes = vp, [vp]
+    L.psa_graph_from_arrays.restype = vp
+    L.psa_graph_from_arrays.argtypes = [u32, u64, vp, u64, vp, vp, vp, vp, u64, vp, vp]
+    L.psa_graph_save.restype, L.psa_graph_save.argtypes = i32, [vp, C.c_char_p]
+    L.psa_graph_load.restype, L.psa_graph_load.argtypes = vp, [C.c_char_p]
     L.psa_synth_transcriptome.restype, L.psa_synth_transcriptome.argtypes = vp, [u64, u32, i32]
     L.psa_transcriptome_from_codes.restype, L.psa_transcriptome_from_codes.argtypes = vp, [vp, vp, u32]
     L.psa_transcriptome_free.argtypes = [vp]
@@ -87,19 +91,15 @@ def encode_transcripts(seqs):
     return np.ascontiguousarray(_CODE[np.frombuffer(joined, dtype=np.uint8)]), off
 
 
-def build_graph(codes, tx_off, k, threads=0, copy=True):
-    """Host graph builder -> flat index dict in the form of psa_index_desc."""
-    codes = np.ascontiguousarray(codes, dtype=np.uint8)
-    tx_off = np.ascontiguousarray(tx_off, dtype=np.uint64)
+def _flat_of_graph(g):
+    """psa_graph handle -> (flat index dict in the form of psa_index_desc, stats); frees the handle."""
     L = lib()
-    g = L.psa_build_graph(_ptr(codes), _ptr(tx_off), len(tx_off) - 1, int(k), int(threads))
-    if not g:
-        raise RuntimeError("psa_build_graph: " + _err())
+    k = int(L.psa_graph_k(g))
     try:
         n_nodes, n_eq, n_words = L.psa_graph_n_nodes(g), L.psa_graph_n_eq(g), L.psa_graph_n_seq_words(g)
         eq_offsets = _view(L.psa_graph_eq_offsets(g), n_eq + 1, np.uint64).copy()
         flat = {
-            "k": int(k),
+            "k": k,
             "seq_words": _view(L.psa_graph_seq_words(g), n_words, np.uint64).copy(),
             "node_start": _view(L.psa_graph_node_start(g), n_nodes, np.uint64).copy(),
             "node_len": _view(L.psa_graph_node_len(g), n_nodes, np.uint32).copy(),
@@ -113,6 +113,40 @@ def build_graph(codes, tx_off, k, threads=0, copy=True):
     finally:
         L.psa_graph_free(g)
     return flat, stats
+
+
+def build_graph(codes, tx_off, k, threads=0, copy=True):
+    """Host graph builder -> flat index dict in the form of psa_index_desc."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    tx_off = np.ascontiguousarray(tx_off, dtype=np.uint64)
+    g = lib().psa_build_graph(_ptr(codes), _ptr(tx_off), len(tx_off) - 1, int(k), int(threads))
+    if not g:
+        raise RuntimeError("psa_build_graph: " + _err())
+    return _flat_of_graph(g)
+
+
+def save_index(flat, path):
+    """Write a flat index (the dict build_graph returns) as one file (psa_graph_save)."""
+    f = {k_: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k_, v in flat.items()}
+    L = lib()
+    g = L.psa_graph_from_arrays(int(f["k"]), len(f["node_len"]), _ptr(f["seq_words"]), len(f["seq_words"]),
+                                _ptr(f["node_start"]), _ptr(f["node_len"]), _ptr(f["node_exts"]), _ptr(f["node_eq"]),
+                                len(f["eq_offsets"]) - 1, _ptr(f["eq_offsets"]), _ptr(f["eq_members"]))
+    if not g:
+        raise RuntimeError("psa_graph_from_arrays: " + _err())
+    try:
+        if L.psa_graph_save(g, os.fsencode(path)) != 0:
+            raise RuntimeError("psa_graph_save: " + _err())
+    finally:
+        L.psa_graph_free(g)
+
+
+def load_index(path):
+    """Read a file written by save_index -> (flat, stats).  Raises on a foreign, truncated or corrupt file."""
+    g = lib().psa_graph_load(os.fsencode(path))
+    if not g:
+        raise RuntimeError("psa_graph_load: " + _err())
+    return _flat_of_graph(g)
 
 
 class Transcriptome:

@@ -389,3 +389,38 @@ def test_large_batch_invariants():
     got_hits = results[0][0][:m]
     _assert_same(reads, got_hits, results[0][1][:len(want_tx)], want_hits, want_tx)
     pa.close()
+
+
+def test_two_mappers_share_one_index_concurrently(orc_index_for, fixture_fasta):
+    """`&Pseudoaligner` is shared immutably across the reference's worker threads (ref :35, :434-474);
+    here: one psa_index, one psa_mapper per host thread, both mapping at the same time."""
+    import threading
+    ix = orc_index_for(20)
+    index = pkg.Index(ix.flat(), device=0)
+    rng = np.random.default_rng(77)
+    jobs = []
+    for t in range(2):
+        reads = util.sample_reads(rng, fixture_fasta[1], 20000, 150 if t == 0 else 91, p_sub=0.01, mix=(0.85, 0.1, 0.05))
+        jobs.append((reads, _oracle(ix, reads)))
+    out = [None, None]
+
+    def work(t):
+        m = pkg.Mapper(index, chunk_reads=1500)
+        res = []
+        for _ in range(3):
+            res.append(m.map_ascii(jobs[t][0]))
+        out[t] = (res, m.counts())
+        m.close()
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for t in range(2):
+        reads, (want_hits, want_tx, want_counts, _) = jobs[t]
+        res, counts = out[t]
+        for got_hits, got_tx in res:
+            _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+        assert np.array_equal(counts, 3 * want_counts)
+    index.close()

@@ -93,3 +93,28 @@ def test_fasta_fastq_readers(tmp_path, fixture_fasta, fixture_fastq):
     ids, data, off = host.read_fastq(fq)
     assert ids == [r[0] for r in fixture_fastq]
     assert all(data[int(off[i]):int(off[i + 1])].tobytes().decode() == fixture_fastq[i][1] for i in range(0, len(ids), 101))
+
+
+def test_index_file_round_trip(tmp_path):
+    """The flat index file (include/psa_host.h): save -> load gives the same arrays; foreign,
+    truncated and corrupted files are refused."""
+    rng = np.random.default_rng(9)
+    seqs = util.random_transcriptome(rng, n_genes=6, k=21)
+    codes, off = host.encode_transcripts(seqs)
+    flat, stats = host.build_graph(codes, off, 21)
+    path = tmp_path / "index.psa"
+    host.save_index(flat, path)
+    back, stats2 = host.load_index(path)
+    assert back["k"] == 21 and stats2["n_kmers"] == stats["n_kmers"] and stats2["n_nodes"] == stats["n_nodes"]
+    for key in ("seq_words", "node_start", "node_len", "node_exts", "node_eq", "eq_offsets", "eq_members"):
+        assert np.array_equal(back[key], flat[key]) and back[key].dtype == flat[key].dtype, key
+    raw = path.read_bytes()
+    assert len(raw) % 64 == 0
+    for name, blob in (("foreign", b"not an index" * 20), ("truncated", raw[:len(raw) // 2]),
+                       ("corrupt", raw[:300] + bytes([raw[300] ^ 1]) + raw[301:])):
+        p = tmp_path / name
+        p.write_bytes(blob)
+        with pytest.raises(RuntimeError):
+            host.load_index(p)
+    with pytest.raises(RuntimeError):
+        host.load_index(tmp_path / "missing")
