@@ -631,14 +631,24 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
                     n_wide += w.g.shfl_xor(n_wide, d);
                 }
                 if (acc.have) {
-                    if (n_wide) {  // wide classes filter the surviving candidates (one range lookup per class)
-                        for (uint32_t j = 0; j < w.n_list && !win_empty(acc.map); j++) {
-                            uint32_t e, l;
-                            uint64_t o;
-                            w.entry(j, e, l, o);
-                            if (__ldg(&ix.class_win[e].len) != kWinWide) continue;
-                            winacc_filter_list(acc, ix.eq_mem + o, l);  // uniform across the group
+                    if (n_wide) {
+                        // wide classes filter the surviving candidates: every lane looks its own entries up
+                        // (one range lookup per class, psa_core.cuh win_of_list_range), a butterfly ANDs the masks
+                        Win keep{~0ULL, ~0ULL, ~0ULL};
+                        if (lane < w.n_list && __ldg(&ix.class_win[w.my_eq].len) == kWinWide)
+                            keep = win_of_list_range(ix.eq_mem + w.my_off, w.my_len, acc.base);
+                        for (uint32_t j = G + lane; j < w.n_list; j += G) {
+                            const uint4 e = w.spill[j - G];
+                            if (__ldg(&ix.class_win[e.x].len) != kWinWide) continue;
+                            keep = win_and(keep, win_of_list_range(ix.eq_mem + ((uint64_t)e.z | ((uint64_t)e.w << 32)), e.y, acc.base));
                         }
+#pragma unroll
+                        for (int d = G / 2; d; d >>= 1) {
+                            keep.w0 &= w.g.shfl_xor(keep.w0, d);
+                            keep.w1 &= w.g.shfl_xor(keep.w1, d);
+                            keep.w2 &= w.g.shfl_xor(keep.w2, d);
+                        }
+                        acc.map = win_and(acc.map, keep);
                     }
                     count = win_popc(acc.map);
                 } else {
