@@ -469,6 +469,7 @@ struct psa_mapper {
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
+    bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
     bool tile_reads = false;    // PSA_TILE=1: k_map_thread stages the packed reads of fixed-stride batches in shared
                                 // memory with one bulk copy (TMA) per CTA; measured 2 % slower than reading them through L1
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
@@ -611,6 +612,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE")) m->tile_reads = atoi(e) != 0;
+    if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
         int g = atoi(e);
         if (g == 0 || g == 8 || g == 16 || g == 32) m->scan_width = (uint32_t)g;
@@ -727,7 +729,14 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             rv.wstride = ((uint64_t)r->fixed_len + 31) / 32;
             if ((rc = m->words.ensure(n * rv.wstride * 8 + 16))) return rc;
         }
-        if (!r->read_len && !r->read_off) {
+        // tile form (TMA): stride and base 16-byte friendly, tile small enough for several CTAs per SM
+        const uint64_t tile_bytes = (uint64_t)kPackTileReads * r->stride;
+        if (!r->read_len && !r->read_off && m->tile_pack && r->fixed_len && r->stride >= r->fixed_len && tile_bytes % 16 == 0 &&
+            ((uintptr_t)r->data & 15) == 0 && tile_bytes <= 40 * 1024) {
+            const uint32_t smem = (uint32_t)(16 + tile_bytes + 48 + 16);
+            k_pack_ascii_tile<<<nblocks(n, kPackTileReads), kPackTileReads, smem, st>>>(
+                (const uint8_t*)r->data, (uint32_t)r->stride, r->fixed_len, n, m->words.as<uint64_t>(), (uint32_t)tile_bytes);
+        } else if (!r->read_len && !r->read_off) {
             // 32-bit word indices inside the kernel: slices of at most 2^31 words
             const uint64_t per = std::max<uint64_t>(1, (1ull << 31) / rv.wstride);
             for (uint64_t r0 = 0; r0 < n; r0 += per) {

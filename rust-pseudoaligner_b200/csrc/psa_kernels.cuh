@@ -264,6 +264,78 @@ __device__ __forceinline__ uint64_t pack32(const uint8_t* s, uint32_t nb) {
     if (nb < 32) v &= ~0ULL << (64 - 2 * nb);
     return v;
 }
+// ---- bulk asynchronous copy (TMA, non-tensor form) + mbarrier, for the read tiles ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    }
+}
+// fixed read length and stride, tile form: the ASCII of the CTA's 128 reads arrives in shared memory as ONE
+// bulk asynchronous copy (cp.async.bulk + mbarrier: TMA), then every thread packs its own read from there
+// (nine aligned 32-bit shared loads per word) and writes its words.  Replaces nine 4-byte global loads per
+// word whose lanes touch 32 different sectors each.
+constexpr int kPackTileReads = 128;
+__device__ __forceinline__ uint64_t pack32_smem(const uint8_t* s, uint32_t nb) {
+    const uint32_t mis = (uint32_t)(smem_u32(s) & 3);
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(s - mis);
+    uint32_t w[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) w[i] = a[i];
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t c = __funnelshift_r(w[i], w[i + 1], 8 * mis);
+        v |= (uint64_t)codes4(c) << (56 - 8 * i);
+    }
+    if (nb < 32) v &= ~0ULL << (64 - 2 * nb);
+    return v;
+}
+__global__ void __launch_bounds__(kPackTileReads) k_pack_ascii_tile(const uint8_t* ascii, uint32_t astride, uint32_t len,
+                                                                   uint64_t n, uint64_t* words, uint32_t tile_cap) {
+    // layout: [16 B slack | tile (tile_cap, multiple of 16) | 48 B slack | mbarrier]
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tile = smem + 16;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16 + tile_cap + 48);
+    const uint32_t nw = (len + 31) >> 5;
+    const uint64_t r0 = blockIdx.x * (uint64_t)kPackTileReads;
+    const uint32_t nr = (uint32_t)min((uint64_t)kPackTileReads, n - r0);
+    const uint8_t* src = ascii + r0 * astride;
+    // a full tile is one bulk copy (the host guarantees 16-byte multiples and alignment); the batch's last
+    // tile may not read the padding after its last read, which need not exist
+    const bool full = nr == kPackTileReads && (r0 + kPackTileReads < n || astride == len);
+    if (full) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, kPackTileReads * astride);
+            bulk_g2s(tile, src, kPackTileReads * astride, bar);
+        }
+        __syncthreads();  // the barrier is initialised before anyone polls it
+        mbar_wait(bar, 0);
+    } else {
+        const uint32_t bytes = (nr - 1) * astride + len;
+        for (uint32_t i = threadIdx.x; i < bytes; i += kPackTileReads) tile[i] = src[i];
+        __syncthreads();
+    }
+    if (threadIdx.x < nr) {
+        const uint8_t* s = tile + threadIdx.x * astride;
+        uint64_t* w = words + (r0 + threadIdx.x) * nw;
+        for (uint32_t j = 0; j < nw; j++) w[j] = pack32_smem(s + 32 * j, min(32u, len - 32 * j));
+    }
+}
 // fixed read length: one thread per output word (32-bit index arithmetic: the host splits larger batches)
 __global__ void k_pack_ascii_fixed(const uint8_t* ascii, uint64_t astride, uint32_t len, uint64_t n, uint64_t* words) {
     const uint32_t nw = (len + 31) >> 5;
@@ -737,26 +809,6 @@ constexpr int kThreadBlock = 128;
 #define PSA_THREAD_MIN_BLOCKS 8
 #endif
 
-// ---- bulk asynchronous copy (TMA, non-tensor form) + mbarrier, for the read tiles ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(phase) : "memory");
-    }
-}
 // HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
 // first seed search was made by k_seed_scan), persistent warps striding over that list.
 // TILE (first pass, fixed word stride): the packed words of the CTA's 128 reads arrive in shared
