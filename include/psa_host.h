@@ -55,6 +55,12 @@ psa_graph* psa_graph_from_arrays(uint32_t k, uint64_t n_nodes, const uint64_t* s
                                  const uint32_t* eq_members);
 int psa_graph_save(const psa_graph*, const char* path); /* 0, or < 0 (psa_host_last_error) */
 psa_graph* psa_graph_load(const char* path);
+/* The reference's own index file (`pseudoaligner index` output: bincode 1.3 of Pseudoaligner<K>, ref
+ * src/utils.rs:22-32): reads `dbg` and `eq_classes`, ignores the rest (the dictionary is rebuilt on the
+ * GPU).  k = the K the index was built with (not stored in the file).  The field order of debruijn's
+ * graph types is as recalled for 0.3.4 @ 8d9a5c5 -- not verifiable in this environment; every length is
+ * cross-checked so that a different layout is refused (NULL) rather than misread. */
+psa_graph* psa_graph_load_bincode(const char* path, uint32_t k);
 
 /* ---- synthetic data; everything is a pure function of the seed ---- */
 typedef struct psa_transcriptome psa_transcriptome;

@@ -155,3 +155,97 @@ extern "C" psa_graph* psa_graph_load(const char* path) {
     }
     return g;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Reader for the reference's own index file: `Pseudoaligner<K>` written by bincode 1.3 with default
+// options (ref src/utils.rs:22-32: fixed-width little-endian integers, u64 length prefixes, struct
+// fields in declaration order, usize as u64, bool as one byte).  Only the first two fields are read --
+// `dbg` and `eq_classes` (ref src/pseudoaligner.rs:27-29); `dbg_index` (boomphf's bit-vectors),
+// `tx_names` and `tx_gene_mapping` that follow are not needed, because the dictionary is rebuilt on the
+// GPU.  The field order inside `dbg` is that of debruijn 0.3.4 @ 8d9a5c5 AS RECALLED (the crate is not
+// available in this environment, so this has not been checked against a reference-built file):
+//   DebruijnGraph { base: BaseGraph { sequences: PackedDnaStringSet { sequence: DnaString { storage:
+//   Vec<u64>, len: usize }, start: Vec<usize>, length: Vec<u32> }, exts: Vec<Exts{val:u8}>, data: Vec<u32>,
+//   stranded: bool }, left_order: Vec<u32>, right_order: Vec<u32> }
+// Every length is cross-checked, so a different layout is refused rather than misread.  K is a type
+// parameter of the reference (not stored): the caller passes k, as the CLI's -k does.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cursor {
+    FILE* f;
+    uint64_t left;  // bytes left in the file
+    bool u64(uint64_t& v) {
+        if (left < 8 || fread(&v, 8, 1, f) != 1) return false;
+        left -= 8;
+        return true;
+    }
+    template <class T>
+    bool vec(std::vector<T>& v, uint64_t max_elems) {
+        uint64_t n;
+        if (!u64(n) || n > max_elems || n * sizeof(T) > left) return false;
+        v.resize(n);
+        if (n && fread(v.data(), sizeof(T), n, f) != n) return false;
+        left -= n * sizeof(T);
+        return true;
+    }
+};
+}  // namespace
+
+extern "C" psa_graph* psa_graph_load_bincode(const char* path, uint32_t k) {
+    if (!path || k < 2 || k > 64) { g_host_err = "psa_graph_load_bincode: bad argument"; return nullptr; }
+    FILE* f = fopen(path, "rb");
+    if (!f) { g_host_err = std::string("cannot open ") + path; return nullptr; }
+    fseek(f, 0, SEEK_END);
+    Cursor c{f, (uint64_t)ftell(f)};
+    rewind(f);
+    psa_graph* g = new psa_graph();
+    g->k = k;
+    const char* why = nullptr;
+    const uint64_t cap = c.left;  // no array can have more elements than the file has bytes
+    uint64_t n_bases = 0;
+    std::vector<uint32_t> left_order, right_order;
+    uint8_t stranded = 0;
+    uint64_t n_classes = 0;
+    if (!c.vec(g->seq_words, cap) || !c.u64(n_bases)) why = "truncated (sequence)";
+    else if (g->seq_words.size() != (n_bases + 31) / 32) why = "DnaString storage does not match its length";
+    else if (!c.vec(g->node_start, cap) || !c.vec(g->node_len, cap) || !c.vec(g->node_exts, cap) || !c.vec(g->node_eq, cap))
+        why = "truncated (node arrays)";
+    else if (g->node_start.size() != g->node_len.size() || g->node_exts.size() != g->node_len.size() ||
+             g->node_eq.size() != g->node_len.size())
+        why = "node arrays of different lengths";
+    else if (c.left < 1 || fread(&stranded, 1, 1, f) != 1) why = "truncated (stranded)";
+    else {
+        c.left -= 1;
+        if (stranded != 1) why = "graph is not stranded (the reference builds with STRANDED = true, src/config.rs:14)";
+        else if (!c.vec(left_order, cap) || !c.vec(right_order, cap)) why = "truncated (node orders)";
+        else if (left_order.size() != g->node_len.size() || right_order.size() != g->node_len.size())
+            why = "node order arrays do not match the node count";
+        else if (!c.u64(n_classes) || n_classes > cap) why = "truncated (eq_classes)";
+    }
+    if (!why) {
+        g->eq_offsets.assign(1, 0);
+        std::vector<uint32_t> cls;
+        for (uint64_t i = 0; i < n_classes && !why; i++) {
+            if (!c.vec(cls, cap)) { why = "truncated (eq_classes)"; break; }
+            for (size_t j = 1; j < cls.size(); j++)
+                if (cls[j] <= cls[j - 1]) { why = "equivalence class not ascending"; break; }
+            g->eq_members.insert(g->eq_members.end(), cls.begin(), cls.end());
+            g->eq_offsets.push_back(g->eq_members.size());
+        }
+    }
+    if (!why) {
+        for (size_t i = 0; i < g->node_len.size() && !why; i++) {
+            if (g->node_len[i] < k) why = "node shorter than k (wrong k?)";
+            else if (g->node_start[i] + g->node_len[i] > n_bases) why = "node outside the sequence";
+            else if (g->node_eq[i] >= n_classes) why = "node class id out of range";
+            else g->n_kmers += g->node_len[i] - k + 1;
+        }
+    }
+    fclose(f);
+    if (why) {
+        delete g;
+        g_host_err = std::string("not a recognised Pseudoaligner bincode file (") + why + "): " + path;
+        return nullptr;
+    }
+    return g;
+}

@@ -37,6 +37,7 @@ def lib():
     L.psa_graph_from_arrays.argtypes = [u32, u64, vp, u64, vp, vp, vp, vp, u64, vp, vp]
     L.psa_graph_save.restype, L.psa_graph_save.argtypes = i32, [vp, C.c_char_p]
     L.psa_graph_load.restype, L.psa_graph_load.argtypes = vp, [C.c_char_p]
+    L.psa_graph_load_bincode.restype, L.psa_graph_load_bincode.argtypes = vp, [C.c_char_p, u32]
     L.psa_synth_transcriptome.restype, L.psa_synth_transcriptome.argtypes = vp, [u64, u32, i32]
     L.psa_transcriptome_from_codes.restype, L.psa_transcriptome_from_codes.argtypes = vp, [vp, vp, u32]
     L.psa_transcriptome_free.argtypes = [vp]
@@ -146,6 +147,15 @@ def load_index(path):
     g = lib().psa_graph_load(os.fsencode(path))
     if not g:
         raise RuntimeError("psa_graph_load: " + _err())
+    return _flat_of_graph(g)
+
+
+def load_reference_index(path, k):
+    """Read `dbg` + `eq_classes` of a reference-built index file (bincode of Pseudoaligner<K>) -> (flat, stats).
+    Layout as recalled for debruijn 0.3.4 (see include/psa_host.h); refuses anything inconsistent."""
+    g = lib().psa_graph_load_bincode(os.fsencode(path), int(k))
+    if not g:
+        raise RuntimeError("psa_graph_load_bincode: " + _err())
     return _flat_of_graph(g)
 
 

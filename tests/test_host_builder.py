@@ -118,3 +118,67 @@ def test_index_file_round_trip(tmp_path):
             host.load_index(p)
     with pytest.raises(RuntimeError):
         host.load_index(tmp_path / "missing")
+
+
+def _write_reference_bincode(flat, path, tx_names=("tx0", "tx1"), stranded=1):
+    """`Pseudoaligner<K>` as bincode 1.3 would lay it out (fixint LE, u64 length prefixes), field order
+    of debruijn 0.3.4 as recalled -- test writer for the reader in csrc/host/index_file.cpp."""
+    import struct
+    n_bases = int(flat["node_start"][-1] + flat["node_len"][-1]) if len(flat["node_len"]) else 0
+    n_bases = max(n_bases, int((flat["node_start"].astype(np.uint64) + flat["node_len"]).max())) if len(flat["node_len"]) else 0
+    words = flat["seq_words"][:(n_bases + 31) // 32]
+    n = len(flat["node_len"])
+    out = [struct.pack("<Q", len(words)), words.astype("<u8").tobytes(), struct.pack("<Q", n_bases),
+           struct.pack("<Q", n), flat["node_start"].astype("<u8").tobytes(),
+           struct.pack("<Q", n), flat["node_len"].astype("<u4").tobytes(),
+           struct.pack("<Q", n), flat["node_exts"].astype("u1").tobytes(),
+           struct.pack("<Q", n), flat["node_eq"].astype("<u4").tobytes(),
+           struct.pack("<B", stranded),
+           struct.pack("<Q", n), np.arange(n, dtype="<u4").tobytes(),       # left_order (unused by the reader)
+           struct.pack("<Q", n), np.arange(n, dtype="<u4")[::-1].tobytes()]  # right_order
+    eo, em = flat["eq_offsets"], flat["eq_members"]
+    out.append(struct.pack("<Q", len(eo) - 1))
+    for c in range(len(eo) - 1):
+        m = em[int(eo[c]):int(eo[c + 1])]
+        out += [struct.pack("<Q", len(m)), m.astype("<u4").tobytes()]
+    # what follows is ignored by the reader: dbg_index (opaque here), tx_names, tx_gene_mapping
+    out.append(b"\x01\x02\x03 opaque boomphf bytes")
+    for s in tx_names:
+        out += [struct.pack("<Q", len(s)), s.encode()]
+    open(path, "wb").write(b"".join(out))
+
+
+def test_reference_bincode_index_reader(tmp_path):
+    """ref src/utils.rs:22-43: the reader takes `dbg` and `eq_classes` of a reference-style file and refuses
+    inconsistent ones.  (Layout recalled, not checked against a reference-built file: see psa_host.h.)"""
+    rng = np.random.default_rng(10)
+    seqs = util.random_transcriptome(rng, n_genes=6, k=20)
+    codes, off = host.encode_transcripts(seqs)
+    flat, stats = host.build_graph(codes, off, 20)
+    path = tmp_path / "ref.idx"
+    _write_reference_bincode(flat, path)
+    back, stats2 = host.load_reference_index(path, 20)
+    assert stats2["n_kmers"] == stats["n_kmers"] and stats2["n_nodes"] == stats["n_nodes"]
+    nw = len(back["seq_words"])
+    assert np.array_equal(back["seq_words"], flat["seq_words"][:nw])
+    for key in ("node_start", "node_len", "node_exts", "node_eq", "eq_offsets", "eq_members"):
+        assert np.array_equal(back[key], flat[key]), key
+    # the oracle maps through the loaded index exactly as through the built one
+    a, b = orc.OrcIndex.from_flat(flat), orc.OrcIndex.from_flat(back)
+    reads = util.sample_reads(rng, seqs, 300, 60, p_sub=0.02)
+    words, roff, lens = orc.pack_reads(reads)
+    ha, ta, _, _ = a.map_batch(words, roff, lens)
+    hb, tb, _, _ = b.map_batch(words, roff, lens)
+    assert np.array_equal(ha, hb) and np.array_equal(ta, tb)
+    with pytest.raises(RuntimeError):
+        host.load_reference_index(path, 64)            # wrong k: nodes shorter than k
+    _write_reference_bincode(flat, path, stranded=0)
+    with pytest.raises(RuntimeError):
+        host.load_reference_index(path, 20)
+    raw = open(path, "rb").read()
+    (tmp_path / "cut").write_bytes(raw[:len(raw) // 3])
+    with pytest.raises(RuntimeError):
+        host.load_reference_index(tmp_path / "cut", 20)
+    (tmp_path / "flat").write_bytes(b"PSAIDX1\0" + b"\0" * 200)
+    with pytest.raises(RuntimeError):
+        host.load_reference_index(tmp_path / "flat", 20)
