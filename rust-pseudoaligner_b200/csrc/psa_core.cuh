@@ -543,15 +543,17 @@ PSA_HD uint32_t view_succ(const NodeView& v, uint32_t b) { return b == 0 ? v.suc
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
 #endif
-template <class W>
-PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allowed_mismatches,
+// P: the integer type of read positions (usize in the reference).  The kernels use uint32_t -- read lengths
+// are 32-bit in the C ABI -- which halves the registers and instructions of the position arithmetic.
+template <class P = uint64_t, class W>
+PSA_HD bool map_read_nodes(W& w, uint32_t k, P read_length, uint32_t allowed_mismatches,
                            uint32_t& coverage) {
-    uint64_t read_coverage = 0;                                                 // :71
-    const uint64_t kmer_length = k;                                             // :80
-    uint64_t left_extend_threshold = (uint64_t)(kLeftExtendFraction * (double)read_length);  // :77
-    uint64_t kmer_pos = 0;                                                      // :79
+    P read_coverage = 0;                                                 // :71
+    const P kmer_length = k;                                             // :80
+    P left_extend_threshold = (P)(kLeftExtendFraction * (double)read_length);  // :77
+    P kmer_pos = 0;                                                      // :79
     if (read_length < kmer_length) return false;                                // :82-84
-    const uint64_t last_kmer_pos = read_length - kmer_length;                   // :86
+    const P last_kmer_pos = read_length - kmer_length;                   // :86
     uint32_t n_pushed = 0;
 
     uint32_t node_id = 0, kmer_offset = 0;
@@ -560,16 +562,16 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
     // left extension, :124-205.  (kmer_pos >= 1 only fails for read_length < 5, where the
     // reference's `kmer_pos - 1` would underflow; unreachable for k >= 5.)
     if (have && kmer_pos >= left_extend_threshold && kmer_pos >= 1) {
-        uint64_t last_pos = kmer_pos - 1;                                       // :127
+        P last_pos = kmer_pos - 1;                                       // :127
         uint32_t prev_node_id = node_id;                                        // :128
-        uint64_t prev_kmer_offset = kmer_offset > 0 ? kmer_offset - 1 : 0;      // :129 (sic)
+        P prev_kmer_offset = kmer_offset > 0 ? kmer_offset - 1 : 0;      // :129 (sic)
         for (;;) {                                                              // :131
             NodeView nv = w.node(prev_node_id);                                 // :132
-            uint64_t skipped_read = last_pos + 1;                               // :139
-            uint64_t skipped_ref = prev_kmer_offset + 1;                        // :142
-            uint64_t max_matchable_pos = skipped_read < skipped_ref ? skipped_read : skipped_ref;  // :145
+            P skipped_read = last_pos + 1;                               // :139
+            P skipped_ref = prev_kmer_offset + 1;                        // :142
+            P max_matchable_pos = skipped_read < skipped_ref ? skipped_read : skipped_ref;  // :145
             bool premature_break = false;                                       // :148
-            uint64_t matched_bases =                                            // :149-170
+            P matched_bases =                                            // :149-170
                 w.cmp_bwd(last_pos, nv.start + prev_kmer_offset, max_matchable_pos, allowed_mismatches,
                           premature_break);
             read_coverage += matched_bases;                                     // :169
@@ -599,13 +601,13 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, uint64_t read_length, uint32_t allo
             w.push(node_id, nv);                                                // :219
             n_pushed++;
             if (w.abort()) return false;
-            uint64_t remaining_read = read_length - kmer_pos;                   // :222
-            uint64_t ref_length = nv.len;                                       // :226
-            uint64_t ref_offset = kmer_offset + kmer_length;                    // :227
-            uint64_t informative_ref = ref_length - ref_offset;                 // :228
-            uint64_t max_matchable_pos = remaining_read < informative_ref ? remaining_read : informative_ref;  // :231
+            P remaining_read = read_length - kmer_pos;                   // :222
+            P ref_length = nv.len;                                       // :226
+            P ref_offset = kmer_offset + kmer_length;                    // :227
+            P informative_ref = ref_length - ref_offset;                 // :228
+            P max_matchable_pos = remaining_read < informative_ref ? remaining_read : informative_ref;  // :231
             bool premature_break = false;                                       // :233
-            uint64_t matched_bases =                                            // :234-255
+            P matched_bases =                                            // :234-255
                 w.cmp_fwd(kmer_pos, nv.start + ref_offset, max_matchable_pos, allowed_mismatches,
                           premature_break);
             read_coverage += matched_bases;                                     // :254
@@ -837,11 +839,11 @@ struct ThreadCtx {
     RD rd;
     uint32_t k, max_probes;
     // online class state
-    uint32_t first_eq, first_len;  // the first class visited; its window is fetched only when a second class shows up
-    bool multi;                    // more than one distinct class visited
+    bool multi;                    // more than one distinct class visited (until then min_eq/min_len ARE the one
+                                   // class seen, whose window is fetched only when a second class shows up)
     uint32_t min_len, min_eq;      // smallest class length seen, and the smallest id among the classes of that length
     WinAcc acc;                    // AND of the narrow classes' windows
-    uint32_t wide_eq[kThreadWide], wide_len[kThreadWide], n_wide, n_inline;
+    uint32_t wide_eq[kThreadWide], n_wide, n_inline;  // (their lengths are re-read from eq_off when needed)
     uint32_t recent[kThreadRecent];  // last few class ids (skips most repeated window loads; repeats are harmless)
     bool defer;
     uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
@@ -852,12 +854,12 @@ struct ThreadCtx {
     ThreadEvents ev;
 
     PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
-        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), first_eq(kNone), first_len(0), multi(false),
+        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), multi(false),
           min_len(kNone), min_eq(kNone), n_wide(0), n_inline(0), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
         acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
     PSA_UNROLL
-        for (int j = 0; j < kThreadWide; j++) { wide_eq[j] = kNone; wide_len[j] = 0; }
+        for (int j = 0; j < kThreadWide; j++) wide_eq[j] = kNone;
     PSA_UNROLL
         for (int j = 0; j < kThreadRecent; j++) recent[j] = kNone;
     }
@@ -865,7 +867,8 @@ struct ThreadCtx {
     PSA_HD uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
 
     // find_kmer_match, ref src/pseudoaligner.rs:91-114, at most max_probes positions
-    PSA_HD bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& o) {
+    template <class P>
+    PSA_HD bool find_seed(P& kmer_pos, P last, uint32_t& node, uint32_t& o) {
         if (kmer_pos > last) return false;
         if (has_hint) {  // the first search of the read (it starts at 0), done by k_seed_scan
             has_hint = false;
@@ -875,8 +878,8 @@ struct ThreadCtx {
             seeded = true;
             return true;
         }
-        const uint64_t start = kmer_pos;
-        uint64_t p = start;
+        const P start = kmer_pos;
+        P p = start;
         for (uint32_t probes = 0;; probes++, p += kSeedStride) {
             if (p > last) {
                 kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
@@ -916,17 +919,17 @@ struct ThreadCtx {
         return p;
     }
     // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step
-    template <bool FWD>
-    PSA_HD uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
+    template <bool FWD, class P>
+    PSA_HD P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
-        for (uint64_t my = 0; my < m; my += 32) {
+        for (P my = 0; my < m; my += 32) {
             uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
             uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
                                 : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
             uint32_t c = (uint32_t)popc64(mask);
             if (snp + c > A) {
                 premature = true;
-                uint64_t matched = my + nth_mismatch(mask, A + 1 - snp);
+                P matched = my + nth_mismatch(mask, A + 1 - snp);
                 if (EV) ev.bases += (uint32_t)matched + 1;
                 return matched;
             }
@@ -935,8 +938,10 @@ struct ThreadCtx {
         if (EV) ev.bases += (uint32_t)m;
         return m;
     }
-    PSA_HD uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
-    PSA_HD uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
+    template <class P>
+    PSA_HD P cmp_fwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    template <class P>
+    PSA_HD P cmp_bwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
     // AND one class into the running intersection (narrow), or list it (wide)
     PSA_HD void and_class(uint32_t e, uint32_t l) {
         const ClassWin c = load_class_win(ix.class_win + e);
@@ -962,7 +967,7 @@ struct ThreadCtx {
         }
     PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++)
-            if (j == (int)n_wide) { wide_eq[j] = e; wide_len[j] = l; }
+            if (j == (int)n_wide) wide_eq[j] = e;
         n_wide++;
     }
     // nodes.push: only the classes matter, and the intersection is idempotent (ref :352-355)
@@ -976,21 +981,17 @@ struct ThreadCtx {
         for (int j = kThreadRecent - 1; j > 0; j--) recent[j] = recent[j - 1];
         recent[0] = nv.eq;
         if (EV) ev.members += nv.class_len;  // (a class revisited after kThreadRecent others is counted again)
+        const bool first = min_eq == kNone;
+        if (!first && !multi) {
+            if (nv.eq == min_eq) return;   // still the one class seen so far
+            multi = true;
+            and_class(min_eq, min_len);
+        }
         if (nv.class_len < min_len || (nv.class_len == min_len && nv.eq < min_eq)) {
             min_len = nv.class_len;
             min_eq = nv.eq;
         }
-        if (first_eq == kNone) {
-            first_eq = nv.eq;
-            first_len = nv.class_len;
-            return;
-        }
-        if (!multi) {
-            if (nv.eq == first_eq) return;
-            multi = true;
-            and_class(first_eq, first_len);
-        }
-        and_class(nv.eq, nv.class_len);
+        if (multi) and_class(nv.eq, nv.class_len);
     }
 };
 
@@ -1004,11 +1005,12 @@ PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, ui
     uint32_t cur[kThreadWide];
     PSA_UNROLL
     for (int j = 0; j < kThreadWide; j++) cur[j] = 0;
-    uint32_t s_len = 0, s_eq = 0;
+    uint32_t s_eq = 0;
     PSA_UNROLL
     for (int j = 0; j < kThreadWide; j++)
-        if (j == s) { s_len = w.wide_len[j]; s_eq = w.wide_eq[j]; }
+        if (j == s) s_eq = w.wide_eq[j];
     const uint64_t s_off = ld_off(w.ix.eq_off + s_eq);
+    const uint32_t s_len = (uint32_t)(ld_off(w.ix.eq_off + s_eq + 1) - s_off);
     uint32_t count = 0;
     for (uint32_t i = 0; i < s_len; i++) {
         const uint32_t x = ld_mem(mem + s_off + i);
@@ -1016,15 +1018,17 @@ PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, ui
     PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) {
             if (j == s || j >= (int)w.n_wide || !alive) continue;
-            const uint32_t* v = mem + ld_off(w.ix.eq_off + w.wide_eq[j]);
-            uint32_t lo = cur[j], hi = w.wide_len[j];
+            const uint64_t o = ld_off(w.ix.eq_off + w.wide_eq[j]);
+            const uint32_t n = (uint32_t)(ld_off(w.ix.eq_off + w.wide_eq[j] + 1) - o);
+            const uint32_t* v = mem + o;
+            uint32_t lo = cur[j], hi = n;
             while (lo < hi) {
                 uint32_t mid = lo + ((hi - lo) >> 1);
                 if (ld_mem(v + mid) < x) lo = mid + 1;
                 else hi = mid;
             }
             cur[j] = lo;
-            alive = lo < w.wide_len[j] && ld_mem(v + lo) == x;
+            alive = lo < n && ld_mem(v + lo) == x;
         }
         if (alive) {
             if (out) out[count] = x;
@@ -1061,7 +1065,7 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, ui
         w.hint_pos = hint[0]; w.hint_node = hint[1]; w.hint_off = hint[2];
     }
     uint32_t coverage = 0;
-    bool some = map_read_nodes(w, ix.k, (uint64_t)L, allowed, coverage);
+    bool some = map_read_nodes<uint32_t>(w, ix.k, L, allowed, coverage);
     res.why = w.why;
     if (w.defer) {
         res.deferred = true;
@@ -1071,24 +1075,29 @@ PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, ui
         uint32_t count, eq_id;
         int s = 0;  // smallest wide class (only used when every class is wide)
         if (!w.multi) {
-            count = w.first_len;
-            eq_id = w.first_eq;
+            count = w.min_len;
+            eq_id = w.min_eq;
         } else {
             if (w.acc.have) {
                 // wide classes filter what survived the windows (ref :399-404 on the candidates)
     PSA_UNROLL
                 for (int j = 0; j < kThreadWide; j++) {
                     if (j >= (int)w.n_wide || win_empty(w.acc.map)) continue;
-                    winacc_filter_list(w.acc, ix.eq_mem + ld_off(ix.eq_off + w.wide_eq[j]), w.wide_len[j]);
+                    const uint64_t o = ld_off(ix.eq_off + w.wide_eq[j]);
+                    winacc_filter_list(w.acc, ix.eq_mem + o, (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o));
                 }
                 count = win_popc(w.acc.map);
             } else {
-                uint32_t s_len = w.wide_len[0], s_eq = w.wide_eq[0];  // smallest class first (ref :331-334)
+                // smallest class first (ref :331-334)
+                uint32_t s_eq = w.wide_eq[0];
+                uint32_t s_len = (uint32_t)(ld_off(ix.eq_off + s_eq + 1) - ld_off(ix.eq_off + s_eq));
     PSA_UNROLL
-                for (int j = 1; j < kThreadWide; j++)
-                    if (j < (int)w.n_wide && (w.wide_len[j] < s_len || (w.wide_len[j] == s_len && w.wide_eq[j] < s_eq))) {
-                        s = j; s_len = w.wide_len[j]; s_eq = w.wide_eq[j];
-                    }
+                for (int j = 1; j < kThreadWide; j++) {
+                    if (j >= (int)w.n_wide) continue;
+                    const uint32_t e = w.wide_eq[j];
+                    const uint32_t l = (uint32_t)(ld_off(ix.eq_off + e + 1) - ld_off(ix.eq_off + e));
+                    if (l < s_len || (l == s_len && e < s_eq)) { s = j; s_len = l; s_eq = e; }
+                }
                 if (s_len > max_small) {  // long lists are the cooperative kernel's job
                     res.why = 3;
                     res.deferred = true;

@@ -453,11 +453,12 @@ struct WarpCtx {
     // whole group on one address (the common case: it hits); after a miss, G stride-3
     // positions are probed at once, one per lane, and the lowest hitting lane wins -- the
     // same answer as the sequential scan.
-    __device__ __forceinline__ bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
+    template <class P>
+    __device__ __forceinline__ bool find_seed(P& kmer_pos, P last, uint32_t& node, uint32_t& off) {
         if (kmer_pos > last) return false;
         ProbeStats st;
-        const uint64_t start = kmer_pos;
-        uint64_t first = start;
+        const P start = kmer_pos;
+        P first = start;
         if (!scan_mode) {  // (k_seed_scan's reads have already missed here: all lanes speculate from `start`)
             Kmer<KW> key = KmerOps<KW>::get(rd, kmer_pos, k);
             bool hit = dict_get<KW>(ix, key, node, off, EV ? &st : nullptr);
@@ -465,8 +466,8 @@ struct WarpCtx {
             if (hit) return true;
             first = start + kSeedStride;
         }
-        for (uint64_t cur = first; cur <= last; cur += G * kSeedStride) {
-            uint64_t p = cur + (uint64_t)kSeedStride * lane;
+        for (P cur = first; cur <= last; cur += G * kSeedStride) {
+            P p = cur + (P)kSeedStride * lane;
             bool h = false;
             uint32_t n = 0, o = 0;
             st.levels = st.hit = st.verified = 0;
@@ -488,7 +489,7 @@ struct WarpCtx {
             if (b) {
                 node = g.shfl(n, j);
                 off = g.shfl(o, j);
-                kmer_pos = cur + (uint64_t)kSeedStride * j;
+                kmer_pos = cur + (P)kSeedStride * j;
                 return true;
             }
         }
@@ -530,12 +531,12 @@ struct WarpCtx {
     }
 
     // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward)
-    template <bool FWD>
-    __device__ __forceinline__ uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
+    template <bool FWD, class P>
+    __device__ __forceinline__ P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
-        for (uint64_t base = 0; base < m; base += 32 * G) {
-            uint64_t my = base + 32 * lane;
-            uint32_t n = my < m ? (uint32_t)min((uint64_t)32, m - my) : 0;
+        for (P base = 0; base < m; base += 32 * G) {
+            P my = base + 32 * lane;
+            uint32_t n = my < m ? (uint32_t)min((P)32, (P)(m - my)) : 0;
             uint64_t mask = 0;
             if (n) mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
                               : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
@@ -543,7 +544,7 @@ struct WarpCtx {
             uint32_t t; int j;
             if (locate_break(mask, snp, A, t, j)) {
                 premature = true;
-                uint64_t matched = base + 32 * (uint64_t)j + t;
+                P matched = base + 32 * (P)j + t;
                 if (EV && lane == 0) ev.bases += (uint32_t)matched + 1;
                 return matched;
             }
@@ -551,8 +552,10 @@ struct WarpCtx {
         if (EV && lane == 0) ev.bases += (uint32_t)m;
         return m;
     }
-    __device__ __forceinline__ uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
-    __device__ __forceinline__ uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
+    template <class P>
+    __device__ __forceinline__ P cmp_fwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    template <class P>
+    __device__ __forceinline__ P cmp_bwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
 
     // nodes.push (ref :199, :219), keeping only what nodes_to_eq_class needs: the distinct
     // classes of the visited nodes (intersection is idempotent, ref :352-355).
@@ -649,7 +652,7 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
         WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
         const uint32_t lane = w.lane;
         uint32_t coverage = 0;
-        bool some = map_read_nodes(w, ix.k, (uint64_t)L, p.allowed_mismatches, coverage);
+        bool some = map_read_nodes<uint32_t>(w, ix.k, L, p.allowed_mismatches, coverage);
 
         HitRec h;
         h.coverage = 0; h.n_tx = 0; h.tx_off = 0; h.eq_id = kNone; h.flags = 0;
@@ -806,7 +809,7 @@ struct DevNovel {
 
 constexpr int kThreadBlock = 128;
 #ifndef PSA_THREAD_MIN_BLOCKS
-#define PSA_THREAD_MIN_BLOCKS 8
+#define PSA_THREAD_MIN_BLOCKS 10
 #endif
 
 // HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
@@ -942,9 +945,9 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;  // >= k: shorter reads never search
         WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
         w.scan_mode = true;
-        uint64_t kmer_pos = 0;
+        uint32_t kmer_pos = 0;
         uint32_t node = 0, off = 0;
-        const bool found = w.find_seed(kmer_pos, (uint64_t)L - ix.k, node, off);
+        const bool found = w.find_seed(kmer_pos, L - ix.k, node, off);
         if (w.lane == 0) {
             if (found) {
                 const unsigned long long at = atomicAdd(p.seeded_count, 1ULL);

@@ -160,11 +160,12 @@ struct SerialWarp {
     std::vector<uint32_t> eqs, lens;  // distinct visited classes
     uint64_t lookups = 0;
 
-    bool find_seed(uint64_t& kmer_pos, uint64_t last, uint32_t& node, uint32_t& off) {
+    template <class P>
+    bool find_seed(P& kmer_pos, P last, uint32_t& node, uint32_t& off) {
         if (kmer_pos > last) return false;
-        const uint64_t start = kmer_pos;
+        const P start = kmer_pos;
         // lane order == position order, so the first hitting lane is the sequential first hit
-        for (uint64_t p = start; p <= last; p += kSeedStride) {
+        for (P p = start; p <= last; p += kSeedStride) {
             lookups++;
             if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr, p != start)) { kmer_pos = p; return true; }
         }
@@ -177,11 +178,11 @@ struct SerialWarp {
     void jumped() {}
     uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes[id].pred[b]; }
     // the two compare loops, chunked by 32 bases exactly as the kernel lanes are
-    template <bool FWD>
-    uint64_t cmp(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& premature) {
+    template <bool FWD, class P>
+    P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
-        for (uint64_t my = 0; my < m; my += 32) {
-            uint32_t n = (uint32_t)std::min<uint64_t>(32, m - my);
+        for (P my = 0; my < m; my += 32) {
+            uint32_t n = (uint32_t)std::min<P>(32, m - my);
             uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
                                 : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
             uint32_t c = (uint32_t)popc64(mask);
@@ -193,8 +194,10 @@ struct SerialWarp {
         }
         return m;
     }
-    uint64_t cmp_fwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
-    uint64_t cmp_bwd(uint64_t rp, uint64_t sp, uint64_t m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
+    template <class P>
+    P cmp_fwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
+    template <class P>
+    P cmp_bwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
     void push(uint32_t, const NodeView& nv) {
         if (std::find(eqs.begin(), eqs.end(), nv.eq) != eqs.end()) return;
         eqs.push_back(nv.eq);
