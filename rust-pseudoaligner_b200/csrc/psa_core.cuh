@@ -819,7 +819,7 @@ constexpr int kThreadWide = 3;
 #define PSA_WIDE_INLINE 2
 #endif
 constexpr uint32_t kThreadWideInline = PSA_WIDE_INLINE;  // further wide classes applied on arrival before giving up
-constexpr int kThreadRecent = 4;
+constexpr int kThreadRecent = 2;
 constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
@@ -837,7 +837,7 @@ template <int KW, bool EV, class RD = PLoad>
 struct ThreadCtx {
     const DevIndex& ix;
     RD rd;
-    uint32_t k, max_probes;
+    uint32_t max_probes;
     // online class state
     bool multi;                    // more than one distinct class visited (until then min_eq/min_len ARE the one
                                    // class seen, whose window is fetched only when a second class shows up)
@@ -854,7 +854,7 @@ struct ThreadCtx {
     ThreadEvents ev;
 
     PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
-        : ix(ix_), rd(rd_), k(ix_.k), max_probes(max_probes_), multi(false),
+        : ix(ix_), rd(rd_), max_probes(max_probes_), multi(false),
           min_len(kNone), min_eq(kNone), n_wide(0), n_inline(0), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
         acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
@@ -895,7 +895,7 @@ struct ThreadCtx {
             ProbeStats st;
             // after a miss the next positions are likely absent too: Bloom first (never when counting
             // events, which are defined on the MPHF path)
-            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, o, EV ? &st : nullptr, !EV && probes > 0,
+            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, ix.k), node, o, EV ? &st : nullptr, !EV && probes > 0,
                                     PSA_TWO_AHEAD && probes == 0);
             if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) {
