@@ -231,7 +231,9 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     // stage 1: raw FASTQ text -> pinned block + record table (four-line records; id = header up to the
     // first blank, as bio::io::fastq::Record::id).  Bytes after the last complete record of a block are
     // carried over to the next one.
-    const uint64_t block_bytes = std::max<uint64_t>(batch_reads * 400, 1ull << 22);
+    // text per block: starts at 400 bytes per record, then follows the record size seen (+3 %), so that little
+    // text is left over after the batch_reads-th record and has to be carried to the next block
+    uint64_t block_bytes = std::max<uint64_t>(batch_reads * 400, 1ull << 22);
     std::thread reader([&]() {
         int s = 0;
         bool done = false, eof = false;
@@ -257,7 +259,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                     carry.clear();
                 }
                 if (!eof) {
-                    const uint64_t room = b.text.cap - 64 - have;
+                    const uint64_t room = std::min<uint64_t>(b.text.cap - 64 - have, want > have ? want - have : (1u << 20));
                     const size_t got = in.read(b.text.p + have, room);
                     have += got;
                     if (got < room) eof = true;
@@ -266,7 +268,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 index_newlines(b.text.p, have, num_threads, nl);
                 if (nl.size() >= 4 || eof) break;
                 // one record larger than the block: grow and read more
-                if ((err = b.text.reserve(2 * b.text.cap, have))) break;
+                block_bytes *= 2;
             }
             if (!err) {
                 // trailing blank lines at the end of the file are not records
@@ -314,6 +316,8 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 }
                 b.n = n_rec;
                 b.text_len = n_rec ? nl[4 * n_rec - 1] + 1 : 0;
+                if (n_rec == batch_reads)
+                    block_bytes = std::max<uint64_t>(b.text_len + b.text_len / 32 + 4096, 1ull << 22);
                 if (!err) {
                     carry.assign(b.text.p + b.text_len, b.text.p + have);
                     // only blank lines may remain at the end of the file
