@@ -184,7 +184,9 @@ int psa_mapper_map(psa_mapper*, const psa_read_batch* reads, psa_result_batch* r
 
 /* Device-resident batch, asynchronous on the mapper's stream, fixed shape helpers for
  * benchmarking: same as psa_mapper_map with location == PSA_MEM_DEVICE but does not
- * synchronise; results->tx_used is valid after psa_mapper_sync. */
+ * synchronise; results->tx_used is valid after psa_mapper_sync.  Several batches may be queued
+ * before one psa_mapper_sync: it then reports an overflow of ANY of them (PSA_ERR_CAPACITY; the
+ * buffers have been grown -- reset the counts and resubmit), and tx_used of the last one. */
 int psa_mapper_map_async(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results);
 int psa_mapper_sync(psa_mapper*);
 void* psa_mapper_stream(psa_mapper*); /* cudaStream_t */

@@ -613,7 +613,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
         return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
     }
     const uint64_t nc = ix->d.n_eq + 2;
-    if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(4)) ||
+    if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(8)) ||
         (rc = m->novel_cursor.ensure(64)) || (rc = m->events.ensure(40 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
         (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16)) ||
         (rc = m->slot[2].meta_dev.ensure(16)) || (rc = m->slot[3].meta_dev.ensure(16))) {
@@ -622,6 +622,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     cudaMemset(m->counts.p, 0, nc * 8);
     cudaMemset(m->events.p, 0, 40 * 8);
+    cudaMemset(m->status.p, 0, 8);
     // PSA_L2_WINDOW=1: a persisting L2 access-policy window over the index's small hot tables on the mapper's
     // stream.  Measured on B200 (config 3): 83 MB carve-out 3.55 ms vs 3.06 ms without, 48 MB 3.12, 16 MB 3.06 --
     // what the window keeps is paid for by the MPHF / values / read traffic it squeezes.  Off by default.
@@ -732,6 +733,7 @@ struct DeviceBatch {
     uint64_t tx_cap;
     uint64_t* meta_out;    // device u64[2]: {running total after the batch, status}
     uint64_t total_words;  // ragged ASCII only: sum of ceil(len/32) if the caller knows it, else 0
+    bool sticky = false;   // accumulate the status word over the batches queued since the last psa_mapper_sync
 };
 
 template <bool EV>
@@ -876,7 +878,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         k_expand<<<nblocks(n * 8, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
                                                       ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
     k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
-                                m->status.as<uint32_t>(), b.meta_out);
+                                m->status.as<uint32_t>(), b.meta_out, b.sticky ? m->status.as<uint32_t>() + 1 : nullptr);
     m->launches++;
     m->launches++;
     CU(cudaGetLastError());
@@ -942,6 +944,7 @@ extern "C" int psa_mapper_map_async(psa_mapper* m, const psa_read_batch* r, psa_
     CU(cudaSetDevice(m->ix->device));
     CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
     DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
+    b.sticky = true;  // earlier batches may still be queued: their overflow bits stay visible until the next sync
     if ((rc = enqueue_device_batch<false>(m, b, true))) return rc;
     CU(cudaMemcpyAsync(m->pin, m->meta.p, 16, cudaMemcpyDeviceToHost, m->st));
     m->pending = o;
@@ -955,6 +958,7 @@ extern "C" int psa_mapper_sync(psa_mapper* m) {
     if (m->pending) {
         psa_result_batch* o = m->pending;
         m->pending = nullptr;
+        CU(cudaMemsetAsync(m->status.as<uint32_t>() + 1, 0, 4, m->st));  // the sticky status restarts here
         o->tx_used = m->pin[0];
         uint32_t status = (uint32_t)m->pin[1];
         if (status & 3u) {
@@ -963,7 +967,8 @@ extern "C" int psa_mapper_sync(psa_mapper* m) {
             if ((status & 2u) && (rc = grow_pool(m))) return rc;
             return fail(PSA_ERR_CAPACITY, "novel-set buffer / class-list pool overflow (buffers grown: reset the counts and resubmit the batch)");
         }
-        if (o->tx_buf && o->tx_used > o->tx_cap) return fail(PSA_ERR_CAPACITY, "tx_buf too small");
+        if ((status & 4u) || (o->tx_buf && o->tx_used > o->tx_cap))
+            return fail(PSA_ERR_CAPACITY, "tx_buf too small (for one of the batches queued since the last sync)");
     }
     return PSA_OK;
 }

@@ -1028,13 +1028,19 @@ __global__ void k_expand(HitRec* hits, uint64_t n, const uint64_t* rel_off, cons
     }
     if (sub == 0) hits[i].tx_off = running[0] + rel;
 }
-// after k_expand: advance the running total, publish {running, status} for the host
+// after k_expand: advance the running total, publish {running, status} for the host.  sticky (may be
+// nullptr): the OR of the status words of every batch since the host last cleared it -- several batches may
+// be queued between two psa_mapper_sync calls and none of their overflows may go unnoticed.
 __global__ void k_advance(uint64_t* running, const uint64_t* batch_total, uint64_t tx_cap, int has_tx,
-                          const uint32_t* status, uint64_t* meta_out) {
+                          const uint32_t* status, uint64_t* meta_out, uint32_t* sticky) {
     if (threadIdx.x || blockIdx.x) return;
     uint64_t t = *batch_total;
     uint32_t st = *status;
     if (has_tx && t > tx_cap) st |= 4u;
+    if (sticky) {
+        *sticky |= st;
+        st = *sticky;
+    }
     running[0] += t;
     meta_out[0] = running[0];
     meta_out[1] = st;

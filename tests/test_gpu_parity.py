@@ -182,6 +182,17 @@ def test_device_batch_and_events(orc_index_for, fixture_fasta):
     pa.mapper.set_scan_width(16)
     ev = pa.mapper.map_device_events(b)
     _check_events(ev, want_ev)
+    # several batches queued before one sync: an overflow of an EARLIER one is still reported
+    b_small = pkg.DeviceBatch(pkg.pseudoaligner.READS_ASCII, data, n, stride=L, fixed_len=L, tx_cap=10)
+    pa.mapper.map_device_async(b_small)
+    pa.mapper.map_device_async(b)
+    with pytest.raises(pkg.PsaError) as e:
+        pa.mapper.sync()
+    assert e.value.code == -4
+    pa.mapper.counts_reset()
+    pa.mapper.map_device_async(b)
+    pa.mapper.sync()                      # and the flag does not stick beyond that sync
+    b_small.free()
     # packed device batch
     words, off, lens = orc.pack_reads(reads)
     b2 = pkg.DeviceBatch(pkg.pseudoaligner.READS_PACKED, words, n, read_off=off, read_len=lens, tx_cap=64 * n)
