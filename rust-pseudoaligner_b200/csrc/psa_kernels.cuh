@@ -233,6 +233,7 @@ struct ReadsView {          // device-resident batch
 __global__ void k_words_per_read(const uint32_t* len, uint64_t n, uint64_t* nw) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n) nw[i] = ((uint64_t)len[i] + 31) >> 5;
+    else if (i == n) nw[i] = 0;  // the scan runs over n + 1 items so that its last output is the total
 }
 
 // 4 ASCII bytes (first base in the low byte) -> 8 bits of 2-bit codes, first base in bits 7:6.
