@@ -875,7 +875,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
     }
     if (n)
-        k_expand<<<nblocks(n * 8, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
+        k_expand<<<nblocks(n * PSA_EXPAND_LANES, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
                                                       ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
     k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
                                 m->status.as<uint32_t>(), b.meta_out, b.sticky ? m->status.as<uint32_t>() + 1 : nullptr);

@@ -1016,16 +1016,22 @@ struct CastU64 {
 
 // rel_off[i] = offset of read i's members inside this batch's tx_buf; running[0] = members
 // emitted by the batches before this one (so that tx_off is global across a chunked call).
+// S lanes per read: the copy is a chain of three dependent accesses (hit -> members -> store), so what
+// matters is how many reads are in flight, not how many lanes share one (S = 2 measured best).
+#ifndef PSA_EXPAND_LANES
+#define PSA_EXPAND_LANES 2
+#endif
 __global__ void k_expand(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
                          const uint32_t* eq_mem, const uint32_t* novel, uint32_t* tx_buf, uint64_t tx_cap) {
-    const uint32_t sub = threadIdx.x & 7;
-    uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 3;
+    constexpr uint32_t S = PSA_EXPAND_LANES;
+    const uint32_t sub = threadIdx.x % S;
+    uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) / S;
     if (i >= n) return;
     HitRec h = hits[i];
     uint64_t rel = rel_off[i];
     if (tx_buf && rel + h.n_tx <= tx_cap) {
         const uint32_t* src = (h.eq_id != kNone ? eq_mem : novel) + h.tx_off;
-        for (uint32_t j = sub; j < h.n_tx; j += 8) tx_buf[rel + j] = src[j];
+        for (uint32_t j = sub; j < h.n_tx; j += S) tx_buf[rel + j] = src[j];
     }
     if (sub == 0) hits[i].tx_off = running[0] + rel;
 }
