@@ -405,8 +405,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         def e2e_step(g):
-            return mapper._map_host(psa.READS_ASCII, host_batches[g].array, R, None, None, L, L, True,
-                                    tx_cap=tx_cap, hits=pin_hits.array, tx=pin_tx.array)
+            return mapper.map_ascii_fixed(host_batches[g].array, R, L, tx_cap=tx_cap, hits=pin_hits.array, tx=pin_tx.array)
         e2e_step(0)
         e2e_step(1 % G)
         barrier()
