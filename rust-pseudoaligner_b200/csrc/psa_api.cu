@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
@@ -1034,9 +1035,14 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         uint64_t stage_need = 0;
         uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
 
+        const bool verbose = getenv("PSA_VERBOSE") != nullptr;
+        double t_wait = 0, t_submit = 0;
+        auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         auto finish = [&](uint64_t c) -> int {  // host side of chunk c: totals, members D2H
             Slot& S = m->slot[c % kSlots];
+            const double tw0 = verbose ? now_s() : 0;
             CU(cudaEventSynchronize(S.meta_done));
+            if (verbose) t_wait += now_s() - tw0;
             uint64_t total = S.meta_host[0];
             uint32_t status = (uint32_t)S.meta_host[1];
             if (status & 1u) novel_overflow = true;
@@ -1057,6 +1063,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         for (uint64_t c = 0; c < nchunks; c++) {
             const ChunkPlan& P = plan[c];
             Slot& S = m->slot[c % kSlots];
+            const double ts0 = verbose ? now_s() : 0;
             // H2D
             if (S.in_free_rec) CU(cudaStreamWaitEvent(m->st_h2d, S.in_free, 0));
             CU(cudaMemcpyAsync(S.in_data.p, (const uint8_t*)r->data + P.d0 * unit, P.dn * unit, cudaMemcpyHostToDevice, m->st_h2d));
@@ -1089,12 +1096,17 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             CU(cudaMemcpyAsync(S.meta_host, S.meta_dev.p, 16, cudaMemcpyDeviceToHost, m->st_d2h));
             CU(cudaEventRecord(S.meta_done, m->st_d2h));
             CU(cudaMemcpyAsync(o->hits + P.r0, S.hits.p, P.nr * sizeof(HitRec), cudaMemcpyDeviceToHost, m->st_d2h));
+            if (verbose) t_submit += now_s() - ts0;
             if (c >= (uint64_t)(kSlots - 1) && (rc = finish(c - (kSlots - 1)))) return rc;
         }
         for (uint64_t c = nchunks > (uint64_t)(kSlots - 1) ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
             if ((rc = finish(c))) return rc;
+        const double td0 = verbose ? now_s() : 0;
         CU(cudaStreamSynchronize(m->st_d2h));
         CU(cudaStreamSynchronize(m->st));
+        if (verbose)
+            fprintf(stderr, "psa: map_host %llu chunks: submit %.2f ms, waits on chunk totals %.2f ms, final drain %.2f ms\n",
+                    (unsigned long long)nchunks, 1e3 * t_submit, 1e3 * t_wait, 1e3 * (now_s() - td0));
         o->tx_used = tx_prev_total;
         if (novel_overflow || stage_overflow || spill_overflow) {
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
