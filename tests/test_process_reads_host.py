@@ -1,0 +1,110 @@
+"""Host logic of psa_process_reads (csrc/process_reads.cpp: FASTQ reader, record table, batching across
+text blocks, ordered `{:?}` line writer -- the mirror of ref src/pseudoaligner.rs:420-514) without a GPU:
+the file is linked against a stand-in mapper (tests/hostsim/process_stub.cpp) that derives a fake result
+from each read's bytes, so every record must reach the mapper intact and come out in input order.  The
+real mapper behind the same driver is covered by the `-m gpu` test test_process_reads_native."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+
+
+class _Stats(C.Structure):
+    _fields_ = [("reads", C.c_uint64), ("mapped", C.c_uint64), ("aligned", C.c_uint64), ("seconds", C.c_double),
+                ("reader_seconds", C.c_double), ("mapper_seconds", C.c_double), ("writer_seconds", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def stub():
+    subprocess.check_call(["make", "-C", _DIR, "libprocess_stub.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(_DIR, "libprocess_stub.so"))
+    L.psa_process_reads.restype = C.c_int
+    L.psa_process_reads.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(_Stats)]
+    return L
+
+
+def _expected(records):
+    out = []
+    for rid, seq in records:
+        flag = "true" if seq[:1] == b"T" else "false"
+        esc = rid.decode().replace("\\", "\\\\").replace('"', '\\"')
+        members = "[%d]" % sum(seq) if seq else "[]"
+        out.append('(%s, "%s", %s, %d)' % (flag, esc, members, len(seq)))
+    return out
+
+
+def _fastq(records, eol=b"\n", comment=b""):
+    return b"".join(b"@" + rid + comment + eol + seq + eol + b"+" + eol + b"I" * len(seq) + eol for rid, seq in records)
+
+
+def _run(stub, path, out, threads=2, batch=0):
+    st = _Stats()
+    rc = stub.psa_process_reads(C.c_void_p(1), str(path).encode(), str(out).encode(), threads, batch, 0, C.byref(st))
+    return rc, st, open(out).read().splitlines()
+
+
+def _records(rng, n, lmin=1, lmax=200):
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(lmin, lmax + 1))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), L).tolist())
+        recs.append((b"read%d/%d" % (i, L), seq))
+    return recs
+
+
+@pytest.mark.parametrize("batch,threads", [(0, 1), (7, 3), (1000, 2), (1, 2)])
+def test_records_reach_the_mapper_in_order(stub, tmp_path, batch, threads):
+    rng = np.random.default_rng(batch + threads)
+    recs = _records(rng, 2500 if batch != 1 else 40)
+    p = tmp_path / "a.fq"
+    p.write_bytes(_fastq(recs, comment=b" some comment\tmore"))
+    rc, st, lines = _run(stub, p, tmp_path / "out.txt", threads, batch)
+    assert rc == 0 and lines == _expected(recs)
+    assert st.reads == len(recs) and st.aligned == len(recs) and st.mapped == sum(1 for _, s in recs if s[:1] == b"T")
+
+
+def test_gzip_crlf_blank_tail_and_no_final_newline(stub, tmp_path):
+    rng = np.random.default_rng(3)
+    recs = _records(rng, 300)
+    want = _expected(recs)
+    gz = tmp_path / "a.fq.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(_fastq(recs))
+    assert _run(stub, gz, tmp_path / "o1", 2, 64)[2] == want
+    crlf = tmp_path / "crlf.fq"
+    crlf.write_bytes(_fastq(recs, eol=b"\r\n") + b"\r\n\r\n\n")
+    assert _run(stub, crlf, tmp_path / "o2", 2, 77)[2] == want
+    nonl = tmp_path / "nonl.fq"
+    nonl.write_bytes(_fastq(recs)[:-1])                      # last quality line without its newline
+    assert _run(stub, nonl, tmp_path / "o3", 1, 50)[2] == want
+    empty = tmp_path / "empty.fq"
+    empty.write_bytes(b"")
+    rc, st, lines = _run(stub, empty, tmp_path / "o4")
+    assert rc == 0 and st.reads == 0 and lines == []
+
+
+def test_quotes_in_ids_and_records_larger_than_a_block(stub, tmp_path):
+    recs = [(b'we"ird\\id', b"ACGT"), (b"big", b"ACGT" * 2_000_000), (b"after", b"TTTT")]   # 8 MB record > 4 MB block
+    p = tmp_path / "big.fq"
+    p.write_bytes(_fastq(recs))
+    rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 2)
+    assert rc == 0 and lines == _expected(recs)
+
+
+def test_malformed_files_are_errors_after_the_good_records(stub, tmp_path):
+    rng = np.random.default_rng(4)
+    recs = _records(rng, 100)
+    good = _fastq(recs)
+    for name, tail in (("truncated", b"@broken\nACGT\n"), ("no_plus", b"@x\nACGT\nACGT\nIIII\n"), ("no_at", b"x\nACGT\n+\nIIII\n")):
+        p = tmp_path / (name + ".fq")
+        p.write_bytes(good + tail + (_fastq(recs[:3]) if name != "truncated" else b""))
+        rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 30)
+        assert rc == -7, name                                 # PSA_ERR_IO (the reference panics, :446)
+        assert lines == _expected(recs), name                 # every complete record before the bad one
+    rc, _, _ = _run(stub, tmp_path / "missing.fq", tmp_path / "out.txt")
+    assert rc == -7
