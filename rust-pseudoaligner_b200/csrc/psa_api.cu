@@ -647,6 +647,10 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
                         ix->hot_bytes / 1e6, max_persist / 1e6, max_window / 1e6, attr.accessPolicyWindow.hitRatio);
         }
     }
+    // PSA_L2_FETCH=32|64|128: device-wide hint for the granularity of L2 fills from HBM (experiment knob)
+    if (const char* e = getenv("PSA_L2_FETCH")) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)) != cudaSuccess) (void)cudaGetLastError();
+    }
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;

@@ -808,6 +808,9 @@ struct DevNovel {
     }
 };
 
+#ifndef PSA_HIT_STREAM
+#define PSA_HIT_STREAM 0
+#endif
 constexpr int kThreadBlock = 128;
 #ifndef PSA_THREAD_MIN_BLOCKS
 #define PSA_THREAD_MIN_BLOCKS 10
@@ -883,9 +886,15 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
             if (!defer) {
                 // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
                 uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
+#if PSA_HIT_STREAM  // experiment: streaming (evict-first) stores for the write-once hit records
+                __stcs(out + 0, (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32));
+                __stcs(out + 1, (uint64_t)res.hit.tx_off);
+                __stcs(out + 2, (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32));
+#else
                 out[0] = (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32);
                 out[1] = res.hit.tx_off;
                 out[2] = (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32);
+#endif
                 if (p.counts) atomicAdd(p.counts + res.count_slot, 1ULL);
                 if (res.novel_overflow) atomicOr(p.status, 1u);
                 n_tx = res.hit.n_tx;
