@@ -14,6 +14,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <chrono>
@@ -32,7 +36,8 @@ struct Pinned {  // growable cudaHostAlloc buffer (contents preserved on growth)
     uint64_t cap = 0;
     int reserve(uint64_t want, uint64_t keep) {
         if (want <= cap) return PSA_OK;
-        uint64_t ncap = want + want / 2 + 4096;
+        // the first allocation is what was asked for (pinning costs ~0.4 s per GB); regrowth leaves headroom
+        uint64_t ncap = p ? want + want / 2 + 4096 : want + 4096;
         void* q = nullptr;
         int rc = psa_host_alloc(&q, ncap);
         if (rc) return rc;
@@ -61,10 +66,13 @@ struct Batch {
     bool last = false;
 };
 
-// raw byte source: plain files through read(2)-style fread, gzip through zlib
+// raw byte source: regular files through pread(2) (any number of threads at once), everything else
+// (pipes, gzip) through a serial stream
 struct ByteSource {
     gzFile gz = nullptr;
     FILE* fp = nullptr;
+    int fd = -1;            // regular plain file: positional reads
+    uint64_t size = 0, pos = 0;
     bool open(const char* path) {
         fp = fopen(path, "rb");
         if (!fp) return false;
@@ -79,8 +87,24 @@ struct ByteSource {
         } else {
             rewind(fp);
             setvbuf(fp, nullptr, _IONBF, 0);
+            struct stat st;
+            if (fstat(fileno(fp), &st) == 0 && S_ISREG(st.st_mode)) {
+                fd = fileno(fp);
+                size = (uint64_t)st.st_size;
+            }
         }
         return true;
+    }
+    bool parallel() const { return fd >= 0; }
+    // positional read of [at, at + n) of a regular file; returns bytes read
+    size_t read_at(uint8_t* dst, size_t n, uint64_t at) const {
+        size_t total = 0;
+        while (total < n) {
+            ssize_t g = pread(fd, dst + total, n - total, (off_t)(at + total));
+            if (g <= 0) break;
+            total += (size_t)g;
+        }
+        return total;
     }
     // fills up to n bytes; returns bytes read (0 at end of file)
     size_t read(uint8_t* dst, size_t n) {
@@ -103,90 +127,238 @@ struct ByteSource {
         if (fp) fclose(fp);
         gz = nullptr;
         fp = nullptr;
+        fd = -1;
     }
 };
 
-// positions of every '\n' in text[0, n), found by `threads` threads over equal slices
-void index_newlines(const uint8_t* text, uint64_t n, uint32_t threads, std::vector<uint64_t>& nl) {
-    std::vector<std::vector<uint64_t>> part(threads);
+// Uninitialised growable array (std::vector would zero-fill tens of megabytes per block on one thread)
+struct U64Buf {
+    uint64_t* p = nullptr;
+    uint64_t cap = 0, n = 0;
+    bool resize(uint64_t want) {
+        if (want > cap) {
+            uint64_t ncap = want + want / 4 + 1024;
+            void* q = realloc(p, ncap * 8);
+            if (!q) return false;
+            p = (uint64_t*)q;
+            cap = ncap;
+        }
+        n = want;
+        return true;
+    }
+    uint64_t size() const { return n; }
+    uint64_t operator[](uint64_t i) const { return p[i]; }
+    ~U64Buf() { free(p); }
+};
+
+// Appends up to `room` bytes of the source to text[have, ...) and finds every '\n' of text[0, have + got):
+// `threads` threads each read one slice of the new bytes (regular files: pread, all at once; streams: one
+// serial read first) and scan it while it is still in their cache; thread 0 also scans the bytes that were
+// there before.  Returns the bytes appended; nl = the newline positions, ascending.
+uint64_t fill_and_index(ByteSource& in, uint8_t* text, uint64_t have, uint64_t room, uint32_t threads, bool& eof,
+                        std::vector<std::vector<uint64_t>>& part, U64Buf& nl, bool& oom) {
+    uint64_t got = 0;
+    const bool par = in.parallel();
+    if (!eof) {
+        if (par) {
+            got = std::min<uint64_t>(room, in.size > in.pos ? in.size - in.pos : 0);
+        } else {
+            got = in.read(text + have, room);
+            if (got < room) eof = true;
+        }
+    }
+    part.resize(threads + 1);
+    std::vector<uint64_t> short_by(threads, 0);
     std::vector<std::thread> th;
+    auto scan = [&](std::vector<uint64_t>& v, uint64_t lo, uint64_t hi) {
+        v.reserve(v.size() + (hi - lo) / 64 + 16);
+        const uint8_t* p = text + lo;
+        const uint8_t* end = text + hi;
+        while (p < end) {
+            const uint8_t* q = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+            if (!q) break;
+            v.push_back((uint64_t)(q - text));
+            p = q + 1;
+        }
+    };
     for (uint32_t t = 0; t < threads; t++) {
         th.emplace_back([&, t]() {
-            const uint64_t lo = n * t / threads, hi = n * (t + 1) / threads;
-            std::vector<uint64_t>& v = part[t];
-            v.reserve((hi - lo) / 64 + 16);
-            const uint8_t* p = text + lo;
-            const uint8_t* end = text + hi;
-            while (p < end) {
-                const uint8_t* q = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
-                if (!q) break;
-                v.push_back((uint64_t)(q - text));
-                p = q + 1;
+            part[t + 1].clear();
+            if (t == 0) {
+                part[0].clear();
+                scan(part[0], 0, have);
             }
+            const uint64_t lo = have + got * t / threads, hi = have + got * (t + 1) / threads;
+            if (par && hi > lo) {
+                const size_t g = in.read_at(text + lo, hi - lo, in.pos + (lo - have));
+                short_by[t] = (hi - lo) - g;
+            }
+            scan(part[t + 1], lo, hi);
         });
     }
     for (auto& x : th) x.join();
-    size_t total = 0;
-    for (auto& v : part) total += v.size();
-    nl.clear();
-    nl.reserve(total);
-    for (auto& v : part) nl.insert(nl.end(), v.begin(), v.end());
+    if (par) {
+        for (uint32_t t = 0; t < threads; t++)
+            if (short_by[t]) {  // the file shrank under us: keep the bytes before the first hole
+                uint64_t keep = got * t / threads + ((got * (t + 1) / threads - got * t / threads) - short_by[t]);
+                for (uint32_t u = t; u < threads; u++) {
+                    auto& v = part[u + 1];
+                    while (!v.empty() && v.back() >= have + keep) v.pop_back();
+                }
+                got = keep;
+                in.size = in.pos + got;
+                break;
+            }
+        in.pos += got;
+        if (in.pos >= in.size) eof = true;
+    }
+    // ascending positions in one array, copied by the threads that found them
+    std::vector<uint64_t> at(threads + 2, 0);
+    for (uint32_t t = 0; t <= threads; t++) at[t + 1] = at[t] + part[t].size();
+    if (!nl.resize(at[threads + 1] + 1)) {  // (+1: the caller may append the newline of an unterminated last line)
+        oom = true;
+        return got;
+    }
+    nl.n = at[threads + 1];
+    th.clear();
+    for (uint32_t t = 0; t < threads; t++)
+        th.emplace_back([&, t]() {
+            if (t == 0 && !part[0].empty()) memcpy(nl.p, part[0].data(), part[0].size() * 8);
+            if (!part[t + 1].empty()) memcpy(nl.p + at[t + 1], part[t + 1].data(), part[t + 1].size() * 8);
+        });
+    for (auto& x : th) x.join();
+    return got;
 }
 
-// Rust's `{:?}` of a String: quotes, with \" \\ \n \r \t \0 and \u{..} for other control chars
-void debug_str(std::string& out, const char* s, size_t n) {
-    out.push_back('"');
-    for (size_t i = 0; i < n; i++) {
-        unsigned char c = (unsigned char)s[i];
-        switch (c) {
-            case '"': out += "\\\""; break;
-            case '\\': out += "\\\\"; break;
-            case '\n': out += "\\n"; break;
-            case '\r': out += "\\r"; break;
-            case '\t': out += "\\t"; break;
-            case 0: out += "\\0"; break;
-            default:
-                if (c < 0x20 || c == 0x7f) {
-                    char t[16];
-                    snprintf(t, sizeof t, "\\u{%x}", c);
-                    out += t;
-                } else {
-                    out.push_back((char)c);
-                }
+// Output text of one formatter thread: a raw growable buffer (no per-append capacity checks on the hot path:
+// the caller reserves the worst case of a record before formatting it)
+struct OutBuf {
+    char* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool ok = true;
+    void reserve_more(size_t extra) {
+        if (n + extra <= cap) return;
+        size_t ncap = std::max(cap + cap / 2, n + extra + (1u << 16));
+        void* q = realloc(p, ncap);
+        if (!q) {
+            ok = false;  // the caller stops formatting and reports the failure
+        } else {
+            p = (char*)q;
+            cap = ncap;
         }
     }
-    out.push_back('"');
+    ~OutBuf() { free(p); }
+};
+
+// Rust's `{:?}` of a String: quotes, with \" \\ \n \r \t \0 and \u{..} for other control chars
+// (at most 6 output bytes per input byte, + 2 quotes)
+char* debug_str(char* o, const char* s, size_t n) {
+    *o++ = '"';
+    for (size_t i = 0; i < n; i++) {
+        unsigned char c = (unsigned char)s[i];
+        if (c >= 0x20 && c != 0x7f && c != '"' && c != '\\') {
+            *o++ = (char)c;
+            continue;
+        }
+        switch (c) {
+            case '"': *o++ = '\\'; *o++ = '"'; break;
+            case '\\': *o++ = '\\'; *o++ = '\\'; break;
+            case '\n': *o++ = '\\'; *o++ = 'n'; break;
+            case '\r': *o++ = '\\'; *o++ = 'r'; break;
+            case '\t': *o++ = '\\'; *o++ = 't'; break;
+            case 0: *o++ = '\\'; *o++ = '0'; break;
+            default: o += sprintf(o, "\\u{%x}", c);
+        }
+    }
+    *o++ = '"';
+    return o;
 }
 
-void put_u64(std::string& out, uint64_t v) {
-    char t[24];
-    int i = 24;
-    do { t[--i] = (char)('0' + v % 10); v /= 10; } while (v);
-    out.append(t + i, 24 - i);
+const char kDigits2[201] =
+    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+// decimal of a 32-bit value, two digits per division
+inline char* put_u32(char* o, uint32_t v) {
+    char t[10];
+    int i = 10;
+    while (v >= 100) {
+        const uint32_t q = v / 100, r = v - q * 100;
+        t[--i] = kDigits2[2 * r + 1];
+        t[--i] = kDigits2[2 * r];
+        v = q;
+    }
+    if (v >= 10) {
+        t[--i] = kDigits2[2 * v + 1];
+        t[--i] = kDigits2[2 * v];
+    } else {
+        t[--i] = (char)('0' + v);
+    }
+    memcpy(o, t + i, (size_t)(10 - i));
+    return o + (10 - i);
 }
 
 // `(flag, "id", [tx, ...], coverage)` -- the tuple printed at ref src/pseudoaligner.rs:490
-void format_range(const Batch& b, uint64_t r0, uint64_t r1, std::string& out, uint64_t& mapped) {
+void format_range(const Batch& b, uint64_t r0, uint64_t r1, OutBuf& out, uint64_t& mapped, uint64_t& aligned) {
     const psa_hit* hits = (const psa_hit*)b.hits.p;
     const uint32_t* tx = (const uint32_t*)b.tx.p;
-    out.clear();
-    out.reserve((r1 - r0) * 64);
+    out.n = 0;
+    out.ok = true;
     for (uint64_t i = r0; i < r1; i++) {
         const psa_hit& h = hits[i];
+        // worst case of this record: flag 8, id 6 per byte + 2, 12 per member ("4294967295, "), brackets/coverage/newline 32
+        out.reserve_more(8 + 6 * (size_t)b.id_len[i] + 2 + 12 * (size_t)h.n_tx + 32);
+        if (!out.ok) return;
+        char* o = out.p + out.n;
         const bool flag = (h.flags & PSA_FLAG_MAPPED) != 0;
         mapped += flag;
-        out += flag ? "(true, " : "(false, ";
-        debug_str(out, (const char*)b.text.p + b.id_off[i], b.id_len[i]);
-        out += ", [";
+        aligned += h.flags & PSA_FLAG_ALIGNED;
+        if (flag) { memcpy(o, "(true, ", 7); o += 7; }
+        else { memcpy(o, "(false, ", 8); o += 8; }
+        o = debug_str(o, (const char*)b.text.p + b.id_off[i], b.id_len[i]);
+        *o++ = ','; *o++ = ' '; *o++ = '[';
+        const uint32_t* m = tx + h.tx_off;
         for (uint32_t j = 0; j < h.n_tx; j++) {
-            if (j) out += ", ";
-            put_u64(out, tx[h.tx_off + j]);
+            if (j) { *o++ = ','; *o++ = ' '; }
+            o = put_u32(o, m[j]);
         }
-        out += "], ";
-        put_u64(out, h.coverage);
-        out += ")\n";
+        *o++ = ']'; *o++ = ','; *o++ = ' ';
+        o = put_u32(o, h.coverage);
+        *o++ = ')'; *o++ = '\n';
+        out.n = (size_t)(o - out.p);
     }
 }
+
+// Ordered output: a regular file is written by all formatter threads at once (each at its own offset,
+// pwrite); pipes and append-mode descriptors take the parts one after the other.
+struct OutFile {
+    FILE* f = nullptr;
+    int fd = -1;          // >= 0: positional writes
+    uint64_t pos = 0;
+    void attach(FILE* file) {
+        f = file;
+        fflush(f);
+        const int d = fileno(f);
+        struct stat st;
+        const int fl = fcntl(d, F_GETFL);
+        if (d >= 0 && fstat(d, &st) == 0 && S_ISREG(st.st_mode) && fl != -1 && !(fl & O_APPEND)) {
+            const off_t at = lseek(d, 0, SEEK_CUR);
+            if (at >= 0) {
+                fd = d;
+                pos = (uint64_t)at;
+            }
+        }
+    }
+    static bool write_at(int fd, const char* p, size_t n, uint64_t at) {
+        while (n) {
+            ssize_t g = pwrite(fd, p, n, (off_t)at);
+            if (g <= 0) return false;
+            p += g; n -= (size_t)g; at += (uint64_t)g;
+        }
+        return true;
+    }
+    void finish() {
+        if (fd >= 0) lseek(fd, (off_t)pos, SEEK_SET);  // stdio continues after what was written
+    }
+};
 
 }  // namespace
 
@@ -194,7 +366,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                                  uint64_t batch_reads, int progress, psa_process_stats* stats) {
     if (!index || !fastq_path) return PSA_ERR_ARG;
     if (!num_threads) num_threads = 1;
-    if (!batch_reads) batch_reads = 1ull << 20;
+    if (!batch_reads) batch_reads = 1ull << 19;  // one pipeline chunk of psa_mapper_map: small blocks keep the start-up short
     const auto t0 = std::chrono::steady_clock::now();
 
     ByteSource in;
@@ -208,6 +380,8 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             return PSA_ERR_IO;
         }
     }
+    OutFile of;
+    of.attach(out);
     psa_mapper* mapper = nullptr;
     int rc = psa_mapper_create(index, 0, &mapper);
     if (rc) {
@@ -223,6 +397,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     int reader_rc = PSA_OK;
     bool abort_all = false;
     double busy_reader = 0, busy_mapper = 0, busy_writer = 0;  // seconds spent working (not waiting) per stage
+    const bool verbose = getenv("PSA_VERBOSE") != nullptr;
     auto now = []() { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double>(b - a).count();
@@ -238,7 +413,8 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
         int s = 0;
         bool done = false, eof = false;
         std::vector<uint8_t> carry;
-        std::vector<uint64_t> nl;
+        U64Buf nl;
+        std::vector<std::vector<uint64_t>> parts;
         while (!done) {
             Batch& b = slot[s];
             {
@@ -247,25 +423,33 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 if (abort_all) return;
             }
             const auto tr0 = now();
+            double t_alloc = 0, t_read = 0;
             int err = PSA_OK;
             b.n = 0; b.tx_used = 0; b.last = false; b.text_len = 0;
             uint64_t have = 0;
             for (;;) {
                 const uint64_t want = std::max<uint64_t>(block_bytes, carry.size() + (1u << 20));
+                const auto ta0 = now();
                 if ((err = b.text.reserve(want + 64, have))) break;
+                t_alloc += secs(ta0, now());
                 if (!have && !carry.empty()) {
                     memcpy(b.text.p, carry.data(), carry.size());
                     have = carry.size();
                     carry.clear();
                 }
-                if (!eof) {
-                    const uint64_t room = std::min<uint64_t>(b.text.cap - 64 - have, want > have ? want - have : (1u << 20));
-                    const size_t got = in.read(b.text.p + have, room);
-                    have += got;
-                    if (got < room) eof = true;
+                const auto tq0 = now();
+                const uint64_t room = std::min<uint64_t>(b.text.cap - 64 - have, want > have ? want - have : (1u << 20));
+                bool oom = false;
+                have += fill_and_index(in, b.text.p, have, room, num_threads, eof, parts, nl, oom);
+                if (oom) {
+                    err = PSA_ERR_NOMEM;
+                    break;
                 }
-                if (eof && have && b.text.p[have - 1] != '\n') b.text.p[have++] = '\n';  // unterminated last line
-                index_newlines(b.text.p, have, num_threads, nl);
+                if (eof && have && b.text.p[have - 1] != '\n') {  // unterminated last line
+                    b.text.p[have] = '\n';
+                    nl.p[nl.n++] = have++;
+                }
+                t_read += secs(tq0, now());
                 if (nl.size() >= 4 || eof) break;
                 // one record larger than the block: grow and read more
                 block_bytes *= 2;
@@ -326,6 +510,9 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 }
             }
             busy_reader += secs(tr0, now());
+            if (verbose)
+                fprintf(stderr, "psa: reader block %llu records, %.1f MB: alloc %.0f ms, read + newline index %.0f ms, total %.0f ms\n",
+                        (unsigned long long)b.n, b.text_len / 1e6, 1e3 * t_alloc, 1e3 * t_read, 1e3 * secs(tr0, now()));
             std::unique_lock<std::mutex> lk(mu);
             if (err) {
                 reader_rc = err;
@@ -343,8 +530,9 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     int writer_rc = PSA_OK;
     std::thread writer([&]() {
         int s = 0;
-        std::vector<std::string> parts(num_threads);
-        std::vector<uint64_t> mapped(num_threads);
+        std::vector<OutBuf> parts(num_threads);
+        std::vector<uint64_t> mapped(num_threads), aligned(num_threads);
+        std::vector<char> failed(num_threads);
         for (;;) {
             Batch& b = slot[s];
             {
@@ -356,17 +544,34 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             if (b.n) {
                 std::vector<std::thread> th;
                 for (uint32_t t = 0; t < num_threads; t++) {
-                    mapped[t] = 0;
+                    mapped[t] = aligned[t] = 0;
                     uint64_t r0 = b.n * t / num_threads, r1 = b.n * (t + 1) / num_threads;
-                    th.emplace_back([&, t, r0, r1]() { format_range(b, r0, r1, parts[t], mapped[t]); });
+                    th.emplace_back([&, t, r0, r1]() { format_range(b, r0, r1, parts[t], mapped[t], aligned[t]); });
                 }
                 for (auto& x : th) x.join();
+                th.clear();
+                const auto tw1 = now();
                 for (uint32_t t = 0; t < num_threads; t++) {
-                    if (fwrite(parts[t].data(), 1, parts[t].size(), out) != parts[t].size()) writer_rc = PSA_ERR_IO;
+                    if (!parts[t].ok) writer_rc = PSA_ERR_NOMEM;
                     n_mapped += mapped[t];
+                    n_aligned += aligned[t];
                 }
-                const psa_hit* hits = (const psa_hit*)b.hits.p;
-                for (uint64_t i = 0; i < b.n; i++) n_aligned += hits[i].flags & PSA_FLAG_ALIGNED;
+                if (of.fd >= 0) {
+                    std::vector<uint64_t> at(num_threads + 1, of.pos);
+                    for (uint32_t t = 0; t < num_threads; t++) at[t + 1] = at[t] + parts[t].n;
+                    for (uint32_t t = 0; t < num_threads; t++)
+                        th.emplace_back([&, t]() { failed[t] = !OutFile::write_at(of.fd, parts[t].p, parts[t].n, at[t]); });
+                    for (auto& x : th) x.join();
+                    for (uint32_t t = 0; t < num_threads; t++)
+                        if (failed[t]) writer_rc = PSA_ERR_IO;
+                    of.pos = at[num_threads];
+                } else {
+                    for (uint32_t t = 0; t < num_threads; t++)
+                        if (parts[t].n && fwrite(parts[t].p, 1, parts[t].n, out) != parts[t].n) writer_rc = PSA_ERR_IO;
+                }
+                if (verbose)
+                    fprintf(stderr, "psa: writer block %llu records: format %.0f ms, write %.0f ms (%s)\n", (unsigned long long)b.n,
+                            1e3 * secs(tw0, tw1), 1e3 * secs(tw1, now()), of.fd >= 0 ? "pwrite by every thread" : "serial");
                 n_reads += b.n;
                 if (progress && n_reads >= next_tick) {  // ref :497-504
                     fprintf(stderr, "\rDone Mapping %llu reads w/ Rate: %g", (unsigned long long)n_reads,
@@ -422,6 +627,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             b.tx_used = o.tx_used;
         }
         busy_mapper += secs(tm0, now());
+        if (verbose) fprintf(stderr, "psa: mapper block %llu records: %.0f ms\n", (unsigned long long)b.n, 1e3 * secs(tm0, now()));
         const bool last = b.last;
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -437,6 +643,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     reader.join();
     writer.join();
     if (progress) fprintf(stderr, "\n");
+    of.finish();
     fflush(out);
     if (own_out) fclose(out);
     in.close();

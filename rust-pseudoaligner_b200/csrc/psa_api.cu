@@ -1027,21 +1027,24 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         int rc;
         CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
         CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
-        for (int s = 0; s < kSlots; s++) {
+        const bool verbose = getenv("PSA_VERBOSE") != nullptr;
+        auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double ta0 = verbose ? now_s() : 0;
+        // staging for as many slots as the call has chunks (a one-chunk call uses slot 0 only)
+        for (int s = 0; s < kSlots && (uint64_t)s < nchunks; s++) {
             Slot& S = m->slot[s];
-            if ((rc = S.in_data.ensure(max_dn * unit + 64)) || (rc = S.hits.ensure(C * sizeof(HitRec)))) return rc;
+            if ((rc = S.in_data.ensure(max_dn * unit + 64)) || (rc = S.hits.ensure(std::min(C, n) * sizeof(HitRec)))) return rc;
             if (r->read_off && (rc = S.in_off.ensure(C * 8))) return rc;
             if (r->read_len && (rc = S.in_len.ensure(C * 4))) return rc;
             if (o->tx_buf && (rc = S.tx.ensure(std::max<uint64_t>(S.tx.cap, std::min(C, n) * 16 * 4)))) return rc;
-            S.in_free_rec = S.out_free_rec = false;
         }
+        for (int s = 0; s < kSlots; s++) m->slot[s].in_free_rec = m->slot[s].out_free_rec = false;
+        const double t_alloc = verbose ? now_s() - ta0 : 0;
         bool novel_overflow = false, spill_overflow = false, stage_overflow = false;
         uint64_t stage_need = 0;
         uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
 
-        const bool verbose = getenv("PSA_VERBOSE") != nullptr;
         double t_wait = 0, t_submit = 0;
-        auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         auto finish = [&](uint64_t c) -> int {  // host side of chunk c: totals, members D2H
             Slot& S = m->slot[c % kSlots];
             const double tw0 = verbose ? now_s() : 0;
@@ -1109,8 +1112,8 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         CU(cudaStreamSynchronize(m->st_d2h));
         CU(cudaStreamSynchronize(m->st));
         if (verbose)
-            fprintf(stderr, "psa: map_host %llu chunks: submit %.2f ms, waits on chunk totals %.2f ms, final drain %.2f ms\n",
-                    (unsigned long long)nchunks, 1e3 * t_submit, 1e3 * t_wait, 1e3 * (now_s() - td0));
+            fprintf(stderr, "psa: map_host %llu chunks: staging buffers %.2f ms, submit %.2f ms, waits on chunk totals %.2f ms, final drain %.2f ms\n",
+                    (unsigned long long)nchunks, 1e3 * t_alloc, 1e3 * t_submit, 1e3 * t_wait, 1e3 * (now_s() - td0));
         o->tx_used = tx_prev_total;
         if (novel_overflow || stage_overflow || spill_overflow) {
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));

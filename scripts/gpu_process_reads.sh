@@ -6,11 +6,15 @@ pkg = importlib.import_module("rust-pseudoaligner_b200")
 host = importlib.import_module("rust-pseudoaligner_b200.host")
 tr = host.Transcriptome.synth(2, 20000, threads=16)
 flat, stats = host.build_graph(tr.codes(), tr.tx_off(), 24, threads=16)
-n, L = 8_000_000, 150
+n, L = int(os.environ.get('N_READS', 8_000_000)), 150
 data = tr.reads(3, 0, n, L, threads=16)[:n * L].reshape(n, L)
 t0 = time.time()
 rec = np.empty((n, 12 + L + 3 + L + 1), np.uint8)          # "@r%09d \n" seq "\n+\n" qual "\n"
-ids = np.char.zfill(np.arange(n).astype("U9"), 9).astype("S9").view(np.uint8).reshape(n, 9)
+ids = np.empty((n, 9), np.uint8)
+v = np.arange(n, dtype=np.int64)
+for d in range(9):
+    ids[:, 8 - d] = 48 + v % 10
+    v //= 10
 rec[:, 0] = ord("@"); rec[:, 1] = ord("r"); rec[:, 2:11] = ids; rec[:, 11] = ord("\n")
 rec[:, 12:12 + L] = data; rec[:, 12 + L:12 + L + 3] = np.frombuffer(b"\n+\n", np.uint8)
 rec[:, 15 + L:15 + 2 * L] = ord("I"); rec[:, 15 + 2 * L] = ord("\n")
@@ -18,7 +22,7 @@ path = "/dev/shm/psa_synth.fq"
 rec.tofile(path)
 print("fastq: %d reads, %.2f GB, written in %.1f s" % (n, rec.nbytes / 1e9, time.time() - t0))
 pa = pkg.Pseudoaligner(flat, device=0)
-for threads in (4, 16):
+for threads in [int(x) for x in os.environ.get('PR_THREADS', '4,16').split(',')]:
     for rep in range(2):
         st = pkg.process_reads_file(path, pa, "/dev/shm/psa_out.txt", num_threads=threads)
         print("threads %2d: %.2f s  %.1f M reads/s  busy: reader %.2f mapper %.2f writer %.2f s  (reads %d, aligned %d, out %.2f GB)" % (

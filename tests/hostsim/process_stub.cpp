@@ -20,6 +20,9 @@ const char* psa_last_error(void) { return ""; }
 int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
     if (r->format != PSA_READS_ASCII || r->location != PSA_MEM_HOST || !r->read_off || !r->read_len) return PSA_ERR_ARG;
     uint64_t used = 0;
+    // PSA_STUB_NTX=n (throughput runs of scripts/host_process_bench.py only): n ids per read instead of one
+    const char* e = getenv("PSA_STUB_NTX");
+    const uint32_t ntx = e ? (uint32_t)atoi(e) : 1;
     for (uint64_t i = 0; i < r->n_reads; i++) {
         const uint8_t* s = (const uint8_t*)r->data + r->read_off[i];
         if (r->read_off[i] + r->read_len[i] > r->data_len) return PSA_ERR_ARG;
@@ -27,13 +30,13 @@ int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
         for (uint32_t j = 0; j < r->read_len[i]; j++) sum += s[j];
         psa_hit& h = o->hits[i];
         h.coverage = r->read_len[i];
-        h.n_tx = r->read_len[i] ? 1 : 0;
+        h.n_tx = r->read_len[i] ? ntx : 0;
         h.tx_off = used;
         h.eq_id = 0;
         h.flags = PSA_FLAG_ALIGNED | ((r->read_len[i] && s[0] == 'T') ? PSA_FLAG_MAPPED : 0);
-        if (h.n_tx) {
+        for (uint32_t j = 0; j < h.n_tx; j++) {
             if (used >= o->tx_cap) return PSA_ERR_CAPACITY;
-            o->tx_buf[used++] = sum;
+            o->tx_buf[used++] = sum + 1000 * j;
         }
     }
     o->tx_used = used;
