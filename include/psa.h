@@ -244,7 +244,7 @@ int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[3], uint64_t map_l
  * read out -- `(flag, "id", [tx, ...], coverage)`, the `{:?}` of the tuple the reference
  * println!s at :490 -- in input order.  out_path NULL or "-" = stdout.  num_threads = host
  * threads that format the lines (the reference's num_threads are its mapping workers; mapping
- * is on the GPU here).  batch_reads 0 = 1 Mi reads per batch.  progress != 0 prints the
+ * is on the GPU here) and read / write the files.  batch_reads 0 = 512 Ki reads per block.  progress != 0 prints the
  * reference's stderr tick every 1 000 000 reads (:497-504).  A malformed FASTQ record returns
  * PSA_ERR_IO after the records before it were processed (the reference panics, :446).
  * ---------------------------------------------------------------------------------------- */
