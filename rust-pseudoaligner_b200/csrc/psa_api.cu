@@ -807,7 +807,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -848,6 +848,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             if ((rc = m->deferred.ensure(n * 4))) return rc;
             p.list = m->deferred.as<uint32_t>();
             p.list_count = m->novel_cursor.as<unsigned long long>() + 2;
+            p.work_cursor = m->novel_cursor.as<unsigned long long>() + 5;
             p.max_probes = m->fast_probes;
             p.max_small = m->fast_max_small;
             if (m->scan_width) {
@@ -879,9 +880,15 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         if ((rc = m->scan_tmp.ensure(tb))) return rc;
         CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
     }
-    if (n)
+    if (n) {
+#if PSA_EXPAND_BALANCED
+        k_expand_balanced<<<nblocks(n, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
+                                                           ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
+#else
         k_expand<<<nblocks(n * PSA_EXPAND_LANES, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
                                                       ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
+#endif
+    }
     k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
                                 m->status.as<uint32_t>(), b.meta_out, b.sticky ? m->status.as<uint32_t>() + 1 : nullptr);
     m->launches++;

@@ -278,7 +278,10 @@ struct Bloom {
     const uint32_t* words;  // 8 per block; nullptr = no filter
     uint64_t n_blocks;
 };
-constexpr uint32_t kBloomBitsPerKey = 12;
+#ifndef PSA_BLOOM_BITS
+#define PSA_BLOOM_BITS 12
+#endif
+constexpr uint32_t kBloomBitsPerKey = PSA_BLOOM_BITS;
 
 struct DevIndex {
     uint32_t k;

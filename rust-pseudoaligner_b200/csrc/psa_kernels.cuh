@@ -14,6 +14,17 @@
 
 #include "psa_core.cuh"
 
+// build-time experiment switches (defaults = the measured best; profiles/r1_exp_*.txt)
+#ifndef PSA_MAP_DYNAMIC
+#define PSA_MAP_DYNAMIC 1   // k_map claims handed-over reads from a counter (0: strides over the list)
+#endif
+#ifndef PSA_EXPAND_BALANCED
+#define PSA_EXPAND_BALANCED 1   // k_expand_balanced (0: S lanes per read)
+#endif
+#ifndef PSA_PACK_V1
+#define PSA_PACK_V1 0       // 1: the first ASCII -> 2-bit formulation (four SIMD byte compares)
+#endif
+
 namespace psa {
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -237,8 +248,11 @@ __global__ void k_words_per_read(const uint32_t* len, uint64_t n, uint64_t* nw) 
 }
 
 // 4 ASCII bytes (first base in the low byte) -> 8 bits of 2-bit codes, first base in bits 7:6.
-// A/a 0, C/c 1, G/g 2, T/t 3, any other byte 0 -- bytewise SIMD, no table.
+// A/a 0, C/c 1, G/g 2, T/t 3, any other byte 0 -- bytewise, two 8-entry table lookups (PRMT):
+// the low three bits of A C G T (1 3 7 4) are distinct, so they select both the code and the
+// letter the byte must be (case folded) for the code to stand.
 __device__ __forceinline__ uint32_t codes4(uint32_t w) {
+#if PSA_PACK_V1  // first version: four SIMD byte compares (~33 instructions)
     uint32_t u = w & 0xDFDFDFDFu;  // fold case
     uint32_t valid = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
                      __vcmpeq4(u, 0x54545454u);
@@ -246,6 +260,17 @@ __device__ __forceinline__ uint32_t codes4(uint32_t w) {
     x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3
     x &= valid;
     return (x * 0x40100401u) >> 24;       // gather the four 2-bit fields (no carries between them)
+#else
+    uint32_t t = w & 0x07070707u;
+    t |= t >> 4;                                              // byte 0: idx0 | idx1 << 4, byte 2: idx2 | idx3 << 4
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);         // four selector nibbles (bit 3 of each is clear)
+    uint32_t x = __byte_perm(0x01000000u, 0x02000003u, sel);  // idx 1 (A) 0, 3 (C) 1, 7 (G) 2, 4 (T) 3, else 0
+    const uint32_t want = __byte_perm(0x43FF41FFu, 0x47FFFF54u, sel);  // the letter with those low bits (0xFF: none)
+    const uint32_t d = (w & 0xDFDFDFDFu) ^ want;              // byte == 0 iff the (case-folded) byte is that letter
+    const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;  // bit 7 of every non-zero byte
+    x &= ~((nz >> 7) | (nz >> 6));
+    return (x * 0x40100401u) >> 24;       // gather the four 2-bit fields (no carries between them)
+#endif
 }
 // nb (1..32) bases at s -> one DnaString word.  Reads only the aligned 32-bit words that hold
 // at least one of the nb bytes.
@@ -383,6 +408,7 @@ struct MapParams {
     // deferred reads: written by k_map_thread, consumed by k_map (list != nullptr: map list[0..*list_count))
     uint32_t* list;
     unsigned long long* list_count;
+    unsigned long long* work_cursor;  // k_map over the list: next entry to claim (zeroed per batch), or nullptr
     // reads whose FIRST seed search was too long for one thread: k_map_thread -> k_seed_scan
     uint32_t* scan_list;
     unsigned long long* scan_count;
@@ -646,7 +672,16 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
 
     const uint64_t n_todo = p.list ? (uint64_t)*p.list_count : p.reads.n;
-    for (uint64_t it = gid; it < n_todo; it += ngroups) {
+    // The handed-over reads differ widely in cost (tens to hundreds of dependent loads): groups claim them one
+    // at a time from a counter instead of striding over the list, so that no group is left with several slow ones.
+    const bool dynamic = PSA_MAP_DYNAMIC && p.list != nullptr && p.work_cursor != nullptr;
+    const Grp<G> wg;
+    auto claim = [&]() -> uint64_t {
+        unsigned long long at = 0;
+        if (wg.lane == 0) at = atomicAdd(p.work_cursor, 1ULL);
+        return wg.shfl(at, 0);
+    };
+    for (uint64_t it = dynamic ? claim() : gid; it < n_todo; it = dynamic ? claim() : it + ngroups) {
         const uint64_t r = p.list ? (uint64_t)p.list[it] : it;
         const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
@@ -811,9 +846,12 @@ struct DevNovel {
 #ifndef PSA_HIT_STREAM
 #define PSA_HIT_STREAM 0
 #endif
-constexpr int kThreadBlock = 128;
+#ifndef PSA_THREAD_BLOCK
+#define PSA_THREAD_BLOCK 64
+#endif
+constexpr int kThreadBlock = PSA_THREAD_BLOCK;
 #ifndef PSA_THREAD_MIN_BLOCKS
-#define PSA_THREAD_MIN_BLOCKS 10
+#define PSA_THREAD_MIN_BLOCKS 20
 #endif
 
 // HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
@@ -1043,6 +1081,48 @@ __global__ void k_expand(HitRec* hits, uint64_t n, const uint64_t* rel_off, cons
         for (uint32_t j = sub; j < h.n_tx; j += S) tx_buf[rel + j] = src[j];
     }
     if (sub == 0) hits[i].tx_off = running[0] + rel;
+}
+// Load-balanced form: a warp takes 32 consecutive reads, whose members are one contiguous range of tx_buf
+// (rel_off is an exclusive scan); lane t of every round writes element t of that range -- it finds the read
+// the element belongs to by a binary search over the lanes' start offsets (shuffles) and fetches the source
+// pointer from that lane.  Stores are fully coalesced and no lane idles behind a read with a long class.
+__global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
+                                                         const uint32_t* eq_mem, const uint32_t* novel, uint32_t* tx_buf,
+                                                         uint64_t tx_cap) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull;
+    if (base >= n) return;  // warp-uniform
+    const uint64_t i = base + lane;
+    const bool live = i < n;
+    uint32_t cnt = 0;
+    uint64_t rel = 0;
+    const uint32_t* src = nullptr;
+    bool fits = false;
+    if (live) {
+        const HitRec h = hits[i];
+        rel = rel_off[i];
+        cnt = h.n_tx;
+        fits = tx_buf != nullptr && rel + cnt <= tx_cap;
+        src = (h.eq_id != kNone ? eq_mem : novel) + h.tx_off;
+        hits[i].tx_off = running[0] + rel;
+    }
+    const uint64_t rel0 = __shfl_sync(kFull, rel, 0);
+    const uint32_t start = live ? (uint32_t)(rel - rel0) : 0xFFFFFFFFu;  // ascending over the lanes; dead lanes last
+    const uint32_t total = __reduce_max_sync(kFull, live ? start + cnt : 0u);
+    const unsigned fitmask = __ballot_sync(kFull, fits);
+    if (!fitmask) return;
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        uint32_t q = 0;  // last lane whose range starts at or before element t (empty ranges are passed over)
+#pragma unroll
+        for (int s = 16; s; s >>= 1) {
+            const uint32_t sv = __shfl_sync(kFull, start, (q + s) & 31);
+            if (sv <= t) q += s;
+        }
+        const uint64_t sp = __shfl_sync(kFull, (uint64_t)(uintptr_t)src, q);
+        const uint32_t ss = __shfl_sync(kFull, start, q);
+        if (t < total && ((fitmask >> q) & 1u)) tx_buf[rel0 + t] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)sp) + (t - ss));
+    }
 }
 // after k_expand: advance the running total, publish {running, status} for the host.  sticky (may be
 // nullptr): the OR of the status words of every batch since the host last cleared it -- several batches may

@@ -435,3 +435,33 @@ def test_two_mappers_share_one_index_concurrently(orc_index_for, fixture_fasta):
             _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
         assert np.array_equal(counts, 3 * want_counts)
     index.close()
+
+
+def test_pack_every_byte_value(pa_for, orc_index_for, fixture_fasta):
+    """DnaString::from_dna_string (ref src/pseudoaligner.rs:449-450): A/a C/c G/g T/t -> 0..3, EVERY other byte -> 0.
+    Reads with bytes of the whole 0..255 range, through the three pack kernels (ragged, fixed stride, tile)."""
+    ix, pa = orc_index_for(20), pa_for(20)
+    rng = np.random.default_rng(77)
+    length = 150
+    base = util.sample_reads(rng, fixture_fasta[1], 1024, length, p_sub=0.0, mix=(1.0, 0.0, 0.0))
+    reads = []
+    for i, r in enumerate(base):
+        b = bytearray(r.encode() if isinstance(r, str) else r)
+        for j in range(6):                       # every byte value appears 24 times over the set
+            b[int(rng.integers(0, length))] = (6 * i + j) % 256
+        if i % 3 == 0:                           # and mixed case
+            p = int(rng.integers(0, length - 20))
+            b[p:p + 20] = bytes(b[p:p + 20]).lower()
+        reads.append(bytes(b))
+    want_hits, want_tx, _, _ = _oracle(ix, reads)
+    got_hits, got_tx = pa.mapper.map_ascii(reads)                                   # ragged: k_pack_ascii
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    flat = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    tile = np.concatenate([flat, np.zeros(64, np.uint8)])                             # 128 x 150 bytes: tile kernel
+    got_hits, got_tx = pa.mapper.map_ascii_fixed(tile, len(reads), length)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    stride = length + 3                                                              # odd stride: k_pack_ascii_fixed
+    padded = np.zeros(len(reads) * stride + 64, np.uint8)
+    padded[:len(reads) * stride].reshape(len(reads), stride)[:, :length] = flat.reshape(len(reads), length)
+    got_hits, got_tx = pa.mapper.map_ascii_fixed(padded, len(reads), length, stride=stride)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
