@@ -123,6 +123,20 @@ __device__ __forceinline__ void ld_v4_last(const void* a, uint64_t& x, uint64_t&
 }
 #endif
 
+#ifndef PSA_PF_SUCC
+#define PSA_PF_SUCC 0   // thread-per-read walk: prefetch the successor's node record before the compare
+#endif
+#ifndef PSA_PF_SPAN
+#define PSA_PF_SPAN 0   // thread-per-read walk: prefetch the last sector of the unitig span before the compare
+#endif
+PSA_HD void prefetch_l2(const void* a) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#else
+    (void)a;
+#endif
+}
+
 struct GLoad {  // immutable index memory (global, ld.global.nc): the unitig sequence
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const {
@@ -543,6 +557,16 @@ PSA_HD NodeView load_node_view(const NodeRec* r) {
 }
 PSA_HD uint32_t view_succ(const NodeView& v, uint32_t b) { return b == 0 ? v.succ[0] : b == 1 ? v.succ[1] : b == 2 ? v.succ[2] : v.succ[3]; }
 
+// Optional policy hook: w.prefetch_succ(nv, pos) -- the forward walk is about to compare the rest of unitig nv
+// and, if every base matches, will continue with the successor selected by read base `pos`.  Policies without
+// the member get the no-op.
+template <class W, class P>
+PSA_HD auto hint_succ(W& w, const NodeView& nv, P pos, int) -> decltype(w.prefetch_succ(nv, pos), void()) {
+    w.prefetch_succ(nv, pos);
+}
+template <class W, class P>
+PSA_HD void hint_succ(W&, const NodeView&, P, long) {}
+
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
 #endif
@@ -609,6 +633,7 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, P read_length, uint32_t allowed_mis
             P ref_offset = kmer_offset + kmer_length;                    // :227
             P informative_ref = ref_length - ref_offset;                 // :228
             P max_matchable_pos = remaining_read < informative_ref ? remaining_read : informative_ref;  // :231
+            if (remaining_read > informative_ref) hint_succ(w, nv, (P)(kmer_pos + informative_ref), 0);
             bool premature_break = false;                                       // :233
             P matched_bases =                                            // :234-255
                 w.cmp_fwd(kmer_pos, nv.start + ref_offset, max_matchable_pos, allowed_mismatches,
@@ -909,6 +934,14 @@ struct ThreadCtx {
         }
     }
     PSA_HD NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
+#if PSA_PF_SUCC
+    // the node record the walk needs next if the rest of this unitig matches: fetched under the compare
+    template <class P>
+    PSA_HD void prefetch_succ(const NodeView& nv, P pos) {
+        const uint32_t s = view_succ(nv, read_base(pos));
+        if (s != kNone) prefetch_l2(ix.nodes + s);
+    }
+#endif
     PSA_HD void jumped() {
         if (EV) ev.jumps++;
     }
@@ -925,6 +958,12 @@ struct ThreadCtx {
     template <bool FWD, class P>
     PSA_HD P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
+#if PSA_PF_SPAN
+        if (m > 32) {  // the far end of the unitig span, if it lies in another 32-byte sector (128 bases)
+            const uint64_t far = FWD ? sp + m - 1 : sp - (m - 1);
+            if ((far >> 7) != (sp >> 7)) prefetch_l2(ix.seq + (far >> 5));
+        }
+#endif
         for (P my = 0; my < m; my += 32) {
             uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
             uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
