@@ -69,30 +69,27 @@ struct Batch {
 // raw byte source: regular files through pread(2) (any number of threads at once), everything else
 // (pipes, gzip) through a serial stream
 struct ByteSource {
-    gzFile gz = nullptr;
-    FILE* fp = nullptr;
+    gzFile gz = nullptr;    // gzip files, and every stream that is not a regular file (zlib passes plain text through)
     int fd = -1;            // regular plain file: positional reads
     uint64_t size = 0, pos = 0;
     bool open(const char* path) {
-        fp = fopen(path, "rb");
-        if (!fp) return false;
+        const int f = ::open(path, O_RDONLY | O_CLOEXEC);
+        if (f < 0) return false;
+        struct stat st;
+        bool regular = fstat(f, &st) == 0 && S_ISREG(st.st_mode);
         unsigned char magic[2] = {0, 0};
-        size_t got = fread(magic, 1, 2, fp);
-        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            fclose(fp);
-            fp = nullptr;
-            gz = gzopen(path, "rb");
-            if (!gz) return false;
-            gzbuffer(gz, 1 << 20);
-        } else {
-            rewind(fp);
-            setvbuf(fp, nullptr, _IONBF, 0);
-            struct stat st;
-            if (fstat(fileno(fp), &st) == 0 && S_ISREG(st.st_mode)) {
-                fd = fileno(fp);
-                size = (uint64_t)st.st_size;
-            }
+        const bool gzip = regular && pread(f, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (regular && !gzip) {
+            fd = f;
+            size = (uint64_t)st.st_size;
+            return true;
         }
+        gz = gzdopen(f, "rb");  // owns f from here on
+        if (!gz) {
+            ::close(f);
+            return false;
+        }
+        gzbuffer(gz, 1 << 20);
         return true;
     }
     bool parallel() const { return fd >= 0; }
@@ -106,27 +103,20 @@ struct ByteSource {
         }
         return total;
     }
-    // fills up to n bytes; returns bytes read (0 at end of file)
+    // serial stream: fills up to n bytes; returns bytes read (0 at end of file)
     size_t read(uint8_t* dst, size_t n) {
         size_t total = 0;
-        while (total < n) {
-            size_t got;
-            if (gz) {
-                int g = gzread(gz, dst + total, (unsigned)std::min<size_t>(n - total, 1u << 30));
-                got = g > 0 ? (size_t)g : 0;
-            } else {
-                got = fread(dst + total, 1, n - total, fp);
-            }
-            if (!got) break;
-            total += got;
+        while (total < n && gz) {
+            int g = gzread(gz, dst + total, (unsigned)std::min<size_t>(n - total, 1u << 30));
+            if (g <= 0) break;
+            total += (size_t)g;
         }
         return total;
     }
     void close() {
         if (gz) gzclose(gz);
-        if (fp) fclose(fp);
+        if (fd >= 0) ::close(fd);
         gz = nullptr;
-        fp = nullptr;
         fd = -1;
     }
 };

@@ -108,3 +108,66 @@ def test_malformed_files_are_errors_after_the_good_records(stub, tmp_path):
         assert lines == _expected(recs), name                 # every complete record before the bad one
     rc, _, _ = _run(stub, tmp_path / "missing.fq", tmp_path / "out.txt")
     assert rc == -7
+
+
+def test_streams_pipes_and_append_mode(stub, tmp_path):
+    """Regular files are read with pread and written with pwrite by every thread; everything else (FIFOs,
+    append-mode descriptors) takes the serial ordered paths.  Same lines either way."""
+    import threading
+    rng = np.random.default_rng(5)
+    recs = _records(rng, 1200)
+    want = _expected(recs)
+    text = _fastq(recs)
+    # input through a FIFO: not seekable, read serially
+    fifo_in = tmp_path / "in.fifo"
+    os.mkfifo(fifo_in)
+    feeder = threading.Thread(target=lambda: open(fifo_in, "wb").write(text))
+    feeder.start()
+    rc, st, lines = _run(stub, fifo_in, tmp_path / "o1", 3, 100)
+    feeder.join()
+    assert rc == 0 and lines == want
+    # output through a FIFO: ordered serial writes
+    p = tmp_path / "a.fq"
+    p.write_bytes(text)
+    fifo_out = tmp_path / "out.fifo"
+    os.mkfifo(fifo_out)
+    got = []
+    drain = threading.Thread(target=lambda: got.append(open(fifo_out, "rb").read()))
+    drain.start()
+    st = _Stats()
+    rc = stub.psa_process_reads(C.c_void_p(1), str(p).encode(), str(fifo_out).encode(), 4, 64, 0, C.byref(st))
+    drain.join()
+    assert rc == 0 and got[0].decode().splitlines() == want
+    # more threads than records, one record per block
+    rc, st, lines = _run(stub, p, tmp_path / "o3", 16, 1)
+    assert rc == 0 and lines == want
+
+
+def test_stdout_redirected_to_a_file_keeps_its_position(stub, tmp_path):
+    """out_path NULL/"-" = stdout: when it is a regular file the lines go after what is already there, and what
+    the process prints afterwards follows them (append mode falls back to ordered serial writes)."""
+    import sys
+    rng = np.random.default_rng(6)
+    recs = _records(rng, 500)
+    p = tmp_path / "a.fq"
+    p.write_bytes(_fastq(recs))
+    code = (
+        "import ctypes as C, os, sys\n"
+        "L = C.CDLL(%r)\n"
+        "L.psa_process_reads.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]\n"
+        "os.write(1, b'before\\n')\n"
+        "rc = L.psa_process_reads(C.c_void_p(1), %r, b'-', 3, 70, 0, None)\n"
+        "os.write(1, b'after %%d\\n' %% rc)\n" % (os.path.join(_DIR, "libprocess_stub.so"), str(p).encode()))
+    for mode in ("wb", "ab"):
+        out = tmp_path / ("stdout_" + mode)
+        with open(out, mode) as f:
+            subprocess.check_call([sys.executable, "-c", code], stdout=f)
+        assert open(out).read().splitlines() == ["before"] + _expected(recs) + ["after 0"], mode
+
+
+def test_control_characters_in_ids(stub, tmp_path):
+    """Rust's {:?} of the id: \\u{..} for control characters, \\\\ and \\" escaped (ref src/pseudoaligner.rs:490)."""
+    p = tmp_path / "c.fq"
+    p.write_bytes(b"@a\x01b\x7f\\\"z\nTACG\n+\nIIII\n")
+    rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 0)
+    assert rc == 0 and lines == ['(true, "a\\u{1}b\\u{7f}\\\\\\"z", [%d], 4)' % sum(b"TACG")]
