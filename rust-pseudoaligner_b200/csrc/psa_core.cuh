@@ -151,6 +151,19 @@ struct PLoad {  // plain pointer (shared memory tile or global read buffer)
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const { return p[i]; }
 };
+#ifndef PSA_READS_EVICT_LAST
+#define PSA_READS_EVICT_LAST 0   // experiment: the reads' packed words keep L2 priority while their read is in flight
+#endif
+struct RLoad {  // the packed words of the reads (global): touched ~10 times over a read's life
+    const uint64_t* p;
+    PSA_HD uint64_t operator()(uint64_t i) const {
+#if defined(__CUDA_ARCH__) && PSA_READS_EVICT_LAST && PSA_L2_HINTS
+        return ld_u64_last(p + i);
+#else
+        return p[i];
+#endif
+    }
+};
 struct RegLoad6 {  // a read of at most 192 bases held in registers (selected, never indexed)
     uint64_t w0, w1, w2, w3, w4, w5;
     PSA_HD uint64_t operator()(uint64_t i) const { return i == 0 ? w0 : i == 1 ? w1 : i == 2 ? w2 : i == 3 ? w3 : i == 4 ? w4 : w5; }

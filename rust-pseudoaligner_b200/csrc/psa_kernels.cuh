@@ -856,10 +856,12 @@ constexpr int kThreadBlock = PSA_THREAD_BLOCK;
 
 // HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
 // first seed search was made by k_seed_scan), persistent warps striding over that list.
-// TILE (first pass, fixed word stride): the packed words of the CTA's 128 reads arrive in shared
-// memory as one bulk asynchronous copy (cp.async.bulk + mbarrier: TMA) and every thread maps its
+// TILE (first pass, fixed word stride; the default): the packed words of the CTA's 64 reads arrive in
+// shared memory as one bulk asynchronous copy (cp.async.bulk + mbarrier: TMA) and every thread maps its
 // read from there -- the read's words are touched ~10 times along the path, and through L1 they
-// kept being evicted by the index gathers.  (Fusing the ASCII packing in as well was measured:
+// kept being evicted by the index gathers (12.9 L2 sectors per read for 40 bytes of read).  Measured:
+// 2.4 % faster than reading through L1 with 64-thread CTAs (2.5 KB of shared memory per CTA), 2 % slower
+// with 128-thread CTAs.  (Fusing the ASCII packing in as well was measured:
 // the 19 KB ASCII tile per CTA shrinks L1 so much that the kernel loses 1 ms.)
 // (Holding a <= 192-base read in six registers instead of re-reading its words through L1 was
 // measured: 3.93 ms vs 3.48 ms -- the extra registers spill at the 64-register cap.  Not used.)
@@ -915,9 +917,12 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
             const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
             L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
             DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
-            ThreadResult res = map_read_thread<KW, EV>(ix, PLoad{TILE ? my_words : p.reads.words + wo}, L, p.allowed_mismatches, p.max_probes,
-                                                       p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
-                                                       HINT ? hint : nullptr);
+            ThreadResult res = TILE ? map_read_thread<KW, EV>(ix, PLoad{my_words}, L, p.allowed_mismatches, p.max_probes,
+                                                              p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              HINT ? hint : nullptr)
+                                    : map_read_thread<KW, EV>(ix, RLoad{p.reads.words + wo}, L, p.allowed_mismatches, p.max_probes,
+                                                              p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              HINT ? hint : nullptr);
             defer = res.deferred;
             why = res.why;
             if (EV && defer && p.events) atomicAdd(p.events + 36 + res.why, 1ULL);

@@ -349,15 +349,16 @@ def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
     assert out.read_text().splitlines() == want[:n_good]      # the records before the bad one were processed
 
 
-def test_tma_read_tiles(orc_index_for, fixture_fasta, monkeypatch):
-    """PSA_TILE=1: the thread-per-read kernel stages the packed reads of a fixed-stride batch in shared
-    memory with one bulk asynchronous copy per CTA (an option, off by default: measured slower).
-    Same results, including a batch whose last tile is partial and odd-sized."""
-    monkeypatch.setenv("PSA_TILE", "1")
+@pytest.mark.parametrize("tile", ["1", "0"])
+def test_tma_read_tiles(orc_index_for, fixture_fasta, monkeypatch, tile):
+    """PSA_TILE=1 (the default): the thread-per-read kernel stages the packed reads of a fixed-stride batch in
+    shared memory with one bulk asynchronous copy (TMA) per CTA; PSA_TILE=0 reads them through L1.
+    Same results, including batches whose last tile is partial and odd-sized."""
+    monkeypatch.setenv("PSA_TILE", tile)
     ix = orc_index_for(20)
     pa = pkg.Pseudoaligner(ix.flat(), device=0)
     rng = np.random.default_rng(21)
-    for L, n in ((150, 128 * 37 + 61), (91, 1000), (60, 127), (33, 3)):
+    for L, n in ((150, 128 * 37 + 61), (91, 1000), (60, 127), (33, 3), (150, 64 * 5 + 1)):
         reads = util.sample_reads(rng, fixture_fasta[1], n, L, p_sub=0.01, mix=(0.85, 0.1, 0.05))
         data = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
         want_hits, want_tx, _, _ = _oracle(ix, reads)
