@@ -465,6 +465,7 @@ struct WarpCtx {
     unsigned long long* pool_cursor;
     uint32_t read_len;
     bool scan_mode;
+    uint32_t scan_skip = 0;  // scan mode: first position not yet known to be absent
     LaneEvents ev;
 
     __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint32_t read_len_,
@@ -492,6 +493,8 @@ struct WarpCtx {
             if (EV && lane == 0) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
             if (hit) return true;
             first = start + kSeedStride;
+        } else {
+            first = start + (P)scan_skip;  // positions the thread-per-read kernel has already found absent
         }
         for (P cur = first; cur <= last; cur += G * kSeedStride) {
             P p = cur + (P)kSeedStride * lane;
@@ -998,6 +1001,10 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;  // >= k: shorter reads never search
         WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
         w.scan_mode = true;
+        // a read is on this list because its own thread probed positions 0, 3, ..., 3 (max_probes - 1) and missed
+        // them all: start behind them (when counting events the whole search is redone: the counters are
+        // sequential-equivalent and the thread kernel did not count a search it gave up)
+        w.scan_skip = EV ? 0u : kSeedStride * p.max_probes;
         uint32_t kmer_pos = 0;
         uint32_t node = 0, off = 0;
         const bool found = w.find_seed(kmer_pos, L - ix.k, node, off);

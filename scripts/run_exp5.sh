@@ -1,4 +1,4 @@
+timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
 export EXP4="X=0|
-PSA_TILE=1|
-PSA_LIB_PATH=$PWD/build/exp/libpsa_rlast.so|"
+X=1|"
 bash scripts/gpu_exp4.sh
