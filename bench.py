@@ -203,6 +203,22 @@ def algorithmic_bytes(ev, k, hit_bytes=24):
     return b
 
 
+def sector_bytes(ev, k, hit_bytes=24):
+    """S_read of SURVEY 8(d): 32 bytes x the distinct sectors the same sequential-equivalent events touch in
+    THIS index layout (one sector per MPHF level, per `values` entry, per node record, per class window; an
+    unaligned span of s bases of 2-bit sequence covers s/128 + 1 sectors on average).  A model, reported next
+    to the DRAM bytes ncu measured (`traffic`); like `algorithmic_bytes` it ignores speculative probes and caches."""
+    sect = 0.0
+    sect += ev["reads"] * (ev["read_bases"] / ev["reads"] / 128.0 + 1.0)      # packed read
+    sect += ev["mphf_levels"]                                              # 32-byte block: bits + rank
+    sect += ev["mphf_hits"]                                                # values entry
+    sect += ev["verifications"] * (1.0 + k / 128.0 + 1.0)                  # node record + unitig k-mer
+    sect += ev["node_visits"] * 2.0                                        # node record sector 0 + class window
+    sect += ev["bases_compared"] / 128.0 + ev["node_visits"]               # unitig spans of the compares
+    sect += ev["reads"] * (hit_bytes / 32.0 + 1.0) + ev["out_members"] / 8.0   # psa_hit, counts[] entry, members
+    return 32.0 * sect
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads):
     """Times the oracle (oracle/psa_oracle.c, the C restatement of the reference's map_read) on
@@ -547,6 +563,7 @@ def main():
                 "kernel": dom, "kernel_ms_per_launch": kernels[dom]["ms_per_launch"],
                 "kernel_share_of_step": kernels[dom]["share_of_step"], "kernels": kernels,
                 "algorithmic_bytes_per_read": a_bytes_per_read,
+                "sector_model_bytes_per_read": sector_bytes(ev, a.k) / ev["reads"],
                 "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_launch"] for v in kernels.values()) / 1e3) / 1e9,
                 "peak_source": peak_src, "handed_over_by_k_map_thread": deferred_by,
                 "kernel_timing": ("CUDA events around every map kernel, inside the timed region" if M == 1 else
