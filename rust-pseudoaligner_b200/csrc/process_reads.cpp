@@ -266,24 +266,20 @@ char* debug_str(char* o, const char* s, size_t n) {
 
 const char kDigits2[201] =
     "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
-// decimal of a 32-bit value, two digits per division
+// decimal of a 32-bit value: digit count first, then two digits per division written in place
 inline char* put_u32(char* o, uint32_t v) {
-    char t[10];
-    int i = 10;
+    const int len = v < 10 ? 1 : v < 100 ? 2 : v < 1000 ? 3 : v < 10000 ? 4 : v < 100000 ? 5 : v < 1000000 ? 6
+                    : v < 10000000 ? 7 : v < 100000000 ? 8 : v < 1000000000 ? 9 : 10;
+    char* e = o + len;
     while (v >= 100) {
         const uint32_t q = v / 100, r = v - q * 100;
-        t[--i] = kDigits2[2 * r + 1];
-        t[--i] = kDigits2[2 * r];
+        e -= 2;
+        memcpy(e, kDigits2 + 2 * r, 2);
         v = q;
     }
-    if (v >= 10) {
-        t[--i] = kDigits2[2 * v + 1];
-        t[--i] = kDigits2[2 * v];
-    } else {
-        t[--i] = (char)('0' + v);
-    }
-    memcpy(o, t + i, (size_t)(10 - i));
-    return o + (10 - i);
+    if (v >= 10) memcpy(o, kDigits2 + 2 * v, 2);
+    else *o = (char)('0' + v);
+    return o + len;
 }
 
 // `(flag, "id", [tx, ...], coverage)` -- the tuple printed at ref src/pseudoaligner.rs:490
@@ -294,6 +290,7 @@ void format_range(const Batch& b, uint64_t r0, uint64_t r1, OutBuf& out, uint64_
     out.ok = true;
     for (uint64_t i = r0; i < r1; i++) {
         const psa_hit& h = hits[i];
+        if (i + 8 < r1) __builtin_prefetch(b.text.p + b.id_off[i + 8]);  // ids sit 300+ bytes apart in the FASTQ text
         // worst case of this record: flag 8, id 6 per byte + 2, 12 per member ("4294967295, "), brackets/coverage/newline 32
         out.reserve_more(8 + 6 * (size_t)b.id_len[i] + 2 + 12 * (size_t)h.n_tx + 32);
         if (!out.ok) return;

@@ -23,6 +23,7 @@ int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
     // PSA_STUB_NTX=n (throughput runs of scripts/host_process_bench.py only): n ids per read instead of one
     const char* e = getenv("PSA_STUB_NTX");
     const uint32_t ntx = e ? (uint32_t)atoi(e) : 1;
+    const bool spread = getenv("PSA_STUB_SPREAD") != nullptr;
     for (uint64_t i = 0; i < r->n_reads; i++) {
         const uint8_t* s = (const uint8_t*)r->data + r->read_off[i];
         if (r->read_off[i] + r->read_len[i] > r->data_len) return PSA_ERR_ARG;
@@ -36,7 +37,8 @@ int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
         h.flags = PSA_FLAG_ALIGNED | ((r->read_len[i] && s[0] == 'T') ? PSA_FLAG_MAPPED : 0);
         for (uint32_t j = 0; j < h.n_tx; j++) {
             if (used >= o->tx_cap) return PSA_ERR_CAPACITY;
-            o->tx_buf[used++] = sum + 1000 * j;
+            // PSA_STUB_SPREAD=1: ids of every decimal length (the formatter's digit paths)
+            o->tx_buf[used++] = spread ? (uint32_t)(((uint64_t)(sum + j) * 2654435761u) >> (j % 30)) : sum + 1000 * j;
         }
     }
     o->tx_used = used;

@@ -171,3 +171,24 @@ def test_control_characters_in_ids(stub, tmp_path):
     p.write_bytes(b"@a\x01b\x7f\\\"z\nTACG\n+\nIIII\n")
     rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 0)
     assert rc == 0 and lines == ['(true, "a\\u{1}b\\u{7f}\\\\\\"z", [%d], 4)' % sum(b"TACG")]
+
+
+def test_numbers_of_every_decimal_length(stub, tmp_path, monkeypatch):
+    """Transcript ids from one to ten digits (the formatter writes two digits per division into a
+    pre-counted field)."""
+    monkeypatch.setenv("PSA_STUB_NTX", "31")
+    monkeypatch.setenv("PSA_STUB_SPREAD", "1")
+    rng = np.random.default_rng(8)
+    recs = _records(rng, 400, lmin=1, lmax=120)
+    p = tmp_path / "n.fq"
+    p.write_bytes(_fastq(recs))
+    rc, st, lines = _run(stub, p, tmp_path / "out.txt", 3, 50)
+    assert rc == 0
+    want, lens = [], set()
+    for rid, seq in recs:
+        ids = [((sum(seq) + j) * 2654435761 & 0xFFFFFFFFFFFFFFFF) >> (j % 30) & 0xFFFFFFFF for j in range(31)]
+        lens.update(len(str(x)) for x in ids)
+        want.append('(%s, "%s", [%s], %d)' % ("true" if seq[:1] == b"T" else "false", rid.decode(),
+                                             ", ".join(str(x) for x in ids), len(seq)))
+    assert lines == want
+    assert lens >= set(range(3, 11))
