@@ -577,6 +577,9 @@ def main():
         v, ci = cpu_arm(a, tr, flat, 3, 1, a.cpu_seconds, threads)
         cpu = {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": ci["sample"],
                "note": "oracle/psa_oracle.c, the C restatement of the reference's map_read (Rust toolchain absent)"}
+        if threads > 1:     # the same port on ONE host thread, next to the all-threads figure
+            v1, ci1 = cpu_arm(a, tr, flat, 1, 0, min(a.cpu_seconds, 3.0), 1)
+            cpu["one_thread"] = {"value": v1, "unit": "reads/s", "sample": ci1["sample"]}
 
     if rank == 0:
         line = {
