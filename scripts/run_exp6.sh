@@ -1,3 +1,5 @@
+# A/B harness of one experiment batch (results: profiles/r1_exp_overlap_knobs.txt).  The libpsa_*.so variants under build/exp/
+# are built first with: make -C rust-pseudoaligner_b200/csrc OUT=../../build/exp/libpsa_<name>.so NVFLAGS="<flags> -D<switch>=<value>" ../../build/exp/libpsa_<name>.so
 # end-to-end arm: host threads (one mapper each) and pipeline chunk size
 mkdir -p gpurun_out; : > gpurun_out/exp6.txt
 for cfg in "2 0" "3 0" "4 0" "2 1048576" "3 262144"; do
