@@ -874,6 +874,35 @@ struct ThreadEvents {
     uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
 };
 
+#ifndef PSA_CMP_CARRY
+#define PSA_CMP_CARRY 0
+#endif
+// Sequential 32-base chunks of a 2-bit sequence, each word loaded once (see ThreadCtx::cmp).  next(n, more)
+// returns the n (1..32) bases at the current position right-aligned, exactly as seq_bits does, and moves on
+// by 32 bases; `more` says whether another chunk follows (only then may the following word be touched).
+template <class L>
+struct CarryStream {
+    uint64_t wi, cur;
+    uint32_t in_word;
+    PSA_HD void start(L ld, uint64_t pos) {
+        wi = pos >> 5;
+        in_word = (uint32_t)(pos & 31);
+        cur = ld(wi);
+    }
+    PSA_HD uint64_t next(L ld, uint32_t n, bool more) {
+        uint64_t v = cur << (2 * in_word);
+        if (n > 32 - in_word) {          // the chunk runs into the next word: that word starts the next chunk
+            const uint64_t nx = ld(wi + 1);
+            v |= nx >> (64 - 2 * in_word);
+            cur = nx;
+        } else if (more) {               // (in_word == 0 and a full chunk: the next chunk is the next word)
+            cur = ld(wi + 1);
+        }
+        wi++;
+        return v >> (64 - 2 * n);
+    }
+};
+
 template <int KW, bool EV, class RD = PLoad>
 struct ThreadCtx {
     const DevIndex& ix;
@@ -977,10 +1006,33 @@ struct ThreadCtx {
             if ((far >> 7) != (sp >> 7)) prefetch_l2(ix.seq + (far >> 5));
         }
 #endif
+#if PSA_CMP_CARRY
+        // forward compare with every word of the read and of the unitig loaded ONCE: consecutive 32-base chunks
+        // start one word apart at a constant in-word offset, so a chunk's second word is the next chunk's first.
+        // (Experiment switch, off: hostsim-verified, not yet measured on the GPU.)
+        CarryStream<RD> rs;
+        CarryStream<GLoad> ss;
+        if (FWD && m > 0) {
+            rs.start(rd, rp);
+            ss.start(GLoad{ix.seq}, sp);
+        }
+#endif
         for (P my = 0; my < m; my += 32) {
             uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
+#if PSA_CMP_CARRY
+            uint64_t mask;
+            if (FWD) {
+                const bool more = my + 32 < m;
+                uint64_t x = rs.next(rd, n, more) ^ ss.next(GLoad{ix.seq}, n, more);  // base t at bits 2(n-1-t)
+                x = rev_pairs(x) >> (64 - 2 * n);
+                mask = fold_pairs(x);
+            } else {
+                mask = mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
+            }
+#else
             uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
                                 : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
+#endif
             uint32_t c = (uint32_t)popc64(mask);
             if (snp + c > A) {
                 premature = true;

@@ -20,10 +20,12 @@ import util
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 
 
-@pytest.fixture(scope="module")
-def hs():
-    subprocess.check_call(["make", "-C", _DIR, "libhostsim.so"], stdout=subprocess.DEVNULL)
-    L = C.CDLL(os.path.join(_DIR, "libhostsim.so"))
+# the default build, and the build with the experiment switches of psa_core.cuh that change host-visible
+# arithmetic turned on (PSA_CMP_CARRY: every word of the forward compare loaded once)
+@pytest.fixture(scope="module", params=["libhostsim.so", "libhostsim_carry.so"])
+def hs(request):
+    subprocess.check_call(["make", "-C", _DIR, request.param], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(_DIR, request.param))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.hs_index_create.restype = vp
     L.hs_index_create.argtypes = [u32, u64, vp, u64, vp, vp, vp, vp, u64, vp, vp, C.c_double]
