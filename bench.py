@@ -57,12 +57,34 @@ def parse_args():
     ap.add_argument("--value-mappers", type=int, default=1, help="mappers (one stream each, shared index) the kernel-resident arm alternates its steps over")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one mapper each) of the end-to-end arm")
     ap.add_argument("--chunk-reads", type=int, default=0, help="reads per pipeline chunk of host batches (0 = library default)")
+    ap.add_argument("--parity-reads", type=int, default=-1, help="reads of the first batch compared with the oracle, untimed (-1: the CPU baseline's sample at 1 GPU, 200k otherwise; 0: off)")
+    ap.add_argument("--verify-reads", type=int, default=1 << 20, help="N > 1: reads per rank of the sharded-vs-single-GPU count check")
     ap.add_argument("--cache-dir", default="/dev/shm")
     ap.add_argument("--host-threads", type=int, default=0)
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------ workload
+def workload_config(a):
+    """The workload's definition: the SAME dict in the product arm and in the reference arm (run-specific
+    facts -- host cores, build times, the CPU arm's bounded sample -- live under other keys)."""
+    return {"workload": workload_name(a), "reads_per_step_per_gpu": a.reads_per_step, "read_len": a.read_len, "k": a.k,
+            "genes": a.genes if a.workload == "gencode_synth" else None,
+            "read_stream": "seed 3: 90 % transcript reads with 0.5 % substitutions, 5 % chimeric, 5 % random",
+            "input": "ASCII reads; each step packs, maps, scans and expands one batch"}
+
+
+def kernel_source_sha16():
+    """Identity of the kernels a measurement belongs to (the GPU box has no .git): sha256 of the CUDA sources."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, PKG, "csrc")
+    for name in ("psa_core.cuh", "psa_lanes.cuh", "psa_kernels.cuh", "psa_api.cu"):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def workload_name(a):
     if a.workload == "gencode_small":
         return "config2: synthetic %d bp reads vs test/gencode_small.fa index, k=%d" % (a.read_len, a.k)
@@ -192,8 +214,8 @@ def algorithmic_bytes(ev, k, hit_bytes=24):
     kb = (2 * k + 7) // 8
     b = 0.0
     b += ev["read_bases"] / 4.0                       # packed read, 2 bit/base
-    b += 8.0 * ev["mphf_levels"]                      # one bit-vector word per level probed
-    b += 16.0 * ev["mphf_hits"]                       # rank header + values entry
+    b += 32.0 * ev["dict_levels"]                     # one dictionary bucket per level probed: four 64-bit entries,
+                                                      # each compared with the key's fingerprint (the value is inline)
     b += (8.0 + kb) * ev["verifications"]             # node start + unitig k-mer
     b += 24.0 * ev["node_visits"]                     # start, len, eq, class_len, exts
     b += 0.25 * ev["bases_compared"]                  # unitig side of the compares
@@ -205,79 +227,138 @@ def algorithmic_bytes(ev, k, hit_bytes=24):
 
 def sector_bytes(ev, k, hit_bytes=24):
     """S_read of SURVEY 8(d): 32 bytes x the distinct sectors the same sequential-equivalent events touch in
-    THIS index layout (one sector per MPHF level, per `values` entry, per node record, per class window; an
+    THIS index layout (one sector per dictionary bucket probed, two per node record -- node + class window; an
     unaligned span of s bases of 2-bit sequence covers s/128 + 1 sectors on average).  A model, reported next
     to the DRAM bytes ncu measured (`traffic`); like `algorithmic_bytes` it ignores speculative probes and caches."""
     sect = 0.0
     sect += ev["reads"] * (ev["read_bases"] / ev["reads"] / 128.0 + 1.0)      # packed read
-    sect += ev["mphf_levels"]                                              # 32-byte block: bits + rank
-    sect += ev["mphf_hits"]                                                # values entry
-    sect += ev["verifications"] * (1.0 + k / 128.0 + 1.0)                  # node record + unitig k-mer
-    sect += ev["node_visits"] * 2.0                                        # node record sector 0 + class window
+    sect += ev["dict_levels"]                                              # one bucket per level probed
+    sect += ev["verifications"] * (2.0 + k / 128.0 + 1.0)                  # node record (two sectors) + unitig k-mer
+    sect += ev["node_visits"] * 2.0                                        # node record: the node + its class window
     sect += ev["bases_compared"] / 128.0 + ev["node_visits"]               # unitig spans of the compares
     sect += ev["reads"] * (hit_bytes / 32.0 + 1.0) + ev["out_members"] / 8.0   # psa_hit, counts[] entry, members
     return 32.0 * sect
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads):
+def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads, keep=False):
     """Times the oracle (oracle/psa_oracle.c, the C restatement of the reference's map_read) on
-    `threads` host threads over bounded samples of the workload.  Returns (reads/s, info)."""
+    `threads` host threads over bounded samples of the workload: every thread runs the reference's
+    worker body (ASCII -> DnaString, then map_read; ref src/pseudoaligner.rs:449-451) over its
+    share of the sample.  Returns (reads/s, info); keep=True also returns the sample's results."""
     import orc
     t0 = time.time()
     ox = orc.OrcIndex.from_flat(flat)
     index_s = time.time() - t0
     L = a.read_len
-    nw = (L + 31) // 32
 
-    shifts = (62 - 2 * np.arange(32, dtype=np.uint64)).astype(np.uint64)
-    lut = np.zeros(256, np.uint64)
-    for ch, v in ((b"C", 1), (b"G", 2), (b"T", 3), (b"c", 1), (b"g", 2), (b"t", 3)):
-        lut[ch[0]] = v
-
-    def make_sample(first, n):
-        data = tr.reads(3, first, n, L, threads=threads)
-        words = np.zeros(n * nw + 1, np.uint64)
-        for c0 in range(0, n, 65536):           # ASCII -> DnaString words, untimed
-            c1 = min(n, c0 + 65536)
-            codes = np.zeros((c1 - c0, nw * 32), np.uint64)
-            codes[:, :L] = lut[data[c0 * L:c1 * L].reshape(c1 - c0, L)]
-            words[c0 * nw:c1 * nw] = np.bitwise_or.reduce(codes.reshape(c1 - c0, nw, 32) << shifts, axis=2).reshape(-1)
-        off = (np.arange(n, dtype=np.uint64) * np.uint64(nw))
-        lens = np.full(n, L, np.uint32)
-        return words, off, lens
-
-    def run(words, off, lens, n):
+    def run(data, n):
         bounds = [n * t // threads for t in range(threads + 1)]
         res = [None] * threads
 
         def work(t):
-            res[t] = ox.map_batch(words, off, lens, start=bounds[t], stop=bounds[t + 1])[0]["flags"].sum()
+            res[t] = ox.map_ascii_fixed(data, n, L, start=bounds[t], stop=bounds[t + 1])
         th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
         t1 = time.perf_counter()
         for x in th:
             x.start()
         for x in th:
             x.join()
-        return time.perf_counter() - t1
+        return time.perf_counter() - t1, res
 
     # calibrate on a small sample, then size the steps to the budget
     n0 = 2000 * threads
-    w, o, l = make_sample(10 ** 9, n0)
-    dt = run(w, o, l, n0)
+    dt, _ = run(tr.reads(3, 10 ** 9, n0, L, threads=threads), n0)
     rate = n0 / dt
     total_steps = max(1, steps + warmup)
     n = int(max(2000 * threads, min(4e6, rate * budget_s / total_steps)))
-    w, o, l = make_sample(0, n)
+    n = min(n, a.reads_per_step)
+    data = tr.reads(3, 0, n, L, threads=threads)
     for _ in range(warmup):
-        run(w, o, l, n)
-    t_sum = 0.0
+        run(data, n)
+    t_sum, res = 0.0, None
     for _ in range(steps):
-        t_sum += run(w, o, l, n)
+        dt, res = run(data, n)
+        t_sum += dt
     value = steps * n / t_sum
+    info = {"sample": "%d steps x %d reads (the first reads of the workload's stream; ASCII -> 2-bit packing inside "
+                      "the timed region), %d threads" % (steps, n, threads),
+            "reads_per_step": n, "ms_per_step": 1e3 * t_sum / steps, "oracle_index_s": index_s}
+    if keep:
+        hits = np.concatenate([r[0] for r in res])
+        base, o = 0, 0
+        for r in res:                    # member offsets: per-thread -> per-sample
+            hits["tx_off"][o:o + len(r[0])] += np.uint64(base)
+            base += len(r[1])
+            o += len(r[0])
+        info["results"] = (hits, np.concatenate([r[1] for r in res]))
     ox.close()
-    return value, {"sample": "%d steps x %d reads (first reads of the workload's stream), %d threads" % (steps, n, threads),
-                   "reads_per_step": n, "ms_per_step": 1e3 * t_sum / steps, "oracle_index_s": index_s}
+    return value, info
+
+
+def oracle_results(a, tr, flat, n, threads):
+    """Untimed: the oracle's results for the first n reads of the workload's stream."""
+    import orc
+    ox = orc.OrcIndex.from_flat(flat)
+    data = tr.reads(3, 0, n, a.read_len, threads=threads)
+    bounds = [n * t // threads for t in range(threads + 1)]
+    res = [None] * threads
+
+    def work(t):
+        res[t] = ox.map_ascii_fixed(data, n, a.read_len, start=bounds[t], stop=bounds[t + 1])
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    hits = np.concatenate([r[0] for r in res])
+    base, o = 0, 0
+    for r in res:
+        hits["tx_off"][o:o + len(r[0])] += np.uint64(base)
+        base += len(r[1])
+        o += len(r[0])
+    ox.close()
+    return hits, np.concatenate([r[1] for r in res])
+
+
+def parity_check(batch, want_hits, want_tx, device):
+    """GPU results of the first len(want_hits) reads of a device batch (just mapped) against the oracle's:
+    per-read equality of every psa_hit field and of the members, plus both checksums."""
+    import orc
+    n = len(want_hits)
+    got_hits = batch.hits.to_numpy(pkg_mod().HIT_DTYPE, n)
+    n_tx = int(want_hits["n_tx"].sum())
+    got_n_tx = int(got_hits["n_tx"].sum())
+    got_tx = batch.tx.to_numpy(np.uint32, max(got_n_tx, 1))[:got_n_tx]
+    bad = np.zeros(n, bool)
+    for f in ("coverage", "n_tx", "eq_id", "flags", "tx_off"):
+        bad |= got_hits[f] != want_hits[f]
+    if got_n_tx == n_tx:
+        diff = np.flatnonzero(got_tx != want_tx)
+        if len(diff):                      # attribute differing members to their reads
+            ends = np.cumsum(want_hits["n_tx"].astype(np.int64))
+            bad[np.unique(np.searchsorted(ends, diff, side="right"))] = True
+    first = int(np.flatnonzero(bad)[0]) if bad.any() else None
+    out = {"reads_checked": n, "mismatches": int(bad.sum()),
+           "checksum_gpu": "%016x" % batch_checksum(batch, n, 0, device),
+           "checksum_cpu": "%016x" % orc.result_checksum(want_hits, want_tx, 0),
+           "fields": "coverage, n_tx, eq_id, flags, tx_off, members"}
+    if first is not None:
+        out["first_mismatch"] = {"read": first, "gpu": [int(x) for x in got_hits[first].tolist()],
+                                 "oracle": [int(x) for x in want_hits[first].tolist()]}
+    return out
+
+
+def pkg_mod():
+    return importlib.import_module(PKG)
+
+
+def batch_checksum(batch, n, first_index, device):
+    import ctypes as C
+    psa = pkg_mod().pseudoaligner
+    out = C.c_uint64()
+    psa._check(psa.lib().psa_result_checksum(int(device), batch.hits.ptr, batch.tx.ptr, int(n), int(first_index), C.byref(out)))
+    return int(out.value)
 
 
 # ------------------------------------------------------------------------------------ main
@@ -307,9 +388,11 @@ def main():
             "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": info["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "reads_per_step": info["reads_per_step"], "read_len": a.read_len,
-                       "k": a.k, "note": "C restatement of the reference's map_read (oracle/psa_oracle.c): the Rust "
-                                         "crate and its debruijn/boomphf dependencies cannot be built in this image"},
+            "config": workload_config(a),
+            "run": {"sample_reads_per_step": info["reads_per_step"], "host_cores": ncores,
+                    "note": "C restatement of the reference's map_read (oracle/psa_oracle.c): the Rust crate and its "
+                            "debruijn/boomphf dependencies cannot be built in this image; each step is a bounded sample "
+                            "of the workload's step"},
             "cpu_baseline": {"value": value, "unit": "reads/s", "cores": threads, "kind": "port", "sample": info["sample"]},
             "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -466,6 +549,15 @@ def main():
     total_reads_counted = int(counts.sum())
     expect = a.steps * R * (world if comm is not None else 1)
     assert total_reads_counted == expect, "per-class counts sum to %d, expected %d" % (total_reads_counted, expect)
+    # order-independent checksum of (global read index, coverage, flags, eq_id, members) over ALL timed reads: the
+    # results of the last pass over every distinct batch are still in HBM; batch g was mapped uses[g] times
+    cks = [batch_checksum(dev_batches[g], R, shard_lo + g * R, local_rank) for g in range(min(G, a.steps))]
+    uses = [len(range(g, a.steps, G)) for g in range(min(G, a.steps))]
+    checksum_timed = sum(c * u for c, u in zip(cks, uses)) & 0xFFFFFFFFFFFFFFFF
+    if world > 1:
+        ct = torch.tensor([checksum_timed - (1 << 64) if checksum_timed >= (1 << 63) else checksum_timed], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ct, op=dist.ReduceOp.SUM)      # int64 wraps: the sum modulo 2^64
+        checksum_timed = int(ct.item()) & 0xFFFFFFFFFFFFFFFF
     ms_t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -536,76 +628,128 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # the map step is two kernels: k_map_thread (one thread per read) and k_map (cooperative, the reads
-    # k_map_thread handed over); each is charged the algorithmic bytes of the reads it completed
+    # the map step is two kernels: k_map_lanes (one thread per read) and k_map (cooperative, the reads
+    # k_map_lanes handed over); each is charged the algorithmic bytes of the reads it completed
     kernels = {}
-    for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
+    for name, part in (("k_map_lanes", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
         k_ms, k_n = prof[name]
         if not k_n:
             continue
-        per_step_ms = k_ms / a.steps                     # k_map_thread runs twice per step (second pass: seeded reads)
+        per_step_ms = k_ms / a.steps                     # per STEP: k_map_lanes runs twice per step (second pass: seeded reads)
         a_bytes = algorithmic_bytes(part, a.k)          # of one batch = one step
-        kernels[name] = {"ms_per_launch": per_step_ms, "launches_per_step": k_n / a.steps,
+        kernels[name] = {"ms_per_step": per_step_ms, "launches_per_step": k_n / a.steps,
                          "share_of_step": k_ms / prof_ms if prof_ms else None,
-                         "reads_per_launch": part["reads"], "algorithmic_bytes_per_launch": a_bytes,
+                         "reads_per_step": part["reads"], "algorithmic_bytes_per_step": a_bytes,
                          "achieved_gbs": a_bytes / (per_step_ms / 1e3) / 1e9}
-    dom = max(kernels, key=lambda kname: kernels[kname]["ms_per_launch"])
+    dom = max(kernels, key=lambda kname: kernels[kname]["ms_per_step"])
     achieved = kernels[dom]["achieved_gbs"]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")    # dram bytes per launch from the committed ncu capture
+    # DRAM bytes per step of the dominant kernel from the committed ncu capture -- only if it was taken from
+    # these very kernel sources (the file is stamped with their hash), else the figure is stale and dropped
+    traffic, traffic_note = None, "no ncu capture committed for this kernel"
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("%s:%s" % (a.workload, dom))
+        tj = json.load(open(tpath))
+        if tj.get("kernel_source_sha16") == kernel_source_sha16():
+            traffic = tj.get("%s:%s" % (a.workload, dom))
+            traffic_note = tj.get("note")
+        else:
+            traffic_note = "stale: profiles/traffic.json was captured from other kernel sources (%s, now %s)" % (
+                tj.get("kernel_source_sha16"), kernel_source_sha16())
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
+                "traffic": traffic, "traffic_note": traffic_note, "kernel_source_sha16": kernel_source_sha16(),
                 # companion figures: the same kernel time against the DRAM bytes ncu counted
-                "traffic_gbs": (traffic / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9) if traffic else None,
-                "traffic_frac": (traffic / (kernels[dom]["ms_per_launch"] / 1e3) / 1e9 / peak) if traffic else None,
-                "kernel": dom, "kernel_ms_per_launch": kernels[dom]["ms_per_launch"],
+                "traffic_gbs": (traffic / (kernels[dom]["ms_per_step"] / 1e3) / 1e9) if traffic else None,
+                "traffic_frac": (traffic / (kernels[dom]["ms_per_step"] / 1e3) / 1e9 / peak) if traffic else None,
+                "traffic_over_algorithmic": (traffic / kernels[dom]["algorithmic_bytes_per_step"]) if traffic else None,
+                "kernel": dom, "kernel_ms_per_step": kernels[dom]["ms_per_step"],
                 "kernel_share_of_step": kernels[dom]["share_of_step"], "kernels": kernels,
                 "algorithmic_bytes_per_read": a_bytes_per_read,
                 "sector_model_bytes_per_read": sector_bytes(ev, a.k) / ev["reads"],
-                "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_launch"] for v in kernels.values()) / 1e3) / 1e9,
-                "peak_source": peak_src, "handed_over_by_k_map_thread": deferred_by,
+                "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_step"] for v in kernels.values()) / 1e3) / 1e9,
+                "peak_source": peak_src, "handed_over_by_k_map_lanes": deferred_by,
                 "kernel_timing": ("CUDA events around every map kernel, inside the timed region" if M == 1 else
                                   "CUDA events around every map kernel over the same %d steps run once more on ONE mapper "
                                   "(%.3f ms per step): in the timed region the kernels of %d mappers overlap" % (a.steps, prof_ms / a.steps, M)),
                 "note": "dependent random 32-byte-sector gathers: see DESIGN.md for the sector-rate view"}
 
     cpu = None
+    want = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = a.host_threads or ncores
-        v, ci = cpu_arm(a, tr, flat, 3, 1, a.cpu_seconds, threads)
+        v, ci = cpu_arm(a, tr, flat, 3, 1, a.cpu_seconds, threads, keep=True)
+        want = ci.pop("results")
         cpu = {"value": v, "unit": "reads/s", "cores": threads, "kind": "port", "sample": ci["sample"],
-               "note": "oracle/psa_oracle.c, the C restatement of the reference's map_read (Rust toolchain absent)"}
+               "note": "oracle/psa_oracle.c, the C restatement of the reference's map_read (Rust toolchain absent); "
+                       "like the GPU arm's `value` it includes the ASCII -> 2-bit packing"}
         if threads > 1:     # the same port on ONE host thread, next to the all-threads figure
             v1, ci1 = cpu_arm(a, tr, flat, 1, 0, min(a.cpu_seconds, 3.0), 1)
             cpu["one_thread"] = {"value": v1, "unit": "reads/s", "sample": ci1["sample"]}
+
+    # ---------------- parity, measured: the oracle's results for the first reads of the stream (the CPU baseline's
+    # sample when it ran, else a smaller untimed sample) against the GPU's for the same reads of batch 0
+    parity = {"checksum_all_timed_reads": "%016x" % checksum_timed,
+              "checksum_of": "sum over reads of a hash chain over (global read index, coverage, flags, eq_id, members)"}
+    if rank == 0 and a.parity_reads != 0:
+        if want is None or (0 < a.parity_reads < len(want[0])):
+            n_par = min(R, a.parity_reads if a.parity_reads > 0 else 200000)
+            want = oracle_results(a, tr, flat, n_par, a.host_threads or ncores)
+        mapper.counts_reset()
+        mapper.map_device(dev_batches[0])
+        parity.update(parity_check(dev_batches[0], want[0], want[1], local_rank))
+        parity["reads"] = "reads [0, %d) of the read stream = the first reads of rank 0's first batch, %s index" % (
+            len(want[0]), workload_name(a))
+    # N > 1 (BASELINE config 4's criterion): the sharded run's all-reduced counts equal a single GPU's counts of the same reads
+    if world > 1 and a.verify_reads > 0:
+        V = min(a.verify_reads, R)
+        vbase = 1 << 40
+        vdata = tr.reads(3, vbase + rank * V, V, L, threads=host_threads)
+        vb = pkg.DeviceBatch(psa.READS_ASCII, vdata, V, stride=L, fixed_len=L, tx_cap=24 * V)
+        mapper.counts_reset()
+        mapper.map_device(vb)
+        mapper.counts_allreduce(comm)
+        sharded = mapper.counts()
+        vb.free()
+        if rank == 0:
+            mapper.counts_reset()
+            for r2 in range(world):
+                d2 = tr.reads(3, vbase + r2 * V, V, L, threads=host_threads)
+                b2 = pkg.DeviceBatch(psa.READS_ASCII, d2, V, stride=L, fixed_len=L, tx_cap=24 * V)
+                mapper.map_device(b2)
+                b2.free()
+            single = mapper.counts()
+            parity["multi_gpu"] = {"reads": world * V, "classes": int(len(single)),
+                                   "sharded_allreduced_counts_equal_single_gpu": bool(np.array_equal(sharded, single)),
+                                   "count_mismatches": int((sharded != single).sum())}
+        barrier()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "reads_per_step_per_gpu": R, "read_len": L, "k": a.k,
-                       "input": "ASCII reads resident in HBM; each step packs, maps, scans and expands one batch",
-                       "mappers": M,
-                       "l2": "inputs larger than L2 (%.0f MB per batch, %d distinct batches rotated; index %.0f MB)" % (
-                           R * L / 1e6, G, (info["mphf_bytes"] + info["values_bytes"] + info["node_bytes"]
-                                            + info["seq_bytes"] + info["eq_bytes"] + info["bloom_bytes"]) / 1e6),
-                       "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
-                                                                  "mphf_levels", "fp_bits", "max_class_len")},
-                       "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",
-                       "host_cores": ncores, "index_build_s": build_s, "setup_s": setup_s},
+            "config": workload_config(a),
+            "run": {"mappers": M,
+                    "l2": "inputs larger than L2 (%.0f MB per batch, %d distinct batches rotated; index %.0f MB)" % (
+                        R * L / 1e6, G, (info["dict_bytes"] + info["node_bytes"] + info["seq_bytes"] + info["eq_bytes"]) / 1e6),
+                    "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
+                                                              "dict_levels", "dict_bytes", "fp_bits", "max_class_len")},
+                    "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",
+                    "host_cores": ncores, "index_build_s": build_s, "setup_s": setup_s},
+            "parity": parity,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "events_per_read": {key: ev[key] / ev["reads"] for key in ev if key != "reads"},
         }
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
+    failed = rank == 0 and (parity.get("mismatches", 0) != 0 or parity.get("checksum_gpu") != parity.get("checksum_cpu")
+                            or parity.get("multi_gpu", {}).get("count_mismatches", 0) != 0)
+    if failed:
+        sys.stderr.write("PARITY FAILURE: %s\n" % json.dumps(parity))
     if comm is not None:
         comm.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 3 if failed else 0
 
 
 if __name__ == "__main__":

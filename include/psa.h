@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PSA_ABI_VERSION 1
+#define PSA_ABI_VERSION 2
 
 /* ---- status codes ---- */
 #define PSA_OK 0
@@ -81,16 +81,17 @@ typedef struct psa_index_desc { /* all pointers host memory, borrowed for the ca
 
 typedef struct psa_index_info {
     uint32_t k;
-    uint32_t mphf_levels;
+    uint32_t dict_levels; /* levels of the k-mer dictionary's bucket cascade                 */
     uint64_t n_nodes, n_kmers, n_eq, n_eq_members, n_seq_words;
-    uint64_t mphf_bytes, values_bytes, node_bytes, seq_bytes, eq_bytes, bloom_bytes; /* device residency */
-    uint32_t node_bits, pos_bits, fp_bits; /* packing of one `values` entry               */
+    uint64_t dict_bytes, node_bytes, seq_bytes, eq_bytes; /* device residency               */
+    uint32_t node_bits, pos_bits, fp_bits; /* layout of one 64-bit dictionary entry         */
     uint32_t max_class_len;
     double gamma;
-    double build_ms; /* device time of the MPHF/edge build                                  */
+    double build_ms; /* device time of the dictionary/edge build                            */
 } psa_index_info;
 
-/* gamma <= 0 selects the reference's 1.7 (ref src/build_index.rs:197). */
+/* gamma: dictionary slots per k-mer at every level of the cascade; <= 0 selects 1.7, the
+ * reference's MPHF load parameter (ref src/build_index.rs:197). */
 int psa_index_create(const psa_index_desc* desc, int device, double gamma, psa_index** out);
 void psa_index_destroy(psa_index*);
 int psa_index_get_info(const psa_index*, psa_index_info* out);
@@ -161,12 +162,12 @@ int psa_mapper_set_allowed_mismatches(psa_mapper*, uint32_t allowed);
 /* Tuning: lanes of a warp that cooperate on one read (8, 16 or 32; default 8, or the
  * PSA_GROUP_WIDTH environment variable).  Results do not depend on it. */
 int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
-/* Tuning: the map step is two kernels.  k_map_thread gives every read one thread and hands a
- * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
- * needs more than max_probes positions, it visits more than 4 distinct classes, or its
- * smallest class has more than max_small members.  max_probes = 0 sends every read to the
- * cooperative kernel.  Defaults ceil(k/3)+2 / 32 (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do
- * not depend on it. */
+/* Tuning: the map step is two kernels.  k_map_lanes gives every read (up to 256 bases) one lane
+ * and hands a read over to the cooperative kernel (k_map, group_width lanes per read) when its
+ * seed search needs more than max_probes positions, it meets more wide classes than a lane
+ * keeps, or all its classes are wide and the smallest has more than max_small members.
+ * max_probes = 0 sends every read to the cooperative kernel.  Defaults ceil(k/3)+2 / 32
+ * (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
 /* Tuning: reads whose FIRST seed search is too long for one thread go to k_seed_scan, where
  * `lanes` lanes (8, 16 or 32; default 8, PSA_SCAN_WIDTH) probe as many stride-3 positions at
@@ -209,8 +210,8 @@ void* psa_mapper_counts_device(psa_mapper*); /* uint64[n_eq+2] in HBM */
 typedef struct psa_events {
     uint64_t reads, read_bases;
     uint64_t kmer_lookups;   /* P: the reference's own counter (src/pseudoaligner.rs:95)     */
-    uint64_t mphf_levels;    /* bit-vector blocks probed                                     */
-    uint64_t mphf_hits;      /* probes that reached `values`                                 */
+    uint64_t dict_levels;    /* dictionary buckets probed                                    */
+    uint64_t dict_hits;      /* buckets with an entry carrying the k-mer's fingerprint       */
     uint64_t verifications;  /* unitig k-mer fetched and compared                            */
     uint64_t node_visits;    /* nodes.push                                                   */
     uint64_t bases_compared; /* base compares of both extension loops                        */
@@ -220,21 +221,21 @@ typedef struct psa_events {
     uint64_t aligned;
 } psa_events;
 /* Same as psa_mapper_map on a device batch, with event counting compiled in (slower).
- * out[0]: the reads completed by k_map_thread, out[1]: by k_map, out[2]: by k_seed_scan (reads
- * without a seed) plus the first seed searches it made for reads k_map_thread completed. */
+ * out[0]: the reads completed by k_map_lanes, out[1]: by k_map, out[2]: by k_seed_scan (reads
+ * without a seed) plus the first seed searches it made for reads k_map_lanes completed. */
 int psa_mapper_map_events(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results,
                           psa_events out[3]);
 
-/* After psa_mapper_map_events: why k_map_thread handed reads over -- [0] first seed search
- * longer than max_probes, [1] re-seed search longer than max_probes, [2] more than 4
- * distinct classes, [3] smallest class longer than max_small.  Diagnostic. */
+/* After psa_mapper_map_events: why k_map_lanes handed reads over -- [0] first seed search
+ * longer than max_probes, [1] re-seed search longer than max_probes, [2] wide-class list
+ * full, [3] smallest class longer than max_small.  Diagnostic. */
 int psa_mapper_defer_reasons(psa_mapper*, uint64_t out[4]);
 
 /* Kernels launched by this mapper since creation (bench.py's gpu_launches). */
 uint64_t psa_mapper_launch_count(const psa_mapper*);
 /* Device timing of the map kernels alone: when enabled, every launch is bracketed by CUDA
  * events on the mapper's stream.  psa_mapper_profile_read synchronises, returns the summed
- * kernel time and launch count since the last read ([0] k_map_thread, both passes; [1] k_map;
+ * kernel time and launch count since the last read ([0] k_map_lanes, both passes; [1] k_map;
  * [2] k_seed_scan), and resets them. */
 int psa_mapper_profile_enable(psa_mapper*, int on);
 int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[3], uint64_t map_launches[3]);
@@ -274,6 +275,12 @@ int psa_mapper_counts_allreduce(psa_mapper*, psa_comm*);
  * the index lookups without their dependencies; the practical ceiling the map kernels are
  * compared with.  chunk_bytes = 0: one random 128-byte line per warp (4 bytes per lane). ---- */
 int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s);
+
+/* ---- verification aid: order-independent 64-bit checksum of a device-resident result batch (the sum over
+ * reads of a hash chain over global read index first_index + i, coverage, flags, eq_id and the members in
+ * tx_buf[tx_off ..)); bench.py compares it with the same function of the oracle's results. ---- */
+int psa_result_checksum(int device, const psa_hit* hits_dev, const uint32_t* tx_dev, uint64_t n, uint64_t first_index,
+                        uint64_t* out);
 
 /* ---- pinned host memory for the batch buffers (pageable memory works, slower) ---- */
 int psa_host_alloc(void** out, uint64_t bytes);

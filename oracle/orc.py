@@ -80,6 +80,15 @@ def lib():
                                vp, u32, C.POINTER(u32), vp]
     L.orc_map_batch.restype = C.c_int
     L.orc_map_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, u64, C.POINTER(u64), vp, vp]
+    L.orc_map_batch_with_mismatch.restype = C.c_int
+    L.orc_map_batch_with_mismatch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64, C.POINTER(u64), vp, vp]
+    L.orc_map_read_with_mismatch.restype = C.c_int
+    L.orc_map_read_with_mismatch.argtypes = [vp, vp, u32, u32, vp, u64, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32),
+                                             vp, u32, C.POINTER(u32), vp]
+    L.orc_map_ascii_batch.restype = C.c_int
+    L.orc_map_ascii_batch.argtypes = [vp, vp, u64, u32, u64, u32, vp, vp, u64, C.POINTER(u64), vp, vp]
+    L.orc_result_checksum.restype = u64
+    L.orc_result_checksum.argtypes = [vp, vp, u64, u64]
     L.orc_intersect.restype = u32
     L.orc_intersect.argtypes = [vp, u32, vp, u32]
     _lib = L
@@ -251,23 +260,23 @@ class OrcIndex:
         r = lib().orc_index_lookup(self.h, _ptr(w), C.byref(n), C.byref(o))
         return (n.value, o.value) if r else None
 
-    def map_read(self, seq, want_nodes=False):
+    def map_read(self, seq, want_nodes=False, allowed=2):
         """Pseudoaligner::map_read: None or (sorted tx list, coverage[, nodes])."""
         if isinstance(seq, str):
             seq = seq.encode()
         words = np.zeros((len(seq) + 31) // 32 + 2, dtype=np.uint64)
         w = pack_ascii(seq)
         words[:len(w)] = w
-        return self.map_packed(words, len(seq), want_nodes)
+        return self.map_packed(words, len(seq), want_nodes, allowed)
 
-    def map_packed(self, words, length, want_nodes=False):
+    def map_packed(self, words, length, want_nodes=False, allowed=2):
         cap = 1 << 16
         while True:
             tx = np.zeros(cap, dtype=np.uint32)
             nodes = np.zeros(2 * length + 2, dtype=np.uint32)
             n_tx, cov, eq, nn = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
-            r = lib().orc_map_read(self.h, _ptr(words), length, _ptr(tx), cap, C.byref(n_tx), C.byref(cov),
-                                   C.byref(eq), _ptr(nodes), len(nodes), C.byref(nn), None)
+            r = lib().orc_map_read_with_mismatch(self.h, _ptr(words), length, int(allowed), _ptr(tx), cap, C.byref(n_tx),
+                                                 C.byref(cov), C.byref(eq), _ptr(nodes), len(nodes), C.byref(nn), None)
             if r >= 0:
                 break
             cap *= 16
@@ -278,7 +287,7 @@ class OrcIndex:
             res = res + (nodes[:nn.value].tolist(),)
         return res
 
-    def map_batch(self, words, read_off, read_len, counts=False, start=0, stop=None):
+    def map_batch(self, words, read_off, read_len, counts=False, start=0, stop=None, allowed=2):
         """process_reads inner loop over reads [start, stop): (hits, tx_buf, counts|None, events)."""
         words = np.ascontiguousarray(words, dtype=np.uint64)
         read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
@@ -294,13 +303,37 @@ class OrcIndex:
             ev = Events()
             if cnt is not None:
                 cnt[:] = 0
-            r = lib().orc_map_batch(self.h, _ptr(words), _ptr(read_off[start:stop]), _ptr(read_len[start:stop]), n,
-                                    _ptr(hits), _ptr(tx), cap, C.byref(used),
-                                    _ptr(cnt) if cnt is not None else None, C.byref(ev))
+            r = lib().orc_map_batch_with_mismatch(self.h, _ptr(words), _ptr(read_off[start:stop]),
+                                                  _ptr(read_len[start:stop]), n, int(allowed), _ptr(hits), _ptr(tx), cap,
+                                                  C.byref(used), _ptr(cnt) if cnt is not None else None, C.byref(ev))
             if r == 0:
                 break
             cap = int(used.value) + 16
         return hits, tx[:used.value].copy(), cnt, ev.as_dict()
+
+    def map_ascii_fixed(self, data, n, length, stride=None, start=0, stop=None, allowed=2, counts=False):
+        """process_reads worker body over fixed-stride ASCII reads [start, stop): packs, then maps."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        stride = length if stride is None else stride
+        stop = n if stop is None else stop
+        m = stop - start
+        hits = np.zeros(m, dtype=HIT_DTYPE)
+        cap = max(16 * m, 1024)
+        cnt = np.zeros(self.n_eq + 2, dtype=np.uint64) if counts else None
+        base = data.ctypes.data + start * stride
+        while True:
+            tx = np.zeros(cap, dtype=np.uint32)
+            used = C.c_uint64()
+            if cnt is not None:
+                cnt[:] = 0
+            r = lib().orc_map_ascii_batch(self.h, C.c_void_p(base), stride, length, m, int(allowed), _ptr(hits), _ptr(tx), cap,
+                                          C.byref(used), _ptr(cnt) if cnt is not None else None, None)
+            if r == 0:
+                break
+            if r == -2:
+                raise MemoryError
+            cap = int(used.value) + 16
+        return hits, tx[:used.value].copy(), cnt
 
     def close(self):
         if self.h:
@@ -319,6 +352,12 @@ def intersect(v1, v2):
     b = np.array(v2, dtype=np.uint32)
     n = lib().orc_intersect(_ptr(a), len(a), _ptr(b), len(b))
     return a[:n].tolist()
+
+
+def result_checksum(hits, tx, first_index=0):
+    hits = np.ascontiguousarray(hits)
+    tx = np.ascontiguousarray(tx, dtype=np.uint32)
+    return int(lib().orc_result_checksum(_ptr(hits), _ptr(tx), len(hits), int(first_index)))
 
 
 def hits_to_tuples(hits, tx):

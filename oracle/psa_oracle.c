@@ -494,8 +494,12 @@ fail:
 }
 
 /* ------------------------------------------------------------------------------------
- * intersect -- ref src/pseudoaligner.rs:389-418.  In place on v1; v2 searched with a
- * binary search over its remaining suffix, exactly as the reference does.
+ * intersect -- ref src/pseudoaligner.rs:389-418, statement by statement.  In place on v1.
+ * Note the reference's `v2[idx2..].binary_search(..)` returns a position RELATIVE to the
+ * suffix it searched and the reference then ASSIGNS it (`idx2 = pos + 1`, :409; `idx2 = pos`,
+ * :413) instead of adding it to the suffix's start; the next search therefore starts from a
+ * smaller (or equal) index than where the previous match was -- it merely searches a larger
+ * suffix than necessary, which cannot change the outcome on ascending inputs.  Restated as is.
  * ---------------------------------------------------------------------------------- */
 /* Rust slice::binary_search on a strictly ascending slice: found -> (1,pos); else (0, insertion pos) */
 static inline int bsearch_u32(const uint32_t* v, uint32_t n, uint32_t x, uint32_t* pos) {
@@ -514,13 +518,14 @@ uint32_t orc_intersect(uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n
     uint32_t fill_idx1 = 0, idx1 = 0, idx2 = 0; /* :398-400 */
     while (idx1 < n1 && idx2 < n2) {       /* :402 */
         uint32_t pos;
-        if (bsearch_u32(v2 + idx2, n2 - idx2, v1[idx1], &pos)) { /* :403-404 */
+        if (bsearch_u32(v2 + idx2, n2 - idx2, v1[idx1], &pos)) { /* :403-404 v2[idx2..].binary_search(&v1[idx1]) */
             uint32_t tmp = v1[fill_idx1]; v1[fill_idx1] = v1[idx1]; v1[idx1] = tmp; /* :406 swap */
-            fill_idx1++; idx1++;
-            idx2 += pos + 1;               /* :409 (pos is relative to the suffix) */
+            fill_idx1++;                   /* :407 */
+            idx1++;                        /* :408 */
+            idx2 = pos + 1;                /* :409 (sic: suffix-relative position assigned) */
         } else {
-            idx1++;
-            idx2 += pos;                   /* :413 */
+            idx1++;                        /* :412 */
+            idx2 = pos;                    /* :413 (sic) */
         }
     }
     return fill_idx1;                      /* :417 truncate */
@@ -694,8 +699,17 @@ int orc_map_read(const orc_index* ix, const uint64_t* read_words, uint32_t read_
                  uint32_t* tx_out, uint64_t tx_cap, uint32_t* n_tx, uint32_t* coverage,
                  uint32_t* eq_id, uint32_t* nodes_out, uint32_t nodes_cap, uint32_t* n_nodes,
                  orc_events* ev) {
+    /* map_read, :381-384: map_read_with_mismatch with DEFAULT_ALLOWED_MISMATCHES */
+    return orc_map_read_with_mismatch(ix, read_words, read_len, DEFAULT_ALLOWED_MISMATCHES, tx_out, tx_cap, n_tx,
+                                      coverage, eq_id, nodes_out, nodes_cap, n_nodes, ev);
+}
+
+int orc_map_read_with_mismatch(const orc_index* ix, const uint64_t* read_words, uint32_t read_len,
+                               uint32_t allowed_mismatches, uint32_t* tx_out, uint64_t tx_cap, uint32_t* n_tx,
+                               uint32_t* coverage, uint32_t* eq_id, uint32_t* nodes_out, uint32_t nodes_cap,
+                               uint32_t* n_nodes, orc_events* ev) {
     orc_events local; if (!ev) { memset(&local, 0, sizeof local); ev = &local; }
-    /* map_read_with_mismatch, :361-376, with DEFAULT_ALLOWED_MISMATCHES (:382) */
+    /* map_read_with_mismatch, :361-376 */
     uint32_t stack_nodes[512];
     node_vec nv; nv.n = 0; nv.overflow = 0;
     uint32_t need = 2 * read_len + 2;
@@ -704,7 +718,7 @@ int orc_map_read(const orc_index* ix, const uint64_t* read_words, uint32_t read_
     else { heap = (uint32_t*)malloc((size_t)need * 4); nv.v = heap; nv.cap = need; }
     uint64_t cov = 0;
     ev->reads++; ev->read_bases += read_len;
-    int some = map_read_to_nodes(ix, read_words, read_len, &nv, DEFAULT_ALLOWED_MISMATCHES, &cov, ev);
+    int some = map_read_to_nodes(ix, read_words, read_len, &nv, allowed_mismatches, &cov, ev);
     *n_tx = 0; *coverage = 0; if (eq_id) *eq_id = ORC_EQ_NONE; if (n_nodes) *n_nodes = 0;
     if (!some) { free(heap); return 0; }
     if (n_nodes) {
@@ -731,16 +745,23 @@ int orc_map_read(const orc_index* ix, const uint64_t* read_words, uint32_t read_
 int orc_map_batch(const orc_index* ix, const uint64_t* read_words, const uint64_t* read_off,
                   const uint32_t* read_len, uint64_t n_reads, orc_hit* hits, uint32_t* tx_buf,
                   uint64_t tx_cap, uint64_t* tx_used, uint64_t* counts, orc_events* ev) {
+    return orc_map_batch_with_mismatch(ix, read_words, read_off, read_len, n_reads, DEFAULT_ALLOWED_MISMATCHES, hits,
+                                       tx_buf, tx_cap, tx_used, counts, ev);
+}
+
+int orc_map_batch_with_mismatch(const orc_index* ix, const uint64_t* read_words, const uint64_t* read_off,
+                                const uint32_t* read_len, uint64_t n_reads, uint32_t allowed_mismatches, orc_hit* hits,
+                                uint32_t* tx_buf, uint64_t tx_cap, uint64_t* tx_used, uint64_t* counts, orc_events* ev) {
     orc_events local; if (!ev) { memset(&local, 0, sizeof local); ev = &local; }
     uint64_t used = 0; int overflow = 0;
     for (uint64_t i = 0; i < n_reads; i++) {
         uint32_t n_tx = 0, cov = 0, eq = ORC_EQ_NONE;
         uint64_t room = used <= tx_cap ? tx_cap - used : 0;
-        int r = orc_map_read(ix, read_words + read_off[i], read_len[i], tx_buf ? tx_buf + used : NULL,
-                             overflow ? 0 : room, &n_tx, &cov, &eq, NULL, 0, NULL, ev);
+        int r = orc_map_read_with_mismatch(ix, read_words + read_off[i], read_len[i], allowed_mismatches,
+                                           tx_buf ? tx_buf + used : NULL, overflow ? 0 : room, &n_tx, &cov, &eq, NULL, 0, NULL, ev);
         if (r < 0) { overflow = 1; /* keep counting the need with a scratch pass */
             uint32_t* tmp = (uint32_t*)malloc(((size_t)ix->eq_offsets[ix->n_eq] + 1) * 4);
-            r = orc_map_read(ix, read_words + read_off[i], read_len[i], tmp, ix->eq_offsets[ix->n_eq], &n_tx, &cov, &eq, NULL, 0, NULL, NULL);
+            r = orc_map_read_with_mismatch(ix, read_words + read_off[i], read_len[i], allowed_mismatches, tmp, ix->eq_offsets[ix->n_eq], &n_tx, &cov, &eq, NULL, 0, NULL, NULL);
             free(tmp);
         }
         hits[i].coverage = cov; hits[i].n_tx = n_tx; hits[i].tx_off = used; hits[i].eq_id = eq;
@@ -759,4 +780,44 @@ int orc_map_batch(const orc_index* ix, const uint64_t* read_words, const uint64_
     }
     *tx_used = used;
     return overflow ? -1 : 0;
+}
+
+/* process_reads worker body over ASCII records (ref :449-462): DnaString::from_dna_string (:449-450)
+ * then map_read (:451), reads of `len` bytes at ascii + i*stride.  Same outputs as orc_map_batch. */
+int orc_map_ascii_batch(const orc_index* ix, const uint8_t* ascii, uint64_t stride, uint32_t len, uint64_t n_reads,
+                        uint32_t allowed_mismatches, orc_hit* hits, uint32_t* tx_buf, uint64_t tx_cap,
+                        uint64_t* tx_used, uint64_t* counts, orc_events* ev) {
+    uint64_t nw = orc_words_for(len) + 2;
+    uint64_t* words = (uint64_t*)calloc(nw, 8);
+    if (!words) return -2;
+    uint64_t used = 0; int overflow = 0;
+    const uint64_t zero = 0;
+    for (uint64_t i = 0; i < n_reads; i++) {
+        orc_pack_ascii((const char*)ascii + i * stride, len, words);             /* :449-450 */
+        uint64_t u = 0;
+        int r = orc_map_batch_with_mismatch(ix, words, &zero, &len, 1, allowed_mismatches, hits + i,
+                                            tx_buf ? tx_buf + used : NULL, overflow || used > tx_cap ? 0 : tx_cap - used,
+                                            &u, counts, ev);                        /* :451-462 */
+        if (r < 0) overflow = 1;
+        hits[i].tx_off = used;
+        used += u;
+    }
+    free(words);
+    *tx_used = used;
+    return overflow ? -1 : 0;
+}
+
+/* Order-independent checksum of a result batch (verification aid; include/psa.h psa_result_checksum
+ * restates it for device buffers): sum over reads of a hash chain over (global read index,
+ * coverage, flags, eq_id, members in order). */
+uint64_t orc_result_checksum(const orc_hit* hits, const uint32_t* tx, uint64_t n, uint64_t first_index) {
+    uint64_t sum = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        uint64_t h = mix64(first_index + i + 0x9E3779B97F4A7C15ULL);
+        h = mix64(h ^ (((uint64_t)hits[i].coverage << 32) | hits[i].flags));
+        h = mix64(h ^ (((uint64_t)hits[i].n_tx << 32) | hits[i].eq_id));
+        for (uint32_t j = 0; j < hits[i].n_tx; j++) h = mix64(h ^ ((uint64_t)tx[hits[i].tx_off + j] + 0xD6E8FEB86659FD93ULL));
+        sum += h;
+    }
+    return sum;
 }

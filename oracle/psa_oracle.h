@@ -122,6 +122,12 @@ int orc_map_read(const orc_index*, const uint64_t* read_words, uint32_t read_len
                  uint32_t* eq_id, uint32_t* nodes_out, uint32_t nodes_cap, uint32_t* n_nodes,
                  orc_events* ev);
 
+/* map_read_with_mismatch (pseudoaligner.rs:361-376): the same with any allowed_mismatches. */
+int orc_map_read_with_mismatch(const orc_index*, const uint64_t* read_words, uint32_t read_len,
+                               uint32_t allowed_mismatches, uint32_t* tx_out, uint64_t tx_cap, uint32_t* n_tx,
+                               uint32_t* coverage, uint32_t* eq_id, uint32_t* nodes_out, uint32_t nodes_cap,
+                               uint32_t* n_nodes, orc_events* ev);
+
 /* process_reads inner loop over a batch (pseudoaligner.rs:449-462), single thread, input
  * order.  Read i occupies read_words[read_off[i] ...] (offsets in 64-bit words).
  * Returns 0, or -1 if tx_buf is too small (tx_used then holds the required size). */
@@ -129,6 +135,19 @@ int orc_map_batch(const orc_index*, const uint64_t* read_words, const uint64_t* 
                   const uint32_t* read_len, uint64_t n_reads, orc_hit* hits, uint32_t* tx_buf,
                   uint64_t tx_cap, uint64_t* tx_used, uint64_t* counts /* n_eq+2 or NULL */,
                   orc_events* ev /* may be NULL */);
+
+int orc_map_batch_with_mismatch(const orc_index*, const uint64_t* read_words, const uint64_t* read_off,
+                                const uint32_t* read_len, uint64_t n_reads, uint32_t allowed_mismatches, orc_hit* hits,
+                                uint32_t* tx_buf, uint64_t tx_cap, uint64_t* tx_used, uint64_t* counts, orc_events* ev);
+
+/* The same over ASCII records (DnaString::from_dna_string at :449-450 inside the loop, as the
+ * reference's worker has it): read i = `len` bytes at ascii + i*stride. */
+int orc_map_ascii_batch(const orc_index*, const uint8_t* ascii, uint64_t stride, uint32_t len, uint64_t n_reads,
+                        uint32_t allowed_mismatches, orc_hit* hits, uint32_t* tx_buf, uint64_t tx_cap,
+                        uint64_t* tx_used, uint64_t* counts, orc_events* ev);
+
+/* Order-independent 64-bit checksum of a result batch (read index, coverage, flags, eq_id, members). */
+uint64_t orc_result_checksum(const orc_hit* hits, const uint32_t* tx, uint64_t n, uint64_t first_index);
 
 /* intersect (pseudoaligner.rs:389-418): in-place on v1, returns the new length. */
 uint32_t orc_intersect(uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n2);

@@ -10,7 +10,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 #include <string>
@@ -97,10 +99,7 @@ struct DevBuf {
 struct psa_index {
     int device = 0;
     DevIndex d{};
-    DevBuf blocks, values, nodes, seq, eq_off, eq_mem, class_win, bloom;
-    DevBuf hot;  // one allocation behind nodes, seq, class_win and eq_off: the small tables every read touches,
-                 // contiguous so that ONE L2 access-policy window can keep them resident (psa_mapper_create)
-    size_t hot_bytes = 0;
+    DevBuf buckets, nodes, nodes_cold, seq, eq_off, eq_mem, class_win;
     psa_index_info info{};
     int kw = 1;
 };
@@ -116,10 +115,11 @@ static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma,
                            const std::vector<uint64_t>& koff_host, uint64_t n_kmers) {
     const uint32_t k = d->k;
     cudaStream_t st = 0;
-    DevBuf koff, key_lo[3], key_hi[3], val[3], coll, cursor, err, cnt, rank, tmp;
+    DevBuf koff, key_lo[3], key_hi[3], val[3], bid[2], idx[2], sel, passed, nsel, err, tmp;
     auto cleanup = [&]() {
-        koff.release(); coll.release(); cursor.release(); err.release(); cnt.release(); rank.release(); tmp.release();
+        koff.release(); sel.release(); passed.release(); nsel.release(); err.release(); tmp.release();
         for (int i = 0; i < 3; i++) { key_lo[i].release(); key_hi[i].release(); val[i].release(); }
+        for (int i = 0; i < 2; i++) { bid[i].release(); idx[i].release(); }
     };
 #define CUB_(call)                                                                                 \
     do {                                                                                           \
@@ -143,7 +143,7 @@ static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma,
     CUB_(cudaMemcpy(koff.p, koff_host.data(), (d->n_nodes + 1) * 8, cudaMemcpyHostToDevice));
     RC_(err.ensure(4));
     CUB_(cudaMemset(err.p, 0, 4));
-    RC_(cursor.ensure(8));
+    RC_(nsel.ensure(8));
 
     // 1. every k-mer of every node
     RC_(key_lo[0].ensure(n_kmers * 8 + 8));
@@ -155,107 +155,98 @@ static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma,
             key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(), val[0].as<uint64_t>());
     CUB_(cudaGetLastError());
 
-    // 1b. absent-key prefilter
+    // 2. the dictionary: a cascade of bucket tables (psa_core.cuh Dict).  Level sizes depend on the keys the
+    // level before passed on (~5 % at 1.7 slots per key); allocate for the geometric bound and check.
+    std::vector<uint64_t> lvl_nbkt, lvl_base;
+    uint64_t total_bkt = 0;
     {
-        const uint64_t nb = std::max<uint64_t>(1, (n_kmers * kBloomBitsPerKey + 255) / 256);
-        RC_(ix->bloom.ensure(nb * 32));
-        CUB_(cudaMemsetAsync(ix->bloom.p, 0, nb * 32, st));
-        Bloom b{ix->bloom.as<uint32_t>(), nb};
-        if (n_kmers)
-            k_bloom_set<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(),
-                                                                    n_kmers, b, ix->bloom.as<uint32_t>());
-        CUB_(cudaGetLastError());
-        ix->d.bloom = b;
-        ix->info.bloom_bytes = nb * 32;
-    }
-    // 2. cascade of bit-vector levels (boomphf's construction, on the device)
-    std::vector<uint64_t> lvl_nblk, lvl_base;
-    uint64_t total_blk = 0;
-    {
-        // level sizes depend on the survivors of the level before; allocate for the geometric bound
-        // (each level keeps < 50% of its keys at gamma >= 1.45; 4x level 0 is a safe cap) and grow if needed
-        uint64_t nblk0 = std::max<uint64_t>(1, (uint64_t)(gamma * (double)n_kmers / kBlockBits) + 1);
-        uint64_t cap_blk = 4 * nblk0 + 4 * kMaxLevels;
-        RC_(ix->blocks.ensure(cap_blk * 32));
-        CUB_(cudaMemsetAsync(ix->blocks.p, 0, ix->blocks.cap, st));
-        RC_(coll.ensure(nblk0 * 32));
-        CUB_(cudaMemsetAsync(coll.p, 0, coll.cap, st));
+        auto level_size = [&](uint64_t n) { return std::max<uint64_t>(1, (uint64_t)(gamma * (double)n / kBucketSlots) + 1); };
+        const uint64_t cap_bkt = 2 * level_size(n_kmers) + 4 * kMaxLevels;
+        RC_(ix->buckets.ensure(cap_bkt * 32));
+        CUB_(cudaMemsetAsync(ix->buckets.p, 0xFF, ix->buckets.cap, st));  // kEmptyEntry
+        RC_(passed.ensure(n_kmers + 8));
+        RC_(sel.ensure(n_kmers * 4 + 8));
+        for (int i = 0; i < 2; i++) {
+            RC_(bid[i].ensure(n_kmers * 4 + 8));
+            RC_(idx[i].ensure(n_kmers * 4 + 8));
+        }
         uint64_t rem = n_kmers;
-        int src = 0;  // buffer holding the remaining keys (0 = the full list, kept for step 4)
+        int src = 0;  // buffer holding the remaining keys (0 = the full list, kept for the self-check)
         while (rem > 0) {
-            if ((int)lvl_nblk.size() >= kMaxLevels) {
+            if ((int)lvl_nbkt.size() >= kMaxLevels) {
                 cleanup();
-                return fail(PSA_ERR_INDEX, "MPHF did not converge: duplicate k-mer in the graph");
+                return fail(PSA_ERR_INDEX, "dictionary did not converge: duplicate k-mer in the graph");
             }
-            uint64_t nblk = std::max<uint64_t>(1, (uint64_t)(gamma * (double)rem / kBlockBits) + 1);
-            if (total_blk + nblk > cap_blk) {
+            const uint64_t nbkt = level_size(rem);
+            if (nbkt >= 0xFFFFFFFFull || total_bkt + nbkt > cap_bkt) {
                 cleanup();
-                return fail(PSA_ERR_INDEX, "MPHF block budget exceeded (gamma too small?)");
+                return fail(PSA_ERR_INDEX, "dictionary bucket budget exceeded");
             }
-            uint32_t lvl = (uint32_t)lvl_nblk.size();
-            int dst = src == 1 ? 2 : 1;
-            RC_(key_lo[dst].ensure(rem * 8 + 8));
-            if (KW == 2) RC_(key_hi[dst].ensure(rem * 8 + 8));
-            RC_(val[dst].ensure(rem * 8 + 8));
-            CUB_(cudaMemsetAsync(cursor.p, 0, 8, st));
-            k_mphf_set<KW><<<nblocks(rem, 256), 256, 0, st>>>(
-                key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(), rem, lvl, nblk, total_blk,
-                ix->blocks.as<unsigned long long>(), coll.as<unsigned long long>());
-            k_mphf_filter<KW><<<nblocks(rem, 256), 256, 0, st>>>(
-                key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(), val[src].as<uint64_t>(), rem, lvl, nblk,
-                coll.as<unsigned long long>(), key_lo[dst].as<uint64_t>(), key_hi[dst].as<uint64_t>(),
-                val[dst].as<uint64_t>(), cursor.as<unsigned long long>());
-            k_mphf_finalize<<<nblocks(4 * nblk, 256), 256, 0, st>>>(ix->blocks.as<unsigned long long>(),
-                                                                   coll.as<unsigned long long>(), total_blk, nblk);
+            const uint32_t lvl = (uint32_t)lvl_nbkt.size();
+            const uint32_t n32 = (uint32_t)rem;
+            k_dict_bucket_ids<KW><<<nblocks(rem, 256), 256, 0, st>>>(key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(), n32, lvl,
+                                                                      nbkt, bid[0].as<uint32_t>(), idx[0].as<uint32_t>());
+            int end_bit = 1;
+            while (end_bit < 32 && (nbkt >> end_bit)) end_bit++;
+            size_t tb = 0;
+            CUB_(cub::DeviceRadixSort::SortPairs(nullptr, tb, bid[0].as<uint32_t>(), bid[1].as<uint32_t>(), idx[0].as<uint32_t>(),
+                                                 idx[1].as<uint32_t>(), (int)n32, 0, end_bit, st));
+            RC_(tmp.ensure(tb));
+            CUB_(cub::DeviceRadixSort::SortPairs(tmp.p, tb, bid[0].as<uint32_t>(), bid[1].as<uint32_t>(), idx[0].as<uint32_t>(),
+                                                 idx[1].as<uint32_t>(), (int)n32, 0, end_bit, st));
+            k_dict_fill<KW><<<nblocks(rem, 256), 256, 0, st>>>(key_lo[src].as<uint64_t>(), key_hi[src].as<uint64_t>(),
+                                                                val[src].as<uint64_t>(), n32, bid[1].as<uint32_t>(),
+                                                                idx[1].as<uint32_t>(), ix->d, total_bkt, ix->buckets.as<uint64_t>(),
+                                                                passed.as<uint8_t>());
             CUB_(cudaGetLastError());
-            unsigned long long next = 0;
-            CUB_(cudaMemcpyAsync(&next, cursor.p, 8, cudaMemcpyDeviceToHost, st));
+            // the keys passed on, in order
+            cub::CountingInputIterator<uint32_t> count_it(0);
+            CUB_(cub::DeviceSelect::Flagged(nullptr, tb, count_it, passed.as<uint8_t>(), sel.as<uint32_t>(), nsel.as<uint32_t>(), (int)n32, st));
+            RC_(tmp.ensure(tb));
+            CUB_(cub::DeviceSelect::Flagged(tmp.p, tb, count_it, passed.as<uint8_t>(), sel.as<uint32_t>(), nsel.as<uint32_t>(), (int)n32, st));
+            uint32_t next = 0;
+            CUB_(cudaMemcpyAsync(&next, nsel.p, 4, cudaMemcpyDeviceToHost, st));
             CUB_(cudaStreamSynchronize(st));
-            lvl_nblk.push_back(nblk);
-            lvl_base.push_back(total_blk);
-            total_blk += nblk;
+            lvl_nbkt.push_back(nbkt);
+            lvl_base.push_back(total_bkt);
+            total_bkt += nbkt;
+            if (next) {
+                const int dst = src == 1 ? 2 : 1;
+                RC_(key_lo[dst].ensure((uint64_t)next * 8 + 8));
+                if (KW == 2) RC_(key_hi[dst].ensure((uint64_t)next * 8 + 8));
+                RC_(val[dst].ensure((uint64_t)next * 8 + 8));
+                k_dict_gather<<<nblocks(next, 256), 256, 0, st>>>(key_lo[src].as<uint64_t>(), KW == 2 ? key_hi[src].as<uint64_t>() : nullptr,
+                                                                  val[src].as<uint64_t>(), sel.as<uint32_t>(), next,
+                                                                  key_lo[dst].as<uint64_t>(), key_hi[dst].as<uint64_t>(),
+                                                                  val[dst].as<uint64_t>());
+                CUB_(cudaGetLastError());
+                src = dst;
+            }
             rem = next;
-            src = dst;
         }
     }
-    // 3. rank headers
-    if (total_blk) {
-        RC_(cnt.ensure(total_blk * 4));
-        RC_(rank.ensure(total_blk * 8));
-        k_block_counts<<<nblocks(total_blk, 256), 256, 0, st>>>(ix->blocks.as<uint64_t>(), total_blk, cnt.as<uint32_t>());
-        size_t tb = 0;
-        auto in = cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*>(cnt.as<uint32_t>(), CastU64());
-        CUB_(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, rank.as<uint64_t>(), total_blk, st));
-        RC_(tmp.ensure(tb));
-        CUB_(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, rank.as<uint64_t>(), total_blk, st));
-        k_block_headers<<<nblocks(total_blk, 256), 256, 0, st>>>(ix->blocks.as<uint64_t>(), total_blk, rank.as<uint64_t>());
-        CUB_(cudaGetLastError());
+    ix->d.dict.buckets = ix->buckets.as<uint64_t>();
+    ix->d.dict.n_levels = (uint32_t)lvl_nbkt.size();
+    for (size_t i = 0; i < lvl_nbkt.size(); i++) {
+        ix->d.dict.level_nbkt[i] = lvl_nbkt[i];
+        ix->d.dict.level_base[i] = lvl_base[i];
     }
-    ix->d.mphf.blocks = ix->blocks.as<uint64_t>();
-    ix->d.mphf.n_levels = (uint32_t)lvl_nblk.size();
-    for (size_t i = 0; i < lvl_nblk.size(); i++) {
-        ix->d.mphf.level_nblk[i] = lvl_nblk[i];
-        ix->d.mphf.level_base[i] = lvl_base[i];
-    }
-    ix->info.mphf_levels = (uint32_t)lvl_nblk.size();
-    ix->info.mphf_bytes = total_blk * 32;
+    ix->info.dict_levels = (uint32_t)lvl_nbkt.size();
+    ix->info.dict_bytes = total_bkt * 32;
 
-    // 4. values[mphf(kmer)] = (node, offset, fingerprint)
-    RC_(ix->values.ensure(n_kmers * 8 + 8));
-    ix->d.values = ix->values.as<uint64_t>();
+    // 3. self-check (every key resolves to itself), then the successor / predecessor tables
     if (n_kmers)
-        k_fill_values<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(),
-                                                                 val[0].as<uint64_t>(), n_kmers, ix->d,
-                                                                 ix->values.as<uint64_t>(), err.as<uint32_t>());
-    // 5. successor / predecessor tables
+        k_dict_check<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(),
+                                                                 val[0].as<uint64_t>(), n_kmers, ix->d, err.as<uint32_t>());
     if (d->n_nodes)
-        k_build_edges<KW><<<nblocks(d->n_nodes, 128), 128, 0, st>>>(ix->d, ix->nodes.as<NodeRec>(), err.as<uint32_t>());
+        k_build_edges<KW><<<nblocks(d->n_nodes, 128), 128, 0, st>>>(ix->d, ix->nodes.as<NodeRec>(), ix->nodes_cold.as<NodeCold>(),
+                                                                   err.as<uint32_t>());
     CUB_(cudaGetLastError());
     uint32_t e = 0;
     CUB_(cudaMemcpyAsync(&e, err.p, 4, cudaMemcpyDeviceToHost, st));
     CUB_(cudaStreamSynchronize(st));
     cleanup();
-    if (e & 2u) return fail(PSA_ERR_INDEX, "MPHF self-check failed (internal)");
+    if (e & 2u) return fail(PSA_ERR_INDEX, "dictionary self-check failed (internal)");
     if (e & 4u) return fail(PSA_ERR_INDEX, "missing link: an extension bit has no neighbouring node");
     return PSA_OK;
 #undef CUB_
@@ -328,19 +319,13 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
             return bail(fail(PSA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)));           \
         }                                                                                                  \
     } while (0)
-    {
-        auto up = [](size_t x) { return (x + 255) / 256 * 256; };
-        const size_t b_nodes = up((d->n_nodes + 1) * sizeof(NodeRec)), b_seq = up((d->n_seq_words + 2) * 8),
-                     b_win = up((d->n_eq + 1) * sizeof(ClassWin)), b_off = up((d->n_eq + 1) * 8);
-        ix->hot_bytes = b_nodes + b_seq + b_win + b_off;
-        RCI(ix->hot.ensure(ix->hot_bytes));
-        uint8_t* base = ix->hot.as<uint8_t>();
-        ix->nodes.set_view(base, b_nodes);
-        ix->seq.set_view(base + b_nodes, b_seq);
-        ix->class_win.set_view(base + b_nodes + b_seq, b_win);
-        ix->eq_off.set_view(base + b_nodes + b_seq + b_win, b_off);
-    }
-    CUI(cudaMemset(ix->seq.p, 0, (d->n_seq_words + 2) * 8));
+    // (the unitig sequence is padded: the kernels fetch it four words at a time)
+    RCI(ix->nodes.ensure((d->n_nodes + 1) * sizeof(NodeRec)));
+    RCI(ix->nodes_cold.ensure((d->n_nodes + 1) * sizeof(NodeCold)));
+    RCI(ix->seq.ensure((d->n_seq_words + 8) * 8));
+    RCI(ix->class_win.ensure((d->n_eq + 1) * sizeof(ClassWin)));
+    RCI(ix->eq_off.ensure((d->n_eq + 1) * 8));
+    CUI(cudaMemset(ix->seq.p, 0, (d->n_seq_words + 8) * 8));
     if (d->n_seq_words) CUI(cudaMemcpy(ix->seq.p, d->seq_words, d->n_seq_words * 8, cudaMemcpyHostToDevice));
     CUI(cudaMemcpy(ix->eq_off.p, d->eq_offsets, (d->n_eq + 1) * 8, cudaMemcpyHostToDevice));
     RCI(ix->eq_mem.ensure(n_mem * 4 + 4));
@@ -361,13 +346,24 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     DevIndex& D = ix->d;
     D.k = d->k;
     D.node_bits = bits_for(d->n_nodes ? d->n_nodes - 1 : 0);
-    D.pos_bits = bits_for(max_pos);
-    int fp = 64 - (int)D.node_bits - (int)D.pos_bits;
-    D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
+    D.pos_bits = bits_for(max_pos + 1);  // (so that no entry is all ones: that is the empty slot)
+    // a dictionary entry is node | pos | fingerprint in 63 bits; fewer than 8 fingerprint bits would let
+    // absent k-mers through to the verification too often
+    const int fp = 63 - (int)D.node_bits - (int)D.pos_bits;
+    if (fp < 8) {
+        rel();
+        return bail(fail(PSA_ERR_INDEX, "graph too large for 64-bit dictionary entries (node bits + position bits > 55)"));
+    }
+    if (n_kmers >= 0xFFFFFFFFull) {
+        rel();
+        return bail(fail(PSA_ERR_INDEX, "too many k-mers (the dictionary build indexes them with 32 bits)"));
+    }
+    D.fp_bits = (uint32_t)std::min(fp, 32);
     D.n_nodes = d->n_nodes;
     D.n_kmers = n_kmers;
     D.n_eq = d->n_eq;
     D.nodes = ix->nodes.as<NodeRec>();
+    D.nodes_cold = ix->nodes_cold.as<NodeCold>();
     D.seq = ix->seq.as<uint64_t>();
     D.eq_off = ix->eq_off.as<uint64_t>();
     D.eq_mem = ix->eq_mem.as<uint32_t>();
@@ -378,14 +374,24 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     CUI(cudaEventCreate(&e1));
     CUI(cudaEventRecord(e0, 0));
     if (d->n_nodes)
-        k_node_basics<<<nblocks(d->n_nodes, 256), 256>>>(ix->nodes.as<NodeRec>(), d->n_nodes, node_start.as<uint64_t>(),
+        k_node_basics<<<nblocks(d->n_nodes, 256), 256>>>(ix->nodes.as<NodeRec>(), ix->nodes_cold.as<NodeCold>(), d->n_nodes, node_start.as<uint64_t>(),
                                                          node_len.as<uint32_t>(), node_exts.as<uint8_t>(),
                                                          node_eq.as<uint32_t>(), ix->eq_off.as<uint64_t>(), d->n_eq,
                                                          d->k, err.as<uint32_t>());
     if (d->n_eq)
         k_build_class_win<<<nblocks(d->n_eq, 256), 256>>>(ix->eq_off.as<uint64_t>(), ix->eq_mem.as<uint32_t>(), d->n_eq,
                                                           ix->class_win.as<ClassWin>());
+    if (d->n_nodes)
+        k_node_windows<<<nblocks(d->n_nodes, 256), 256>>>(ix->nodes.as<NodeRec>(), d->n_nodes, d->n_eq, ix->class_win.as<ClassWin>());
     CUI(cudaGetLastError());
+    {
+        uint32_t e = 0;
+        CUI(cudaMemcpy(&e, err.p, 4, cudaMemcpyDeviceToHost));
+        if (e) {
+            rel();
+            return bail(fail(PSA_ERR_INDEX, "invalid node table"));
+        }
+    }
     if (ix->kw == 1) RCI(build_on_device<1>(ix, d, gamma, node_start, koff, n_kmers));
     else RCI(build_on_device<2>(ix, d, gamma, node_start, koff, n_kmers));
     CUI(cudaEventRecord(e1, 0));
@@ -405,8 +411,7 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     I.n_eq = d->n_eq;
     I.n_eq_members = n_mem;
     I.n_seq_words = d->n_seq_words;
-    I.values_bytes = n_kmers * 8;
-    I.node_bytes = d->n_nodes * sizeof(NodeRec);
+    I.node_bytes = d->n_nodes * (sizeof(NodeRec) + sizeof(NodeCold));
     I.seq_bytes = d->n_seq_words * 8;
     I.eq_bytes = (d->n_eq + 1) * 8 + n_mem * 4 + d->n_eq * sizeof(ClassWin);
     I.node_bits = D.node_bits;
@@ -422,9 +427,8 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
 extern "C" void psa_index_destroy(psa_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    ix->blocks.release(); ix->values.release(); ix->nodes.release();
-    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release(); ix->bloom.release();
-    ix->hot.release();
+    ix->buckets.release(); ix->nodes.release(); ix->nodes_cold.release();
+    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
     delete ix;
 }
 
@@ -489,46 +493,37 @@ struct psa_mapper {
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
-    bool l2_window = false;     // PSA_L2_WINDOW=1: persisting L2 window over the index's hot tables (measured slower)
     bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
-    bool tile_reads = true;     // PSA_TILE=0: k_map_thread reads the packed reads through L1 instead of staging the CTA's
-                                // reads of a fixed-stride batch in shared memory with one bulk copy (TMA); with 64-thread
-                                // CTAs the staging is 2.4 % faster (it was 2 % slower with 128-thread CTAs)
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[kSlots];
     uint64_t launches = 0;
     // map-kernel timing (psa_mapper_profile_*)
     bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];  // [0] k_map_thread, [1] k_map, [2] k_seed_scan
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];  // [0] k_map_lanes, [1] k_map, [2] k_seed_scan
     // pending async call
     psa_result_batch* pending = nullptr;
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
 
-// shared memory of the TILE variant (packed words of 128 reads + the mbarrier), 0 = not eligible
-static uint32_t tile_smem_bytes(const ReadsView& rv) {
-    if (rv.woff || rv.len || !rv.wstride) return 0;
-    const uint64_t total = 16 + (uint64_t)kThreadBlock * rv.wstride * 8;
-    return total > 12 * 1024 ? 0 : (uint32_t)total;  // longer reads keep the L1 for the index instead
+// the lane kernel: persistent warps, one resident wave.  hint: the reads of p.seeded (second pass)
+static int lanes_grid(psa_mapper* m, uint64_t n) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->ix->device);
+    const uint64_t full = (uint64_t)sms * PSA_LANE_MIN_BLOCKS;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(nblocks(n, kLaneBlock), full));
 }
 template <bool EV>
-static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p, uint32_t smem) {
-    const unsigned grid = nblocks(p.reads.n, kThreadBlock);
-    if (smem) {
-        if (m->ix->kw == 1) k_map_thread<1, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
-        else k_map_thread<2, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
+static void launch_map_lanes(psa_mapper* m, cudaStream_t st, const MapParams& p, bool hint) {
+    const unsigned grid = (unsigned)lanes_grid(m, p.reads.n);
+    const size_t smem = (size_t)kLaneBlock * p.lane_words * 8;
+    if (m->ix->kw == 1) {
+        if (hint) k_map_lanes<1, EV, true><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
+        else k_map_lanes<1, EV, false><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
     } else {
-        if (m->ix->kw == 1) k_map_thread<1, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
-        else k_map_thread<2, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        if (hint) k_map_lanes<2, EV, true><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
+        else k_map_lanes<2, EV, false><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
     }
-}
-// second pass over the reads k_seed_scan seeded: persistent warps, the list length is on the device
-template <bool EV>
-static void launch_map_thread_seeded(psa_mapper* m, cudaStream_t st, const MapParams& p) {
-    const unsigned grid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n, kThreadBlock), 148 * PSA_THREAD_MIN_BLOCKS);
-    if (m->ix->kw == 1) k_map_thread<1, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
-    else k_map_thread<2, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
 }
 template <bool EV>
 static void launch_seed_scan(psa_mapper* m, cudaStream_t st, const MapParams& p) {
@@ -625,33 +620,6 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     cudaMemset(m->counts.p, 0, nc * 8);
     cudaMemset(m->events.p, 0, 40 * 8);
     cudaMemset(m->status.p, 0, 8);
-    // PSA_L2_WINDOW=1: a persisting L2 access-policy window over the index's small hot tables on the mapper's
-    // stream.  Measured on B200 (config 3): 83 MB carve-out 3.55 ms vs 3.06 ms without, 48 MB 3.12, 16 MB 3.06 --
-    // what the window keeps is paid for by the MPHF / values / read traffic it squeezes.  Off by default.
-    if (const char* e = getenv("PSA_L2_WINDOW")) m->l2_window = atoi(e) != 0;
-    if (m->l2_window && ix->hot_bytes) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ix->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ix->device);
-        if (const char* e = getenv("PSA_L2_PERSIST_MB")) max_persist = std::min(max_persist, atoi(e) << 20);
-        if (max_persist > 0 && max_window > 0) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-            cudaStreamAttrValue attr{};
-            attr.accessPolicyWindow.base_ptr = ix->hot.p;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(ix->hot_bytes, (size_t)max_window);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)attr.accessPolicyWindow.num_bytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-            if (cudaStreamSetAttribute(m->st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
-            if (getenv("PSA_VERBOSE"))
-                fprintf(stderr, "psa: L2 window %.1f MB of hot tables, persisting L2 max %.1f MB, window max %.1f MB, hit ratio %.2f\n",
-                        ix->hot_bytes / 1e6, max_persist / 1e6, max_window / 1e6, attr.accessPolicyWindow.hitRatio);
-        }
-    }
-    // PSA_L2_FETCH=32|64|128: device-wide hint for the granularity of L2 fills from HBM (experiment knob)
-    if (const char* e = getenv("PSA_L2_FETCH")) {
-        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)) != cudaSuccess) (void)cudaGetLastError();
-    }
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
         int g = atoi(e);
         if (g == 8 || g == 16 || g == 32) m->group = (uint32_t)g;
@@ -661,7 +629,6 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     m->fast_probes = (ix->d.k + 2) / 3 + 2;
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
-    if (const char* e = getenv("PSA_TILE")) m->tile_reads = atoi(e) != 0;
     if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
         int g = atoi(e);
@@ -787,6 +754,8 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             const uint32_t smem = (uint32_t)(16 + tile_bytes + 48 + 16);
             k_pack_ascii_tile<<<nblocks(n, kPackTileReads), kPackTileReads, smem, st>>>(
                 (const uint8_t*)r->data, (uint32_t)r->stride, r->fixed_len, n, m->words.as<uint64_t>(), (uint32_t)tile_bytes);
+        } else if (!r->read_len && !r->read_off && rv.wstride == 0) {
+            // fixed_len == 0: nothing to pack (every read is None, ref src/pseudoaligner.rs:82-84)
         } else if (!r->read_len && !r->read_off) {
             // 32-bit word indices inside the kernel: slices of at most 2^31 words
             const uint64_t per = std::max<uint64_t>(1, (1ull << 31) / rv.wstride);
@@ -808,7 +777,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -861,11 +830,15 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 p.seeded_count = m->novel_cursor.as<unsigned long long>() + 4;
                 p.seeded_ev = EV ? m->seeded_ev.as<uint4>() : nullptr;
             }
-            const uint32_t tile_smem = m->tile_reads ? tile_smem_bytes(rv) : 0;
-            if ((rc = timed(0, [&]() { launch_map_thread<EV>(m, st, p, tile_smem); }))) return rc;
+            p.lane_cursor = m->novel_cursor.as<unsigned long long>() + 6;
+            {   // a lane's shared-memory slot holds the longest read of a fixed-length batch, 256 bases at most
+                const uint64_t nw = r->read_len ? kLaneMaxWords : ((uint64_t)r->fixed_len + 31) / 32;
+                p.lane_words = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nw, 1), kLaneMaxWords);
+            }
+            if ((rc = timed(0, [&]() { launch_map_lanes<EV>(m, st, p, false); }))) return rc;
             if (m->scan_width) {
                 if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
-                if ((rc = timed(0, [&]() { launch_map_thread_seeded<EV>(m, st, p); }))) return rc;
+                if ((rc = timed(0, [&]() { launch_map_lanes<EV>(m, st, p, true); }))) return rc;
             }
         }
         if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, st, p); }))) return rc;
@@ -882,13 +855,8 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         CU(cub::DeviceScan::ExclusiveSum(m->scan_tmp.p, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
     }
     if (n) {
-#if PSA_EXPAND_BALANCED
         k_expand_balanced<<<nblocks(n, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
-                                                           ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
-#else
-        k_expand<<<nblocks(n * PSA_EXPAND_LANES, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
-                                                      ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
-#endif
+                                                           ix->d.eq_off, ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
     }
     k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
                                 m->status.as<uint32_t>(), b.meta_out, b.sticky ? m->status.as<uint32_t>() + 1 : nullptr);
@@ -1365,6 +1333,21 @@ extern "C" int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk
     table.release();
     sink.release();
     *gbytes_per_s = (double)grid * block * iters * (chunk_bytes ? chunk_bytes : 4) / (best / 1e3) / 1e9;
+    return PSA_OK;
+}
+
+extern "C" int psa_result_checksum(int device, const psa_hit* hits_dev, const uint32_t* tx_dev, uint64_t n,
+                                   uint64_t first_index, uint64_t* out) {
+    if (!out || (n && (!hits_dev || !tx_dev))) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    DevBuf acc;
+    int rc = acc.ensure(8);
+    if (rc) return rc;
+    cudaMemset(acc.p, 0, 8);
+    if (n) k_result_checksum<<<nblocks(n, 256), 256>>>((const HitRec*)hits_dev, tx_dev, n, first_index, 0, acc.as<unsigned long long>());
+    cudaError_t e = cudaMemcpy(out, acc.p, 8, cudaMemcpyDeviceToHost);
+    acc.release();
+    if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
     return PSA_OK;
 }
 

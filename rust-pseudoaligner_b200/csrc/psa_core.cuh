@@ -1,22 +1,25 @@
 // psa_core.cuh -- arithmetic of the pseudoalignment hot path, shared by every kernel.
 //
 // Everything here is scalar __host__ __device__ code: 2-bit sequence access, the k-mer hash,
-// the sector-block minimal perfect hash probe, the `values` packing, the k-mer verification,
-// the per-word mismatch masks of the two extension loops and the map_read state machine
-// (templated on a "warp" policy that supplies the cooperative steps).  The CUDA kernels in
-// psa_kernels.cu instantiate it with warp-shuffle policies; tests/hostsim instantiates the
-// same text with a serial policy so that the state machine and the hash layout are checked
-// against the oracle on machines without a GPU.  That host instantiation is a unit-test
-// harness only -- the product library (psa_api.cu) has no CPU path.
+// the bucket-cascade k-mer dictionary, the k-mer verification, the per-word mismatch masks of
+// the two extension loops, the class-window intersection and the map_read state machine in its
+// blocking form (templated on a policy that supplies the loads; used by the cooperative kernels).
+// psa_lanes.cuh holds the same state machine cut at every load (the thread-per-read kernel).
+// The CUDA kernels in psa_kernels.cuh instantiate this text; tests/hostsim instantiates the same
+// text with serial policies so that it is checked against the oracle on machines without a GPU.
+// That host instantiation is a unit-test harness only -- the product library (psa_api.cu) has
+// no CPU path.
 //
 // Reference being restated: 10XGenomics/rust-pseudoaligner @ 9d9cab8
 //   src/pseudoaligner.rs:64-319   map_read_to_nodes_with_mismatch   -> map_read_nodes()
 //   src/pseudoaligner.rs:91-114   find_kmer_match                   -> W::find_seed + dict_get()
-//   src/pseudoaligner.rs:99-107   MPHF answer verification          -> dict_get()
+//   src/pseudoaligner.rs:99-107   dictionary answer verification    -> dict_get()
+//   src/pseudoaligner.rs:323-356  nodes_to_eq_class                 -> ClassAcc
 //   src/config.rs:16-18           constants
 // and, from the un-vendored crates (published algorithms, see oracle/psa_oracle.h):
-//   debruijn DnaString packing / get_kmer, boomphf Mphf::try_hash (structure only: cascaded
-//   bit-vectors + rank; hash function, block layout and fingerprints are this project's own).
+//   debruijn DnaString packing / get_kmer; boomphf's NoKeyBoomHashMap::get is replaced by an
+//   exact k-mer -> (node, position) dictionary of this project's own design (any exact dictionary
+//   gives the reference's output because every answer is verified against the unitig).
 #pragma once
 #include <stdint.h>
 
@@ -24,9 +27,6 @@
 #define PSA_HD __host__ __device__ __forceinline__
 #else
 #define PSA_HD inline
-#endif
-#ifndef PSA_TWO_AHEAD
-#define PSA_TWO_AHEAD 0
 #endif
 #if defined(__CUDA_ARCH__)
 #define PSA_UNROLL _Pragma("unroll")
@@ -37,8 +37,7 @@
 namespace psa {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kMaxLevels = 48;        // MPHF cascade depth cap (1e8 keys need ~25 at gamma 1.7)
-constexpr uint32_t kBlockBits = 192;  // 3 data words per 32-byte block; word 0 is the rank header
+constexpr int kMaxLevels = 32;        // dictionary cascade depth cap (1e8 keys need ~9 at 1.7 slots per key)
 constexpr uint32_t kSeedStride = 3;   // ref src/pseudoaligner.rs:110
 constexpr uint32_t kCoverageThreshold = 32;  // ref src/config.rs:16
 constexpr double kLeftExtendFraction = 0.2;  // ref src/config.rs:17
@@ -82,15 +81,12 @@ PSA_HD uint64_t mix64(uint64_t x) {  // murmur3 finaliser (a bijection on 64 bit
 }
 
 // ---------------------------------------------------------------------------------------------
-// word loaders: the same text reads the index through the read-only path on the device
+// loaders: the same text reads the index through the read-only path on the device
 // ---------------------------------------------------------------------------------------------
-// L2 residency hints (PSA_L2_HINTS): the big single-use table (`values`, 8 bytes used per 32-byte
-// sector, no reuse) is loaded evict-first so that it does not push the small hot tables (node
-// records, unitig sequence, class windows) out of the 126 MB L2; those are loaded evict-last.
-#ifndef PSA_L2_HINTS
-#define PSA_L2_HINTS 1
-#endif
-#if defined(__CUDA_ARCH__) && PSA_L2_HINTS
+// L2 residency hints: the dictionary (one use per sector, no reuse, 10x the size of L2) is loaded
+// evict-first and kept out of L1 so that it does not push the small hot tables (node records,
+// unitig sequence) out of the 126 MB L2; those are loaded evict-last.
+#if defined(__CUDACC__)
 __device__ __forceinline__ uint64_t l2_policy_first() {
     uint64_t p;
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -101,11 +97,6 @@ __device__ __forceinline__ uint64_t l2_policy_last() {
     asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t ld_u64_first(const uint64_t* a) {
-    uint64_t v;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(l2_policy_first()));
-    return v;
-}
 __device__ __forceinline__ uint64_t ld_u64_last(const uint64_t* a) {
     uint64_t v;
     asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(l2_policy_last()));
@@ -115,26 +106,37 @@ __device__ __forceinline__ void ld_v4_last(const void* a, uint64_t& x, uint64_t&
     asm("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
         : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(a), "l"(l2_policy_last()));
 }
-#elif defined(__CUDA_ARCH__)
-__device__ __forceinline__ uint64_t ld_u64_first(const uint64_t* a) { return __ldg(a); }
-__device__ __forceinline__ uint64_t ld_u64_last(const uint64_t* a) { return __ldg(a); }
-__device__ __forceinline__ void ld_v4_last(const void* a, uint64_t& x, uint64_t& y, uint64_t& z, uint64_t& w) {
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(a));
+__device__ __forceinline__ void ld_v4_first(const void* a, uint64_t& x, uint64_t& y, uint64_t& z, uint64_t& w) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(x), "=l"(y), "=l"(z), "=l"(w) : "l"(a), "l"(l2_policy_first()));
 }
 #endif
 
-#ifndef PSA_PF_SUCC
-#define PSA_PF_SUCC 0   // thread-per-read walk: prefetch the successor's node record before the compare
-#endif
-#ifndef PSA_PF_SPAN
-#define PSA_PF_SPAN 0   // thread-per-read walk: prefetch the last sector of the unitig span before the compare
-#endif
-PSA_HD void prefetch_l2(const void* a) {
+// one 32-byte sector (LDG.E.256 on the device) as four named words: never indexed dynamically,
+// so that it stays in registers
+struct Sector {
+    uint64_t w0, w1, w2, w3;
+};
+PSA_HD uint64_t sector_word(const Sector& s, uint32_t i) { return i == 0 ? s.w0 : i == 1 ? s.w1 : i == 2 ? s.w2 : s.w3; }
+PSA_HD Sector load_sector_hot(const void* p) {  // node records, class windows: reused across reads
+    Sector s;
 #ifdef __CUDA_ARCH__
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    ld_v4_last(p, s.w0, s.w1, s.w2, s.w3);
 #else
-    (void)a;
+    const uint64_t* q = static_cast<const uint64_t*>(p);
+    s.w0 = q[0]; s.w1 = q[1]; s.w2 = q[2]; s.w3 = q[3];
 #endif
+    return s;
+}
+PSA_HD Sector load_sector_stream(const void* p) {  // dictionary buckets: one use
+    Sector s;
+#ifdef __CUDA_ARCH__
+    ld_v4_first(p, s.w0, s.w1, s.w2, s.w3);
+#else
+    const uint64_t* q = static_cast<const uint64_t*>(p);
+    s.w0 = q[0]; s.w1 = q[1]; s.w2 = q[2]; s.w3 = q[3];
+#endif
+    return s;
 }
 
 struct GLoad {  // immutable index memory (global, ld.global.nc): the unitig sequence
@@ -147,26 +149,19 @@ struct GLoad {  // immutable index memory (global, ld.global.nc): the unitig seq
 #endif
     }
 };
-struct PLoad {  // plain pointer (shared memory tile or global read buffer)
+struct PLoad {  // plain pointer (global read buffer, host memory)
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const { return p[i]; }
 };
-#ifndef PSA_READS_EVICT_LAST
-#define PSA_READS_EVICT_LAST 0   // experiment: the reads' packed words keep L2 priority while their read is in flight
-#endif
-struct RLoad {  // the packed words of the reads (global): touched ~10 times over a read's life
+struct SLoad {  // strided words: the shared-memory slot of one lane, word j at p[j * stride]
     const uint64_t* p;
-    PSA_HD uint64_t operator()(uint64_t i) const {
-#if defined(__CUDA_ARCH__) && PSA_READS_EVICT_LAST && PSA_L2_HINTS
-        return ld_u64_last(p + i);
-#else
-        return p[i];
-#endif
-    }
+    uint32_t stride;
+    PSA_HD uint64_t operator()(uint64_t i) const { return p[i * stride]; }
 };
-struct RegLoad6 {  // a read of at most 192 bases held in registers (selected, never indexed)
-    uint64_t w0, w1, w2, w3, w4, w5;
-    PSA_HD uint64_t operator()(uint64_t i) const { return i == 0 ? w0 : i == 1 ? w1 : i == 2 ? w2 : i == 3 ? w3 : i == 4 ? w4 : w5; }
+struct WLoad {  // four consecutive words held in registers, the first one being word `base`
+    Sector s;
+    uint64_t base;
+    PSA_HD uint64_t operator()(uint64_t i) const { return sector_word(s, (uint32_t)(i - base)); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -266,67 +261,75 @@ struct KmerOps<2> {
         return r;
     }
 };
-
 // ---------------------------------------------------------------------------------------------
 // The index as the kernels see it (all pointers device memory, immutable)
 // ---------------------------------------------------------------------------------------------
-// 64 bytes in two 32-byte sectors.  Sector 0 is all the forward walk needs (one LDG.E.256 per
-// node visit: sequence, class, successors); sector 1 is read only by the left extension, the
-// cooperative kernel's class list and the index self-checks.
+// 64 bytes in two 32-byte sectors, both fetched at every node visit (adjacent: one DRAM row).
+// Sector 0 is the node itself -- sequence span, class, all four successors (the reference does up
+// to 4 binary searches over all nodes per jump, ref src/pseudoaligner.rs:275).  Sector 1 is the
+// window of the node's class (see "Class windows"): the intersection needs nothing else for a
+// narrow class, so nodes_to_eq_class costs no gather of its own.
 struct NodeRec {
     uint64_t start_len;  // first base in the concatenated sequence (low 40 bits) | bases << 40
     uint32_t eq;         // equivalence-class id (*node.data())
     uint32_t class_len;  // |eq_classes[eq]|
     uint32_t succ[4];    // node reached by right extension b (kNone if the ext bit is clear)
+    uint32_t win_lo;     // ClassWin of eq
+    uint32_t win_len;
+    uint64_t win_bits[3];
+};
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte line");
+// Read only by the left extension (ref :183-196) and the index self-checks.
+struct NodeCold {
     uint32_t pred[4];    // node reached by left extension b
     uint32_t exts;       // debruijn Exts byte
     uint32_t pad;
     uint64_t class_off;  // eq_classes[eq] starts at eq_mem[class_off]
 };
-static_assert(sizeof(NodeRec) == 64, "NodeRec must be one 64-byte line");
+static_assert(sizeof(NodeCold) == 32, "NodeCold must be one 32-byte sector");
 constexpr uint64_t kStartMask = (1ULL << 40) - 1;
 constexpr uint32_t kMaxNodeLen = (1u << 24) - 1;
 PSA_HD uint64_t pack_start_len(uint64_t start, uint32_t len) { return start | ((uint64_t)len << 40); }
 
-struct Mphf {
-    const uint64_t* blocks;  // 4 words per block: [rank:48 | c1:7 | c2:8] w1 w2 w3
+// k-mer dictionary: dbg_index of the reference (NoKeyBoomHashMap<K, (u32, u32)>, ref
+// src/pseudoaligner.rs:31, built at src/build_index.rs:182-221) as a cascade of bucket tables.
+// A bucket is one 32-byte sector of four 64-bit entries
+//     entry = node | pos << node_bits | fingerprint << (node_bits + pos_bits)   (bit 63 clear)
+// (pos = absolute base position of the k-mer in `seq`); unused entries are all ones.  A key lives in
+// the first level whose bucket had room for it and no entry with the same fingerprint; bit 63 of
+// entry 0 says that some key of this bucket was passed on to the next level.  So a probe is ONE
+// sector for ~94 % of the present keys and ~91 % of the absent ones (1.7 slots per key), a
+// fingerprint matches at most one entry of a bucket, and a matching entry is verified against the
+// unitig exactly as the reference verifies its MPHF's answer (ref :99-107) -- dictionary membership
+// is exact.  (boomphf needs ~1.8 bit-vector words + a rank + the `values` entry per present key and
+// ~3 levels + a false-positive `values` entry per absent one; round 1 of this project did the same
+// with 32-byte blocks and paid 2.8 / 4 sectors.)
+constexpr uint64_t kEmptyEntry = ~0ULL;
+constexpr uint64_t kMoreBit = 1ULL << 63;
+constexpr uint32_t kBucketSlots = 4;
+struct Dict {
+    const uint64_t* buckets;  // 4 words per bucket
     uint32_t n_levels;
     uint32_t pad;
-    uint64_t level_nblk[kMaxLevels];
-    uint64_t level_base[kMaxLevels];  // first block of the level
+    uint64_t level_nbkt[kMaxLevels];  // buckets of the level (< 2^32)
+    uint64_t level_base[kMaxLevels];  // first bucket of the level
 };
-
-// Absent-key prefilter: a split-block Bloom filter over every k-mer of the graph.  One 32-byte
-// block per key, one bit in each of its eight 32-bit words.  No false negatives, so consulting it
-// before the MPHF never changes dict_get's answer; it lets a seed scan drop an absent k-mer after
-// one sector instead of ~3 MPHF levels + the `values` sector.  (Not part of the reference: boomphf
-// has nothing comparable; it pays off because unmappable reads probe 43 absent k-mers each.)
-struct Bloom {
-    const uint32_t* words;  // 8 per block; nullptr = no filter
-    uint64_t n_blocks;
-};
-#ifndef PSA_BLOOM_BITS
-#define PSA_BLOOM_BITS 12
-#endif
-constexpr uint32_t kBloomBitsPerKey = PSA_BLOOM_BITS;
 
 struct DevIndex {
     uint32_t k;
-    uint32_t node_bits, pos_bits, fp_bits;  // `values` entry = node | pos << node_bits | fp << (node_bits+pos_bits),
-                                            // pos = absolute base position of the k-mer in `seq`
+    uint32_t node_bits, pos_bits, fp_bits;  // dictionary entry layout
     uint64_t n_nodes, n_kmers, n_eq;
-    const uint64_t* values;
     const NodeRec* nodes;
+    const NodeCold* nodes_cold;
     const uint64_t* seq;
     const uint64_t* eq_off;
     const uint32_t* eq_mem;
-    const struct ClassWin* class_win;  // one 32-byte window per class (see below)
-    Bloom bloom;
-    Mphf mphf;
+    const struct ClassWin* class_win;  // one 32-byte window per class (cooperative kernel, wide classes)
+    Dict dict;
 };
 
-// Two 64-bit hashes per k-mer, computed once; level l probes h1 + l*h2 (double hashing, as
-// in BBHash), the fingerprint is the top bits of h2.
+// Two 64-bit hashes per k-mer, computed once; level l probes h1 + l*h2 (double hashing), the
+// fingerprint is the top bits of h2.
 struct KeyHash {
     uint64_t h1, h2;
 };
@@ -339,155 +342,69 @@ PSA_HD KeyHash make_hash(uint64_t folded) {
 }
 PSA_HD uint64_t level_hash(KeyHash kh, uint32_t lvl) { return kh.h1 + (uint64_t)lvl * kh.h2; }
 PSA_HD uint64_t fp_of(KeyHash kh, uint32_t fp_bits) { return kh.h2 >> (64 - fp_bits); }
-
-// Bloom position of a key: block, and eight 5-bit in-word positions packed in `bits`
-PSA_HD void bloom_pos(KeyHash kh, uint64_t n_blocks, uint64_t& blk, uint64_t& bits) {
-    const uint64_t g = kh.h1 * 0x9E3779B97F4A7C15ULL + kh.h2;
-    blk = mulhi64(g, n_blocks);
-    bits = g * 0xD6E8FEB86659FD93ULL >> 24;  // 40 bits
+// bucket of a key at a level; nbkt < 2^32
+PSA_HD uint64_t level_bucket(KeyHash kh, uint32_t lvl, uint64_t nbkt) {
+    return ((level_hash(kh, lvl) >> 32) * (uint64_t)(uint32_t)nbkt) >> 32;
 }
-PSA_HD bool bloom_maybe(const Bloom& b, KeyHash kh) {
-    uint64_t blk, bits;
-    bloom_pos(kh, b.n_blocks, blk, bits);
-    uint32_t w[8];
-#ifdef __CUDA_ARCH__
-    const uint4* p = reinterpret_cast<const uint4*>(b.words + 8 * blk);
-    const uint4 lo = __ldg(p), hi = __ldg(p + 1);
-    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
-#else
-    for (int i = 0; i < 8; i++) w[i] = b.words[8 * blk + i];
-#endif
-    uint32_t all = 1;
-    PSA_UNROLL
-    for (int i = 0; i < 8; i++) all &= w[i] >> ((bits >> (5 * i)) & 31);
-    return all & 1;
+PSA_HD const uint64_t* bucket_addr(const Dict& d, KeyHash kh, uint32_t lvl) {
+    return d.buckets + 4 * (d.level_base[lvl] + level_bucket(kh, lvl, d.level_nbkt[lvl]));
 }
-
-// position of a key at a level: (block within level, bit 0..191 within block); nblk < 2^32
-PSA_HD void level_pos(uint64_t h, uint64_t nblk, uint64_t& blk, uint32_t& bit) {
-    blk = ((h >> 32) * (uint64_t)(uint32_t)nblk) >> 32;
-    bit = (uint32_t)(((h & 0xffffffffULL) * kBlockBits) >> 32);
+PSA_HD uint64_t pack_entry(const DevIndex& ix, uint32_t node, uint64_t pos, KeyHash hk) {
+    return (uint64_t)node | (pos << ix.node_bits) | (fp_of(hk, ix.fp_bits) << (ix.node_bits + ix.pos_bits));
 }
-
-struct Block {  // named words, never indexed dynamically: the block must stay in registers
-    uint64_t hdr, w1, w2, w3;
-};
-PSA_HD Block load_block(const uint64_t* blocks, uint64_t b) {
-    Block r;
-#ifdef __CUDA_ARCH__
-    // one 32-byte sector per probe: header + 3 bit-vector words (LDG.E.256)
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
-        : "=l"(r.hdr), "=l"(r.w1), "=l"(r.w2), "=l"(r.w3)
-        : "l"(blocks + 4 * b));
-#else
-    r.hdr = blocks[4 * b]; r.w1 = blocks[4 * b + 1]; r.w2 = blocks[4 * b + 2]; r.w3 = blocks[4 * b + 3];
-#endif
+PSA_HD uint32_t entry_node(const DevIndex& ix, uint64_t e) { return (uint32_t)(e & ((1ULL << ix.node_bits) - 1)); }
+PSA_HD uint64_t entry_pos(const DevIndex& ix, uint64_t e) { return (e >> ix.node_bits) & ((1ULL << ix.pos_bits) - 1); }
+// the entry of bucket b that carries hk's fingerprint (at most one by construction), or kEmptyEntry
+PSA_HD uint64_t bucket_find(const DevIndex& ix, const Sector& b, KeyHash hk) {
+    const uint32_t shift = ix.node_bits + ix.pos_bits;
+    const uint64_t mask = ((1ULL << ix.fp_bits) - 1) << shift;
+    const uint64_t want = fp_of(hk, ix.fp_bits) << shift;
+    uint64_t r = kEmptyEntry;
+    if (((b.w0 ^ want) & mask) == 0 && b.w0 != kEmptyEntry) r = b.w0 & ~kMoreBit;
+    if (((b.w1 ^ want) & mask) == 0 && b.w1 != kEmptyEntry) r = b.w1;
+    if (((b.w2 ^ want) & mask) == 0 && b.w2 != kEmptyEntry) r = b.w2;
+    if (((b.w3 ^ want) & mask) == 0 && b.w3 != kEmptyEntry) r = b.w3;
     return r;
 }
-PSA_HD uint64_t block_word(const Block& b, uint32_t wi) { return wi == 0 ? b.w1 : wi == 1 ? b.w2 : b.w3; }
-constexpr uint64_t kRankMask = (1ULL << 48) - 1;
-PSA_HD uint64_t make_header(uint64_t rank, uint32_t c1, uint32_t c2) {
-    return rank | ((uint64_t)c1 << 48) | ((uint64_t)c2 << 55);
-}
-// rank of bit `bit` of a block whose bit is set = number of set bits before it in the cascade
-PSA_HD uint64_t block_rank(const Block& b, uint32_t bit) {
-    uint32_t wi = bit >> 6, bi = bit & 63;
-    uint64_t hdr = b.hdr;
-    uint64_t r = hdr & kRankMask;
-    r += wi == 0 ? 0 : wi == 1 ? ((hdr >> 48) & 0x7f) : ((hdr >> 55) & 0xff);
-    r += (uint64_t)popc64(block_word(b, wi) & ((1ULL << bi) - 1));
-    return r;
-}
+// true if a key that hashes to this bucket may live in a later level
+PSA_HD bool bucket_more(const Sector& b) { return b.w0 != kEmptyEntry && (b.w0 & kMoreBit) != 0; }
 
 struct ProbeStats {  // sequential-equivalent event counts of one dictionary probe
     uint32_t levels, hit, verified;
 };
 
-// Mphf::try_hash: cascade of bit-vectors; the first level whose bit is set gives the slot.
-// two_ahead: fetch the blocks of levels 0 and 1 together (a likely-present key resolves at level
-// 0 with p ~ 0.55 and at level 1 with p ~ 0.25: one round trip instead of two for the latter, at
-// the price of one extra sector for the former).  `levels` stays the sequential count.
-// Measured on B200 (config 3): k_map_thread 3.74 ms with it, 3.40 ms without -- the kernel is
-// bound by the random-sector rate of HBM, not by the length of the dependent chain, so the extra
-// sector costs more than the saved round trip.  Kept for reference, off (PSA_TWO_AHEAD=0).
-PSA_HD bool mphf_lookup(const Mphf& m, KeyHash hk, uint64_t& slot, uint32_t& levels, bool two_ahead = false) {
-    levels = 0;
-    uint32_t lvl = 0;
-    if (two_ahead && m.n_levels >= 2) {
-        uint64_t blk0, blk1;
-        uint32_t bit0, bit1;
-        level_pos(level_hash(hk, 0), m.level_nblk[0], blk0, bit0);
-        level_pos(level_hash(hk, 1), m.level_nblk[1], blk1, bit1);
-        const Block b0 = load_block(m.blocks, m.level_base[0] + blk0);
-        const Block b1 = load_block(m.blocks, m.level_base[1] + blk1);
-        levels = 1;
-        if ((block_word(b0, bit0 >> 6) >> (bit0 & 63)) & 1) {
-            slot = block_rank(b0, bit0);
-            return true;
+// dbg_index.get(kmer) followed by the reference's verification (src/pseudoaligner.rs:96-107), in
+// its blocking form (cooperative kernels, index construction).  A fingerprint mismatch proves that
+// the entry's key differs from `key`, so skipping its unitig fetch cannot change the outcome of
+// the reference's `read_kmer == ref_kmer` test.
+template <int KW>
+PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st) {
+    const KeyHash hk = make_hash(KmerOps<KW>::fold(key));
+    if (st) { st->levels = 0; st->hit = 0; st->verified = 0; }
+    for (uint32_t lvl = 0; lvl < ix.dict.n_levels; lvl++) {
+        const Sector b = load_sector_stream(bucket_addr(ix.dict, hk, lvl));
+        if (st) st->levels++;
+        const uint64_t e = bucket_find(ix, b, hk);
+        if (e != kEmptyEntry) {
+            const uint32_t n = entry_node(ix, e);
+            const uint64_t pos = entry_pos(ix, e);
+            if (st) { st->hit++; st->verified++; }
+            // the unitig k-mer and the node's start are independent loads: both addresses come from the entry
+#ifdef __CUDA_ARCH__
+            const uint64_t start = ld_u64_last(&ix.nodes[n].start_len) & kStartMask;
+#else
+            const uint64_t start = ix.nodes[n].start_len & kStartMask;
+#endif
+            const Kmer<KW> ref = KmerOps<KW>::get(GLoad{ix.seq}, pos, ix.k);
+            if (ref == key) {
+                node = n;
+                off = (uint32_t)(pos - start);
+                return true;
+            }
         }
-        levels = 2;
-        if ((block_word(b1, bit1 >> 6) >> (bit1 & 63)) & 1) {
-            slot = block_rank(b1, bit1);
-            return true;
-        }
-        lvl = 2;
-    }
-    for (; lvl < m.n_levels; lvl++) {
-        uint64_t blk;
-        uint32_t bit;
-        level_pos(level_hash(hk, lvl), m.level_nblk[lvl], blk, bit);
-        Block b = load_block(m.blocks, m.level_base[lvl] + blk);
-        levels++;
-        if ((block_word(b, bit >> 6) >> (bit & 63)) & 1) {
-            slot = block_rank(b, bit);
-            return true;
-        }
+        if (!bucket_more(b)) return false;
     }
     return false;
-}
-
-PSA_HD uint64_t pack_value(const DevIndex& ix, uint32_t node, uint64_t pos, KeyHash hk) {
-    uint64_t v = (uint64_t)node | (pos << ix.node_bits);
-    if (ix.fp_bits) v |= fp_of(hk, ix.fp_bits) << (ix.node_bits + ix.pos_bits);
-    return v;
-}
-
-// dbg_index.get(kmer) followed by the reference's verification (src/pseudoaligner.rs:96-107).
-// A fingerprint mismatch proves the slot's key differs from `key`, so skipping the unitig
-// fetch cannot change the outcome of the reference's `read_kmer == ref_kmer` test.
-// prefilter: ask the Bloom filter first (callers do when the key is likely absent).
-template <int KW>
-PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st,
-                     bool prefilter = false, bool two_ahead = false) {
-    KeyHash hk = make_hash(KmerOps<KW>::fold(key));
-    if (prefilter && ix.bloom.words && !bloom_maybe(ix.bloom, hk)) return false;
-    uint64_t slot;
-    uint32_t levels;
-    bool in = mphf_lookup(ix.mphf, hk, slot, levels, two_ahead);
-    if (st) { st->levels = levels; st->hit = in; st->verified = 0; }
-    if (!in) return false;
-#ifdef __CUDA_ARCH__
-    uint64_t v = ld_u64_first(ix.values + slot);
-#else
-    uint64_t v = ix.values[slot];
-#endif
-    if (ix.fp_bits) {
-        if ((v >> (ix.node_bits + ix.pos_bits)) != fp_of(hk, ix.fp_bits)) return false;
-    }
-    uint32_t n = (uint32_t)(v & ((1ULL << ix.node_bits) - 1));
-    uint64_t pos = (v >> ix.node_bits) & ((1ULL << ix.pos_bits) - 1);
-    if (st) st->verified = 1;
-    // the unitig k-mer and the node's start are independent loads: both addresses come from `v`
-#ifdef __CUDA_ARCH__
-    uint64_t start = ld_u64_last(&ix.nodes[n].start_len) & kStartMask;
-#else
-    uint64_t start = ix.nodes[n].start_len & kStartMask;
-#endif
-    Kmer<KW> ref = KmerOps<KW>::get(GLoad{ix.seq}, pos, ix.k);
-    if (!(ref == key)) return false;
-    node = n;
-    off = (uint32_t)(pos - start);
-    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -525,7 +442,6 @@ PSA_HD uint32_t nth_mismatch(uint64_t m, uint32_t j) {
     for (uint32_t i = 1; i < j; i++) m &= m - 1;
     return (uint32_t)ctz64(m) >> 1;
 }
-
 // ---------------------------------------------------------------------------------------------
 // map_read_to_nodes_with_mismatch, ref src/pseudoaligner.rs:64-319.
 //
@@ -549,36 +465,17 @@ struct NodeView {
     uint32_t succ[4];  // never indexed dynamically (view_succ)
 };
 // sector 0 of a node record
-PSA_HD NodeView load_node_view(const NodeRec* r) {
+PSA_HD NodeView node_view_of(const Sector& s) {
     NodeView v;
-#ifdef __CUDA_ARCH__
-    uint64_t a, b, c, d;
-    ld_v4_last(r, a, b, c, d);
-    v.start = a & kStartMask;
-    v.len = (uint32_t)(a >> 40);
-    v.eq = (uint32_t)b;
-    v.class_len = (uint32_t)(b >> 32);
-    v.succ[0] = (uint32_t)c; v.succ[1] = (uint32_t)(c >> 32); v.succ[2] = (uint32_t)d; v.succ[3] = (uint32_t)(d >> 32);
-#else
-    v.start = r->start_len & kStartMask;
-    v.len = (uint32_t)(r->start_len >> 40);
-    v.eq = r->eq;
-    v.class_len = r->class_len;
-    for (int i = 0; i < 4; i++) v.succ[i] = r->succ[i];
-#endif
+    v.start = s.w0 & kStartMask;
+    v.len = (uint32_t)(s.w0 >> 40);
+    v.eq = (uint32_t)s.w1;
+    v.class_len = (uint32_t)(s.w1 >> 32);
+    v.succ[0] = (uint32_t)s.w2; v.succ[1] = (uint32_t)(s.w2 >> 32); v.succ[2] = (uint32_t)s.w3; v.succ[3] = (uint32_t)(s.w3 >> 32);
     return v;
 }
+PSA_HD NodeView load_node_view(const NodeRec* r) { return node_view_of(load_sector_hot(r)); }
 PSA_HD uint32_t view_succ(const NodeView& v, uint32_t b) { return b == 0 ? v.succ[0] : b == 1 ? v.succ[1] : b == 2 ? v.succ[2] : v.succ[3]; }
-
-// Optional policy hook: w.prefetch_succ(nv, pos) -- the forward walk is about to compare the rest of unitig nv
-// and, if every base matches, will continue with the successor selected by read base `pos`.  Policies without
-// the member get the no-op.
-template <class W, class P>
-PSA_HD auto hint_succ(W& w, const NodeView& nv, P pos, int) -> decltype(w.prefetch_succ(nv, pos), void()) {
-    w.prefetch_succ(nv, pos);
-}
-template <class W, class P>
-PSA_HD void hint_succ(W&, const NodeView&, P, long) {}
 
 #ifdef __CUDACC__
 #pragma nv_exec_check_disable
@@ -646,7 +543,6 @@ PSA_HD bool map_read_nodes(W& w, uint32_t k, P read_length, uint32_t allowed_mis
             P ref_offset = kmer_offset + kmer_length;                    // :227
             P informative_ref = ref_length - ref_offset;                 // :228
             P max_matchable_pos = remaining_read < informative_ref ? remaining_read : informative_ref;  // :231
-            if (remaining_read > informative_ref) hint_succ(w, nv, (P)(kmer_pos + informative_ref), 0);
             bool premature_break = false;                                       // :233
             P matched_bases =                                            // :234-255
                 w.cmp_fwd(kmer_pos, nv.start + ref_offset, max_matchable_pos, allowed_mismatches,
@@ -751,19 +647,14 @@ PSA_HD ClassWin make_class_win(const uint32_t* members, uint64_t len) {
     }
     return c;
 }
-PSA_HD ClassWin load_class_win(const ClassWin* p) {
+PSA_HD ClassWin class_win_of(const Sector& s) {  // a ClassWin sector, or sector 1 of a node record
     ClassWin c;
-#ifdef __CUDA_ARCH__
-    uint64_t a, b0, b1, b2;
-    ld_v4_last(p, a, b0, b1, b2);
-    c.lo = (uint32_t)a;
-    c.len = (uint32_t)(a >> 32);
-    c.bits[0] = b0; c.bits[1] = b1; c.bits[2] = b2;
-#else
-    c = *p;
-#endif
+    c.lo = (uint32_t)s.w0;
+    c.len = (uint32_t)(s.w0 >> 32);
+    c.bits[0] = s.w1; c.bits[1] = s.w2; c.bits[2] = s.w3;
     return c;
 }
+PSA_HD ClassWin load_class_win(const ClassWin* p) { return class_win_of(load_sector_hot(p)); }
 // Running intersection of narrow classes: {base, map} means the set {base + t : bit t set}.
 struct WinAcc {
     uint32_t base;
@@ -840,27 +731,17 @@ PSA_HD Win win_of_list_range(const uint32_t* v, uint32_t n, uint32_t base) {
 PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
     a.map = win_and(a.map, win_of_list_range(v, n, a.base));
 }
-
 // ---------------------------------------------------------------------------------------------
-// One thread = one read: the policy of the fast kernel (k_map_thread).  It runs the same
-// map_read_nodes text with every step done serially by the calling thread, and gives a read
-// up ("defer") as soon as it needs something a single thread does badly: a seed scan longer
-// than max_probes positions, more than kThreadWide distinct WIDE classes, or only wide classes
-// with a smallest one of more than max_small members.  Deferred reads are redone from scratch
-// by the cooperative kernel (k_map over the deferred list), so the split never changes a result.
-//
-// Classes are intersected ONLINE: the window of every newly visited class is ANDed into one
-// accumulator as the walk goes (any number of narrow classes in constant registers, and the
-// window load overlaps the next compare); only wide classes are listed, for the final filter.
-// eq_id needs no list either: the result equals a visited class iff its size equals the smallest
-// visited class length, and then it is the smallest-id class of that length.
+// nodes_to_eq_class (ref src/pseudoaligner.rs:323-356) ONLINE, for one thread: the window of
+// every newly visited class is ANDed into one accumulator as the walk goes (any number of narrow
+// classes in constant space); only wide classes are listed, for the final filter.  eq_id needs
+// no list either: the result is contained in every visited class, so it equals a visited class
+// iff its size equals the smallest visited class length, and then it is the smallest-id class of
+// that length.  A read whose classes do not fit (more than kThreadWide wide ones before any
+// narrow one, ...) sets `defer`: the cooperative kernel redoes it from scratch.
 // ---------------------------------------------------------------------------------------------
 constexpr int kThreadWide = 3;
-#ifndef PSA_WIDE_INLINE
-#define PSA_WIDE_INLINE 2
-#endif
-constexpr uint32_t kThreadWideInline = PSA_WIDE_INLINE;  // further wide classes applied on arrival before giving up
-constexpr int kThreadRecent = 2;
+constexpr uint32_t kThreadWideInline = 2;  // further wide classes applied on arrival before giving up
 constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;
 
@@ -874,193 +755,33 @@ struct ThreadEvents {
     uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
 };
 
-#ifndef PSA_CMP_CARRY
-#define PSA_CMP_CARRY 0
-#endif
-// Sequential 32-base chunks of a 2-bit sequence, each word loaded once (see ThreadCtx::cmp).  next(n, more)
-// returns the n (1..32) bases at the current position right-aligned, exactly as seq_bits does, and moves on
-// by 32 bases; `more` says whether another chunk follows (only then may the following word be touched).
-template <class L>
-struct CarryStream {
-    uint64_t wi, cur;
-    uint32_t in_word;
-    PSA_HD void start(L ld, uint64_t pos) {
-        wi = pos >> 5;
-        in_word = (uint32_t)(pos & 31);
-        cur = ld(wi);
-    }
-    PSA_HD uint64_t next(L ld, uint32_t n, bool more) {
-        uint64_t v = cur << (2 * in_word);
-        if (n > 32 - in_word) {          // the chunk runs into the next word: that word starts the next chunk
-            const uint64_t nx = ld(wi + 1);
-            v |= nx >> (64 - 2 * in_word);
-            cur = nx;
-        } else if (more) {               // (in_word == 0 and a full chunk: the next chunk is the next word)
-            cur = ld(wi + 1);
-        }
-        wi++;
-        return v >> (64 - 2 * n);
-    }
-};
-
-template <int KW, bool EV, class RD = PLoad>
-struct ThreadCtx {
-    const DevIndex& ix;
-    RD rd;
-    uint32_t max_probes;
-    // online class state
-    bool multi;                    // more than one distinct class visited (until then min_eq/min_len ARE the one
-                                   // class seen, whose window is fetched only when a second class shows up)
-    uint32_t min_len, min_eq;      // smallest class length seen, and the smallest id among the classes of that length
-    WinAcc acc;                    // AND of the narrow classes' windows
-    uint32_t wide_eq[kThreadWide], n_wide, n_inline;  // (their lengths are re-read from eq_off when needed)
-    uint32_t recent[kThreadRecent];  // last few class ids (skips most repeated window loads; repeats are harmless)
+struct ClassAcc {
+    uint32_t min_len, min_eq;  // smallest class length seen, and the smallest id among the classes of that length
+    uint32_t last_eq;          // class of the previous push (consecutive repeats cost nothing)
+    WinAcc acc;                // AND of the narrow classes' windows
+    uint32_t wide_eq[kThreadWide];
+    uint8_t n_wide, n_inline;
+    bool multi;                // more than one distinct class visited
     bool defer;
-    uint32_t why;  // diagnostic: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long
-    bool seeded;
-    // answer of the read's first seed search when k_seed_scan has already made it
-    bool has_hint;
-    uint32_t hint_pos, hint_node, hint_off;
-    ThreadEvents ev;
 
-    PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
-        : ix(ix_), rd(rd_), max_probes(max_probes_), multi(false),
-          min_len(kNone), min_eq(kNone), n_wide(0), n_inline(0), defer(false), why(0), seeded(false),
-          has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
+    PSA_HD void init() {
+        min_len = kNone; min_eq = kNone; last_eq = kNone;
         acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
-    PSA_UNROLL
+        PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) wide_eq[j] = kNone;
-    PSA_UNROLL
-        for (int j = 0; j < kThreadRecent; j++) recent[j] = kNone;
+        n_wide = 0; n_inline = 0; multi = false; defer = false;
     }
-    PSA_HD bool abort() const { return defer; }
-    PSA_HD uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
-
-    // find_kmer_match, ref src/pseudoaligner.rs:91-114, at most max_probes positions
-    template <class P>
-    PSA_HD bool find_seed(P& kmer_pos, P last, uint32_t& node, uint32_t& o) {
-        if (kmer_pos > last) return false;
-        if (has_hint) {  // the first search of the read (it starts at 0), done by k_seed_scan
-            has_hint = false;
-            kmer_pos = hint_pos;
-            node = hint_node;
-            o = hint_off;
-            seeded = true;
-            return true;
-        }
-        const P start = kmer_pos;
-        P p = start;
-        for (uint32_t probes = 0;; probes++, p += kSeedStride) {
-            if (p > last) {
-                kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
-                return false;
-            }
-            // re-seed searches (ref :293) are short as a rule and have no scan kernel of their own: allow them more
-            if (probes >= (seeded ? (max_probes > kReseedProbes ? max_probes : kReseedProbes) : max_probes)) {
-                defer = true;
-                why = seeded ? 1 : 0;
-                kmer_pos = last + 1;  // keeps map_read_nodes out of the forward loop
-                return false;
-            }
-            ProbeStats st;
-            // after a miss the next positions are likely absent too: Bloom first (never when counting
-            // events, which are defined on the MPHF path)
-            bool hit = dict_get<KW>(ix, KmerOps<KW>::get(rd, p, ix.k), node, o, EV ? &st : nullptr, !EV && probes > 0,
-                                    PSA_TWO_AHEAD && probes == 0);
-            if (EV) { ev.lookups++; ev.levels += st.levels; ev.hits += st.hit; ev.verifs += st.verified; }
-            if (hit) {
-                kmer_pos = p;
-                seeded = true;
-                return true;
-            }
-        }
-    }
-    PSA_HD NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
-#if PSA_PF_SUCC
-    // the node record the walk needs next if the rest of this unitig matches: fetched under the compare
-    template <class P>
-    PSA_HD void prefetch_succ(const NodeView& nv, P pos) {
-        const uint32_t s = view_succ(nv, read_base(pos));
-        if (s != kNone) prefetch_l2(ix.nodes + s);
-    }
-#endif
-    PSA_HD void jumped() {
-        if (EV) ev.jumps++;
-    }
-    PSA_HD uint32_t pred(uint32_t id, uint32_t b) {
-#ifdef __CUDA_ARCH__
-        const uint32_t p = __ldg(&ix.nodes[id].pred[b]);
-#else
-        const uint32_t p = ix.nodes[id].pred[b];
-#endif
-        if (EV && p != kNone) ev.jumps++;
-        return p;
-    }
-    // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step
-    template <bool FWD, class P>
-    PSA_HD P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
-        uint32_t snp = 0;
-#if PSA_PF_SPAN
-        if (m > 32) {  // the far end of the unitig span, if it lies in another 32-byte sector (128 bases)
-            const uint64_t far = FWD ? sp + m - 1 : sp - (m - 1);
-            if ((far >> 7) != (sp >> 7)) prefetch_l2(ix.seq + (far >> 5));
-        }
-#endif
-#if PSA_CMP_CARRY
-        // forward compare with every word of the read and of the unitig loaded ONCE: consecutive 32-base chunks
-        // start one word apart at a constant in-word offset, so a chunk's second word is the next chunk's first.
-        // (Experiment switch, off: hostsim-verified, not yet measured on the GPU.)
-        CarryStream<RD> rs;
-        CarryStream<GLoad> ss;
-        if (FWD && m > 0) {
-            rs.start(rd, rp);
-            ss.start(GLoad{ix.seq}, sp);
-        }
-#endif
-        for (P my = 0; my < m; my += 32) {
-            uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
-#if PSA_CMP_CARRY
-            uint64_t mask;
-            if (FWD) {
-                const bool more = my + 32 < m;
-                uint64_t x = rs.next(rd, n, more) ^ ss.next(GLoad{ix.seq}, n, more);  // base t at bits 2(n-1-t)
-                x = rev_pairs(x) >> (64 - 2 * n);
-                mask = fold_pairs(x);
-            } else {
-                mask = mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
-            }
-#else
-            uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
-                                : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
-#endif
-            uint32_t c = (uint32_t)popc64(mask);
-            if (snp + c > A) {
-                premature = true;
-                P matched = my + nth_mismatch(mask, A + 1 - snp);
-                if (EV) ev.bases += (uint32_t)matched + 1;
-                return matched;
-            }
-            snp += c;
-        }
-        if (EV) ev.bases += (uint32_t)m;
-        return m;
-    }
-    template <class P>
-    PSA_HD P cmp_fwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<true>(rp, sp, m, A, pb); }
-    template <class P>
-    PSA_HD P cmp_bwd(P rp, uint64_t sp, P m, uint32_t A, bool& pb) { return cmp<false>(rp, sp, m, A, pb); }
     // AND one class into the running intersection (narrow), or list it (wide)
-    PSA_HD void and_class(uint32_t e, uint32_t l) {
-        const ClassWin c = load_class_win(ix.class_win + e);
+    PSA_HD void and_class(const DevIndex& ix, uint32_t e, uint32_t l, const ClassWin& c) {
         if (c.len != kWinWide) {
             winacc_and(acc, c);
             return;
         }
         bool dup = false;
-    PSA_UNROLL
+        PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) dup |= (j < (int)n_wide && wide_eq[j] == e);
         if (dup) return;
-        if (n_wide >= (uint32_t)kThreadWide) {
+        if (n_wide >= kThreadWide) {
             // no room to remember it: apply it now to the candidates the windows have left (the filter
             // is idempotent and commutes with the ANDs still to come); without any window yet, give up
             if (acc.have && n_inline < kThreadWideInline) {
@@ -1069,36 +790,25 @@ struct ThreadCtx {
                 return;
             }
             defer = true;
-            why = 2;
             return;
         }
-    PSA_UNROLL
+        PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++)
             if (j == (int)n_wide) wide_eq[j] = e;
         n_wide++;
     }
-    // nodes.push: only the classes matter, and the intersection is idempotent (ref :352-355)
-    PSA_HD void push(uint32_t /*node_id*/, const NodeView& nv) {
-        if (EV) ev.visits++;
-        bool dup = false;
-    PSA_UNROLL
-        for (int j = 0; j < kThreadRecent; j++) dup |= (recent[j] == nv.eq);
-        if (dup) return;
-    PSA_UNROLL
-        for (int j = kThreadRecent - 1; j > 0; j--) recent[j] = recent[j - 1];
-        recent[0] = nv.eq;
-        if (EV) ev.members += nv.class_len;  // (a class revisited after kThreadRecent others is counted again)
-        const bool first = min_eq == kNone;
-        if (!first && !multi) {
-            if (nv.eq == min_eq) return;   // still the one class seen so far
-            multi = true;
-            and_class(min_eq, min_len);
+    // nodes.push: only the classes matter, and the intersection is idempotent (ref :352-355).
+    // Returns true when the class was not the previous push's (event counting).
+    PSA_HD bool push(const DevIndex& ix, uint32_t eq, uint32_t class_len, const ClassWin& win) {
+        if (eq == last_eq) return false;
+        if (min_eq != kNone) multi = true;
+        last_eq = eq;
+        if (class_len < min_len || (class_len == min_len && eq < min_eq)) {
+            min_len = class_len;
+            min_eq = eq;
         }
-        if (nv.class_len < min_len || (nv.class_len == min_len && nv.eq < min_eq)) {
-            min_len = nv.class_len;
-            min_eq = nv.eq;
-        }
-        if (multi) and_class(nv.eq, nv.class_len);
+        and_class(ix, eq, class_len, win);
+        return true;
     }
 };
 
@@ -1106,9 +816,8 @@ struct ThreadCtx {
 // smallest listed class (index s) that every other listed class contains, ascending; each other
 // class is searched only in the suffix after its previous match (ref :399-404).
 // out == nullptr counts.
-template <int KW, bool EV, class RD>
-PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, uint32_t* out) {
-    const uint32_t* mem = w.ix.eq_mem;
+PSA_HD uint32_t thread_intersect_lists(const DevIndex& ix, const ClassAcc& w, int s, uint32_t* out) {
+    const uint32_t* mem = ix.eq_mem;
     uint32_t cur[kThreadWide];
     PSA_UNROLL
     for (int j = 0; j < kThreadWide; j++) cur[j] = 0;
@@ -1116,17 +825,17 @@ PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, ui
     PSA_UNROLL
     for (int j = 0; j < kThreadWide; j++)
         if (j == s) s_eq = w.wide_eq[j];
-    const uint64_t s_off = ld_off(w.ix.eq_off + s_eq);
-    const uint32_t s_len = (uint32_t)(ld_off(w.ix.eq_off + s_eq + 1) - s_off);
+    const uint64_t s_off = ld_off(ix.eq_off + s_eq);
+    const uint32_t s_len = (uint32_t)(ld_off(ix.eq_off + s_eq + 1) - s_off);
     uint32_t count = 0;
     for (uint32_t i = 0; i < s_len; i++) {
         const uint32_t x = ld_mem(mem + s_off + i);
         bool alive = true;
-    PSA_UNROLL
+        PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) {
             if (j == s || j >= (int)w.n_wide || !alive) continue;
-            const uint64_t o = ld_off(w.ix.eq_off + w.wide_eq[j]);
-            const uint32_t n = (uint32_t)(ld_off(w.ix.eq_off + w.wide_eq[j] + 1) - o);
+            const uint64_t o = ld_off(ix.eq_off + w.wide_eq[j]);
+            const uint32_t n = (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o);
             const uint32_t* v = mem + o;
             uint32_t lo = cur[j], hi = n;
             while (lo < hi) {
@@ -1145,97 +854,47 @@ PSA_HD uint32_t thread_intersect_lists(const ThreadCtx<KW, EV, RD>& w, int s, ui
     return count;
 }
 
-// Result of map_read for one read as the kernels store it (flag = ref :453-462).
-struct ThreadResult {
-    HitRec hit;
-    uint64_t count_slot;  // index into counts[]: eq id, n_eq (no visited class), n_eq + 1 (None)
-    bool deferred;
-    bool novel_overflow;
-    uint32_t why;  // ThreadCtx::why when deferred
-};
-
-// map_read + the process_reads flag for one read, by one thread.  NovelAlloc::operator()(count,
-// off_out) returns room for `count` members of a set that is no visited class (nullptr: no
-// room / members not wanted).
-template <int KW, bool EV, class NovelAlloc, class RD>
-PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t L, uint32_t allowed,
-                                    uint32_t max_probes, uint32_t max_small, NovelAlloc& novel, bool want_members,
-                                    ThreadEvents* ev_out, const uint32_t* hint = nullptr /* pos, node, off */) {
-    ThreadResult res;
-    res.hit.coverage = 0; res.hit.n_tx = 0; res.hit.tx_off = 0; res.hit.eq_id = kNone; res.hit.flags = 0;
-    res.count_slot = ix.n_eq + 1;
-    res.deferred = false;
-    res.novel_overflow = false;
-    ThreadCtx<KW, EV, RD> w(ix, words, max_probes);
-    if (hint) {
-        w.has_hint = true;
-        w.hint_pos = hint[0]; w.hint_node = hint[1]; w.hint_off = hint[2];
+// The eq_class of a read from its accumulated classes: |set| and the id of the visited class it
+// equals (kNone if none).  `s` receives the smallest wide class (used when every class is wide).
+// Returns false when the lists are too long for one thread (smallest class > max_small).
+PSA_HD bool class_result(const DevIndex& ix, ClassAcc& w, uint32_t max_small, uint32_t& count, uint32_t& eq_id, int& s) {
+    s = 0;
+    if (!w.multi) {
+        count = w.min_len;
+        eq_id = w.min_eq;
+        return true;
     }
-    uint32_t coverage = 0;
-    bool some = map_read_nodes<uint32_t>(w, ix.k, L, allowed, coverage);
-    res.why = w.why;
-    if (w.defer) {
-        res.deferred = true;
-        return res;
-    }
-    if (some) {
-        uint32_t count, eq_id;
-        int s = 0;  // smallest wide class (only used when every class is wide)
-        if (!w.multi) {
-            count = w.min_len;
-            eq_id = w.min_eq;
-        } else {
-            if (w.acc.have) {
-                // wide classes filter what survived the windows (ref :399-404 on the candidates)
-    PSA_UNROLL
-                for (int j = 0; j < kThreadWide; j++) {
-                    if (j >= (int)w.n_wide || win_empty(w.acc.map)) continue;
-                    const uint64_t o = ld_off(ix.eq_off + w.wide_eq[j]);
-                    winacc_filter_list(w.acc, ix.eq_mem + o, (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o));
-                }
-                count = win_popc(w.acc.map);
-            } else {
-                // smallest class first (ref :331-334)
-                uint32_t s_eq = w.wide_eq[0];
-                uint32_t s_len = (uint32_t)(ld_off(ix.eq_off + s_eq + 1) - ld_off(ix.eq_off + s_eq));
-    PSA_UNROLL
-                for (int j = 1; j < kThreadWide; j++) {
-                    if (j >= (int)w.n_wide) continue;
-                    const uint32_t e = w.wide_eq[j];
-                    const uint32_t l = (uint32_t)(ld_off(ix.eq_off + e + 1) - ld_off(ix.eq_off + e));
-                    if (l < s_len || (l == s_len && e < s_eq)) { s = j; s_len = l; s_eq = e; }
-                }
-                if (s_len > max_small) {  // long lists are the cooperative kernel's job
-                    res.why = 3;
-                    res.deferred = true;
-                    return res;
-                }
-                count = thread_intersect_lists(w, s, (uint32_t*)nullptr);
-            }
-            // the result equals a visited class iff it has as many members as the smallest visited class
-            eq_id = count == w.min_len ? w.min_eq : kNone;
+    if (w.acc.have) {
+        // wide classes filter what survived the windows (ref :399-404 on the candidates)
+        PSA_UNROLL
+        for (int j = 0; j < kThreadWide; j++) {
+            if (j >= (int)w.n_wide || win_empty(w.acc.map)) continue;
+            const uint64_t o = ld_off(ix.eq_off + w.wide_eq[j]);
+            winacc_filter_list(w.acc, ix.eq_mem + o, (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o));
         }
-        res.hit.coverage = coverage;
-        res.hit.n_tx = count;
-        res.hit.eq_id = eq_id;
-        res.hit.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
-        if (eq_id != kNone) {
-            res.hit.tx_off = ld_off(ix.eq_off + eq_id);  // members are read from the index by k_expand
-            res.count_slot = eq_id;
-        } else {
-            res.count_slot = ix.n_eq;
-            if (count && want_members) {
-                uint64_t o = 0;
-                uint32_t* dst = novel(count, o);
-                if (!dst) res.novel_overflow = true;
-                else if (w.acc.have) win_write(w.acc, dst);
-                else thread_intersect_lists(w, s, dst);
-                res.hit.tx_off = o;
-            }
+        count = win_popc(w.acc.map);
+    } else {
+        // smallest class first (ref :331-334)
+        uint32_t s_eq = w.wide_eq[0];
+        uint32_t s_len = (uint32_t)(ld_off(ix.eq_off + s_eq + 1) - ld_off(ix.eq_off + s_eq));
+        PSA_UNROLL
+        for (int j = 1; j < kThreadWide; j++) {
+            if (j >= (int)w.n_wide) continue;
+            const uint32_t e = w.wide_eq[j];
+            const uint32_t l = (uint32_t)(ld_off(ix.eq_off + e + 1) - ld_off(ix.eq_off + e));
+            if (l < s_len || (l == s_len && e < s_eq)) { s = j; s_len = l; s_eq = e; }
         }
+        if (s_len > max_small) return false;  // long lists are the cooperative kernel's job
+        count = thread_intersect_lists(ix, w, s, (uint32_t*)nullptr);
     }
-    if (EV && ev_out) *ev_out = w.ev;
-    return res;
+    // the result equals a visited class iff it has as many members as the smallest visited class
+    eq_id = count == w.min_len ? w.min_eq : kNone;
+    return true;
+}
+// the members of a result that is no visited class, ascending
+PSA_HD void class_members(const DevIndex& ix, const ClassAcc& w, int s, uint32_t* dst) {
+    if (w.acc.have) win_write(w.acc, dst);
+    else thread_intersect_lists(ix, w, s, dst);
 }
 
 // ASCII -> 2-bit code, DnaString::from_dna_string (call site ref src/pseudoaligner.rs:450):

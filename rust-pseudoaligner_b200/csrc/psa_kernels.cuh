@@ -1,29 +1,19 @@
 // psa_kernels.cuh -- the sm_100a kernels: index construction on the device (k-mer enumeration,
-// cascaded-bit-vector MPHF, `values` scatter, successor/predecessor tables), ASCII -> 2-bit
-// packing, the one-warp-per-read map kernel, and the result expansion.
+// bucket-cascade dictionary, successor/predecessor tables, class windows), ASCII -> 2-bit
+// packing, the map kernels, and the result expansion.
 //
 // Reference items replaced (10XGenomics/rust-pseudoaligner @ 9d9cab8):
-//   k_map            Pseudoaligner::map_read + the per-record body of process_reads
-//                    (src/pseudoaligner.rs:64-384, :449-462)
-//   k_pack_ascii     DnaString::from_dna_string at src/pseudoaligner.rs:449-450
-//   k_mphf_* / k_fill_values   make_dbg_index (src/build_index.rs:182-221)
+//   k_map_lanes / k_seed_scan / k_map   Pseudoaligner::map_read + the per-record body of
+//                    process_reads (src/pseudoaligner.rs:64-384, :449-462)
+//   k_pack_ascii*    DnaString::from_dna_string at src/pseudoaligner.rs:449-450
+//   k_dict_*         make_dbg_index (src/build_index.rs:182-221)
 //   k_build_edges    what Node::r_edges()/l_edges() compute per call (src/pseudoaligner.rs:191,275)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "psa_core.cuh"
-
-// build-time experiment switches (defaults = the measured best; profiles/r1_exp_*.txt)
-#ifndef PSA_MAP_DYNAMIC
-#define PSA_MAP_DYNAMIC 1   // k_map claims handed-over reads from a counter (0: strides over the list)
-#endif
-#ifndef PSA_EXPAND_BALANCED
-#define PSA_EXPAND_BALANCED 1   // k_expand_balanced (0: S lanes per read)
-#endif
-#ifndef PSA_PACK_V1
-#define PSA_PACK_V1 0       // 1: the first ASCII -> 2-bit formulation (four SIMD byte compares)
-#endif
+#include "psa_lanes.cuh"
 
 namespace psa {
 
@@ -33,27 +23,40 @@ constexpr unsigned kFull = 0xffffffffu;
 // index construction
 // ---------------------------------------------------------------------------------------------
 // first pass over the nodes: record everything that does not need the dictionary
-__global__ void k_node_basics(NodeRec* nodes, uint64_t n_nodes, const uint64_t* node_start,
+__global__ void k_node_basics(NodeRec* nodes, NodeCold* cold, uint64_t n_nodes, const uint64_t* node_start,
                               const uint32_t* node_len, const uint8_t* node_exts, const uint32_t* node_eq,
                               const uint64_t* eq_off, uint64_t n_eq, uint32_t k, uint32_t* err) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     NodeRec r;
+    NodeCold c;
     const uint32_t len = node_len[i];
     r.start_len = pack_start_len(node_start[i], len);
     r.eq = node_eq[i];
-    r.exts = node_exts[i];
-    r.pad = 0;
+    c.exts = node_exts[i];
+    c.pad = 0;
     if (r.eq >= n_eq || len < k || len > kMaxNodeLen || node_start[i] > kStartMask) {
         atomicOr(err, 1u);
         r.class_len = 0;
-        r.class_off = 0;
+        c.class_off = 0;
     } else {
-        r.class_off = eq_off[r.eq];
-        r.class_len = (uint32_t)(eq_off[r.eq + 1] - r.class_off);
+        c.class_off = eq_off[r.eq];
+        r.class_len = (uint32_t)(eq_off[r.eq + 1] - c.class_off);
     }
-    for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
+    for (int b = 0; b < 4; b++) r.succ[b] = c.pred[b] = kNone;
+    r.win_lo = 0; r.win_len = 0; r.win_bits[0] = r.win_bits[1] = r.win_bits[2] = 0;
     nodes[i] = r;
+    cold[i] = c;
+}
+// sector 1 of every node record: the window of the node's class
+__global__ void k_node_windows(NodeRec* nodes, uint64_t n_nodes, uint64_t n_eq, const ClassWin* win) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const uint32_t e = nodes[i].eq;
+    if (e >= n_eq) return;
+    const ClassWin c = win[e];
+    nodes[i].win_lo = c.lo; nodes[i].win_len = c.len;
+    nodes[i].win_bits[0] = c.bits[0]; nodes[i].win_bits[1] = c.bits[1]; nodes[i].win_bits[2] = c.bits[2];
 }
 
 // every k-mer of every node: key and its (node, offset); koff = exclusive scan of (len-k+1)
@@ -87,104 +90,85 @@ __device__ __forceinline__ KeyHash key_hash_at(const uint64_t* key_lo, const uin
     }
 }
 
-// one cascade level, step 1: every remaining key sets its bit; a second arrival marks a collision
+// ---- the dictionary (psa_core.cuh Dict), one cascade level at a time --------------------------
+// step 1: the bucket of every remaining key at this level (sort key) and its index (sort value)
 template <int KW>
-__global__ void k_mphf_set(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t n, uint32_t lvl,
-                           uint64_t nblk, uint64_t base, unsigned long long* blocks,
-                           unsigned long long* coll) {
+__global__ void k_dict_bucket_ids(const uint64_t* key_lo, const uint64_t* key_hi, uint32_t n, uint32_t lvl, uint64_t nbkt,
+                                  uint32_t* bid, uint32_t* idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bid[i] = (uint32_t)level_bucket(key_hash_at<KW>(key_lo, key_hi, i), lvl, nbkt);
+    idx[i] = i;
+}
+// step 2 (after a stable sort by bucket): the thread at the head of a bucket's run fills the bucket with
+// the first keys of the run, at most kBucketSlots of them and no two with the same fingerprint; the rest
+// are flagged for the next level and the bucket's "more" bit is set.  Deterministic: the order of the
+// keys is the order of their enumeration.
+template <int KW>
+__global__ void k_dict_fill(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint32_t n,
+                            const uint32_t* bid_sorted, const uint32_t* idx_sorted, DevIndex ix, uint64_t base,
+                            uint64_t* buckets, uint8_t* passed_on) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t b = bid_sorted[j];
+    if (j > 0 && bid_sorted[j - 1] == b) return;  // not the head of its run
+    uint64_t e[kBucketSlots];
+    uint64_t fps[kBucketSlots];
+    uint32_t cnt = 0;
+    bool more = false;
+    for (uint32_t t = j; t < n && bid_sorted[t] == b; t++) {
+        const uint32_t i = idx_sorted[t];
+        const KeyHash hk = key_hash_at<KW>(key_lo, key_hi, i);
+        const uint64_t fp = fp_of(hk, ix.fp_bits);
+        bool clash = cnt >= kBucketSlots;
+        for (uint32_t q = 0; q < cnt && q < kBucketSlots; q++) clash |= fps[q] == fp;
+        if (clash) {
+            passed_on[i] = 1;
+            more = true;
+            continue;
+        }
+        passed_on[i] = 0;
+        const uint64_t v = val[i];
+        const uint32_t node = (uint32_t)(v >> 32);
+        e[cnt] = pack_entry(ix, node, (ix.nodes[node].start_len & kStartMask) + (uint32_t)v, hk);
+        fps[cnt] = fp;
+        cnt++;
+    }
+    uint64_t* dst = buckets + 4 * (base + b);
+    for (uint32_t q = 0; q < cnt; q++) dst[q] = q == 0 && more ? (e[q] | kMoreBit) : e[q];
+}
+// step 3: the keys passed on, compacted in order (sel = their indices, ascending)
+__global__ void k_dict_gather(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, const uint32_t* sel, uint32_t n,
+                              uint64_t* out_lo, uint64_t* out_hi, uint64_t* out_val) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = sel[i];
+    out_lo[i] = key_lo[s];
+    if (key_hi) out_hi[i] = key_hi[s];
+    out_val[i] = val[s];
+}
+// self-check after the build: every key resolves to its own (node, offset)
+template <int KW>
+__global__ void k_dict_check(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n, DevIndex ix,
+                             uint32_t* err) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t blk; uint32_t bit;
-    level_pos(level_hash(key_hash_at<KW>(key_lo, key_hi, i), lvl), nblk, blk, bit);
-    uint64_t w = 4 * (base + blk) + 1 + (bit >> 6);
-    unsigned long long m = 1ULL << (bit & 63);
-    unsigned long long old = atomicOr(blocks + w, m);
-    if (old & m) atomicOr(coll + 4 * blk + 1 + (bit >> 6), m);
-}
-// step 2: keys on collided bits move on to the next level
-template <int KW>
-__global__ void k_mphf_filter(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n,
-                              uint32_t lvl, uint64_t nblk, const unsigned long long* coll, uint64_t* out_lo,
-                              uint64_t* out_hi, uint64_t* out_val, unsigned long long* cursor) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    bool keep = false;
-    if (i < n) {
-        uint64_t blk; uint32_t bit;
-        level_pos(level_hash(key_hash_at<KW>(key_lo, key_hi, i), lvl), nblk, blk, bit);
-        keep = (coll[4 * blk + 1 + (bit >> 6)] >> (bit & 63)) & 1;
-    }
-    unsigned b = __ballot_sync(kFull, keep);
-    if (!b) return;
-    unsigned lane = threadIdx.x & 31;
-    unsigned long long basepos = 0;
-    if (lane == 0) basepos = atomicAdd(cursor, (unsigned long long)__popc(b));
-    basepos = __shfl_sync(kFull, basepos, 0);
-    if (keep) {
-        uint64_t o = basepos + __popc(b & ((1u << lane) - 1));
-        out_lo[o] = key_lo[i];
-        if (KW == 2) out_hi[o] = key_hi[i];
-        out_val[o] = val[i];
-    }
-}
-// step 3: collided bits are cleared from the level, the scratch is zeroed for the next level
-__global__ void k_mphf_finalize(unsigned long long* blocks, unsigned long long* coll, uint64_t base,
-                                uint64_t nblk) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= 4 * nblk) return;
-    unsigned long long c = coll[i];
-    if (c) {
-        blocks[4 * base + i] &= ~c;
-        coll[i] = 0;
-    }
-}
-__global__ void k_block_counts(const uint64_t* blocks, uint64_t nblk, uint32_t* cnt) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= nblk) return;
-    cnt[i] = __popcll(blocks[4 * i + 1]) + __popcll(blocks[4 * i + 2]) + __popcll(blocks[4 * i + 3]);
-}
-__global__ void k_block_headers(uint64_t* blocks, uint64_t nblk, const uint64_t* rank_excl) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= nblk) return;
-    uint32_t c1 = __popcll(blocks[4 * i + 1]);
-    uint32_t c2 = c1 + __popcll(blocks[4 * i + 2]);
-    blocks[4 * i] = make_header(rank_excl[i], c1, c2);
-}
-
-// absent-key prefilter (psa_core.cuh Bloom): every key sets one bit in each word of its block
-template <int KW>
-__global__ void k_bloom_set(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t n, Bloom b, uint32_t* words) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t blk, bits;
-    bloom_pos(key_hash_at<KW>(key_lo, key_hi, i), b.n_blocks, blk, bits);
-#pragma unroll
-    for (int w = 0; w < 8; w++) atomicOr(words + 8 * blk + w, 1u << ((bits >> (5 * w)) & 31));
-}
-
-// values[mphf(kmer)] = (node, offset) -- ref src/build_index.rs:200-220
-template <int KW>
-__global__ void k_fill_values(const uint64_t* key_lo, const uint64_t* key_hi, const uint64_t* val, uint64_t n,
-                              DevIndex ix, uint64_t* values, uint32_t* err) {
-    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    KeyHash hk = key_hash_at<KW>(key_lo, key_hi, i);
-    uint64_t slot; uint32_t levels;
-    if (!mphf_lookup(ix.mphf, hk, slot, levels) || slot >= ix.n_kmers) {
-        atomicOr(err, 2u);
-        return;
-    }
-    uint64_t v = val[i];
-    const uint32_t node = (uint32_t)(v >> 32);
-    values[slot] = pack_value(ix, node, (ix.nodes[node].start_len & kStartMask) + (uint32_t)v, hk);
+    Kmer<KW> key;
+    key.lo = key_lo[i];
+    if constexpr (KW == 2) key.hi = key_hi[i];
+    uint32_t node = 0, off = 0;
+    const uint64_t v = val[i];
+    if (!dict_get<KW>(ix, key, node, off, nullptr) || node != (uint32_t)(v >> 32) || off != (uint32_t)v) atomicOr(err, 2u);
 }
 
 // succ[b] / pred[b]: the node whose first k-mer is last(k-1)+b, resp. whose last k-mer is
 // b+first(k-1).  debruijn's find_link expects every ext bit to resolve ("missing link").
 template <int KW>
-__global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
+__global__ void k_build_edges(DevIndex ix, NodeRec* nodes, NodeCold* cold, uint32_t* err) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= ix.n_nodes) return;
     const NodeRec r = nodes[i];
+    const uint32_t exts = cold[i].exts;
     const uint64_t r_start = r.start_len & kStartMask;
     const uint32_t r_len = (uint32_t)(r.start_len >> 40);
     if (r_len < ix.k) return;
@@ -192,16 +176,16 @@ __global__ void k_build_edges(DevIndex ix, NodeRec* nodes, uint32_t* err) {
     Kmer<KW> last = KmerOps<KW>::get(GLoad{ix.seq}, r_start + r_len - ix.k, ix.k);
     for (uint32_t b = 0; b < 4; b++) {
         uint32_t n, o;
-        if ((r.exts >> b) & 1) {
+        if ((exts >> b) & 1) {
             if (dict_get<KW>(ix, KmerOps<KW>::extend_right(last, b, ix.k), n, o, nullptr) && o == 0)
                 nodes[i].succ[b] = n;
             else
                 atomicOr(err, 4u);
         }
-        if ((r.exts >> (4 + b)) & 1) {
+        if ((exts >> (4 + b)) & 1) {
             if (dict_get<KW>(ix, KmerOps<KW>::extend_left(first, b, ix.k), n, o, nullptr) &&
                 o == (uint32_t)(nodes[n].start_len >> 40) - ix.k)
-                nodes[i].pred[b] = n;
+                cold[i].pred[b] = n;
             else
                 atomicOr(err, 4u);
         }
@@ -252,15 +236,6 @@ __global__ void k_words_per_read(const uint32_t* len, uint64_t n, uint64_t* nw) 
 // the low three bits of A C G T (1 3 7 4) are distinct, so they select both the code and the
 // letter the byte must be (case folded) for the code to stand.
 __device__ __forceinline__ uint32_t codes4(uint32_t w) {
-#if PSA_PACK_V1  // first version: four SIMD byte compares (~33 instructions)
-    uint32_t u = w & 0xDFDFDFDFu;  // fold case
-    uint32_t valid = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) |
-                     __vcmpeq4(u, 0x54545454u);
-    uint32_t x = (w >> 1) & 0x03030303u;  // A0 C1 G3 T2
-    x ^= (x >> 1) & 0x01010101u;          // A0 C1 G2 T3
-    x &= valid;
-    return (x * 0x40100401u) >> 24;       // gather the four 2-bit fields (no carries between them)
-#else
     uint32_t t = w & 0x07070707u;
     t |= t >> 4;                                              // byte 0: idx0 | idx1 << 4, byte 2: idx2 | idx3 << 4
     const uint32_t sel = __byte_perm(t, 0u, 0x4420u);         // four selector nibbles (bit 3 of each is clear)
@@ -270,7 +245,6 @@ __device__ __forceinline__ uint32_t codes4(uint32_t w) {
     const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;  // bit 7 of every non-zero byte
     x &= ~((nz >> 7) | (nz >> 6));
     return (x * 0x40100401u) >> 24;       // gather the four 2-bit fields (no carries between them)
-#endif
 }
 // nb (1..32) bases at s -> one DnaString word.  Reads only the aligned 32-bit words that hold
 // at least one of the nb bytes.
@@ -405,21 +379,23 @@ struct MapParams {
     unsigned long long pool_cap;  // entries
     unsigned long long* pool_cursor;
     uint32_t allowed_mismatches;
-    // deferred reads: written by k_map_thread, consumed by k_map (list != nullptr: map list[0..*list_count))
+    // deferred reads: written by k_map_lanes, consumed by k_map (list != nullptr: map list[0..*list_count))
     uint32_t* list;
     unsigned long long* list_count;
     unsigned long long* work_cursor;  // k_map over the list: next entry to claim (zeroed per batch), or nullptr
-    // reads whose FIRST seed search was too long for one thread: k_map_thread -> k_seed_scan
+    unsigned long long* lane_cursor;  // k_map_lanes: [0] next read of the first pass, [1] next entry of the seeded list
+    uint32_t lane_words;              // k_map_lanes: words of a lane's shared-memory read slot
+    // reads whose FIRST seed search was too long for one thread: k_map_lanes -> k_seed_scan
     uint32_t* scan_list;
     unsigned long long* scan_count;
-    // reads k_seed_scan found a seed for: {read, pos, node, off} -> second pass of k_map_thread
+    // reads k_seed_scan found a seed for: {read, pos, node, off} -> second pass of k_map_lanes
     uint4* seeded;
     unsigned long long* seeded_count;
     uint4* seeded_ev;             // event counting only: {lookups, levels, hits, verifs} of that search
-    uint32_t max_probes;          // k_map_thread: seed positions one thread tries per search
-    uint32_t max_small;           // k_map_thread: largest smallest-class one thread intersects
+    uint32_t max_probes;          // k_map_lanes: seed positions one thread tries per search
+    uint32_t max_small;           // k_map_lanes: largest smallest-class one thread intersects
     uint32_t* status;             // bit0: novel buffer overflow, bit1: spill pool overflow
-    unsigned long long* events;   // 3 x psa_events layout ([0] k_map_thread, [1] k_map, [2] k_seed_scan), or nullptr
+    unsigned long long* events;   // 3 x psa_events layout ([0] k_map_lanes, [1] k_map, [2] k_seed_scan), or nullptr
 };
 
 struct LaneEvents {
@@ -503,7 +479,7 @@ struct WarpCtx {
             st.levels = st.hit = st.verified = 0;
             if (p <= last) {
                 Kmer<KW> key = KmerOps<KW>::get(rd, p, k);
-                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr, !EV);  // speculative positions: Bloom first
+                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
             }
             unsigned b = g.ballot(h);
             int j = b ? (__ffs(b) - 1) : G;
@@ -532,7 +508,7 @@ struct WarpCtx {
         if (EV && lane == 0) ev.jumps++;
     }
     __device__ __forceinline__ uint32_t pred(uint32_t id, uint32_t b) {
-        const uint32_t p = __ldg(&ix.nodes[id].pred[b]);
+        const uint32_t p = __ldg(&ix.nodes_cold[id].pred[b]);
         if (EV && lane == 0 && p != kNone) ev.jumps++;
         return p;
     }
@@ -677,7 +653,7 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     const uint64_t n_todo = p.list ? (uint64_t)*p.list_count : p.reads.n;
     // The handed-over reads differ widely in cost (tens to hundreds of dependent loads): groups claim them one
     // at a time from a counter instead of striding over the list, so that no group is left with several slow ones.
-    const bool dynamic = PSA_MAP_DYNAMIC && p.list != nullptr && p.work_cursor != nullptr;
+    const bool dynamic = p.list != nullptr && p.work_cursor != nullptr;
     const Grp<G> wg;
     auto claim = [&]() -> uint64_t {
         unsigned long long at = 0;
@@ -791,9 +767,7 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
             h.eq_id = eq_id;
             h.flags = kFlagAligned | ((coverage >= kCoverageThreshold && count == 0) ? kFlagMapped : 0u);  // ref :455 (sic)
             if (eq_id != kNone) {
-                // members are read from the index by k_expand; eq_id is one of the visited classes
-                h.tx_off = __ldg(ix.eq_off + eq_id);
-                count_slot = eq_id;
+                count_slot = eq_id;  // (members: k_expand reads them from the index through eq_id)
             } else {
                 count_slot = ix.n_eq;
                 if (count && p.novel) {
@@ -832,154 +806,170 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
 }
 
 // ---------------------------------------------------------------------------------------------
-// the fast map kernel: one thread per read (psa_core.cuh ThreadCtx / map_read_thread).  Reads
-// it gives up are appended to p.list for k_map.
+// the fast map kernel: one lane per read, every lane a state machine (psa_lanes.cuh).  Persistent
+// warps; a lane that finishes its read takes the next one from a counter.  Reads a lane gives up
+// are appended to p.scan_list (first seed search too long -> k_seed_scan) or p.list (-> k_map).
+// HINT = true: the reads of p.seeded, whose first seed search k_seed_scan has made.
 // ---------------------------------------------------------------------------------------------
-struct DevNovel {
-    uint32_t* buf;
-    unsigned long long cap;
-    unsigned long long* cursor;
-    __device__ __forceinline__ uint32_t* operator()(uint32_t count, uint64_t& off) {
-        unsigned long long base = atomicAdd(cursor, (unsigned long long)count);
+struct DevSink {
+    const MapParams& p;
+    __device__ __forceinline__ void result(uint32_t r, const HitRec& h, uint64_t count_slot) {
+        // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
+        uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
+        out[0] = (uint64_t)h.coverage | ((uint64_t)h.n_tx << 32);
+        out[1] = h.tx_off;
+        out[2] = (uint64_t)h.eq_id | ((uint64_t)h.flags << 32);
+        if (p.counts) atomicAdd(p.counts + count_slot, 1ULL);
+    }
+    __device__ __forceinline__ uint32_t* novel(uint32_t count, uint64_t& off) {
+        unsigned long long base = atomicAdd(p.novel_cursor, (unsigned long long)count);
         off = base;
-        return base + count <= cap ? buf + base : nullptr;
+        return base + count <= p.novel_cap ? p.novel + base : nullptr;
     }
+    __device__ __forceinline__ void novel_overflow() { atomicOr(p.status, 1u); }
 };
+struct SmemWords {  // a lane's read words in shared memory: word j at base[j * stride]
+    uint64_t* base;
+    uint32_t stride;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return base[i * stride]; }
+    __device__ __forceinline__ void store(uint32_t i, uint64_t v) { base[i * stride] = v; }
+};
+__device__ __forceinline__ Sector ld_sector_policy(const void* a, uint64_t policy) {
+    Sector s;
+    asm("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(s.w0), "=l"(s.w1), "=l"(s.w2), "=l"(s.w3) : "l"(a), "l"(policy));
+    return s;
+}
 
-#ifndef PSA_HIT_STREAM
-#define PSA_HIT_STREAM 0
+#ifndef PSA_LANE_BLOCK
+#define PSA_LANE_BLOCK 128
 #endif
-#ifndef PSA_THREAD_BLOCK
-#define PSA_THREAD_BLOCK 64
+#ifndef PSA_LANE_MIN_BLOCKS
+#define PSA_LANE_MIN_BLOCKS 6
 #endif
-constexpr int kThreadBlock = PSA_THREAD_BLOCK;
-#ifndef PSA_THREAD_MIN_BLOCKS
-#define PSA_THREAD_MIN_BLOCKS 20
-#endif
+constexpr int kLaneBlock = PSA_LANE_BLOCK;
+constexpr uint32_t kLaneChunk = 128;     // reads a warp claims at a time
+constexpr uint32_t kLaneMaxWords = 8;    // longest read a lane takes: 256 bases (longer ones go to k_map)
 
-// HINT = false: read r = global thread id, one pass.  HINT = true: the reads of p.seeded (their
-// first seed search was made by k_seed_scan), persistent warps striding over that list.
-// TILE (first pass, fixed word stride; the default): the packed words of the CTA's 64 reads arrive in
-// shared memory as one bulk asynchronous copy (cp.async.bulk + mbarrier: TMA) and every thread maps its
-// read from there -- the read's words are touched ~10 times along the path, and through L1 they
-// kept being evicted by the index gathers (12.9 L2 sectors per read for 40 bytes of read).  Measured:
-// 2.4 % faster than reading through L1 with 64-thread CTAs (2.5 KB of shared memory per CTA), 2 % slower
-// with 128-thread CTAs.  (Fusing the ASCII packing in as well was measured:
-// the 19 KB ASCII tile per CTA shrinks L1 so much that the kernel loses 1 ms.)
-// (Holding a <= 192-base read in six registers instead of re-reading its words through L1 was
-// measured: 3.93 ms vs 3.48 ms -- the extra registers spill at the 64-register cap.  Not used.)
-template <int KW, bool EV, bool HINT, bool TILE = false>
-__global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
-                                                                                     const __grid_constant__ MapParams p) {
+template <int KW, bool EV, bool HINT>
+__global__ void __launch_bounds__(kLaneBlock, PSA_LANE_MIN_BLOCKS) k_map_lanes(const __grid_constant__ DevIndex ix,
+                                                                                const __grid_constant__ MapParams p) {
+    extern __shared__ __align__(16) uint64_t lane_smem[];
     const unsigned lane = threadIdx.x & 31;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const uint64_t* my_words = nullptr;
-    if (TILE) {
-        // layout: [mbarrier (16 B slot) | packed words of the CTA's reads]
-        uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-        uint64_t* pw = reinterpret_cast<uint64_t*>(smem + 16);
-        const uint64_t r0 = blockIdx.x * (uint64_t)kThreadBlock;
-        const uint32_t nr = (uint32_t)min((uint64_t)kThreadBlock, p.reads.n - r0);
-        const uint32_t nw = (uint32_t)p.reads.wstride;
-        const uint64_t* src = p.reads.words + r0 * nw;
-        const uint32_t bytes = nr * nw * 8;
-        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            if (threadIdx.x == 0) {
-                mbar_init(bar, 1);
-                mbar_expect_tx(bar, bytes);
-                bulk_g2s(pw, src, bytes, bar);
-            }
-            __syncthreads();  // the barrier is initialised before anyone polls it
-            mbar_wait(bar, 0);
-        } else {  // odd-sized last tile: plain loads
-            for (uint32_t i = threadIdx.x; i < nr * nw; i += kThreadBlock) pw[i] = src[i];
-            __syncthreads();
-        }
-        my_words = pw + threadIdx.x * nw;
-    }
+    SmemWords rw{lane_smem + threadIdx.x, (uint32_t)blockDim.x};
+    Lane<KW, EV> ln;
+    ln.idle();
+    Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
+    DevSink sink{p};
+    LaneParams lp;
+    lp.allowed = p.allowed_mismatches; lp.max_probes = p.max_probes; lp.max_small = p.max_small;
+    lp.want_members = p.novel != nullptr;
+    lp.to_scan = !HINT && p.scan_list != nullptr;
     const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
-    const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
-    // warp-uniform trip count: the hand-over below uses full-warp votes
-    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); base < n_todo; base += stride) {
-        const uint64_t it = base + lane;
-        const bool live = it < n_todo;
-        bool defer = false;
-        uint32_t why = 0;
-        uint64_t r = it;
-        ThreadEvents ev{};
-        uint4 sev = make_uint4(0, 0, 0, 0);
-        uint32_t L = 0, n_tx = 0, aligned = 0;
-        if (live) {
-            uint32_t hint[3];
-            if (HINT) {
-                const uint4 e = p.seeded[it];
-                r = e.x;
-                hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
-                if (EV) sev = p.seeded_ev[it];
+    unsigned long long* cursor = p.lane_cursor + (HINT ? 1 : 0);
+    const uint64_t pol_first = l2_policy_first(), pol_last = l2_policy_last();
+    uint64_t w_next = 0, w_end = 0;  // the warp's claimed range of reads (uniform)
+    bool exhausted = false;
+    const uint64_t* my_words = nullptr;
+    ThreadEvents tot{};
+    uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
+    uint4 sev = make_uint4(0, 0, 0, 0);
+
+    for (;;) {
+        // ---- lanes without a read take the next ones
+        unsigned need = __ballot_sync(kFull, ln.st == LS_NEW);
+        while (need && !exhausted) {
+            if (w_next == w_end) {
+                unsigned long long at = 0;
+                if (lane == 0) at = atomicAdd(cursor, (unsigned long long)kLaneChunk);
+                at = __shfl_sync(kFull, at, 0);
+                if (at >= n_todo) {
+                    exhausted = true;
+                    break;
+                }
+                w_next = at;
+                w_end = at + kLaneChunk < n_todo ? at + kLaneChunk : n_todo;
             }
-            const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
-            L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-            DevNovel novel{p.novel, p.novel_cap, p.novel_cursor};
-            ThreadResult res = TILE ? map_read_thread<KW, EV>(ix, PLoad{my_words}, L, p.allowed_mismatches, p.max_probes,
-                                                              p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
-                                                              HINT ? hint : nullptr)
-                                    : map_read_thread<KW, EV>(ix, RLoad{p.reads.words + wo}, L, p.allowed_mismatches, p.max_probes,
-                                                              p.max_small, novel, p.novel != nullptr, EV ? &ev : nullptr,
-                                                              HINT ? hint : nullptr);
-            defer = res.deferred;
-            why = res.why;
-            if (EV && defer && p.events) atomicAdd(p.events + 36 + res.why, 1ULL);
-            if (!defer) {
-                // psa_hit is 24 bytes at an 8-byte aligned address: three 8-byte stores
-                uint64_t* out = reinterpret_cast<uint64_t*>(p.hits + r);
-#if PSA_HIT_STREAM  // experiment: streaming (evict-first) stores for the write-once hit records
-                __stcs(out + 0, (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32));
-                __stcs(out + 1, (uint64_t)res.hit.tx_off);
-                __stcs(out + 2, (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32));
-#else
-                out[0] = (uint64_t)res.hit.coverage | ((uint64_t)res.hit.n_tx << 32);
-                out[1] = res.hit.tx_off;
-                out[2] = (uint64_t)res.hit.eq_id | ((uint64_t)res.hit.flags << 32);
-#endif
-                if (p.counts) atomicAdd(p.counts + res.count_slot, 1ULL);
-                if (res.novel_overflow) atomicOr(p.status, 1u);
-                n_tx = res.hit.n_tx;
-                aligned = res.hit.flags & kFlagAligned;
-            } else if (EV && HINT && p.events) {
-                // k_map redoes this read from scratch and counts its first search again
-                atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
-                atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
+            const uint64_t it = w_next + __popc(need & ((1u << lane) - 1));
+            const bool take = ((need >> lane) & 1u) && it < w_end;
+            if (take) {
+                uint64_t r = it;
+                uint32_t hint[3];
+                if (HINT) {
+                    const uint4 e = p.seeded[it];
+                    r = e.x;
+                    hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
+                    if (EV) sev = p.seeded_ev[it];
+                }
+                const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+                const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+                my_words = p.reads.words + wo;
+                ln.begin((uint32_t)r, L, p.lane_words, HINT ? hint : nullptr);
+            }
+            const unsigned taken = __ballot_sync(kFull, take);
+            w_next += __popc(taken);
+            need &= ~taken;
+        }
+        if (exhausted && ln.st == LS_NEW) ln.st = LS_IDLE;
+        if (!__ballot_sync(kFull, ln.st != LS_IDLE)) break;
+
+        // ---- the requests of all lanes, issued together
+        if (ln.st == LS_READ) {
+            const uint32_t nw = (ln.L + 31) >> 5;
+            A.w0 = nw > 0 ? my_words[0] : 0; A.w1 = nw > 1 ? my_words[1] : 0;
+            A.w2 = nw > 2 ? my_words[2] : 0; A.w3 = nw > 3 ? my_words[3] : 0;
+            if (nw > 4) {
+                C.w0 = my_words[4]; C.w1 = nw > 5 ? my_words[5] : 0;
+                C.w2 = nw > 6 ? my_words[6] : 0; C.w3 = nw > 7 ? my_words[7] : 0;
+            }
+        } else {
+            if (ln.reqA) A = ld_sector_policy(ln.reqA, ln.a_stream ? pol_first : pol_last);
+            if (ln.reqB) B = ld_sector_policy(ln.reqB, pol_last);
+            if (ln.reqC) {
+                C.w0 = ld_u64_last(ln.reqC); C.w1 = ld_u64_last(ln.reqC + 1);
+                C.w2 = ld_u64_last(ln.reqC + 2); C.w3 = ld_u64_last(ln.reqC + 3);
             }
         }
-        // hand the given-up reads over (one atomic per warp and list): a too long FIRST seed search
-        // goes to k_seed_scan, everything else to the cooperative kernel
-        const bool to_scan = defer && !HINT && why == 0 && p.scan_list != nullptr;
-        const unsigned bs = __ballot_sync(kFull, to_scan);
+        ln.step(ix, lp, rw, A, B, C, sink);
+
+        // ---- hand the given-up reads over (one atomic per warp and list)
+        const unsigned bs = __ballot_sync(kFull, ln.emit == LE_TO_SCAN);
         if (bs) {
             unsigned long long at = 0;
             if (lane == (unsigned)(__ffs(bs) - 1)) at = atomicAdd(p.scan_count, (unsigned long long)__popc(bs));
             at = __shfl_sync(kFull, at, __ffs(bs) - 1);
-            if (to_scan) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = (uint32_t)r;
+            if (ln.emit == LE_TO_SCAN) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = ln.r;
         }
-        const bool to_coop = defer && !to_scan;
-        const unsigned bc = __ballot_sync(kFull, to_coop);
+        const unsigned bc = __ballot_sync(kFull, ln.emit == LE_TO_COOP);
         if (bc) {
             unsigned long long at = 0;
             if (lane == (unsigned)(__ffs(bc) - 1)) at = atomicAdd(p.list_count, (unsigned long long)__popc(bc));
             at = __shfl_sync(kFull, at, __ffs(bc) - 1);
-            if (to_coop) p.list[at + __popc(bc & ((1u << lane) - 1))] = (uint32_t)r;
+            if (ln.emit == LE_TO_COOP) p.list[at + __popc(bc & ((1u << lane) - 1))] = ln.r;
         }
         if (EV && p.events) {
-            const bool cnt = live && !defer;
-            unsigned long long v[12] = {cnt ? 1ull : 0ull, cnt ? L : 0ull, ev.lookups, ev.levels, ev.hits, ev.verifs,
-                                        ev.visits, ev.bases, ev.jumps, ev.members, n_tx, aligned};
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                unsigned long long x = cnt ? v[i] : 0ull;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
-                if (lane == 0 && x) atomicAdd(p.events + i, x);
+            if (ln.emit == LE_RESULT) {
+                tot.lookups += ln.ev.lookups; tot.levels += ln.ev.levels; tot.hits += ln.ev.hits; tot.verifs += ln.ev.verifs;
+                tot.visits += ln.ev.visits; tot.bases += ln.ev.bases; tot.jumps += ln.ev.jumps; tot.members += ln.ev.members;
+                ev_reads++; ev_bases += ln.L; ev_out += ln.out_n_tx; ev_aligned += ln.out_aligned ? 1 : 0;
+            } else if (ln.emit == LE_TO_SCAN || ln.emit == LE_TO_COOP) {
+                if (ln.why < 4) atomicAdd(p.events + 36 + ln.why, 1ULL);
+                if (HINT) {  // k_map redoes this read from scratch and counts its first search again
+                    atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
+                    atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
+                }
             }
+        }
+    }
+    if (EV && p.events) {
+        unsigned long long v[12] = {ev_reads, ev_bases, tot.lookups, tot.levels, tot.hits, tot.verifs,
+                                    tot.visits, tot.bases, tot.jumps, tot.members, ev_out, ev_aligned};
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            unsigned long long x = v[i];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+            if (lane == 0 && x) atomicAdd(p.events + i, x);
         }
     }
 }
@@ -1073,34 +1063,14 @@ struct CastU64 {
     __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }
 };
 
-// rel_off[i] = offset of read i's members inside this batch's tx_buf; running[0] = members
-// emitted by the batches before this one (so that tx_off is global across a chunked call).
-// S lanes per read: the copy is a chain of three dependent accesses (hit -> members -> store), so what
-// matters is how many reads are in flight, not how many lanes share one (S = 2 measured best).
-#ifndef PSA_EXPAND_LANES
-#define PSA_EXPAND_LANES 2
-#endif
-__global__ void k_expand(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
-                         const uint32_t* eq_mem, const uint32_t* novel, uint32_t* tx_buf, uint64_t tx_cap) {
-    constexpr uint32_t S = PSA_EXPAND_LANES;
-    const uint32_t sub = threadIdx.x % S;
-    uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) / S;
-    if (i >= n) return;
-    HitRec h = hits[i];
-    uint64_t rel = rel_off[i];
-    if (tx_buf && rel + h.n_tx <= tx_cap) {
-        const uint32_t* src = (h.eq_id != kNone ? eq_mem : novel) + h.tx_off;
-        for (uint32_t j = sub; j < h.n_tx; j += S) tx_buf[rel + j] = src[j];
-    }
-    if (sub == 0) hits[i].tx_off = running[0] + rel;
-}
-// Load-balanced form: a warp takes 32 consecutive reads, whose members are one contiguous range of tx_buf
-// (rel_off is an exclusive scan); lane t of every round writes element t of that range -- it finds the read
+// rel_off[i] = offset of read i's members inside this batch's tx_buf (an exclusive scan of n_tx); running[0] =
+// members emitted by the batches before this one (so that tx_off is global across a chunked call).
+// A warp takes 32 consecutive reads, whose members are one contiguous range of tx_buf; lane t of every round writes element t of that range -- it finds the read
 // the element belongs to by a binary search over the lanes' start offsets (shuffles) and fetches the source
 // pointer from that lane.  Stores are fully coalesced and no lane idles behind a read with a long class.
 __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
-                                                         const uint32_t* eq_mem, const uint32_t* novel, uint32_t* tx_buf,
-                                                         uint64_t tx_cap) {
+                                                         const uint64_t* eq_off, const uint32_t* eq_mem, const uint32_t* novel,
+                                                         uint32_t* tx_buf, uint64_t tx_cap) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull;
     if (base >= n) return;  // warp-uniform
@@ -1115,7 +1085,8 @@ __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t 
         rel = rel_off[i];
         cnt = h.n_tx;
         fits = tx_buf != nullptr && rel + cnt <= tx_cap;
-        src = (h.eq_id != kNone ? eq_mem : novel) + h.tx_off;
+        // members of an index class come from the index (through eq_id), any other set from the novel-set buffer
+        src = h.eq_id != kNone ? eq_mem + __ldg(eq_off + h.eq_id) : novel + h.tx_off;
         hits[i].tx_off = running[0] + rel;
     }
     const uint64_t rel0 = __shfl_sync(kFull, rel, 0);
@@ -1136,6 +1107,24 @@ __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t 
         if (t < total && ((fitmask >> q) & 1u)) tx_buf[rel0 + t] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)sp) + (t - ss));
     }
 }
+// Verification aid: order-independent checksum of a result batch -- the sum over reads of a hash chain over
+// (global read index, coverage, flags, eq_id, members in order).  oracle/psa_oracle.c restates it for host buffers.
+__global__ void k_result_checksum(const HitRec* hits, const uint32_t* tx, uint64_t n, uint64_t first_index, uint64_t tx_base,
+                                  unsigned long long* out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t h = 0;
+    if (i < n) {
+        const HitRec r = hits[i];
+        h = mix64(first_index + i + 0x9E3779B97F4A7C15ULL);
+        h = mix64(h ^ (((uint64_t)r.coverage << 32) | r.flags));
+        h = mix64(h ^ (((uint64_t)r.n_tx << 32) | r.eq_id));
+        for (uint32_t j = 0; j < r.n_tx; j++) h = mix64(h ^ ((uint64_t)tx[r.tx_off - tx_base + j] + 0xD6E8FEB86659FD93ULL));
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(kFull, h, d);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, (unsigned long long)h);
+}
+
 // after k_expand: advance the running total, publish {running, status} for the host.  sticky (may be
 // nullptr): the OR of the status words of every batch since the host last cleared it -- several batches may
 // be queued between two psa_mapper_sync calls and none of their overflows may go unnoticed.

@@ -24,7 +24,7 @@ HIT_DTYPE = np.dtype(
     [("coverage", "<u4"), ("n_tx", "<u4"), ("tx_off", "<u8"), ("eq_id", "<u4"), ("flags", "<u4")]
 )
 
-EVENT_FIELDS = ("reads", "read_bases", "kmer_lookups", "mphf_levels", "mphf_hits", "verifications",
+EVENT_FIELDS = ("reads", "read_bases", "kmer_lookups", "dict_levels", "dict_hits", "verifications",
                 "node_visits", "bases_compared", "edge_jumps", "class_members", "out_members", "aligned")
 
 
@@ -42,11 +42,11 @@ class _IndexDesc(C.Structure):
 
 
 class _IndexInfo(C.Structure):
-    _fields_ = [("k", C.c_uint32), ("mphf_levels", C.c_uint32),
+    _fields_ = [("k", C.c_uint32), ("dict_levels", C.c_uint32),
                 ("n_nodes", C.c_uint64), ("n_kmers", C.c_uint64), ("n_eq", C.c_uint64),
                 ("n_eq_members", C.c_uint64), ("n_seq_words", C.c_uint64),
-                ("mphf_bytes", C.c_uint64), ("values_bytes", C.c_uint64), ("node_bytes", C.c_uint64),
-                ("seq_bytes", C.c_uint64), ("eq_bytes", C.c_uint64), ("bloom_bytes", C.c_uint64),
+                ("dict_bytes", C.c_uint64), ("node_bytes", C.c_uint64),
+                ("seq_bytes", C.c_uint64), ("eq_bytes", C.c_uint64),
                 ("node_bits", C.c_uint32), ("pos_bits", C.c_uint32), ("fp_bits", C.c_uint32),
                 ("max_class_len", C.c_uint32), ("gamma", C.c_double), ("build_ms", C.c_double)]
 
@@ -83,7 +83,7 @@ EXPORTS = (
     "psa_mapper_profile_enable", "psa_mapper_profile_read",
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
-    "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe",
+    "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe", "psa_result_checksum",
 )
 
 
@@ -150,6 +150,8 @@ def lib():
     L.psa_memcpy_d2h.restype, L.psa_memcpy_d2h.argtypes = i32, [vp, vp, u64]
     L.psa_gather_probe.restype = i32
     L.psa_gather_probe.argtypes = [i32, u64, u32, u32, C.POINTER(C.c_double)]
+    L.psa_result_checksum.restype = i32
+    L.psa_result_checksum.argtypes = [i32, vp, vp, u64, u64, C.POINTER(u64)]
     L.psa_process_reads.restype = i32
     L.psa_process_reads.argtypes = [vp, C.c_char_p, C.c_char_p, u32, u64, i32, C.POINTER(_ProcessStats)]
     _lib = L
@@ -314,6 +316,12 @@ class DeviceBatch:
         tx = self.tx.to_numpy(np.uint32, min(used, self.tx_cap)) if self.tx else np.zeros(0, np.uint32)
         return hits, tx
 
+    def checksum(self, first_index=0, device=0):
+        """Order-independent checksum of the batch's results (psa_result_checksum)."""
+        out = C.c_uint64()
+        _check(lib().psa_result_checksum(int(device), self.hits.ptr, self.tx.ptr, self.n, int(first_index), C.byref(out)))
+        return int(out.value)
+
     def free(self):
         for b in (self.data, self.read_off, self.read_len, self.hits, self.tx):
             if b is not None:
@@ -408,7 +416,7 @@ class Mapper:
         _check(lib().psa_mapper_sync(self.h))
 
     def map_device_events(self, batch, split=False):
-        """Event counts of one batch; split=True -> per kernel (k_map_thread, k_map, k_seed_scan)."""
+        """Event counts of one batch; split=True -> per kernel (k_map_lanes, k_map, k_seed_scan)."""
         ev = (_Events * 3)()
         _check(lib().psa_mapper_map_events(self.h, C.byref(batch.rb), C.byref(batch.ob), C.byref(ev)))
         parts = [{f: int(getattr(e, f)) for f in EVENT_FIELDS} for e in ev]
@@ -469,7 +477,7 @@ class Mapper:
         """-> {kernel: (summed device ms, launches)} since the last read."""
         ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
         _check(lib().psa_mapper_profile_read(self.h, C.byref(ms), C.byref(n)))
-        return {"k_map_thread": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1])),
+        return {"k_map_lanes": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1])),
                 "k_seed_scan": (float(ms[2]), int(n[2]))}
 
     def close(self):

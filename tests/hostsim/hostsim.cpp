@@ -1,14 +1,16 @@
 // hostsim.cpp -- UNIT-TEST HARNESS, not product code.
 //
-// Compiles rust-pseudoaligner_b200/csrc/psa_core.cuh (the __host__ __device__ arithmetic the
-// CUDA kernels are made of: 2-bit access, k-mer hash, sector-block MPHF probe, value packing,
-// fingerprint + verification, per-word mismatch masks, the map_read state machine) with g++
-// and a serial "warp" policy, so that the tests that run without a GPU can compare that text
-// against the oracle.  It is built into tests/hostsim/libhostsim.so, loaded only by
-// tests/test_hostsim.py, and never linked into libpsa_b200.so -- the product has no CPU path.
-// The MPHF here is built serially on the host with the same layout rules the device builder
-// uses (level size = floor(gamma*n/192)+1 blocks, bits cleared on collision, cumulative rank
-// header), so the probe code sees a structure of identical shape.
+// Compiles rust-pseudoaligner_b200/csrc/psa_core.cuh and psa_lanes.cuh (the __host__ __device__
+// arithmetic the CUDA kernels are made of: 2-bit access, k-mer hash, the bucket-cascade dictionary,
+// fingerprint + verification, per-word mismatch masks, class windows, the map_read state machine in
+// its blocking form and as the per-lane state machine of the thread-per-read kernel) with g++ and
+// serial drivers, so that the tests that run without a GPU can compare that text against the oracle.
+// It is built into tests/hostsim/libhostsim.so, loaded only by tests/test_hostsim.py, and never
+// linked into libpsa_b200.so -- the product has no CPU path.
+// The dictionary here is built serially on the host with the same layout rules the device builder
+// uses (level size = floor(gamma*n/4)+1 buckets, keys in enumeration order, at most four per bucket
+// and no two with one fingerprint, the rest passed on), so the probe code sees a structure of
+// identical shape.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,16 +19,17 @@
 #include <vector>
 
 #include "../../rust-pseudoaligner_b200/csrc/psa_core.cuh"
+#include "../../rust-pseudoaligner_b200/csrc/psa_lanes.cuh"
 
 using namespace psa;
 
 struct HsIndex {
     DevIndex d{};
-    std::vector<uint64_t> blocks, values, seq, eq_off;
+    std::vector<uint64_t> buckets, seq, eq_off;
     std::vector<NodeRec> nodes;
+    std::vector<NodeCold> cold;
     std::vector<uint32_t> eq_mem;
     std::vector<ClassWin> class_win;
-    std::vector<uint32_t> bloom;
     int kw = 1;
     int error = 0;
 };
@@ -56,95 +59,83 @@ static void build(HsIndex* ix, uint32_t k, uint64_t n_nodes, const uint64_t* nod
     auto bits_for = [](uint64_t v) { uint32_t b = 1; while (b < 64 && (v >> b)) b++; return b; };
     D.k = k;
     D.node_bits = bits_for(n_nodes ? n_nodes - 1 : 0);
-    D.pos_bits = bits_for(max_pos);
-    int fp = 64 - (int)D.node_bits - (int)D.pos_bits;
-    D.fp_bits = fp <= 0 ? 0 : (uint32_t)std::min(fp, 32);
+    D.pos_bits = bits_for(max_pos + 1);
+    int fp = 63 - (int)D.node_bits - (int)D.pos_bits;
+    if (fp < 8) { ix->error = 5; return; }
+    D.fp_bits = (uint32_t)std::min(fp, 32);
     D.n_nodes = n_nodes;
     D.n_kmers = n_kmers;
 
-    // cascade
-    std::vector<KeyHash> rem_h(n_kmers);
-    for (uint64_t i = 0; i < n_kmers; i++) rem_h[i] = make_hash(KmerOps<KW>::fold(keys[i]));
-    // absent-key prefilter, same layout rule as the device builder
-    {
-        const uint64_t nb = std::max<uint64_t>(1, (n_kmers * kBloomBitsPerKey + 255) / 256);
-        ix->bloom.assign(8 * nb, 0);
-        for (uint64_t i = 0; i < n_kmers; i++) {
-            uint64_t blk, bits;
-            bloom_pos(rem_h[i], nb, blk, bits);
-            for (int w = 0; w < 8; w++) ix->bloom[8 * blk + w] |= 1u << ((bits >> (5 * w)) & 31);
-        }
-        D.bloom = Bloom{ix->bloom.data(), nb};
+    // nodes (the dictionary entries need their starts)
+    ix->nodes.resize(n_nodes + 1);
+    ix->cold.resize(n_nodes + 1);
+    for (uint64_t i = 0; i < n_nodes; i++) {
+        NodeRec& r = ix->nodes[i];
+        NodeCold& c = ix->cold[i];
+        r.start_len = pack_start_len(node_start[i], node_len[i]); r.eq = node_eq[i]; c.exts = node_exts[i]; c.pad = 0;
+        r.class_len = (uint32_t)(ix->eq_off[r.eq + 1] - ix->eq_off[r.eq]);
+        c.class_off = ix->eq_off[r.eq];
+        for (int b = 0; b < 4; b++) r.succ[b] = c.pred[b] = kNone;
+        const ClassWin& w = ix->class_win[r.eq];
+        r.win_lo = w.lo; r.win_len = w.len; r.win_bits[0] = w.bits[0]; r.win_bits[1] = w.bits[1]; r.win_bits[2] = w.bits[2];
     }
-    std::vector<KeyHash> cur = rem_h;
-    uint64_t total_blk = 0;
+    D.nodes = ix->nodes.data();
+    D.nodes_cold = ix->cold.data();
+
+    // cascade
+    std::vector<uint64_t> cur(n_kmers);
+    for (uint64_t i = 0; i < n_kmers; i++) cur[i] = i;
+    uint64_t total_bkt = 0;
     uint32_t lvl = 0;
     while (!cur.empty()) {
         if (lvl >= (uint32_t)kMaxLevels) { ix->error = 1; return; }
-        uint64_t nblk = std::max<uint64_t>(1, (uint64_t)(gamma * (double)cur.size() / kBlockBits) + 1);
-        ix->blocks.resize(4 * (total_blk + nblk), 0);
-        std::vector<uint64_t> coll(4 * nblk, 0);
-        for (KeyHash h : cur) {
-            uint64_t blk; uint32_t bit;
-            level_pos(level_hash(h, lvl), nblk, blk, bit);
-            uint64_t& w = ix->blocks[4 * (total_blk + blk) + 1 + (bit >> 6)];
-            uint64_t m = 1ULL << (bit & 63);
-            if (w & m) coll[4 * blk + 1 + (bit >> 6)] |= m;
-            w |= m;
+        const uint64_t nbkt = std::max<uint64_t>(1, (uint64_t)(gamma * (double)cur.size() / kBucketSlots) + 1);
+        ix->buckets.resize(4 * (total_bkt + nbkt), kEmptyEntry);
+        std::vector<uint8_t> cnt(nbkt, 0);
+        std::vector<uint64_t> next;
+        for (uint64_t i : cur) {
+            const KeyHash hk = make_hash(KmerOps<KW>::fold(keys[i]));
+            const uint64_t b = level_bucket(hk, lvl, nbkt);
+            uint64_t* e = &ix->buckets[4 * (total_bkt + b)];
+            const uint64_t fpv = fp_of(hk, D.fp_bits);
+            bool clash = cnt[b] >= kBucketSlots;
+            for (uint32_t q = 0; q < cnt[b]; q++)
+                clash |= ((e[q] & ~kMoreBit) >> (D.node_bits + D.pos_bits)) == fpv;
+            if (clash) {
+                next.push_back(i);
+                e[0] |= kMoreBit;  // (cnt[b] >= 1 here)
+                continue;
+            }
+            const uint32_t node = (uint32_t)(vals[i] >> 32);
+            e[cnt[b]] = pack_entry(D, node, node_start[node] + (uint32_t)vals[i], hk);
+            cnt[b]++;
         }
-        std::vector<KeyHash> next;
-        for (KeyHash h : cur) {
-            uint64_t blk; uint32_t bit;
-            level_pos(level_hash(h, lvl), nblk, blk, bit);
-            if ((coll[4 * blk + 1 + (bit >> 6)] >> (bit & 63)) & 1) next.push_back(h);
-        }
-        for (uint64_t i = 0; i < 4 * nblk; i++) ix->blocks[4 * total_blk + i] &= ~coll[i];
-        D.mphf.level_nblk[lvl] = nblk;
-        D.mphf.level_base[lvl] = total_blk;
-        total_blk += nblk;
+        D.dict.level_nbkt[lvl] = nbkt;
+        D.dict.level_base[lvl] = total_bkt;
+        total_bkt += nbkt;
         lvl++;
         cur.swap(next);
     }
-    D.mphf.n_levels = lvl;
-    uint64_t rank = 0;
-    for (uint64_t b = 0; b < total_blk; b++) {
-        uint32_t c1 = popc64(ix->blocks[4 * b + 1]), c2 = c1 + popc64(ix->blocks[4 * b + 2]);
-        ix->blocks[4 * b] = make_header(rank, c1, c2);
-        rank += c2 + popc64(ix->blocks[4 * b + 3]);
-    }
-    if (rank != n_kmers) { ix->error = 2; return; }
-    D.mphf.blocks = ix->blocks.data();
-    ix->values.assign(n_kmers + 1, 0);
-    D.values = ix->values.data();
-    std::vector<uint8_t> seen(n_kmers, 0);
+    D.dict.n_levels = lvl;
+    D.dict.buckets = ix->buckets.data();
     for (uint64_t i = 0; i < n_kmers; i++) {
-        uint64_t slot; uint32_t levels;
-        if (!mphf_lookup(D.mphf, rem_h[i], slot, levels) || slot >= n_kmers || seen[slot]) { ix->error = 3; return; }
-        seen[slot] = 1;
-        ix->values[slot] = pack_value(D, (uint32_t)(vals[i] >> 32), node_start[vals[i] >> 32] + (uint32_t)vals[i], rem_h[i]);
+        uint32_t n = 0, o = 0;
+        if (!dict_get<KW>(D, keys[i], n, o, nullptr) || n != (uint32_t)(vals[i] >> 32) || o != (uint32_t)vals[i]) { ix->error = 3; return; }
     }
-    // nodes + edges
-    ix->nodes.resize(n_nodes + 1);
+    // edges
     for (uint64_t i = 0; i < n_nodes; i++) {
         NodeRec& r = ix->nodes[i];
-        r.start_len = pack_start_len(node_start[i], node_len[i]); r.eq = node_eq[i]; r.exts = node_exts[i]; r.pad = 0;
-        r.class_len = (uint32_t)(ix->eq_off[r.eq + 1] - ix->eq_off[r.eq]);
-        r.class_off = ix->eq_off[r.eq];
-        for (int b = 0; b < 4; b++) r.succ[b] = r.pred[b] = kNone;
-    }
-    D.nodes = ix->nodes.data();
-    for (uint64_t i = 0; i < n_nodes; i++) {
-        NodeRec& r = ix->nodes[i];
+        NodeCold& c = ix->cold[i];
         Kmer<KW> first = KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i], k);
         Kmer<KW> last = KmerOps<KW>::get(PLoad{ix->seq.data()}, node_start[i] + node_len[i] - k, k);
         for (uint32_t b = 0; b < 4; b++) {
             uint32_t n, o;
-            if ((r.exts >> b) & 1) {
+            if ((c.exts >> b) & 1) {
                 if (dict_get<KW>(D, KmerOps<KW>::extend_right(last, b, k), n, o, nullptr) && o == 0) r.succ[b] = n;
                 else ix->error = 4;
             }
-            if ((r.exts >> (4 + b)) & 1) {
-                if (dict_get<KW>(D, KmerOps<KW>::extend_left(first, b, k), n, o, nullptr) && o == node_len[n] - k) r.pred[b] = n;
+            if ((c.exts >> (4 + b)) & 1) {
+                if (dict_get<KW>(D, KmerOps<KW>::extend_left(first, b, k), n, o, nullptr) && o == node_len[n] - k) c.pred[b] = n;
                 else ix->error = 4;
             }
         }
@@ -167,7 +158,7 @@ struct SerialWarp {
         // lane order == position order, so the first hitting lane is the sequential first hit
         for (P p = start; p <= last; p += kSeedStride) {
             lookups++;
-            if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr, p != start)) { kmer_pos = p; return true; }
+            if (dict_get<KW>(ix, KmerOps<KW>::get(rd, p, k), node, off, nullptr)) { kmer_pos = p; return true; }
         }
         kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);
         return false;
@@ -176,7 +167,7 @@ struct SerialWarp {
     bool abort() const { return false; }
     NodeView node(uint32_t id) const { return load_node_view(ix.nodes + id); }
     void jumped() {}
-    uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes[id].pred[b]; }
+    uint32_t pred(uint32_t id, uint32_t b) { return ix.nodes_cold[id].pred[b]; }
     // the two compare loops, chunked by 32 bases exactly as the kernel lanes are
     template <bool FWD, class P>
     P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
@@ -239,7 +230,7 @@ HsIndex* hs_index_create(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words
                          const uint32_t* eq_members, double gamma) {
     HsIndex* ix = new HsIndex();
     ix->seq.assign(seq_words, seq_words + n_seq_words);
-    ix->seq.push_back(0); ix->seq.push_back(0);
+    for (int i = 0; i < 8; i++) ix->seq.push_back(0);
     ix->eq_off.assign(eq_offsets, eq_offsets + n_eq + 1);
     ix->eq_mem.assign(eq_members, eq_members + eq_offsets[n_eq]);
     ix->d.seq = ix->seq.data();
@@ -257,7 +248,7 @@ HsIndex* hs_index_create(uint32_t k, uint64_t n_nodes, const uint64_t* seq_words
     return ix;
 }
 int hs_index_error(const HsIndex* ix) { return ix->error; }
-uint32_t hs_index_levels(const HsIndex* ix) { return ix->d.mphf.n_levels; }
+uint32_t hs_index_levels(const HsIndex* ix) { return ix->d.dict.n_levels; }
 uint32_t hs_index_fp_bits(const HsIndex* ix) { return ix->d.fp_bits; }
 void hs_index_destroy(HsIndex* ix) { delete ix; }
 
@@ -278,47 +269,103 @@ uint64_t hs_map_batch(const HsIndex* ix, const uint64_t* words, const uint64_t* 
     return tx.size();
 }
 
-// The fast kernel's one-thread-per-read policy (psa_core.cuh ThreadCtx / map_read_thread), with
-// deferred reads redone by the serial stand-in of the cooperative kernel -- the same split the
-// product makes between k_map_thread and k_map.  *n_deferred receives the number of deferrals.
-struct HostNovel {
-    std::vector<uint32_t> buf;
-    uint32_t* operator()(uint32_t count, uint64_t& off) {
-        off = 0;
-        buf.assign(count, 0);
-        return buf.data();
+}  // extern "C"
+
+// The thread-per-read kernel's lane state machine (psa_lanes.cuh), driven serially: the requests a
+// step makes are served from host memory before the next step, exactly as k_map_lanes serves them
+// from HBM.  Reads a lane hands over are redone by the serial stand-in of the cooperative kernel --
+// the same split the product makes between k_map_lanes and k_seed_scan / k_map.  `hinted` != 0
+// imitates the second pass: the first seed of every read is searched by the serial policy and given
+// to the lane as k_seed_scan would.
+struct HostWords {
+    uint64_t w[8];
+    uint64_t operator()(uint64_t i) const { return w[i]; }
+    void store(uint32_t i, uint64_t v) { w[i] = v; }
+};
+struct HostSink {
+    HsHit* hit;
+    std::vector<uint32_t> novel_buf;
+    bool got = false;
+    void result(uint32_t, const HitRec& h, uint64_t) {
+        hit->coverage = h.coverage; hit->n_tx = h.n_tx; hit->tx_off = h.tx_off; hit->eq_id = h.eq_id; hit->flags = h.flags;
+        got = true;
     }
+    uint32_t* novel(uint32_t count, uint64_t& off) {
+        off = 0;
+        novel_buf.assign(count, 0);
+        return novel_buf.data();
+    }
+    void novel_overflow() {}
 };
 
-uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,
-                             const uint32_t* read_len, uint64_t n, uint32_t allowed, uint32_t max_probes,
-                             uint32_t max_small, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap, uint64_t* n_deferred) {
-    std::vector<uint32_t> tx;
-    uint64_t nd = 0;
-    for (uint64_t i = 0; i < n; i++) {
-        HostNovel novel;
-        ThreadResult r;
-        if (read_len[i] <= 192) {  // the register-resident reader of the fixed-length kernel variant
-            const uint64_t* q = words + read_off[i];
-            const uint32_t nw = (read_len[i] + 31) / 32;
-            RegLoad6 rr{nw > 0 ? q[0] : 0, nw > 1 ? q[1] : 0, nw > 2 ? q[2] : 0, nw > 3 ? q[3] : 0, nw > 4 ? q[4] : 0, nw > 5 ? q[5] : 0};
-            if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, rr, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
-            else r = map_read_thread<2, false>(ix->d, rr, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
-        } else if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, PLoad{words + read_off[i]}, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
-        else r = map_read_thread<2, false>(ix->d, PLoad{words + read_off[i]}, read_len[i], allowed, max_probes, max_small, novel, true, nullptr);
-        if (r.deferred) {
-            nd++;
-            if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
-            else map_one<2>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
-            continue;
+template <int KW>
+static uint32_t lane_one(const HsIndex* ix, const uint64_t* words, uint32_t L, const LaneParams& lp, const uint32_t* hint,
+                         HsHit& h, std::vector<uint32_t>& tx, uint64_t* steps) {
+    Lane<KW, false> ln;
+    ln.idle();
+    ln.begin(0, L, 8, hint);
+    HostWords rw{};
+    HostSink sink{&h, {}};
+    Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
+    const uint32_t nw = (L + 31) / 32;
+    for (;;) {
+        if (ln.st == LS_READ) {
+            A.w0 = nw > 0 ? words[0] : 0; A.w1 = nw > 1 ? words[1] : 0; A.w2 = nw > 2 ? words[2] : 0; A.w3 = nw > 3 ? words[3] : 0;
+            if (nw > 4) { C.w0 = words[4]; C.w1 = nw > 5 ? words[5] : 0; C.w2 = nw > 6 ? words[6] : 0; C.w3 = nw > 7 ? words[7] : 0; }
+        } else {
+            if (ln.reqA) A = load_sector_hot(ln.reqA);
+            if (ln.reqB) B = load_sector_hot(ln.reqB);
+            if (ln.reqC) { C.w0 = ln.reqC[0]; C.w1 = ln.reqC[1]; C.w2 = ln.reqC[2]; C.w3 = ln.reqC[3]; }
         }
-        HsHit& h = hits[i];
-        h.coverage = r.hit.coverage; h.n_tx = r.hit.n_tx; h.eq_id = r.hit.eq_id; h.flags = r.hit.flags;
+        ln.step(ix->d, lp, rw, A, B, C, sink);
+        if (steps) (*steps)++;
+        if (ln.emit != LE_NONE) break;
+    }
+    if (ln.emit == LE_RESULT) {
         h.tx_off = tx.size();
-        const uint32_t* src = r.hit.eq_id != kNone ? ix->eq_mem.data() + r.hit.tx_off : novel.buf.data();
-        tx.insert(tx.end(), src, src + r.hit.n_tx);
+        const uint32_t* src = h.eq_id != kNone ? ix->eq_mem.data() + ix->eq_off[h.eq_id] : sink.novel_buf.data();
+        tx.insert(tx.end(), src, src + h.n_tx);
+    }
+    return ln.emit;
+}
+
+extern "C" {
+
+uint64_t hs_map_batch_lanes(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,
+                            const uint32_t* read_len, uint64_t n, uint32_t allowed, uint32_t max_probes,
+                            uint32_t max_small, int hinted, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap,
+                            uint64_t* n_deferred, uint64_t* n_steps) {
+    std::vector<uint32_t> tx;
+    uint64_t nd = 0, steps = 0;
+    LaneParams lp;
+    lp.allowed = allowed; lp.max_probes = max_probes; lp.max_small = max_small; lp.want_members = true; lp.to_scan = !hinted;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t* q = words + read_off[i];
+        const uint32_t L = read_len[i];
+        uint32_t hint[3];
+        bool have_hint = false;
+        if (hinted && L >= ix->d.k) {  // the first search, as k_seed_scan makes it
+            uint32_t pos = 0, node = 0, off = 0;
+            bool found;
+            if (ix->kw == 1) { SerialWarp<1> w{ix->d, PLoad{q}, ix->d.k, {}, {}}; found = w.find_seed(pos, L - ix->d.k, node, off); }
+            else { SerialWarp<2> w{ix->d, PLoad{q}, ix->d.k, {}, {}}; found = w.find_seed(pos, L - ix->d.k, node, off); }
+            if (found) { hint[0] = pos; hint[1] = node; hint[2] = off; have_hint = true; }
+            else {  // no seed at all: k_seed_scan finishes the read
+                hits[i].coverage = 0; hits[i].n_tx = 0; hits[i].tx_off = tx.size(); hits[i].eq_id = kNone; hits[i].flags = 0;
+                continue;
+            }
+        }
+        uint32_t emit;
+        if (ix->kw == 1) emit = lane_one<1>(ix, q, L, lp, have_hint ? hint : nullptr, hits[i], tx, &steps);
+        else emit = lane_one<2>(ix, q, L, lp, have_hint ? hint : nullptr, hits[i], tx, &steps);
+        if (emit != LE_RESULT) {
+            nd++;
+            if (ix->kw == 1) map_one<1>(ix, q, L, allowed, hits[i], tx);
+            else map_one<2>(ix, q, L, allowed, hits[i], tx);
+        }
     }
     if (n_deferred) *n_deferred = nd;
+    if (n_steps) *n_steps = steps;
     memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
     return tx.size();
 }

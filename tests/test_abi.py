@@ -37,7 +37,7 @@ def test_no_compute_without_gpu_is_an_error_not_a_fallback():
     """Without a device the library must fail loudly (PSA_ERR_CUDA), never compute on the CPU."""
     import numpy as np
     L = pkg.lib()
-    assert L.psa_abi_version() == 1
+    assert L.psa_abi_version() == 2
     assert L.psa_strerror(-2) == b"CUDA error"
     try:
         import torch

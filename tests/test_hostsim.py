@@ -2,10 +2,11 @@
 
 tests/hostsim/ compiles rust-pseudoaligner_b200/csrc/psa_core.cuh with g++ and a serial warp
 policy; here its results are compared with the oracle read by read.  This pins, without a
-GPU: the MPHF block layout + rank + fingerprint + verification, the successor/predecessor
-tables, the 32-base mismatch masks of both extension loops, the map_read state machine as the
-kernel runs it, and ASCII packing.  (The warp-shuffle glue itself is covered by the
-`-m gpu` parity tests.)"""
+GPU: the bucket-cascade dictionary layout + fingerprint + verification, the
+successor/predecessor tables, the mismatch masks of both extension loops, the map_read state
+machine in its blocking form (cooperative kernels) AND as the per-lane state machine of the
+thread-per-read kernel (psa_lanes.cuh, every request served serially), class windows, and ASCII
+packing.  (The warp-level glue itself is covered by the `-m gpu` parity tests.)"""
 import ctypes as C
 import os
 import subprocess
@@ -20,12 +21,10 @@ import util
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 
 
-# the default build, and the build with the experiment switches of psa_core.cuh that change host-visible
-# arithmetic turned on (PSA_CMP_CARRY: every word of the forward compare loaded once)
-@pytest.fixture(scope="module", params=["libhostsim.so", "libhostsim_carry.so"])
-def hs(request):
-    subprocess.check_call(["make", "-C", _DIR, request.param], stdout=subprocess.DEVNULL)
-    L = C.CDLL(os.path.join(_DIR, request.param))
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["make", "-C", _DIR, "libhostsim.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(_DIR, "libhostsim.so"))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.hs_index_create.restype = vp
     L.hs_index_create.argtypes = [u32, u64, vp, u64, vp, vp, vp, vp, u64, vp, vp, C.c_double]
@@ -36,8 +35,8 @@ def hs(request):
     L.hs_lookup.restype, L.hs_lookup.argtypes = C.c_int, [vp, vp, C.POINTER(u32), C.POINTER(u32)]
     L.hs_map_batch.restype = u64
     L.hs_map_batch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64]
-    L.hs_map_batch_thread.restype = u64
-    L.hs_map_batch_thread.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, vp, vp, u64, C.POINTER(u64)]
+    L.hs_map_batch_lanes.restype = u64
+    L.hs_map_batch_lanes.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, C.c_int, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.hs_pack_ascii.argtypes = [C.c_char_p, u64, vp]
     return L
 
@@ -67,38 +66,39 @@ class HsIndex:
                 return hits, tx[:need]
             cap = int(need)
 
-    def map_batch_thread(self, words, off, lens, max_probes, max_small, allowed=2):
-        """The fast kernel's one-thread-per-read policy, deferrals redone by the serial policy."""
+    def map_batch_lanes(self, words, off, lens, max_probes, max_small, allowed=2, hinted=False):
+        """The thread-per-read kernel's lane state machine, hand-overs redone by the serial policy.
+        -> (hits, tx, reads handed over, steps made)"""
         n = len(lens)
         hits = np.zeros(n, dtype=orc.HIT_DTYPE)
         cap = max(64 * n, 4096)
-        nd = C.c_uint64()
+        nd, ns = C.c_uint64(), C.c_uint64()
         while True:
             tx = np.zeros(cap, np.uint32)
-            need = self.L.hs_map_batch_thread(self.h, _p(words), _p(off), _p(lens), n, allowed, max_probes, max_small,
-                                              _p(hits), _p(tx), cap, C.byref(nd))
+            need = self.L.hs_map_batch_lanes(self.h, _p(words), _p(off), _p(lens), n, allowed, max_probes, max_small,
+                                             1 if hinted else 0, _p(hits), _p(tx), cap, C.byref(nd), C.byref(ns))
             if need <= cap:
-                return hits, tx[:need], int(nd.value)
+                return hits, tx[:need], int(nd.value), int(ns.value)
             cap = int(need)
 
     def close(self):
         self.L.hs_index_destroy(self.h)
 
 
-def _compare(ix_orc, ix_hs, reads, thread_cfgs=((1, 4), (3, 64), (64, 1 << 30))):
+def _compare(ix_orc, ix_hs, reads, lane_cfgs=((1, 4, False), (3, 64, False), (64, 1 << 30, False), (10, 32, True)), allowed=2):
     words, off, lens = orc.pack_reads(reads)
-    h1, t1, _, _ = ix_orc.map_batch(words, off, lens)
-    h2, t2 = ix_hs.map_batch(words, off, lens)
+    h1, t1, _, _ = ix_orc.map_batch(words, off, lens, allowed=allowed)
+    h2, t2 = ix_hs.map_batch(words, off, lens, allowed=allowed)
     a, b = orc.hits_to_tuples(h1, t1), orc.hits_to_tuples(h2, t2)
     for i, (x, y) in enumerate(zip(a, b)):
         assert x == y, (i, reads[i], x, y)
     assert np.array_equal(h1["eq_id"], h2["eq_id"])
-    # the thread-per-read policy with its deferrals: same results whatever the split
-    for max_probes, max_small in thread_cfgs:
-        h3, t3, nd = ix_hs.map_batch_thread(words, off, lens, max_probes, max_small)
+    # the lane state machine with its hand-overs: same results whatever the split, with and without a given first seed
+    for max_probes, max_small, hinted in lane_cfgs:
+        h3, t3, nd, _ = ix_hs.map_batch_lanes(words, off, lens, max_probes, max_small, allowed=allowed, hinted=hinted)
         c = orc.hits_to_tuples(h3, t3)
         for i, (x, y) in enumerate(zip(a, c)):
-            assert x == y, ("thread", max_probes, max_small, i, reads[i], x, y)
+            assert x == y, ("lanes", max_probes, max_small, hinted, i, reads[i], x, y)
         assert np.array_equal(h1["eq_id"], h3["eq_id"])
         assert np.array_equal(t1, t3)
         _DEFER[(max_probes, max_small)] = _DEFER.get((max_probes, max_small), 0) + nd
@@ -109,17 +109,19 @@ def _compare(ix_orc, ix_hs, reads, thread_cfgs=((1, 4), (3, 64), (64, 1 << 30)))
 _DEFER = {}
 
 
-def test_thread_policy_defers_some_but_not_all(hs, orc_index_for, fixture_fasta):
-    """With one probe per seed search the fast policy must hand the noisy reads over and keep
-    the clean ones; with unbounded probes only class-list overflows are handed over."""
+def test_lanes_hand_over_some_but_not_all(hs, orc_index_for, fixture_fasta):
+    """With one probe per seed search the lanes must hand the noisy reads over and keep the clean
+    ones; with unbounded probes only class-list overflows are handed over.  A clean 150-base read
+    takes a handful of steps (one request round trip each)."""
     ix = orc_index_for(20)
     hx = HsIndex(hs, ix.flat())
     rng = np.random.default_rng(5)
     reads = util.sample_reads(rng, fixture_fasta[1], 3000, 150, p_sub=0.005)
     words, off, lens = orc.pack_reads(reads)
-    _, _, nd1 = hx.map_batch_thread(words, off, lens, 1, 64)
-    _, _, nd64 = hx.map_batch_thread(words, off, lens, 64, 1 << 30)
-    assert 0 < nd64 <= nd1 < len(reads) // 2, (nd1, nd64)
+    _, _, nd1, _ = hx.map_batch_lanes(words, off, lens, 1, 64)
+    _, _, nd64, steps = hx.map_batch_lanes(words, off, lens, 64, 1 << 30)
+    assert 0 <= nd64 <= nd1 < len(reads) // 2 and nd1 > 0, (nd1, nd64)
+    assert 5 * len(reads) < steps < 20 * len(reads), steps / len(reads)
     hx.close()
 
 
