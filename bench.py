@@ -631,7 +631,7 @@ def main():
     # the map step is two kernels: k_map_lanes (one thread per read) and k_map (cooperative, the reads
     # k_map_lanes handed over); each is charged the algorithmic bytes of the reads it completed
     kernels = {}
-    for name, part in (("k_map_lanes", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
+    for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
         k_ms, k_n = prof[name]
         if not k_n:
             continue
@@ -666,7 +666,7 @@ def main():
                 "algorithmic_bytes_per_read": a_bytes_per_read,
                 "sector_model_bytes_per_read": sector_bytes(ev, a.k) / ev["reads"],
                 "map_step_achieved_gbs": a_bytes_per_read * R / (sum(v["ms_per_step"] for v in kernels.values()) / 1e3) / 1e9,
-                "peak_source": peak_src, "handed_over_by_k_map_lanes": deferred_by,
+                "peak_source": peak_src, "handed_over_by_k_map_thread": deferred_by,
                 "kernel_timing": ("CUDA events around every map kernel, inside the timed region" if M == 1 else
                                   "CUDA events around every map kernel over the same %d steps run once more on ONE mapper "
                                   "(%.3f ms per step): in the timed region the kernels of %d mappers overlap" % (a.steps, prof_ms / a.steps, M)),

@@ -35,6 +35,7 @@ extern "C" {
                                  out of range                                              */
 #define PSA_ERR_NCCL (-6)     /* NCCL error or libnccl not loadable                        */
 #define PSA_ERR_IO (-7)       /* file could not be read / parsed                           */
+#define PSA_ERR_INTERNAL (-8) /* an internal self-check failed (never a wrong answer)      */
 
 const char* psa_strerror(int code);
 /* Text of the last error raised on the calling thread ("" if none). */
@@ -197,12 +198,32 @@ void* psa_mapper_stream(psa_mapper*); /* cudaStream_t */
 int psa_mapper_map_read(psa_mapper*, const uint64_t* read_words, uint32_t read_len,
                         uint32_t* tx_out, uint64_t tx_cap, uint32_t* n_tx, uint32_t* coverage);
 
-/* counts[c] for c < n_eq: reads whose eq_class equals index class c; counts[n_eq]: aligned
- * reads whose set is no visited class (incl. the empty set); counts[n_eq+1]: None.
- * The array has n_eq+2 entries. */
+/* counts[c] for c < n_eq: reads whose eq_class equals index class c; counts[n_eq+1]: None.
+ * Reads whose eq_class is NO index class are counted per distinct set in the mapper's novel-set
+ * table (below); counts[n_eq] is the sum of that table, kept so that the array always sums to the
+ * reads mapped.  The array has n_eq+2 entries. */
 int psa_mapper_counts_get(psa_mapper*, uint64_t* counts_host);
 int psa_mapper_counts_reset(psa_mapper*);
 void* psa_mapper_counts_device(psa_mapper*); /* uint64[n_eq+2] in HBM */
+
+/* Novel sets.  map_read returns the transcript SET (ref src/pseudoaligner.rs:323-356, :381-384); most
+ * sets equal the class of a visited node and carry that class's id (psa_hit.eq_id), the others --
+ * intersections that no k-mer of the index has as its colour, incl. the empty set -- have
+ * eq_id == PSA_EQ_NONE in psa_hit and are counted here, per distinct set, since the last
+ * psa_mapper_counts_reset.  The view is sorted by (length, contents): the id of set i is n_eq + i.
+ * Ids of this kind are final only once the run is complete (a later batch may bring a set that sorts
+ * earlier); they are deterministic -- the same reads give the same table whatever the batching, the
+ * kernel split or the number of GPUs (psa_novel_sets_merge / psa_mapper_novel_allgather). */
+typedef struct psa_novel_sets {
+    uint64_t n_sets, n_members;
+    uint64_t* offsets; /* n_sets + 1                                                          */
+    uint32_t* members; /* set i = members[offsets[i] .. offsets[i+1]), ascending              */
+    uint64_t* counts;  /* reads whose eq_class is set i                                       */
+} psa_novel_sets;
+int psa_mapper_novel_sets(psa_mapper*, psa_novel_sets* out); /* arrays malloc'ed: psa_novel_sets_free */
+/* The union of several views (e.g. one per GPU), equal sets merged, counts added, sorted again. */
+int psa_novel_sets_merge(const psa_novel_sets* parts, uint32_t n_parts, psa_novel_sets* out);
+void psa_novel_sets_free(psa_novel_sets*);
 
 /* Work actually done by the mapper's kernels since the last reset, in the units of the
  * algorithmic-bytes model of DESIGN.md (sequential-equivalent events: speculative probes
@@ -269,12 +290,22 @@ int psa_comm_create(const uint8_t id[PSA_NCCL_UNIQUE_ID_BYTES], int world, int r
 void psa_comm_destroy(psa_comm*);
 /* ncclAllReduce(sum, uint64, n_eq+2) in place on the mapper's counts, on its stream. */
 int psa_mapper_counts_allreduce(psa_mapper*, psa_comm*);
+/* The novel-set tables of all ranks merged (two ncclAllGather: sizes, then the serialised tables):
+ * every rank receives the same view, ids n_eq + i valid across the whole job. */
+int psa_mapper_novel_allgather(psa_mapper*, psa_comm*, psa_novel_sets* out);
 
 /* ---- measurement aid: GB/s of independent random gathers of chunk_bytes-sized (32, 64 or 128)
  * aligned chunks from a table_bytes table in HBM, one chunk per thread -- the access pattern of
  * the index lookups without their dependencies; the practical ceiling the map kernels are
  * compared with.  chunk_bytes = 0: one random 128-byte line per warp (4 bytes per lane). ---- */
 int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s);
+
+/* ---- self-test entry: the device routines behind nodes_to_eq_class / intersect (ref src/pseudoaligner.rs:323-356,
+ * :389-418) on two ascending lists in isolation: out[0..cap) one thread's list scheme, out[cap..2cap) the cooperative
+ * kernel's lane-group scheme, out[2cap..3cap) the class windows (n_out[2] = PSA_EQ_NONE when a list spans >= 192 ids
+ * and has no window).  The reference's own intersect vectors (ref :544-559) are run through it by the tests. ---- */
+int psa_selftest_intersect(int device, const uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n2,
+                           uint32_t* out, uint32_t cap, uint32_t n_out[3]);
 
 /* ---- verification aid: order-independent 64-bit checksum of a device-resident result batch (the sum over
  * reads of a hash chain over global read index first_index + i, coverage, flags, eq_id and the members in

@@ -53,6 +53,7 @@ extern "C" const char* psa_strerror(int code) {
         case PSA_ERR_INDEX: return "invalid index graph";
         case PSA_ERR_NCCL: return "NCCL error";
         case PSA_ERR_IO: return "I/O error";
+        case PSA_ERR_INTERNAL: return "internal self-check failed";
         default: return "unknown error";
     }
 }
@@ -486,6 +487,8 @@ struct psa_mapper {
     uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
     cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
     DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, pool, running;
+    DevBuf ntab, ntab_backup, ncur_backup, npool, ncur, nlist, nslot;   // the novel-set table (NovelTable), this batch's list of novel reads and their entries
+    uint64_t ntab_cap = 1ull << 18, npool_cap = 1ull << 22;
     DevBuf words, woff, nwords, dst_off, scan_tmp, meta, deferred, scan_list, seeded, seeded_ev;
     uint64_t novel_cap = 0;
     uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
@@ -494,6 +497,8 @@ struct psa_mapper {
     uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
     bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
+    bool fast_kernel_lanes = false;  // PSA_FAST_KERNEL=lanes: the thread-per-read step as the lane state machine over
+                                     // shared-memory pools (k_map_lanes) instead of one blocking call per read (k_map_thread)
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[kSlots];
@@ -506,23 +511,54 @@ struct psa_mapper {
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
 
-// the lane kernel: persistent warps, one resident wave.  hint: the reads of p.seeded (second pass)
-static int lanes_grid(psa_mapper* m, uint64_t n) {
+// the lane kernel: persistent warps over shared-memory pools of reads in flight, one resident wave.
+// hint: the reads of p.seeded (second pass)
+template <int KW, bool EV, bool HINT>
+static int launch_lanes_kw(psa_mapper* m, cudaStream_t st, const MapParams& p) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->ix->device);
-    const uint64_t full = (uint64_t)sms * PSA_LANE_MIN_BLOCKS;
-    return (int)std::max<uint64_t>(1, std::min<uint64_t>(nblocks(n, kLaneBlock), full));
+    const size_t smem = (size_t)kPoolWarps * pool_bytes_per_warp<KW, EV>(p.lane_words);
+    auto kern = k_map_lanes<KW, EV, HINT>;
+    static thread_local size_t set_for = 0;
+    if (smem > 48 * 1024 && smem > set_for) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set_for = smem;
+    }
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kPoolWarps, smem));
+    if (per_sm < 1) return fail(PSA_ERR_CUDA, "k_map_lanes does not fit the SM's shared memory");
+    const uint64_t pools_needed = (p.reads.n + kPoolItems - 1) / kPoolItems;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((pools_needed + kPoolWarps - 1) / kPoolWarps, (uint64_t)sms * per_sm));
+    kern<<<grid, 32 * kPoolWarps, smem, st>>>(m->ix->d, p);
+    return PSA_OK;
 }
 template <bool EV>
-static void launch_map_lanes(psa_mapper* m, cudaStream_t st, const MapParams& p, bool hint) {
-    const unsigned grid = (unsigned)lanes_grid(m, p.reads.n);
-    const size_t smem = (size_t)kLaneBlock * p.lane_words * 8;
-    if (m->ix->kw == 1) {
-        if (hint) k_map_lanes<1, EV, true><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
-        else k_map_lanes<1, EV, false><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
+static int launch_map_lanes(psa_mapper* m, cudaStream_t st, const MapParams& p, bool hint) {
+    if (m->ix->kw == 1) return hint ? launch_lanes_kw<1, EV, true>(m, st, p) : launch_lanes_kw<1, EV, false>(m, st, p);
+    return hint ? launch_lanes_kw<2, EV, true>(m, st, p) : launch_lanes_kw<2, EV, false>(m, st, p);
+}
+// the blocking thread-per-read kernel (PSA_FAST_KERNEL=thread)
+static uint32_t tile_smem_bytes(const ReadsView& rv) {  // shared memory of the TILE variant, 0 = not eligible
+    if (rv.woff || rv.len || !rv.wstride) return 0;
+    const uint64_t total = 16 + (uint64_t)kThreadBlock * rv.wstride * 8;
+    return total > 12 * 1024 ? 0 : (uint32_t)total;  // longer reads keep the L1 for the index instead
+}
+template <bool EV>
+static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p, bool hint) {
+    if (hint) {  // second pass over the reads k_seed_scan seeded: persistent warps, the list length is on the device
+        const unsigned grid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n, kThreadBlock), 148 * PSA_THREAD_MIN_BLOCKS);
+        if (m->ix->kw == 1) k_map_thread<1, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        return;
+    }
+    const unsigned grid = nblocks(p.reads.n, kThreadBlock);
+    const uint32_t smem = tile_smem_bytes(p.reads);
+    if (smem) {
+        if (m->ix->kw == 1) k_map_thread<1, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, false, true><<<grid, kThreadBlock, smem, st>>>(m->ix->d, p);
     } else {
-        if (hint) k_map_lanes<2, EV, true><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
-        else k_map_lanes<2, EV, false><<<grid, kLaneBlock, smem, st>>>(m->ix->d, p);
+        if (m->ix->kw == 1) k_map_thread<1, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, false><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
     }
 }
 template <bool EV>
@@ -593,6 +629,13 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     if (!m) return fail(PSA_ERR_NOMEM, "out of memory");
     m->ix = ix;
     m->chunk_reads = chunk_reads ? chunk_reads : (1ull << 19);  // 512 Ki: best H2D|kernel|D2H overlap measured on B200
+    // initial size of the novel-set table (it grows on demand; the tests start it tiny)
+    if (const char* e = getenv("PSA_NOVEL_TABLE_CAP")) {
+        uint64_t c = 16;
+        while (c < (uint64_t)std::max(16, atoi(e))) c <<= 1;
+        m->ntab_cap = c;
+        m->npool_cap = 4 * c;
+    }
     int rc = PSA_OK;
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking);
@@ -611,13 +654,16 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     }
     const uint64_t nc = ix->d.n_eq + 2;
     if ((rc = m->counts.ensure(nc * 8)) || (rc = m->counts_backup.ensure(nc * 8)) || (rc = m->status.ensure(8)) ||
-        (rc = m->novel_cursor.ensure(64)) || (rc = m->events.ensure(40 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
+        (rc = m->novel_cursor.ensure(128)) || (rc = m->ntab.ensure(m->ntab_cap * sizeof(NovelEntry))) ||
+        (rc = m->npool.ensure(m->npool_cap * 4)) || (rc = m->ncur.ensure(16)) || (rc = m->events.ensure(40 * 8)) || (rc = m->running.ensure(16)) || (rc = m->meta.ensure(16)) ||
         (rc = m->slot[0].meta_dev.ensure(16)) || (rc = m->slot[1].meta_dev.ensure(16)) ||
         (rc = m->slot[2].meta_dev.ensure(16)) || (rc = m->slot[3].meta_dev.ensure(16))) {
         psa_mapper_destroy(m);
         return rc;
     }
     cudaMemset(m->counts.p, 0, nc * 8);
+    cudaMemset(m->ntab.p, 0, m->ntab_cap * sizeof(NovelEntry));
+    cudaMemset(m->ncur.p, 0, 16);
     cudaMemset(m->events.p, 0, 40 * 8);
     cudaMemset(m->status.p, 0, 8);
     if (const char* e = getenv("PSA_GROUP_WIDTH")) {
@@ -630,6 +676,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
+    if (const char* e = getenv("PSA_FAST_KERNEL")) m->fast_kernel_lanes = strcmp(e, "lanes") == 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
         int g = atoi(e);
         if (g == 0 || g == 8 || g == 16 || g == 32) m->scan_width = (uint32_t)g;
@@ -649,7 +696,7 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
     if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
     DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
-                      &m->running, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
+                      &m->running, &m->ntab, &m->ntab_backup, &m->ncur_backup, &m->npool, &m->ncur, &m->nlist, &m->nslot, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
     for (auto b : bufs) b->release();
     for (int s = 0; s < kSlots; s++) {
         Slot& S = m->slot[s];
@@ -773,18 +820,21 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         CU(cudaGetLastError());
         rv.words = m->words.as<uint64_t>();
     }
-    if (b.tx_buf && !m->novel_cap) {
+    if (!m->novel_cap) {
         m->novel_cap = std::max<uint64_t>(1 << 20, 32 * std::min<uint64_t>(n, 1 << 22));
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 64, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's
+    if ((rc = m->nlist.ensure((n + 1) * 4)) || (rc = m->nslot.ensure((n + 1) * 4))) return rc;
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 128, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's, [8] novel reads listed
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
     p.reads = rv;
     p.hits = b.hits;
     p.counts = want_counts ? m->counts.as<unsigned long long>() : nullptr;
-    p.novel = b.tx_buf ? m->novel.as<uint32_t>() : nullptr;
+    p.novel = m->novel.as<uint32_t>();   // sets that are no visited class are always materialised: they are counted per set
+    p.novel_list = m->nlist.as<uint32_t>();
+    p.novel_list_count = m->novel_cursor.as<unsigned long long>() + 8;
     p.novel_cap = m->novel_cap;
     p.novel_cursor = m->novel_cursor.as<unsigned long long>();
     p.spill = m->spill.as<uint4>();
@@ -835,13 +885,27 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 const uint64_t nw = r->read_len ? kLaneMaxWords : ((uint64_t)r->fixed_len + 31) / 32;
                 p.lane_words = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nw, 1), kLaneMaxWords);
             }
-            if ((rc = timed(0, [&]() { launch_map_lanes<EV>(m, st, p, false); }))) return rc;
+            int lrc = PSA_OK;
+            auto fast = [&](bool hint) {
+                if (m->fast_kernel_lanes) lrc = launch_map_lanes<EV>(m, st, p, hint);
+                else launch_map_thread<EV>(m, st, p, hint);
+            };
+            if ((rc = timed(0, [&]() { fast(false); })) || (rc = lrc)) return rc;
             if (m->scan_width) {
                 if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
-                if ((rc = timed(0, [&]() { launch_map_lanes<EV>(m, st, p, true); }))) return rc;
+                if ((rc = timed(0, [&]() { fast(true); })) || (rc = lrc)) return rc;
             }
         }
         if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, st, p); }))) return rc;
+    }
+    // sets that are no index class: find or claim their entries in the mapper's table (counted below, once the
+    // batch is known to stand)
+    NovelTable nt{m->ntab.as<NovelEntry>(), m->ntab_cap, m->npool.as<uint32_t>(), m->npool_cap, m->ncur.as<unsigned long long>()};
+    if (n && want_counts) {
+        k_novel_claim<<<296, 256, 0, st>>>(p.novel_list, p.novel_list_count, b.hits, p.novel, nt, m->nslot.as<uint32_t>(), p.status);
+        k_novel_verify<<<296, 256, 0, st>>>(p.novel_list, p.novel_list_count, b.hits, p.novel, nt, m->nslot.as<uint32_t>(), p.status);
+        m->launches += 2;
+        CU(cudaGetLastError());
     }
     // exclusive scan of n_tx (n+1 items: the last one is the batch total), seeded by the running total
     if ((rc = m->dst_off.ensure((n + 2) * 8))) return rc;
@@ -857,6 +921,11 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     if (n) {
         k_expand_balanced<<<nblocks(n, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
                                                            ix->d.eq_off, ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
+    }
+    if (n && want_counts) {
+        k_novel_add<<<296, 256, 0, st>>>(p.novel_list_count, nt, m->nslot.as<uint32_t>(), p.status, m->dst_off.as<uint64_t>() + n, b.tx_cap,
+                                         b.tx_buf != nullptr);
+        m->launches++;
     }
     k_advance<<<1, 32, 0, st>>>(m->running.as<uint64_t>(), m->dst_off.as<uint64_t>() + n, b.tx_cap, b.tx_buf != nullptr,
                                 m->status.as<uint32_t>(), b.meta_out, b.sticky ? m->status.as<uint32_t>() + 1 : nullptr);
@@ -881,6 +950,48 @@ static int grow_novel(psa_mapper* m) {
     m->novel_cap *= 4;
     return m->novel.ensure(m->novel_cap * 4);
 }
+// the novel-set table filled up (status bit 16): four times the entries and members, the used entries rehashed
+static int grow_novel_table(psa_mapper* m) {
+    DevBuf tab, pool;
+    const uint64_t cap = m->ntab_cap * 4, pcap = m->npool_cap * 4;
+    int rc;
+    if ((rc = tab.ensure(cap * sizeof(NovelEntry))) || (rc = pool.ensure(pcap * 4))) {
+        tab.release(); pool.release();
+        return rc;
+    }
+    CU(cudaMemsetAsync(tab.p, 0, cap * sizeof(NovelEntry), m->st));
+    k_novel_rehash<<<nblocks(m->ntab_cap, 256), 256, 0, m->st>>>(m->ntab.as<NovelEntry>(), m->ntab_cap, tab.as<NovelEntry>(), cap);
+    CU(cudaMemcpyAsync(pool.p, m->npool.p, m->npool_cap * 4, cudaMemcpyDeviceToDevice, m->st));
+    // entries claimed by the failed attempt whose members did not fit are dropped by the rehash; the member cursor may
+    // have run past the old pool: clamp it
+    unsigned long long cur[2];
+    CU(cudaMemcpyAsync(cur, m->ncur.p, 16, cudaMemcpyDeviceToHost, m->st));
+    CU(cudaStreamSynchronize(m->st));
+    cur[0] = std::min<unsigned long long>(cur[0], m->npool_cap);
+    CU(cudaMemcpyAsync(m->ncur.p, cur, 16, cudaMemcpyHostToDevice, m->st));
+    CU(cudaStreamSynchronize(m->st));
+    m->ntab.release(); m->npool.release();
+    m->ntab = tab; m->npool = pool;
+    m->ntab_cap = cap; m->npool_cap = pcap;
+    return PSA_OK;
+}
+// the table as it was when the call began (a call that overflows somewhere is redone as a whole)
+static int novel_backup(psa_mapper* m) {
+    int rc;
+    if ((rc = m->ntab_backup.ensure(m->ntab_cap * sizeof(NovelEntry))) || (rc = m->ncur_backup.ensure(16))) return rc;
+    CU(cudaMemcpyAsync(m->ntab_backup.p, m->ntab.p, m->ntab_cap * sizeof(NovelEntry), cudaMemcpyDeviceToDevice, m->st));
+    CU(cudaMemcpyAsync(m->ncur_backup.p, m->ncur.p, 16, cudaMemcpyDeviceToDevice, m->st));
+    return PSA_OK;
+}
+static int novel_restore(psa_mapper* m) {
+    CU(cudaMemcpyAsync(m->ntab.p, m->ntab_backup.p, m->ntab_cap * sizeof(NovelEntry), cudaMemcpyDeviceToDevice, m->st));
+    CU(cudaMemcpyAsync(m->ncur.p, m->ncur_backup.p, 16, cudaMemcpyDeviceToDevice, m->st));
+    CU(cudaStreamSynchronize(m->st));
+    return PSA_OK;
+}
+static int novel_clash() {
+    return fail(PSA_ERR_INTERNAL, "two different transcript sets share a 64-bit hash in the novel-set table (never merged silently)");
+}
 static int grow_pool(psa_mapper* m) {
     m->pool_cap *= 8;
     return m->pool.ensure(m->pool_cap * sizeof(uint4));
@@ -891,6 +1002,10 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
     const uint64_t nc = m->ix->d.n_eq + 2;
     for (int attempt = 0; attempt < 6; attempt++) {
         CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+        {
+            int rcb = novel_backup(m);
+            if (rcb) return rcb;
+        }
         CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
         DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
         int rc = enqueue_device_batch<EV>(m, b, true);
@@ -899,16 +1014,20 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
         CU(cudaStreamSynchronize(m->st));
         uint32_t status = (uint32_t)m->pin[1];
         o->tx_used = m->pin[0];
-        if (status & 3u) {  // novel-set buffer / class-list pool overflow: undo the counts, retry with larger buffers
+        if (status & 8u) return novel_clash();
+        if (status & 19u) {  // novel-set buffer / class-list pool / novel-set table overflow: undo the counts, retry with larger buffers
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
             CU(cudaStreamSynchronize(m->st));
+            if ((rc = novel_restore(m))) return rc;
             if ((status & 1u) && (rc = grow_novel(m))) return rc;
             if ((status & 2u) && (rc = grow_pool(m))) return rc;
+            if ((status & 16u) && (rc = grow_novel_table(m))) return rc;
             continue;
         }
         if (o->tx_buf && o->tx_used > o->tx_cap) {  // the caller resubmits: leave the counts as they were
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
             CU(cudaStreamSynchronize(m->st));
+            if ((rc = novel_restore(m))) return rc;
             return fail(PSA_ERR_CAPACITY, "tx_buf too small");
         }
         return PSA_OK;
@@ -942,11 +1061,13 @@ extern "C" int psa_mapper_sync(psa_mapper* m) {
         CU(cudaMemsetAsync(m->status.as<uint32_t>() + 1, 0, 4, m->st));  // the sticky status restarts here
         o->tx_used = m->pin[0];
         uint32_t status = (uint32_t)m->pin[1];
-        if (status & 3u) {
+        if (status & 8u) return novel_clash();
+        if (status & 19u) {
             int rc = PSA_OK;
             if ((status & 1u) && (rc = grow_novel(m))) return rc;
             if ((status & 2u) && (rc = grow_pool(m))) return rc;
-            return fail(PSA_ERR_CAPACITY, "novel-set buffer / class-list pool overflow (buffers grown: reset the counts and resubmit the batch)");
+            if ((status & 16u) && (rc = grow_novel_table(m))) return rc;
+            return fail(PSA_ERR_CAPACITY, "novel-set buffer / class-list pool / novel-set table overflow (buffers grown: reset the counts and resubmit the batch)");
         }
         if ((status & 4u) || (o->tx_buf && o->tx_used > o->tx_cap))
             return fail(PSA_ERR_CAPACITY, "tx_buf too small (for one of the batches queued since the last sync)");
@@ -1002,6 +1123,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
     for (int attempt = 0; attempt < 6; attempt++) {
         int rc;
         CU(cudaMemcpyAsync(m->counts_backup.p, m->counts.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
+        if ((rc = novel_backup(m))) return rc;
         CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
         const bool verbose = getenv("PSA_VERBOSE") != nullptr;
         auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1016,7 +1138,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         }
         for (int s = 0; s < kSlots; s++) m->slot[s].in_free_rec = m->slot[s].out_free_rec = false;
         const double t_alloc = verbose ? now_s() - ta0 : 0;
-        bool novel_overflow = false, spill_overflow = false, stage_overflow = false;
+        bool novel_overflow = false, spill_overflow = false, stage_overflow = false, ntab_overflow = false, clash = false;
         uint64_t stage_need = 0;
         uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
 
@@ -1030,6 +1152,8 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             uint32_t status = (uint32_t)S.meta_host[1];
             if (status & 1u) novel_overflow = true;
             if (status & 2u) spill_overflow = true;
+            if (status & 8u) clash = true;
+            if (status & 16u) ntab_overflow = true;
             uint64_t cnt = total - tx_prev_total;
             if (status & 4u) {  // the chunk produced more members than its staging buffer holds
                 stage_overflow = true;
@@ -1091,11 +1215,16 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             fprintf(stderr, "psa: map_host %llu chunks: staging buffers %.2f ms, submit %.2f ms, waits on chunk totals %.2f ms, final drain %.2f ms\n",
                     (unsigned long long)nchunks, 1e3 * t_alloc, 1e3 * t_submit, 1e3 * t_wait, 1e3 * (now_s() - td0));
         o->tx_used = tx_prev_total;
-        if (novel_overflow || stage_overflow || spill_overflow) {
+        if (clash) return novel_clash();
+        if (novel_overflow || stage_overflow || spill_overflow || ntab_overflow) {
+            // (a chunk that overflowed counted nothing, but the chunks around it did: the novel-set counts of this call
+            // are undone with the per-class counts -- the table's counts are part of the backup below)
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
             CU(cudaStreamSynchronize(m->st));
+            if ((rc = novel_restore(m))) return rc;
             if (novel_overflow && m->novel_cap && (rc = grow_novel(m))) return rc;
             if (spill_overflow && (rc = grow_pool(m))) return rc;
+            if (ntab_overflow && (rc = grow_novel_table(m))) return rc;
             if (stage_overflow)
                 for (int s = 0; s < kSlots; s++)
                     if ((rc = m->slot[s].tx.ensure(stage_need * 4 + 4096))) return rc;
@@ -1104,6 +1233,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         if (o->tx_buf && o->tx_used > o->tx_cap) {  // the caller resubmits: leave the counts as they were
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
             CU(cudaStreamSynchronize(m->st));
+            if ((rc = novel_restore(m))) return rc;
             return fail(PSA_ERR_CAPACITY, "tx_buf too small");
         }
         return PSA_OK;
@@ -1205,8 +1335,94 @@ extern "C" int psa_mapper_counts_reset(psa_mapper* m) {
     if (!m) return fail(PSA_ERR_ARG, "null argument");
     CU(cudaSetDevice(m->ix->device));
     CU(cudaMemsetAsync(m->counts.p, 0, (m->ix->d.n_eq + 2) * 8, m->st));
+    CU(cudaMemsetAsync(m->ntab.p, 0, m->ntab_cap * sizeof(NovelEntry), m->st));
+    CU(cudaMemsetAsync(m->ncur.p, 0, 16, m->st));
     CU(cudaStreamSynchronize(m->st));
     return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// novel sets: the table as a sorted host view, the merge of several views
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SetRef {
+    const uint32_t* m;
+    uint32_t len;
+    uint64_t count;
+};
+bool set_less(const SetRef& a, const SetRef& b) {   // (length, contents)
+    if (a.len != b.len) return a.len < b.len;
+    return std::lexicographical_compare(a.m, a.m + a.len, b.m, b.m + b.len);
+}
+bool set_equal(const SetRef& a, const SetRef& b) { return a.len == b.len && std::equal(a.m, a.m + a.len, b.m); }
+// sorted, duplicates merged (counts added) -> malloc'ed arrays of *out
+int build_sets(std::vector<SetRef>& v, psa_novel_sets* out) {
+    std::sort(v.begin(), v.end(), set_less);
+    size_t n = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+        if (n && set_equal(v[n - 1], v[i])) v[n - 1].count += v[i].count;
+        else v[n++] = v[i];
+    }
+    v.resize(n);
+    uint64_t nm = 0;
+    for (auto& e : v) nm += e.len;
+    out->n_sets = n;
+    out->n_members = nm;
+    out->offsets = (uint64_t*)malloc((n + 1) * 8);
+    out->members = (uint32_t*)malloc((nm + 1) * 4);
+    out->counts = (uint64_t*)malloc((n + 1) * 8);
+    if (!out->offsets || !out->members || !out->counts) {
+        psa_novel_sets_free(out);
+        return fail(PSA_ERR_NOMEM, "out of memory");
+    }
+    uint64_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        out->offsets[i] = o;
+        if (v[i].len) memcpy(out->members + o, v[i].m, (size_t)v[i].len * 4);
+        o += v[i].len;
+        out->counts[i] = v[i].count;
+    }
+    out->offsets[n] = o;
+    return PSA_OK;
+}
+}  // namespace
+
+extern "C" void psa_novel_sets_free(psa_novel_sets* s) {
+    if (!s) return;
+    free(s->offsets); free(s->members); free(s->counts);
+    s->offsets = nullptr; s->members = nullptr; s->counts = nullptr;
+    s->n_sets = s->n_members = 0;
+}
+
+extern "C" int psa_novel_sets_merge(const psa_novel_sets* parts, uint32_t n_parts, psa_novel_sets* out) {
+    if (!out || (n_parts && !parts)) return fail(PSA_ERR_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    std::vector<SetRef> v;
+    for (uint32_t p = 0; p < n_parts; p++)
+        for (uint64_t i = 0; i < parts[p].n_sets; i++) {
+            const uint64_t a = parts[p].offsets[i], b = parts[p].offsets[i + 1];
+            if (b < a || b > parts[p].n_members) return fail(PSA_ERR_ARG, "inconsistent offsets");
+            v.push_back(SetRef{parts[p].members + a, (uint32_t)(b - a), parts[p].counts[i]});
+        }
+    return build_sets(v, out);
+}
+
+extern "C" int psa_mapper_novel_sets(psa_mapper* m, psa_novel_sets* out) {
+    if (!m || !out) return fail(PSA_ERR_ARG, "null argument");
+    memset(out, 0, sizeof *out);
+    CU(cudaSetDevice(m->ix->device));
+    CU(cudaStreamSynchronize(m->st));
+    unsigned long long cur[2] = {0, 0};
+    CU(cudaMemcpy(cur, m->ncur.p, 16, cudaMemcpyDeviceToHost));
+    std::vector<NovelEntry> tab(m->ntab_cap);
+    const uint64_t used = std::min<uint64_t>(cur[0], m->npool_cap);
+    std::vector<uint32_t> pool(used + 1);
+    CU(cudaMemcpy(tab.data(), m->ntab.p, m->ntab_cap * sizeof(NovelEntry), cudaMemcpyDeviceToHost));
+    if (used) CU(cudaMemcpy(pool.data(), m->npool.p, used * 4, cudaMemcpyDeviceToHost));
+    std::vector<SetRef> v;
+    for (const NovelEntry& e : tab)
+        if (e.key && e.count && e.len != 0xFFFFFFFFu && e.off + e.len <= used) v.push_back(SetRef{pool.data() + e.off, e.len, e.count});
+    return build_sets(v, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1222,6 +1438,7 @@ struct NcclApi {
     int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -1236,8 +1453,9 @@ static int nccl_load() {
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.AllGather)
         return fail(PSA_ERR_NCCL, "libnccl lacks a required symbol");
     g_nccl.h = h;
     return PSA_OK;
@@ -1291,6 +1509,58 @@ extern "C" int psa_mapper_counts_allreduce(psa_mapper* m, psa_comm* c) {
     return PSA_OK;
 }
 
+// The novel-set tables of all ranks: every rank serialises its view as u64 words
+// [n_sets, n_members, offsets (n_sets+1), counts (n_sets), members (packed two per word)], the sizes are
+// all-gathered, then the tables padded to the largest one; the merge is psa_novel_sets_merge on every rank.
+extern "C" int psa_mapper_novel_allgather(psa_mapper* m, psa_comm* c, psa_novel_sets* out) {
+    if (!m || !c || !out) return fail(PSA_ERR_ARG, "null argument");
+    psa_novel_sets mine{};
+    int rc = psa_mapper_novel_sets(m, &mine);
+    if (rc) return rc;
+    std::vector<uint64_t> ser;
+    ser.push_back(mine.n_sets);
+    ser.push_back(mine.n_members);
+    ser.insert(ser.end(), mine.offsets, mine.offsets + mine.n_sets + 1);
+    ser.insert(ser.end(), mine.counts, mine.counts + mine.n_sets);
+    const size_t mw = (mine.n_members + 1) / 2;
+    const size_t at = ser.size();
+    ser.resize(at + mw, 0);
+    if (mine.n_members) memcpy(ser.data() + at, mine.members, mine.n_members * 4);
+    psa_novel_sets_free(&mine);
+    const int W = c->world;
+    DevBuf dsz, dall_sz, dsend, drecv;
+    auto rel = [&]() { dsz.release(); dall_sz.release(); dsend.release(); drecv.release(); };
+    unsigned long long my_words = ser.size();
+    std::vector<unsigned long long> sizes(W);
+    if ((rc = dsz.ensure(8)) || (rc = dall_sz.ensure(8 * (size_t)W))) { rel(); return rc; }
+    cudaMemcpyAsync(dsz.p, &my_words, 8, cudaMemcpyHostToDevice, m->st);
+    int e = g_nccl.AllGather(dsz.p, dall_sz.p, 1, 5 /* ncclUint64 */, c->comm, m->st);
+    if (e) { rel(); return nccl_fail("ncclAllGather", e); }
+    cudaMemcpyAsync(sizes.data(), dall_sz.p, 8 * (size_t)W, cudaMemcpyDeviceToHost, m->st);
+    if (cudaStreamSynchronize(m->st) != cudaSuccess) { rel(); return fail(PSA_ERR_CUDA, "novel all-gather (sizes)"); }
+    unsigned long long max_words = 0;
+    for (auto x : sizes) max_words = std::max(max_words, x);
+    ser.resize(max_words, 0);
+    if ((rc = dsend.ensure(max_words * 8)) || (rc = drecv.ensure(max_words * 8 * (size_t)W))) { rel(); return rc; }
+    cudaMemcpyAsync(dsend.p, ser.data(), max_words * 8, cudaMemcpyHostToDevice, m->st);
+    e = g_nccl.AllGather(dsend.p, drecv.p, max_words, 5, c->comm, m->st);
+    if (e) { rel(); return nccl_fail("ncclAllGather", e); }
+    std::vector<uint64_t> all(max_words * (size_t)W);
+    cudaMemcpyAsync(all.data(), drecv.p, all.size() * 8, cudaMemcpyDeviceToHost, m->st);
+    if (cudaStreamSynchronize(m->st) != cudaSuccess) { rel(); return fail(PSA_ERR_CUDA, "novel all-gather (tables)"); }
+    rel();
+    std::vector<psa_novel_sets> parts(W);
+    for (int r = 0; r < W; r++) {
+        uint64_t* b = all.data() + (size_t)r * max_words;
+        parts[r].n_sets = b[0];
+        parts[r].n_members = b[1];
+        parts[r].offsets = b + 2;
+        parts[r].counts = b + 2 + parts[r].n_sets + 1;
+        parts[r].members = reinterpret_cast<uint32_t*>(b + 2 + 2 * parts[r].n_sets + 1);
+    }
+    return psa_novel_sets_merge(parts.data(), (uint32_t)W, out);
+}
+
 // ---------------------------------------------------------------------------------------------
 // measurement aid
 // ---------------------------------------------------------------------------------------------
@@ -1333,6 +1603,36 @@ extern "C" int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk
     table.release();
     sink.release();
     *gbytes_per_s = (double)grid * block * iters * (chunk_bytes ? chunk_bytes : 4) / (best / 1e3) / 1e9;
+    return PSA_OK;
+}
+
+extern "C" int psa_selftest_intersect(int device, const uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n2,
+                                      uint32_t* out, uint32_t cap, uint32_t n_out[3]) {
+    if (!out || !n_out || (n1 && !v1) || (n2 && !v2)) return fail(PSA_ERR_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    DevBuf mem, off, dout, dn;
+    int rc;
+    auto rel = [&]() { mem.release(); off.release(); dout.release(); dn.release(); };
+    if ((rc = mem.ensure(((uint64_t)n1 + n2 + 1) * 4)) || (rc = off.ensure(3 * 8)) || (rc = dout.ensure(3 * (uint64_t)cap * 4 + 4)) ||
+        (rc = dn.ensure(3 * 4))) {
+        rel();
+        return rc;
+    }
+    const uint64_t offs[3] = {0, n1, (uint64_t)n1 + n2};
+    cudaMemcpy(off.p, offs, sizeof offs, cudaMemcpyHostToDevice);
+    if (n1) cudaMemcpy(mem.p, v1, (uint64_t)n1 * 4, cudaMemcpyHostToDevice);
+    if (n2) cudaMemcpy(mem.as<uint32_t>() + n1, v2, (uint64_t)n2 * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dn.p, 0, 12);
+    DevIndex d{};
+    d.n_eq = 2;
+    d.eq_off = off.as<uint64_t>();
+    d.eq_mem = mem.as<uint32_t>();
+    MapParams p{};
+    k_selftest_intersect<<<1, 32>>>(d, p, dout.as<uint32_t>(), cap, dn.as<uint32_t>());
+    cudaError_t e = cudaMemcpy(n_out, dn.p, 12, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, 3 * (uint64_t)cap * 4, cudaMemcpyDeviceToHost);
+    rel();
+    if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
     return PSA_OK;
 }
 

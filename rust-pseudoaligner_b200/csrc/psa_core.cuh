@@ -755,26 +755,38 @@ struct ThreadEvents {
     uint32_t lookups, levels, hits, verifs, visits, bases, jumps, members;
 };
 
-struct ClassAcc {
+struct ClassAcc {  // 60 bytes: it lives in shared memory, one per read in flight
     uint32_t min_len, min_eq;  // smallest class length seen, and the smallest id among the classes of that length
     uint32_t last_eq;          // class of the previous push (consecutive repeats cost nothing)
-    WinAcc acc;                // AND of the narrow classes' windows
+    uint32_t acc_base;         // AND of the narrow classes' windows: {acc_base + t : bit t of acc_map set}
+    uint64_t acc_w0, acc_w1, acc_w2;
     uint32_t wide_eq[kThreadWide];
     uint8_t n_wide, n_inline;
-    bool multi;                // more than one distinct class visited
-    bool defer;
+    uint8_t bits;              // kAccHave | kAccMulti | kAccDefer
+
+    static constexpr uint8_t kAccHave = 1, kAccMulti = 2, kAccDefer = 4;
+    PSA_HD bool have() const { return bits & kAccHave; }
+    PSA_HD bool multi() const { return bits & kAccMulti; }   // more than one distinct class visited
+    PSA_HD bool defer() const { return bits & kAccDefer; }
+    PSA_HD WinAcc acc() const { return WinAcc{acc_base, Win{acc_w0, acc_w1, acc_w2}, have()}; }
+    PSA_HD void set_acc(const WinAcc& a) {
+        acc_base = a.base; acc_w0 = a.map.w0; acc_w1 = a.map.w1; acc_w2 = a.map.w2;
+        if (a.have) bits |= kAccHave;
+    }
 
     PSA_HD void init() {
         min_len = kNone; min_eq = kNone; last_eq = kNone;
-        acc.base = 0; acc.map = Win{0, 0, 0}; acc.have = false;
+        acc_base = 0; acc_w0 = 0; acc_w1 = 0; acc_w2 = 0;
         PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) wide_eq[j] = kNone;
-        n_wide = 0; n_inline = 0; multi = false; defer = false;
+        n_wide = 0; n_inline = 0; bits = 0;
     }
     // AND one class into the running intersection (narrow), or list it (wide)
     PSA_HD void and_class(const DevIndex& ix, uint32_t e, uint32_t l, const ClassWin& c) {
         if (c.len != kWinWide) {
-            winacc_and(acc, c);
+            WinAcc a = acc();
+            winacc_and(a, c);
+            set_acc(a);
             return;
         }
         bool dup = false;
@@ -784,12 +796,14 @@ struct ClassAcc {
         if (n_wide >= kThreadWide) {
             // no room to remember it: apply it now to the candidates the windows have left (the filter
             // is idempotent and commutes with the ANDs still to come); without any window yet, give up
-            if (acc.have && n_inline < kThreadWideInline) {
+            if (have() && n_inline < kThreadWideInline) {
                 n_inline++;
-                winacc_filter_list(acc, ix.eq_mem + ld_off(ix.eq_off + e), l);
+                WinAcc a = acc();
+                winacc_filter_list(a, ix.eq_mem + ld_off(ix.eq_off + e), l);
+                set_acc(a);
                 return;
             }
-            defer = true;
+            bits |= kAccDefer;
             return;
         }
         PSA_UNROLL
@@ -801,7 +815,7 @@ struct ClassAcc {
     // Returns true when the class was not the previous push's (event counting).
     PSA_HD bool push(const DevIndex& ix, uint32_t eq, uint32_t class_len, const ClassWin& win) {
         if (eq == last_eq) return false;
-        if (min_eq != kNone) multi = true;
+        if (min_eq != kNone) bits |= kAccMulti;
         last_eq = eq;
         if (class_len < min_len || (class_len == min_len && eq < min_eq)) {
             min_len = class_len;
@@ -859,20 +873,22 @@ PSA_HD uint32_t thread_intersect_lists(const DevIndex& ix, const ClassAcc& w, in
 // Returns false when the lists are too long for one thread (smallest class > max_small).
 PSA_HD bool class_result(const DevIndex& ix, ClassAcc& w, uint32_t max_small, uint32_t& count, uint32_t& eq_id, int& s) {
     s = 0;
-    if (!w.multi) {
+    if (!w.multi()) {
         count = w.min_len;
         eq_id = w.min_eq;
         return true;
     }
-    if (w.acc.have) {
+    if (w.have()) {
         // wide classes filter what survived the windows (ref :399-404 on the candidates)
+        WinAcc a = w.acc();
         PSA_UNROLL
         for (int j = 0; j < kThreadWide; j++) {
-            if (j >= (int)w.n_wide || win_empty(w.acc.map)) continue;
+            if (j >= (int)w.n_wide || win_empty(a.map)) continue;
             const uint64_t o = ld_off(ix.eq_off + w.wide_eq[j]);
-            winacc_filter_list(w.acc, ix.eq_mem + o, (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o));
+            winacc_filter_list(a, ix.eq_mem + o, (uint32_t)(ld_off(ix.eq_off + w.wide_eq[j] + 1) - o));
         }
-        count = win_popc(w.acc.map);
+        w.set_acc(a);
+        count = win_popc(a.map);
     } else {
         // smallest class first (ref :331-334)
         uint32_t s_eq = w.wide_eq[0];
@@ -893,7 +909,7 @@ PSA_HD bool class_result(const DevIndex& ix, ClassAcc& w, uint32_t max_small, ui
 }
 // the members of a result that is no visited class, ascending
 PSA_HD void class_members(const DevIndex& ix, const ClassAcc& w, int s, uint32_t* dst) {
-    if (w.acc.have) win_write(w.acc, dst);
+    if (w.have()) win_write(w.acc(), dst);
     else thread_intersect_lists(ix, w, s, dst);
 }
 

@@ -14,6 +14,7 @@
 
 #include "psa_core.cuh"
 #include "psa_lanes.cuh"
+#include "psa_thread.cuh"
 
 namespace psa {
 
@@ -373,6 +374,8 @@ struct MapParams {
     uint32_t* novel;              // members of sets that are no index class
     unsigned long long novel_cap;
     unsigned long long* novel_cursor;
+    uint32_t* novel_list;         // reads whose eq_class is no visited class, in no particular order
+    unsigned long long* novel_list_count;
     uint4* spill;                 // per-group overflow of the visited-class list
     uint32_t spill_cap;           // entries per group
     uint4* pool;                  // bump-allocated overflow of `spill` (very long reads)
@@ -770,9 +773,12 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
                 count_slot = eq_id;  // (members: k_expand reads them from the index through eq_id)
             } else {
                 count_slot = ix.n_eq;
-                if (count && p.novel) {
+                if (p.novel) {
                     unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(p.novel_cursor, (unsigned long long)count);
+                    if (lane == 0) {
+                        base = atomicAdd(p.novel_cursor, (unsigned long long)count);
+                        if (p.novel_list) p.novel_list[atomicAdd(p.novel_list_count, 1ULL)] = (uint32_t)r;
+                    }
                     base = w.g.shfl(base, 0);
                     if (base + count > p.novel_cap) {
                         if (lane == 0) atomicOr(p.status, 1u);
@@ -806,10 +812,18 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
 }
 
 // ---------------------------------------------------------------------------------------------
-// the fast map kernel: one lane per read, every lane a state machine (psa_lanes.cuh).  Persistent
-// warps; a lane that finishes its read takes the next one from a counter.  Reads a lane gives up
-// are appended to p.scan_list (first seed search too long -> k_seed_scan) or p.list (-> k_map).
-// HINT = true: the reads of p.seeded, whose first seed search k_seed_scan has made.
+// the fast map kernel: one lane per read STEP.  Every read in flight is a 136-byte state record
+// (psa_lanes.cuh Lane) in shared memory; a warp owns a pool of 32 * J of them.  Each iteration
+// the warp counts its pool by state, takes the most populous state, gathers up to 32 reads that
+// are in it and advances them by one step -- all 32 lanes run the same block of the state machine
+// on different reads, fetch their sectors with the same load instructions and write the records
+// back.  When a step leaves a read waiting for data, the lane prefetches those sectors into L2, so
+// that by the time the read's state comes up again its loads are L2 hits.  Finished reads are
+// replaced from a counter.  (A first version kept one read per lane in registers and ran every
+// block present in the warp each iteration: 8 states -> ~5 active lanes per block, 3.3 G warp
+// instructions per batch against round 1's 1.7 G -- profiles/r2_ncu_config3.md.)
+// Reads a lane gives up are appended to p.scan_list (first seed search too long -> k_seed_scan) or
+// p.list (-> k_map).  HINT = true: the reads of p.seeded, whose first seed search k_seed_scan made.
 // ---------------------------------------------------------------------------------------------
 struct DevSink {
     const MapParams& p;
@@ -821,14 +835,15 @@ struct DevSink {
         out[2] = (uint64_t)h.eq_id | ((uint64_t)h.flags << 32);
         if (p.counts) atomicAdd(p.counts + count_slot, 1ULL);
     }
-    __device__ __forceinline__ uint32_t* novel(uint32_t count, uint64_t& off) {
+    __device__ __forceinline__ uint32_t* novel(uint32_t r, uint32_t count, uint64_t& off) {
         unsigned long long base = atomicAdd(p.novel_cursor, (unsigned long long)count);
+        if (p.novel_list) p.novel_list[atomicAdd(p.novel_list_count, 1ULL)] = r;
         off = base;
         return base + count <= p.novel_cap ? p.novel + base : nullptr;
     }
     __device__ __forceinline__ void novel_overflow() { atomicOr(p.status, 1u); }
 };
-struct SmemWords {  // a lane's read words in shared memory: word j at base[j * stride]
+struct SmemWords {  // a read's packed words in shared memory: word j at base[j * stride]
     uint64_t* base;
     uint32_t stride;
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return base[i * stride]; }
@@ -840,26 +855,46 @@ __device__ __forceinline__ Sector ld_sector_policy(const void* a, uint64_t polic
         : "=l"(s.w0), "=l"(s.w1), "=l"(s.w2), "=l"(s.w3) : "l"(a), "l"(policy));
     return s;
 }
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
 
-#ifndef PSA_LANE_BLOCK
-#define PSA_LANE_BLOCK 128
+#ifndef PSA_POOL_WARPS
+#define PSA_POOL_WARPS 4      // warps per CTA
 #endif
-#ifndef PSA_LANE_MIN_BLOCKS
-#define PSA_LANE_MIN_BLOCKS 6
+#ifndef PSA_POOL_J
+#define PSA_POOL_J 4          // reads in flight per lane: a warp's pool holds 32 * J
 #endif
-constexpr int kLaneBlock = PSA_LANE_BLOCK;
-constexpr uint32_t kLaneChunk = 128;     // reads a warp claims at a time
+#ifndef PSA_POOL_CTAS
+#define PSA_POOL_CTAS 2       // CTAs per SM the shared memory is sized for
+#endif
+constexpr int kPoolWarps = PSA_POOL_WARPS;
+constexpr int kPoolItems = 32 * PSA_POOL_J;
+constexpr uint32_t kLaneChunk = 256;     // reads a warp claims at a time
 constexpr uint32_t kLaneMaxWords = 8;    // longest read a lane takes: 256 bases (longer ones go to k_map)
+#ifndef PSA_POOL_REFILL
+#define PSA_POOL_REFILL 8
+#endif
+constexpr uint32_t kRefillMin = PSA_POOL_REFILL;   // free items that trigger a refill pass
+static_assert(kPoolItems <= 128 && (PSA_POOL_J & (PSA_POOL_J - 1)) == 0, "pool counters are eight bits; J a power of two");
+
+template <int KW, bool EV>
+__host__ __device__ constexpr size_t pool_bytes_per_warp(uint32_t lane_words) {
+    return (size_t)kPoolItems * (sizeof(Lane<KW, EV>) + (size_t)lane_words * 8 + 1) + 32 * 4;
+}
 
 template <int KW, bool EV, bool HINT>
-__global__ void __launch_bounds__(kLaneBlock, PSA_LANE_MIN_BLOCKS) k_map_lanes(const __grid_constant__ DevIndex ix,
-                                                                                const __grid_constant__ MapParams p) {
-    extern __shared__ __align__(16) uint64_t lane_smem[];
-    const unsigned lane = threadIdx.x & 31;
-    SmemWords rw{lane_smem + threadIdx.x, (uint32_t)blockDim.x};
-    Lane<KW, EV> ln;
-    ln.idle();
-    Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
+__global__ void __launch_bounds__(32 * kPoolWarps, PSA_POOL_CTAS) k_map_lanes(const __grid_constant__ DevIndex ix,
+                                                                              const __grid_constant__ MapParams p) {
+    extern __shared__ __align__(16) uint8_t pool_smem[];
+    using LaneT = Lane<KW, EV>;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lw = p.lane_words;
+    // this warp's pool: [records | read words (word j of item q at [j * items + q]) | state bytes | gather list]
+    uint8_t* base = pool_smem + warp * pool_bytes_per_warp<KW, EV>(lw);
+    LaneT* recs = reinterpret_cast<LaneT*>(base);
+    uint64_t* words = reinterpret_cast<uint64_t*>(base + (size_t)kPoolItems * sizeof(LaneT));
+    uint8_t* stb = reinterpret_cast<uint8_t*>(words + (size_t)kPoolItems * lw);
+    uint32_t* sel = reinterpret_cast<uint32_t*>(stb + kPoolItems);
+
     DevSink sink{p};
     LaneParams lp;
     lp.allowed = p.allowed_mismatches; lp.max_probes = p.max_probes; lp.max_small = p.max_small;
@@ -870,96 +905,186 @@ __global__ void __launch_bounds__(kLaneBlock, PSA_LANE_MIN_BLOCKS) k_map_lanes(c
     const uint64_t pol_first = l2_policy_first(), pol_last = l2_policy_last();
     uint64_t w_next = 0, w_end = 0;  // the warp's claimed range of reads (uniform)
     bool exhausted = false;
-    const uint64_t* my_words = nullptr;
     ThreadEvents tot{};
     uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
-    uint4 sev = make_uint4(0, 0, 0, 0);
 
-    for (;;) {
-        // ---- lanes without a read take the next ones
-        unsigned need = __ballot_sync(kFull, ln.st == LS_NEW);
-        while (need && !exhausted) {
-            if (w_next == w_end) {
-                unsigned long long at = 0;
-                if (lane == 0) at = atomicAdd(cursor, (unsigned long long)kLaneChunk);
-                at = __shfl_sync(kFull, at, 0);
-                if (at >= n_todo) {
-                    exhausted = true;
-                    break;
-                }
-                w_next = at;
-                w_end = at + kLaneChunk < n_todo ? at + kLaneChunk : n_todo;
-            }
-            const uint64_t it = w_next + __popc(need & ((1u << lane) - 1));
-            const bool take = ((need >> lane) & 1u) && it < w_end;
-            if (take) {
-                uint64_t r = it;
-                uint32_t hint[3];
-                if (HINT) {
-                    const uint4 e = p.seeded[it];
-                    r = e.x;
-                    hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
-                    if (EV) sev = p.seeded_ev[it];
-                }
-                const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
-                const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-                my_words = p.reads.words + wo;
-                ln.begin((uint32_t)r, L, p.lane_words, HINT ? hint : nullptr);
-            }
-            const unsigned taken = __ballot_sync(kFull, take);
-            w_next += __popc(taken);
-            need &= ~taken;
+    // lane l owns the state bytes of items 4l .. 4l+3 (J = 4) for counting; any lane may step any item
+    uint32_t* stw = reinterpret_cast<uint32_t*>(stb);
+    for (int j = 0; j < PSA_POOL_J; j++) stb[PSA_POOL_J * lane + j] = LS_NEW;
+    __syncwarp();
+
+    for (uint32_t iter = 0;; iter++) {
+        // ---- count the pool by state (four bits of state -> 16 eight-bit counters in four words)
+        uint32_t mine[PSA_POOL_J];
+#pragma unroll
+        for (int j = 0; j < PSA_POOL_J; j++) mine[j] = stb[PSA_POOL_J * lane + j];
+        uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+#pragma unroll
+        for (int j = 0; j < PSA_POOL_J; j++) {
+            const uint32_t b = mine[j], inc = 1u << (8 * (b & 3));
+            h0 += (b >> 2) == 0 ? inc : 0; h1 += (b >> 2) == 1 ? inc : 0; h2 += (b >> 2) == 2 ? inc : 0; h3 += (b >> 2) == 3 ? inc : 0;
         }
-        if (exhausted && ln.st == LS_NEW) ln.st = LS_IDLE;
-        if (!__ballot_sync(kFull, ln.st != LS_IDLE)) break;
+        h0 = __reduce_add_sync(kFull, h0); h1 = __reduce_add_sync(kFull, h1);
+        h2 = __reduce_add_sync(kFull, h2); h3 = __reduce_add_sync(kFull, h3);
+        const uint32_t n_free = h0 & 0xff;  // LS_NEW == 0
 
-        // ---- the requests of all lanes, issued together
-        if (ln.st == LS_READ) {
-            const uint32_t nw = (ln.L + 31) >> 5;
-            A.w0 = nw > 0 ? my_words[0] : 0; A.w1 = nw > 1 ? my_words[1] : 0;
-            A.w2 = nw > 2 ? my_words[2] : 0; A.w3 = nw > 3 ? my_words[3] : 0;
-            if (nw > 4) {
-                C.w0 = my_words[4]; C.w1 = nw > 5 ? my_words[5] : 0;
-                C.w2 = nw > 6 ? my_words[6] : 0; C.w3 = nw > 7 ? my_words[7] : 0;
+        // ---- refill: free items take the next reads
+        // (not for every single finished read: a refill pass costs as much as a short step)
+        if (n_free && !exhausted && (n_free >= kRefillMin || (h0 >> 8) + h1 + h2 + h3 == 0)) {
+            uint32_t given = 0;
+#pragma unroll
+            for (int j = 0; j < PSA_POOL_J; j++) {
+                const bool fre = mine[j] == LS_NEW;
+                unsigned need = __ballot_sync(kFull, fre);
+                while (need && !exhausted) {
+                    if (w_next == w_end) {
+                        unsigned long long at = 0;
+                        if (lane == 0) at = atomicAdd(cursor, (unsigned long long)kLaneChunk);
+                        at = __shfl_sync(kFull, at, 0);
+                        if (at >= n_todo) {
+                            exhausted = true;
+                            break;
+                        }
+                        w_next = at;
+                        w_end = at + kLaneChunk < n_todo ? at + kLaneChunk : n_todo;
+                    }
+                    const uint64_t it = w_next + __popc(need & ((1u << lane) - 1));
+                    const bool take = ((need >> lane) & 1u) && it < w_end;
+                    if (take) {
+                        uint64_t r = it;
+                        uint32_t hint[3];
+                        if (HINT) {
+                            const uint4 e = p.seeded[it];
+                            r = e.x;
+                            hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
+                        }
+                        const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+                        const uint32_t q = PSA_POOL_J * lane + j;
+                        LaneT& ln = recs[q];
+                        ln.idle();
+                        ln.begin((uint32_t)r, L, lw, HINT ? hint : nullptr);
+                        if (EV && HINT) ln.why = (uint32_t)it;   // (the entry of p.seeded_ev, should the read be handed over)
+                        stb[q] = (uint8_t)ln.st;
+                        mine[j] = ln.st;
+                        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+                        prefetch_l2(p.reads.words + wo);
+                        if (((L + 31) >> 5) > 4) prefetch_l2(p.reads.words + wo + 4);
+                    }
+                    const unsigned taken = __ballot_sync(kFull, take);
+                    w_next += __popc(taken);
+                    given += __popc(taken);
+                    need &= ~taken;
+                }
             }
-        } else {
-            if (ln.reqA) A = ld_sector_policy(ln.reqA, ln.a_stream ? pol_first : pol_last);
-            if (ln.reqB) B = ld_sector_policy(ln.reqB, pol_last);
-            if (ln.reqC) {
-                C.w0 = ld_u64_last(ln.reqC); C.w1 = ld_u64_last(ln.reqC + 1);
-                C.w2 = ld_u64_last(ln.reqC + 2); C.w3 = ld_u64_last(ln.reqC + 3);
+            if (given) {
+                __syncwarp();
+                continue;  // count again
             }
         }
-        ln.step(ix, lp, rw, A, B, C, sink);
 
+        // ---- the most populous state (LS_NEW and LS_IDLE excepted)
+        uint32_t best = 0, best_n = 0;
+#pragma unroll
+        for (int sidx = 1; sidx < LS_IDLE; sidx++) {
+            const uint32_t w = sidx < 4 ? h0 : sidx < 8 ? h1 : sidx < 12 ? h2 : h3;
+            const uint32_t c = (w >> (8 * (sidx & 3))) & 0xff;
+            if (c > best_n) { best_n = c; best = sidx; }
+        }
+        if (best_n == 0) {
+            if (exhausted) break;   // nothing in flight, nothing left
+            continue;               // (cannot happen: a non-exhausted warp refills above)
+        }
+        // ---- gather up to 32 items that are in it (the item order rotates so that none is passed over for long)
+        uint32_t basei = 0;
+#pragma unroll
+        for (int jj = 0; jj < PSA_POOL_J; jj++) {
+            const int j = (jj + iter) & (PSA_POOL_J - 1);
+            uint32_t mj = 0;
+#pragma unroll
+            for (int t = 0; t < PSA_POOL_J; t++) mj = t == j ? mine[t] : mj;
+            const bool in = mj == best;
+            const unsigned m = __ballot_sync(kFull, in);
+            const uint32_t idx = basei + __popc(m & ((1u << lane) - 1));
+            if (in && idx < 32) sel[idx] = PSA_POOL_J * lane + j;
+            basei += __popc(m);
+        }
+        const uint32_t n_sel = basei < 32 ? basei : 32;
+        __syncwarp();
+
+        // ---- one step for each of them
+        uint32_t emit = LE_NONE, handed_r = 0, why = 0;
+        if (lane < n_sel) {
+            const uint32_t q = sel[lane];
+            LaneT& ln = recs[q];
+            SmemWords rw{words + q, (uint32_t)kPoolItems};
+            Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
+            if (best == LS_READ) {
+                const uint64_t r = ln.r;
+                const uint64_t* src = p.reads.words + (p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride);
+                const uint32_t nw = (ln.L + 31) >> 5;
+                A.w0 = nw > 0 ? src[0] : 0; A.w1 = nw > 1 ? src[1] : 0;
+                A.w2 = nw > 2 ? src[2] : 0; A.w3 = nw > 3 ? src[3] : 0;
+                if (nw > 4) {
+                    C.w0 = src[4]; C.w1 = nw > 5 ? src[5] : 0;
+                    C.w2 = nw > 6 ? src[6] : 0; C.w3 = nw > 7 ? src[7] : 0;
+                }
+            } else {
+                const LaneRequests rq = ln.requests(ix);
+                if (rq.a) A = ld_sector_policy(rq.a, rq.a_stream ? pol_first : pol_last);
+                if (rq.b) B = ld_sector_policy(rq.b, pol_last);
+                if (rq.c) {
+                    C.w0 = ld_u64_last(rq.c); C.w1 = ld_u64_last(rq.c + 1);
+                    C.w2 = ld_u64_last(rq.c + 2); C.w3 = ld_u64_last(rq.c + 3);
+                }
+            }
+            const uint32_t seeded_at = ln.why;
+            const StepOut so = ln.step(ix, lp, rw, A, B, C, sink);
+            emit = so.emit;
+            stb[q] = (uint8_t)ln.st;
+            if (emit == LE_NONE) {
+                // the sectors the read's next step needs: on their way to L2 while other reads are stepped
+                const LaneRequests nx = ln.requests(ix);
+                if (nx.a) prefetch_l2(nx.a);
+                if (nx.c) {
+                    prefetch_l2(nx.c);
+                    prefetch_l2(nx.c + 3);
+                }
+            } else {
+                handed_r = ln.r;
+                why = ln.why;
+                if constexpr (EV) if (p.events) {
+                    if (emit == LE_RESULT) {
+                        const ThreadEvents& e = ln.ev;
+                        tot.lookups += e.lookups; tot.levels += e.levels; tot.hits += e.hits; tot.verifs += e.verifs;
+                        tot.visits += e.visits; tot.bases += e.bases; tot.jumps += e.jumps; tot.members += e.members;
+                        ev_reads++; ev_bases += ln.L; ev_out += so.n_tx; ev_aligned += so.aligned ? 1 : 0;
+                    } else {
+                        if (why < 4) atomicAdd(p.events + 36 + why, 1ULL);
+                        if (HINT) {  // k_map redoes this read from scratch and counts its first search again
+                            const uint4 sev = p.seeded_ev[seeded_at];
+                            atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
+                            atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
+                        }
+                    }
+                }
+            }
+        }
         // ---- hand the given-up reads over (one atomic per warp and list)
-        const unsigned bs = __ballot_sync(kFull, ln.emit == LE_TO_SCAN);
+        const unsigned bs = __ballot_sync(kFull, emit == LE_TO_SCAN);
         if (bs) {
             unsigned long long at = 0;
             if (lane == (unsigned)(__ffs(bs) - 1)) at = atomicAdd(p.scan_count, (unsigned long long)__popc(bs));
             at = __shfl_sync(kFull, at, __ffs(bs) - 1);
-            if (ln.emit == LE_TO_SCAN) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = ln.r;
+            if (emit == LE_TO_SCAN) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = handed_r;
         }
-        const unsigned bc = __ballot_sync(kFull, ln.emit == LE_TO_COOP);
+        const unsigned bc = __ballot_sync(kFull, emit == LE_TO_COOP);
         if (bc) {
             unsigned long long at = 0;
             if (lane == (unsigned)(__ffs(bc) - 1)) at = atomicAdd(p.list_count, (unsigned long long)__popc(bc));
             at = __shfl_sync(kFull, at, __ffs(bc) - 1);
-            if (ln.emit == LE_TO_COOP) p.list[at + __popc(bc & ((1u << lane) - 1))] = ln.r;
+            if (emit == LE_TO_COOP) p.list[at + __popc(bc & ((1u << lane) - 1))] = handed_r;
         }
-        if (EV && p.events) {
-            if (ln.emit == LE_RESULT) {
-                tot.lookups += ln.ev.lookups; tot.levels += ln.ev.levels; tot.hits += ln.ev.hits; tot.verifs += ln.ev.verifs;
-                tot.visits += ln.ev.visits; tot.bases += ln.ev.bases; tot.jumps += ln.ev.jumps; tot.members += ln.ev.members;
-                ev_reads++; ev_bases += ln.L; ev_out += ln.out_n_tx; ev_aligned += ln.out_aligned ? 1 : 0;
-            } else if (ln.emit == LE_TO_SCAN || ln.emit == LE_TO_COOP) {
-                if (ln.why < 4) atomicAdd(p.events + 36 + ln.why, 1ULL);
-                if (HINT) {  // k_map redoes this read from scratch and counts its first search again
-                    atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
-                    atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
-                }
-            }
-        }
+        __syncwarp();
     }
     if (EV && p.events) {
         unsigned long long v[12] = {ev_reads, ev_bases, tot.lookups, tot.levels, tot.hits, tot.verifs,
@@ -970,6 +1095,125 @@ __global__ void __launch_bounds__(kLaneBlock, PSA_LANE_MIN_BLOCKS) k_map_lanes(c
 #pragma unroll
             for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
             if (lane == 0 && x) atomicAdd(p.events + i, x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the thread-per-read kernel in its blocking form (psa_thread.cuh): read r = global thread id, one
+// call of map_read per thread, 64-thread CTAs at 20 per SM.  HINT = true: the reads of p.seeded,
+// persistent warps striding over that list.  TILE (first pass, fixed word stride): the packed words of
+// the CTA's 64 reads arrive in shared memory as one bulk asynchronous copy (cp.async.bulk + mbarrier:
+// TMA) and every thread maps its read from there.
+// ---------------------------------------------------------------------------------------------
+#ifndef PSA_THREAD_BLOCK
+#define PSA_THREAD_BLOCK 64
+#endif
+constexpr int kThreadBlock = PSA_THREAD_BLOCK;
+#ifndef PSA_THREAD_MIN_BLOCKS
+#define PSA_THREAD_MIN_BLOCKS 20
+#endif
+template <int KW, bool EV, bool HINT, bool TILE = false>
+__global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
+                                                                                     const __grid_constant__ MapParams p) {
+    const unsigned lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint64_t* my_words = nullptr;
+    if (TILE) {
+        // layout: [mbarrier (16 B slot) | packed words of the CTA's reads]
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+        uint64_t* pw = reinterpret_cast<uint64_t*>(smem + 16);
+        const uint64_t r0 = blockIdx.x * (uint64_t)kThreadBlock;
+        const uint32_t nr = (uint32_t)min((uint64_t)kThreadBlock, p.reads.n - r0);
+        const uint32_t nw = (uint32_t)p.reads.wstride;
+        const uint64_t* src = p.reads.words + r0 * nw;
+        const uint32_t bytes = nr * nw * 8;
+        if ((bytes & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            if (threadIdx.x == 0) {
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, bytes);
+                bulk_g2s(pw, src, bytes, bar);
+            }
+            __syncthreads();  // the barrier is initialised before anyone polls it
+            mbar_wait(bar, 0);
+        } else {  // odd-sized last tile: plain loads
+            for (uint32_t i = threadIdx.x; i < nr * nw; i += kThreadBlock) pw[i] = src[i];
+            __syncthreads();
+        }
+        my_words = pw + threadIdx.x * nw;
+    }
+    DevSink sink{p};
+    const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
+    const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
+    // warp-uniform trip count: the hand-over below uses full-warp votes
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); base < n_todo; base += stride) {
+        const uint64_t it = base + lane;
+        const bool live = it < n_todo;
+        bool defer = false;
+        uint32_t why = 0;
+        uint64_t r = it;
+        ThreadEvents ev{};
+        uint4 sev = make_uint4(0, 0, 0, 0);
+        uint32_t L = 0, n_tx = 0, aligned = 0;
+        if (live) {
+            uint32_t hint[3];
+            if (HINT) {
+                const uint4 e = p.seeded[it];
+                r = e.x;
+                hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
+                if (EV) sev = p.seeded_ev[it];
+            }
+            const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+            L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+            ThreadResult res = TILE ? map_read_thread<KW, EV>(ix, PLoad{my_words}, (uint32_t)r, L, p.allowed_mismatches, p.max_probes,
+                                                              p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              HINT ? hint : nullptr)
+                                    : map_read_thread<KW, EV>(ix, PLoad{p.reads.words + wo}, (uint32_t)r, L, p.allowed_mismatches, p.max_probes,
+                                                              p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              HINT ? hint : nullptr);
+            defer = res.deferred;
+            why = res.why;
+            if (EV && defer && p.events) atomicAdd(p.events + 36 + res.why, 1ULL);
+            if (!defer) {
+                sink.result((uint32_t)r, res.hit, res.count_slot);
+                if (res.novel_overflow) sink.novel_overflow();
+                n_tx = res.hit.n_tx;
+                aligned = res.hit.flags & kFlagAligned;
+            } else if (EV && HINT && p.events) {
+                // k_map redoes this read from scratch and counts its first search again
+                atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
+                atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
+            }
+        }
+        // hand the given-up reads over (one atomic per warp and list): a too long FIRST seed search
+        // goes to k_seed_scan, everything else to the cooperative kernel
+        const bool to_scan = defer && !HINT && why == 0 && p.scan_list != nullptr;
+        const unsigned bs = __ballot_sync(kFull, to_scan);
+        if (bs) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(bs) - 1)) at = atomicAdd(p.scan_count, (unsigned long long)__popc(bs));
+            at = __shfl_sync(kFull, at, __ffs(bs) - 1);
+            if (to_scan) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = (uint32_t)r;
+        }
+        const bool to_coop = defer && !to_scan;
+        const unsigned bc = __ballot_sync(kFull, to_coop);
+        if (bc) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(bc) - 1)) at = atomicAdd(p.list_count, (unsigned long long)__popc(bc));
+            at = __shfl_sync(kFull, at, __ffs(bc) - 1);
+            if (to_coop) p.list[at + __popc(bc & ((1u << lane) - 1))] = (uint32_t)r;
+        }
+        if (EV && p.events) {
+            const bool cnt = live && !defer;
+            unsigned long long v[12] = {cnt ? 1ull : 0ull, cnt ? L : 0ull, ev.lookups, ev.levels, ev.hits, ev.verifs,
+                                        ev.visits, ev.bases, ev.jumps, ev.members, n_tx, aligned};
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                unsigned long long x = cnt ? v[i] : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+                if (lane == 0 && x) atomicAdd(p.events + i, x);
+            }
         }
     }
 }
@@ -1017,6 +1261,50 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
                 atomicAdd(e + 4, (unsigned long long)w.ev.hits); atomicAdd(e + 5, (unsigned long long)w.ev.verifs);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self-test entry: the three device routines that compute nodes_to_eq_class / intersect (ref
+// src/pseudoaligner.rs:323-356, :389-418) applied to two ascending lists in isolation -- one thread's
+// list scheme (thread_intersect_lists), the lane group's (intersect_pass) and the class windows.
+// ix holds the two lists as classes 0 and 1.  out: 3 x cap entries, n_out[3] (kNone: not applicable).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_selftest_intersect(DevIndex ix, MapParams p, uint32_t* out, uint32_t cap, uint32_t* n_out) {
+    const uint32_t n0 = (uint32_t)(ix.eq_off[1] - ix.eq_off[0]), n1 = (uint32_t)(ix.eq_off[2] - ix.eq_off[1]);
+    const int s = n1 < n0 ? 1 : 0;  // smallest class first, ties by id (ref :331-334)
+    if (threadIdx.x == 0) {
+        ClassAcc w;
+        w.init();
+        w.wide_eq[0] = 0; w.wide_eq[1] = 1; w.n_wide = 2;
+        const uint32_t c = thread_intersect_lists(ix, w, s, (uint32_t*)nullptr);
+        n_out[0] = c;
+        if (c <= cap) thread_intersect_lists(ix, w, s, out);
+        // windows
+        const ClassWin c0 = make_class_win(ix.eq_mem + ix.eq_off[0], n0), c1 = make_class_win(ix.eq_mem + ix.eq_off[1], n1);
+        if (c0.len == kWinWide || c1.len == kWinWide) {
+            n_out[2] = kNone;
+        } else {
+            WinAcc a;
+            a.base = 0; a.map = Win{0, 0, 0}; a.have = false;
+            winacc_and(a, c0);
+            winacc_and(a, c1);
+            n_out[2] = win_popc(a.map);
+            if (n_out[2] <= cap) win_write(a, out + 2 * (uint64_t)cap);
+        }
+    }
+    if (threadIdx.x < 8) {  // one group of the cooperative kernel
+        WarpCtx<1, false, 8> w(ix, nullptr, 0, p, 0);
+        w.n_list = 2;
+        if (w.lane < 2) {
+            w.my_eq = w.lane;
+            w.my_len = w.lane == 0 ? n0 : n1;
+            w.my_off = ix.eq_off[w.lane];
+        }
+        const uint32_t s_len = s ? n1 : n0;
+        const uint32_t c = intersect_pass(w, (uint32_t)s, s_len, ix.eq_off[s], (uint32_t*)nullptr);
+        if (w.lane == 0) n_out[1] = c;
+        if (c <= cap) intersect_pass(w, (uint32_t)s, s_len, ix.eq_off[s], out + cap);
     }
 }
 
@@ -1107,6 +1395,107 @@ __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t 
         if (t < total && ((fitmask >> q) & 1u)) tx_buf[rel0 + t] = __ldg(reinterpret_cast<const uint32_t*>((uintptr_t)sp) + (t - ss));
     }
 }
+// ---------------------------------------------------------------------------------------------
+// Novel sets: an eq_class that is no index class (the reference returns the set itself, ref
+// src/pseudoaligner.rs:323-356, :381-384) is counted per distinct set in a table that lives with the
+// mapper.  After the map kernels of a batch, one thread per read whose set is no index class hashes
+// the members, finds or claims the set's entry (open addressing, 64-bit compare-and-swap on the hash)
+// and adds one to its count; the claimer copies the members into the table's pool.  k_novel_verify
+// then compares every such read's members with its entry's: two different sets behind one 64-bit
+// hash would be reported (status bit 8), never merged silently.
+// ---------------------------------------------------------------------------------------------
+struct NovelEntry {
+    unsigned long long key;    // hash of the set (0 = empty slot)
+    unsigned long long count;  // reads whose eq_class is this set
+    unsigned long long off;    // members at pool[off ..) -- written by the claimer
+    uint32_t len;              // 0xFFFFFFFF: claimed, members not stored (pool full)
+    uint32_t pad;
+};
+static_assert(sizeof(NovelEntry) == 32, "NovelEntry");
+struct NovelTable {
+    NovelEntry* tab;
+    uint64_t cap;              // entries, a power of two
+    uint32_t* pool;
+    uint64_t pool_cap;
+    unsigned long long* cursors;  // [0] members used in pool, [1] entries claimed
+};
+constexpr uint32_t kStatusNovelClash = 8u, kStatusNovelFull = 16u;
+__device__ __forceinline__ unsigned long long novel_hash(const uint32_t* m, uint32_t n) {
+    unsigned long long h = mix64(0x9E3779B97F4A7C15ULL + n);
+    for (uint32_t i = 0; i < n; i++) h = mix64(h ^ ((unsigned long long)m[i] + 0xD6E8FEB86659FD93ULL));
+    return h ? h : 1ULL;
+}
+// step 1, over the batch's list of novel reads (written by the map kernels): find or claim the set's entry
+__global__ void k_novel_claim(const uint32_t* list, const unsigned long long* list_count, const HitRec* hits, const uint32_t* novel,
+                              NovelTable t, uint32_t* slot_out, uint32_t* status) {
+    const uint64_t n = *list_count;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (uint64_t)blockDim.x) {
+        const HitRec h = hits[list[i]];
+        const uint32_t* m = novel + h.tx_off;
+        const unsigned long long key = novel_hash(m, h.n_tx);
+        uint32_t found = kNone;
+        for (uint64_t probe = 0, slot = key & (t.cap - 1); probe < t.cap; probe++, slot = (slot + 1) & (t.cap - 1)) {
+            unsigned long long cur = t.tab[slot].key;
+            if (cur == 0) cur = atomicCAS(&t.tab[slot].key, 0ULL, key);
+            if (cur == 0) {  // claimed: publish the members
+                const unsigned long long off = atomicAdd(t.cursors, (unsigned long long)h.n_tx);
+                const unsigned long long ne = atomicAdd(t.cursors + 1, 1ULL);
+                if (off + h.n_tx > t.pool_cap || 2 * (ne + 1) > t.cap) {
+                    atomicOr(status, kStatusNovelFull);   // the host grows the table and redoes the batch
+                    t.tab[slot].len = 0xFFFFFFFFu;
+                } else {
+                    for (uint32_t j = 0; j < h.n_tx; j++) t.pool[off + j] = m[j];
+                    t.tab[slot].off = off;
+                    t.tab[slot].len = h.n_tx;
+                }
+                found = (uint32_t)slot;
+                break;
+            }
+            if (cur == key) {
+                found = (uint32_t)slot;
+                break;
+            }
+        }
+        if (found == kNone) atomicOr(status, kStatusNovelFull);
+        slot_out[i] = found;
+    }
+}
+// step 2: every listed read's members against its entry's -- two sets behind one hash are reported, never merged
+__global__ void k_novel_verify(const uint32_t* list, const unsigned long long* list_count, const HitRec* hits, const uint32_t* novel,
+                               NovelTable t, const uint32_t* slot_in, uint32_t* status) {
+    const uint64_t n = *list_count;
+    if (*status & kStatusNovelFull) return;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (uint64_t)blockDim.x) {
+        const HitRec h = hits[list[i]];
+        const uint32_t* m = novel + h.tx_off;
+        const NovelEntry e = t.tab[slot_in[i]];
+        bool same = e.len == h.n_tx;
+        for (uint32_t j = 0; same && j < h.n_tx; j++) same = t.pool[e.off + j] == m[j];
+        if (!same) atomicOr(status, kStatusNovelClash);
+    }
+}
+// step 3, once the batch is known to stand (no overflow of any buffer, tx_buf large enough): count
+__global__ void k_novel_add(const unsigned long long* list_count, NovelTable t, const uint32_t* slot_in, const uint32_t* status,
+                            const uint64_t* batch_total, uint64_t tx_cap, int has_tx) {
+    const uint64_t n = *list_count;
+    if ((*status & 31u) || (has_tx && *batch_total > tx_cap)) return;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (uint64_t)blockDim.x)
+        atomicAdd(&t.tab[slot_in[i]].count, 1ULL);
+}
+// growing the table: every used entry of the old one moves to the new one
+__global__ void k_novel_rehash(const NovelEntry* old_tab, uint64_t old_cap, NovelEntry* tab, uint64_t cap) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= old_cap) return;
+    const NovelEntry e = old_tab[i];
+    if (e.key == 0 || e.len == 0xFFFFFFFFu) return;
+    for (uint64_t slot = e.key & (cap - 1);; slot = (slot + 1) & (cap - 1)) {
+        if (atomicCAS(&tab[slot].key, 0ULL, e.key) == 0ULL) {
+            tab[slot].count = e.count; tab[slot].off = e.off; tab[slot].len = e.len;
+            return;
+        }
+    }
+}
+
 // Verification aid: order-independent checksum of a result batch -- the sum over reads of a hash chain over
 // (global read index, coverage, flags, eq_id, members in order).  oracle/psa_oracle.c restates it for host buffers.
 __global__ void k_result_checksum(const HitRec* hits, const uint32_t* tx, uint64_t n, uint64_t first_index, uint64_t tx_base,

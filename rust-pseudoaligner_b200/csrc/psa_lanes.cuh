@@ -16,9 +16,11 @@
 // cooperative kernels and the host simulation run).  A lane moves from block to block within one
 // call as long as it needs no new data (`wait` is set by every request).
 //
-// Payload registers: A = one sector (dictionary bucket | node record sector 0 | NodeCold),
-// B = node record sector 1 (the class window), C = four consecutive words of unitig sequence
-// starting at word c_base.  LS_READ alone uses A and C as the eight words of a new read.
+// Payloads: A = one sector (dictionary bucket | node record sector 0 | NodeCold), B = node record
+// sector 1 (the class window), C = four consecutive words of unitig sequence.  Which addresses a
+// state needs is a function of the lane's fields (requests()); LS_READ alone uses A and C as the
+// eight words of a new read.  The lane record is 136 bytes: the kernel keeps one per read in
+// flight in shared memory.
 #pragma once
 #include "psa_core.cuh"
 
@@ -61,85 +63,116 @@ struct LaneParams {
     bool to_scan;           // a too long FIRST search goes to the seed-scan kernel (else: cooperative kernel)
 };
 
+struct LaneRequests {
+    const void* a;        // one sector (nullptr: none)
+    const void* b;        // one sector
+    const uint64_t* c;    // four words
+    bool a_stream;        // a is a dictionary bucket (one use: evict-first)
+};
+
+template <bool EV>
+struct LaneEv {};
+template <>
+struct LaneEv<true> {
+    ThreadEvents ev;  // sequential-equivalent events of the read in flight
+};
+struct StepOut {
+    uint32_t emit;            // LE_*
+    uint32_t n_tx, aligned;   // with LE_RESULT
+};
+
 template <int KW, bool EV>
-struct Lane {
+struct Lane : LaneEv<EV> {
     uint32_t st;
     uint32_t r, L, flags;
     uint32_t kmer_pos, cov, node_id, kmer_offset;     // the reference's variables of the same names
-    // find_kmer_match
-    uint32_t f_start, f_p, f_probes, f_lvl;
-    KeyHash hk;
-    // the running compare: t-th base = read[cm_r +- t] vs seq[cm_s +- t]
-    uint32_t cm_r, cm_left, cm_done, snp;
     uint32_t cand;          // forward: successor taken if the whole span matches; left: the base selecting the predecessor
-    uint64_t cm_s, c_base;
-    // left extension
-    uint32_t last_pos, prev_node, prev_off;
-    uint32_t hint_pos, hint_node, hint_off;
+    uint32_t why;           // when a read is handed over: 0 first seed search, 1 re-seed search, 2 class list full,
+                            // 3 smallest class too long, 4 read too long
+    uint64_t cm_s;          // unitig position of the running compare / of the candidate k-mer being verified
+    union {
+        struct {            // find_kmer_match
+            uint32_t f_start, f_p, f_probes, f_lvl;
+            KeyHash hk;
+        };
+        struct {            // the running compare: t-th base = read[cm_r +- t] vs seq[cm_s +- t]; left extension
+            uint32_t cm_r, cm_left, cm_done, snp;
+            uint32_t last_pos, prev_node, prev_off, pad_;
+        };
+    };
     ClassAcc cls;
-    // requests served by the kernel's loop before the next step
-    const void* reqA;
-    const void* reqB;
-    const uint64_t* reqC;
-    uint32_t a_stream;      // reqA is a dictionary bucket (streamed: evict-first)
-    // output of the last step
-    uint32_t emit, why;     // why: 0 first seed search, 1 re-seed search, 2 class list full, 3 smallest class too long, 4 read too long
-    uint32_t out_n_tx, out_aligned;
-    ThreadEvents ev;
 
     PSA_HD void idle() {
-        st = LS_NEW; emit = LE_NONE; why = 0;
-        reqA = nullptr; reqB = nullptr; reqC = nullptr; a_stream = 0;
+        st = LS_NEW; why = 0;
         r = 0; L = 0; flags = 0;
     }
     // a new read for this lane; hint = {pos, node, off} of its first seed or nullptr
     PSA_HD void begin(uint32_t r_, uint32_t L_, uint32_t slot_words, const uint32_t* hint) {
         r = r_; L = L_;
         flags = hint ? LF_HINT : 0u;
-        if (hint) { hint_pos = hint[0]; hint_node = hint[1]; hint_off = hint[2]; }
+        if (hint) { kmer_pos = hint[0]; node_id = hint[1]; kmer_offset = hint[2]; }
         st = ((L + 31) >> 5) > slot_words ? LS_TOOLONG : LS_READ;
+    }
+
+    // first word of the four the backward compare fetches
+    static PSA_HD uint64_t left_base(uint64_t pos) {
+        const uint64_t w = pos >> 5;
+        return w >= 3 ? w - 3 : 0;
+    }
+    // what the lane's state needs before its next step (LS_READ: the read's words, fetched by the caller)
+    PSA_HD LaneRequests requests(const DevIndex& ix) const {
+        LaneRequests q;
+        q.a = nullptr; q.b = nullptr; q.c = nullptr; q.a_stream = false;
+        if (st == LS_BUCKET) {
+            q.a = bucket_addr(ix.dict, hk, f_lvl);
+            q.a_stream = true;
+        } else if (st == LS_VERIFY || st == LS_NODE) {
+            q.a = ix.nodes + node_id;
+            q.b = reinterpret_cast<const char*>(ix.nodes + node_id) + 32;
+            if (st == LS_VERIFY) q.c = ix.seq + (cm_s >> 5);
+        } else if (st == LS_LNODE) {
+            q.a = ix.nodes + prev_node;
+            q.b = reinterpret_cast<const char*>(ix.nodes + prev_node) + 32;
+        } else if (st == LS_LPRED) {
+            q.a = ix.nodes_cold + prev_node;
+        } else if (st == LS_CMP) {
+            q.c = ix.seq + (cm_s >> 5);
+        } else if (st == LS_LCMP) {
+            q.c = ix.seq + left_base(cm_s);
+        }
+        return q;
     }
 
     template <class RW>
     PSA_HD uint32_t read_base(const RW& rw, uint32_t pos) const { return seq_get(rw, pos); }
 
-    PSA_HD void req_node(const DevIndex& ix, uint32_t id) {
-        reqA = ix.nodes + id;
-        reqB = reinterpret_cast<const char*>(ix.nodes + id) + 32;
-        a_stream = 0;
-    }
-    PSA_HD void req_bucket(const DevIndex& ix) {
-        reqA = bucket_addr(ix.dict, hk, f_lvl);
-        a_stream = 1;
-    }
-    // ref :139-150: the span the backward compare may cover in node `start`, then its first words
-    PSA_HD void left_span(const DevIndex& ix, uint64_t start) {
+    // ref :139-150: the span the backward compare may cover in the node that starts at `start`
+    PSA_HD void left_span(uint64_t start) {
         const uint32_t skipped_read = last_pos + 1;                                     // :139
         const uint32_t skipped_ref = prev_off + 1;                                      // :142
         cm_left = skipped_read < skipped_ref ? skipped_read : skipped_ref;              // :145
         cm_r = last_pos; cm_s = start + prev_off; cm_done = 0; snp = 0;                 // :148-150
         flags &= ~LF_PREMATURE;
-        const uint64_t w = cm_s >> 5;
-        c_base = w >= 3 ? w - 3 : 0;
-        reqC = ix.seq + c_base;
         st = LS_LCMP;
     }
 
-    // One step.  A, B, C: the payloads requested by the previous step.  rw: the lane's read words
+    // One step.  A, B, C: the payloads requests() named before the call.  rw: the lane's read words
     // (rw(i) loads word i, rw.store(i, v) stores it).  sink: result(r, hit, count_slot),
-    // novel(count, off&) -> room for the members of a set that is no visited class (or nullptr),
+    // novel(r, count, off&) -> room for the members of a set that is no visited class (or nullptr),
     // novel_overflow().
     template <class RW, class Sink>
-    PSA_HD void step(const DevIndex& ix, const LaneParams& lp, RW& rw, const Sector& A, const Sector& B, const Sector& C,
-                     Sink& sink) {
-        emit = LE_NONE;
-        reqA = nullptr; reqB = nullptr; reqC = nullptr;
-        bool wait = false;  // a request has been made: no further block this step
+    PSA_HD StepOut step(const DevIndex& ix, const LaneParams& lp, RW& rw, const Sector& A, const Sector& B, const Sector& C,
+                        Sink& sink) {
+        StepOut out;
+        out.emit = LE_NONE; out.n_tx = 0; out.aligned = 0;
+        bool wait = false;  // the lane's next block needs data it does not have: no further block this step
         const uint32_t k = ix.k;
+        // the first of the four words C holds
+        uint64_t c_base = (st == LS_VERIFY || st == LS_CMP) ? cm_s >> 5 : st == LS_LCMP ? left_base(cm_s) : kNoWords;
 
         if (st == LS_TOOLONG) {
-            why = 4; emit = LE_TO_COOP; st = LS_NEW;
-            return;
+            why = 4; out.emit = LE_TO_COOP; st = LS_NEW;
+            return out;
         }
         if (st == LS_READ) {
             const uint32_t nw = (L + 31) >> 5;
@@ -151,18 +184,15 @@ struct Lane {
             if (nw > 5) rw.store(5, C.w1);
             if (nw > 6) rw.store(6, C.w2);
             if (nw > 7) rw.store(7, C.w3);
-            c_base = kNoWords;                                                         // C holds no unitig words
             cov = 0;                                                                   // :71
-            kmer_pos = 0;                                                              // :79
+            if (!(flags & LF_HINT)) kmer_pos = 0;                                      // :79
             cls.init();                                                                // :75
-            if (EV) ev = ThreadEvents{};
+            if constexpr (EV) this->ev = ThreadEvents{};
             if (L < k) {                                                               // :82-84
                 flags = 0;
                 st = LS_FIN;
-            } else if (flags & LF_HINT) {                                              // :118-121, answer given
-                kmer_pos = hint_pos; node_id = hint_node; kmer_offset = hint_off;
+            } else if (flags & LF_HINT) {                                              // :118-121, answer given (begin())
                 flags = LF_SEEDED | LF_FRESH;
-                req_node(ix, node_id);
                 wait = true;
                 st = LS_NODE;
             } else {
@@ -174,22 +204,18 @@ struct Lane {
 
         // ---- dbg_index.get (ref :96): one bucket of the cascade
         if (st == LS_BUCKET && !wait) {
-            if (EV) ev.levels++;
+            if constexpr (EV) this->ev.levels++;
             const uint64_t e = bucket_find(ix, A, hk);
             const bool more = bucket_more(A) && f_lvl + 1 < ix.dict.n_levels;
             if (e != kEmptyEntry) {
-                if (EV) { ev.hits++; ev.verifs++; }
+                if constexpr (EV) { this->ev.hits++; this->ev.verifs++; }
                 node_id = entry_node(ix, e);                      // (the previous node is done with: find runs between nodes)
                 cm_s = entry_pos(ix, e);
                 flags = more ? (flags | LF_MORE) : (flags & ~LF_MORE);
-                req_node(ix, node_id);
-                c_base = cm_s >> 5;
-                reqC = ix.seq + c_base;
                 wait = true;
                 st = LS_VERIFY;
             } else if (more) {
                 f_lvl++;
-                req_bucket(ix);
                 wait = true;
             } else {
                 f_probes++; f_p += kSeedStride;                                        // :110
@@ -209,7 +235,6 @@ struct Lane {
                 st = LS_NODE;                                                          // A, B are node_id's record
             } else if (flags & LF_MORE) {
                 f_lvl++;
-                req_bucket(ix);
                 wait = true;
                 st = LS_BUCKET;
             } else {
@@ -228,7 +253,7 @@ struct Lane {
                     last_pos = kmer_pos - 1;                                           // :127
                     prev_node = node_id;                                               // :128
                     prev_off = kmer_offset > 0 ? kmer_offset - 1 : 0;                  // :129 (sic)
-                    left_span(ix, nv.start);                                           // :132-150
+                    left_span(nv.start);                                               // :132-150
                     wait = true;
                     left = true;
                 }
@@ -236,13 +261,13 @@ struct Lane {
             if (!left) {
                 kmer_pos += k;                                                         // :215
                 cov += k;                                                              // :216
-                if (EV) ev.visits++;
+                if constexpr (EV) this->ev.visits++;
                 const bool fresh = cls.push(ix, nv.eq, nv.class_len, class_win_of(B)); // :219
-                if (EV && fresh) ev.members += nv.class_len;
+                if constexpr (EV) if (fresh) this->ev.members += nv.class_len;
                 flags |= LF_PUSHED;
-                if (cls.defer) {
-                    why = 2; emit = LE_TO_COOP; st = LS_NEW;
-                    return;
+                if (cls.defer()) {
+                    why = 2; out.emit = LE_TO_COOP; st = LS_NEW;
+                    return out;
                 }
                 const uint32_t remaining_read = L - kmer_pos;                          // :222
                 const uint32_t ref_offset = kmer_offset + k;                           // :227
@@ -257,11 +282,7 @@ struct Lane {
                     st = LS_AFTER;
                 } else {
                     st = LS_CMP;
-                    if ((cm_s >> 5) - c_base >= 4) {                                   // not in C (it is, right after a verification)
-                        c_base = cm_s >> 5;
-                        reqC = ix.seq + c_base;
-                        wait = true;
-                    }
+                    if ((cm_s >> 5) - c_base >= 4) wait = true;                        // not in C (it is, right after a verification)
                 }
             }
         }
@@ -270,29 +291,26 @@ struct Lane {
             const uint32_t pred_id = cand == 0 ? (uint32_t)A.w0 : cand == 1 ? (uint32_t)(A.w0 >> 32)
                                    : cand == 2 ? (uint32_t)A.w1 : (uint32_t)(A.w1 >> 32);
             if (pred_id != kNone) {                                                    // :183
-                if (EV) ev.jumps++;
+                if constexpr (EV) this->ev.jumps++;
                 prev_node = pred_id;                                                   // :185-194
-                req_node(ix, pred_id);
-                wait = true;
                 st = LS_LNODE;
             } else {                                                                   // :201
-                req_node(ix, node_id);
-                wait = true;
-                st = LS_NODE;
+                st = LS_NODE;                                                          // on to the forward search
             }
+            wait = true;
         }
         if (st == LS_LNODE && !wait) {
             const NodeView pv = node_view_of(A);                                       // :195
             prev_off = pv.len - k;                                                     // :196
-            if (EV) ev.visits++;
+            if constexpr (EV) this->ev.visits++;
             const bool fresh = cls.push(ix, pv.eq, pv.class_len, class_win_of(B));     // :199
-            if (EV && fresh) ev.members += pv.class_len;
+            if constexpr (EV) if (fresh) this->ev.members += pv.class_len;
             flags |= LF_PUSHED;
-            if (cls.defer) {
-                why = 2; emit = LE_TO_COOP; st = LS_NEW;
-                return;
+            if (cls.defer()) {
+                why = 2; out.emit = LE_TO_COOP; st = LS_NEW;
+                return out;
             }
-            left_span(ix, pv.start);                                                   // :132-150 of the next round
+            left_span(pv.start);                                                       // :132-150 of the next round
             wait = true;
         }
         if (st == LS_LCMP && !wait) {                                                  // :151-170, up to 128 bases
@@ -322,32 +340,23 @@ struct Lane {
             }
             if (prem) {
                 cm_done += matched_here;
-                if (EV) ev.bases += matched_here + 1;
+                if constexpr (EV) this->ev.bases += matched_here + 1;
                 flags |= LF_PREMATURE;
                 st = LS_LAFTER;
             } else {
                 cm_done += n; cm_left -= n; cm_r -= n; cm_s -= n;
-                if (EV) ev.bases += n;
-                if (cm_left == 0) {
-                    st = LS_LAFTER;
-                } else {
-                    const uint64_t w = cm_s >> 5;
-                    c_base = w >= 3 ? w - 3 : 0;
-                    reqC = ix.seq + c_base;
-                    wait = true;
-                }
+                if constexpr (EV) this->ev.bases += n;
+                if (cm_left == 0) st = LS_LAFTER;
+                else wait = true;
             }
         }
         if (st == LS_LAFTER && !wait) {
             cov += cm_done;                                                            // :169
             if (last_pos + 1 - cm_done == 0 || (flags & LF_PREMATURE)) {               // :173-175
-                req_node(ix, node_id);                                                 // on to the forward search
-                st = LS_NODE;
+                st = LS_NODE;                                                          // on to the forward search
             } else {
                 last_pos -= cm_done;                                                   // :178
                 cand = read_base(rw, last_pos);                                        // :182
-                reqA = ix.nodes_cold + prev_node;
-                a_stream = 0;
                 st = LS_LPRED;
             }
             wait = true;
@@ -380,19 +389,14 @@ struct Lane {
             }
             if (prem) {
                 cm_done += matched_here;
-                if (EV) ev.bases += matched_here + 1;
+                if constexpr (EV) this->ev.bases += matched_here + 1;
                 flags |= LF_PREMATURE;
                 st = LS_AFTER;
             } else {
                 cm_done += n; cm_left -= n; cm_r += n; cm_s += n;
-                if (EV) ev.bases += n;
-                if (cm_left == 0) {
-                    st = LS_AFTER;
-                } else {
-                    c_base = cm_s >> 5;
-                    reqC = ix.seq + c_base;
-                    wait = true;
-                }
+                if constexpr (EV) this->ev.bases += n;
+                if (cm_left == 0) st = LS_AFTER;
+                else wait = true;
             }
         }
         // ---- after the compare (ref :254-300)
@@ -402,12 +406,11 @@ struct Lane {
             if (kmer_pos >= L) {                                                       // :259-261
                 st = LS_FIN;
             } else if (!(flags & LF_PREMATURE) && cand != kNone) {                     // :267
-                if (EV) ev.jumps++;
+                if constexpr (EV) this->ev.jumps++;
                 node_id = cand;                                                        // :269-278
                 kmer_offset = 0;                                                       // :279
                 kmer_pos -= k - 1;                                                     // :282
                 cov -= k - 1;                                                          // :283
-                req_node(ix, node_id);
                 wait = true;
                 st = LS_NODE;
             } else if (kmer_pos > L - k) {                                             // :287-290
@@ -427,14 +430,13 @@ struct Lane {
                 const uint32_t reseed = lp.max_probes > kReseedProbes ? lp.max_probes : kReseedProbes;
                 if (f_probes >= ((flags & LF_SEEDED) ? reseed : lp.max_probes)) {      // hand the read over
                     why = (flags & LF_SEEDED) ? 1u : 0u;
-                    emit = (why == 0 && lp.to_scan) ? LE_TO_SCAN : LE_TO_COOP;
+                    out.emit = (why == 0 && lp.to_scan) ? LE_TO_SCAN : LE_TO_COOP;
                     st = LS_NEW;
-                    return;
+                    return out;
                 }
-                if (EV) ev.lookups++;                                                  // :95
+                if constexpr (EV) this->ev.lookups++;                                                  // :95
                 hk = make_hash(KmerOps<KW>::fold(KmerOps<KW>::get(rw, f_p, k)));       // :93
                 f_lvl = 0;
-                req_bucket(ix);
                 wait = true;
                 st = LS_BUCKET;
             }
@@ -448,8 +450,8 @@ struct Lane {
                 uint32_t count, eq_id;
                 int s;
                 if (!class_result(ix, cls, lp.max_small, count, eq_id, s)) {
-                    why = 3; emit = LE_TO_COOP; st = LS_NEW;
-                    return;
+                    why = 3; out.emit = LE_TO_COOP; st = LS_NEW;
+                    return out;
                 }
                 h.coverage = cov;
                 h.n_tx = count;
@@ -459,21 +461,22 @@ struct Lane {
                     count_slot = eq_id;  // (members: k_expand reads them from the index through eq_id)
                 } else {
                     count_slot = ix.n_eq;
-                    if (count && lp.want_members) {
+                    if (lp.want_members) {   // (the empty set too: it is listed and counted like any other)
                         uint64_t o = 0;
-                        uint32_t* dst = sink.novel(count, o);
+                        uint32_t* dst = sink.novel(r, count, o);
                         if (!dst) sink.novel_overflow();
-                        else class_members(ix, cls, s, dst);
+                        else if (count) class_members(ix, cls, s, dst);
                         h.tx_off = o;
                     }
                 }
             }
             sink.result(r, h, count_slot);
-            out_n_tx = h.n_tx;
-            out_aligned = h.flags & kFlagAligned;
-            emit = LE_RESULT;
+            out.n_tx = h.n_tx;
+            out.aligned = h.flags & kFlagAligned;
+            out.emit = LE_RESULT;
             st = LS_NEW;
         }
+        return out;
     }
 };
 

@@ -68,6 +68,11 @@ class _ProcessStats(C.Structure):
                 ("reader_seconds", C.c_double), ("mapper_seconds", C.c_double), ("writer_seconds", C.c_double)]
 
 
+class _NovelSets(C.Structure):
+    _fields_ = [("n_sets", C.c_uint64), ("n_members", C.c_uint64), ("offsets", C.POINTER(C.c_uint64)),
+                ("members", C.POINTER(C.c_uint32)), ("counts", C.POINTER(C.c_uint64))]
+
+
 class _Events(C.Structure):
     _fields_ = [(f, C.c_uint64) for f in EVENT_FIELDS]
 
@@ -84,6 +89,8 @@ EXPORTS = (
     "psa_comm_unique_id", "psa_comm_create", "psa_comm_destroy", "psa_mapper_counts_allreduce",
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
     "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe", "psa_result_checksum",
+    "psa_selftest_intersect", "psa_mapper_novel_sets", "psa_novel_sets_merge", "psa_novel_sets_free",
+    "psa_mapper_novel_allgather",
 )
 
 
@@ -150,12 +157,61 @@ def lib():
     L.psa_memcpy_d2h.restype, L.psa_memcpy_d2h.argtypes = i32, [vp, vp, u64]
     L.psa_gather_probe.restype = i32
     L.psa_gather_probe.argtypes = [i32, u64, u32, u32, C.POINTER(C.c_double)]
+    L.psa_mapper_novel_sets.restype, L.psa_mapper_novel_sets.argtypes = i32, [vp, C.POINTER(_NovelSets)]
+    L.psa_novel_sets_merge.restype, L.psa_novel_sets_merge.argtypes = i32, [C.POINTER(_NovelSets), u32, C.POINTER(_NovelSets)]
+    L.psa_novel_sets_free.restype, L.psa_novel_sets_free.argtypes = None, [C.POINTER(_NovelSets)]
+    L.psa_mapper_novel_allgather.restype, L.psa_mapper_novel_allgather.argtypes = i32, [vp, vp, C.POINTER(_NovelSets)]
+    L.psa_selftest_intersect.restype = i32
+    L.psa_selftest_intersect.argtypes = [i32, vp, u32, vp, u32, vp, u32, C.POINTER(u32 * 3)]
     L.psa_result_checksum.restype = i32
     L.psa_result_checksum.argtypes = [i32, vp, vp, u64, u64, C.POINTER(u64)]
     L.psa_process_reads.restype = i32
     L.psa_process_reads.argtypes = [vp, C.c_char_p, C.c_char_p, u32, u64, i32, C.POINTER(_ProcessStats)]
     _lib = L
     return L
+
+
+def _novel_to_py(ns):
+    """psa_novel_sets -> [(tuple(members), count)] in id order (id = n_eq + position)."""
+    n = int(ns.n_sets)
+    off = np.ctypeslib.as_array(ns.offsets, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
+    mem = np.ctypeslib.as_array(ns.members, shape=(max(int(ns.n_members), 1),)).copy()
+    cnt = np.ctypeslib.as_array(ns.counts, shape=(n,)).copy() if n else np.zeros(0, np.uint64)
+    return [(tuple(int(x) for x in mem[int(off[i]):int(off[i + 1])]), int(cnt[i])) for i in range(n)]
+
+
+def novel_sets_merge(tables):
+    """psa_novel_sets_merge over tables given as [(members tuple, count)] lists -> the merged, sorted table."""
+    parts = (_NovelSets * max(len(tables), 1))()
+    keep = []
+    for p, t in zip(parts, tables):
+        off = np.zeros(len(t) + 1, np.uint64)
+        off[1:] = np.cumsum([len(m) for m, _ in t])
+        mem = np.array([x for m, _ in t for x in m] + [0], dtype=np.uint32)
+        cnt = np.array([c for _, c in t] + [0], dtype=np.uint64)
+        keep.append((off, mem, cnt))
+        p.n_sets, p.n_members = len(t), int(off[-1])
+        p.offsets = off.ctypes.data_as(C.POINTER(C.c_uint64))
+        p.members = mem.ctypes.data_as(C.POINTER(C.c_uint32))
+        p.counts = cnt.ctypes.data_as(C.POINTER(C.c_uint64))
+    out = _NovelSets()
+    _check(lib().psa_novel_sets_merge(parts, len(tables), C.byref(out)))
+    res = _novel_to_py(out)
+    lib().psa_novel_sets_free(C.byref(out))
+    return res
+
+
+def selftest_intersect(v1, v2, device=0):
+    """The three device intersection routines on two ascending lists -> (thread lists, lane group, windows | None)."""
+    a = np.ascontiguousarray(v1, dtype=np.uint32)
+    b = np.ascontiguousarray(v2, dtype=np.uint32)
+    cap = max(len(a), len(b), 1)
+    out = np.zeros(3 * cap, np.uint32)
+    n = (C.c_uint32 * 3)()
+    _check(lib().psa_selftest_intersect(int(device), _ptr(a), len(a), _ptr(b), len(b), _ptr(out), cap, C.byref(n)))
+    res = [out[i * cap:i * cap + n[i]].tolist() for i in range(2)]
+    res.append(None if n[2] == EQ_NONE else out[2 * cap:2 * cap + n[2]].tolist())
+    return res
 
 
 def gather_probe(device=0, table_bytes=1 << 30, chunk_bytes=32, iters=64):
@@ -461,6 +517,18 @@ class Mapper:
     def counts_allreduce(self, comm):
         _check(lib().psa_mapper_counts_allreduce(self.h, comm.h))
 
+    def novel_sets(self, comm=None):
+        """[(members tuple, count)] of the sets that are no index class, sorted by (length, contents): the id of
+        entry i is n_eq + i.  With `comm`: the tables of all ranks merged (psa_mapper_novel_allgather)."""
+        out = _NovelSets()
+        if comm is None:
+            _check(lib().psa_mapper_novel_sets(self.h, C.byref(out)))
+        else:
+            _check(lib().psa_mapper_novel_allgather(self.h, comm.h, C.byref(out)))
+        res = _novel_to_py(out)
+        lib().psa_novel_sets_free(C.byref(out))
+        return res
+
     def launch_count(self):
         return int(lib().psa_mapper_launch_count(self.h))
 
@@ -477,7 +545,7 @@ class Mapper:
         """-> {kernel: (summed device ms, launches)} since the last read."""
         ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
         _check(lib().psa_mapper_profile_read(self.h, C.byref(ms), C.byref(n)))
-        return {"k_map_lanes": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1])),
+        return {"k_map_thread": (float(ms[0]), int(n[0])), "k_map": (float(ms[1]), int(n[1])),
                 "k_seed_scan": (float(ms[2]), int(n[2]))}
 
     def close(self):

@@ -20,6 +20,7 @@
 
 #include "../../rust-pseudoaligner_b200/csrc/psa_core.cuh"
 #include "../../rust-pseudoaligner_b200/csrc/psa_lanes.cuh"
+#include "../../rust-pseudoaligner_b200/csrc/psa_thread.cuh"
 
 using namespace psa;
 
@@ -290,7 +291,7 @@ struct HostSink {
         hit->coverage = h.coverage; hit->n_tx = h.n_tx; hit->tx_off = h.tx_off; hit->eq_id = h.eq_id; hit->flags = h.flags;
         got = true;
     }
-    uint32_t* novel(uint32_t count, uint64_t& off) {
+    uint32_t* novel(uint32_t, uint32_t count, uint64_t& off) {
         off = 0;
         novel_buf.assign(count, 0);
         return novel_buf.data();
@@ -302,31 +303,36 @@ template <int KW>
 static uint32_t lane_one(const HsIndex* ix, const uint64_t* words, uint32_t L, const LaneParams& lp, const uint32_t* hint,
                          HsHit& h, std::vector<uint32_t>& tx, uint64_t* steps) {
     Lane<KW, false> ln;
+    static_assert(sizeof(Lane<KW, false>) == 136, "the lane record is sized for shared memory");
     ln.idle();
     ln.begin(0, L, 8, hint);
     HostWords rw{};
     HostSink sink{&h, {}};
     Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
     const uint32_t nw = (L + 31) / 32;
+    uint32_t emit = LE_NONE;
     for (;;) {
+        // payloads are NOT kept between steps (the pool kernel reloads them): poison them
+        A = Sector{~0ULL, ~0ULL, ~0ULL, ~0ULL}; B = A; C = A;
         if (ln.st == LS_READ) {
             A.w0 = nw > 0 ? words[0] : 0; A.w1 = nw > 1 ? words[1] : 0; A.w2 = nw > 2 ? words[2] : 0; A.w3 = nw > 3 ? words[3] : 0;
             if (nw > 4) { C.w0 = words[4]; C.w1 = nw > 5 ? words[5] : 0; C.w2 = nw > 6 ? words[6] : 0; C.w3 = nw > 7 ? words[7] : 0; }
         } else {
-            if (ln.reqA) A = load_sector_hot(ln.reqA);
-            if (ln.reqB) B = load_sector_hot(ln.reqB);
-            if (ln.reqC) { C.w0 = ln.reqC[0]; C.w1 = ln.reqC[1]; C.w2 = ln.reqC[2]; C.w3 = ln.reqC[3]; }
+            const LaneRequests q = ln.requests(ix->d);
+            if (q.a) A = load_sector_hot(q.a);
+            if (q.b) B = load_sector_hot(q.b);
+            if (q.c) { C.w0 = q.c[0]; C.w1 = q.c[1]; C.w2 = q.c[2]; C.w3 = q.c[3]; }
         }
-        ln.step(ix->d, lp, rw, A, B, C, sink);
+        emit = ln.step(ix->d, lp, rw, A, B, C, sink).emit;
         if (steps) (*steps)++;
-        if (ln.emit != LE_NONE) break;
+        if (emit != LE_NONE) break;
     }
-    if (ln.emit == LE_RESULT) {
+    if (emit == LE_RESULT) {
         h.tx_off = tx.size();
         const uint32_t* src = h.eq_id != kNone ? ix->eq_mem.data() + ix->eq_off[h.eq_id] : sink.novel_buf.data();
         tx.insert(tx.end(), src, src + h.n_tx);
     }
-    return ln.emit;
+    return emit;
 }
 
 extern "C" {
@@ -366,6 +372,35 @@ uint64_t hs_map_batch_lanes(const HsIndex* ix, const uint64_t* words, const uint
     }
     if (n_deferred) *n_deferred = nd;
     if (n_steps) *n_steps = steps;
+    memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
+    return tx.size();
+}
+
+// The blocking thread-per-read policy (psa_thread.cuh ThreadCtx / map_read_thread), hand-overs redone by the
+// serial stand-in of the cooperative kernel.
+uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,
+                             const uint32_t* read_len, uint64_t n, uint32_t allowed, uint32_t max_probes,
+                             uint32_t max_small, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap, uint64_t* n_deferred) {
+    std::vector<uint32_t> tx;
+    uint64_t nd = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        HostSink sink{&hits[i], {}};
+        ThreadResult r;
+        if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, max_small, sink, true, nullptr);
+        else r = map_read_thread<2, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, max_small, sink, true, nullptr);
+        if (r.deferred) {
+            nd++;
+            if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+            else map_one<2>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
+            continue;
+        }
+        HsHit& h = hits[i];
+        h.coverage = r.hit.coverage; h.n_tx = r.hit.n_tx; h.eq_id = r.hit.eq_id; h.flags = r.hit.flags;
+        h.tx_off = tx.size();
+        const uint32_t* src = r.hit.eq_id != kNone ? ix->eq_mem.data() + ix->eq_off[r.hit.eq_id] : sink.novel_buf.data();
+        tx.insert(tx.end(), src, src + r.hit.n_tx);
+    }
+    if (n_deferred) *n_deferred = nd;
     memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
     return tx.size();
 }

@@ -148,6 +148,7 @@ def _check_events(ev, want_ev):
                              ("edge_jumps", "edge_jumps"), ("out_members", "out_members"), ("aligned", "aligned")):
         assert ev[key_gpu] == want_ev[key_orc], (key_gpu, ev, want_ev)
     assert ev["verifications"] >= want_ev["dict_hits"] and ev["dict_levels"] >= ev["kmer_lookups"]
+    assert ev["dict_hits"] == ev["verifications"]
 
 
 def test_device_batch_and_events(orc_index_for, fixture_fasta):
@@ -250,7 +251,135 @@ def test_parity_random_transcriptomes(k):
         pa.close()
 
 
-def test_allowed_mismatches_and_invalid_index(orc_index_for, fixture_fasta):
+# the reference's own vectors for intersect, ref src/pseudoaligner.rs:544-559
+INTERSECT_VECTORS = [
+    [1, 2, 3, 4, 5, 6, 7, 8, 9], [1, 2, 3], [1, 4, 5], [7, 8, 9], [9], [], [1, 2, 3, 6, 7, 8, 9], [1, 7, 8, 9, 10],
+    [10, 15, 20], [21, 22, 23], [0], [0, 1000, 5000], [0, 1000, 1000001], [5], [100000000], [1, 23, 45, 1000001, 100000000],
+]
+
+
+def test_intersect_vectors_on_device():
+    """intersect_test + intersect_prop_test (ref src/pseudoaligner.rs:542-586) against the DEVICE routines in
+    isolation: one thread's list scheme, the cooperative kernel's lane-group scheme and the class windows
+    (psa_selftest_intersect), every ordered pair of the reference's 16 vectors, then random ascending lists."""
+    psa = pkg.pseudoaligner
+
+    def check(v1, v2):
+        want = sorted(set(v1) & set(v2))
+        assert orc.intersect(v1, v2) == want
+        t, g, w = psa.selftest_intersect(v1, v2)
+        assert t == want and g == want, (v1, v2, t, g, want)
+        narrow = all((not v) or v[-1] - v[0] < 192 for v in (v1, v2))
+        assert (w is not None) == narrow
+        if w is not None:
+            assert w == want, (v1, v2, w, want)
+
+    for v1 in INTERSECT_VECTORS:
+        for v2 in INTERSECT_VECTORS:
+            check(v1, v2)
+            check(v2, v1)
+    rng = np.random.default_rng(6)
+    for case in range(300):
+        hi = (100, 150, 400, 100000)[case % 4]
+        v1 = sorted(set(rng.integers(0, hi, int(rng.integers(0, 400))).tolist()))
+        v2 = sorted(set(rng.integers(0, hi, int(rng.integers(0, 400))).tolist()))
+        check(v1, v2)
+
+
+def test_constructed_branches(fixture_fasta):
+    """QUIRK-1 (seed at unitig offset 0 + left extension, ref :129), QUIRK-3 (left walk over >= 2 predecessors, ref
+    :199), QUIRK-2, re-seed into a visited node (ref :293), break near the read's end (ref :287-290): constructed
+    reads on a constructed graph.  The branch is asserted on the oracle's walk; the GPU must give the oracle's
+    answer AND count the oracle's events (node visits, edge jumps, bases compared, k-mer lookups) -- the same walk."""
+    from test_hostsim import _assert_constructed_walks
+    S, seqs = cases.constructed_transcriptome()
+    ix = orc.OrcIndex.build(seqs, 20)
+    named = cases.constructed_reads(S)
+    _assert_constructed_walks(ix, named)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0)
+    for name, read in named.items():
+        reads = [read.decode()]
+        want_hits, want_tx, _, want_ev = _oracle(ix, reads)
+        for probes, scan in ((64, 0), (3, 8), (0, 8)):        # the lanes alone / lanes + seed scan / cooperative kernel alone
+            pa.mapper.set_fast_path(probes, 32)
+            pa.mapper.set_scan_width(scan)
+            got_hits, got_tx = pa.mapper.map_ascii(reads)
+            _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+            data = np.frombuffer(read, dtype=np.uint8)
+            b = pkg.DeviceBatch(pkg.pseudoaligner.READS_ASCII, data, 1, stride=len(read), fixed_len=len(read), tx_cap=1024)
+            ev = pa.mapper.map_device_events(b)
+            b.free()
+            _check_events(ev, want_ev)
+    pa.close()
+
+
+@pytest.mark.parametrize("allowed", [0, 1, 3, 7])
+def test_allowed_mismatches(pa_for, orc_index_for, fixture_fasta, allowed):
+    """map_read_with_mismatch (ref :361) with allowed_mismatches other than DEFAULT_ALLOWED_MISMATCHES:
+    psa_mapper_set_allowed_mismatches against an oracle that takes A."""
+    ix = orc_index_for(20)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0)
+    rng = np.random.default_rng(40 + allowed)
+    reads = util.sample_reads(rng, fixture_fasta[1], 3000, 150, p_sub=0.03, mix=(0.9, 0.1, 0.0))
+    reads += cases.left_extension_reads(rng, fixture_fasta[1], 500, 150, 20)
+    words, off, lens = orc.pack_reads(reads)
+    want_hits, want_tx, want_counts, _ = ix.map_batch(words, off, lens, counts=True, allowed=allowed)
+    base_hits = ix.map_batch(words, off, lens)[0]
+    assert not np.array_equal(base_hits["coverage"], want_hits["coverage"])      # the answers do depend on A
+    pa.mapper.set_allowed_mismatches(allowed)
+    for probes, scan in ((None, None), (0, 8), (64, 0)):
+        if probes is not None:
+            pa.mapper.set_fast_path(probes, 32)
+            pa.mapper.set_scan_width(scan)
+        pa.mapper.counts_reset()
+        got_hits, got_tx = pa.mapper.map_ascii(reads)
+        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+        assert np.array_equal(pa.mapper.counts(), want_counts)
+    pa.close()
+
+
+def test_config2_one_million_reads(fixture_fasta):
+    """BASELINE config 2 as stated: 1 M synthetic 150 bp reads (seed 1: 90 % transcript reads with 0.5 %
+    substitutions, 5 % chimeric, 5 % random) vs the gencode_small.fa index, k = 20, one GPU, FULL per-read
+    equality with the oracle on (aligned?, flag, transcript set, coverage, eq_id, member layout) and equal counts."""
+    codes, off = host.encode_transcripts(fixture_fasta[1])
+    tr = host.Transcriptome.from_codes(codes, off)
+    flat, _ = host.build_graph(codes, off, 20)
+    n, L = 1000000, 150
+    data = tr.reads(1, 0, n, L)
+    pa = pkg.Pseudoaligner(flat, device=0)
+    got_hits, got_tx = pa.mapper.map_ascii_fixed(data, n, L)
+    ox = orc.OrcIndex.from_flat(flat)
+    import threading
+    T = min(16, os.cpu_count() or 1)
+    bounds = [n * t // T for t in range(T + 1)]
+    res = [None] * T
+
+    def work(t):
+        res[t] = ox.map_ascii_fixed(data, n, L, start=bounds[t], stop=bounds[t + 1], counts=True)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(T)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    want_hits = np.concatenate([r[0] for r in res])
+    base, o = 0, 0
+    for r in res:
+        want_hits["tx_off"][o:o + len(r[0])] += np.uint64(base)
+        base += len(r[1])
+        o += len(r[0])
+    want_tx = np.concatenate([r[1] for r in res])
+    want_counts = sum(r[2] for r in res)
+    for f in ("coverage", "n_tx", "eq_id", "flags", "tx_off"):
+        assert np.array_equal(got_hits[f], want_hits[f]), f
+    assert np.array_equal(got_tx, want_tx)
+    assert np.array_equal(pa.mapper.counts(), want_counts)
+    assert 0.93 * n < int((got_hits["flags"] & 1).sum()) < 0.97 * n       # ~5 % random reads do not align
+    assert orc.result_checksum(want_hits, want_tx) == orc.result_checksum(got_hits, got_tx)
+    pa.close()
+
+
+def test_invalid_index(orc_index_for, fixture_fasta):
     ix = orc_index_for(20)
     flat = ix.flat()
     bad = dict(flat)
@@ -466,3 +595,52 @@ def test_pack_every_byte_value(pa_for, orc_index_for, fixture_fasta):
     padded[:len(reads) * stride].reshape(len(reads), stride)[:, :length] = flat.reshape(len(reads), length)
     got_hits, got_tx = pa.mapper.map_ascii_fixed(padded, len(reads), length, stride=stride)
     _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+
+
+def _oracle_novel_table(hits, tx):
+    """[(members tuple, count)] sorted by (length, contents) of the oracle's results that are no visited class."""
+    tab = {}
+    for h in hits[(hits["flags"] & 1).astype(bool) & (hits["eq_id"] == 0xFFFFFFFF)]:
+        key = tuple(int(x) for x in tx[int(h["tx_off"]):int(h["tx_off"]) + int(h["n_tx"])])
+        tab[key] = tab.get(key, 0) + 1
+    return sorted(tab.items(), key=lambda kv: (len(kv[0]), kv[0]))
+
+
+@pytest.mark.parametrize("table_cap", ["", "16"])
+def test_novel_sets(fixture_fasta, monkeypatch, table_cap):
+    """Sets that are no index class (ref src/pseudoaligner.rs:323-356 returns the set itself): one entry per distinct
+    set with its read count, ids by (length, contents) order, equal to the oracle's whatever the kernel split, the
+    chunking of the call or the table's initial size (16 entries: it must grow several times); counts[n_eq] is the
+    table's sum; a reset clears it."""
+    if table_cap:
+        monkeypatch.setenv("PSA_NOVEL_TABLE_CAP", table_cap)
+    rng = np.random.default_rng(17)
+    seqs = list(fixture_fasta[1][:500])
+    ix = orc.OrcIndex.build(seqs, 20)
+    reads = util.sample_reads(rng, seqs, 6000, 150, p_sub=0.02, mix=(0.6, 0.4, 0.0))     # chimeric + noisy: many novel sets
+    want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
+    want_tab = _oracle_novel_table(want_hits, want_tx)
+    assert len(want_tab) > 50 and any(len(m) == 0 for m, _ in want_tab) and any(c > 1 for _, c in want_tab)
+    pa = pkg.Pseudoaligner(ix.flat(), device=0, chunk_reads=700)
+    n_eq = pa.index.n_eq
+    for probes, scan, lanes in ((None, None, False), (0, 8, False), (64, 0, False), (3, 8, True)):
+        if lanes:
+            monkeypatch.setenv("PSA_FAST_KERNEL", "lanes")
+            pa.close()
+            pa = pkg.Pseudoaligner(ix.flat(), device=0, chunk_reads=700)
+        if probes is not None:
+            pa.mapper.set_fast_path(probes, 32)
+            pa.mapper.set_scan_width(scan)
+        pa.mapper.counts_reset()
+        got_hits, got_tx = pa.mapper.map_ascii(reads)
+        _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+        tab = pa.mapper.novel_sets()
+        assert tab == want_tab
+        counts = pa.mapper.counts()
+        assert np.array_equal(counts, want_counts) and int(counts[n_eq]) == sum(c for _, c in tab)
+        # a second call doubles every count; hits-only calls count too
+        pa.mapper.map_ascii(reads, want_tx=False)
+        assert pa.mapper.novel_sets() == [(m, 2 * c) for m, c in want_tab]
+    pa.mapper.counts_reset()
+    assert pa.mapper.novel_sets() == []
+    pa.close()

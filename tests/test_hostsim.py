@@ -35,6 +35,8 @@ def hs():
     L.hs_lookup.restype, L.hs_lookup.argtypes = C.c_int, [vp, vp, C.POINTER(u32), C.POINTER(u32)]
     L.hs_map_batch.restype = u64
     L.hs_map_batch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64]
+    L.hs_map_batch_thread.restype = u64
+    L.hs_map_batch_thread.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, vp, vp, u64, C.POINTER(u64)]
     L.hs_map_batch_lanes.restype = u64
     L.hs_map_batch_lanes.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, C.c_int, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.hs_pack_ascii.argtypes = [C.c_char_p, u64, vp]
@@ -81,6 +83,20 @@ class HsIndex:
                 return hits, tx[:need], int(nd.value), int(ns.value)
             cap = int(need)
 
+    def map_batch_thread(self, words, off, lens, max_probes, max_small, allowed=2):
+        """The blocking thread-per-read policy, hand-overs redone by the serial policy."""
+        n = len(lens)
+        hits = np.zeros(n, dtype=orc.HIT_DTYPE)
+        cap = max(64 * n, 4096)
+        nd = C.c_uint64()
+        while True:
+            tx = np.zeros(cap, np.uint32)
+            need = self.L.hs_map_batch_thread(self.h, _p(words), _p(off), _p(lens), n, allowed, max_probes, max_small,
+                                              _p(hits), _p(tx), cap, C.byref(nd))
+            if need <= cap:
+                return hits, tx[:need], int(nd.value)
+            cap = int(need)
+
     def close(self):
         self.L.hs_index_destroy(self.h)
 
@@ -103,6 +119,12 @@ def _compare(ix_orc, ix_hs, reads, lane_cfgs=((1, 4, False), (3, 64, False), (64
         assert np.array_equal(t1, t3)
         _DEFER[(max_probes, max_small)] = _DEFER.get((max_probes, max_small), 0) + nd
         _DEFER["reads"] = _DEFER.get("reads", 0) + len(reads)
+        if not hinted:   # the same split by the blocking thread-per-read policy
+            h4, t4, _ = ix_hs.map_batch_thread(words, off, lens, max_probes, max_small, allowed=allowed)
+            d = orc.hits_to_tuples(h4, t4)
+            for i, (x, y) in enumerate(zip(a, d)):
+                assert x == y, ("thread", max_probes, max_small, i, reads[i], x, y)
+            assert np.array_equal(h1["eq_id"], h4["eq_id"]) and np.array_equal(t1, t4)
     return a
 
 
@@ -207,4 +229,51 @@ def test_hostsim_wide_classes(hs, fixture_fasta):
     hx = HsIndex(hs, flat)
     for name, reads in cases.read_sets(rng, seqs, 150, 20, scale=0.5).items():
         _compare(ix, hx, reads)
+    hx.close()
+
+
+def _assert_constructed_walks(ix, reads):
+    """The constructed reads take the branches they were built for (asserted on the oracle's walk)."""
+    d = {name: cases.describe_walk(ix, r) for name, r in reads.items()}
+    q1 = d["quirk1_offset0_left_walk"]
+    assert q1["first_seed"][0] == 30 and q1["first_seed"][2] == 0 and q1["left_steps"] >= 1      # QUIRK-1: seed at unitig offset 0, left walk
+    assert d["left_walk_offset2"]["first_seed"][0] == 30 and d["left_walk_offset2"]["left_steps"] >= 2   # QUIRK-3: >= 2 predecessors
+    assert d["left_to_read_start"]["first_seed"][0] == 30 and d["left_to_read_start"]["left_steps"] == 0
+    assert d["left_to_read_start"]["result"][1] == 150                      # every base covered: the walk reached the read's start
+    assert d["two_errors_per_node"]["result"][1] == 150 and len(d["two_errors_per_node"]["nodes"]) >= 3   # QUIRK-2
+    assert d["reseed_into_visited_node"]["revisits"] >= 1                   # QUIRK-5 + re-seed into a visited node
+    assert d["break_near_end"]["result"][1] < 150 and d["break_near_end"]["revisits"] == 0
+    assert d["ends_at_unitig_end"]["result"][1] == 150
+    assert d["no_right_ext"]["result"][1] == 100
+    return d
+
+
+def test_constructed_branches(hs):
+    """QUIRK-1 (seed at unitig offset 0 + left extension, ref :129), QUIRK-3 (left walk over >= 2 predecessors,
+    ref :199), QUIRK-2 (per-node budget), re-seed into a visited node (ref :293), break near the read's end
+    (ref :287-290), read ending at a unitig end, missing right extension: constructed reads on a constructed
+    graph, the branch asserted on the oracle's walk, then blocking form and lane state machine against the oracle."""
+    S, seqs = cases.constructed_transcriptome()
+    ix = orc.OrcIndex.build(seqs, 20)
+    reads = cases.constructed_reads(S)
+    _assert_constructed_walks(ix, reads)
+    hx = HsIndex(hs, ix.flat())
+    _compare(ix, hx, [r.decode() for r in reads.values()])
+    hx.close()
+
+
+@pytest.mark.parametrize("allowed", [0, 1, 3, 7])
+def test_allowed_mismatches(hs, orc_index_for, fixture_fasta, allowed):
+    """map_read_with_mismatch (ref :361) with allowed_mismatches other than the default 2."""
+    ix = orc_index_for(20)
+    hx = HsIndex(hs, ix.flat())
+    rng = np.random.default_rng(40 + allowed)
+    reads = util.sample_reads(rng, fixture_fasta[1], 1500, 150, p_sub=0.03, mix=(0.9, 0.1, 0.0))
+    reads += cases.left_extension_reads(rng, fixture_fasta[1], 300, 150, 20)
+    res = _compare(ix, hx, reads, allowed=allowed)
+    words, off, lens = orc.pack_reads(reads)
+    base = ix.map_batch(words, off, lens)[0]                        # A = 2: the answers must actually depend on A
+    h = ix.map_batch(words, off, lens, allowed=allowed)[0]
+    assert not np.array_equal(h["coverage"], base["coverage"])
+    assert len(res) == len(reads)
     hx.close()

@@ -75,3 +75,28 @@ def test_sharded_counts_equal_single_process(tmp_path, orc_index_for, fixture_fa
     assert np.array_equal(got["counts"], want_counts)
     assert orc.hits_to_tuples(got["hits"], got["tx"]) == orc.hits_to_tuples(want_hits, want_tx)
     assert np.array_equal(got["hits"]["tx_off"], want_hits["tx_off"])
+
+
+def test_novel_set_tables_merge_like_one_table():
+    """psa_novel_sets_merge (host code of libpsa_b200.so): per-rank tables of novel sets merge into the table a
+    single rank would have built -- equal sets once, counts added, order by (length, contents), whatever the split."""
+    import importlib
+    import numpy as np
+    psa = importlib.import_module("rust-pseudoaligner_b200").pseudoaligner
+    rng = np.random.default_rng(3)
+    universe = [tuple(sorted(set(rng.integers(0, 50, int(rng.integers(0, 6))).tolist()))) for _ in range(200)]
+    draws = [universe[int(i)] for i in rng.integers(0, len(universe), 5000)]
+
+    def table(sample):
+        t = {}
+        for s in sample:
+            t[s] = t.get(s, 0) + 1
+        return sorted(t.items(), key=lambda kv: (len(kv[0]), kv[0]))
+
+    whole = table(draws)
+    for world in (1, 2, 3, 8):
+        parts = [table(draws[r::world]) for r in range(world)]
+        assert psa.novel_sets_merge(parts) == whole
+    assert psa.novel_sets_merge([]) == [] and psa.novel_sets_merge([[], []]) == []
+    ids = {m: i for i, (m, _) in enumerate(whole)}
+    assert ids[()] == 0 and all(len(whole[i][0]) <= len(whole[i + 1][0]) for i in range(len(whole) - 1))
