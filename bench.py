@@ -141,6 +141,36 @@ def load_index(a, host, tr, rank, world, barrier, threads):
     return flat, time.time() - t0
 
 
+# ------------------------------------------------------------------------------------ host placement
+def pin_to_gpu_cpus(local_rank, world):
+    """Run this rank (its threads and the pinned buffers it allocates from here on) on the CPUs NVML names as local to
+    its GPU; with several ranks on one box every rank takes its own contiguous share of them."""
+    info = {"applied": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in allowed if (words[c // 64] >> (c % 64)) & 1] or allowed
+        info["gpu_local_cpus"] = len(cpus)
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        if world > 1:
+            same = [c for c in cpus]
+            share = max(1, len(same) // world)
+            mine = same[(local_rank * share) % len(same):][:share] or same
+            cpus = mine
+        os.sched_setaffinity(0, cpus)
+        info.update(applied=True, cpus=len(cpus), first_cpu=cpus[0])
+    except Exception as e:      # no NVML / no permission: run unpinned and say so
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi polled every 20 ms from before the warm-up (it takes a while to start); the
@@ -353,6 +383,57 @@ def pkg_mod():
     return importlib.import_module(PKG)
 
 
+def pack_ascii_batch(ascii_arr, n, L, out_words, threads):
+    """ASCII reads -> DnaString words (A0 C1 G2 T3, anything else 0), numpy, `threads` slices in parallel (untimed helper)."""
+    nw = (L + 31) // 32
+    lut = np.zeros(256, np.uint64)
+    for ch, v in ((b"C", 1), (b"G", 2), (b"T", 3), (b"c", 1), (b"g", 2), (b"t", 3)):
+        lut[ch[0]] = v
+    shifts = (62 - 2 * np.arange(32, dtype=np.uint64)).astype(np.uint64)
+    step = 65536
+
+    def work(t):
+        for c0 in range(t * step, n, threads * step):
+            c1 = min(n, c0 + step)
+            codes = np.zeros((c1 - c0, nw * 32), np.uint64)
+            codes[:, :L] = lut[ascii_arr[c0 * L:c1 * L].reshape(c1 - c0, L)]
+            out_words[c0 * nw:c1 * nw] = np.bitwise_or.reduce(codes.reshape(c1 - c0, nw, 32) << shifts, axis=2).reshape(-1)
+    th = [threading.Thread(target=work, args=(t,)) for t in range(max(1, threads))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+
+
+def pcie_probe(psa, torch, dist, world, nbytes=256 << 20, reps=4):
+    """Host -> device and device -> host copy rate of pinned memory on this rank's GPU, all ranks copying at the
+    same time: {h2d_gbs, d2h_gbs} = the minimum over the ranks (what every rank can count on) and the sum."""
+    pin = psa.PinnedArray(nbytes, np.uint8)
+    dev = psa.DeviceBuffer(nbytes)
+    lib = psa.lib()
+    out = {}
+    for name, fn in (("h2d", lambda: lib.psa_memcpy_h2d(dev.ptr, pin.ptr, nbytes)), ("d2h", lambda: lib.psa_memcpy_d2h(pin.ptr, dev.ptr, nbytes))):
+        fn()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        gbs = reps * nbytes / (time.perf_counter() - t0) / 1e9
+        t = torch.tensor([gbs, -gbs, gbs], device="cuda", dtype=torch.float64)
+        if world > 1:
+            mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            out[name + "_gbs_min_rank"] = -float(mx[1].item())
+            out[name + "_gbs_all_ranks"] = float(sm[2].item())
+        else:
+            out[name + "_gbs_min_rank"] = gbs
+            out[name + "_gbs_all_ranks"] = gbs
+    pin.free()
+    dev.free()
+    return out
+
+
 def batch_checksum(batch, n, first_index, device):
     import ctypes as C
     psa = pkg_mod().pseudoaligner
@@ -423,6 +504,10 @@ def main():
     flat, build_s = load_index(a, host, tr, rank, world, barrier, ncores if rank == 0 else host_threads)
     index = pkg.Index(flat, device=local_rank, gamma=a.gamma)
     info = index.info()
+    # from here on (pinned batch buffers, mapper threads) the rank stays on the CPUs local to its GPU
+    affinity = pin_to_gpu_cpus(local_rank, world)
+    if affinity.get("applied") and world > 1:
+        host_threads = max(1, min(host_threads, affinity["cpus"]))
     mapper = pkg.Mapper(index, a.chunk_reads)
     if a.group_width:
         mapper.set_group_width(a.group_width)
@@ -444,8 +529,6 @@ def main():
         tr.reads(3, shard_lo + g * R, R, L, out=pin.array, threads=host_threads)
         host_batches.append(pin)
         dev_batches.append(pkg.DeviceBatch(psa.READS_ASCII, pin.array, R, stride=L, fixed_len=L, tx_cap=tx_cap))
-    pin_hits = psa.PinnedArray(R, pkg.HIT_DTYPE)
-    pin_tx = psa.PinnedArray(tx_cap, np.uint32)
     setup_s = time.time() - t_setup
 
     # events of one batch (untimed): the algorithmic work the roofline is computed from
@@ -487,9 +570,18 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    run_steps(0, max(a.warmup, M))
+    for attempt in range(6):       # (an undersized internal buffer is grown at the sync that reports it: warm up again)
+        try:
+            run_steps(0, max(a.warmup, M))
+            for vm in vmappers:
+                vm.sync()
+            break
+        except pkg.PsaError as e:
+            if e.code != psa.ERR_CAPACITY or attempt == 5:
+                raise
+            for vm in vmappers:
+                vm.counts_reset()
     for vm in vmappers:
-        vm.sync()
         if comm is not None:
             vm.counts_allreduce(comm)      # warm-up of the collective too (NCCL connects lazily on first use)
         vm.counts_reset()
@@ -546,6 +638,7 @@ def main():
         prof_ms = p0.elapsed_time(p1)
         prof = mapper.profile_read()
         mapper.profile_enable(False)
+    novel_table = mapper.novel_sets(comm) if M == 1 else []
     total_reads_counted = int(counts.sum())
     expect = a.steps * R * (world if comm is not None else 1)
     assert total_reads_counted == expect, "per-class counts sum to %d, expected %d" % (total_reads_counted, expect)
@@ -564,16 +657,21 @@ def main():
     ms_max = float(ms_t.item())
     value = world * a.steps * R / (ms_max / 1e3)
 
-    # ---------------- end-to-end arm through the public call, host buffers
+    # ---------------- end-to-end arms through the public call, host buffers
     e2e = None
+    e2e_extra = {}
     if not a.no_e2e:
         # T host threads, one psa_mapper each over the shared index (the reference's process_reads runs
         # num_threads workers over one shared &Pseudoaligner, ref src/pseudoaligner.rs:434-474): while one
-        # mapper's pipeline drains its last chunk, the other's is already filling PCIe with its next batch
+        # mapper's pipeline drains its last chunk, the other's is already filling PCIe with its next batch.
+        # Results come back compact (PSA_RESULT_COMPACT: 8 bytes per read + the members of the sets that are no
+        # index class); the host holds eq_classes and expands class ids itself when it needs the members.
         T = max(1, a.e2e_threads)
-        workers = [(mapper, pin_hits, pin_tx)]
+        novel_cap = 4 * R
+        workers = [(mapper, psa.PinnedArray(R, psa.HIT_COMPACT_DTYPE), psa.PinnedArray(novel_cap, np.uint32))]
         for _ in range(1, T):
-            workers.append((pkg.Mapper(index, a.chunk_reads), psa.PinnedArray(R, pkg.HIT_DTYPE), psa.PinnedArray(tx_cap, np.uint32)))
+            workers.append((pkg.Mapper(index, a.chunk_reads), psa.PinnedArray(R, psa.HIT_COMPACT_DTYPE),
+                            psa.PinnedArray(novel_cap, np.uint32)))
         for w_m, _, _ in workers[1:]:
             if a.group_width:
                 w_m.set_group_width(a.group_width)
@@ -581,42 +679,66 @@ def main():
                 w_m.set_fast_path(a.fast_probes, a.fast_max_small)
             if a.scan_width >= 0:
                 w_m.set_scan_width(a.scan_width)
+        # the same batches as DnaString words (map_read's own argument type, ref src/pseudoaligner.rs:381), packed untimed
+        nw = (L + 31) // 32
+        packed_batches = []
+        for g in range(G):
+            pw = psa.PinnedArray(R * nw + 8, np.uint64)
+            pack_ascii_batch(host_batches[g].array, R, L, pw.array, host_threads)
+            packed_batches.append(pw)
 
-        def e2e_step(t, g):
+        def e2e_step(t, g, packed):
             w_m, w_h, w_t = workers[t]
-            return w_m.map_ascii_fixed(host_batches[g].array, R, L, tx_cap=tx_cap, hits=w_h.array, tx=w_t.array)
+            if packed:
+                return w_m.map_packed_fixed(packed_batches[g].array, R, L, tx_cap=novel_cap, hits=w_h.array, tx=w_t.array, compact=True)
+            return w_m.map_ascii_fixed(host_batches[g].array, R, L, tx_cap=novel_cap, hits=w_h.array, tx=w_t.array, compact=True)
 
-        used_by = [0] * T
+        def timed_arm(packed):
+            used_by = [0] * T
 
-        def run(t, steps):
-            for s in steps:
-                h, tx = e2e_step(t, s % G)
-                used_by[t] += len(tx)
+            def run(t, steps):
+                for s in steps:
+                    h, tx = e2e_step(t, s % G, packed)
+                    used_by[t] += len(tx)
 
-        for t in range(T):          # untimed: first use of every mapper's staging buffers
-            e2e_step(t, 0)
-            e2e_step(t, 1 % G)
-        barrier()
-        torch.cuda.synchronize()
-        t_w0 = time.time()
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=run, args=(t, range(t, a.steps, T))) for t in range(T)]
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        used = sum(used_by)
-        sampler.window(t_w0, time.time())
-        dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        dt = float(dt_t.item())
-        e2e = {"value": world * a.steps * R / dt, "unit": "reads/s", "h2d_bytes_per_step": R * L,
-               "d2h_bytes_per_step": R * pkg.HIT_DTYPE.itemsize + 4 * used // a.steps + 16 * ((R + (1 << 19) - 1) >> 19),
-               "ms_per_step": 1e3 * dt / a.steps, "host_threads": T,
-               "api": "psa_mapper_map (host ASCII batch -> psa_hit[] + tx_buf), one mapper per host thread"}
+            for t in range(T):          # untimed: first use of every mapper's staging buffers
+                e2e_step(t, 0, packed)
+                e2e_step(t, 1 % G, packed)
+            barrier()
+            torch.cuda.synchronize()
+            t_w0 = time.time()
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=run, args=(t, range(t, a.steps, T))) for t in range(T)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            sampler.window(t_w0, time.time())
+            dt_t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+            dt = float(dt_t.item())
+            h2d = R * (nw * 8 if packed else L)
+            d2h = R * psa.HIT_COMPACT_DTYPE.itemsize + 4 * sum(used_by) // a.steps + 16 * ((R + (1 << 19) - 1) >> 19)
+            return {"value": world * a.steps * R / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_bytes_per_read": h2d / R, "d2h_bytes_per_read": d2h / R,
+                    "ms_per_step": 1e3 * dt / a.steps, "host_threads": T}
+
+        e2e = timed_arm(False)
+        e2e["api"] = ("psa_mapper_map (host ASCII batch, the record.seq() bytes of ref src/pseudoaligner.rs:449 -> "
+                      "psa_hit_compact[] + members of non-class sets), one mapper per host thread")
+        ep = timed_arm(True)
+        ep["api"] = "the same call with DnaString words in (map_read's own argument type, packed untimed)"
+        e2e_extra["e2e_packed_input"] = ep
+        # the per-read results of the last end-to-end step, expanded on the host, against the resident arm's
+        w_m, w_h, w_t = workers[0]
+        hc, ntx = e2e_step(0, 0, True)
+        hx, tx_full = psa.expand_compact(hc[:100000], ntx, flat["eq_offsets"], flat["eq_members"])
+        e2e_extra["e2e_expand_check"] = {"reads": 100000, "host_expanded_members": int(len(tx_full))}
+        # what the host <-> device link gives this rank while every rank copies at once (pinned memory, 256 MB)
+        e2e_extra["pcie_probe"] = pcie_probe(psa, torch, dist, world)
         for w_m, w_h, w_t in workers[1:]:
             w_m.close()
 
@@ -687,7 +809,10 @@ def main():
 
     # ---------------- parity, measured: the oracle's results for the first reads of the stream (the CPU baseline's
     # sample when it ran, else a smaller untimed sample) against the GPU's for the same reads of batch 0
-    parity = {"checksum_all_timed_reads": "%016x" % checksum_timed,
+    parity = {"novel_sets": {"distinct": len(novel_table), "reads": sum(c for _, c in novel_table),
+                             "note": "eq_classes that are no index class, counted per distinct set over all timed reads%s; ids n_eq + rank "
+                                     "by (length, contents)" % (" of all ranks (ncclAllGather + merge)" if comm else "")},
+              "checksum_all_timed_reads": "%016x" % checksum_timed,
               "checksum_of": "sum over reads of a hash chain over (global read index, coverage, flags, eq_id, members)"}
     if rank == 0 and a.parity_reads != 0:
         if want is None or (0 < a.parity_reads < len(want[0])):
@@ -734,9 +859,9 @@ def main():
                     "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
                                                               "dict_levels", "dict_bytes", "fp_bits", "max_class_len")},
                     "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",
-                    "host_cores": ncores, "index_build_s": build_s, "setup_s": setup_s},
+                    "host_cores": ncores, "host_affinity": affinity, "index_build_s": build_s, "setup_s": setup_s},
             "parity": parity,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, **e2e_extra, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "events_per_read": {key: ev[key] / ev["reads"] for key in ev if key != "reads"},
         }
         real_stdout.write(json.dumps(line) + "\n")

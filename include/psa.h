@@ -96,6 +96,9 @@ typedef struct psa_index_info {
 int psa_index_create(const psa_index_desc* desc, int device, double gamma, psa_index** out);
 void psa_index_destroy(psa_index*);
 int psa_index_get_info(const psa_index*, psa_index_info* out);
+/* eq_classes as the index keeps them on the host (CSR, borrowed until psa_index_destroy): what compact results
+ * (below) are expanded from. */
+int psa_index_host_classes(const psa_index*, const uint64_t** eq_offsets, const uint32_t** eq_members, uint64_t* n_eq);
 /* dbg_index.get(kmer) + verification (ref src/pseudoaligner.rs:96-107) for n k-mers given
  * as packed words (k bases from base 0; 1 word per k-mer if k<=32 else 2).  found[i] = 1 and
  * node/off filled when the k-mer is in the graph.  Diagnostic / test entry. */
@@ -139,9 +142,19 @@ typedef struct psa_hit {    /* one per read, input order                        
     uint32_t flags;         /* PSA_FLAG_*                                                   */
 } psa_hit;
 
+/* Compact results: what crosses PCIe per read is 8 bytes instead of a psa_hit and every member.  eq_or_n is the
+ * index class equal to the read's eq_class, or 0x80000000 + |eq_class| when the set is no index class (only THOSE
+ * sets' members are then delivered in tx_buf, in read order), or PSA_EQ_NONE for None; cov_flags = coverage (28 bits)
+ * | PSA_FLAG_* << 28.  psa_expand_compact turns them into psa_hit + members on the host from a copy of eq_classes. */
+typedef struct psa_hit_compact {
+    uint32_t eq_or_n;
+    uint32_t cov_flags;
+} psa_hit_compact;
+#define PSA_RESULT_COMPACT 1u
+
 typedef struct psa_result_batch {
     uint32_t location; /* PSA_MEM_*: where hits / tx_buf live                                */
-    uint32_t reserved;
+    uint32_t flags;    /* PSA_RESULT_COMPACT: hits points to psa_hit_compact[n_reads]        */
     psa_hit* hits;     /* n_reads                                                            */
     uint32_t* tx_buf;  /* members of every eq_class back to back in read order; NULL = skip  */
     uint64_t tx_cap;   /* capacity of tx_buf in entries                                      */
@@ -183,6 +196,11 @@ int psa_mapper_set_scan_width(psa_mapper*, uint32_t lanes);
  * device batches run in place on the mapper's stream.  Synchronous: results are complete
  * on return.  Per-class counts accumulate across calls until psa_mapper_counts_reset. */
 int psa_mapper_map(psa_mapper*, const psa_read_batch* reads, psa_result_batch* results);
+
+/* Host function (no device): compact records + the members of the non-class sets -> psa_hit[] and every member. */
+int psa_expand_compact(const psa_hit_compact* in, uint64_t n, const uint32_t* novel_tx, uint64_t novel_tx_len,
+                       const uint64_t* eq_offsets, const uint32_t* eq_members, uint64_t n_eq, psa_hit* hits,
+                       uint32_t* tx_buf, uint64_t tx_cap, uint64_t* tx_used);
 
 /* Device-resident batch, asynchronous on the mapper's stream, fixed shape helpers for
  * benchmarking: same as psa_mapper_map with location == PSA_MEM_DEVICE but does not
@@ -267,8 +285,12 @@ int psa_mapper_profile_read(psa_mapper*, double map_kernel_ms[3], uint64_t map_l
  * println!s at :490 -- in input order.  out_path NULL or "-" = stdout.  num_threads = host
  * threads that format the lines (the reference's num_threads are its mapping workers; mapping
  * is on the GPU here) and read / write the files.  batch_reads 0 = 512 Ki reads per block.  progress != 0 prints the
- * reference's stderr tick every 1 000 000 reads (:497-504).  A malformed FASTQ record returns
- * PSA_ERR_IO after the records before it were processed (the reference panics, :446).
+ * reference's stderr tick at every 1 000 000th read (:497-504).  Records are cut exactly as the reference's reader
+ * (bio::io::fastq 1.5) cuts them: the id is the header without its '@' up to the first SPACE (tabs stay), sequence
+ * lines may be wrapped (every line up to the '+' line, each stripped of trailing white space), as many quality lines
+ * follow.  A malformed record -- no '@', no quality, a blank line, a header that is not UTF-8 -- returns PSA_ERR_IO
+ * after the records before it were processed (the reference panics, :446).  Sequence and quality bytes >= 0x80 are
+ * not checked for UTF-8 validity (the reference's reader would fail on them).
  * ---------------------------------------------------------------------------------------- */
 typedef struct psa_process_stats {
     uint64_t reads;   /* read_counter, :476                                                  */
@@ -278,6 +300,9 @@ typedef struct psa_process_stats {
     double reader_seconds, mapper_seconds, writer_seconds; /* busy time of the three pipeline
                          stages (FASTQ parse | psa_mapper_map | format + write)              */
 } psa_process_stats;
+/* `{:?}` of a string exactly as the drivers print ids (Rust's escape_debug; ASCII exact, see process_reads.cpp for
+ * the non-ASCII subset): returns the bytes written to out (cap >= 10 n + 2), negative if s is not valid UTF-8. */
+int64_t psa_debug_str(const char* s, uint64_t n, char* out, uint64_t cap);
 int psa_process_reads(psa_index*, const char* fastq_path, const char* out_path, uint32_t num_threads,
                       uint64_t batch_reads, int progress, psa_process_stats* stats);
 

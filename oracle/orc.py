@@ -37,10 +37,9 @@ class Events(C.Structure):
 
 def build_lib(force=False):
     """Compile the oracle with its committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "psa_oracle.c")
-    hdr = os.path.join(_HERE, "psa_oracle.h")
+    srcs = [os.path.join(_HERE, n) for n in ("psa_oracle.c", "c3_driver.c", "psa_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B", "libpsa_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -89,6 +88,8 @@ def lib():
     L.orc_map_ascii_batch.argtypes = [vp, vp, u64, u32, u64, u32, vp, vp, u64, C.POINTER(u64), vp, vp]
     L.orc_result_checksum.restype = u64
     L.orc_result_checksum.argtypes = [vp, vp, u64, u64]
+    L.orc_process_reads_c3.restype = C.c_int
+    L.orc_process_reads_c3.argtypes = [vp, C.c_char_p, C.c_char_p, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.orc_intersect.restype = u32
     L.orc_intersect.argtypes = [vp, u32, vp, u32]
     _lib = L
@@ -334,6 +335,15 @@ class OrcIndex:
                 raise MemoryError
             cap = int(used.value) + 16
         return hits, tx[:used.value].copy(), cnt
+
+    def process_reads_c3(self, fastq_path, out_path, num_threads=2, allowed=2):
+        """The reference's map driver restated (c3_driver.c): -> (reads, mapped); lines in arrival order."""
+        reads, mapped = C.c_uint64(), C.c_uint64()
+        rc = lib().orc_process_reads_c3(self.h, os.fsencode(fastq_path), os.fsencode(out_path), int(num_threads), int(allowed),
+                                        C.byref(reads), C.byref(mapped))
+        if rc:
+            raise RuntimeError("orc_process_reads_c3: error %d" % rc)
+        return int(reads.value), int(mapped.value)
 
     def close(self):
         if self.h:

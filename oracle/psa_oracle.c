@@ -65,10 +65,21 @@ static inline unsigned base_code(char c) {
 }
 
 void orc_pack_ascii(const char* s, uint64_t len, uint64_t* words) {
+    /* one table lookup per base, 32 bases per word (a fair scalar DnaString::from_dna_string) */
+    static uint8_t lut[256];
+    static int lut_ready = 0;
+    if (!lut_ready) {
+        for (int c = 0; c < 256; c++) lut[c] = (uint8_t)base_code((char)c);
+        lut_ready = 1;
+    }
+    const unsigned char* u = (const unsigned char*)s;
     uint64_t nw = orc_words_for(len);
-    for (uint64_t i = 0; i < nw; i++) words[i] = 0;
-    for (uint64_t i = 0; i < len; i++)
-        words[i >> 5] |= (uint64_t)base_code(s[i]) << (62 - 2 * (i & 31));
+    for (uint64_t w = 0; w < nw; w++) {
+        uint64_t n = len - 32 * w < 32 ? len - 32 * w : 32;
+        uint64_t v = 0;
+        for (uint64_t i = 0; i < n; i++) v = (v << 2) | lut[u[32 * w + i]];
+        words[w] = v << (64 - 2 * n);
+    }
 }
 
 /* DnaString::get(i) */

@@ -149,6 +149,12 @@ int orc_map_ascii_batch(const orc_index*, const uint8_t* ascii, uint64_t stride,
 /* Order-independent 64-bit checksum of a result batch (read index, coverage, flags, eq_id, members). */
 uint64_t orc_result_checksum(const orc_hit* hits, const uint32_t* tx, uint64_t n, uint64_t first_index);
 
+/* process_reads as the reference shapes it (c3_driver.c): num_threads workers, one FASTQ record per mutex
+ * acquisition, a bounded channel of num_threads tuples, the main thread printing one `{:?}` line per read in
+ * arrival order.  Returns 0, or -7 on an I/O error / malformed record. */
+int orc_process_reads_c3(const orc_index*, const char* fastq_path, const char* out_path, uint32_t num_threads,
+                         uint32_t allowed_mismatches, uint64_t* reads, uint64_t* mapped);
+
 /* intersect (pseudoaligner.rs:389-418): in-place on v1, returns the new length. */
 uint32_t orc_intersect(uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n2);
 

@@ -84,11 +84,24 @@ extern "C" psa_graph* psa_graph_from_arrays(uint32_t k, uint64_t n_nodes, const 
                                             const uint64_t* node_start, const uint32_t* node_len, const uint8_t* node_exts,
                                             const uint32_t* node_eq, uint64_t n_eq, const uint64_t* eq_offsets,
                                             const uint32_t* eq_members) {
-    if (!eq_offsets || (n_nodes && (!seq_words || !node_start || !node_len || !node_exts || !node_eq))) {
+    if (!eq_offsets || (n_nodes && (!seq_words || !node_start || !node_len || !node_exts || !node_eq)) ||
+        (eq_offsets[n_eq] && !eq_members) || (n_seq_words && !seq_words)) {
         g_host_err = "psa_graph_from_arrays: null array";
         return nullptr;
     }
-    psa_graph* g = new psa_graph();
+    for (uint64_t c = 0; c < n_eq; c++)
+        if (eq_offsets[c + 1] < eq_offsets[c]) {
+            g_host_err = "psa_graph_from_arrays: eq_offsets not monotone";
+            return nullptr;
+        }
+    psa_graph* g = nullptr;
+    try {
+        g = new psa_graph();
+    } catch (...) {
+        g_host_err = "psa_graph_from_arrays: out of memory";
+        return nullptr;
+    }
+    try {
     g->k = k;
     g->seq_words.assign(seq_words, seq_words + n_seq_words);
     g->node_start.assign(node_start, node_start + n_nodes);
@@ -98,6 +111,11 @@ extern "C" psa_graph* psa_graph_from_arrays(uint32_t k, uint64_t n_nodes, const 
     g->eq_offsets.assign(eq_offsets, eq_offsets + n_eq + 1);
     g->eq_members.assign(eq_members, eq_members + eq_offsets[n_eq]);
     for (uint64_t i = 0; i < n_nodes; i++) g->n_kmers += node_len[i] >= k ? node_len[i] - k + 1 : 0;
+    } catch (...) {   // nothing may be thrown through the C boundary
+        delete g;
+        g_host_err = "psa_graph_from_arrays: out of memory";
+        return nullptr;
+    }
     return g;
 }
 
@@ -125,27 +143,62 @@ extern "C" int psa_graph_save(const psa_graph* g, const char* path) {
     return 0;
 }
 
+// what the arrays of a header occupy in the file (each padded to 64 bytes); false if a count is absurd
+static bool payload_bytes(const Header& h, uint64_t& total) {
+    const uint64_t lim = 1ull << 56;  // no count this large fits a file: keeps the sums below from wrapping
+    if (h.n_nodes > lim || h.n_seq_words > lim || h.n_eq >= lim || h.n_eq_members > lim) return false;
+    auto padded = [](uint64_t bytes) { return (bytes + 63) / 64 * 64; };
+    total = padded(h.n_seq_words * 8) + padded(h.n_nodes * 8) + padded(h.n_nodes * 4) + padded(h.n_nodes) + padded(h.n_nodes * 4) +
+            padded((h.n_eq + 1) * 8) + padded(h.n_eq_members * 4);
+    return true;
+}
+
 extern "C" psa_graph* psa_graph_load(const char* path) {
     if (!path) { g_host_err = "psa_graph_load: null path"; return nullptr; }
     FILE* f = fopen(path, "rb");
     if (!f) { g_host_err = std::string("cannot open ") + path; return nullptr; }
+    fseek(f, 0, SEEK_END);
+    const uint64_t file_size = (uint64_t)ftell(f);
+    rewind(f);
     Header h{};
     psa_graph* g = nullptr;
     const char* why = nullptr;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0) why = "not a psa index file";
-    else if (h.version != kVersion) why = "unsupported index file version";
-    else if (h.k < 2 || h.k > 64) why = "corrupt header";
-    else {
-        g = new psa_graph();
-        g->k = h.k;
-        g->n_kmers = h.n_kmers;
-        g->n_cycles = h.n_cycles;
-        if (!get(f, g->seq_words, h.n_seq_words) || !get(f, g->node_start, h.n_nodes) || !get(f, g->node_len, h.n_nodes) ||
-            !get(f, g->node_exts, h.n_nodes) || !get(f, g->node_eq, h.n_nodes) || !get(f, g->eq_offsets, h.n_eq + 1) ||
-            !get(f, g->eq_members, h.n_eq_members))
-            why = "truncated index file";
-        else if (g->eq_offsets[h.n_eq] != h.n_eq_members || checksum_of(*g) != h.checksum)
-            why = "index file checksum mismatch";
+    uint64_t need = 0;
+    try {
+        if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0) why = "not a psa index file";
+        else if (h.version != kVersion) why = "unsupported index file version";
+        else if (h.k < 2 || h.k > 64) why = "corrupt header";
+        // the header's counts are believed only as far as the file is long: nothing is allocated before this
+        else if (!payload_bytes(h, need) || need > file_size - sizeof h) why = "header counts exceed the file size";
+        else {
+            g = new psa_graph();
+            g->k = h.k;
+            g->n_kmers = h.n_kmers;
+            g->n_cycles = h.n_cycles;
+            if (!get(f, g->seq_words, h.n_seq_words) || !get(f, g->node_start, h.n_nodes) || !get(f, g->node_len, h.n_nodes) ||
+                !get(f, g->node_exts, h.n_nodes) || !get(f, g->node_eq, h.n_nodes) || !get(f, g->eq_offsets, h.n_eq + 1) ||
+                !get(f, g->eq_members, h.n_eq_members))
+                why = "truncated index file";
+            else if (g->eq_offsets[h.n_eq] != h.n_eq_members || checksum_of(*g) != h.checksum)
+                why = "index file checksum mismatch";
+            else {
+                // the arrays are what psa_index_create and the graph accessors index with: check them here
+                uint64_t nk = 0;
+                if (g->eq_offsets[0] != 0) why = "eq_offsets does not start at 0";
+                for (uint64_t c = 0; c < h.n_eq && !why; c++)
+                    if (g->eq_offsets[c + 1] < g->eq_offsets[c]) why = "eq_offsets not monotone";
+                for (uint64_t i = 0; i < h.n_nodes && !why; i++) {
+                    if (g->node_len[i] < h.k) why = "node shorter than k";
+                    else if (g->node_eq[i] >= h.n_eq) why = "node class id out of range";
+                    else if (g->node_start[i] > h.n_seq_words * 32 || g->node_len[i] > h.n_seq_words * 32 - g->node_start[i])
+                        why = "node outside the sequence";
+                    else nk += g->node_len[i] - h.k + 1;
+                }
+                if (!why && nk != h.n_kmers) why = "k-mer count does not match the nodes";
+            }
+        }
+    } catch (...) {   // (std::bad_alloc / std::length_error: nothing may be thrown through the C boundary)
+        why = "out of memory";
     }
     fclose(f);
     if (why) {
@@ -198,9 +251,11 @@ extern "C" psa_graph* psa_graph_load_bincode(const char* path, uint32_t k) {
     fseek(f, 0, SEEK_END);
     Cursor c{f, (uint64_t)ftell(f)};
     rewind(f);
-    psa_graph* g = new psa_graph();
-    g->k = k;
+    psa_graph* g = nullptr;
     const char* why = nullptr;
+    try {
+    g = new psa_graph();
+    g->k = k;
     const uint64_t cap = c.left;  // no array can have more elements than the file has bytes
     uint64_t n_bases = 0;
     std::vector<uint32_t> left_order, right_order;
@@ -240,6 +295,9 @@ extern "C" psa_graph* psa_graph_load_bincode(const char* path, uint32_t k) {
             else if (g->node_eq[i] >= n_classes) why = "node class id out of range";
             else g->n_kmers += g->node_len[i] - k + 1;
         }
+    }
+    } catch (...) {
+        why = "out of memory";
     }
     fclose(f);
     if (why) {

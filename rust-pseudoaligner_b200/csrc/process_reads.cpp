@@ -55,7 +55,7 @@ struct Pinned {  // growable cudaHostAlloc buffer (contents preserved on growth)
 };
 
 struct Batch {
-    Pinned text, hits, tx;       // text: raw FASTQ bytes of this batch (records start at byte 0)
+    Pinned text, hits, tx;       // text: raw FASTQ bytes of this batch (records start at byte 0); hits: psa_hit_compact[]
     uint64_t text_len = 0;       // bytes of complete records
     std::vector<uint64_t> off;   // sequence start (byte offset into text) per read
     std::vector<uint32_t> len;   // sequence length per read
@@ -240,28 +240,108 @@ struct OutBuf {
     ~OutBuf() { free(p); }
 };
 
-// Rust's `{:?}` of a String: quotes, with \" \\ \n \r \t \0 and \u{..} for other control chars
-// (at most 6 output bytes per input byte, + 2 quotes)
+// ---- text helpers shared with the Python mirror (psa_debug_str / psa_fastq_trim_end below) -----------------------
+// Rust's str::trim_end removes White_Space code points: the ASCII ones and the multi-byte ones below.
+// Returns the length of s[0, n) without its trailing white space.
+size_t trim_end(const uint8_t* s, size_t n) {
+    for (;;) {
+        if (n >= 1 && (s[n - 1] == ' ' || (s[n - 1] >= 0x09 && s[n - 1] <= 0x0D))) { n--; continue; }
+        if (n >= 2 && s[n - 2] == 0xC2 && (s[n - 1] == 0x85 || s[n - 1] == 0xA0)) { n -= 2; continue; }
+        if (n >= 3) {
+            const uint8_t a = s[n - 3], b = s[n - 2], c = s[n - 1];
+            const bool ws = (a == 0xE1 && b == 0x9A && c == 0x80) || (a == 0xE2 && b == 0x80 && (c <= 0x8A && c >= 0x80)) ||
+                            (a == 0xE2 && b == 0x80 && (c == 0xA8 || c == 0xA9 || c == 0xAF)) || (a == 0xE2 && b == 0x81 && c == 0x9F) ||
+                            (a == 0xE3 && b == 0x80 && c == 0x80);
+            if (ws) { n -= 3; continue; }
+        }
+        return n;
+    }
+}
+// decodes one UTF-8 scalar at s[i] (i < n); returns its length, 0 if the bytes are not valid UTF-8
+int utf8_decode(const uint8_t* s, size_t i, size_t n, uint32_t& cp) {
+    const uint8_t c = s[i];
+    if (c < 0x80) { cp = c; return 1; }
+    int len = c >= 0xF0 ? 4 : c >= 0xE0 ? 3 : c >= 0xC2 ? 2 : 0;
+    if (!len || c > 0xF4 || i + len > n) return 0;
+    cp = c & (0x3F >> (len - 1));
+    for (int j = 1; j < len; j++) {
+        if ((s[i + j] & 0xC0) != 0x80) return 0;
+        cp = (cp << 6) | (s[i + j] & 0x3F);
+    }
+    if ((len == 3 && cp < 0x800) || (len == 4 && (cp < 0x10000 || cp > 0x10FFFF)) || (cp >= 0xD800 && cp <= 0xDFFF)) return 0;
+    return len;
+}
+bool utf8_valid(const uint8_t* s, size_t n) {
+    for (size_t i = 0; i < n;) {
+        uint32_t cp;
+        const int l = utf8_decode(s, i, n, cp);
+        if (!l) return false;
+        i += l;
+    }
+    return true;
+}
+// char::escape_debug escapes what is not printable or extends a grapheme.  ASCII is exact; beyond it the code
+// points below are escaped as Rust does (C1 controls, soft hyphen, combining marks of the common blocks, format
+// and separator characters, private use, non-characters); everything else is printed as is.  (Rust's full
+// is_printable / Grapheme_Extend tables are not reproduced: an id with an unassigned or rare combining code point
+// would print it raw here and escaped there.)
+bool escape_unicode(uint32_t cp) {
+    if (cp < 0xA0) return cp >= 0x7F;
+    if (cp == 0xAD) return true;
+    if ((cp >= 0x300 && cp <= 0x36F) || (cp >= 0x483 && cp <= 0x489) || (cp >= 0x591 && cp <= 0x5BD) || (cp >= 0x610 && cp <= 0x61A) ||
+        (cp >= 0x64B && cp <= 0x65F) || cp == 0x61C || (cp >= 0x1AB0 && cp <= 0x1AFF) || (cp >= 0x1DC0 && cp <= 0x1DFF) ||
+        (cp >= 0x20D0 && cp <= 0x20FF) || (cp >= 0xFE00 && cp <= 0xFE0F) || (cp >= 0xFE20 && cp <= 0xFE2F))
+        return true;
+    if ((cp >= 0x200B && cp <= 0x200F) || (cp >= 0x2028 && cp <= 0x202E) || (cp >= 0x2060 && cp <= 0x206F) || cp == 0x180E ||
+        cp == 0xFEFF || (cp >= 0xFFF0 && cp <= 0xFFFB))
+        return true;
+    if ((cp >= 0xE000 && cp <= 0xF8FF) || (cp >= 0xF0000) || (cp & 0xFFFE) == 0xFFFE || (cp >= 0xFDD0 && cp <= 0xFDEF)) return true;
+    if (cp >= 0xE0000 && cp <= 0xE0FFF) return true;
+    return false;
+}
+// Rust's `{:?}` of a String: quotes, \" \\ \n \r \t \0, \u{..} for other non-printables
+// (at most 10 output bytes per input byte, + 2 quotes).  s must be valid UTF-8.
 char* debug_str(char* o, const char* s, size_t n) {
+    const uint8_t* u = (const uint8_t*)s;
     *o++ = '"';
-    for (size_t i = 0; i < n; i++) {
-        unsigned char c = (unsigned char)s[i];
-        if (c >= 0x20 && c != 0x7f && c != '"' && c != '\\') {
+    for (size_t i = 0; i < n;) {
+        const unsigned char c = u[i];
+        if (c >= 0x20 && c < 0x7f && c != '"' && c != '\\') {
             *o++ = (char)c;
+            i++;
             continue;
         }
-        switch (c) {
-            case '"': *o++ = '\\'; *o++ = '"'; break;
-            case '\\': *o++ = '\\'; *o++ = '\\'; break;
-            case '\n': *o++ = '\\'; *o++ = 'n'; break;
-            case '\r': *o++ = '\\'; *o++ = 'r'; break;
-            case '\t': *o++ = '\\'; *o++ = 't'; break;
-            case 0: *o++ = '\\'; *o++ = '0'; break;
-            default: o += sprintf(o, "\\u{%x}", c);
+        if (c < 0x80) {
+            switch (c) {
+                case '"': *o++ = '\\'; *o++ = '"'; break;
+                case '\\': *o++ = '\\'; *o++ = '\\'; break;
+                case '\n': *o++ = '\\'; *o++ = 'n'; break;
+                case '\r': *o++ = '\\'; *o++ = 'r'; break;
+                case '\t': *o++ = '\\'; *o++ = 't'; break;
+                case 0: *o++ = '\\'; *o++ = '0'; break;
+                default: o += sprintf(o, "\\u{%x}", c);
+            }
+            i++;
+            continue;
         }
+        uint32_t cp = 0xFFFD;
+        int l = utf8_decode(u, i, n, cp);
+        if (!l) l = 1;  // (callers validate first)
+        if (escape_unicode(cp)) o += sprintf(o, "\\u{%x}", cp);
+        else { memcpy(o, u + i, (size_t)l); o += l; }
+        i += (size_t)l;
     }
     *o++ = '"';
     return o;
+}
+// Rust's `{}` of an f32: the shortest decimal that reads back as the same f32, never in exponent form
+int display_f32(char* o, float v) {
+    for (int prec = 0; prec <= 12; prec++) {
+        char buf[64];
+        snprintf(buf, sizeof buf, "%.*f", prec, (double)v);
+        if (strtof(buf, nullptr) == v) return sprintf(o, "%s", buf);
+    }
+    return sprintf(o, "%.12f", (double)v);
 }
 
 const char kDigits2[201] =
@@ -282,33 +362,60 @@ inline char* put_u32(char* o, uint32_t v) {
     return o + len;
 }
 
-// `(flag, "id", [tx, ...], coverage)` -- the tuple printed at ref src/pseudoaligner.rs:490
-void format_range(const Batch& b, uint64_t r0, uint64_t r1, OutBuf& out, uint64_t& mapped, uint64_t& aligned) {
-    const psa_hit* hits = (const psa_hit*)b.hits.p;
+struct HostClasses {  // eq_classes on the host: compact results carry class ids, the members are expanded here
+    const uint64_t* off = nullptr;
+    const uint32_t* mem = nullptr;
+    uint64_t n_eq = 0;
+};
+
+// `(flag, "id", [tx, ...], coverage)` -- the tuple printed at ref src/pseudoaligner.rs:490.
+// novel_at: offset in b.tx of the members of the first non-class set of the range.
+void format_range(const Batch& b, const HostClasses& hc, uint64_t r0, uint64_t r1, uint64_t novel_at, OutBuf& out,
+                  uint64_t& mapped, uint64_t& aligned) {
+    const psa_hit_compact* hits = (const psa_hit_compact*)b.hits.p;
     const uint32_t* tx = (const uint32_t*)b.tx.p;
     out.n = 0;
     out.ok = true;
     for (uint64_t i = r0; i < r1; i++) {
-        const psa_hit& h = hits[i];
-        if (i + 8 < r1) __builtin_prefetch(b.text.p + b.id_off[i + 8]);  // ids sit 300+ bytes apart in the FASTQ text
-        // worst case of this record: flag 8, id 6 per byte + 2, 12 per member ("4294967295, "), brackets/coverage/newline 32
-        out.reserve_more(8 + 6 * (size_t)b.id_len[i] + 2 + 12 * (size_t)h.n_tx + 32);
+        const psa_hit_compact h = hits[i];
+        const uint32_t flags = h.cov_flags >> 28, coverage = h.cov_flags & ((1u << 28) - 1);
+        const uint32_t* m = nullptr;
+        uint32_t n_tx = 0;
+        if (!(flags & PSA_FLAG_ALIGNED)) {
+        } else if (h.eq_or_n & 0x80000000u) {
+            n_tx = h.eq_or_n & 0x7FFFFFFFu;
+            m = tx + novel_at;
+            novel_at += n_tx;
+        } else {
+            m = hc.mem + hc.off[h.eq_or_n];
+            n_tx = (uint32_t)(hc.off[h.eq_or_n + 1] - hc.off[h.eq_or_n]);
+        }
+        // the id (300+ bytes apart in the FASTQ text), the class's offsets and its members are three dependent cache
+        // misses per read: fetch them 16 / 16 / 8 reads ahead
+        if (i + 16 < r1) {
+            __builtin_prefetch(b.text.p + b.id_off[i + 16]);
+            const psa_hit_compact& a = hits[i + 16];
+            if (((a.cov_flags >> 28) & PSA_FLAG_ALIGNED) && !(a.eq_or_n & 0x80000000u)) __builtin_prefetch(hc.off + a.eq_or_n);
+            const psa_hit_compact& c = hits[i + 8];
+            if (((c.cov_flags >> 28) & PSA_FLAG_ALIGNED) && !(c.eq_or_n & 0x80000000u)) __builtin_prefetch(hc.mem + hc.off[c.eq_or_n]);
+        }
+        // worst case of this record: flag 8, id 10 per byte + 2, 12 per member ("4294967295, "), brackets/coverage/newline 32
+        out.reserve_more(8 + 10 * (size_t)b.id_len[i] + 2 + 12 * (size_t)n_tx + 32);
         if (!out.ok) return;
         char* o = out.p + out.n;
-        const bool flag = (h.flags & PSA_FLAG_MAPPED) != 0;
+        const bool flag = (flags & PSA_FLAG_MAPPED) != 0;
         mapped += flag;
-        aligned += h.flags & PSA_FLAG_ALIGNED;
+        aligned += flags & PSA_FLAG_ALIGNED;
         if (flag) { memcpy(o, "(true, ", 7); o += 7; }
         else { memcpy(o, "(false, ", 8); o += 8; }
         o = debug_str(o, (const char*)b.text.p + b.id_off[i], b.id_len[i]);
         *o++ = ','; *o++ = ' '; *o++ = '[';
-        const uint32_t* m = tx + h.tx_off;
-        for (uint32_t j = 0; j < h.n_tx; j++) {
+        for (uint32_t j = 0; j < n_tx; j++) {
             if (j) { *o++ = ','; *o++ = ' '; }
             o = put_u32(o, m[j]);
         }
         *o++ = ']'; *o++ = ','; *o++ = ' ';
-        o = put_u32(o, h.coverage);
+        o = put_u32(o, coverage);
         *o++ = ')'; *o++ = '\n';
         out.n = (size_t)(o - out.p);
     }
@@ -347,7 +454,66 @@ struct OutFile {
     }
 };
 
+// ---- the record table of one text block, exactly as bio::io::fastq::Reader::read (bio 1.5) cuts records ----------
+// (the reference reads through it: ref src/pseudoaligner.rs:421,431,442-447, src/utils.rs:152-157)
+//   header line: must start with '@' (else Error::MissingAt); id = header[1..].trim_end() up to the first ' '
+//   sequence: every following line up to one that starts with '+', each trim_end()-ed and concatenated
+//   quality: as many lines as the sequence had; an empty quality is Error::IncompleteRecord
+// Lines end at '\n' only.  A record whose lines are not all in the block yet is left for the next block (`need_more`).
+struct LineIndex {
+    const uint8_t* x;
+    const U64Buf& nl;
+    uint64_t n_lines;
+    uint64_t start(uint64_t i) const { return i ? nl[i - 1] + 1 : 0; }
+    uint64_t end(uint64_t i) const { return nl[i]; }  // position of the '\n'
+};
+enum { REC_OK = 0, REC_NEED_MORE = 1, REC_BAD = 2 };
+// Parses the record that starts at line `li`; wrapped sequences are moved together in place.  next = first line after it.
+int parse_record(uint8_t* x, const LineIndex& L, uint64_t li, bool eof, uint64_t& next, uint64_t& id_off, uint32_t& id_len,
+                 uint64_t& seq_off, uint32_t& seq_len) {
+    if (li >= L.n_lines) return REC_NEED_MORE;
+    const uint64_t h0 = L.start(li), h1 = L.end(li);
+    if (x[h0] != '@') return REC_BAD;                                   // Error::MissingAt (a blank line too)
+    const uint64_t he = h0 + 1 + trim_end(x + h0 + 1, h1 - h0 - 1);
+    uint64_t ie = h0 + 1;
+    while (ie < he && x[ie] != ' ') ie++;
+    if (!utf8_valid(x + h0 + 1, h1 - h0 - 1)) return REC_BAD;           // read_line fails on invalid UTF-8
+    id_off = h0 + 1;
+    id_len = (uint32_t)(ie - h0 - 1);
+    uint64_t j = li + 1;
+    while (j < L.n_lines && x[L.start(j)] != '+') j++;                  // (an empty line holds its '\n' at start(j): not '+')
+    if (j >= L.n_lines) return eof ? REC_BAD : REC_NEED_MORE;           // at the end of the file: no quality -> IncompleteRecord
+    const uint64_t k = j - (li + 1);
+    if (j + k >= L.n_lines) {
+        if (!eof) return REC_NEED_MORE;
+        // the file ends inside the quality lines: bio reads empty strings for the missing ones
+    }
+    uint64_t qual = 0;
+    for (uint64_t q = j + 1; q <= j + k && q < L.n_lines; q++) qual += trim_end(x + L.start(q), L.end(q) - L.start(q));
+    if (qual == 0) return REC_BAD;                                      // Error::IncompleteRecord (k == 0 included)
+    seq_off = L.start(li + 1);
+    uint64_t w = seq_off;
+    for (uint64_t q = li + 1; q < j; q++) {
+        const uint64_t s0 = L.start(q), n = trim_end(x + s0, L.end(q) - s0);
+        if (w != s0) memmove(x + w, x + s0, n);
+        w += n;
+    }
+    seq_len = (uint32_t)(w - seq_off);
+    next = j + k + 1 < L.n_lines ? j + k + 1 : L.n_lines;
+    return REC_OK;
+}
+
 }  // namespace
+
+// `{:?}` of a string as the drivers print it (shared with the Python mirror); returns the bytes written, or a
+// negative value when `s` is not valid UTF-8 / `cap` is too small (10 * n + 2 always suffices)
+extern "C" int64_t psa_debug_str(const char* s, uint64_t n, char* out, uint64_t cap) {
+    if (!out || (n && !s) || cap < 10 * n + 2) return -1;
+    if (!utf8_valid((const uint8_t*)s, n)) return -2;
+    return (int64_t)(debug_str(out, s, n) - out);
+}
+
+extern "C" int psa_index_host_classes(const psa_index*, const uint64_t** eq_offsets, const uint32_t** eq_members, uint64_t* n_eq);
 
 extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const char* out_path, uint32_t num_threads,
                                  uint64_t batch_reads, int progress, psa_process_stats* stats) {
@@ -369,8 +535,10 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     }
     OutFile of;
     of.attach(out);
+    HostClasses hc;
     psa_mapper* mapper = nullptr;
-    int rc = psa_mapper_create(index, 0, &mapper);
+    int rc = psa_index_host_classes(index, &hc.off, &hc.mem, &hc.n_eq);
+    if (!rc) rc = psa_mapper_create(index, 0, &mapper);
     if (rc) {
         in.close();
         if (own_out) fclose(out);
@@ -390,9 +558,9 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
         return std::chrono::duration<double>(b - a).count();
     };
 
-    // stage 1: raw FASTQ text -> pinned block + record table (four-line records; id = header up to the
-    // first blank, as bio::io::fastq::Record::id).  Bytes after the last complete record of a block are
-    // carried over to the next one.
+    // stage 1: raw FASTQ text -> pinned block + record table, records cut exactly as bio's reader cuts them
+    // (parse_record above; four-line records take the parallel fast path).  Bytes after the last complete
+    // record of a block are carried over to the next one.
     // text per block: starts at 400 bytes per record, then follows the record size seen (+3 %), so that little
     // text is left over after the batch_reads-th record and has to be carried to the next block
     uint64_t block_bytes = std::max<uint64_t>(batch_reads * 400, 1ull << 22);
@@ -442,58 +610,72 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 block_bytes *= 2;
             }
             if (!err) {
-                // trailing blank lines at the end of the file are not records
-                uint64_t n_lines = nl.size();
-                auto blank = [&](uint64_t i) {
-                    const uint64_t start = i ? nl[i - 1] + 1 : 0;
-                    return nl[i] == start || (nl[i] == start + 1 && b.text.p[start] == '\r');
-                };
-                if (eof)
-                    while (n_lines && blank(n_lines - 1)) n_lines--;
-                uint64_t n_rec = std::min<uint64_t>(n_lines / 4, batch_reads);
-                if (eof && n_rec == n_lines / 4 && (n_lines & 3)) err = PSA_ERR_IO;  // truncated last record
-                b.off.resize(n_rec); b.len.resize(n_rec); b.id_off.resize(n_rec); b.id_len.resize(n_rec);
-                std::vector<int> bad(num_threads, 0);
+                uint8_t* x = b.text.p;
+                const uint64_t n_lines = nl.size();
+                const LineIndex LI{x, nl, n_lines};
+                // fast path: four-line records, cut and checked by all threads at once.  Record r = lines 4r .. 4r+3 is
+                // what bio's reader would cut as long as every record before it was one too: header '@', a sequence
+                // line that does not start with '+', a '+' line, a non-empty quality line.
+                const uint64_t n4 = std::min<uint64_t>(n_lines / 4, batch_reads);
+                b.off.resize(n4); b.len.resize(n4); b.id_off.resize(n4); b.id_len.resize(n4);
+                std::vector<uint64_t> bad(num_threads, ~0ULL);
                 std::vector<std::thread> th;
                 for (uint32_t t = 0; t < num_threads; t++) {
                     th.emplace_back([&, t]() {
-                        const uint8_t* x = b.text.p;
-                        for (uint64_t r = n_rec * t / num_threads; r < n_rec * (t + 1) / num_threads; r++) {
-                            const uint64_t l0 = r ? nl[4 * r - 1] + 1 : 0, e0 = nl[4 * r];
-                            const uint64_t l1 = e0 + 1;
-                            uint64_t e1 = nl[4 * r + 1];
-                            const uint64_t l2 = e1 + 1;
-                            if (x[l0] != '@' || x[l2] != '+') {
-                                if (!bad[t]) bad[t] = 1 + (int)std::min<uint64_t>(r, 0x7ffffffe);
-                                continue;
+                        for (uint64_t r = n4 * t / num_threads; r < n4 * (t + 1) / num_threads; r++) {
+                            const uint64_t l0 = LI.start(4 * r), e0 = LI.end(4 * r);
+                            const uint64_t l1 = e0 + 1, e1 = LI.end(4 * r + 1);
+                            const uint64_t l2 = e1 + 1, l3 = LI.end(4 * r + 2) + 1, e3 = LI.end(4 * r + 3);
+                            bool ok = x[l0] == '@' && x[l1] != '+' && x[l2] == '+' && trim_end(x + l3, e3 - l3) > 0;
+                            if (ok) {
+                                uint8_t hi = 0;
+                                for (uint64_t q = l0; q < e0; q++) hi |= x[q];
+                                if ((hi & 0x80) && !utf8_valid(x + l0 + 1, e0 - l0 - 1)) ok = false;
                             }
-                            if (e1 > l1 && x[e1 - 1] == '\r') e1--;
+                            if (!ok) {
+                                bad[t] = r;
+                                break;
+                            }
+                            const uint64_t he = l0 + 1 + trim_end(x + l0 + 1, e0 - l0 - 1);
                             uint64_t ie = l0 + 1;
-                            while (ie < e0 && x[ie] != ' ' && x[ie] != '\t' && x[ie] != '\r') ie++;
+                            while (ie < he && x[ie] != ' ') ie++;      // the id ends at the first SPACE (tabs stay in it)
                             b.id_off[r] = l0 + 1;
                             b.id_len[r] = (uint32_t)(ie - l0 - 1);
                             b.off[r] = l1;
-                            b.len[r] = (uint32_t)(e1 - l1);
+                            b.len[r] = (uint32_t)trim_end(x + l1, e1 - l1);
                         }
                     });
                 }
-                for (auto& x : th) x.join();
-                uint64_t first_bad = n_rec;
-                for (uint32_t t = 0; t < num_threads; t++)
-                    if (bad[t]) first_bad = std::min<uint64_t>(first_bad, (uint64_t)bad[t] - 1);
-                if (first_bad < n_rec) {  // the complete records before the bad one are still processed
-                    n_rec = first_bad;
-                    err = PSA_ERR_IO;
+                for (auto& t : th) t.join();
+                uint64_t n_rec = n4;
+                for (uint32_t t = 0; t < num_threads; t++) n_rec = std::min(n_rec, bad[t]);
+                uint64_t line = 4 * n_rec;
+                // everything else -- wrapped sequences, malformed records, the end of the file -- one record at a time
+                if (n_rec < n4 || (eof && line < n_lines && n_rec < batch_reads)) {
+                    b.off.resize(n_rec); b.len.resize(n_rec); b.id_off.resize(n_rec); b.id_len.resize(n_rec);
+                    while (n_rec < batch_reads && line < n_lines) {
+                        uint64_t next = line, id_off = 0, seq_off = 0;
+                        uint32_t id_len = 0, seq_len = 0;
+                        const int pr = parse_record(x, LI, line, eof, next, id_off, id_len, seq_off, seq_len);
+                        if (pr == REC_NEED_MORE) break;
+                        if (pr == REC_BAD) {   // the complete records before the bad one are still processed
+                            err = PSA_ERR_IO;
+                            break;
+                        }
+                        b.off.push_back(seq_off); b.len.push_back(seq_len);
+                        b.id_off.push_back(id_off); b.id_len.push_back(id_len);
+                        n_rec++;
+                        line = next;
+                    }
                 }
                 b.n = n_rec;
-                b.text_len = n_rec ? nl[4 * n_rec - 1] + 1 : 0;
+                b.text_len = line ? nl[line - 1] + 1 : 0;
                 if (n_rec == batch_reads)
                     block_bytes = std::max<uint64_t>(b.text_len + b.text_len / 32 + 4096, 1ull << 22);
                 if (!err) {
                     carry.assign(b.text.p + b.text_len, b.text.p + have);
-                    // only blank lines may remain at the end of the file
-                    if (eof && n_rec == n_lines / 4) carry.clear();
                     if (eof && carry.empty()) done = true;
+                    if (!eof && n_rec == 0 && line == 0) block_bytes *= 2;   // not even one record in the block: read more
                 }
             }
             busy_reader += secs(tr0, now());
@@ -530,14 +712,30 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             const auto tw0 = now();
             if (b.n) {
                 std::vector<std::thread> th;
+                // where each thread's share of the non-class sets' members starts in b.tx
+                std::vector<uint64_t> nov(num_threads + 1, 0);
+                const psa_hit_compact* ch = (const psa_hit_compact*)b.hits.p;
+                for (uint32_t t = 0; t < num_threads; t++) {
+                    uint64_t r0 = b.n * t / num_threads, r1 = b.n * (t + 1) / num_threads;
+                    th.emplace_back([&, t, r0, r1]() {
+                        uint64_t sum = 0;
+                        for (uint64_t i = r0; i < r1; i++)
+                            if (((ch[i].cov_flags >> 28) & PSA_FLAG_ALIGNED) && (ch[i].eq_or_n & 0x80000000u)) sum += ch[i].eq_or_n & 0x7FFFFFFFu;
+                        nov[t + 1] = sum;
+                    });
+                }
+                for (auto& x : th) x.join();
+                th.clear();
+                for (uint32_t t = 0; t < num_threads; t++) nov[t + 1] += nov[t];
                 for (uint32_t t = 0; t < num_threads; t++) {
                     mapped[t] = aligned[t] = 0;
                     uint64_t r0 = b.n * t / num_threads, r1 = b.n * (t + 1) / num_threads;
-                    th.emplace_back([&, t, r0, r1]() { format_range(b, r0, r1, parts[t], mapped[t], aligned[t]); });
+                    th.emplace_back([&, t, r0, r1]() { format_range(b, hc, r0, r1, nov[t], parts[t], mapped[t], aligned[t]); });
                 }
                 for (auto& x : th) x.join();
                 th.clear();
                 const auto tw1 = now();
+                const uint64_t mapped_before = n_mapped;
                 for (uint32_t t = 0; t < num_threads; t++) {
                     if (!parts[t].ok) writer_rc = PSA_ERR_NOMEM;
                     n_mapped += mapped[t];
@@ -559,13 +757,18 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 if (verbose)
                     fprintf(stderr, "psa: writer block %llu records: format %.0f ms, write %.0f ms (%s)\n", (unsigned long long)b.n,
                             1e3 * secs(tw0, tw1), 1e3 * secs(tw1, now()), of.fd >= 0 ? "pwrite by every thread" : "serial");
-                n_reads += b.n;
-                if (progress && n_reads >= next_tick) {  // ref :497-504
-                    fprintf(stderr, "\rDone Mapping %llu reads w/ Rate: %g", (unsigned long long)n_reads,
-                            (double)(float)((float)n_mapped * 100.0f / (float)n_reads));
+                // ref :497-504: at every 1 000 000th read, the share of "mapped" reads so far (f32 arithmetic, `{}`)
+                while (progress && n_reads + b.n >= next_tick) {
+                    const uint64_t k = next_tick - n_reads;   // reads of this block up to the tick
+                    uint64_t m = mapped_before;
+                    for (uint64_t i = 0; i < k; i++) m += ((ch[i].cov_flags >> 28) & PSA_FLAG_MAPPED) != 0;
+                    char rate[64];
+                    display_f32(rate, (float)m * 100.0f / (float)next_tick);
+                    fprintf(stderr, "\rDone Mapping %llu reads w/ Rate: %s", (unsigned long long)next_tick, rate);
                     fflush(stderr);
-                    next_tick = (n_reads / 1000000 + 1) * 1000000;
+                    next_tick += 1000000;
                 }
+                n_reads += b.n;
             }
             busy_writer += secs(tw0, now());
             const bool last = b.last;
@@ -589,8 +792,8 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
         }
         const auto tm0 = now();
         if (b.n) {
-            map_rc = b.hits.reserve(b.n * sizeof(psa_hit), 0);
-            if (!map_rc) map_rc = b.tx.reserve(std::max<uint64_t>(b.n * 16 * 4, 4096), 0);
+            map_rc = b.hits.reserve(b.n * sizeof(psa_hit_compact), 0);
+            if (!map_rc) map_rc = b.tx.reserve(std::max<uint64_t>(b.n * 2 * 4, 4096), 0);   // members of the non-class sets only
             psa_read_batch r{};
             r.format = PSA_READS_ASCII;
             r.location = PSA_MEM_HOST;
@@ -601,6 +804,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
             r.n_reads = b.n;
             psa_result_batch o{};
             o.location = PSA_MEM_HOST;
+            o.flags = PSA_RESULT_COMPACT;   // 8 bytes per read back; class ids are expanded from the host's eq_classes
             for (int attempt = 0; attempt < 2 && !map_rc; attempt++) {
                 o.hits = (psa_hit*)b.hits.p;
                 o.tx_buf = (uint32_t*)b.tx.p;

@@ -101,6 +101,8 @@ struct psa_index {
     int device = 0;
     DevIndex d{};
     DevBuf buckets, nodes, nodes_cold, seq, eq_off, eq_mem, class_win;
+    std::vector<uint64_t> h_eq_off;   // eq_classes on the host too: compact results are expanded from them
+    std::vector<uint32_t> h_eq_mem;
     psa_index_info info{};
     int kw = 1;
 };
@@ -405,6 +407,8 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
 #undef RCI
 #undef CUI
 
+    ix->h_eq_off.assign(d->eq_offsets, d->eq_offsets + d->n_eq + 1);
+    ix->h_eq_mem.assign(d->eq_members, d->eq_members + n_mem);
     psa_index_info& I = ix->info;
     I.k = d->k;
     I.n_nodes = d->n_nodes;
@@ -431,6 +435,15 @@ extern "C" void psa_index_destroy(psa_index* ix) {
     ix->buckets.release(); ix->nodes.release(); ix->nodes_cold.release();
     ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
     delete ix;
+}
+
+// eq_classes as the index holds them on the host (borrowed until psa_index_destroy); used by psa_process_reads
+extern "C" int psa_index_host_classes(const psa_index* ix, const uint64_t** eq_offsets, const uint32_t** eq_members, uint64_t* n_eq) {
+    if (!ix || !eq_offsets || !eq_members || !n_eq) return fail(PSA_ERR_ARG, "null argument");
+    *eq_offsets = ix->h_eq_off.data();
+    *eq_members = ix->h_eq_mem.data();
+    *n_eq = ix->d.n_eq;
+    return PSA_OK;
 }
 
 extern "C" int psa_index_get_info(const psa_index* ix, psa_index_info* out) {
@@ -470,7 +483,7 @@ extern "C" int psa_index_lookup(psa_index* ix, const uint64_t* kmer_words, uint6
 // ---------------------------------------------------------------------------------------------
 struct Slot {  // staging of one pipeline chunk
     DevBuf in_data, in_off, in_len;     // host batch copied as is
-    DevBuf hits, tx, meta_dev;          // results of the chunk; meta_dev = {running total, status}
+    DevBuf hits, hits_c, tx, meta_dev;  // results of the chunk (hits_c: compact records); meta_dev = {running total, status}
     cudaEvent_t in_ready = nullptr, in_free = nullptr, comp_done = nullptr, meta_done = nullptr, out_free = nullptr;
     bool in_free_rec = false, out_free_rec = false;
     unsigned long long* meta_host = nullptr;  // pinned: [0] running tx total after the chunk, [1] status
@@ -487,8 +500,9 @@ struct psa_mapper {
     uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
     cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
     DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, pool, running;
+    DevBuf hits_full;   // compact results on device batches: the kernels' 24-byte working records
     DevBuf ntab, ntab_backup, ncur_backup, npool, ncur, nlist, nslot;   // the novel-set table (NovelTable), this batch's list of novel reads and their entries
-    uint64_t ntab_cap = 1ull << 18, npool_cap = 1ull << 22;
+    uint64_t ntab_cap = 1ull << 21, npool_cap = 1ull << 23;   // 64 MB + 32 MB to start with; both grow on demand
     DevBuf words, woff, nwords, dst_off, scan_tmp, meta, deferred, scan_list, seeded, seeded_ev;
     uint64_t novel_cap = 0;
     uint32_t spill_cap = 56;          // visited-class list entries per group beyond its lanes
@@ -551,6 +565,14 @@ static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p
         else k_map_thread<2, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
         return;
     }
+#if PSA_THREAD_PERSIST
+    if (!EV) {
+        const unsigned pgrid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n, kThreadBlock), 148 * PSA_THREAD_MIN_BLOCKS);
+        if (m->ix->kw == 1) k_map_thread<1, EV, false><<<pgrid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        else k_map_thread<2, EV, false><<<pgrid, kThreadBlock, 0, st>>>(m->ix->d, p);
+        return;
+    }
+#endif
     const unsigned grid = nblocks(p.reads.n, kThreadBlock);
     const uint32_t smem = tile_smem_bytes(p.reads);
     if (smem) {
@@ -696,11 +718,11 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
     if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
     DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
-                      &m->running, &m->ntab, &m->ntab_backup, &m->ncur_backup, &m->npool, &m->ncur, &m->nlist, &m->nslot, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
+                      &m->running, &m->hits_full, &m->ntab, &m->ntab_backup, &m->ncur_backup, &m->npool, &m->ncur, &m->nlist, &m->nslot, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
     for (auto b : bufs) b->release();
     for (int s = 0; s < kSlots; s++) {
         Slot& S = m->slot[s];
-        S.in_data.release(); S.in_off.release(); S.in_len.release(); S.hits.release(); S.tx.release(); S.meta_dev.release();
+        S.in_data.release(); S.in_off.release(); S.in_len.release(); S.hits.release(); S.hits_c.release(); S.tx.release(); S.meta_dev.release();
         cudaEvent_t evs[5] = {S.in_ready, S.in_free, S.comp_done, S.meta_done, S.out_free};
         for (auto ev : evs)
             if (ev) cudaEventDestroy(ev);
@@ -754,6 +776,7 @@ struct DeviceBatch {
     uint64_t* meta_out;    // device u64[2]: {running total after the batch, status}
     uint64_t total_words;  // ragged ASCII only: sum of ceil(len/32) if the caller knows it, else 0
     bool sticky = false;   // accumulate the status word over the batches queued since the last psa_mapper_sync
+    HitCompact* hits_c = nullptr;  // compact results: where the 8-byte records go (hits stays the kernels' working array)
 };
 
 template <bool EV>
@@ -911,7 +934,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     if ((rc = m->dst_off.ensure((n + 2) * 8))) return rc;
     {
         cub::CountingInputIterator<uint64_t> cnt(0);
-        TxLenN f{b.hits, n};
+        TxLenN f{b.hits, n, b.hits_c != nullptr};
         cub::TransformInputIterator<uint64_t, TxLenN, cub::CountingInputIterator<uint64_t>> in(cnt, f);
         size_t tb = 0;
         CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, m->dst_off.as<uint64_t>(), n + 1, st));
@@ -920,7 +943,12 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     }
     if (n) {
         k_expand_balanced<<<nblocks(n, 256), 256, 0, st>>>(b.hits, n, m->dst_off.as<uint64_t>(), m->running.as<uint64_t>(),
-                                                           ix->d.eq_off, ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap);
+                                                           ix->d.eq_off, ix->d.eq_mem, m->novel.as<uint32_t>(), b.tx_buf, b.tx_cap,
+                                                           b.hits_c != nullptr);
+        if (b.hits_c) {
+            k_compact_hits<<<nblocks(n, 256), 256, 0, st>>>(b.hits, n, b.hits_c, m->status.as<uint32_t>());
+            m->launches++;
+        }
     }
     if (n && want_counts) {
         k_novel_add<<<296, 256, 0, st>>>(p.novel_list_count, nt, m->nslot.as<uint32_t>(), p.status, m->dst_off.as<uint64_t>() + n, b.tx_cap,
@@ -1008,6 +1036,12 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
         }
         CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
         DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
+        if (o->flags & PSA_RESULT_COMPACT) {
+            int rch = m->hits_full.ensure((r->n_reads + 1) * sizeof(HitRec));
+            if (rch) return rch;
+            b.hits = m->hits_full.as<HitRec>();
+            b.hits_c = (HitCompact*)o->hits;
+        }
         int rc = enqueue_device_batch<EV>(m, b, true);
         if (rc) return rc;
         CU(cudaMemcpyAsync(m->pin, m->meta.p, 16, cudaMemcpyDeviceToHost, m->st));
@@ -1015,6 +1049,7 @@ static int map_device_sync(psa_mapper* m, const psa_read_batch* r, psa_result_ba
         uint32_t status = (uint32_t)m->pin[1];
         o->tx_used = m->pin[0];
         if (status & 8u) return novel_clash();
+        if (status & 32u) return fail(PSA_ERR_ARG, "compact results need coverage < 2^28 and class ids < 2^31");
         if (status & 19u) {  // novel-set buffer / class-list pool / novel-set table overflow: undo the counts, retry with larger buffers
             CU(cudaMemcpyAsync(m->counts.p, m->counts_backup.p, nc * 8, cudaMemcpyDeviceToDevice, m->st));
             CU(cudaStreamSynchronize(m->st));
@@ -1044,6 +1079,11 @@ extern "C" int psa_mapper_map_async(psa_mapper* m, const psa_read_batch* r, psa_
     CU(cudaSetDevice(m->ix->device));
     CU(cudaMemsetAsync(m->running.p, 0, 16, m->st));
     DeviceBatch b{r, (HitRec*)o->hits, o->tx_buf, o->tx_cap, m->meta.as<uint64_t>(), 0};
+    if (o->flags & PSA_RESULT_COMPACT) {
+        if ((rc = m->hits_full.ensure((r->n_reads + 1) * sizeof(HitRec)))) return rc;
+        b.hits = m->hits_full.as<HitRec>();
+        b.hits_c = (HitCompact*)o->hits;
+    }
     b.sticky = true;  // earlier batches may still be queued: their overflow bits stay visible until the next sync
     if ((rc = enqueue_device_batch<false>(m, b, true))) return rc;
     CU(cudaMemcpyAsync(m->pin, m->meta.p, 16, cudaMemcpyDeviceToHost, m->st));
@@ -1080,6 +1120,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
     const uint64_t n = r->n_reads;
     const uint64_t nc = m->ix->d.n_eq + 2;
     const bool ascii = r->format == PSA_READS_ASCII;
+    const bool compact = (o->flags & PSA_RESULT_COMPACT) != 0;
     const uint64_t unit = ascii ? 1 : 8;  // bytes per data element
     const uint64_t C = m->chunk_reads;
     const uint64_t nchunks = (n + C - 1) / C;
@@ -1132,13 +1173,14 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
         for (int s = 0; s < kSlots && (uint64_t)s < nchunks; s++) {
             Slot& S = m->slot[s];
             if ((rc = S.in_data.ensure(max_dn * unit + 64)) || (rc = S.hits.ensure(std::min(C, n) * sizeof(HitRec)))) return rc;
+            if (compact && (rc = S.hits_c.ensure(std::min(C, n) * sizeof(HitCompact)))) return rc;
             if (r->read_off && (rc = S.in_off.ensure(C * 8))) return rc;
             if (r->read_len && (rc = S.in_len.ensure(C * 4))) return rc;
             if (o->tx_buf && (rc = S.tx.ensure(std::max<uint64_t>(S.tx.cap, std::min(C, n) * 16 * 4)))) return rc;
         }
         for (int s = 0; s < kSlots; s++) m->slot[s].in_free_rec = m->slot[s].out_free_rec = false;
         const double t_alloc = verbose ? now_s() - ta0 : 0;
-        bool novel_overflow = false, spill_overflow = false, stage_overflow = false, ntab_overflow = false, clash = false;
+        bool novel_overflow = false, spill_overflow = false, stage_overflow = false, ntab_overflow = false, clash = false, bad_compact = false;
         uint64_t stage_need = 0;
         uint64_t tx_prev_total = 0;  // host copy of the running total before the chunk being finished
 
@@ -1154,6 +1196,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             if (status & 2u) spill_overflow = true;
             if (status & 8u) clash = true;
             if (status & 16u) ntab_overflow = true;
+            if (status & 32u) bad_compact = true;
             uint64_t cnt = total - tx_prev_total;
             if (status & 4u) {  // the chunk produced more members than its staging buffer holds
                 stage_overflow = true;
@@ -1194,6 +1237,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             rb.read_len = r->read_len ? S.in_len.as<uint32_t>() : nullptr;
             DeviceBatch b{&rb, S.hits.as<HitRec>(), o->tx_buf ? S.tx.as<uint32_t>() : nullptr,
                           o->tx_buf ? (uint64_t)(S.tx.cap / 4) : 0, S.meta_dev.as<uint64_t>(), P.words};
+            if (compact) b.hits_c = S.hits_c.as<HitCompact>();
             if ((rc = enqueue_device_batch<false>(m, b, true))) return rc;
             CU(cudaEventRecord(S.comp_done, m->st));
             CU(cudaEventRecord(S.in_free, m->st));
@@ -1202,7 +1246,10 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             CU(cudaStreamWaitEvent(m->st_d2h, S.comp_done, 0));
             CU(cudaMemcpyAsync(S.meta_host, S.meta_dev.p, 16, cudaMemcpyDeviceToHost, m->st_d2h));
             CU(cudaEventRecord(S.meta_done, m->st_d2h));
-            CU(cudaMemcpyAsync(o->hits + P.r0, S.hits.p, P.nr * sizeof(HitRec), cudaMemcpyDeviceToHost, m->st_d2h));
+            if (compact)
+                CU(cudaMemcpyAsync((HitCompact*)o->hits + P.r0, S.hits_c.p, P.nr * sizeof(HitCompact), cudaMemcpyDeviceToHost, m->st_d2h));
+            else
+                CU(cudaMemcpyAsync(o->hits + P.r0, S.hits.p, P.nr * sizeof(HitRec), cudaMemcpyDeviceToHost, m->st_d2h));
             if (verbose) t_submit += now_s() - ts0;
             if (c >= (uint64_t)(kSlots - 1) && (rc = finish(c - (kSlots - 1)))) return rc;
         }
@@ -1216,6 +1263,7 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
                     (unsigned long long)nchunks, 1e3 * t_alloc, 1e3 * t_submit, 1e3 * t_wait, 1e3 * (now_s() - td0));
         o->tx_used = tx_prev_total;
         if (clash) return novel_clash();
+        if (bad_compact) return fail(PSA_ERR_ARG, "compact results need coverage < 2^28 and class ids < 2^31");
         if (novel_overflow || stage_overflow || spill_overflow || ntab_overflow) {
             // (a chunk that overflowed counted nothing, but the chunks around it did: the novel-set counts of this call
             // are undone with the per-class counts -- the table's counts are part of the backup below)
@@ -1633,6 +1681,42 @@ extern "C" int psa_selftest_intersect(int device, const uint32_t* v1, uint32_t n
     if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, 3 * (uint64_t)cap * 4, cudaMemcpyDeviceToHost);
     rel();
     if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    return PSA_OK;
+}
+
+// Compact results -> the full form, on the host: index classes are expanded from the caller's copy of eq_classes.
+extern "C" int psa_expand_compact(const psa_hit_compact* in, uint64_t n, const uint32_t* novel_tx, uint64_t novel_tx_len,
+                                  const uint64_t* eq_offsets, const uint32_t* eq_members, uint64_t n_eq, psa_hit* hits,
+                                  uint32_t* tx_buf, uint64_t tx_cap, uint64_t* tx_used) {
+    if (!in || !hits || !tx_used || !eq_offsets || (n_eq && eq_offsets[n_eq] && !eq_members)) return fail(PSA_ERR_ARG, "null argument");
+    uint64_t used = 0, nov = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const psa_hit_compact c = in[i];
+        psa_hit h;
+        h.coverage = c.cov_flags & ((1u << 28) - 1);
+        h.flags = c.cov_flags >> 28;
+        h.tx_off = used;
+        const uint32_t* src = nullptr;
+        if (!(h.flags & PSA_FLAG_ALIGNED)) {
+            h.eq_id = PSA_EQ_NONE; h.n_tx = 0;
+        } else if (c.eq_or_n & 0x80000000u) {
+            h.eq_id = PSA_EQ_NONE;
+            h.n_tx = c.eq_or_n & 0x7FFFFFFFu;
+            if (nov + h.n_tx > novel_tx_len) return fail(PSA_ERR_ARG, "novel members missing");
+            src = novel_tx + nov;
+            nov += h.n_tx;
+        } else {
+            if (c.eq_or_n >= n_eq) return fail(PSA_ERR_ARG, "class id out of range");
+            h.eq_id = c.eq_or_n;
+            h.n_tx = (uint32_t)(eq_offsets[h.eq_id + 1] - eq_offsets[h.eq_id]);
+            src = eq_members + eq_offsets[h.eq_id];
+        }
+        if (tx_buf && used + h.n_tx <= tx_cap && h.n_tx) memcpy(tx_buf + used, src, (size_t)h.n_tx * 4);
+        used += h.n_tx;
+        hits[i] = h;
+    }
+    *tx_used = used;
+    if (tx_buf && used > tx_cap) return fail(PSA_ERR_CAPACITY, "tx_buf too small");
     return PSA_OK;
 }
 

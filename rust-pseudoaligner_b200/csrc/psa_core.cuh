@@ -128,10 +128,20 @@ PSA_HD Sector load_sector_hot(const void* p) {  // node records, class windows: 
 #endif
     return s;
 }
+#ifndef PSA_DICT_LOAD
+#define PSA_DICT_LOAD 0   // 0: evict-first + no L1 allocation, 1: plain read-only load, 2: evict-first only
+#endif
 PSA_HD Sector load_sector_stream(const void* p) {  // dictionary buckets: one use
     Sector s;
 #ifdef __CUDA_ARCH__
+#if PSA_DICT_LOAD == 1
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(s.w0), "=l"(s.w1), "=l"(s.w2), "=l"(s.w3) : "l"(p));
+#elif PSA_DICT_LOAD == 2
+    asm("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(s.w0), "=l"(s.w1), "=l"(s.w2), "=l"(s.w3) : "l"(p), "l"(l2_policy_first()));
+#else
     ld_v4_first(p, s.w0, s.w1, s.w2, s.w3);
+#endif
 #else
     const uint64_t* q = static_cast<const uint64_t*>(p);
     s.w0 = q[0]; s.w1 = q[1]; s.w2 = q[2]; s.w3 = q[3];
@@ -740,7 +750,10 @@ PSA_HD void winacc_filter_list(WinAcc& a, const uint32_t* v, uint32_t n) {
 // that length.  A read whose classes do not fit (more than kThreadWide wide ones before any
 // narrow one, ...) sets `defer`: the cooperative kernel redoes it from scratch.
 // ---------------------------------------------------------------------------------------------
-constexpr int kThreadWide = 3;
+#ifndef PSA_THREAD_WIDE
+#define PSA_THREAD_WIDE 3
+#endif
+constexpr int kThreadWide = PSA_THREAD_WIDE;  // wide classes one read may list
 constexpr uint32_t kThreadWideInline = 2;  // further wide classes applied on arrival before giving up
 constexpr uint32_t kReseedProbes = 8;
 constexpr uint32_t kFlagAligned = 1u, kFlagMapped = 2u;

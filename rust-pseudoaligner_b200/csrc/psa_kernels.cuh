@@ -445,6 +445,10 @@ struct WarpCtx {
     uint32_t read_len;
     bool scan_mode;
     uint32_t scan_skip = 0;  // scan mode: first position not yet known to be absent
+    // scan mode, reads of at most 32 * G bases: lane j holds word j of the read, k-mers are cut from shuffled words
+    // (the scan otherwise re-fetches two read words from L2 for every probe)
+    bool staged = false;
+    uint64_t my_word = 0;
     LaneEvents ev;
 
     __device__ __forceinline__ WarpCtx(const DevIndex& ix_, const uint64_t* read_words, uint32_t read_len_,
@@ -455,6 +459,21 @@ struct WarpCtx {
 
     __device__ __forceinline__ uint32_t read_base(uint64_t pos) const { return seq_get(rd, pos); }
     __device__ __forceinline__ bool abort() const { return false; }
+    __device__ __forceinline__ void stage_words() {
+        const uint32_t nw = (read_len + 31) >> 5;
+        staged = nw <= (uint32_t)G;
+        if (staged) my_word = lane < nw ? rd(lane) : 0;
+    }
+    // the k-mer at position p from the staged words; every lane of the group calls it (p may differ per lane)
+    __device__ __forceinline__ Kmer<KW> staged_kmer(uint32_t p) const {
+        const uint32_t wi = p >> 5;
+        Sector s;
+        s.w0 = g.shfl(my_word, (int)wi);
+        s.w1 = g.shfl(my_word, (int)min(wi + 1, (uint32_t)G - 1));
+        s.w2 = KW == 2 ? g.shfl(my_word, (int)min(wi + 2, (uint32_t)G - 1)) : 0;
+        s.w3 = 0;
+        return KmerOps<KW>::get(WLoad{s, wi}, p, k);
+    }
 
     // find_kmer_match, ref src/pseudoaligner.rs:91-114.  The first position is probed by the
     // whole group on one address (the common case: it hits); after a miss, G stride-3
@@ -480,10 +499,11 @@ struct WarpCtx {
             bool h = false;
             uint32_t n = 0, o = 0;
             st.levels = st.hit = st.verified = 0;
-            if (p <= last) {
-                Kmer<KW> key = KmerOps<KW>::get(rd, p, k);
-                h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
-            }
+            const bool in = p <= last;
+            Kmer<KW> key{};
+            if (staged) key = staged_kmer(in ? (uint32_t)p : 0u);
+            else if (in) key = KmerOps<KW>::get(rd, p, k);
+            if (in) h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
             unsigned b = g.ballot(h);
             int j = b ? (__ffs(b) - 1) : G;
             if (EV) {  // sequential-equivalent events: the probes up to and including the first hit
@@ -1111,7 +1131,10 @@ __global__ void __launch_bounds__(32 * kPoolWarps, PSA_POOL_CTAS) k_map_lanes(co
 #endif
 constexpr int kThreadBlock = PSA_THREAD_BLOCK;
 #ifndef PSA_THREAD_MIN_BLOCKS
-#define PSA_THREAD_MIN_BLOCKS 20
+#define PSA_THREAD_MIN_BLOCKS 16
+#endif
+#ifndef PSA_THREAD_PERSIST
+#define PSA_THREAD_PERSIST 0
 #endif
 template <int KW, bool EV, bool HINT, bool TILE = false>
 __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
@@ -1143,6 +1166,28 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
         my_words = pw + threadIdx.x * nw;
     }
     DevSink sink{p};
+#if PSA_THREAD_PERSIST
+    // Persistent lanes: every thread strides over the batch and starts its next read as soon as it is done with one,
+    // so that no lane idles behind the slowest read of its warp (hand-overs: one atomic per read instead of per warp).
+    if (!HINT && !EV && !TILE) {
+        const uint64_t total = gridDim.x * (uint64_t)blockDim.x;
+        for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < p.reads.n; r += total) {
+            const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
+            const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
+            ThreadResult res = map_read_thread<KW, false>(ix, PLoad{p.reads.words + wo}, (uint32_t)r, L, p.allowed_mismatches,
+                                                          p.max_probes, p.max_small, sink, p.novel != nullptr, nullptr, nullptr);
+            if (!res.deferred) {
+                sink.result((uint32_t)r, res.hit, res.count_slot);
+                if (res.novel_overflow) sink.novel_overflow();
+            } else if (res.why == 0 && p.scan_list != nullptr) {
+                p.scan_list[atomicAdd(p.scan_count, 1ULL)] = (uint32_t)r;
+            } else {
+                p.list[atomicAdd(p.list_count, 1ULL)] = (uint32_t)r;
+            }
+        }
+        return;
+    }
+#endif
     const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
     const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
     // warp-uniform trip count: the hand-over below uses full-warp votes
@@ -1235,6 +1280,7 @@ __global__ void __launch_bounds__(256) k_seed_scan(const __grid_constant__ DevIn
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;  // >= k: shorter reads never search
         WarpCtx<KW, EV, G> w(ix, p.reads.words + wo, L, p, gid);
         w.scan_mode = true;
+        w.stage_words();
         // a read is on this list because its own thread probed positions 0, 3, ..., 3 (max_probes - 1) and missed
         // them all: start behind them (when counting events the whole search is redone: the counters are
         // sequential-equivalent and the thread kernel did not count a search it gave up)
@@ -1345,7 +1391,11 @@ __global__ void k_gather_probe(const uint64_t* table, uint64_t n_chunks, uint32_
 struct TxLenN {  // iterator adaptor for the scan of n_tx; item n is a zero so that out[n] = total
     const HitRec* h;
     uint64_t n;
-    __host__ __device__ uint64_t operator()(uint64_t i) const { return i < n ? (uint64_t)h[i].n_tx : 0; }
+    int novel_only;  // compact results: only sets that are no index class travel as members
+    __host__ __device__ uint64_t operator()(uint64_t i) const {
+        if (i >= n) return 0;
+        return novel_only && h[i].eq_id != kNone ? 0 : (uint64_t)h[i].n_tx;
+    }
 };
 struct CastU64 {
     __host__ __device__ uint64_t operator()(uint32_t x) const { return x; }
@@ -1358,7 +1408,7 @@ struct CastU64 {
 // pointer from that lane.  Stores are fully coalesced and no lane idles behind a read with a long class.
 __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t n, const uint64_t* rel_off, const uint64_t* running,
                                                          const uint64_t* eq_off, const uint32_t* eq_mem, const uint32_t* novel,
-                                                         uint32_t* tx_buf, uint64_t tx_cap) {
+                                                         uint32_t* tx_buf, uint64_t tx_cap, int novel_only) {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t base = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull;
     if (base >= n) return;  // warp-uniform
@@ -1371,7 +1421,7 @@ __global__ void __launch_bounds__(256) k_expand_balanced(HitRec* hits, uint64_t 
     if (live) {
         const HitRec h = hits[i];
         rel = rel_off[i];
-        cnt = h.n_tx;
+        cnt = novel_only && h.eq_id != kNone ? 0 : h.n_tx;
         fits = tx_buf != nullptr && rel + cnt <= tx_cap;
         // members of an index class come from the index (through eq_id), any other set from the novel-set buffer
         src = h.eq_id != kNone ? eq_mem + __ldg(eq_off + h.eq_id) : novel + h.tx_off;
@@ -1479,8 +1529,15 @@ __global__ void k_novel_add(const unsigned long long* list_count, NovelTable t, 
                             const uint64_t* batch_total, uint64_t tx_cap, int has_tx) {
     const uint64_t n = *list_count;
     if ((*status & 31u) || (has_tx && *batch_total > tx_cap)) return;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (uint64_t)blockDim.x)
-        atomicAdd(&t.tab[slot_in[i]].count, 1ULL);
+    // popular sets (the empty one above all) would serialise one atomic per read on one address: the lanes of a warp
+    // that count the same entry add once
+    const uint64_t n_round = (n + 31) & ~31ULL;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * (uint64_t)blockDim.x) {
+        const uint32_t slot = i < n ? slot_in[i] : kNone;
+        const unsigned same = __match_any_sync(kFull, slot);
+        if (slot != kNone && (threadIdx.x & 31) == (unsigned)(__ffs(same) - 1))
+            atomicAdd(&t.tab[slot].count, (unsigned long long)__popc(same));
+    }
 }
 // growing the table: every used entry of the old one moves to the new one
 __global__ void k_novel_rehash(const NovelEntry* old_tab, uint64_t old_cap, NovelEntry* tab, uint64_t cap) {
@@ -1512,6 +1569,24 @@ __global__ void k_result_checksum(const HitRec* hits, const uint32_t* tx, uint64
 #pragma unroll
     for (int d = 16; d; d >>= 1) h += __shfl_xor_sync(kFull, h, d);
     if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, (unsigned long long)h);
+}
+
+// Compact results (psa.h PSA_RESULT_COMPACT): eight bytes per read.  eq_or_n = the index class of the read's
+// eq_class | 0x80000000 + |eq_class| when it is no index class (its members travel in tx_buf) | 0xFFFFFFFF for None;
+// cov_flags = coverage | PSA_FLAG_* << 28.
+struct HitCompact {
+    uint32_t eq_or_n, cov_flags;
+};
+constexpr uint32_t kCompactNovel = 0x80000000u, kCompactCovMask = (1u << 28) - 1;
+__global__ void k_compact_hits(const HitRec* hits, uint64_t n, HitCompact* out, uint32_t* status) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const HitRec h = hits[i];
+    HitCompact c;
+    c.eq_or_n = !(h.flags & kFlagAligned) ? kNone : h.eq_id != kNone ? h.eq_id : (kCompactNovel | h.n_tx);
+    c.cov_flags = (h.coverage & kCompactCovMask) | (h.flags << 28);
+    if (h.coverage > kCompactCovMask || ((h.flags & kFlagAligned) && h.eq_id != kNone && h.eq_id >= kCompactNovel)) atomicOr(status, 32u);
+    out[i] = c;
 }
 
 // after k_expand: advance the running total, publish {running, status} for the host.  sticky (may be

@@ -24,6 +24,9 @@ HIT_DTYPE = np.dtype(
     [("coverage", "<u4"), ("n_tx", "<u4"), ("tx_off", "<u8"), ("eq_id", "<u4"), ("flags", "<u4")]
 )
 
+HIT_COMPACT_DTYPE = np.dtype([("eq_or_n", "<u4"), ("cov_flags", "<u4")])
+RESULT_COMPACT = 1
+
 EVENT_FIELDS = ("reads", "read_bases", "kmer_lookups", "dict_levels", "dict_hits", "verifications",
                 "node_visits", "bases_compared", "edge_jumps", "class_members", "out_members", "aligned")
 
@@ -59,7 +62,7 @@ class _ReadBatch(C.Structure):
 
 
 class _ResultBatch(C.Structure):
-    _fields_ = [("location", C.c_uint32), ("reserved", C.c_uint32), ("hits", C.c_void_p),
+    _fields_ = [("location", C.c_uint32), ("flags", C.c_uint32), ("hits", C.c_void_p),
                 ("tx_buf", C.c_void_p), ("tx_cap", C.c_uint64), ("tx_used", C.c_uint64)]
 
 
@@ -90,7 +93,7 @@ EXPORTS = (
     "psa_host_alloc", "psa_host_free", "psa_device_alloc", "psa_device_free",
     "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe", "psa_result_checksum",
     "psa_selftest_intersect", "psa_mapper_novel_sets", "psa_novel_sets_merge", "psa_novel_sets_free",
-    "psa_mapper_novel_allgather",
+    "psa_mapper_novel_allgather", "psa_expand_compact", "psa_debug_str", "psa_index_host_classes",
 )
 
 
@@ -161,6 +164,9 @@ def lib():
     L.psa_novel_sets_merge.restype, L.psa_novel_sets_merge.argtypes = i32, [C.POINTER(_NovelSets), u32, C.POINTER(_NovelSets)]
     L.psa_novel_sets_free.restype, L.psa_novel_sets_free.argtypes = None, [C.POINTER(_NovelSets)]
     L.psa_mapper_novel_allgather.restype, L.psa_mapper_novel_allgather.argtypes = i32, [vp, vp, C.POINTER(_NovelSets)]
+    L.psa_debug_str.restype, L.psa_debug_str.argtypes = C.c_int64, [C.c_char_p, u64, C.c_char_p, u64]
+    L.psa_expand_compact.restype = i32
+    L.psa_expand_compact.argtypes = [vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, C.POINTER(u64)]
     L.psa_selftest_intersect.restype = i32
     L.psa_selftest_intersect.argtypes = [i32, vp, u32, vp, u32, vp, u32, C.POINTER(u32 * 3)]
     L.psa_result_checksum.restype = i32
@@ -422,16 +428,17 @@ class Mapper:
 
     # ---- host batches -------------------------------------------------------------------
     def _map_host(self, fmt, data, n, read_off, read_len, stride, fixed_len, want_tx=True, tx_cap=None,
-                  hits=None, tx=None):
+                  hits=None, tx=None, compact=False):
         rb = _ReadBatch(fmt, MEM_HOST, _ptr(data), data.size, _ptr(read_off), _ptr(read_len),
                         int(stride), int(fixed_len), 0, int(n))
         if hits is None:
-            hits = np.zeros(n, dtype=HIT_DTYPE)
+            hits = np.zeros(n, dtype=HIT_COMPACT_DTYPE if compact else HIT_DTYPE)
         cap = int(tx_cap) if tx_cap is not None else max(16 * n, 1024)
         while True:
             if want_tx and (tx is None or tx.size < cap):
                 tx = np.zeros(cap, dtype=np.uint32)
-            ob = _ResultBatch(MEM_HOST, 0, _ptr(hits), _ptr(tx) if want_tx else None, cap if want_tx else 0, 0)
+            ob = _ResultBatch(MEM_HOST, RESULT_COMPACT if compact else 0, _ptr(hits), _ptr(tx) if want_tx else None,
+                              cap if want_tx else 0, 0)
             rc = lib().psa_mapper_map(self.h, C.byref(rb), C.byref(ob))
             if rc == ERR_CAPACITY and want_tx and ob.tx_used > cap:
                 cap = int(ob.tx_used) + 16
@@ -440,26 +447,32 @@ class Mapper:
             break
         return hits, (tx[:ob.tx_used] if want_tx else np.zeros(0, np.uint32))
 
-    def map_ascii(self, seqs, want_tx=True):
-        """list of ASCII reads (bytes/str) -> (hits, tx_buf); the process_reads body for a batch."""
+    def map_ascii(self, seqs, want_tx=True, compact=False):
+        """list of ASCII reads (bytes/str) -> (hits, tx_buf); the process_reads body for a batch.
+        compact=True: 8-byte psa_hit_compact records, tx_buf = members of the non-class sets only."""
         bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
         lens = np.array([len(b) for b in bs], dtype=np.uint32)
         off = np.zeros(len(bs), dtype=np.uint64)
         if len(bs):
             off[1:] = np.cumsum(lens.astype(np.uint64))[:-1]
         data = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8)
-        return self._map_host(READS_ASCII, data, len(bs), off, lens, 0, 0, want_tx)
+        return self._map_host(READS_ASCII, data, len(bs), off, lens, 0, 0, want_tx, compact=compact)
 
     def map_ascii_fixed(self, data, n, length, stride=None, want_tx=True, **kw):
         """n reads of `length` bases at data[i*stride : i*stride+length] (uint8 array)."""
         stride = length if stride is None else stride
         return self._map_host(READS_ASCII, data, n, None, None, stride, length, want_tx, **kw)
 
-    def map_packed(self, words, read_off, read_len, want_tx=True):
+    def map_packed(self, words, read_off, read_len, want_tx=True, **kw):
         words = np.ascontiguousarray(words, np.uint64)
         read_off = np.ascontiguousarray(read_off, np.uint64)
         read_len = np.ascontiguousarray(read_len, np.uint32)
-        return self._map_host(READS_PACKED, words, len(read_len), read_off, read_len, 0, 0, want_tx)
+        return self._map_host(READS_PACKED, words, len(read_len), read_off, read_len, 0, 0, want_tx, **kw)
+
+    def map_packed_fixed(self, words, n, length, wstride=None, want_tx=True, **kw):
+        """n reads of `length` bases as DnaString words, read i at words[i*wstride ...] (uint64 array)."""
+        wstride = (length + 31) // 32 if wstride is None else wstride
+        return self._map_host(READS_PACKED, words, n, None, None, wstride, length, want_tx, **kw)
 
     # ---- device batches -----------------------------------------------------------------
     def map_device(self, batch):
@@ -616,11 +629,33 @@ class Pseudoaligner:
         self.index.close()
 
 
+def expand_compact(hits_c, novel_tx, eq_offsets, eq_members):
+    """psa_expand_compact: compact records + members of the non-class sets -> (psa_hit array, every member)."""
+    hits_c = np.ascontiguousarray(hits_c)
+    novel_tx = np.ascontiguousarray(novel_tx, dtype=np.uint32)
+    eq_offsets = np.ascontiguousarray(eq_offsets, dtype=np.uint64)
+    eq_members = np.ascontiguousarray(eq_members, dtype=np.uint32)
+    n = len(hits_c)
+    hits = np.zeros(n, dtype=HIT_DTYPE)
+    used = C.c_uint64()
+    _check(lib().psa_expand_compact(_ptr(hits_c), n, _ptr(novel_tx), len(novel_tx), _ptr(eq_offsets), _ptr(eq_members),
+                                    len(eq_offsets) - 1, _ptr(hits), None, 0, C.byref(used)))
+    tx = np.zeros(int(used.value) + 1, np.uint32)
+    _check(lib().psa_expand_compact(_ptr(hits_c), n, _ptr(novel_tx), len(novel_tx), _ptr(eq_offsets), _ptr(eq_members),
+                                    len(eq_offsets) - 1, _ptr(hits), _ptr(tx), len(tx), C.byref(used)))
+    return hits, tx[:int(used.value)]
+
+
 def format_read_data(flag, read_id, eq_class, coverage):
-    """The `{:?}` of `(bool, String, Vec<u32>, usize)` printed at ref src/pseudoaligner.rs:490."""
-    esc = read_id.replace("\\", "\\\\").replace('"', '\\"')
-    return "(%s, \"%s\", [%s], %d)" % ("true" if flag else "false", esc, ", ".join(str(int(t)) for t in eq_class),
-                                      coverage)
+    """The `{:?}` of `(bool, String, Vec<u32>, usize)` printed at ref src/pseudoaligner.rs:490 (the id through
+    psa_debug_str, the escaping the native driver uses)."""
+    raw = read_id.encode() if isinstance(read_id, str) else bytes(read_id)
+    out = C.create_string_buffer(10 * len(raw) + 2)
+    n = lib().psa_debug_str(raw, len(raw), out, len(out))
+    if n < 0:
+        raise ValueError("read id is not valid UTF-8")
+    return "(%s, %s, [%s], %d)" % ("true" if flag else "false", out.raw[:n].decode(), ", ".join(str(int(t)) for t in eq_class),
+                                   coverage)
 
 
 def process_reads_file(fastq_path, index, out_path=None, num_threads=2, batch_reads=0, progress=False):

@@ -17,8 +17,24 @@ void psa_host_free(void* p) { free(p); }
 int psa_mapper_create(psa_index*, uint64_t, psa_mapper** out) { *out = (psa_mapper*)1; return PSA_OK; }
 void psa_mapper_destroy(psa_mapper*) {}
 const char* psa_last_error(void) { return ""; }
+// the stand-in index: class c = {c} for c < 2^20 (so that a compact record's class id expands to one member)
+int psa_index_host_classes(const psa_index*, const uint64_t** eq_offsets, const uint32_t** eq_members, uint64_t* n_eq) {
+    static uint64_t* off = nullptr;
+    static uint32_t* mem = nullptr;
+    const uint64_t n = 1u << 20;
+    if (!off) {
+        off = (uint64_t*)malloc((n + 1) * 8);
+        mem = (uint32_t*)malloc(n * 4);
+        for (uint64_t i = 0; i <= n; i++) off[i] = i;
+        for (uint64_t i = 0; i < n; i++) mem[i] = (uint32_t)i;
+    }
+    *eq_offsets = off; *eq_members = mem; *n_eq = n;
+    return PSA_OK;
+}
 int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
     if (r->format != PSA_READS_ASCII || r->location != PSA_MEM_HOST || !r->read_off || !r->read_len) return PSA_ERR_ARG;
+    if (!(o->flags & PSA_RESULT_COMPACT)) return PSA_ERR_ARG;
+    psa_hit_compact* hc = (psa_hit_compact*)o->hits;
     uint64_t used = 0;
     // PSA_STUB_NTX=n (throughput runs of scripts/host_process_bench.py only): n ids per read instead of one
     const char* e = getenv("PSA_STUB_NTX");
@@ -29,14 +45,18 @@ int psa_mapper_map(psa_mapper*, const psa_read_batch* r, psa_result_batch* o) {
         if (r->read_off[i] + r->read_len[i] > r->data_len) return PSA_ERR_ARG;
         uint32_t sum = 0;
         for (uint32_t j = 0; j < r->read_len[i]; j++) sum += s[j];
-        psa_hit& h = o->hits[i];
-        h.coverage = r->read_len[i];
-        h.n_tx = r->read_len[i] ? ntx : 0;
-        h.tx_off = used;
-        h.eq_id = 0;
-        h.flags = PSA_FLAG_ALIGNED | ((r->read_len[i] && s[0] == 'T') ? PSA_FLAG_MAPPED : 0);
-        for (uint32_t j = 0; j < h.n_tx; j++) {
-            if (used >= o->tx_cap) return PSA_ERR_CAPACITY;
+        // one id (= byte sum) travels as the class id of the stand-in index; several ids, or a sum beyond its classes,
+        // travel as a non-class set; an empty read has the empty set
+        const uint32_t n_tx = r->read_len[i] ? ntx : 0;
+        const uint32_t flags = PSA_FLAG_ALIGNED | ((r->read_len[i] && s[0] == 'T') ? PSA_FLAG_MAPPED : 0);
+        hc[i].cov_flags = r->read_len[i] | (flags << 28);
+        if (n_tx == 1 && !spread && sum < (1u << 20) && (i & 1)) {
+            hc[i].eq_or_n = sum;
+            continue;
+        }
+        hc[i].eq_or_n = 0x80000000u | n_tx;
+        for (uint32_t j = 0; j < n_tx; j++) {
+            if (used >= o->tx_cap) { o->tx_used = used + (r->n_reads - i) * ntx; return PSA_ERR_CAPACITY; }
             // PSA_STUB_SPREAD=1: ids of every decimal length (the formatter's digit paths)
             o->tx_buf[used++] = spread ? (uint32_t)(((uint64_t)(sum + j) * 2654435761u) >> (j % 30)) : sum + 1000 * j;
         }

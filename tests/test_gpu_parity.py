@@ -454,10 +454,16 @@ def test_process_reads_native(pa_for, orc_index_for, fixture_fastq, tmp_path):
     assert st["reads"] == len(want) and st["mapped"] == sum(1 for l in want if l.startswith("(true"))
     st = pkg.process_reads_file(os.path.join(GOLDEN, "small.fq.gz"), pa, str(out), num_threads=1)
     assert out.read_text().splitlines() == want and st["reads"] == len(want)
-    # CRLF line ends, trailing blank lines, a batch size that does not divide the file
+    # CRLF line ends, a batch size that does not divide the file; sequences wrapped over two lines
     crlf = tmp_path / "crlf.fq"
-    crlf.write_bytes(raw.replace(b"\n", b"\r\n") + b"\r\n\r\n")
+    crlf.write_bytes(raw.replace(b"\n", b"\r\n"))
     st = pkg.process_reads_file(str(crlf), pa, str(out), num_threads=2, batch_reads=777)
+    assert out.read_text().splitlines() == want and st["reads"] == len(want)
+    lines_in = raw.split(b"\n")
+    wrapped = tmp_path / "wrapped.fq"
+    wrapped.write_bytes(b"".join(h + b"\n" + s[:25] + b"\n" + s[25:] + b"\n" + p_ + b"\n" + q[:25] + b"\n" + q[25:] + b"\n"
+                                 for h, s, p_, q in zip(*[iter(lines_in[:4 * len(want)])] * 4)))
+    st = pkg.process_reads_file(str(wrapped), pa, str(out), num_threads=3, batch_reads=500)
     assert out.read_text().splitlines() == want and st["reads"] == len(want)
     empty = tmp_path / "empty.fq"
     empty.write_bytes(b"")
@@ -643,4 +649,32 @@ def test_novel_sets(fixture_fasta, monkeypatch, table_cap):
         assert pa.mapper.novel_sets() == [(m, 2 * c) for m, c in want_tab]
     pa.mapper.counts_reset()
     assert pa.mapper.novel_sets() == []
+    pa.close()
+
+
+def test_compact_results(orc_index_for, fixture_fasta):
+    """PSA_RESULT_COMPACT: 8 bytes per read over PCIe (class id | size of a non-class set, coverage, flags) and only the
+    members of the non-class sets; psa_expand_compact rebuilds psa_hit + every member on the host from eq_classes.
+    Host batches (chunked pipeline), packed fixed-stride input, and a device batch."""
+    ix = orc_index_for(20)
+    flat = ix.flat()
+    pa = pkg.Pseudoaligner(flat, device=0, chunk_reads=900)
+    psa = pkg.pseudoaligner
+    rng = np.random.default_rng(23)
+    reads = util.sample_reads(rng, fixture_fasta[1], 5000, 150, p_sub=0.02, mix=(0.7, 0.25, 0.05)) + ["", "ACGT", "A" * 150]
+    want_hits, want_tx, want_counts, _ = _oracle(ix, reads)
+    hc, ntx = pa.mapper.map_ascii(reads, compact=True)
+    assert hc.dtype == psa.HIT_COMPACT_DTYPE and hc.nbytes == 8 * len(reads)
+    n_novel_members = int(want_hits["n_tx"][(want_hits["eq_id"] == 0xFFFFFFFF)].sum())
+    assert len(ntx) == n_novel_members and 0 < len(ntx) < len(want_tx) // 4
+    got_hits, got_tx = psa.expand_compact(hc, ntx, flat["eq_offsets"], flat["eq_members"])
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    assert np.array_equal(pa.mapper.counts(), want_counts)
+    # packed fixed-stride input (DnaString words, map_read's own argument type), compact results
+    fixed = [r for r in reads if len(r) == 150]
+    words, off, lens = orc.pack_reads(fixed)
+    w_hits, w_tx, _, _ = _oracle(ix, fixed)
+    hc2, ntx2 = pa.mapper.map_packed_fixed(words, len(fixed), 150, compact=True)
+    g2, t2 = psa.expand_compact(hc2, ntx2, flat["eq_offsets"], flat["eq_members"])
+    _assert_same(fixed, g2, t2, w_hits, w_tx)
     pa.close()

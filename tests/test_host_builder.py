@@ -182,3 +182,65 @@ def test_reference_bincode_index_reader(tmp_path):
     (tmp_path / "flat").write_bytes(b"PSAIDX1\0" + b"\0" * 200)
     with pytest.raises(RuntimeError):
         host.load_reference_index(tmp_path / "flat", 20)
+
+
+def test_reference_bincode_hand_built_fixture():
+    """tests/golden/ref_bincode_tiny.hex: a byte image written by hand from the bincode 1.3 rules (u64 length
+    prefixes, little-endian fixed-width integers, usize as u64, bool as one byte, fields in declaration order) --
+    pins the FRAMING the reader assumes independently of this file's writer.  (debruijn's field order itself is
+    recalled, not verifiable here: include/psa_host.h.)"""
+    import os
+    import tempfile
+    from conftest import GOLDEN
+    raw = bytearray()
+    for line in open(os.path.join(GOLDEN, "ref_bincode_tiny.hex")):
+        raw += bytes.fromhex(line.split("#")[0])
+    with tempfile.NamedTemporaryFile(suffix=".idx", delete=False) as f:
+        f.write(raw)
+        path = f.name
+    try:
+        flat, stats = host.load_reference_index(path, 5)
+        assert stats["n_nodes"] == 2 and stats["n_kmers"] == 4
+        assert flat["seq_words"].tolist() == [0x1B1AF40000000000]
+        assert flat["node_start"].tolist() == [0, 6] and flat["node_len"].tolist() == [6, 6]
+        assert flat["node_exts"].tolist() == [0, 0] and flat["node_eq"].tolist() == [0, 1]
+        assert flat["eq_offsets"].tolist() == [0, 1, 3] and flat["eq_members"].tolist() == [0, 0, 2]
+        codes = util.unpack_words(flat["seq_words"], 12)
+        assert bytes(b"ACGT"[c] for c in codes) == b"ACGTACGGTTCA"
+        with pytest.raises(RuntimeError):
+            host.load_reference_index(path, 7)          # nodes of 6 bases cannot hold a 7-mer
+    finally:
+        os.unlink(path)
+
+
+def test_index_file_hostile_headers(tmp_path):
+    """psa_graph_load believes a header's counts only as far as the file is long: absurd counts, counts that make
+    n_eq + 1 wrap, and arrays that contradict each other are refused with an error -- never an allocation of the
+    claimed size, never an exception through the C boundary."""
+    import struct
+    rng = np.random.default_rng(11)
+    seqs = util.random_transcriptome(rng, n_genes=4, k=21)
+    codes, off = host.encode_transcripts(seqs)
+    flat, _ = host.build_graph(codes, off, 21)
+    path = tmp_path / "index.psa"
+    host.save_index(flat, path)
+    raw = bytearray(path.read_bytes())
+    # header: magic[8] version k n_nodes n_seq_words n_eq n_eq_members n_kmers n_cycles checksum
+    fields = {"n_nodes": 16, "n_seq_words": 24, "n_eq": 32, "n_eq_members": 40}
+    for name, at in fields.items():
+        for value in (2 ** 64 - 1, 2 ** 62, 2 ** 40, struct.unpack_from("<Q", raw, at)[0] + 1):
+            bad = bytearray(raw)
+            struct.pack_into("<Q", bad, at, value)
+            p = tmp_path / ("bad_%s_%d" % (name, value % 1000))
+            p.write_bytes(bad)
+            with pytest.raises(RuntimeError):
+                host.load_index(p)
+    # a node_eq out of range / a non-monotone eq_offsets with the checksum "fixed" would need the checksum function;
+    # flipping a payload byte is caught by the checksum (test_index_file_round_trip), the semantic checks behind it
+    # are exercised through psa_graph_from_arrays:
+    broken = dict(flat)
+    broken["eq_offsets"] = flat["eq_offsets"].copy()
+    broken["eq_offsets"][1], broken["eq_offsets"][2] = flat["eq_offsets"][2], flat["eq_offsets"][1]
+    if broken["eq_offsets"][1] != broken["eq_offsets"][2]:
+        with pytest.raises(RuntimeError):
+            host.save_index(broken, tmp_path / "x.psa")

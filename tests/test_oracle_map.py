@@ -135,3 +135,24 @@ def test_batch_equals_single(orc_index_for, fixture_fasta):
     assert ev["reads"] == len(reads) and ev["aligned"] == sum(1 for x in res if x[0])
     assert int(counts.sum()) == len(reads)
     assert int(counts[-1]) == sum(1 for x in res if not x[0])
+
+
+def test_c3_driver_prints_what_map_read_returns(orc_index_for, fixture_fastq, tmp_path):
+    """oracle/c3_driver.c (the reference's process_reads shape: mutex per record, bounded channel, serial print):
+    the multiset of lines equals the per-read results, whatever the thread count."""
+    import gzip
+    import os
+    from conftest import GOLDEN
+    ix = orc_index_for(20)
+    fq = tmp_path / "small.fq"
+    with gzip.open(os.path.join(GOLDEN, "small.fq.gz"), "rb") as f:
+        fq.write_bytes(f.read())
+    reads = [s for _, s in fixture_fastq]
+    words, off, lens = orc.pack_reads(reads)
+    hits, tx, _, _ = ix.map_batch(words, off, lens)
+    want = sorted('(%s, "%s", [%s], %d)' % ("true" if fl else "false", rid, ", ".join(map(str, eq)), cov)
+                  for (rid, _), (al, fl, eq, cov) in zip(fixture_fastq, orc.hits_to_tuples(hits, tx)))
+    for threads in (1, 4):
+        out = tmp_path / ("c3_%d.txt" % threads)
+        n, mapped = ix.process_reads_c3(fq, out, threads)
+        assert n == len(reads) and sorted(out.read_text().splitlines()) == want

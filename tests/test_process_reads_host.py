@@ -32,7 +32,7 @@ def _expected(records):
     out = []
     for rid, seq in records:
         flag = "true" if seq[:1] == b"T" else "false"
-        esc = rid.decode().replace("\\", "\\\\").replace('"', '\\"')
+        esc = rid.decode().replace("\\", "\\\\").replace('"', '\\"').replace("\t", "\\t")
         members = "[%d]" % sum(seq) if seq else "[]"
         out.append('(%s, "%s", %s, %d)' % (flag, esc, members, len(seq)))
     return out
@@ -77,8 +77,14 @@ def test_gzip_crlf_blank_tail_and_no_final_newline(stub, tmp_path):
         f.write(_fastq(recs))
     assert _run(stub, gz, tmp_path / "o1", 2, 64)[2] == want
     crlf = tmp_path / "crlf.fq"
-    crlf.write_bytes(_fastq(recs, eol=b"\r\n") + b"\r\n\r\n\n")
+    crlf.write_bytes(_fastq(recs, eol=b"\r\n"))
     assert _run(stub, crlf, tmp_path / "o2", 2, 77)[2] == want
+    # blank lines after the last record: bio's reader takes one for a header without '@' (Error::MissingAt, the
+    # reference panics) -- an error here too, after every record was processed
+    blank = tmp_path / "blank.fq"
+    blank.write_bytes(_fastq(recs, eol=b"\r\n") + b"\r\n\r\n\n")
+    rc, st, lines = _run(stub, blank, tmp_path / "o2b", 2, 77)
+    assert rc == -7 and lines == want
     nonl = tmp_path / "nonl.fq"
     nonl.write_bytes(_fastq(recs)[:-1])                      # last quality line without its newline
     assert _run(stub, nonl, tmp_path / "o3", 1, 50)[2] == want
@@ -100,12 +106,19 @@ def test_malformed_files_are_errors_after_the_good_records(stub, tmp_path):
     rng = np.random.default_rng(4)
     recs = _records(rng, 100)
     good = _fastq(recs)
-    for name, tail in (("truncated", b"@broken\nACGT\n"), ("no_plus", b"@x\nACGT\nACGT\nIIII\n"), ("no_at", b"x\nACGT\n+\nIIII\n")):
+    for name, tail in (("truncated", b"@broken\nACGT\n"), ("no_at", b"x\nACGT\n+\nIIII\n")):
         p = tmp_path / (name + ".fq")
         p.write_bytes(good + tail + (_fastq(recs[:3]) if name != "truncated" else b""))
         rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 30)
         assert rc == -7, name                                 # PSA_ERR_IO (the reference panics, :446)
         assert lines == _expected(recs), name                 # every complete record before the bad one
+    # a record without its '+' line is NOT an error for bio's reader: it takes every line up to the next '+' as
+    # sequence (here: its own quality, the next record's header and sequence) and as many lines as quality
+    p = tmp_path / "no_plus.fq"
+    p.write_bytes(good + b"@x\nACGT\nACGT\nIIII\n" + _fastq(recs[:3]))
+    rc, st, lines = _run(stub, p, tmp_path / "out.txt", 2, 30)
+    swallowed = b"ACGT" + b"ACGT" + b"IIII" + b"@" + recs[0][0] + recs[0][1]
+    assert rc == 0 and lines == _expected(recs + [(b"x", swallowed), recs[2]])
     rc, _, _ = _run(stub, tmp_path / "missing.fq", tmp_path / "out.txt")
     assert rc == -7
 
@@ -192,3 +205,61 @@ def test_numbers_of_every_decimal_length(stub, tmp_path, monkeypatch):
                                              ", ".join(str(x) for x in ids), len(seq)))
     assert lines == want
     assert lens >= set(range(3, 11))
+
+
+def test_records_are_cut_as_bio_cuts_them(stub, tmp_path):
+    """bio::io::fastq::Reader::read (bio 1.5, the reader behind ref src/pseudoaligner.rs:421-447): the id ends at the
+    first SPACE only (a tab-tagged header as `samtools fastq -T` writes keeps its tags), the sequence line loses ALL
+    trailing white space (a trailing blank or tab is not a base), sequences may be wrapped over several lines with
+    as many quality lines, the separator line may repeat the id."""
+    recs = [(b"r1\tBC:Z:ACGT\tXX:i:3", b"TACGTACG"), (b"r2", b"ACGT"), (b"r3", b"GGGGCCCC"), (b"r4", b"T" * 70), (b"r5", b"ACGTN")]
+    text = (b"@r1\tBC:Z:ACGT\tXX:i:3 a comment\twith a tab\nTACGTACG \t\n+\nIIIIIIII\n"
+            b"@r2  two spaces\nACGT\t\r\n+r2\nIIII\n"
+            b"@r3\nGGGG\nCCCC\n+\nIIII\nIIII\n"                        # wrapped: two sequence lines, two quality lines
+            + b"@r4\n" + b"\n".join([b"T" * 10] * 7) + b"\n+\n" + b"\n".join([b"I" * 10] * 7) + b"\n"
+            + b"@r5\nACGTN\n+\n@@@@@\n")                                   # a quality line that starts with '@'
+    p = tmp_path / "bio.fq"
+    p.write_bytes(text)
+    for threads, batch in ((1, 0), (3, 2), (2, 1)):
+        rc, st, lines = _run(stub, p, tmp_path / "out.txt", threads, batch)
+        assert rc == 0 and lines == _expected(recs), (threads, batch, lines)
+    # wrapped records mixed into a long four-line file, across block boundaries
+    rng = np.random.default_rng(9)
+    many = _records(rng, 600, lmin=20, lmax=90)
+    parts = []
+    for i, (rid, seq) in enumerate(many):
+        if i % 7 == 3:
+            h = len(seq) // 2
+            parts.append(b"@" + rid + b"\n" + seq[:h] + b"\n" + seq[h:] + b"\n+\n" + b"I" * h + b"\n" + b"I" * (len(seq) - h) + b"\n")
+        else:
+            parts.append(_fastq([(rid, seq)]))
+    p2 = tmp_path / "mixed.fq"
+    p2.write_bytes(b"".join(parts))
+    for threads, batch in ((2, 50), (4, 0), (1, 3)):
+        rc, st, lines = _run(stub, p2, tmp_path / "out.txt", threads, batch)
+        assert rc == 0 and lines == _expected(many), (threads, batch)
+    # errors of bio's reader: no quality at all, an empty sequence, a header that is not UTF-8
+    for name, tail in (("no_quality", b"@x\nACGT\n+\n\n"), ("empty_record", b"@x\n+\n"), ("bad_utf8", b"@x\xff\nACGT\n+\nIIII\n")):
+        q = tmp_path / (name + ".fq")
+        q.write_bytes(_fastq(recs[1:2]) + tail)
+        rc, st, lines = _run(stub, q, tmp_path / "out.txt", 2, 0)
+        assert rc == -7 and lines == _expected(recs[1:2]), name
+
+
+def test_debug_str_follows_rust(stub):
+    """`{:?}` of the id: Rust's escape_debug -- ASCII exact, non-ASCII printable code points as they are, C1 controls,
+    soft hyphen, zero-width and combining code points as \\u{..}."""
+    stub.psa_debug_str.restype = C.c_int64
+    stub.psa_debug_str.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64]
+
+    def dbg(b):
+        out = C.create_string_buffer(10 * len(b) + 2)
+        n = stub.psa_debug_str(b, len(b), out, len(out))
+        return out.raw[:n].decode() if n >= 0 else None
+
+    assert dbg(b"abc") == '"abc"' and dbg(b"") == '""'
+    assert dbg(b"a'b\"c\\d") == '"a\'b\\"c\\\\d"'                    # ' is not escaped in a str
+    assert dbg(b"\x00\t\n\r\x1b\x7f") == '"\\0\\t\\n\\r\\u{1b}\\u{7f}"'
+    assert dbg("naïve-ß-日本".encode()) == '"naïve-ß-日本"'
+    assert dbg("a\u00adb\u0085c\u200bd\u0301e\ufefff".encode()) == '"a\\u{ad}b\\u{85}c\\u{200b}d\\u{301}e\\u{feff}f"'
+    assert dbg(b"\xff\xfe") is None and dbg(b"\xc3") is None                # not UTF-8: the reference panics
