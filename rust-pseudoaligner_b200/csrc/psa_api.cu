@@ -105,6 +105,7 @@ struct psa_index {
     std::vector<uint32_t> h_eq_mem;
     psa_index_info info{};
     int kw = 1;
+    int sms = 148;   // multiprocessors of the device
 };
 
 static uint32_t bits_for(uint64_t max_value) {  // bits needed to store 0..max_value
@@ -297,6 +298,8 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     if (!ix) return fail(PSA_ERR_NOMEM, "out of memory");
     ix->device = device;
     ix->kw = d->k <= 32 ? 1 : 2;
+    cudaDeviceGetAttribute(&ix->sms, cudaDevAttrMultiProcessorCount, device);
+    if (ix->sms < 1) ix->sms = 148;
     auto bail = [&](int rc) {
         psa_index_destroy(ix);
         return rc;
@@ -510,6 +513,7 @@ struct psa_mapper {
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
+    uint32_t reseed_first = 0xFFFFFFFFu;  // re-seed positions a thread of the FIRST pass tries (PSA_RESEED_FIRST); the second pass allows max(fast_probes, 8)
     bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
     bool fast_kernel_lanes = false;  // PSA_FAST_KERNEL=lanes: the thread-per-read step as the lane state machine over
                                      // shared-memory pools (k_map_lanes) instead of one blocking call per read (k_map_thread)
@@ -697,6 +701,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     m->fast_probes = (ix->d.k + 2) / 3 + 2;
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("PSA_RESEED_FIRST")) m->reseed_first = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
     if (const char* e = getenv("PSA_FAST_KERNEL")) m->fast_kernel_lanes = strcmp(e, "lanes") == 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
@@ -909,7 +914,11 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 p.lane_words = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nw, 1), kLaneMaxWords);
             }
             int lrc = PSA_OK;
+            const uint32_t reseed_long = std::max(m->fast_probes, (uint32_t)kReseedProbes);
             auto fast = [&](bool hint) {
+                // first pass: a read that has to search for a new seed mid-way is handed to the second pass (when there
+                // is one), so that the other 31 reads of its warp do not wait for the search; second pass: long budget
+                p.reseed_probes = (!hint && m->scan_width && !m->fast_kernel_lanes) ? std::min(m->reseed_first, reseed_long) : reseed_long;
                 if (m->fast_kernel_lanes) lrc = launch_map_lanes<EV>(m, st, p, hint);
                 else launch_map_thread<EV>(m, st, p, hint);
             };

@@ -395,7 +395,8 @@ struct MapParams {
     uint4* seeded;
     unsigned long long* seeded_count;
     uint4* seeded_ev;             // event counting only: {lookups, levels, hits, verifs} of that search
-    uint32_t max_probes;          // k_map_lanes: seed positions one thread tries per search
+    uint32_t max_probes;          // seed positions one thread tries in a read's first search
+    uint32_t reseed_probes;       // k_map_thread: ... and in a re-seed search (first pass: small, the read is redone by the second pass)
     uint32_t max_small;           // k_map_lanes: largest smallest-class one thread intersects
     uint32_t* status;             // bit0: novel buffer overflow, bit1: spill pool overflow
     unsigned long long* events;   // 3 x psa_events layout ([0] k_map_lanes, [1] k_map, [2] k_seed_scan), or nullptr
@@ -1175,12 +1176,14 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
             const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
             const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
             ThreadResult res = map_read_thread<KW, false>(ix, PLoad{p.reads.words + wo}, (uint32_t)r, L, p.allowed_mismatches,
-                                                          p.max_probes, p.max_small, sink, p.novel != nullptr, nullptr, nullptr);
+                                                          p.max_probes, p.reseed_probes, p.max_small, sink, p.novel != nullptr, nullptr, nullptr);
             if (!res.deferred) {
                 sink.result((uint32_t)r, res.hit, res.count_slot);
                 if (res.novel_overflow) sink.novel_overflow();
             } else if (res.why == 0 && p.scan_list != nullptr) {
                 p.scan_list[atomicAdd(p.scan_count, 1ULL)] = (uint32_t)r;
+            } else if (res.why == 1 && p.seeded != nullptr) {
+                p.seeded[atomicAdd(p.seeded_count, 1ULL)] = make_uint4((uint32_t)r, kNone, 0u, 0u);
             } else {
                 p.list[atomicAdd(p.list_count, 1ULL)] = (uint32_t)r;
             }
@@ -1202,20 +1205,22 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
         uint32_t L = 0, n_tx = 0, aligned = 0;
         if (live) {
             uint32_t hint[3];
+            bool hinted = false;
             if (HINT) {
                 const uint4 e = p.seeded[it];
                 r = e.x;
                 hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
+                hinted = e.y != kNone;   // (kNone: a read the first pass gave up at a re-seed search -- no answer to reuse)
                 if (EV) sev = p.seeded_ev[it];
             }
             const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
             L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
             ThreadResult res = TILE ? map_read_thread<KW, EV>(ix, PLoad{my_words}, (uint32_t)r, L, p.allowed_mismatches, p.max_probes,
-                                                              p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
-                                                              HINT ? hint : nullptr)
+                                                              p.reseed_probes, p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              hinted ? hint : nullptr)
                                     : map_read_thread<KW, EV>(ix, PLoad{p.reads.words + wo}, (uint32_t)r, L, p.allowed_mismatches, p.max_probes,
-                                                              p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
-                                                              HINT ? hint : nullptr);
+                                                              p.reseed_probes, p.max_small, sink, p.novel != nullptr, EV ? &ev : nullptr,
+                                                              hinted ? hint : nullptr);
             defer = res.deferred;
             why = res.why;
             if (EV && defer && p.events) atomicAdd(p.events + 36 + res.why, 1ULL);
@@ -1240,7 +1245,20 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
             at = __shfl_sync(kFull, at, __ffs(bs) - 1);
             if (to_scan) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = (uint32_t)r;
         }
-        const bool to_coop = defer && !to_scan;
+        // a re-seed search beyond the first pass's budget: the second pass redoes the read with the long one
+        const bool to_retry = defer && !HINT && why == 1 && p.seeded != nullptr;
+        const unsigned br = __ballot_sync(kFull, to_retry);
+        if (br) {
+            unsigned long long at = 0;
+            if (lane == (unsigned)(__ffs(br) - 1)) at = atomicAdd(p.seeded_count, (unsigned long long)__popc(br));
+            at = __shfl_sync(kFull, at, __ffs(br) - 1);
+            if (to_retry) {
+                const unsigned long long slot = at + __popc(br & ((1u << lane) - 1));
+                p.seeded[slot] = make_uint4((uint32_t)r, kNone, 0u, 0u);
+                if (EV) p.seeded_ev[slot] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        const bool to_coop = defer && !to_scan && !to_retry;
         const unsigned bc = __ballot_sync(kFull, to_coop);
         if (bc) {
             unsigned long long at = 0;

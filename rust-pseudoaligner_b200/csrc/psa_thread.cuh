@@ -16,6 +16,7 @@ struct ThreadCtx {
     const DevIndex& ix;
     RD rd;
     uint32_t max_probes;
+    uint32_t reseed_probes;  // positions a re-seed search (ref :293) may try before the read is given up
     ClassAcc cls;
     uint32_t first_node;   // the node that brought the first class (its window is fetched only when a second class shows up)
     bool defer;
@@ -26,8 +27,8 @@ struct ThreadCtx {
     uint32_t hint_pos, hint_node, hint_off;
     ThreadEvents ev;
 
-    PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_)
-        : ix(ix_), rd(rd_), max_probes(max_probes_), first_node(kNone), defer(false), why(0), seeded(false),
+    PSA_HD ThreadCtx(const DevIndex& ix_, RD rd_, uint32_t max_probes_, uint32_t reseed_probes_)
+        : ix(ix_), rd(rd_), max_probes(max_probes_), reseed_probes(reseed_probes_), first_node(kNone), defer(false), why(0), seeded(false),
           has_hint(false), hint_pos(0), hint_node(0), hint_off(0), ev{} {
         cls.init();
     }
@@ -53,8 +54,9 @@ struct ThreadCtx {
                 kmer_pos = start + kSeedStride * ((last - start) / kSeedStride + 1);  // where the loop at :92-111 stops
                 return false;
             }
-            // re-seed searches (ref :293) are short as a rule and have no scan kernel of their own: allow them more
-            if (probes >= (seeded ? (max_probes > kReseedProbes ? max_probes : kReseedProbes) : max_probes)) {
+            // re-seed searches (ref :293) have no scan kernel of their own: the first pass may hand the read to the
+            // second one early (small reseed_probes: its warp is not held up by the search), which allows them more
+            if (probes >= (seeded ? reseed_probes : max_probes)) {
                 defer = true;
                 why = seeded ? 1 : 0;
                 kmer_pos = last + 1;  // keeps map_read_nodes out of the forward loop
@@ -150,14 +152,14 @@ struct ThreadResult {
 // for `count` members of a set that is no visited class (nullptr: no room).
 template <int KW, bool EV, class Sink, class RD>
 PSA_HD ThreadResult map_read_thread(const DevIndex& ix, RD words, uint32_t r, uint32_t L, uint32_t allowed,
-                                    uint32_t max_probes, uint32_t max_small, Sink& sink, bool want_members,
+                                    uint32_t max_probes, uint32_t reseed_probes, uint32_t max_small, Sink& sink, bool want_members,
                                     ThreadEvents* ev_out, const uint32_t* hint = nullptr /* pos, node, off */) {
     ThreadResult res;
     res.hit.coverage = 0; res.hit.n_tx = 0; res.hit.tx_off = 0; res.hit.eq_id = kNone; res.hit.flags = 0;
     res.count_slot = ix.n_eq + 1;
     res.deferred = false;
     res.novel_overflow = false;
-    ThreadCtx<KW, EV, RD> w(ix, words, max_probes);
+    ThreadCtx<KW, EV, RD> w(ix, words, max_probes, reseed_probes);
     if (hint) {
         w.has_hint = true;
         w.hint_pos = hint[0]; w.hint_node = hint[1]; w.hint_off = hint[2];

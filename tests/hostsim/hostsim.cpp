@@ -386,8 +386,16 @@ uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uin
     for (uint64_t i = 0; i < n; i++) {
         HostSink sink{&hits[i], {}};
         ThreadResult r;
-        if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, max_small, sink, true, nullptr);
-        else r = map_read_thread<2, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, max_small, sink, true, nullptr);
+        // first pass: a small re-seed budget (0, 1 or 2 positions, varied with max_probes so that the tests see all three);
+        // a read that runs out of it is redone by the second pass with the long budget, as the kernels do
+        const uint32_t reseed1 = max_probes % 3, reseed2 = max_probes > kReseedProbes ? max_probes : kReseedProbes;
+        for (int pass = 0; pass < 2; pass++) {
+            sink.novel_buf.clear();
+            const uint32_t rs = pass == 0 ? reseed1 : reseed2;
+            if (ix->kw == 1) r = map_read_thread<1, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, rs, max_small, sink, true, nullptr);
+            else r = map_read_thread<2, false>(ix->d, PLoad{words + read_off[i]}, (uint32_t)i, read_len[i], allowed, max_probes, rs, max_small, sink, true, nullptr);
+            if (!(r.deferred && r.why == 1)) break;
+        }
         if (r.deferred) {
             nd++;
             if (ix->kw == 1) map_one<1>(ix, words + read_off[i], read_len[i], allowed, hits[i], tx);
