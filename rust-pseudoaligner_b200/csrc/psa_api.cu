@@ -501,7 +501,9 @@ struct psa_mapper {
     psa_index* ix = nullptr;
     uint64_t chunk_reads = 0;
     uint32_t allowed = PSA_DEFAULT_ALLOWED_MISMATCHES;
-    cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr;
+    cudaStream_t st = nullptr, st_h2d = nullptr, st_d2h = nullptr, st_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // k_map's first launch runs on st_aux beside k_seed_scan + second pass
+    bool overlap_coop = true;   // PSA_OVERLAP_COOP=0: one k_map launch after everything else, on the mapper's stream
     DevBuf counts, counts_backup, status, novel_cursor, events, novel, spill, pool, running;
     DevBuf hits_full;   // compact results on device batches: the kernels' 24-byte working records
     DevBuf ntab, ntab_backup, ncur_backup, npool, ncur, nlist, nslot;   // the novel-set table (NovelTable), this batch's list of novel reads and their entries
@@ -513,7 +515,8 @@ struct psa_mapper {
     uint32_t group = 8;  // lanes cooperating on one read (8, 16 or 32)
     uint32_t fast_probes = 10;  // 0: every read goes to the cooperative kernel; default set from k at creation
     uint32_t fast_max_small = 32;
-    uint32_t reseed_first = 0xFFFFFFFFu;  // re-seed positions a thread of the FIRST pass tries (PSA_RESEED_FIRST); the second pass allows max(fast_probes, 8)
+    uint32_t reseed_first = 2;  // re-seed positions a thread of the FIRST pass tries (PSA_RESEED_FIRST) before it leaves the read to the second pass,
+                                // which allows max(fast_probes, 8): 2.36 vs 2.39 ms per batch on B200 (profiles/r2_exp_walk_kernel.md)
     bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
     bool fast_kernel_lanes = false;  // PSA_FAST_KERNEL=lanes: the thread-per-read step as the lane state machine over
                                      // shared-memory pools (k_map_lanes) instead of one blocking call per read (k_map_thread)
@@ -666,6 +669,9 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->st_aux, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming);
     for (int s = 0; s < kSlots && e == cudaSuccess; s++) {
         Slot& S = m->slot[s];
         cudaEvent_t* evs[5] = {&S.in_ready, &S.in_free, &S.comp_done, &S.meta_done, &S.out_free};
@@ -701,6 +707,7 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     m->fast_probes = (ix->d.k + 2) / 3 + 2;
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
+    if (const char* e = getenv("PSA_OVERLAP_COOP")) m->overlap_coop = atoi(e) != 0;
     if (const char* e = getenv("PSA_RESEED_FIRST")) m->reseed_first = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
     if (const char* e = getenv("PSA_FAST_KERNEL")) m->fast_kernel_lanes = strcmp(e, "lanes") == 0;
@@ -722,6 +729,7 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st) cudaStreamSynchronize(m->st);
     if (m->st_h2d) cudaStreamSynchronize(m->st_h2d);
     if (m->st_d2h) cudaStreamSynchronize(m->st_d2h);
+    if (m->st_aux) cudaStreamSynchronize(m->st_aux);
     DevBuf* bufs[] = {&m->counts, &m->counts_backup, &m->status, &m->novel_cursor, &m->events, &m->novel, &m->spill, &m->pool,
                       &m->running, &m->hits_full, &m->ntab, &m->ntab_backup, &m->ncur_backup, &m->npool, &m->ncur, &m->nlist, &m->nslot, &m->words, &m->woff, &m->nwords, &m->dst_off, &m->scan_tmp, &m->meta, &m->deferred, &m->scan_list, &m->seeded, &m->seeded_ev};
     for (auto b : bufs) b->release();
@@ -737,6 +745,9 @@ extern "C" void psa_mapper_destroy(psa_mapper* m) {
     if (m->st) cudaStreamDestroy(m->st);
     if (m->st_h2d) cudaStreamDestroy(m->st_h2d);
     if (m->st_d2h) cudaStreamDestroy(m->st_d2h);
+    if (m->st_aux) cudaStreamDestroy(m->st_aux);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
 }
 
@@ -853,7 +864,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
     if ((rc = m->nlist.ensure((n + 1) * 4)) || (rc = m->nslot.ensure((n + 1) * 4))) return rc;
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 128, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's, [8] novel reads listed
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 128, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's, [8] novel reads listed, [9] list length when k_map's first launch began, [10] claim counter of its second launch
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -874,16 +885,17 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
     p.status = m->status.as<uint32_t>();
     p.events = EV ? m->events.as<unsigned long long>() : nullptr;
     const int grid = mapper_grid(m);
-    auto timed = [&](int which, auto&& launch) -> int {
+    auto timed = [&](int which, auto&& launch, cudaStream_t on = nullptr) -> int {
+        if (!on) on = st;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (m->profiling) {
             CU(cudaEventCreate(&e0));
             CU(cudaEventCreate(&e1));
-            CU(cudaEventRecord(e0, st));
+            CU(cudaEventRecord(e0, on));
         }
         launch();
         if (m->profiling) {
-            CU(cudaEventRecord(e1, st));
+            CU(cudaEventRecord(e1, on));
             m->prof_events[which].emplace_back(e0, e1);
         }
         m->launches++;
@@ -924,8 +936,24 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             };
             if ((rc = timed(0, [&]() { fast(false); })) || (rc = lrc)) return rc;
             if (m->scan_width) {
+                // The reads the first pass handed to k_map are few and slow (a latency-bound tail): they are mapped on a
+                // second stream while k_seed_scan and the second pass run; what the second pass hands over follows below.
+                if (m->overlap_coop) {
+                    unsigned long long* cur = m->novel_cursor.as<unsigned long long>();
+                    CU(cudaEventRecord(m->ev_fork, st));
+                    CU(cudaStreamWaitEvent(m->st_aux, m->ev_fork, 0));
+                    k_list_snapshot<<<1, 32, 0, m->st_aux>>>(p.list_count, cur + 9);
+                    MapParams p1 = p;
+                    p1.list_end = cur + 9;
+                    if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, m->st_aux, p1); }, m->st_aux))) return rc;
+                    CU(cudaEventRecord(m->ev_join, m->st_aux));
+                    m->launches++;
+                    p.list_first = cur + 9;
+                    p.work_cursor = cur + 10;
+                }
                 if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
                 if ((rc = timed(0, [&]() { fast(true); })) || (rc = lrc)) return rc;
+                if (m->overlap_coop) CU(cudaStreamWaitEvent(st, m->ev_join, 0));
             }
         }
         if ((rc = timed(1, [&]() { launch_map<EV>(m, grid, st, p); }))) return rc;

@@ -386,6 +386,9 @@ struct MapParams {
     uint32_t* list;
     unsigned long long* list_count;
     unsigned long long* work_cursor;  // k_map over the list: next entry to claim (zeroed per batch), or nullptr
+    // k_map in two launches (the first one overlaps k_seed_scan and the second pass of the thread kernel on another stream):
+    const unsigned long long* list_first;  // first entry of this launch (nullptr: 0)
+    const unsigned long long* list_end;    // one past its last entry (nullptr: *list_count)
     unsigned long long* lane_cursor;  // k_map_lanes: [0] next read of the first pass, [1] next entry of the seeded list
     uint32_t lane_words;              // k_map_lanes: words of a lane's shared-memory read slot
     // reads whose FIRST seed search was too long for one thread: k_map_lanes -> k_seed_scan
@@ -667,6 +670,11 @@ __device__ __forceinline__ uint32_t intersect_pass(WarpCtx<KW, EV, G>& w, uint32
     return count;
 }
 
+// the length the hand-over list has now (k_map's first launch maps exactly these entries while the list keeps growing)
+__global__ void k_list_snapshot(const unsigned long long* list_count, unsigned long long* out) {
+    if (threadIdx.x == 0) *out = *list_count;
+}
+
 template <int KW, bool EV, int G>
 __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix, const __grid_constant__ MapParams p) {
     const uint64_t gid = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) / G;
@@ -674,7 +682,8 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     LaneEvents tot{};
     uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
 
-    const uint64_t n_todo = p.list ? (uint64_t)*p.list_count : p.reads.n;
+    const uint64_t n_todo = p.list ? (uint64_t)(p.list_end ? *p.list_end : *p.list_count) : p.reads.n;
+    const uint64_t first = p.list && p.list_first ? (uint64_t)*p.list_first : 0;
     // The handed-over reads differ widely in cost (tens to hundreds of dependent loads): groups claim them one
     // at a time from a counter instead of striding over the list, so that no group is left with several slow ones.
     const bool dynamic = p.list != nullptr && p.work_cursor != nullptr;
@@ -682,9 +691,9 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     auto claim = [&]() -> uint64_t {
         unsigned long long at = 0;
         if (wg.lane == 0) at = atomicAdd(p.work_cursor, 1ULL);
-        return wg.shfl(at, 0);
+        return first + wg.shfl(at, 0);
     };
-    for (uint64_t it = dynamic ? claim() : gid; it < n_todo; it = dynamic ? claim() : it + ngroups) {
+    for (uint64_t it = dynamic ? claim() : first + gid; it < n_todo; it = dynamic ? claim() : it + ngroups) {
         const uint64_t r = p.list ? (uint64_t)p.list[it] : it;
         const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
         const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
