@@ -15,11 +15,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -28,6 +30,8 @@
 #include <vector>
 
 #include "../../include/psa.h"
+#include "psa_fastq.cuh"
+#include "psa_fastq.h"
 
 namespace {
 
@@ -427,6 +431,14 @@ struct OutFile {
     FILE* f = nullptr;
     int fd = -1;          // >= 0: positional writes
     uint64_t pos = 0;
+    // Regular files that can be mapped are written through ONE shared mapping of the region the output is expected to
+    // fill: write(2) holds the inode's lock for the whole call, so the pwrites of many threads to one file run one after
+    // the other (tmpfs: ~2 GB/s in total), while stores into a mapping fault their pages in independently.  The file is
+    // extended to the end of the window first and cut to its real size at the end; output beyond the window is pwritten.
+    bool can_map = false;
+    uint8_t* map_base = nullptr;
+    uint64_t map_off = 0, map_len = 0;
+    uint64_t grown_to = 0;   // length the file was extended to (0: not extended)
     void attach(FILE* file) {
         f = file;
         fflush(f);
@@ -438,8 +450,29 @@ struct OutFile {
             if (at >= 0) {
                 fd = d;
                 pos = (uint64_t)at;
+                const char* e = getenv("PSA_OUT_MMAP");
+                can_map = (fl & O_ACCMODE) == O_RDWR && !(e && atoi(e) == 0);
             }
         }
+    }
+    // maps [pos, pos + expect) (page-rounded); harmless when it fails: put() falls back to pwrite
+    void open_window(uint64_t expect) {
+        if (!can_map || map_base) return;
+        struct stat st;
+        if (fstat(fd, &st) != 0) return;
+        map_off = pos & ~4095ull;
+        const uint64_t len = ((pos - map_off) + std::max<uint64_t>(expect, 1ull << 24) + 4095) & ~4095ull;
+        if ((uint64_t)st.st_size < map_off + len) {
+            if (ftruncate(fd, (off_t)(map_off + len)) != 0) return;
+            grown_to = map_off + len;
+        }
+        void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_off);
+        if (m == MAP_FAILED) {
+            can_map = false;
+            return;
+        }
+        map_base = (uint8_t*)m;
+        map_len = len;
     }
     static bool write_at(int fd, const char* p, size_t n, uint64_t at) {
         while (n) {
@@ -449,8 +482,34 @@ struct OutFile {
         }
         return true;
     }
-    void finish() {
-        if (fd >= 0) lseek(fd, (off_t)pos, SEEK_SET);  // stdio continues after what was written
+    // [at, at + n) of the file = p[0, n)
+    bool put(const char* p, size_t n, uint64_t at) const {
+        if (!n) return true;
+        if (map_base && at >= map_off && at + n <= map_off + map_len) {
+            uint8_t* dst = map_base + (at - map_off);
+#ifdef MADV_POPULATE_WRITE
+            {   // fault the pages in with one call instead of one trap per page (Linux 5.14+; ignored when unsupported)
+                const uintptr_t a0 = (uintptr_t)dst & ~(uintptr_t)4095, a1 = ((uintptr_t)dst + n + 4095) & ~(uintptr_t)4095;
+                (void)madvise((void*)a0, a1 - a0, MADV_POPULATE_WRITE);
+            }
+#endif
+            memcpy(dst, p, n);
+            return true;
+        }
+        return write_at(fd, p, n, at);
+    }
+    bool finish() {
+        bool ok = true;
+        if (map_base) {
+            munmap(map_base, map_len);
+            map_base = nullptr;
+        }
+        if (fd >= 0) {
+            if (grown_to > pos) ok = ftruncate(fd, (off_t)pos) == 0;
+            grown_to = 0;
+            lseek(fd, (off_t)pos, SEEK_SET);  // stdio continues after what was written
+        }
+        return ok;
     }
 };
 
@@ -503,6 +562,255 @@ int parse_record(uint8_t* x, const LineIndex& L, uint64_t li, bool eof, uint64_t
     return REC_OK;
 }
 
+
+// ---- the block pipeline with the text work on the device (psa_fastq.h) ------------------------------------------
+// The file is cut into fixed byte ranges ("blocks") with no regard to record boundaries.  A lane thread reads block i
+// plus a tail that reaches into block i + 1 straight into its lane's pinned buffer (several threads pread slices of
+// it), the device indexes the newlines, cuts the records whose HEADER starts inside the block (their remaining lines may
+// lie in the tail), maps them and formats their lines, and the lane writes the text at the block's place in the output.
+// Two numbers chain the blocks: the count of newlines before a block -- line number mod 4 tells headers from the other
+// lines as long as every record so far was four lines -- and the output offset.  Both are known early (right after the
+// newline index resp. the formatting), so the lanes overlap almost completely.  The first block with anything but plain
+// four-line ASCII records ends this pipeline: the blocks before it are committed, and the caller's host parser resumes at
+// the first record that was not.
+struct FastState {
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next_block = 0;      // next block to hand to a lane
+    uint64_t idx_turn = 0;        // block whose newline count is folded in next
+    uint64_t lines_before = 0, reads_before = 0;   // ... before block idx_turn
+    uint64_t commit_turn = 0;     // block that is committed (output offset assigned, counters added) next
+    uint64_t out_pos = 0, resume_off = 0;
+    uint64_t n_reads = 0, n_mapped = 0, n_aligned = 0, next_tick = 1000000;
+    int64_t stop_block = -1;      // first block that is not plain (or failed): nothing from it on is committed
+    int rc = PSA_OK;
+    double busy_reader = 0, busy_mapper = 0, busy_writer = 0;
+};
+struct FastConfig {
+    uint64_t block_bytes, tail_bytes;
+    uint32_t lanes, io_threads, write_threads;   // lane threads; pread threads and writer threads of each lane
+    bool verbose;
+};
+// runs `fn(t)` on `threads` threads (the calling one included)
+template <class F>
+void parallel_for(uint32_t threads, F&& fn) {
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < threads; t++) th.emplace_back([&fn, t]() { fn(t); });
+    fn(0);
+    for (auto& x : th) x.join();
+}
+// Returns true when the whole file went through; false: the caller continues at st.resume_off (st.rc tells errors).
+bool fast_blocks(psa_index* index, ByteSource& in, OutFile& of, FILE* out, int progress, const FastConfig& cfg, FastState& st) {
+    const uint64_t S = in.size;
+    bool needs_nl = false;   // the file does not end in '\n': bio reads the last line all the same
+    if (S) {
+        uint8_t lastb = 0;
+        if (in.read_at(&lastb, 1, S - 1) != 1) {
+            st.rc = PSA_ERR_IO;
+            return false;
+        }
+        needs_nl = lastb != '\n';
+    }
+    const uint64_t S1 = S + (needs_nl ? 1 : 0);   // size with the virtual last newline
+    const uint64_t B = cfg.block_bytes, T = cfg.tail_bytes;
+    const uint64_t n_blocks = (S1 + B - 1) / B;
+    st.out_pos = of.pos;
+    if (!n_blocks) return true;
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double>(b - a).count();
+    };
+    const auto tc0 = now();
+    const uint32_t lanes = (uint32_t)std::min<uint64_t>(cfg.lanes, n_blocks);
+    std::vector<psa_fq_lane*> lane(lanes, nullptr);
+    std::vector<int> lane_rc(lanes, PSA_OK);
+    parallel_for(lanes, [&](uint32_t a) { lane_rc[a] = psa_fq_lane_create(index, B, T, &lane[a]); });   // (pinning the buffers is the slow part)
+    for (uint32_t a = 0; a < lanes; a++)
+        if (lane_rc[a]) {
+            for (auto l : lane)
+                if (l) psa_fq_lane_destroy(l);
+            st.rc = lane_rc[a];
+            return false;
+        }
+    if (cfg.verbose)
+        fprintf(stderr, "psa: block pipeline: %llu blocks of %.1f MB (+ %.2f MB tail), %u lanes x %u I/O threads, lanes ready in %.1f ms, output %s\n",
+                (unsigned long long)n_blocks, B / 1e6, T / 1e6, lanes, cfg.io_threads, 1e3 * secs(tc0, now()),
+                of.fd < 0 ? "serial" : of.map_base ? "mapped" : "pwrite");
+    auto lane_main = [&](uint32_t a) {
+        psa_fq_lane* L = lane[a];
+        uint8_t* text = psa_fq_lane_text(L);
+        for (;;) {
+            uint64_t i;
+            {
+                std::unique_lock<std::mutex> lk(st.mu);
+                if (st.stop_block >= 0 || st.next_block >= n_blocks) return;
+                i = st.next_block++;
+            }
+            // ---- read block i and its tail
+            const auto t0 = now();
+            const uint64_t lo = i * B, hi = std::min(S, lo + B + T);
+            uint64_t len = hi - lo;
+            std::vector<uint64_t> short_by(cfg.io_threads, 0);
+            parallel_for(cfg.io_threads, [&](uint32_t t) {
+                const uint64_t a0 = len * t / cfg.io_threads, a1 = len * (t + 1) / cfg.io_threads;
+                if (a1 > a0) short_by[t] = (a1 - a0) - in.read_at(text + a0, a1 - a0, lo + a0);
+            });
+            bool io_fail = false;
+            for (auto sb : short_by) io_fail |= sb != 0;   // (the file shrank under us)
+            if (hi == S && needs_nl) text[len++] = '\n';
+            const uint64_t own = std::min(B, S1 - lo);     // (== len in the last block, a multiple of 4096 elsewhere)
+            const bool last = i + 1 == n_blocks;
+            const auto t1 = now();
+            // ---- newline index on the device
+            uint64_t nl_own = 0, nl_total = 0;
+            int rc = io_fail ? PSA_ERR_IO : psa_fq_lane_index(L, len, last ? len : own, &nl_own, &nl_total);
+            const auto t2 = now();
+            // ---- my turn in the line chain
+            psa::FqOwned ow{};
+            uint64_t reads_before = 0;
+            bool plain = true;
+            {
+                std::unique_lock<std::mutex> lk(st.mu);
+                st.cv.wait(lk, [&]() { return st.idx_turn == i; });
+                st.busy_reader += secs(t0, t1);
+                ow = psa::fq_owned_records(i, st.lines_before, nl_own);
+                if (!rc) {
+                    // a header right at the end of the file is no record
+                    if (last && ow.n_rec && ow.j0 + 4 * (int64_t)(ow.n_rec - 1) == (int64_t)nl_total - 1) ow.n_rec--;
+                    // every owned record needs its four lines inside block + tail; the file must end with a whole record
+                    if (ow.n_rec && ow.j0 + 4 * (int64_t)(ow.n_rec - 1) + 4 > (int64_t)nl_total - 1) plain = false;
+                    if (last && (st.lines_before + nl_total) % 4 != 0) plain = false;
+                }
+                reads_before = st.reads_before;
+                st.lines_before += nl_own;
+                st.reads_before += plain ? ow.n_rec : 0;
+                st.idx_turn++;
+                st.cv.notify_all();
+            }
+            const auto t2w = now();
+            // ---- cut, map, format
+            psa_fq_result res{};
+            res.plain = plain ? 1 : 0;
+            uint64_t tick_at[PSA_FQ_MAX_TICKS];
+            uint32_t n_ticks = 0;
+            if (!rc && plain) {
+                if (progress)
+                    for (uint64_t t = reads_before / 1000000 + 1; t * 1000000 <= reads_before + ow.n_rec && n_ticks < PSA_FQ_MAX_TICKS; t++)
+                        tick_at[n_ticks++] = t * 1000000 - reads_before;
+                rc = psa_fq_lane_run(L, ow.j0, ow.n_rec, tick_at, n_ticks, &res);
+            }
+            const auto t3 = now();
+            // ---- commit in block order
+            uint64_t my_out = 0;
+            bool write_it = false;
+            {
+                std::unique_lock<std::mutex> lk(st.mu);
+                st.cv.wait(lk, [&]() { return st.commit_turn == i; });
+                st.busy_mapper += secs(t1, t2) + secs(t2w, t3);
+                if (st.stop_block < 0) {
+                    if (rc) {
+                        st.rc = rc;
+                        st.stop_block = (int64_t)i;
+                    } else if (!res.plain) {
+                        st.stop_block = (int64_t)i;
+                    } else {
+                        my_out = st.out_pos;
+                        st.out_pos += res.out_bytes;
+                        for (uint32_t t = 0; t < n_ticks; t++) {   // ref :497-504
+                            char rate[64];
+                            display_f32(rate, (float)(st.n_mapped + res.tick_mapped[t]) * 100.0f / (float)st.next_tick);
+                            fprintf(stderr, "\rDone Mapping %llu reads w/ Rate: %s", (unsigned long long)st.next_tick, rate);
+                            fflush(stderr);
+                            st.next_tick += 1000000;
+                        }
+                        st.n_reads += ow.n_rec;
+                        st.n_mapped += res.mapped;
+                        st.n_aligned += res.aligned;
+                        if (ow.n_rec) st.resume_off = lo + res.end_off;
+                        write_it = res.out_bytes != 0;
+                    }
+                }
+                if (of.fd >= 0 || !write_it) {   // positional writes need no order: pass the turn on at once
+                    st.commit_turn++;
+                    st.cv.notify_all();
+                }
+            }
+            const auto t4 = now();
+            if (write_it) {
+                bool ok = true;
+                if (of.fd >= 0) {
+                    std::vector<char> failed(cfg.write_threads, 0);
+                    parallel_for(cfg.write_threads, [&](uint32_t t) {
+                        const uint64_t a0 = res.out_bytes * t / cfg.write_threads, a1 = res.out_bytes * (t + 1) / cfg.write_threads;
+                        if (a1 > a0) failed[t] = !of.put(res.out_text + a0, a1 - a0, my_out + a0);
+                    });
+                    for (auto f : failed) ok &= !f;
+                } else {
+                    ok = fwrite(res.out_text, 1, res.out_bytes, out) == res.out_bytes;
+                }
+                std::unique_lock<std::mutex> lk(st.mu);
+                st.busy_writer += secs(t4, now());
+                if (!ok && !st.rc) st.rc = PSA_ERR_IO;
+                if (of.fd < 0) {
+                    st.commit_turn++;
+                    st.cv.notify_all();
+                }
+            }
+            if (cfg.verbose)
+                fprintf(stderr, "psa: block %llu lane %u: %llu records, read %.1f ms, index %.1f ms, map+format %.1f ms (waited %.1f ms for its turns), write %.1f ms\n",
+                        (unsigned long long)i, a, (unsigned long long)ow.n_rec, 1e3 * secs(t0, t1), 1e3 * secs(t1, t2), 1e3 * secs(t2w, t3),
+                        1e3 * (secs(t2, t2w) + secs(t3, t4)), 1e3 * secs(t4, now()));
+            std::unique_lock<std::mutex> lk(st.mu);
+            if (st.stop_block >= 0) return;
+        }
+    };
+    const auto tp0 = now();
+    // The pages of the output mapping are faulted in ahead of the writers by two helper threads (a fresh page of a tmpfs /
+    // page-cache file costs microseconds: allocation, zeroing, accounting), a bounded distance ahead of the committed output.
+    std::atomic<bool> pipeline_done{false};
+    std::vector<std::thread> prefault;
+#ifdef MADV_POPULATE_WRITE
+    if (of.map_base && !getenv("PSA_NO_PREFAULT")) {
+        for (uint32_t h = 0; h < 2; h++)
+            prefault.emplace_back([&, h]() {
+                const uint64_t chunk = 4ull << 20, ahead = 160ull << 20;
+                uint64_t at = (of.pos & ~(chunk - 1)) + h * chunk;
+                while (!pipeline_done.load(std::memory_order_relaxed)) {
+                    uint64_t committed;
+                    {
+                        std::unique_lock<std::mutex> lk(st.mu);
+                        committed = st.out_pos;
+                    }
+                    while (at + chunk <= committed) at += 2 * chunk;   // never behind the writers
+                    if (at + chunk > of.map_off + of.map_len) return;
+                    if (at > committed + ahead) {
+                        std::this_thread::sleep_for(std::chrono::microseconds(200));
+                        continue;
+                    }
+                    const uint64_t lo = std::max(at, of.map_off);
+                    if (madvise(of.map_base + (lo - of.map_off), (size_t)(at + chunk - lo), MADV_POPULATE_WRITE) != 0) return;
+                    at += 2 * chunk;
+                }
+            });
+    }
+#endif
+    {
+        std::vector<std::thread> th;
+        for (uint32_t a = 1; a < lanes; a++) th.emplace_back(lane_main, a);
+        lane_main(0);
+        for (auto& x : th) x.join();
+    }
+    pipeline_done.store(true);
+    for (auto& x : prefault) x.join();
+    const auto tp1 = now();
+    parallel_for(lanes, [&](uint32_t a) { psa_fq_lane_destroy(lane[a]); });
+    if (cfg.verbose)
+        fprintf(stderr, "psa: block pipeline summary: lanes created in %.1f ms, blocks %.1f ms, lanes destroyed in %.1f ms\n", 1e3 * secs(tc0, tp0),
+                1e3 * secs(tp0, tp1), 1e3 * secs(tp1, now()));
+    of.pos = st.out_pos;
+    return st.stop_block < 0 && st.rc == PSA_OK;
+}
+
 }  // namespace
 
 // `{:?}` of a string as the drivers print it (shared with the Python mirror); returns the bytes written, or a
@@ -519,6 +827,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                                  uint64_t batch_reads, int progress, psa_process_stats* stats) {
     if (!index || !fastq_path) return PSA_ERR_ARG;
     if (!num_threads) num_threads = 1;
+    const uint64_t batch_reads_arg = batch_reads;
     if (!batch_reads) batch_reads = 1ull << 19;  // one pipeline chunk of psa_mapper_map: small blocks keep the start-up short
     const auto t0 = std::chrono::steady_clock::now();
 
@@ -527,7 +836,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     FILE* out = stdout;
     const bool own_out = out_path && strcmp(out_path, "-") != 0;
     if (own_out) {
-        out = fopen(out_path, "wb");
+        out = fopen(out_path, "w+b");   // (read access too: the writers map it)
         if (!out) {
             in.close();
             return PSA_ERR_IO;
@@ -535,11 +844,60 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     }
     OutFile of;
     of.attach(out);
+    if (in.parallel()) of.open_window(in.size);
+    const double t_open = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    (void)t_open;   // (result lines are about a third of the FASTQ text; more than the window is pwritten)
+    const bool verbose = getenv("PSA_VERBOSE") != nullptr;
+    uint64_t n_reads = 0, n_mapped = 0, n_aligned = 0, next_tick = 1000000;
+    double busy_reader = 0, busy_mapper = 0, busy_writer = 0;  // seconds spent working (not waiting) per stage
+
+    // Plain files first go through the block pipeline whose text work is on the device (fast_blocks above); it stops at the
+    // first record that is not a plain four-line ASCII record, and the host parser below takes over from there (gzip, pipes
+    // and PSA_PROCESS_FAST=0 start there).  batch_reads sizes its blocks too (~320 bytes of FASTQ per 150-base record).
+    bool fast_done = false;
+    {
+        const char* e = getenv("PSA_PROCESS_FAST");
+        if (in.parallel() && !(e && atoi(e) == 0)) {
+            FastConfig cfg;
+            uint64_t bb = batch_reads_arg ? batch_reads_arg * 320 : (32ull << 20);
+            if (const char* b = getenv("PSA_FQ_BLOCK_BYTES")) bb = strtoull(b, nullptr, 10);
+            bb = std::min<uint64_t>(std::max<uint64_t>(bb, 4096), 1ull << 30);
+            cfg.block_bytes = (bb + 4095) / 4096 * 4096;
+            cfg.tail_bytes = std::min<uint64_t>(std::max<uint64_t>(cfg.block_bytes / 8, 4096), 1ull << 20);
+            if (const char* t = getenv("PSA_FQ_TAIL_BYTES")) cfg.tail_bytes = strtoull(t, nullptr, 10);
+            cfg.lanes = 3;
+            if (const char* l = getenv("PSA_FQ_LANES")) cfg.lanes = (uint32_t)std::max(1, atoi(l));
+            cfg.io_threads = std::max<uint32_t>(1, num_threads / cfg.lanes);
+            cfg.write_threads = cfg.io_threads;
+            if (const char* w = getenv("PSA_FQ_WRITE_THREADS")) cfg.write_threads = (uint32_t)std::max(1, atoi(w));
+            cfg.verbose = verbose;
+            FastState fs;
+            fast_done = fast_blocks(index, in, of, out, progress, cfg, fs);
+            n_reads = fs.n_reads; n_mapped = fs.n_mapped; n_aligned = fs.n_aligned; next_tick = fs.next_tick;
+            busy_reader = fs.busy_reader; busy_mapper = fs.busy_mapper; busy_writer = fs.busy_writer;
+            if (fs.rc) {
+                of.finish();
+                fflush(out);
+                if (own_out) fclose(out);
+                in.close();
+                return fs.rc;
+            }
+            if (!fast_done) {
+                in.pos = fs.resume_off;
+                if (verbose) fprintf(stderr, "psa: block pipeline stopped after %llu reads; host parser resumes at byte %llu\n",
+                                     (unsigned long long)n_reads, (unsigned long long)fs.resume_off);
+            }
+        }
+    }
+
+    int map_rc = PSA_OK, reader_rc = PSA_OK, writer_rc = PSA_OK;
+    if (!fast_done) {
     HostClasses hc;
     psa_mapper* mapper = nullptr;
     int rc = psa_index_host_classes(index, &hc.off, &hc.mem, &hc.n_eq);
     if (!rc) rc = psa_mapper_create(index, 0, &mapper);
     if (rc) {
+        of.finish();
         in.close();
         if (own_out) fclose(out);
         return rc;
@@ -549,10 +907,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     Batch slot[kSlots];
     std::mutex mu;
     std::condition_variable cv;
-    int reader_rc = PSA_OK;
     bool abort_all = false;
-    double busy_reader = 0, busy_mapper = 0, busy_writer = 0;  // seconds spent working (not waiting) per stage
-    const bool verbose = getenv("PSA_VERBOSE") != nullptr;
     auto now = []() { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double>(b - a).count();
@@ -695,8 +1050,6 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     });
 
     // stage 3: format + write, in input order
-    uint64_t n_reads = 0, n_mapped = 0, n_aligned = 0, next_tick = 1000000;
-    int writer_rc = PSA_OK;
     std::thread writer([&]() {
         int s = 0;
         std::vector<OutBuf> parts(num_threads);
@@ -745,7 +1098,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                     std::vector<uint64_t> at(num_threads + 1, of.pos);
                     for (uint32_t t = 0; t < num_threads; t++) at[t + 1] = at[t] + parts[t].n;
                     for (uint32_t t = 0; t < num_threads; t++)
-                        th.emplace_back([&, t]() { failed[t] = !OutFile::write_at(of.fd, parts[t].p, parts[t].n, at[t]); });
+                        th.emplace_back([&, t]() { failed[t] = !of.put(parts[t].p, parts[t].n, at[t]); });
                     for (auto& x : th) x.join();
                     for (uint32_t t = 0; t < num_threads; t++)
                         if (failed[t]) writer_rc = PSA_ERR_IO;
@@ -756,7 +1109,7 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
                 }
                 if (verbose)
                     fprintf(stderr, "psa: writer block %llu records: format %.0f ms, write %.0f ms (%s)\n", (unsigned long long)b.n,
-                            1e3 * secs(tw0, tw1), 1e3 * secs(tw1, now()), of.fd >= 0 ? "pwrite by every thread" : "serial");
+                            1e3 * secs(tw0, tw1), 1e3 * secs(tw1, now()), of.fd >= 0 ? (of.map_base ? "every thread through the mapping" : "pwrite by every thread") : "serial");
                 // ref :497-504: at every 1 000 000th read, the share of "mapped" reads so far (f32 arithmetic, `{}`)
                 while (progress && n_reads + b.n >= next_tick) {
                     const uint64_t k = next_tick - n_reads;   // reads of this block up to the tick
@@ -783,7 +1136,6 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     });
 
     // stage 2 (this thread): the GPU
-    int map_rc = PSA_OK;
     for (int s = 0;; s = (s + 1) % kSlots) {
         Batch& b = slot[s];
         {
@@ -833,13 +1185,19 @@ extern "C" int psa_process_reads(psa_index* index, const char* fastq_path, const
     }
     reader.join();
     writer.join();
+    psa_mapper_destroy(mapper);
+    for (auto& b : slot) { b.text.release(); b.hits.release(); b.tx.release(); }
+    }  // host parser
     if (progress) fprintf(stderr, "\n");
+    const auto tf0 = std::chrono::steady_clock::now();
     of.finish();
     fflush(out);
     if (own_out) fclose(out);
     in.close();
-    psa_mapper_destroy(mapper);
-    for (auto& b : slot) { b.text.release(); b.hits.release(); b.tx.release(); }
+    if (verbose)
+        fprintf(stderr, "psa: summary: files opened after %.1f ms, output finished (unmap, cut to size, close) in %.1f ms, total %.1f ms\n", 1e3 * t_open,
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count(),
+                1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     if (stats) {
         stats->reads = n_reads;
         stats->mapped = n_mapped;

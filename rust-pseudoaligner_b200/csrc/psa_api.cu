@@ -15,12 +15,15 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "../../include/psa.h"
 #include "psa_kernels.cuh"
+#include "psa_fastq.cuh"
+#include "psa_fastq.h"
 
 using namespace psa;
 
@@ -106,6 +109,10 @@ struct psa_index {
     psa_index_info info{};
     int kw = 1;
     int sms = 148;   // multiprocessors of the device
+    // idle FASTQ text lanes (psa_fastq.h) kept for the next psa_process_reads call: pinning their buffers and creating
+    // their mappers costs 0.1-0.2 s per call otherwise.  Freed with the index.
+    std::mutex lanes_mu;
+    std::vector<struct psa_fq_lane*> idle_lanes;
 };
 
 static uint32_t bits_for(uint64_t max_value) {  // bits needed to store 0..max_value
@@ -432,9 +439,13 @@ extern "C" int psa_index_create(const psa_index_desc* d, int device, double gamm
     return PSA_OK;
 }
 
+struct psa_fq_lane;
+static void fq_lane_free(psa_fq_lane* l);
 extern "C" void psa_index_destroy(psa_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
+    for (auto l : ix->idle_lanes) fq_lane_free(l);
+    ix->idle_lanes.clear();
     ix->buckets.release(); ix->nodes.release(); ix->nodes_cold.release();
     ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
     delete ix;
@@ -1769,6 +1780,235 @@ extern "C" int psa_result_checksum(int device, const psa_hit* hits_dev, const ui
     cudaError_t e = cudaMemcpy(out, acc.p, 8, cudaMemcpyDeviceToHost);
     acc.release();
     if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FASTQ text lanes (psa_fastq.h): raw FASTQ block in, `{:?}` lines out, everything in between on the
+// device -- newline index, record table, ASCII -> 2-bit, map_read, decimal formatting (psa_fastq.cuh).
+// One lane = one mapper (own stream) + the buffers of one block; psa_process_reads runs several lanes
+// side by side so that one lane's copies overlap another's kernels.
+// ---------------------------------------------------------------------------------------------
+struct psa_fq_lane {
+    psa_index* ix = nullptr;
+    psa_mapper* m = nullptr;
+    uint64_t block_bytes = 0, tail_bytes = 0;
+    uint8_t* h_text = nullptr;            // pinned: block + tail (+ 64)
+    char* h_out = nullptr;                // pinned: result lines
+    uint64_t h_out_cap = 0;
+    unsigned long long* h_small = nullptr;  // pinned scratch for the small read-backs
+    DevBuf d_text, d_tile, d_tile_off, d_nl, d_seq_off, d_seq_len, d_id_off, d_id_len, d_hits, d_tx, d_line_len, d_line_off, d_out,
+        d_small, d_scan;
+    uint64_t len = 0, n_tiles = 0, nl_total = 0;
+};
+
+// a lane that is done goes back to its index (at most kIdleLanes are kept)
+constexpr size_t kIdleLanes = 4;
+extern "C" void psa_fq_lane_destroy(psa_fq_lane* l) {
+    if (!l) return;
+    if (l->m && !getenv("PSA_FQ_NO_LANE_CACHE")) {
+        cudaSetDevice(l->ix->device);
+        cudaStreamSynchronize(l->m->st);
+        std::lock_guard<std::mutex> g(l->ix->lanes_mu);
+        if (l->ix->idle_lanes.size() < kIdleLanes) {
+            l->ix->idle_lanes.push_back(l);
+            return;
+        }
+    }
+    fq_lane_free(l);
+}
+static void fq_lane_free(psa_fq_lane* l) {
+    if (!l) return;
+    if (l->m) {
+        cudaSetDevice(l->ix->device);
+        cudaStreamSynchronize(l->m->st);
+    }
+    DevBuf* bufs[] = {&l->d_text, &l->d_tile, &l->d_tile_off, &l->d_nl, &l->d_seq_off, &l->d_seq_len, &l->d_id_off, &l->d_id_len,
+                      &l->d_hits, &l->d_tx, &l->d_line_len, &l->d_line_off, &l->d_out, &l->d_small, &l->d_scan};
+    for (auto b : bufs) b->release();
+    if (l->h_text) cudaFreeHost(l->h_text);
+    if (l->h_out) cudaFreeHost(l->h_out);
+    if (l->h_small) cudaFreeHost(l->h_small);
+    if (l->m) psa_mapper_destroy(l->m);
+    delete l;
+}
+
+extern "C" int psa_fq_lane_create(psa_index* ix, uint64_t block_bytes, uint64_t tail_bytes, psa_fq_lane** out) {
+    if (!ix || !out || !block_bytes || block_bytes % kFqTile) return fail(PSA_ERR_ARG, "block_bytes must be a positive multiple of 4096");
+    if (block_bytes + tail_bytes >= (1ull << 32) - 2 * kFqTile) return fail(PSA_ERR_ARG, "a FASTQ block is at most 4 GB");
+    *out = nullptr;
+    CU(cudaSetDevice(ix->device));
+    {   // an idle lane of the same geometry?
+        std::lock_guard<std::mutex> g(ix->lanes_mu);
+        for (size_t i = 0; i < ix->idle_lanes.size(); i++) {
+            psa_fq_lane* c = ix->idle_lanes[i];
+            if (c->block_bytes == block_bytes && c->tail_bytes == tail_bytes) {
+                ix->idle_lanes.erase(ix->idle_lanes.begin() + (long)i);
+                psa_mapper_counts_reset(c->m);
+                *out = c;
+                return PSA_OK;
+            }
+        }
+    }
+    psa_fq_lane* l = new (std::nothrow) psa_fq_lane();
+    if (!l) return fail(PSA_ERR_NOMEM, "out of memory");
+    l->ix = ix;
+    l->block_bytes = block_bytes;
+    l->tail_bytes = tail_bytes;
+    int rc = psa_mapper_create(ix, 0, &l->m);
+    const uint64_t text_cap = block_bytes + tail_bytes + 64;
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaHostAlloc((void**)&l->h_text, text_cap, cudaHostAllocDefault);
+    if (!rc && e == cudaSuccess) e = cudaHostAlloc((void**)&l->h_small, 256, cudaHostAllocDefault);
+    l->h_out_cap = std::max<uint64_t>(block_bytes / 2, 1u << 16);
+    if (!rc && e == cudaSuccess) e = cudaHostAlloc((void**)&l->h_out, l->h_out_cap, cudaHostAllocDefault);
+    if (!rc && e != cudaSuccess) rc = fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    if (!rc) rc = l->d_text.ensure(text_cap + 2 * kFqTile);
+    if (!rc) rc = l->d_small.ensure(256);
+    if (!rc) rc = l->d_out.ensure(l->h_out_cap + 64);
+    if (rc) {
+        fq_lane_free(l);
+        return rc;
+    }
+    *out = l;
+    return PSA_OK;
+}
+
+extern "C" uint8_t* psa_fq_lane_text(psa_fq_lane* l) { return l ? l->h_text : nullptr; }
+
+extern "C" int psa_fq_lane_index(psa_fq_lane* l, uint64_t len, uint64_t own_bytes, uint64_t* nl_own, uint64_t* nl_total) {
+    if (!l || !nl_own || !nl_total || len > l->block_bytes + l->tail_bytes + 64 || own_bytes > len ||
+        (own_bytes != len && own_bytes % kFqTile))
+        return fail(PSA_ERR_ARG, "bad FASTQ block geometry");
+    CU(cudaSetDevice(l->ix->device));
+    cudaStream_t st = l->m->st;
+    l->len = len;
+    l->n_tiles = (len + kFqTile - 1) / kFqTile;
+    l->nl_total = 0;
+    *nl_own = *nl_total = 0;
+    if (!len) return PSA_OK;
+    int rc;
+    if ((rc = l->d_tile.ensure((l->n_tiles + 1) * 4)) || (rc = l->d_tile_off.ensure((l->n_tiles + 1) * 4))) return rc;
+    CU(cudaMemcpyAsync(l->d_text.p, l->h_text, len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(l->d_text.as<uint8_t>() + len, 0, l->n_tiles * kFqTile - len, st));   // the last tile is read whole
+    CU(cudaMemsetAsync(l->d_tile.as<uint32_t>() + l->n_tiles, 0, 4, st));
+    k_fq_count<<<(unsigned)l->n_tiles, 256, 0, st>>>(l->d_text.as<uint8_t>(), l->d_tile.as<uint32_t>());
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, l->d_tile.as<uint32_t>(), l->d_tile_off.as<uint32_t>(), l->n_tiles + 1, st));
+    if ((rc = l->d_scan.ensure(tb))) return rc;
+    CU(cub::DeviceScan::ExclusiveSum(l->d_scan.p, tb, l->d_tile.as<uint32_t>(), l->d_tile_off.as<uint32_t>(), l->n_tiles + 1, st));
+    const uint64_t own_tiles = own_bytes == len ? l->n_tiles : own_bytes / kFqTile;
+    uint32_t* hs = reinterpret_cast<uint32_t*>(l->h_small);
+    CU(cudaMemcpyAsync(hs, l->d_tile_off.as<uint32_t>() + own_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hs + 1, l->d_tile_off.as<uint32_t>() + l->n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *nl_own = hs[0];
+    *nl_total = l->nl_total = hs[1];
+    if ((rc = l->d_nl.ensure((l->nl_total + 1) * 4))) return rc;
+    k_fq_positions<<<(unsigned)l->n_tiles, 256, 0, st>>>(l->d_text.as<uint8_t>(), l->d_tile_off.as<uint32_t>(), l->d_nl.as<uint32_t>());
+    l->m->launches += 3;
+    CU(cudaGetLastError());
+    return PSA_OK;
+}
+
+extern "C" int psa_fq_lane_run(psa_fq_lane* l, int64_t j0, uint64_t n, const uint64_t* tick_at, uint32_t n_ticks, psa_fq_result* out) {
+    if (!l || !out || n_ticks > PSA_FQ_MAX_TICKS || (n_ticks && !tick_at)) return fail(PSA_ERR_ARG, "bad argument");
+    memset(out, 0, sizeof *out);
+    out->plain = 1;
+    out->out_text = l->h_out;
+    if (!n) return PSA_OK;
+    if (j0 < -1 || (uint64_t)(j0 + 4 * (int64_t)(n - 1) + 4) >= l->nl_total) return fail(PSA_ERR_ARG, "records beyond the indexed newlines");
+    CU(cudaSetDevice(l->ix->device));
+    cudaStream_t st = l->m->st;
+    int rc;
+    if ((rc = l->d_seq_off.ensure(n * 8)) || (rc = l->d_seq_len.ensure(n * 4)) || (rc = l->d_id_off.ensure(n * 4)) ||
+        (rc = l->d_id_len.ensure(n * 4)) || (rc = l->d_hits.ensure((n + 1) * sizeof(HitRec))) || (rc = l->d_line_len.ensure((n + 1) * 4)) ||
+        (rc = l->d_line_off.ensure((n + 2) * 8)))
+        return rc;
+    if (!l->d_tx.cap && (rc = l->d_tx.ensure(std::max<uint64_t>(n * 16 * 4, 1 << 20)))) return rc;
+    unsigned long long* ds = l->d_small.as<unsigned long long>();   // [0] status, [1] mapped, [2] aligned, [3] end offset, [8..16) tick positions, [16..24) tick counts
+    CU(cudaMemsetAsync(ds, 0, 256, st));
+    k_fq_records<<<nblocks(n, 128), 128, 0, st>>>(l->d_text.as<uint8_t>(), l->d_nl.as<uint32_t>(), j0, n, l->d_seq_off.as<uint64_t>(),
+                                                  l->d_seq_len.as<uint32_t>(), l->d_id_off.as<uint32_t>(), l->d_id_len.as<uint32_t>(),
+                                                  reinterpret_cast<uint32_t*>(ds));
+    l->m->launches++;
+    CU(cudaGetLastError());
+    // map_read for every record: the sequences are addressed by offset in the block's text
+    psa_read_batch r{};
+    r.format = PSA_READS_ASCII;
+    r.location = PSA_MEM_DEVICE;
+    r.data = l->d_text.p;
+    r.data_len = l->len;
+    r.read_off = l->d_seq_off.as<uint64_t>();
+    r.read_len = l->d_seq_len.as<uint32_t>();
+    r.n_reads = n;
+    psa_result_batch o{};
+    o.location = PSA_MEM_DEVICE;
+    for (int attempt = 0;; attempt++) {
+        o.hits = reinterpret_cast<psa_hit*>(l->d_hits.p);
+        o.tx_buf = l->d_tx.as<uint32_t>();
+        o.tx_cap = l->d_tx.cap / 4;
+        rc = map_device_sync<false>(l->m, &r, &o);
+        if (rc == PSA_ERR_CAPACITY && o.tx_used > o.tx_cap && attempt == 0) {
+            if ((rc = l->d_tx.ensure(o.tx_used * 4 + 4096))) return rc;
+            continue;
+        }
+        break;
+    }
+    if (rc) return rc;
+    // (map_device_sync has synchronised the stream: the record kernel's verdict is there)
+    CU(cudaMemcpyAsync(l->h_small, ds, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (l->h_small[0] & 1ull) {
+        out->plain = 0;
+        return PSA_OK;
+    }
+    // line lengths -> offsets
+    k_fq_line_len<<<nblocks(n, 128), 128, 0, st>>>(l->d_text.as<uint8_t>(), l->d_id_off.as<uint32_t>(), l->d_id_len.as<uint32_t>(),
+                                                   l->d_hits.as<HitRec>(), l->d_tx.as<uint32_t>(), n, l->d_line_len.as<uint32_t>(), ds + 1);
+    {
+        cub::CountingInputIterator<uint64_t> cnt(0);
+        FqLenToU64 f{l->d_line_len.as<uint32_t>(), n};
+        cub::TransformInputIterator<uint64_t, FqLenToU64, cub::CountingInputIterator<uint64_t>> in(cnt, f);
+        size_t tb = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, l->d_line_off.as<uint64_t>(), n + 1, st));
+        if ((rc = l->d_scan.ensure(tb))) return rc;
+        CU(cub::DeviceScan::ExclusiveSum(l->d_scan.p, tb, in, l->d_line_off.as<uint64_t>(), n + 1, st));
+    }
+    CU(cudaMemcpyAsync(l->h_small, l->d_line_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(l->h_small + 1, ds + 1, 16, cudaMemcpyDeviceToHost, st));
+    {   // end of the last record = the newline that ends its quality line, + 1
+        const uint64_t last_nl = (uint64_t)(j0 + 4 * (int64_t)(n - 1) + 4);
+        CU(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(l->h_small + 3), l->d_nl.as<uint32_t>() + last_nl, 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    const uint64_t total = l->h_small[0];
+    out->mapped = l->h_small[1];
+    out->aligned = l->h_small[2];
+    out->end_off = (uint64_t)*reinterpret_cast<uint32_t*>(l->h_small + 3) + 1;
+    if (total > l->h_out_cap) {
+        cudaFreeHost(l->h_out);
+        l->h_out = nullptr;
+        l->h_out_cap = total + total / 4 + 4096;
+        CU(cudaHostAlloc((void**)&l->h_out, l->h_out_cap, cudaHostAllocDefault));
+        out->out_text = l->h_out;
+    }
+    if ((rc = l->d_out.ensure(total + 64))) return rc;
+    k_fq_format<<<nblocks(n, kFqFmtBlock), kFqFmtBlock, 0, st>>>(l->d_text.as<uint8_t>(), l->d_id_off.as<uint32_t>(), l->d_id_len.as<uint32_t>(),
+                                                                 l->d_hits.as<HitRec>(), l->d_tx.as<uint32_t>(), l->d_line_off.as<uint64_t>(), n,
+                                                                 l->d_out.as<char>());
+    l->m->launches += 3;
+    if (n_ticks) {
+        CU(cudaMemcpyAsync(ds + 8, tick_at, n_ticks * 8, cudaMemcpyHostToDevice, st));
+        k_fq_mapped_prefix<<<148, 256, 0, st>>>(l->d_hits.as<HitRec>(), reinterpret_cast<const uint64_t*>(ds + 8), n_ticks, ds + 16);
+        CU(cudaMemcpyAsync(l->h_small + 8, ds + 16, n_ticks * 8, cudaMemcpyDeviceToHost, st));
+        l->m->launches++;
+    }
+    CU(cudaMemcpyAsync(l->h_out, l->d_out.p, total, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (uint32_t t = 0; t < n_ticks; t++) out->tick_mapped[t] = l->h_small[8 + t];
+    out->out_bytes = total;
     return PSA_OK;
 }
 

@@ -678,3 +678,54 @@ def test_compact_results(orc_index_for, fixture_fasta):
     g2, t2 = psa.expand_compact(hc2, ntx2, flat["eq_offsets"], flat["eq_members"])
     _assert_same(fixed, g2, t2, w_hits, w_tx)
     pa.close()
+
+
+@pytest.mark.gpu
+def test_process_reads_block_pipeline(pa_for, orc_index_for, fixture_fastq, tmp_path, monkeypatch):
+    """psa_process_reads' block pipeline (raw FASTQ blocks -> newline index, record table, map, `{:?}` formatting, all on
+    the device: csrc/psa_fastq.cuh) against the oracle and against the host parser, line by line: default blocks, 64 KB
+    blocks on 4 lanes (records across block boundaries, tails), ids that need escaping, empty sets, a file without a final
+    newline, a wrapped record in mid-file (hand-over to the host parser), progress counters."""
+    ix, pa = orc_index_for(20), pa_for(20)
+    base = list(fixture_fastq)
+    ids = [b'plain', b'with"quote', b'back\\slash', b'tab\there', b'ctl\x01\x1f\x7f', b"it's", b'', b'x' * 300]
+    recs = []
+    for rep in range(6):
+        for i, (rid, seq) in enumerate(base):
+            rid = rid.encode() if isinstance(rid, str) else rid
+            seq = seq.encode() if isinstance(seq, str) else seq
+            tag = ids[(i + rep) % len(ids)]
+            recs.append((tag + b"#%d/%d" % (rep, i) if tag else (b"" if (i + rep) % 97 == 0 else b"r%d" % i), seq if (i + rep) % 53 else seq[:rep + 3]))
+    want_hits, want_tx, _, _ = _oracle(ix, [s for _, s in recs])
+    want = [pkg.format_read_data(flag, rid, eq, cov) for (rid, _), (al, flag, eq, cov) in zip(recs, orc.hits_to_tuples(want_hits, want_tx))]
+    text = b"".join(b"@" + rid + b" desc\n" + seq + b"\n+\n" + b"I" * max(1, len(seq)) + b"\n" for rid, seq in recs)
+    fq = tmp_path / "blocks.fq"
+    fq.write_bytes(text)
+    out = tmp_path / "out.txt"
+    for env in ({}, {"PSA_FQ_BLOCK_BYTES": "65536", "PSA_FQ_TAIL_BYTES": "8192", "PSA_FQ_LANES": "4"}, {"PSA_PROCESS_FAST": "0"}):
+        for k in ("PSA_FQ_BLOCK_BYTES", "PSA_FQ_TAIL_BYTES", "PSA_FQ_LANES", "PSA_PROCESS_FAST"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        st = pkg.process_reads_file(str(fq), pa, str(out), num_threads=4)
+        got = out.read_bytes().decode().splitlines()
+        assert len(got) == len(want), env
+        bad = [i for i in range(len(want)) if got[i] != want[i]]
+        assert not bad, (env, bad[:3], got[bad[0]], want[bad[0]])
+        assert st["reads"] == len(want) and st["mapped"] == sum(1 for l in want if l.startswith("(true"))
+        assert st["aligned"] == int((want_hits["flags"] & 1).sum())
+    monkeypatch.setenv("PSA_FQ_BLOCK_BYTES", "65536")
+    monkeypatch.setenv("PSA_FQ_TAIL_BYTES", "8192")
+    # no final newline; a wrapped record in the middle of the file
+    fq.write_bytes(text[:-1])
+    st = pkg.process_reads_file(str(fq), pa, str(out), num_threads=3)
+    assert out.read_bytes().decode().splitlines() == want
+    half = len(recs) // 2
+    cut = sum(len(b"@" + rid + b" desc\n" + seq + b"\n+\n" + b"I" * max(1, len(seq)) + b"\n") for rid, seq in recs[:half])
+    rid, seq = recs[half]
+    assert len(seq) > 10
+    wrapped = b"@" + rid + b"\n" + seq[:7] + b"\n" + seq[7:] + b"\n+\n" + b"I" * 7 + b"\n" + b"I" * (len(seq) - 7) + b"\n"
+    rest = cut + len(b"@" + rid + b" desc\n" + seq + b"\n+\n" + b"I" * max(1, len(seq)) + b"\n")
+    fq.write_bytes(text[:cut] + wrapped + text[rest:])
+    st = pkg.process_reads_file(str(fq), pa, str(out), num_threads=3)
+    assert out.read_bytes().decode().splitlines() == want and st["reads"] == len(want)

@@ -28,6 +28,20 @@ def stub():
     return L
 
 
+@pytest.fixture(autouse=True, params=["blocks", "blocks_tiny", "host_parser"])
+def pipeline(request, monkeypatch):
+    """Every test runs three times: through the block pipeline whose text work belongs to the device (here: the stub's
+    serial stand-in built from the same psa_fastq.cuh routines) with default and with 4 KB blocks on 4 lanes (block
+    boundaries inside records, tails, hand-over to the host parser in mid-file), and through the host parser alone."""
+    if request.param == "host_parser":
+        monkeypatch.setenv("PSA_PROCESS_FAST", "0")
+    elif request.param == "blocks_tiny":
+        monkeypatch.setenv("PSA_FQ_BLOCK_BYTES", "4096")
+        monkeypatch.setenv("PSA_FQ_TAIL_BYTES", "4096")
+        monkeypatch.setenv("PSA_FQ_LANES", "4")
+    return request.param
+
+
 def _expected(records):
     out = []
     for rid, seq in records:
@@ -263,3 +277,58 @@ def test_debug_str_follows_rust(stub):
     assert dbg("naïve-ß-日本".encode()) == '"naïve-ß-日本"'
     assert dbg("a\u00adb\u0085c\u200bd\u0301e\ufefff".encode()) == '"a\\u{ad}b\\u{85}c\\u{200b}d\\u{301}e\\u{feff}f"'
     assert dbg(b"\xff\xfe") is None and dbg(b"\xc3") is None                # not UTF-8: the reference panics
+
+
+def test_block_pipeline_hands_over_in_mid_file(stub, tmp_path, pipeline):
+    """Plain four-line records go through the block pipeline; the first record that is not plain (here: a header with a
+    non-ASCII character, then a wrapped record, then a record longer than block + tail) hands the rest of the file to the
+    host parser.  Lines, order and counters are the same whichever path a record took."""
+    rng = np.random.default_rng(21)
+    a, b, c = _records(rng, 700, 30, 120), _records(rng, 300, 30, 120), _records(rng, 200, 30, 120)
+    uni = ("r\u00e9sum\u00e9".encode(), b"TTGCA")
+    text = (_fastq(a) + b"@" + uni[0] + b"\n" + uni[1] + b"\n+\nIIIII\n" + _fastq(b)
+            + b"@wrapped\nACGT\nACGT\n+\nIIII\nIIII\n" + _fastq(c) + _fastq([(b"long", b"ACGT" * 5000)]) + _fastq(a[:50]))
+    p = tmp_path / "mid.fq"
+    p.write_bytes(text)
+    want = _expected(a) + ['(true, "r\u00e9sum\u00e9", [%d], 5)' % sum(uni[1])] + _expected(b) + _expected([(b"wrapped", b"ACGTACGT")]) + \
+        _expected(c) + _expected([(b"long", b"ACGT" * 5000)]) + _expected(a[:50])
+    for threads in (1, 5):
+        rc, st, lines = _run(stub, p, tmp_path / "out.txt", threads, 0)
+        assert rc == 0 and lines == want
+        assert st.reads == len(want) and st.aligned == len(want)
+    # a file that does not end in a newline, cut into blocks
+    p2 = tmp_path / "nonl.fq"
+    p2.write_bytes(_fastq(a)[:-1])
+    rc, st, lines = _run(stub, p2, tmp_path / "out.txt", 3, 0)
+    assert rc == 0 and lines == _expected(a)
+    # block boundary exactly at a record boundary (4096-byte records)
+    rec = (b"x" * 10, b"ACGT" * 509)     # '@' + 10 + '\n' + 2036 + '\n' + '+' + '\n' + 2036 + '\n' = 2 * 2036 + 16 = 4088
+    pad = [(rec[0], rec[1] + b"AAAA")]    # 2 * 2040 + 16 = 4096 bytes
+    assert len(_fastq(pad)) == 4096
+    p3 = tmp_path / "aligned.fq"
+    p3.write_bytes(_fastq(pad * 9 + a[:10]))
+    rc, st, lines = _run(stub, p3, tmp_path / "out.txt", 2, 0)
+    assert rc == 0 and lines == _expected(pad * 9 + a[:10])
+
+
+def test_progress_ticks_are_the_same_on_both_paths(tmp_path):
+    """ref src/pseudoaligner.rs:497-504: a line on stderr at every 1 000 000th read with the share of "mapped" reads so
+    far.  The block pipeline gets the counts of the reads before each tick from the device; same text as the host parser."""
+    import sys
+    n = 2_100_000
+    rec = b"@r\nTA\n+\nII\n@s\nAC\n+\nII\n@t\nCC\n+\nII\n"
+    p = tmp_path / "ticks.fq"
+    p.write_bytes(rec * (n // 3))
+    code = ("import ctypes as C, sys\n"
+            "L = C.CDLL(%r)\n"
+            "L.psa_process_reads.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]\n"
+            "sys.exit(L.psa_process_reads(C.c_void_p(1), %r, b'/dev/null', 4, 0, 1, None))\n"
+            % (os.path.join(_DIR, "libprocess_stub.so"), str(p).encode()))
+    subprocess.check_call(["make", "-C", _DIR, "libprocess_stub.so"], stdout=subprocess.DEVNULL)
+    outs = []
+    for env in ({"PSA_PROCESS_FAST": "0"}, {"PSA_FQ_BLOCK_BYTES": str(1 << 20)}, {}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True)
+        assert r.returncode == 0
+        outs.append(r.stderr)
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0].count(b"Done Mapping") == 2 and b"Done Mapping 2000000 reads w/ Rate: 33.333" in outs[0]
