@@ -79,7 +79,7 @@ def kernel_source_sha16():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, PKG, "csrc")
-    for name in ("psa_core.cuh", "psa_lanes.cuh", "psa_kernels.cuh", "psa_api.cu"):
+    for name in ("psa_core.cuh", "psa_thread.cuh", "psa_kernels.cuh"):
         with open(os.path.join(d, name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -328,14 +328,18 @@ def cpu_arm(a, tr, flat, steps, warmup, budget_s, threads, keep=False):
 
 def oracle_results(a, tr, flat, n, threads):
     """Untimed: the oracle's results for the first n reads of the workload's stream."""
+    return oracle_results_from(tr.reads(3, 0, n, a.read_len, threads=threads), n, a.read_len, flat, threads)
+
+
+def oracle_results_from(data, n, read_len, flat, threads):
+    """Untimed: the oracle's results (hits, tx) for n ASCII reads of read_len bytes stored back to back in `data`."""
     import orc
     ox = orc.OrcIndex.from_flat(flat)
-    data = tr.reads(3, 0, n, a.read_len, threads=threads)
     bounds = [n * t // threads for t in range(threads + 1)]
     res = [None] * threads
 
     def work(t):
-        res[t] = ox.map_ascii_fixed(data, n, a.read_len, start=bounds[t], stop=bounds[t + 1])
+        res[t] = ox.map_ascii_fixed(data, n, read_len, start=bounds[t], stop=bounds[t + 1])
     th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     for x in th:
         x.start()

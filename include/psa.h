@@ -325,6 +325,23 @@ int psa_mapper_novel_allgather(psa_mapper*, psa_comm*, psa_novel_sets* out);
  * compared with.  chunk_bytes = 0: one random 128-byte line per warp (4 bytes per lane). ---- */
 int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s);
 
+/* ---- measurement aid: the synthetic read stream of psa_host.h (psa_synth_reads: 90 % transcript reads with 0.5 %
+ * substitutions, 5 % chimeric, 5 % random) generated ON THE DEVICE by the same counter-based generator -- read i is a
+ * function of (seed, i) only, so BASELINE config 5 (10^9 reads) needs no host generation and any sample of the stream can
+ * be regenerated on the host for the oracle.  All pointers are device memory: codes / tx_off = the transcriptome (2-bit
+ * codes, one per byte); elig[w] / cum[w] (n_elig[w] and n_elig[w] + 1 entries) = the transcripts of at least len_w bases
+ * and the running count of their start positions, for len_0 = L, len_1 = L / 2, len_2 = L - L / 2.  out: n reads of L
+ * ASCII bytes, `stride` bytes apart.  Synchronous. ---- */
+typedef struct psa_synth_tables {
+    const uint8_t* codes;
+    const uint64_t* tx_off;
+    const uint32_t* elig[3];
+    const uint64_t* cum[3];
+    uint64_t n_elig[3];
+} psa_synth_tables;
+int psa_synth_reads_device(int device, const psa_synth_tables* tables, uint64_t seed, uint64_t first, uint64_t n, uint32_t L,
+                           uint8_t* out_dev, uint64_t stride);
+
 /* ---- self-test entry: the device routines behind nodes_to_eq_class / intersect (ref src/pseudoaligner.rs:323-356,
  * :389-418) on two ascending lists in isolation: out[0..cap) one thread's list scheme, out[cap..2cap) the cooperative
  * kernel's lane-group scheme, out[2cap..3cap) the class windows (n_out[2] = PSA_EQ_NONE when a list spans >= 192 ids

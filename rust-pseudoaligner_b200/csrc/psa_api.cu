@@ -1702,6 +1702,83 @@ extern "C" int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk
     return PSA_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// measurement aid: the synthetic read stream of include/psa_host.h (psa_synth_reads, csrc/host/synth.cpp)
+// generated on the device -- the same counter-based generator, read i = f(seed, i), so that a billion-read
+// configuration needs no host generation and any sample of it can be regenerated on the host for the oracle.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DevRng {  // == synth.cpp Rng
+    uint64_t s;
+    __device__ static uint64_t splitmix(uint64_t& s) {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    __device__ DevRng(uint64_t seed, uint64_t tag, uint64_t index) {
+        s = seed * 0xD1342543DE82EF95ULL + tag;
+        s = splitmix(s) ^ (index * 0xA24BAED4963EE407ULL);
+        splitmix(s);
+    }
+    __device__ uint64_t next() { return splitmix(s); }
+    __device__ double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    __device__ uint64_t below(uint64_t n) { return __umul64hi(next(), n); }
+};
+__device__ const uint8_t* synth_pick(const psa_synth_tables& t, int w, DevRng& g) {
+    const uint64_t* cum = t.cum[w];
+    const uint64_t x = g.below(cum[t.n_elig[w]]);
+    uint64_t lo = 0, hi = t.n_elig[w] + 1;   // upper_bound(cum, x) - 1
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (cum[mid] <= x) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint64_t i = lo - 1;
+    return t.codes + t.tx_off[t.elig[w][i]] + (x - cum[i]);
+}
+__global__ void k_synth_reads(psa_synth_tables t, uint64_t seed, uint64_t first, uint64_t n, uint32_t L, uint8_t* out, uint64_t stride) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevRng g(seed, 3, first + i);
+    uint8_t* r = out + i * stride;
+    const uint32_t h0 = L / 2, h1 = L - L / 2;
+    const double u = g.uniform();
+    int kind = u < 0.90 ? 0 : (u < 0.95 ? 1 : 2);
+    if (kind == 0 && !t.n_elig[0]) kind = 2;
+    if (kind == 1 && !(t.n_elig[1] && t.n_elig[2])) kind = 2;
+    if (kind == 0) {
+        const uint8_t* s = synth_pick(t, 0, g);
+        for (uint32_t j = 0; j < L; j++) r[j] = s[j];
+    } else if (kind == 1) {
+        const uint8_t* a = synth_pick(t, 1, g);
+        const uint8_t* c = synth_pick(t, 2, g);
+        for (uint32_t j = 0; j < h0; j++) r[j] = a[j];
+        for (uint32_t j = 0; j < h1; j++) r[h0 + j] = c[j];
+    } else {
+        for (uint32_t j = 0; j < L; j++) r[j] = (uint8_t)(g.next() >> 62);
+    }
+    if (kind != 2) {  // substitutions, p = 0.005 per base: geometric gaps
+        const double lq = log(1.0 - 0.005);
+        uint64_t j = (uint64_t)(log(1.0 - g.uniform()) / lq);
+        while (j < L) {
+            r[j] = (uint8_t)((r[j] + 1 + g.below(3)) & 3);
+            j += 1 + (uint64_t)(log(1.0 - g.uniform()) / lq);
+        }
+    }
+    for (uint32_t j = 0; j < L; j++) r[j] = (uint8_t)"ACGT"[r[j]];
+}
+}  // namespace
+extern "C" int psa_synth_reads_device(int device, const psa_synth_tables* t, uint64_t seed, uint64_t first, uint64_t n, uint32_t L,
+                                      uint8_t* out_dev, uint64_t stride) {
+    if (!t || !out_dev || stride < L || !t->codes || !t->tx_off) return fail(PSA_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(device));
+    if (n) k_synth_reads<<<nblocks(n, 128), 128>>>(*t, seed, first, n, L, out_dev, stride);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return PSA_OK;
+}
+
 extern "C" int psa_selftest_intersect(int device, const uint32_t* v1, uint32_t n1, const uint32_t* v2, uint32_t n2,
                                       uint32_t* out, uint32_t cap, uint32_t n_out[3]) {
     if (!out || !n_out || (n1 && !v1) || (n2 && !v2)) return fail(PSA_ERR_ARG, "null argument");

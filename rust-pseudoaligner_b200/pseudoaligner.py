@@ -94,6 +94,7 @@ EXPORTS = (
     "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe", "psa_result_checksum",
     "psa_selftest_intersect", "psa_mapper_novel_sets", "psa_novel_sets_merge", "psa_novel_sets_free",
     "psa_mapper_novel_allgather", "psa_expand_compact", "psa_debug_str", "psa_index_host_classes",
+    "psa_synth_reads_device",
 )
 
 
@@ -169,6 +170,8 @@ def lib():
     L.psa_expand_compact.argtypes = [vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, C.POINTER(u64)]
     L.psa_selftest_intersect.restype = i32
     L.psa_selftest_intersect.argtypes = [i32, vp, u32, vp, u32, vp, u32, C.POINTER(u32 * 3)]
+    L.psa_synth_reads_device.restype = i32
+    L.psa_synth_reads_device.argtypes = [i32, vp, u64, u64, u64, u32, vp, u64]
     L.psa_result_checksum.restype = i32
     L.psa_result_checksum.argtypes = [i32, vp, vp, u64, u64, C.POINTER(u64)]
     L.psa_process_reads.restype = i32
@@ -388,6 +391,41 @@ class DeviceBatch:
         for b in (self.data, self.read_off, self.read_len, self.hits, self.tx):
             if b is not None:
                 b.free()
+
+
+class _SynthTables(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("tx_off", C.c_void_p), ("elig", C.c_void_p * 3), ("cum", C.c_void_p * 3),
+                ("n_elig", C.c_uint64 * 3)]
+
+
+class DeviceReadGenerator:
+    """psa_synth_reads_device: the synthetic read stream of host.Transcriptome.reads generated in HBM (measurement aid
+    for configurations too large to generate on the host).  `codes`, `tx_off`: the transcriptome (host.Transcriptome)."""
+
+    def __init__(self, codes, tx_off, read_len, device=0):
+        self.device, self.L = int(device), int(read_len)
+        tx_off = np.ascontiguousarray(tx_off, np.uint64)
+        lens = tx_off[1:] - tx_off[:-1]
+        self.bufs = [DeviceBuffer.from_numpy(np.ascontiguousarray(codes, np.uint8)), DeviceBuffer.from_numpy(tx_off)]
+        t = _SynthTables()
+        t.codes, t.tx_off = self.bufs[0].ptr, self.bufs[1].ptr
+        for w, lw in enumerate((self.L, self.L // 2, self.L - self.L // 2)):
+            elig = np.nonzero((lens >= lw) & (lw > 0))[0].astype(np.uint32)
+            cum = np.zeros(len(elig) + 1, np.uint64)
+            cum[1:] = np.cumsum(lens[elig] - np.uint64(lw) + np.uint64(1))
+            be, bc = DeviceBuffer.from_numpy(elig), DeviceBuffer.from_numpy(cum)
+            self.bufs += [be, bc]
+            t.elig[w], t.cum[w], t.n_elig[w] = be.ptr, bc.ptr, len(elig)
+        self.tables = t
+
+    def generate(self, seed, first, n, out_ptr, stride):
+        _check(lib().psa_synth_reads_device(self.device, C.byref(self.tables), int(seed), int(first), int(n), self.L,
+                                            C.c_void_p(out_ptr), int(stride)))
+
+    def free(self):
+        for b in self.bufs:
+            b.free()
+        self.bufs = []
 
 
 class Comm:
