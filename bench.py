@@ -754,14 +754,14 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # the map step is two kernels: k_map_lanes (one thread per read) and k_map (cooperative, the reads
-    # k_map_lanes handed over); each is charged the algorithmic bytes of the reads it completed
+    # the map step is two kernels: k_map_thread (one thread per read) and k_map (cooperative, the reads
+    # k_map_thread handed over); each is charged the algorithmic bytes of the reads it completed
     kernels = {}
     for name, part in (("k_map_thread", ev_split[0]), ("k_map", ev_split[1]), ("k_seed_scan", ev_split[2])):
         k_ms, k_n = prof[name]
         if not k_n:
             continue
-        per_step_ms = k_ms / a.steps                     # per STEP: k_map_lanes runs twice per step (second pass: seeded reads)
+        per_step_ms = k_ms / a.steps                     # per STEP: k_map_thread runs twice per step (second pass: seeded reads)
         a_bytes = algorithmic_bytes(part, a.k)          # of one batch = one step
         kernels[name] = {"ms_per_step": per_step_ms, "launches_per_step": k_n / a.steps,
                          "share_of_step": k_ms / prof_ms if prof_ms else None,

@@ -176,10 +176,10 @@ int psa_mapper_set_allowed_mismatches(psa_mapper*, uint32_t allowed);
 /* Tuning: lanes of a warp that cooperate on one read (8, 16 or 32; default 8, or the
  * PSA_GROUP_WIDTH environment variable).  Results do not depend on it. */
 int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
-/* Tuning: the map step is two kernels.  k_map_lanes gives every read (up to 256 bases) one lane
- * and hands a read over to the cooperative kernel (k_map, group_width lanes per read) when its
- * seed search needs more than max_probes positions, it meets more wide classes than a lane
- * keeps, or all its classes are wide and the smallest has more than max_small members.
+/* Tuning: the map step is two kernels.  k_map_thread gives every read one thread and hands a
+ * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
+ * needs more than max_probes positions, it meets more wide classes than a thread keeps, or all
+ * its classes are wide and the smallest has more than max_small members.
  * max_probes = 0 sends every read to the cooperative kernel.  Defaults ceil(k/3)+2 / 32
  * (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);

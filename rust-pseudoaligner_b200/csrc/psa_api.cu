@@ -529,47 +529,19 @@ struct psa_mapper {
     uint32_t reseed_first = 2;  // re-seed positions a thread of the FIRST pass tries (PSA_RESEED_FIRST) before it leaves the read to the second pass,
                                 // which allows max(fast_probes, 8): 2.36 vs 2.39 ms per batch on B200 (profiles/r2_exp_walk_kernel.md)
     bool tile_pack = true;      // PSA_TILE_PACK=0: pack fixed-stride ASCII without the shared-memory tiles
-    bool fast_kernel_lanes = false;  // PSA_FAST_KERNEL=lanes: the thread-per-read step as the lane state machine over
-                                     // shared-memory pools (k_map_lanes) instead of one blocking call per read (k_map_thread)
     uint32_t scan_width = 8;    // lanes per read of k_seed_scan (0: long first searches go to k_map)
     int grid = 0;
     Slot slot[kSlots];
     uint64_t launches = 0;
     // map-kernel timing (psa_mapper_profile_*)
     bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];  // [0] k_map_lanes, [1] k_map, [2] k_seed_scan
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[3];  // [0] k_map_thread, [1] k_map, [2] k_seed_scan
     // pending async call
     psa_result_batch* pending = nullptr;
     unsigned long long* pin = nullptr;  // pinned scratch: [0] tx total, [1] status
 };
 
-// the lane kernel: persistent warps over shared-memory pools of reads in flight, one resident wave.
-// hint: the reads of p.seeded (second pass)
-template <int KW, bool EV, bool HINT>
-static int launch_lanes_kw(psa_mapper* m, cudaStream_t st, const MapParams& p) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->ix->device);
-    const size_t smem = (size_t)kPoolWarps * pool_bytes_per_warp<KW, EV>(p.lane_words);
-    auto kern = k_map_lanes<KW, EV, HINT>;
-    static thread_local size_t set_for = 0;
-    if (smem > 48 * 1024 && smem > set_for) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_for = smem;
-    }
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kPoolWarps, smem));
-    if (per_sm < 1) return fail(PSA_ERR_CUDA, "k_map_lanes does not fit the SM's shared memory");
-    const uint64_t pools_needed = (p.reads.n + kPoolItems - 1) / kPoolItems;
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((pools_needed + kPoolWarps - 1) / kPoolWarps, (uint64_t)sms * per_sm));
-    kern<<<grid, 32 * kPoolWarps, smem, st>>>(m->ix->d, p);
-    return PSA_OK;
-}
-template <bool EV>
-static int launch_map_lanes(psa_mapper* m, cudaStream_t st, const MapParams& p, bool hint) {
-    if (m->ix->kw == 1) return hint ? launch_lanes_kw<1, EV, true>(m, st, p) : launch_lanes_kw<1, EV, false>(m, st, p);
-    return hint ? launch_lanes_kw<2, EV, true>(m, st, p) : launch_lanes_kw<2, EV, false>(m, st, p);
-}
-// the blocking thread-per-read kernel (PSA_FAST_KERNEL=thread)
+// the thread-per-read kernel
 static uint32_t tile_smem_bytes(const ReadsView& rv) {  // shared memory of the TILE variant, 0 = not eligible
     if (rv.woff || rv.len || !rv.wstride) return 0;
     const uint64_t total = 16 + (uint64_t)kThreadBlock * rv.wstride * 8;
@@ -583,14 +555,6 @@ static void launch_map_thread(psa_mapper* m, cudaStream_t st, const MapParams& p
         else k_map_thread<2, EV, true><<<grid, kThreadBlock, 0, st>>>(m->ix->d, p);
         return;
     }
-#if PSA_THREAD_PERSIST
-    if (!EV) {
-        const unsigned pgrid = (unsigned)std::min<uint64_t>(nblocks(p.reads.n, kThreadBlock), 148 * PSA_THREAD_MIN_BLOCKS);
-        if (m->ix->kw == 1) k_map_thread<1, EV, false><<<pgrid, kThreadBlock, 0, st>>>(m->ix->d, p);
-        else k_map_thread<2, EV, false><<<pgrid, kThreadBlock, 0, st>>>(m->ix->d, p);
-        return;
-    }
-#endif
     const unsigned grid = nblocks(p.reads.n, kThreadBlock);
     const uint32_t smem = tile_smem_bytes(p.reads);
     if (smem) {
@@ -721,7 +685,6 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     if (const char* e = getenv("PSA_OVERLAP_COOP")) m->overlap_coop = atoi(e) != 0;
     if (const char* e = getenv("PSA_RESEED_FIRST")) m->reseed_first = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_TILE_PACK")) m->tile_pack = atoi(e) != 0;
-    if (const char* e = getenv("PSA_FAST_KERNEL")) m->fast_kernel_lanes = strcmp(e, "lanes") == 0;
     if (const char* e = getenv("PSA_SCAN_WIDTH")) {
         int g = atoi(e);
         if (g == 0 || g == 8 || g == 16 || g == 32) m->scan_width = (uint32_t)g;
@@ -931,21 +894,14 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 p.seeded_count = m->novel_cursor.as<unsigned long long>() + 4;
                 p.seeded_ev = EV ? m->seeded_ev.as<uint4>() : nullptr;
             }
-            p.lane_cursor = m->novel_cursor.as<unsigned long long>() + 6;
-            {   // a lane's shared-memory slot holds the longest read of a fixed-length batch, 256 bases at most
-                const uint64_t nw = r->read_len ? kLaneMaxWords : ((uint64_t)r->fixed_len + 31) / 32;
-                p.lane_words = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(nw, 1), kLaneMaxWords);
-            }
-            int lrc = PSA_OK;
             const uint32_t reseed_long = std::max(m->fast_probes, (uint32_t)kReseedProbes);
             auto fast = [&](bool hint) {
                 // first pass: a read that has to search for a new seed mid-way is handed to the second pass (when there
                 // is one), so that the other 31 reads of its warp do not wait for the search; second pass: long budget
-                p.reseed_probes = (!hint && m->scan_width && !m->fast_kernel_lanes) ? std::min(m->reseed_first, reseed_long) : reseed_long;
-                if (m->fast_kernel_lanes) lrc = launch_map_lanes<EV>(m, st, p, hint);
-                else launch_map_thread<EV>(m, st, p, hint);
+                p.reseed_probes = (!hint && m->scan_width) ? std::min(m->reseed_first, reseed_long) : reseed_long;
+                launch_map_thread<EV>(m, st, p, hint);
             };
-            if ((rc = timed(0, [&]() { fast(false); })) || (rc = lrc)) return rc;
+            if ((rc = timed(0, [&]() { fast(false); }))) return rc;
             if (m->scan_width) {
                 // The reads the first pass handed to k_map are few and slow (a latency-bound tail): they are mapped on a
                 // second stream while k_seed_scan and the second pass run; what the second pass hands over follows below.
@@ -963,7 +919,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                     p.work_cursor = cur + 10;
                 }
                 if ((rc = timed(2, [&]() { launch_seed_scan<EV>(m, st, p); }))) return rc;
-                if ((rc = timed(0, [&]() { fast(true); })) || (rc = lrc)) return rc;
+                if ((rc = timed(0, [&]() { fast(true); }))) return rc;
                 if (m->overlap_coop) CU(cudaStreamWaitEvent(st, m->ev_join, 0));
             }
         }

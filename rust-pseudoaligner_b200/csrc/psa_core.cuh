@@ -3,8 +3,8 @@
 // Everything here is scalar __host__ __device__ code: 2-bit sequence access, the k-mer hash,
 // the bucket-cascade k-mer dictionary, the k-mer verification, the per-word mismatch masks of
 // the two extension loops, the class-window intersection and the map_read state machine in its
-// blocking form (templated on a policy that supplies the loads; used by the cooperative kernels).
-// psa_lanes.cuh holds the same state machine cut at every load (the thread-per-read kernel).
+// blocking form, templated on a policy that supplies the loads: WarpCtx (psa_kernels.cuh, a group of lanes per
+// read: the cooperative kernels) and ThreadCtx (psa_thread.cuh, one thread per read).
 // The CUDA kernels in psa_kernels.cuh instantiate this text; tests/hostsim instantiates the same
 // text with serial policies so that it is checked against the oracle on machines without a GPU.
 // That host instantiation is a unit-test harness only -- the product library (psa_api.cu) has

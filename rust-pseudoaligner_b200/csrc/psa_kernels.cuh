@@ -3,7 +3,7 @@
 // packing, the map kernels, and the result expansion.
 //
 // Reference items replaced (10XGenomics/rust-pseudoaligner @ 9d9cab8):
-//   k_map_lanes / k_seed_scan / k_map   Pseudoaligner::map_read + the per-record body of
+//   k_map_thread / k_seed_scan / k_map   Pseudoaligner::map_read + the per-record body of
 //                    process_reads (src/pseudoaligner.rs:64-384, :449-462)
 //   k_pack_ascii*    DnaString::from_dna_string at src/pseudoaligner.rs:449-450
 //   k_dict_*         make_dbg_index (src/build_index.rs:182-221)
@@ -13,7 +13,7 @@
 #include <stdint.h>
 
 #include "psa_core.cuh"
-#include "psa_lanes.cuh"
+#include "psa_thread.cuh"
 #include "psa_thread.cuh"
 
 namespace psa {
@@ -382,27 +382,25 @@ struct MapParams {
     unsigned long long pool_cap;  // entries
     unsigned long long* pool_cursor;
     uint32_t allowed_mismatches;
-    // deferred reads: written by k_map_lanes, consumed by k_map (list != nullptr: map list[0..*list_count))
+    // deferred reads: written by k_map_thread, consumed by k_map (list != nullptr: map list[0..*list_count))
     uint32_t* list;
     unsigned long long* list_count;
     unsigned long long* work_cursor;  // k_map over the list: next entry to claim (zeroed per batch), or nullptr
     // k_map in two launches (the first one overlaps k_seed_scan and the second pass of the thread kernel on another stream):
     const unsigned long long* list_first;  // first entry of this launch (nullptr: 0)
     const unsigned long long* list_end;    // one past its last entry (nullptr: *list_count)
-    unsigned long long* lane_cursor;  // k_map_lanes: [0] next read of the first pass, [1] next entry of the seeded list
-    uint32_t lane_words;              // k_map_lanes: words of a lane's shared-memory read slot
-    // reads whose FIRST seed search was too long for one thread: k_map_lanes -> k_seed_scan
+    // reads whose FIRST seed search was too long for one thread: k_map_thread -> k_seed_scan
     uint32_t* scan_list;
     unsigned long long* scan_count;
-    // reads k_seed_scan found a seed for: {read, pos, node, off} -> second pass of k_map_lanes
+    // reads k_seed_scan found a seed for: {read, pos, node, off} -> second pass of k_map_thread
     uint4* seeded;
     unsigned long long* seeded_count;
     uint4* seeded_ev;             // event counting only: {lookups, levels, hits, verifs} of that search
     uint32_t max_probes;          // seed positions one thread tries in a read's first search
     uint32_t reseed_probes;       // k_map_thread: ... and in a re-seed search (first pass: small, the read is redone by the second pass)
-    uint32_t max_small;           // k_map_lanes: largest smallest-class one thread intersects
+    uint32_t max_small;           // k_map_thread: largest smallest-class one thread intersects
     uint32_t* status;             // bit0: novel buffer overflow, bit1: spill pool overflow
-    unsigned long long* events;   // 3 x psa_events layout ([0] k_map_lanes, [1] k_map, [2] k_seed_scan), or nullptr
+    unsigned long long* events;   // 3 x psa_events layout ([0] k_map_thread, [1] k_map, [2] k_seed_scan), or nullptr
 };
 
 struct LaneEvents {
@@ -841,20 +839,7 @@ __global__ void __launch_bounds__(256) k_map(const __grid_constant__ DevIndex ix
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// the fast map kernel: one lane per read STEP.  Every read in flight is a 136-byte state record
-// (psa_lanes.cuh Lane) in shared memory; a warp owns a pool of 32 * J of them.  Each iteration
-// the warp counts its pool by state, takes the most populous state, gathers up to 32 reads that
-// are in it and advances them by one step -- all 32 lanes run the same block of the state machine
-// on different reads, fetch their sectors with the same load instructions and write the records
-// back.  When a step leaves a read waiting for data, the lane prefetches those sectors into L2, so
-// that by the time the read's state comes up again its loads are L2 hits.  Finished reads are
-// replaced from a counter.  (A first version kept one read per lane in registers and ran every
-// block present in the warp each iteration: 8 states -> ~5 active lanes per block, 3.3 G warp
-// instructions per batch against round 1's 1.7 G -- profiles/r2_ncu_config3.md.)
-// Reads a lane gives up are appended to p.scan_list (first seed search too long -> k_seed_scan) or
-// p.list (-> k_map).  HINT = true: the reads of p.seeded, whose first seed search k_seed_scan made.
-// ---------------------------------------------------------------------------------------------
+// where the thread-per-read kernel puts a finished read's result
 struct DevSink {
     const MapParams& p;
     __device__ __forceinline__ void result(uint32_t r, const HitRec& h, uint64_t count_slot) {
@@ -873,261 +858,6 @@ struct DevSink {
     }
     __device__ __forceinline__ void novel_overflow() { atomicOr(p.status, 1u); }
 };
-struct SmemWords {  // a read's packed words in shared memory: word j at base[j * stride]
-    uint64_t* base;
-    uint32_t stride;
-    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return base[i * stride]; }
-    __device__ __forceinline__ void store(uint32_t i, uint64_t v) { base[i * stride] = v; }
-};
-__device__ __forceinline__ Sector ld_sector_policy(const void* a, uint64_t policy) {
-    Sector s;
-    asm("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
-        : "=l"(s.w0), "=l"(s.w1), "=l"(s.w2), "=l"(s.w3) : "l"(a), "l"(policy));
-    return s;
-}
-__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
-
-#ifndef PSA_POOL_WARPS
-#define PSA_POOL_WARPS 4      // warps per CTA
-#endif
-#ifndef PSA_POOL_J
-#define PSA_POOL_J 4          // reads in flight per lane: a warp's pool holds 32 * J
-#endif
-#ifndef PSA_POOL_CTAS
-#define PSA_POOL_CTAS 2       // CTAs per SM the shared memory is sized for
-#endif
-constexpr int kPoolWarps = PSA_POOL_WARPS;
-constexpr int kPoolItems = 32 * PSA_POOL_J;
-constexpr uint32_t kLaneChunk = 256;     // reads a warp claims at a time
-constexpr uint32_t kLaneMaxWords = 8;    // longest read a lane takes: 256 bases (longer ones go to k_map)
-#ifndef PSA_POOL_REFILL
-#define PSA_POOL_REFILL 8
-#endif
-constexpr uint32_t kRefillMin = PSA_POOL_REFILL;   // free items that trigger a refill pass
-static_assert(kPoolItems <= 128 && (PSA_POOL_J & (PSA_POOL_J - 1)) == 0, "pool counters are eight bits; J a power of two");
-
-template <int KW, bool EV>
-__host__ __device__ constexpr size_t pool_bytes_per_warp(uint32_t lane_words) {
-    return (size_t)kPoolItems * (sizeof(Lane<KW, EV>) + (size_t)lane_words * 8 + 1) + 32 * 4;
-}
-
-template <int KW, bool EV, bool HINT>
-__global__ void __launch_bounds__(32 * kPoolWarps, PSA_POOL_CTAS) k_map_lanes(const __grid_constant__ DevIndex ix,
-                                                                              const __grid_constant__ MapParams p) {
-    extern __shared__ __align__(16) uint8_t pool_smem[];
-    using LaneT = Lane<KW, EV>;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lw = p.lane_words;
-    // this warp's pool: [records | read words (word j of item q at [j * items + q]) | state bytes | gather list]
-    uint8_t* base = pool_smem + warp * pool_bytes_per_warp<KW, EV>(lw);
-    LaneT* recs = reinterpret_cast<LaneT*>(base);
-    uint64_t* words = reinterpret_cast<uint64_t*>(base + (size_t)kPoolItems * sizeof(LaneT));
-    uint8_t* stb = reinterpret_cast<uint8_t*>(words + (size_t)kPoolItems * lw);
-    uint32_t* sel = reinterpret_cast<uint32_t*>(stb + kPoolItems);
-
-    DevSink sink{p};
-    LaneParams lp;
-    lp.allowed = p.allowed_mismatches; lp.max_probes = p.max_probes; lp.max_small = p.max_small;
-    lp.want_members = p.novel != nullptr;
-    lp.to_scan = !HINT && p.scan_list != nullptr;
-    const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
-    unsigned long long* cursor = p.lane_cursor + (HINT ? 1 : 0);
-    const uint64_t pol_first = l2_policy_first(), pol_last = l2_policy_last();
-    uint64_t w_next = 0, w_end = 0;  // the warp's claimed range of reads (uniform)
-    bool exhausted = false;
-    ThreadEvents tot{};
-    uint64_t ev_reads = 0, ev_bases = 0, ev_out = 0, ev_aligned = 0;
-
-    // lane l owns the state bytes of items 4l .. 4l+3 (J = 4) for counting; any lane may step any item
-    uint32_t* stw = reinterpret_cast<uint32_t*>(stb);
-    for (int j = 0; j < PSA_POOL_J; j++) stb[PSA_POOL_J * lane + j] = LS_NEW;
-    __syncwarp();
-
-    for (uint32_t iter = 0;; iter++) {
-        // ---- count the pool by state (four bits of state -> 16 eight-bit counters in four words)
-        uint32_t mine[PSA_POOL_J];
-#pragma unroll
-        for (int j = 0; j < PSA_POOL_J; j++) mine[j] = stb[PSA_POOL_J * lane + j];
-        uint32_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-#pragma unroll
-        for (int j = 0; j < PSA_POOL_J; j++) {
-            const uint32_t b = mine[j], inc = 1u << (8 * (b & 3));
-            h0 += (b >> 2) == 0 ? inc : 0; h1 += (b >> 2) == 1 ? inc : 0; h2 += (b >> 2) == 2 ? inc : 0; h3 += (b >> 2) == 3 ? inc : 0;
-        }
-        h0 = __reduce_add_sync(kFull, h0); h1 = __reduce_add_sync(kFull, h1);
-        h2 = __reduce_add_sync(kFull, h2); h3 = __reduce_add_sync(kFull, h3);
-        const uint32_t n_free = h0 & 0xff;  // LS_NEW == 0
-
-        // ---- refill: free items take the next reads
-        // (not for every single finished read: a refill pass costs as much as a short step)
-        if (n_free && !exhausted && (n_free >= kRefillMin || (h0 >> 8) + h1 + h2 + h3 == 0)) {
-            uint32_t given = 0;
-#pragma unroll
-            for (int j = 0; j < PSA_POOL_J; j++) {
-                const bool fre = mine[j] == LS_NEW;
-                unsigned need = __ballot_sync(kFull, fre);
-                while (need && !exhausted) {
-                    if (w_next == w_end) {
-                        unsigned long long at = 0;
-                        if (lane == 0) at = atomicAdd(cursor, (unsigned long long)kLaneChunk);
-                        at = __shfl_sync(kFull, at, 0);
-                        if (at >= n_todo) {
-                            exhausted = true;
-                            break;
-                        }
-                        w_next = at;
-                        w_end = at + kLaneChunk < n_todo ? at + kLaneChunk : n_todo;
-                    }
-                    const uint64_t it = w_next + __popc(need & ((1u << lane) - 1));
-                    const bool take = ((need >> lane) & 1u) && it < w_end;
-                    if (take) {
-                        uint64_t r = it;
-                        uint32_t hint[3];
-                        if (HINT) {
-                            const uint4 e = p.seeded[it];
-                            r = e.x;
-                            hint[0] = e.y; hint[1] = e.z; hint[2] = e.w;
-                        }
-                        const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-                        const uint32_t q = PSA_POOL_J * lane + j;
-                        LaneT& ln = recs[q];
-                        ln.idle();
-                        ln.begin((uint32_t)r, L, lw, HINT ? hint : nullptr);
-                        if (EV && HINT) ln.why = (uint32_t)it;   // (the entry of p.seeded_ev, should the read be handed over)
-                        stb[q] = (uint8_t)ln.st;
-                        mine[j] = ln.st;
-                        const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
-                        prefetch_l2(p.reads.words + wo);
-                        if (((L + 31) >> 5) > 4) prefetch_l2(p.reads.words + wo + 4);
-                    }
-                    const unsigned taken = __ballot_sync(kFull, take);
-                    w_next += __popc(taken);
-                    given += __popc(taken);
-                    need &= ~taken;
-                }
-            }
-            if (given) {
-                __syncwarp();
-                continue;  // count again
-            }
-        }
-
-        // ---- the most populous state (LS_NEW and LS_IDLE excepted)
-        uint32_t best = 0, best_n = 0;
-#pragma unroll
-        for (int sidx = 1; sidx < LS_IDLE; sidx++) {
-            const uint32_t w = sidx < 4 ? h0 : sidx < 8 ? h1 : sidx < 12 ? h2 : h3;
-            const uint32_t c = (w >> (8 * (sidx & 3))) & 0xff;
-            if (c > best_n) { best_n = c; best = sidx; }
-        }
-        if (best_n == 0) {
-            if (exhausted) break;   // nothing in flight, nothing left
-            continue;               // (cannot happen: a non-exhausted warp refills above)
-        }
-        // ---- gather up to 32 items that are in it (the item order rotates so that none is passed over for long)
-        uint32_t basei = 0;
-#pragma unroll
-        for (int jj = 0; jj < PSA_POOL_J; jj++) {
-            const int j = (jj + iter) & (PSA_POOL_J - 1);
-            uint32_t mj = 0;
-#pragma unroll
-            for (int t = 0; t < PSA_POOL_J; t++) mj = t == j ? mine[t] : mj;
-            const bool in = mj == best;
-            const unsigned m = __ballot_sync(kFull, in);
-            const uint32_t idx = basei + __popc(m & ((1u << lane) - 1));
-            if (in && idx < 32) sel[idx] = PSA_POOL_J * lane + j;
-            basei += __popc(m);
-        }
-        const uint32_t n_sel = basei < 32 ? basei : 32;
-        __syncwarp();
-
-        // ---- one step for each of them
-        uint32_t emit = LE_NONE, handed_r = 0, why = 0;
-        if (lane < n_sel) {
-            const uint32_t q = sel[lane];
-            LaneT& ln = recs[q];
-            SmemWords rw{words + q, (uint32_t)kPoolItems};
-            Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
-            if (best == LS_READ) {
-                const uint64_t r = ln.r;
-                const uint64_t* src = p.reads.words + (p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride);
-                const uint32_t nw = (ln.L + 31) >> 5;
-                A.w0 = nw > 0 ? src[0] : 0; A.w1 = nw > 1 ? src[1] : 0;
-                A.w2 = nw > 2 ? src[2] : 0; A.w3 = nw > 3 ? src[3] : 0;
-                if (nw > 4) {
-                    C.w0 = src[4]; C.w1 = nw > 5 ? src[5] : 0;
-                    C.w2 = nw > 6 ? src[6] : 0; C.w3 = nw > 7 ? src[7] : 0;
-                }
-            } else {
-                const LaneRequests rq = ln.requests(ix);
-                if (rq.a) A = ld_sector_policy(rq.a, rq.a_stream ? pol_first : pol_last);
-                if (rq.b) B = ld_sector_policy(rq.b, pol_last);
-                if (rq.c) {
-                    C.w0 = ld_u64_last(rq.c); C.w1 = ld_u64_last(rq.c + 1);
-                    C.w2 = ld_u64_last(rq.c + 2); C.w3 = ld_u64_last(rq.c + 3);
-                }
-            }
-            const uint32_t seeded_at = ln.why;
-            const StepOut so = ln.step(ix, lp, rw, A, B, C, sink);
-            emit = so.emit;
-            stb[q] = (uint8_t)ln.st;
-            if (emit == LE_NONE) {
-                // the sectors the read's next step needs: on their way to L2 while other reads are stepped
-                const LaneRequests nx = ln.requests(ix);
-                if (nx.a) prefetch_l2(nx.a);
-                if (nx.c) {
-                    prefetch_l2(nx.c);
-                    prefetch_l2(nx.c + 3);
-                }
-            } else {
-                handed_r = ln.r;
-                why = ln.why;
-                if constexpr (EV) if (p.events) {
-                    if (emit == LE_RESULT) {
-                        const ThreadEvents& e = ln.ev;
-                        tot.lookups += e.lookups; tot.levels += e.levels; tot.hits += e.hits; tot.verifs += e.verifs;
-                        tot.visits += e.visits; tot.bases += e.bases; tot.jumps += e.jumps; tot.members += e.members;
-                        ev_reads++; ev_bases += ln.L; ev_out += so.n_tx; ev_aligned += so.aligned ? 1 : 0;
-                    } else {
-                        if (why < 4) atomicAdd(p.events + 36 + why, 1ULL);
-                        if (HINT) {  // k_map redoes this read from scratch and counts its first search again
-                            const uint4 sev = p.seeded_ev[seeded_at];
-                            atomicAdd(p.events + 24 + 2, 0ULL - sev.x); atomicAdd(p.events + 24 + 3, 0ULL - sev.y);
-                            atomicAdd(p.events + 24 + 4, 0ULL - sev.z); atomicAdd(p.events + 24 + 5, 0ULL - sev.w);
-                        }
-                    }
-                }
-            }
-        }
-        // ---- hand the given-up reads over (one atomic per warp and list)
-        const unsigned bs = __ballot_sync(kFull, emit == LE_TO_SCAN);
-        if (bs) {
-            unsigned long long at = 0;
-            if (lane == (unsigned)(__ffs(bs) - 1)) at = atomicAdd(p.scan_count, (unsigned long long)__popc(bs));
-            at = __shfl_sync(kFull, at, __ffs(bs) - 1);
-            if (emit == LE_TO_SCAN) p.scan_list[at + __popc(bs & ((1u << lane) - 1))] = handed_r;
-        }
-        const unsigned bc = __ballot_sync(kFull, emit == LE_TO_COOP);
-        if (bc) {
-            unsigned long long at = 0;
-            if (lane == (unsigned)(__ffs(bc) - 1)) at = atomicAdd(p.list_count, (unsigned long long)__popc(bc));
-            at = __shfl_sync(kFull, at, __ffs(bc) - 1);
-            if (emit == LE_TO_COOP) p.list[at + __popc(bc & ((1u << lane) - 1))] = handed_r;
-        }
-        __syncwarp();
-    }
-    if (EV && p.events) {
-        unsigned long long v[12] = {ev_reads, ev_bases, tot.lookups, tot.levels, tot.hits, tot.verifs,
-                                    tot.visits, tot.bases, tot.jumps, tot.members, ev_out, ev_aligned};
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            unsigned long long x = v[i];
-#pragma unroll
-            for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
-            if (lane == 0 && x) atomicAdd(p.events + i, x);
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // the thread-per-read kernel in its blocking form (psa_thread.cuh): read r = global thread id, one
@@ -1142,9 +872,6 @@ __global__ void __launch_bounds__(32 * kPoolWarps, PSA_POOL_CTAS) k_map_lanes(co
 constexpr int kThreadBlock = PSA_THREAD_BLOCK;
 #ifndef PSA_THREAD_MIN_BLOCKS
 #define PSA_THREAD_MIN_BLOCKS 16
-#endif
-#ifndef PSA_THREAD_PERSIST
-#define PSA_THREAD_PERSIST 0
 #endif
 template <int KW, bool EV, bool HINT, bool TILE = false>
 __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thread(const __grid_constant__ DevIndex ix,
@@ -1176,30 +903,6 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
         my_words = pw + threadIdx.x * nw;
     }
     DevSink sink{p};
-#if PSA_THREAD_PERSIST
-    // Persistent lanes: every thread strides over the batch and starts its next read as soon as it is done with one,
-    // so that no lane idles behind the slowest read of its warp (hand-overs: one atomic per read instead of per warp).
-    if (!HINT && !EV && !TILE) {
-        const uint64_t total = gridDim.x * (uint64_t)blockDim.x;
-        for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < p.reads.n; r += total) {
-            const uint64_t wo = p.reads.woff ? p.reads.woff[r] : r * p.reads.wstride;
-            const uint32_t L = p.reads.len ? p.reads.len[r] : p.reads.fixed_len;
-            ThreadResult res = map_read_thread<KW, false>(ix, PLoad{p.reads.words + wo}, (uint32_t)r, L, p.allowed_mismatches,
-                                                          p.max_probes, p.reseed_probes, p.max_small, sink, p.novel != nullptr, nullptr, nullptr);
-            if (!res.deferred) {
-                sink.result((uint32_t)r, res.hit, res.count_slot);
-                if (res.novel_overflow) sink.novel_overflow();
-            } else if (res.why == 0 && p.scan_list != nullptr) {
-                p.scan_list[atomicAdd(p.scan_count, 1ULL)] = (uint32_t)r;
-            } else if (res.why == 1 && p.seeded != nullptr) {
-                p.seeded[atomicAdd(p.seeded_count, 1ULL)] = make_uint4((uint32_t)r, kNone, 0u, 0u);
-            } else {
-                p.list[atomicAdd(p.list_count, 1ULL)] = (uint32_t)r;
-            }
-        }
-        return;
-    }
-#endif
     const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
     const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
     // warp-uniform trip count: the hand-over below uses full-warp votes

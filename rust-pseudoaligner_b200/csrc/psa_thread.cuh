@@ -4,8 +4,8 @@
 // needs something a single thread does badly: a seed search longer than max_probes positions, more wide
 // classes than ClassAcc keeps, or only wide classes with a smallest one of more than max_small members.
 // Deferred reads are redone from scratch by the cooperative kernels, so the split never changes a result.
-// (psa_lanes.cuh is the same control flow cut at every load; which of the two the mapper launches is a
-// measured choice, see profiles/.)
+// (A formulation cut at every load -- persistent warps over pools of reads in flight -- and one with a read per lane
+// refilled as reads end were measured and rejected: profiles/r2_exp_walk_kernel.md.)
 #pragma once
 #include "psa_core.cuh"
 
@@ -85,18 +85,28 @@ struct ThreadCtx {
         if (EV && p != kNone) ev.jumps++;
         return p;
     }
-    // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step
+    // ref src/pseudoaligner.rs:234-255 (FWD) and :149-170 (backward), 32 bases per step.  Forward, the mismatches of a
+    // window are only counted; the bit reversal that puts them in base order is needed for the one window in which the
+    // budget runs out.  (Carrying each word into the next step instead of loading it twice was measured slower: 2.49 vs
+    // 2.36 ms per batch -- the second load is an L1 hit and the carried words cost registers.)
     template <bool FWD, class P>
     PSA_HD P cmp(P rp, uint64_t sp, P m, uint32_t A, bool& premature) {
         uint32_t snp = 0;
         for (P my = 0; my < m; my += 32) {
-            uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
-            uint64_t mask = FWD ? mismatch_fwd(rd, rp + my, GLoad{ix.seq}, sp + my, n)
-                                : mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);
-            uint32_t c = (uint32_t)popc64(mask);
+            const uint32_t n = m - my < 32 ? (uint32_t)(m - my) : 32u;
+            uint64_t mask;
+            uint32_t c;
+            if (FWD) {
+                mask = seq_bits(rd, rp + my, n) ^ seq_bits(GLoad{ix.seq}, sp + my, n);   // base t of the window at bits 2(n-1-t)
+                c = (uint32_t)popc64(fold_pairs(mask));
+            } else {
+                mask = mismatch_bwd(rd, rp - my, GLoad{ix.seq}, sp - my, n);            // base t at bit 2t
+                c = (uint32_t)popc64(mask);
+            }
             if (snp + c > A) {
                 premature = true;
-                P matched = my + nth_mismatch(mask, A + 1 - snp);
+                if (FWD) mask = fold_pairs(rev_pairs(mask) >> (64 - 2 * n));              // base t at bit 2t
+                const P matched = my + nth_mismatch(mask, A + 1 - snp);
                 if (EV) ev.bases += (uint32_t)matched + 1;
                 return matched;
             }

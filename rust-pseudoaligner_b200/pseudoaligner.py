@@ -523,7 +523,7 @@ class Mapper:
         _check(lib().psa_mapper_sync(self.h))
 
     def map_device_events(self, batch, split=False):
-        """Event counts of one batch; split=True -> per kernel (k_map_lanes, k_map, k_seed_scan)."""
+        """Event counts of one batch; split=True -> per kernel (k_map_thread, k_map, k_seed_scan)."""
         ev = (_Events * 3)()
         _check(lib().psa_mapper_map_events(self.h, C.byref(batch.rb), C.byref(batch.ob), C.byref(ev)))
         parts = [{f: int(getattr(e, f)) for f in EVENT_FIELDS} for e in ev]

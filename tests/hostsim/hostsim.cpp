@@ -1,9 +1,9 @@
 // hostsim.cpp -- UNIT-TEST HARNESS, not product code.
 //
-// Compiles rust-pseudoaligner_b200/csrc/psa_core.cuh and psa_lanes.cuh (the __host__ __device__
+// Compiles rust-pseudoaligner_b200/csrc/psa_core.cuh and psa_thread.cuh (the __host__ __device__
 // arithmetic the CUDA kernels are made of: 2-bit access, k-mer hash, the bucket-cascade dictionary,
-// fingerprint + verification, per-word mismatch masks, class windows, the map_read state machine in
-// its blocking form and as the per-lane state machine of the thread-per-read kernel) with g++ and
+// fingerprint + verification, per-word mismatch masks, class windows, the map_read state machine under
+// the cooperative policy and under the thread-per-read policy with its hand-overs) with g++ and
 // serial drivers, so that the tests that run without a GPU can compare that text against the oracle.
 // It is built into tests/hostsim/libhostsim.so, loaded only by tests/test_hostsim.py, and never
 // linked into libpsa_b200.so -- the product has no CPU path.
@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "../../rust-pseudoaligner_b200/csrc/psa_core.cuh"
-#include "../../rust-pseudoaligner_b200/csrc/psa_lanes.cuh"
+#include "../../rust-pseudoaligner_b200/csrc/psa_thread.cuh"
 #include "../../rust-pseudoaligner_b200/csrc/psa_thread.cuh"
 
 using namespace psa;
@@ -272,17 +272,7 @@ uint64_t hs_map_batch(const HsIndex* ix, const uint64_t* words, const uint64_t* 
 
 }  // extern "C"
 
-// The thread-per-read kernel's lane state machine (psa_lanes.cuh), driven serially: the requests a
-// step makes are served from host memory before the next step, exactly as k_map_lanes serves them
-// from HBM.  Reads a lane hands over are redone by the serial stand-in of the cooperative kernel --
-// the same split the product makes between k_map_lanes and k_seed_scan / k_map.  `hinted` != 0
-// imitates the second pass: the first seed of every read is searched by the serial policy and given
-// to the lane as k_seed_scan would.
-struct HostWords {
-    uint64_t w[8];
-    uint64_t operator()(uint64_t i) const { return w[i]; }
-    void store(uint32_t i, uint64_t v) { w[i] = v; }
-};
+// what the thread-per-read policy delivers a finished read to
 struct HostSink {
     HsHit* hit;
     std::vector<uint32_t> novel_buf;
@@ -299,83 +289,7 @@ struct HostSink {
     void novel_overflow() {}
 };
 
-template <int KW>
-static uint32_t lane_one(const HsIndex* ix, const uint64_t* words, uint32_t L, const LaneParams& lp, const uint32_t* hint,
-                         HsHit& h, std::vector<uint32_t>& tx, uint64_t* steps) {
-    Lane<KW, false> ln;
-    static_assert(sizeof(Lane<KW, false>) == 136, "the lane record is sized for shared memory");
-    ln.idle();
-    ln.begin(0, L, 8, hint);
-    HostWords rw{};
-    HostSink sink{&h, {}};
-    Sector A{0, 0, 0, 0}, B{0, 0, 0, 0}, C{0, 0, 0, 0};
-    const uint32_t nw = (L + 31) / 32;
-    uint32_t emit = LE_NONE;
-    for (;;) {
-        // payloads are NOT kept between steps (the pool kernel reloads them): poison them
-        A = Sector{~0ULL, ~0ULL, ~0ULL, ~0ULL}; B = A; C = A;
-        if (ln.st == LS_READ) {
-            A.w0 = nw > 0 ? words[0] : 0; A.w1 = nw > 1 ? words[1] : 0; A.w2 = nw > 2 ? words[2] : 0; A.w3 = nw > 3 ? words[3] : 0;
-            if (nw > 4) { C.w0 = words[4]; C.w1 = nw > 5 ? words[5] : 0; C.w2 = nw > 6 ? words[6] : 0; C.w3 = nw > 7 ? words[7] : 0; }
-        } else {
-            const LaneRequests q = ln.requests(ix->d);
-            if (q.a) A = load_sector_hot(q.a);
-            if (q.b) B = load_sector_hot(q.b);
-            if (q.c) { C.w0 = q.c[0]; C.w1 = q.c[1]; C.w2 = q.c[2]; C.w3 = q.c[3]; }
-        }
-        emit = ln.step(ix->d, lp, rw, A, B, C, sink).emit;
-        if (steps) (*steps)++;
-        if (emit != LE_NONE) break;
-    }
-    if (emit == LE_RESULT) {
-        h.tx_off = tx.size();
-        const uint32_t* src = h.eq_id != kNone ? ix->eq_mem.data() + ix->eq_off[h.eq_id] : sink.novel_buf.data();
-        tx.insert(tx.end(), src, src + h.n_tx);
-    }
-    return emit;
-}
-
 extern "C" {
-
-uint64_t hs_map_batch_lanes(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,
-                            const uint32_t* read_len, uint64_t n, uint32_t allowed, uint32_t max_probes,
-                            uint32_t max_small, int hinted, HsHit* hits, uint32_t* tx_buf, uint64_t tx_cap,
-                            uint64_t* n_deferred, uint64_t* n_steps) {
-    std::vector<uint32_t> tx;
-    uint64_t nd = 0, steps = 0;
-    LaneParams lp;
-    lp.allowed = allowed; lp.max_probes = max_probes; lp.max_small = max_small; lp.want_members = true; lp.to_scan = !hinted;
-    for (uint64_t i = 0; i < n; i++) {
-        const uint64_t* q = words + read_off[i];
-        const uint32_t L = read_len[i];
-        uint32_t hint[3];
-        bool have_hint = false;
-        if (hinted && L >= ix->d.k) {  // the first search, as k_seed_scan makes it
-            uint32_t pos = 0, node = 0, off = 0;
-            bool found;
-            if (ix->kw == 1) { SerialWarp<1> w{ix->d, PLoad{q}, ix->d.k, {}, {}}; found = w.find_seed(pos, L - ix->d.k, node, off); }
-            else { SerialWarp<2> w{ix->d, PLoad{q}, ix->d.k, {}, {}}; found = w.find_seed(pos, L - ix->d.k, node, off); }
-            if (found) { hint[0] = pos; hint[1] = node; hint[2] = off; have_hint = true; }
-            else {  // no seed at all: k_seed_scan finishes the read
-                hits[i].coverage = 0; hits[i].n_tx = 0; hits[i].tx_off = tx.size(); hits[i].eq_id = kNone; hits[i].flags = 0;
-                continue;
-            }
-        }
-        uint32_t emit;
-        if (ix->kw == 1) emit = lane_one<1>(ix, q, L, lp, have_hint ? hint : nullptr, hits[i], tx, &steps);
-        else emit = lane_one<2>(ix, q, L, lp, have_hint ? hint : nullptr, hits[i], tx, &steps);
-        if (emit != LE_RESULT) {
-            nd++;
-            if (ix->kw == 1) map_one<1>(ix, q, L, allowed, hits[i], tx);
-            else map_one<2>(ix, q, L, allowed, hits[i], tx);
-        }
-    }
-    if (n_deferred) *n_deferred = nd;
-    if (n_steps) *n_steps = steps;
-    memcpy(tx_buf, tx.data(), std::min<uint64_t>(tx.size(), tx_cap) * 4);
-    return tx.size();
-}
-
 // The blocking thread-per-read policy (psa_thread.cuh ThreadCtx / map_read_thread), hand-overs redone by the
 // serial stand-in of the cooperative kernel.
 uint64_t hs_map_batch_thread(const HsIndex* ix, const uint64_t* words, const uint64_t* read_off,

@@ -300,7 +300,7 @@ def test_constructed_branches(fixture_fasta):
     for name, read in named.items():
         reads = [read.decode()]
         want_hits, want_tx, _, want_ev = _oracle(ix, reads)
-        for probes, scan in ((64, 0), (3, 8), (0, 8)):        # the lanes alone / lanes + seed scan / cooperative kernel alone
+        for probes, scan in ((64, 0), (3, 8), (0, 8)):        # the thread kernel alone / with the seed scan / cooperative kernel alone
             pa.mapper.set_fast_path(probes, 32)
             pa.mapper.set_scan_width(scan)
             got_hits, got_tx = pa.mapper.map_ascii(reads)
@@ -629,11 +629,7 @@ def test_novel_sets(fixture_fasta, monkeypatch, table_cap):
     assert len(want_tab) > 50 and any(len(m) == 0 for m, _ in want_tab) and any(c > 1 for _, c in want_tab)
     pa = pkg.Pseudoaligner(ix.flat(), device=0, chunk_reads=700)
     n_eq = pa.index.n_eq
-    for probes, scan, lanes in ((None, None, False), (0, 8, False), (64, 0, False), (3, 8, True)):
-        if lanes:
-            monkeypatch.setenv("PSA_FAST_KERNEL", "lanes")
-            pa.close()
-            pa = pkg.Pseudoaligner(ix.flat(), device=0, chunk_reads=700)
+    for probes, scan in ((None, None), (0, 8), (64, 0), (3, 8)):
         if probes is not None:
             pa.mapper.set_fast_path(probes, 32)
             pa.mapper.set_scan_width(scan)

@@ -4,8 +4,8 @@ tests/hostsim/ compiles rust-pseudoaligner_b200/csrc/psa_core.cuh with g++ and a
 policy; here its results are compared with the oracle read by read.  This pins, without a
 GPU: the bucket-cascade dictionary layout + fingerprint + verification, the
 successor/predecessor tables, the mismatch masks of both extension loops, the map_read state
-machine in its blocking form (cooperative kernels) AND as the per-lane state machine of the
-thread-per-read kernel (psa_lanes.cuh, every request served serially), class windows, and ASCII
+machine under the cooperative policy AND under the thread-per-read policy (psa_thread.cuh, its
+hand-overs redone by the serial stand-in of the cooperative kernel), class windows, and ASCII
 packing.  (The warp-level glue itself is covered by the `-m gpu` parity tests.)"""
 import ctypes as C
 import os
@@ -37,8 +37,6 @@ def hs():
     L.hs_map_batch.argtypes = [vp, vp, vp, vp, u64, u32, vp, vp, u64]
     L.hs_map_batch_thread.restype = u64
     L.hs_map_batch_thread.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, vp, vp, u64, C.POINTER(u64)]
-    L.hs_map_batch_lanes.restype = u64
-    L.hs_map_batch_lanes.argtypes = [vp, vp, vp, vp, u64, u32, u32, u32, C.c_int, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.hs_pack_ascii.argtypes = [C.c_char_p, u64, vp]
     return L
 
@@ -68,21 +66,6 @@ class HsIndex:
                 return hits, tx[:need]
             cap = int(need)
 
-    def map_batch_lanes(self, words, off, lens, max_probes, max_small, allowed=2, hinted=False):
-        """The thread-per-read kernel's lane state machine, hand-overs redone by the serial policy.
-        -> (hits, tx, reads handed over, steps made)"""
-        n = len(lens)
-        hits = np.zeros(n, dtype=orc.HIT_DTYPE)
-        cap = max(64 * n, 4096)
-        nd, ns = C.c_uint64(), C.c_uint64()
-        while True:
-            tx = np.zeros(cap, np.uint32)
-            need = self.L.hs_map_batch_lanes(self.h, _p(words), _p(off), _p(lens), n, allowed, max_probes, max_small,
-                                             1 if hinted else 0, _p(hits), _p(tx), cap, C.byref(nd), C.byref(ns))
-            if need <= cap:
-                return hits, tx[:need], int(nd.value), int(ns.value)
-            cap = int(need)
-
     def map_batch_thread(self, words, off, lens, max_probes, max_small, allowed=2):
         """The blocking thread-per-read policy, hand-overs redone by the serial policy."""
         n = len(lens)
@@ -101,7 +84,7 @@ class HsIndex:
         self.L.hs_index_destroy(self.h)
 
 
-def _compare(ix_orc, ix_hs, reads, lane_cfgs=((1, 4, False), (3, 64, False), (64, 1 << 30, False), (10, 32, True)), allowed=2):
+def _compare(ix_orc, ix_hs, reads, cfgs=((1, 4), (3, 64), (64, 1 << 30), (10, 32), (11, 32)), allowed=2):
     words, off, lens = orc.pack_reads(reads)
     h1, t1, _, _ = ix_orc.map_batch(words, off, lens, allowed=allowed)
     h2, t2 = ix_hs.map_batch(words, off, lens, allowed=allowed)
@@ -109,41 +92,32 @@ def _compare(ix_orc, ix_hs, reads, lane_cfgs=((1, 4, False), (3, 64, False), (64
     for i, (x, y) in enumerate(zip(a, b)):
         assert x == y, (i, reads[i], x, y)
     assert np.array_equal(h1["eq_id"], h2["eq_id"])
-    # the lane state machine with its hand-overs: same results whatever the split, with and without a given first seed
-    for max_probes, max_small, hinted in lane_cfgs:
-        h3, t3, nd, _ = ix_hs.map_batch_lanes(words, off, lens, max_probes, max_small, allowed=allowed, hinted=hinted)
-        c = orc.hits_to_tuples(h3, t3)
-        for i, (x, y) in enumerate(zip(a, c)):
-            assert x == y, ("lanes", max_probes, max_small, hinted, i, reads[i], x, y)
-        assert np.array_equal(h1["eq_id"], h3["eq_id"])
-        assert np.array_equal(t1, t3)
+    # the thread-per-read policy with its hand-overs: same results whatever the split
+    for max_probes, max_small in cfgs:
+        h4, t4, nd = ix_hs.map_batch_thread(words, off, lens, max_probes, max_small, allowed=allowed)
+        d = orc.hits_to_tuples(h4, t4)
+        for i, (x, y) in enumerate(zip(a, d)):
+            assert x == y, ("thread", max_probes, max_small, i, reads[i], x, y)
+        assert np.array_equal(h1["eq_id"], h4["eq_id"]) and np.array_equal(t1, t4)
         _DEFER[(max_probes, max_small)] = _DEFER.get((max_probes, max_small), 0) + nd
         _DEFER["reads"] = _DEFER.get("reads", 0) + len(reads)
-        if not hinted:   # the same split by the blocking thread-per-read policy
-            h4, t4, _ = ix_hs.map_batch_thread(words, off, lens, max_probes, max_small, allowed=allowed)
-            d = orc.hits_to_tuples(h4, t4)
-            for i, (x, y) in enumerate(zip(a, d)):
-                assert x == y, ("thread", max_probes, max_small, i, reads[i], x, y)
-            assert np.array_equal(h1["eq_id"], h4["eq_id"]) and np.array_equal(t1, t4)
     return a
 
 
 _DEFER = {}
 
 
-def test_lanes_hand_over_some_but_not_all(hs, orc_index_for, fixture_fasta):
-    """With one probe per seed search the lanes must hand the noisy reads over and keep the clean
-    ones; with unbounded probes only class-list overflows are handed over.  A clean 150-base read
-    takes a handful of steps (one request round trip each)."""
+def test_thread_policy_hands_over_some_but_not_all(hs, orc_index_for, fixture_fasta):
+    """With one probe per seed search a thread must hand the noisy reads over and keep the clean
+    ones; with unbounded probes only class-list overflows are handed over."""
     ix = orc_index_for(20)
     hx = HsIndex(hs, ix.flat())
     rng = np.random.default_rng(5)
     reads = util.sample_reads(rng, fixture_fasta[1], 3000, 150, p_sub=0.005)
     words, off, lens = orc.pack_reads(reads)
-    _, _, nd1, _ = hx.map_batch_lanes(words, off, lens, 1, 64)
-    _, _, nd64, steps = hx.map_batch_lanes(words, off, lens, 64, 1 << 30)
+    _, _, nd1 = hx.map_batch_thread(words, off, lens, 1, 64)
+    _, _, nd64 = hx.map_batch_thread(words, off, lens, 64, 1 << 30)
     assert 0 <= nd64 <= nd1 < len(reads) // 2 and nd1 > 0, (nd1, nd64)
-    assert 5 * len(reads) < steps < 20 * len(reads), steps / len(reads)
     hx.close()
 
 
@@ -252,7 +226,7 @@ def test_constructed_branches(hs):
     """QUIRK-1 (seed at unitig offset 0 + left extension, ref :129), QUIRK-3 (left walk over >= 2 predecessors,
     ref :199), QUIRK-2 (per-node budget), re-seed into a visited node (ref :293), break near the read's end
     (ref :287-290), read ending at a unitig end, missing right extension: constructed reads on a constructed
-    graph, the branch asserted on the oracle's walk, then blocking form and lane state machine against the oracle."""
+    graph, the branch asserted on the oracle's walk, then both policies against the oracle."""
     S, seqs = cases.constructed_transcriptome()
     ix = orc.OrcIndex.build(seqs, 20)
     reads = cases.constructed_reads(S)
