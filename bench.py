@@ -505,7 +505,10 @@ def main():
 
     t_setup = time.time()
     tr = load_transcriptome(a, host, host_threads)
-    flat, build_s = load_index(a, host, tr, rank, world, barrier, ncores if rank == 0 else host_threads)
+    # the graph (k-mer sort, colour interning, unitig compaction) is built on this rank's GPU: psa_build_graph_device
+    t_b = time.time()
+    flat, graph_stats = psa.build_graph_device(tr.codes(), tr.tx_off(), a.k, device=local_rank)
+    build_s = time.time() - t_b
     index = pkg.Index(flat, device=local_rank, gamma=a.gamma)
     info = index.info()
     # from here on (pinned batch buffers, mapper threads) the rank stays on the CPUs local to its GPU
@@ -863,7 +866,8 @@ def main():
                     "index": {key: int(info[key]) for key in ("n_nodes", "n_kmers", "n_eq", "n_eq_members",
                                                               "dict_levels", "dict_bytes", "fp_bits", "max_class_len")},
                     "collective": "ncclAllReduce(uint64 counts[n_eq+2]) once, inside the timed region" if comm else "none (1 GPU)",
-                    "host_cores": ncores, "host_affinity": affinity, "index_build_s": build_s, "setup_s": setup_s},
+                    "host_cores": ncores, "host_affinity": affinity, "index_build_s": build_s,
+                    "index_built_by": "psa_build_graph_device (graph) + psa_index_create (dictionary), both on the GPU", "setup_s": setup_s},
             "parity": parity,
             "clocks": clocks, "e2e": e2e, **e2e_extra, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "events_per_read": {key: ev[key] / ev["reads"] for key in ev if key != "reads"},

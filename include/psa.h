@@ -325,6 +325,35 @@ int psa_mapper_novel_allgather(psa_mapper*, psa_comm*, psa_novel_sets* out);
  * compared with.  chunk_bytes = 0: one random 128-byte line per warp (4 bytes per lane). ---- */
 int psa_gather_probe(int device, uint64_t table_bytes, uint32_t chunk_bytes, uint32_t iters, double* gbytes_per_s);
 
+/* ---- index construction on the device (the reference: make_dbg / debruijn's compression on the host, ref
+ * src/build_index.rs:27-179, src/equiv_classes.rs:62-91): every k-mer of every transcript of at least k bases (stranded),
+ * radix-sorted; colour = ascending de-duplicated transcript list, interned in order of first appearance over the sorted k-mers;
+ * exts = union over occurrences; unitigs = maximal paths of unique, same-colour links (ScmapCompress).  codes: one byte per
+ * base (0..3), transcript t = codes[tx_off[t] .. tx_off[t+1]).  The arrays returned (host memory, psa_built_graph_free) are
+ * exactly the fields of psa_index_desc and bit-identical to those of the host builder (psa_build_graph, psa_host.h). ---- */
+typedef struct psa_built_graph {
+    uint32_t k, reserved;
+    uint64_t n_nodes, n_kmers, n_eq, n_seq_words, n_eq_members, n_cycles;
+    uint64_t* seq_words;
+    uint64_t* node_start;
+    uint32_t* node_len;
+    uint8_t* node_exts;
+    uint32_t* node_eq;
+    uint64_t* eq_offsets;  /* n_eq + 1 */
+    uint32_t* eq_members;
+} psa_built_graph;
+int psa_build_graph_device(int device, const uint8_t* codes, const uint64_t* tx_off, uint32_t n_tx, uint32_t k, psa_built_graph* out);
+void psa_built_graph_free(psa_built_graph*);
+
+/* ---- mappability::analyze_graph (ref src/mappability.rs:120-156) on the device.  tx_gene[t] = an integer naming the
+ * gene of transcript t (ref: tx_gene_mapping, src/utils.rs:83-86); bins = MAPPABILITY_COUNTS_LEN (ref src/config.rs: 11).
+ * Out (host, n_tx x bins each, row-major): tx_multiplicity[t][j] = k-mers of unitigs whose class contains t and has j + 1
+ * transcripts (the last bin: bins or more -- ref :59-65 puts multiplicity == bins there too), gene_multiplicity likewise
+ * by the class's number of distinct genes.  total_kmer_count / fraction_unique_* (ref :54-82) are sums and ratios of a row. ---- */
+#define PSA_MAPPABILITY_COUNTS_LEN 11u
+int psa_index_mappability(psa_index*, const uint32_t* tx_gene, uint32_t n_tx, uint32_t bins, uint64_t* tx_multiplicity,
+                          uint64_t* gene_multiplicity);
+
 /* ---- measurement aid: the synthetic read stream of psa_host.h (psa_synth_reads: 90 % transcript reads with 0.5 %
  * substitutions, 5 % chimeric, 5 % random) generated ON THE DEVICE by the same counter-based generator -- read i is a
  * function of (seed, i) only, so BASELINE config 5 (10^9 reads) needs no host generation and any sample of the stream can

@@ -378,3 +378,26 @@ def hits_to_tuples(hits, tx):
         out.append((bool(h["flags"] & FLAG_ALIGNED), bool(h["flags"] & FLAG_MAPPED), tuple(tx[o:o + n].tolist()),
                     int(h["coverage"])))
     return out
+
+
+def mappability(flat, tx_gene, bins=11):
+    """CPU restatement of mappability::analyze_graph, ref src/mappability.rs:120-156 (records' add_tx_count / add_gene_count
+    :59-73): -> (tx_multiplicity, gene_multiplicity), uint64 [n_tx, bins]."""
+    k = int(flat["k"])
+    n_tx = len(tx_gene)
+    tm = np.zeros((n_tx, bins), np.uint64)
+    gm = np.zeros((n_tx, bins), np.uint64)
+    off, mem = flat["eq_offsets"], flat["eq_members"]
+    for length, eq in zip(flat["node_len"], flat["node_eq"]):          # :127 for node in index.dbg.iter_nodes()
+        num_kmer = int(length) - k + 1                                  # :128
+        members = mem[int(off[eq]):int(off[eq + 1])]                    # :130-131
+        num_tx = len(members)                                           # :133
+        if num_tx == 0:
+            continue
+        num_genes = len(set(int(tx_gene[t]) for t in members))          # :135-143
+        tb = bins - 1 if num_tx > bins else num_tx - 1                  # :59-65
+        gb = bins - 1 if num_genes > bins else num_genes - 1            # :67-73
+        for t in members:                                               # :145-149
+            tm[int(t), tb] += np.uint64(num_kmer)
+            gm[int(t), gb] += np.uint64(num_kmer)
+    return tm, gm

@@ -46,6 +46,8 @@ static int fail(int code, const std::string& msg) {
         }                                                                                          \
     } while (0)
 
+extern "C" int psa_internal_fail(int code, const char* msg) { return fail(code, msg ? msg : ""); }   // for the other translation units
+
 extern "C" const char* psa_strerror(int code) {
     switch (code) {
         case PSA_OK: return "ok";
@@ -1812,6 +1814,74 @@ extern "C" int psa_result_checksum(int device, const psa_hit* hits_dev, const ui
     if (n) k_result_checksum<<<nblocks(n, 256), 256>>>((const HitRec*)hits_dev, tx_dev, n, first_index, 0, acc.as<unsigned long long>());
     cudaError_t e = cudaMemcpy(out, acc.p, 8, cudaMemcpyDeviceToHost);
     acc.release();
+    if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
+    return PSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mappability::analyze_graph (ref src/mappability.rs:120-156) on the device: for every node, its k-mer
+// count goes into the histograms of every transcript of its class, binned by the class's number of
+// transcripts resp. distinct genes (ref :59-73: bin = multiplicity - 1, everything above the last bin
+// into the last one).
+// ---------------------------------------------------------------------------------------------
+namespace {
+// distinct genes per class (ref :136-143: eq_class.iter().map(gene).unique().count())
+__global__ void k_class_genes(const uint64_t* eq_off, const uint32_t* eq_mem, uint64_t n_eq, const uint32_t* tx_gene, uint32_t* n_genes) {
+    const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c >= n_eq) return;
+    const uint64_t o = eq_off[c], n = eq_off[c + 1] - o;
+    uint32_t distinct = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t g = tx_gene[eq_mem[o + i]];
+        bool seen = false;
+        for (uint64_t j = 0; j < i && !seen; j++) seen = tx_gene[eq_mem[o + j]] == g;
+        distinct += seen ? 0u : 1u;
+    }
+    n_genes[c] = distinct;
+}
+__global__ void k_mappability(const NodeRec* nodes, uint64_t n_nodes, uint32_t k, const uint64_t* eq_off, const uint32_t* eq_mem,
+                              const uint32_t* n_genes, uint32_t bins, unsigned long long* tx_mult, unsigned long long* gene_mult) {
+    const uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    const NodeRec nr = nodes[v];
+    const unsigned long long num_kmer = (uint32_t)(nr.start_len >> 40) - k + 1;   // :128
+    const uint64_t o = eq_off[nr.eq], num_tx = eq_off[nr.eq + 1] - o;             // :130-133
+    if (!num_tx) return;
+    const uint32_t num_genes = n_genes[nr.eq];
+    const uint32_t tb = num_tx > bins ? bins - 1 : (uint32_t)num_tx - 1;          // :59-65
+    const uint32_t gb = num_genes > bins ? bins - 1 : num_genes - 1;              // :67-73
+    for (uint64_t i = 0; i < num_tx; i++) {                                       // :145-149
+        const uint64_t tx = eq_mem[o + i];
+        atomicAdd(tx_mult + tx * bins + tb, num_kmer);
+        atomicAdd(gene_mult + tx * bins + gb, num_kmer);
+    }
+}
+}  // namespace
+extern "C" int psa_index_mappability(psa_index* ix, const uint32_t* tx_gene, uint32_t n_tx, uint32_t bins, uint64_t* tx_multiplicity,
+                                     uint64_t* gene_multiplicity) {
+    if (!ix || !tx_gene || !bins || !tx_multiplicity || !gene_multiplicity) return fail(PSA_ERR_ARG, "null argument");
+    for (uint64_t i = 0; i < ix->h_eq_mem.size(); i++)
+        if (ix->h_eq_mem[i] >= n_tx) return fail(PSA_ERR_ARG, "a class names a transcript >= n_tx");
+    CU(cudaSetDevice(ix->device));
+    DevBuf genes, ng, tm, gm;
+    int rc;
+    const size_t hist = (size_t)n_tx * bins * 8;
+    if ((rc = genes.ensure((size_t)n_tx * 4 + 4)) || (rc = ng.ensure(ix->d.n_eq * 4 + 4)) || (rc = tm.ensure(hist + 8)) || (rc = gm.ensure(hist + 8))) {
+        genes.release(); ng.release(); tm.release(); gm.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpy(genes.p, tx_gene, (size_t)n_tx * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(tm.p, 0, hist);
+    if (e == cudaSuccess) e = cudaMemset(gm.p, 0, hist);
+    if (e == cudaSuccess && ix->d.n_eq)
+        k_class_genes<<<nblocks(ix->d.n_eq, 128), 128>>>(ix->d.eq_off, ix->d.eq_mem, ix->d.n_eq, genes.as<uint32_t>(), ng.as<uint32_t>());
+    if (e == cudaSuccess && ix->d.n_nodes)
+        k_mappability<<<nblocks(ix->d.n_nodes, 128), 128>>>(ix->d.nodes, ix->d.n_nodes, ix->d.k, ix->d.eq_off, ix->d.eq_mem, ng.as<uint32_t>(), bins,
+                                                            tm.as<unsigned long long>(), gm.as<unsigned long long>());
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(tx_multiplicity, tm.p, hist, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(gene_multiplicity, gm.p, hist, cudaMemcpyDeviceToHost);
+    genes.release(); ng.release(); tm.release(); gm.release();
     if (e != cudaSuccess) return fail(PSA_ERR_CUDA, cudaGetErrorString(e));
     return PSA_OK;
 }

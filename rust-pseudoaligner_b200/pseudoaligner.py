@@ -94,7 +94,7 @@ EXPORTS = (
     "psa_memcpy_h2d", "psa_memcpy_d2h", "psa_process_reads", "psa_gather_probe", "psa_result_checksum",
     "psa_selftest_intersect", "psa_mapper_novel_sets", "psa_novel_sets_merge", "psa_novel_sets_free",
     "psa_mapper_novel_allgather", "psa_expand_compact", "psa_debug_str", "psa_index_host_classes",
-    "psa_synth_reads_device",
+    "psa_synth_reads_device", "psa_index_mappability", "psa_build_graph_device", "psa_built_graph_free",
 )
 
 
@@ -170,6 +170,11 @@ def lib():
     L.psa_expand_compact.argtypes = [vp, u64, vp, u64, vp, vp, u64, vp, vp, u64, C.POINTER(u64)]
     L.psa_selftest_intersect.restype = i32
     L.psa_selftest_intersect.argtypes = [i32, vp, u32, vp, u32, vp, u32, C.POINTER(u32 * 3)]
+    L.psa_build_graph_device.restype = i32
+    L.psa_build_graph_device.argtypes = [i32, vp, vp, u32, u32, vp]
+    L.psa_built_graph_free.restype, L.psa_built_graph_free.argtypes = None, [vp]
+    L.psa_index_mappability.restype = i32
+    L.psa_index_mappability.argtypes = [vp, vp, u32, u32, vp, vp]
     L.psa_synth_reads_device.restype = i32
     L.psa_synth_reads_device.argtypes = [i32, vp, u64, u64, u64, u32, vp, u64]
     L.psa_result_checksum.restype = i32
@@ -342,6 +347,16 @@ class Index:
         _check(lib().psa_index_lookup(self.h, _ptr(w), n, _ptr(found), _ptr(node), _ptr(off)))
         return found.astype(bool), node, off
 
+    def mappability(self, tx_gene, bins=11):
+        """mappability::analyze_graph (ref src/mappability.rs:120-156) on the device -> (tx_multiplicity, gene_multiplicity),
+        uint64 [n_tx, bins] each.  tx_gene[t]: an integer naming transcript t's gene."""
+        tx_gene = np.ascontiguousarray(tx_gene, np.uint32)
+        n_tx = len(tx_gene)
+        tm = np.zeros((n_tx, bins), np.uint64)
+        gm = np.zeros((n_tx, bins), np.uint64)
+        _check(lib().psa_index_mappability(self.h, _ptr(tx_gene), n_tx, int(bins), _ptr(tm), _ptr(gm)))
+        return tm, gm
+
     def close(self):
         if getattr(self, "h", None):
             lib().psa_index_destroy(self.h)
@@ -391,6 +406,34 @@ class DeviceBatch:
         for b in (self.data, self.read_off, self.read_len, self.hits, self.tx):
             if b is not None:
                 b.free()
+
+
+class _BuiltGraph(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("reserved", C.c_uint32), ("n_nodes", C.c_uint64), ("n_kmers", C.c_uint64), ("n_eq", C.c_uint64),
+                ("n_seq_words", C.c_uint64), ("n_eq_members", C.c_uint64), ("n_cycles", C.c_uint64),
+                ("seq_words", C.POINTER(C.c_uint64)), ("node_start", C.POINTER(C.c_uint64)), ("node_len", C.POINTER(C.c_uint32)),
+                ("node_exts", C.POINTER(C.c_uint8)), ("node_eq", C.POINTER(C.c_uint32)), ("eq_offsets", C.POINTER(C.c_uint64)),
+                ("eq_members", C.POINTER(C.c_uint32))]
+
+
+def build_graph_device(codes, tx_off, k, device=0):
+    """psa_build_graph_device: the coloured compacted de Bruijn graph built on the GPU -> (flat index dict in the form of
+    psa_index_desc, stats), the same arrays host.build_graph returns."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    tx_off = np.ascontiguousarray(tx_off, dtype=np.uint64)
+    g = _BuiltGraph()
+    _check(lib().psa_build_graph_device(int(device), _ptr(codes), _ptr(tx_off), len(tx_off) - 1, int(k), C.byref(g)))
+    try:
+        def arr(p, n, dt):
+            return np.ctypeslib.as_array(p, shape=(int(n),)).astype(dt, copy=True) if n else np.zeros(0, dt)
+        flat = {"k": int(k), "seq_words": arr(g.seq_words, g.n_seq_words, np.uint64), "node_start": arr(g.node_start, g.n_nodes, np.uint64),
+                "node_len": arr(g.node_len, g.n_nodes, np.uint32), "node_exts": arr(g.node_exts, g.n_nodes, np.uint8),
+                "node_eq": arr(g.node_eq, g.n_nodes, np.uint32), "eq_offsets": arr(g.eq_offsets, g.n_eq + 1, np.uint64),
+                "eq_members": arr(g.eq_members, g.n_eq_members, np.uint32)}
+        stats = {"n_nodes": int(g.n_nodes), "n_kmers": int(g.n_kmers), "n_eq": int(g.n_eq), "n_cycles": int(g.n_cycles)}
+    finally:
+        lib().psa_built_graph_free(C.byref(g))
+    return flat, stats
 
 
 class _SynthTables(C.Structure):
@@ -740,3 +783,27 @@ def process_reads(records, index, outdir=None, num_threads=1, out=None, batch_re
             flush()
     flush()
     return n_reads, n_mapped
+
+
+def _rust_f64(x):
+    """`{}` of an f64 as Rust prints it: the shortest decimal that round-trips, never in exponent form, NaN as `NaN`."""
+    import decimal
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "inf" if x > 0 else "-inf"
+    t = format(decimal.Decimal(repr(float(x))), "f")
+    if "." in t:
+        t = t.rstrip("0").rstrip(".")
+    return t
+
+
+def mappability_tsv(tx_names, gene_names, tx_multiplicity, gene_multiplicity):
+    """tx_mappability.tsv as the reference writes it (ref src/mappability.rs:30-31 header, :74-91 to_tsv / fractions)."""
+    lines = ["tx_name\tgene_name\ttx_kmer_count\tfrac_kmer_unique_tx\tfrac_kmer_unique_gene"]
+    for name, gene, tm, gm in zip(tx_names, gene_names, tx_multiplicity, gene_multiplicity):
+        total = int(np.sum(tm, dtype=np.uint64))
+        fu_tx = float(tm[0]) / total if total else float("nan")
+        fu_gene = float(gm[0]) / total if total else float("nan")
+        lines.append("%s\t%s\t%d\t%s\t%s" % (name, gene, total, _rust_f64(fu_tx), _rust_f64(fu_gene)))
+    return "\n".join(lines) + "\n"

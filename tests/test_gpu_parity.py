@@ -725,3 +725,66 @@ def test_process_reads_block_pipeline(pa_for, orc_index_for, fixture_fastq, tmp_
     fq.write_bytes(text[:cut] + wrapped + text[rest:])
     st = pkg.process_reads_file(str(fq), pa, str(out), num_threads=3)
     assert out.read_bytes().decode().splitlines() == want and st["reads"] == len(want)
+
+
+@pytest.mark.gpu
+def test_device_graph_builder_equals_host_builder(fixture_fasta):
+    """psa_build_graph_device (csrc/psa_build.cu: k-mer sort, colour interning, unitig compaction on the GPU) returns
+    the very arrays of the host builder -- the reference's fixture at the CLI's two k, adversarial transcriptomes
+    (shared exons, repeats, poly-A self loop, tandem cycle) at every k-mer width edge, a synthetic GENCODE-shaped
+    transcriptome -- and an index created from them maps like the oracle."""
+    def same(codes, off, k):
+        want, ws = host.build_graph(codes, off, k)
+        got, gs = pkg.pseudoaligner.build_graph_device(codes, off, k)
+        for key in ("seq_words", "node_start", "node_len", "node_exts", "node_eq", "eq_offsets", "eq_members"):
+            assert np.array_equal(np.asarray(want[key]), got[key]), (k, key)
+        assert gs["n_kmers"] == ws["n_kmers"] and gs["n_nodes"] == ws["n_nodes"] and gs["n_cycles"] == ws.get("n_cycles", gs["n_cycles"])
+        return got, gs
+    codes, off = host.encode_transcripts(fixture_fasta[1])
+    for k in (20, 64):
+        same(codes, off, k)
+    cycles = 0
+    for k in (5, 19, 31, 32, 33, 47, 64):
+        rng = np.random.default_rng(300 + k)
+        seqs = util.random_transcriptome(rng, n_genes=8, k=k)
+        c2, o2 = host.encode_transcripts(seqs)
+        _, gs = same(c2, o2, k)
+        cycles += gs["n_cycles"]
+    assert cycles > 0                                   # the tandem repeats close cycles: the host-side cut ran
+    t = host.Transcriptome.synth(5, 300)
+    flat, _ = same(t.codes(), t.tx_off(), 24)
+    # degenerate inputs: nothing long enough, no transcripts at all
+    got, gs = pkg.pseudoaligner.build_graph_device(np.array([0, 1, 2], np.uint8), np.array([0, 3], np.uint64), 5)
+    assert gs["n_nodes"] == 0 and gs["n_kmers"] == 0 and len(got["eq_offsets"]) == 1
+    with pytest.raises(pkg.PsaError):
+        pkg.pseudoaligner.build_graph_device(np.array([0, 1, 7, 3, 2, 1], np.uint8), np.array([0, 6], np.uint64), 4)   # code > 3
+    # the device-built index maps like the oracle
+    ix = orc.OrcIndex.from_flat(flat)
+    pa = pkg.Pseudoaligner(flat, device=0)
+    reads = [r.tobytes() for r in t.reads(9, 0, 3000, 100)[:300000].reshape(3000, 100)]
+    want_hits, want_tx, _, _ = _oracle(ix, reads)
+    got_hits, got_tx = pa.mapper.map_ascii(reads)
+    _assert_same(reads, got_hits, got_tx, want_hits, want_tx)
+    pa.close()
+    ix.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [20, 64])
+def test_device_mappability_equals_oracle(pa_for, orc_index_for, fixture_fasta, k):
+    names = fixture_fasta[0]
+    genes = [n.split("|")[1] if "|" in n else n for n in names]      # gencode headers: tx|gene|... (ref src/utils.rs:119-130)
+    ids = {g: i for i, g in enumerate(dict.fromkeys(genes))}
+    tx_gene = np.array([ids[g] for g in genes], np.uint32)
+    assert 1 < len(ids) < len(names)
+    ix, pa = orc_index_for(k), pa_for(k)
+    want_tm, want_gm = orc.mappability(ix.flat(), tx_gene)
+    for bins in (11, 3):
+        w_tm, w_gm = (want_tm, want_gm) if bins == 11 else orc.mappability(ix.flat(), tx_gene, bins=bins)
+        tm, gm = pa.index.mappability(tx_gene, bins=bins)
+        assert np.array_equal(tm, w_tm) and np.array_equal(gm, w_gm)
+    assert want_tm[:, 1:].sum() > 0 and (want_gm[:, 0] >= want_tm[:, 0]).all()   # isoforms share k-mers; genes are coarser
+    text = pkg.pseudoaligner.mappability_tsv(names, genes, tm, gm)
+    assert text.count("\n") == len(names) + 1
+    with pytest.raises(pkg.PsaError):
+        pa.index.mappability(tx_gene[:-1])          # a class names a transcript beyond the table
