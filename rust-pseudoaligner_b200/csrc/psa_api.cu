@@ -995,13 +995,13 @@ static int grow_novel_table(psa_mapper* m) {
     }
     CU(cudaMemsetAsync(tab.p, 0, cap * sizeof(NovelEntry), m->st));
     k_novel_rehash<<<nblocks(m->ntab_cap, 256), 256, 0, m->st>>>(m->ntab.as<NovelEntry>(), m->ntab_cap, tab.as<NovelEntry>(), cap);
-    CU(cudaMemcpyAsync(pool.p, m->npool.p, m->npool_cap * 4, cudaMemcpyDeviceToDevice, m->st));
     // entries claimed by the failed attempt whose members did not fit are dropped by the rehash; the member cursor may
     // have run past the old pool: clamp it
     unsigned long long cur[2];
     CU(cudaMemcpyAsync(cur, m->ncur.p, 16, cudaMemcpyDeviceToHost, m->st));
     CU(cudaStreamSynchronize(m->st));
     cur[0] = std::min<unsigned long long>(cur[0], m->npool_cap);
+    CU(cudaMemcpyAsync(pool.p, m->npool.p, cur[0] * 4, cudaMemcpyDeviceToDevice, m->st));   // the members in use
     CU(cudaMemcpyAsync(m->ncur.p, cur, 16, cudaMemcpyHostToDevice, m->st));
     CU(cudaStreamSynchronize(m->st));
     m->ntab.release(); m->npool.release();
@@ -1223,6 +1223,8 @@ static int map_host(psa_mapper* m, const psa_read_batch* r, psa_result_batch* o)
             // H2D
             if (S.in_free_rec) CU(cudaStreamWaitEvent(m->st_h2d, S.in_free, 0));
             CU(cudaMemcpyAsync(S.in_data.p, (const uint8_t*)r->data + P.d0 * unit, P.dn * unit, cudaMemcpyHostToDevice, m->st_h2d));
+            // (the pack kernels read whole aligned words: the bytes behind the last read are masked out, but defined)
+            CU(cudaMemsetAsync((uint8_t*)S.in_data.p + P.dn * unit, 0, 16, m->st_h2d));
             if (r->read_off) CU(cudaMemcpyAsync(S.in_off.p, r->read_off + P.r0, P.nr * 8, cudaMemcpyHostToDevice, m->st_h2d));
             if (r->read_len) CU(cudaMemcpyAsync(S.in_len.p, r->read_len + P.r0, P.nr * 4, cudaMemcpyHostToDevice, m->st_h2d));
             CU(cudaEventRecord(S.in_ready, m->st_h2d));
