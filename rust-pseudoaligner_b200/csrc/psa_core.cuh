@@ -163,11 +163,6 @@ struct PLoad {  // plain pointer (global read buffer, host memory)
     const uint64_t* p;
     PSA_HD uint64_t operator()(uint64_t i) const { return p[i]; }
 };
-struct SLoad {  // strided words: the shared-memory slot of one lane, word j at p[j * stride]
-    const uint64_t* p;
-    uint32_t stride;
-    PSA_HD uint64_t operator()(uint64_t i) const { return p[i * stride]; }
-};
 struct WLoad {  // four consecutive words held in registers, the first one being word `base`
     Sector s;
     uint64_t base;
