@@ -180,7 +180,7 @@ int psa_mapper_set_group_width(psa_mapper*, uint32_t lanes);
  * read over to the cooperative kernel (k_map, group_width lanes per read) when its seed search
  * needs more than max_probes positions, it meets more wide classes than a thread keeps, or all
  * its classes are wide and the smallest has more than max_small members.
- * max_probes = 0 sends every read to the cooperative kernel.  Defaults ceil(k/3)+2 / 32
+ * max_probes = 0 sends every read to the cooperative kernel.  Defaults 3 (ceil(k/3)+2 for an index without the seed-scan filter) / 32
  * (PSA_FAST_PROBES / PSA_FAST_MAX_SMALL).  Results do not depend on it. */
 int psa_mapper_set_fast_path(psa_mapper*, uint32_t max_probes, uint32_t max_small);
 /* Tuning: reads whose FIRST seed search is too long for one thread go to k_seed_scan, where

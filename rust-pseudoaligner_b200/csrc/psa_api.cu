@@ -105,7 +105,7 @@ struct DevBuf {
 struct psa_index {
     int device = 0;
     DevIndex d{};
-    DevBuf buckets, nodes, nodes_cold, seq, eq_off, eq_mem, class_win;
+    DevBuf buckets, nodes, nodes_cold, seq, eq_off, eq_mem, class_win, bloom;
     std::vector<uint64_t> h_eq_off;   // eq_classes on the host too: compact results are expanded from them
     std::vector<uint32_t> h_eq_mem;
     psa_index_info info{};
@@ -167,6 +167,23 @@ static int build_on_device(psa_index* ix, const psa_index_desc* d, double gamma,
             ix->seq.as<uint64_t>(), node_start.as<uint64_t>(), koff.as<uint64_t>(), d->n_nodes, n_kmers, k,
             key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(), val[0].as<uint64_t>());
     CUB_(cudaGetLastError());
+
+    // 1b. the absent-k-mer filter of k_seed_scan (PSA_BLOOM_BITS per key, default 10; 0: none)
+    {
+        double bits = 10.0;
+        if (const char* e = getenv("PSA_BLOOM_BITS")) bits = atof(e);
+        ix->d.bloom = nullptr;
+        ix->d.bloom_blocks = 0;
+        if (bits > 0 && n_kmers) {
+            const uint64_t nb = std::max<uint64_t>(1, (uint64_t)((double)n_kmers * bits / 256.0) + 1);
+            RC_(ix->bloom.ensure(nb * 32));
+            CUB_(cudaMemsetAsync(ix->bloom.p, 0, nb * 32, st));
+            k_bloom_set<KW><<<nblocks(n_kmers, 256), 256, 0, st>>>(key_lo[0].as<uint64_t>(), key_hi[0].as<uint64_t>(), n_kmers, ix->bloom.as<uint32_t>(), nb);
+            CUB_(cudaGetLastError());
+            ix->d.bloom = ix->bloom.as<uint32_t>();
+            ix->d.bloom_blocks = nb;
+        }
+    }
 
     // 2. the dictionary: a cascade of bucket tables (psa_core.cuh Dict).  Level sizes depend on the keys the
     // level before passed on (~5 % at 1.7 slots per key); allocate for the geometric bound and check.
@@ -449,7 +466,7 @@ extern "C" void psa_index_destroy(psa_index* ix) {
     for (auto l : ix->idle_lanes) fq_lane_free(l);
     ix->idle_lanes.clear();
     ix->buckets.release(); ix->nodes.release(); ix->nodes_cold.release();
-    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release();
+    ix->seq.release(); ix->eq_off.release(); ix->eq_mem.release(); ix->class_win.release(); ix->bloom.release();
     delete ix;
 }
 
@@ -682,6 +699,9 @@ extern "C" int psa_mapper_create(psa_index* ix, uint64_t chunk_reads, psa_mapper
     // one substitution knocks out the seeds at positions (e-k, e]: ceil(k/3) stride-3 positions; two more and a
     // read with a single error in its head is seeded by its own thread (measured best on B200)
     m->fast_probes = (ix->d.k + 2) / 3 + 2;
+    // ... unless k_seed_scan has its filter: then a search that misses three times is cheaper there (eight lanes ask the
+    // L2-resident filter, one dictionary probe for the seed) than in a thread that probes alone: 3.62 vs 3.65 ms per batch
+    if (ix->d.bloom) m->fast_probes = 3;
     if (const char* e = getenv("PSA_FAST_PROBES")) m->fast_probes = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_FAST_MAX_SMALL")) m->fast_max_small = (uint32_t)std::max(0, atoi(e));
     if (const char* e = getenv("PSA_OVERLAP_COOP")) m->overlap_coop = atoi(e) != 0;
@@ -901,6 +921,9 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
                 // first pass: a read that has to search for a new seed mid-way is handed to the second pass (when there
                 // is one), so that the other 31 reads of its warp do not wait for the search; second pass: long budget
                 p.reseed_probes = (!hint && m->scan_width) ? std::min(m->reseed_first, reseed_long) : reseed_long;
+                // (a read the first pass handed over at a re-seed search makes its first search again in the second pass:
+                // whatever the first pass's budget was, it finds the seed there)
+                p.max_probes = (hint && m->scan_width) ? std::max(m->fast_probes, (m->ix->d.k + 2) / 3 + 2) : m->fast_probes;
                 launch_map_thread<EV>(m, st, p, hint);
             };
             if ((rc = timed(0, [&]() { fast(false); }))) return rc;

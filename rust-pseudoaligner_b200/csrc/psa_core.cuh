@@ -330,6 +330,9 @@ struct DevIndex {
     const uint64_t* eq_off;
     const uint32_t* eq_mem;
     const struct ClassWin* class_win;  // one 32-byte window per class (cooperative kernel, wide classes)
+    // absent-k-mer filter of k_seed_scan: a split-block Bloom filter over all k-mers, 32-byte blocks (nullptr: none)
+    const uint32_t* bloom;
+    uint64_t bloom_blocks;
     Dict dict;
 };
 
@@ -374,6 +377,26 @@ PSA_HD uint64_t bucket_find(const DevIndex& ix, const Sector& b, KeyHash hk) {
 // true if a key that hashes to this bucket may live in a later level
 PSA_HD bool bucket_more(const Sector& b) { return b.w0 != kEmptyEntry && (b.w0 & kMoreBit) != 0; }
 
+// ---- the filter in front of the dictionary for searches that are mostly misses (k_seed_scan: an unmappable read probes
+// 43 absent k-mers, and a dictionary probe -- any random access -- is a 128-byte DRAM line).  Split-block Bloom filter: a
+// key sets one bit in each of the eight 32-bit words of ONE 32-byte block, so a query is one sector; at ~10 bits per key
+// the filter of a human-scale index (74 MB) stays in L2 for the length of the scan kernel, where nothing else is hot.
+// No false negatives, so dict_get's answer is unchanged; ~1 % of absent keys go on to the dictionary.
+PSA_HD uint64_t bloom_block_of(KeyHash kh, uint64_t n_blocks) {
+    return mulhi64((kh.h1 ^ (kh.h2 >> 17)) * 0x9E3779B97F4A7C15ULL, n_blocks);
+}
+PSA_HD uint64_t bloom_bits_of(KeyHash kh) { return (kh.h2 * 0xD6E8FEB86659FD93ULL) ^ kh.h1; }   // eight 5-bit fields used
+PSA_HD bool bloom_test(const DevIndex& ix, KeyHash kh) {
+    const Sector b = load_sector_hot(reinterpret_cast<const char*>(ix.bloom) + 32 * bloom_block_of(kh, ix.bloom_blocks));
+    const uint64_t x = bloom_bits_of(kh);
+    // words 0..7 of the block are the two halves of w0..w3
+    uint64_t need0 = (1ULL << (x & 31)) | (1ULL << (32 + ((x >> 5) & 31)));
+    uint64_t need1 = (1ULL << ((x >> 10) & 31)) | (1ULL << (32 + ((x >> 15) & 31)));
+    uint64_t need2 = (1ULL << ((x >> 20) & 31)) | (1ULL << (32 + ((x >> 25) & 31)));
+    uint64_t need3 = (1ULL << ((x >> 30) & 31)) | (1ULL << (32 + ((x >> 35) & 31)));
+    return (b.w0 & need0) == need0 && (b.w1 & need1) == need1 && (b.w2 & need2) == need2 && (b.w3 & need3) == need3;
+}
+
 struct ProbeStats {  // sequential-equivalent event counts of one dictionary probe
     uint32_t levels, hit, verified;
 };
@@ -383,8 +406,13 @@ struct ProbeStats {  // sequential-equivalent event counts of one dictionary pro
 // the entry's key differs from `key`, so skipping its unitig fetch cannot change the outcome of
 // the reference's `read_kmer == ref_kmer` test.
 template <int KW>
+PSA_HD bool dict_get_hashed(const DevIndex& ix, Kmer<KW> key, KeyHash hk, uint32_t& node, uint32_t& off, ProbeStats* st);
+template <int KW>
 PSA_HD bool dict_get(const DevIndex& ix, Kmer<KW> key, uint32_t& node, uint32_t& off, ProbeStats* st) {
-    const KeyHash hk = make_hash(KmerOps<KW>::fold(key));
+    return dict_get_hashed<KW>(ix, key, make_hash(KmerOps<KW>::fold(key)), node, off, st);
+}
+template <int KW>
+PSA_HD bool dict_get_hashed(const DevIndex& ix, Kmer<KW> key, KeyHash hk, uint32_t& node, uint32_t& off, ProbeStats* st) {
     if (st) { st->levels = 0; st->hit = 0; st->verified = 0; }
     for (uint32_t lvl = 0; lvl < ix.dict.n_levels; lvl++) {
         const Sector b = load_sector_stream(bucket_addr(ix.dict, hk, lvl));

@@ -505,8 +505,33 @@ struct WarpCtx {
             Kmer<KW> key{};
             if (staged) key = staged_kmer(in ? (uint32_t)p : 0u);
             else if (in) key = KmerOps<KW>::get(rd, p, k);
-            if (in) h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
-            unsigned b = g.ballot(h);
+            unsigned b;
+            if (!EV && scan_mode && ix.bloom) {
+                // k_seed_scan: most of these k-mers are absent, and a dictionary probe is a 128-byte DRAM line plus the
+                // verification loads.  Every lane asks the L2-resident filter; then only the LOWEST position that may be
+                // present goes to the dictionary (for a mappable read that is its seed: one probe instead of up to G, the
+                // positions behind a seed being present as well), the next one only after a false positive.
+                KeyHash hk{0, 0};
+                bool maybe = false;
+                if (in) {
+                    hk = make_hash(KmerOps<KW>::fold(key));
+                    maybe = bloom_test(ix, hk);
+                }
+                unsigned mb = g.ballot(maybe);
+                b = 0;
+                while (mb) {
+                    const int jj = __ffs(mb) - 1;
+                    if ((int)lane == jj) h = dict_get_hashed<KW>(ix, key, hk, n, o, nullptr);
+                    if (g.shfl((int)h, jj)) {
+                        b = 1u << jj;
+                        break;
+                    }
+                    mb &= mb - 1;
+                }
+            } else {
+                if (in) h = dict_get<KW>(ix, key, n, o, EV ? &st : nullptr);
+                b = g.ballot(h);
+            }
             int j = b ? (__ffs(b) - 1) : G;
             if (EV) {  // sequential-equivalent events: the probes up to and including the first hit
                 const bool counted = p <= last && (int)lane <= j;
@@ -666,6 +691,21 @@ __device__ __forceinline__ uint32_t intersect_pass(WarpCtx<KW, EV, G>& w, uint32
         count += __popc(b);
     }
     return count;
+}
+
+// index construction: every k-mer sets its eight bits in the seed-scan filter (psa_core.cuh bloom_*)
+template <int KW>
+__global__ void k_bloom_set(const uint64_t* key_lo, const uint64_t* key_hi, uint64_t n, uint32_t* bloom, uint64_t n_blocks) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Kmer<KW> key;
+    key.lo = key_lo[i];
+    if constexpr (KW == 2) key.hi = key_hi[i];
+    const KeyHash kh = make_hash(KmerOps<KW>::fold(key));
+    uint32_t* blk = bloom + 8 * bloom_block_of(kh, n_blocks);
+    const uint64_t x = bloom_bits_of(kh);
+#pragma unroll
+    for (int j = 0; j < 8; j++) atomicOr(blk + j, 1u << ((x >> (5 * j)) & 31));
 }
 
 // the length the hand-over list has now (k_map's first launch maps exactly these entries while the list keeps growing)
