@@ -382,19 +382,18 @@ PSA_HD bool bucket_more(const Sector& b) { return b.w0 != kEmptyEntry && (b.w0 &
 // key sets one bit in each of the eight 32-bit words of ONE 32-byte block, so a query is one sector; at ~10 bits per key
 // the filter of a human-scale index (74 MB) stays in L2 for the length of the scan kernel, where nothing else is hot.
 // No false negatives, so dict_get's answer is unchanged; ~1 % of absent keys go on to the dictionary.
-PSA_HD uint64_t bloom_block_of(KeyHash kh, uint64_t n_blocks) {
-    return mulhi64((kh.h1 ^ (kh.h2 >> 17)) * 0x9E3779B97F4A7C15ULL, n_blocks);
-}
-PSA_HD uint64_t bloom_bits_of(KeyHash kh) { return (kh.h2 * 0xD6E8FEB86659FD93ULL) ^ kh.h1; }   // eight 5-bit fields used
+PSA_HD uint64_t bloom_block_of(KeyHash kh, uint64_t n_blocks) { return mulhi64(kh.h2, n_blocks); }
+PSA_HD uint64_t bloom_bits_of(KeyHash kh) { return kh.h1; }   // eight 5-bit fields: bits 0..39 (the dictionary uses the top 32)
 PSA_HD bool bloom_test(const DevIndex& ix, KeyHash kh) {
     const Sector b = load_sector_hot(reinterpret_cast<const char*>(ix.bloom) + 32 * bloom_block_of(kh, ix.bloom_blocks));
     const uint64_t x = bloom_bits_of(kh);
-    // words 0..7 of the block are the two halves of w0..w3
-    uint64_t need0 = (1ULL << (x & 31)) | (1ULL << (32 + ((x >> 5) & 31)));
-    uint64_t need1 = (1ULL << ((x >> 10) & 31)) | (1ULL << (32 + ((x >> 15) & 31)));
-    uint64_t need2 = (1ULL << ((x >> 20) & 31)) | (1ULL << (32 + ((x >> 25) & 31)));
-    uint64_t need3 = (1ULL << ((x >> 30) & 31)) | (1ULL << (32 + ((x >> 35) & 31)));
-    return (b.w0 & need0) == need0 && (b.w1 & need1) == need1 && (b.w2 & need2) == need2 && (b.w3 & need3) == need3;
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 30);   // fields 0..5 in xl, 6..7 in xh
+    // words 0..7 of the block are the two halves of w0..w3; 32-bit shifts only
+    const uint32_t hit = ((uint32_t)b.w0 >> (xl & 31)) & ((uint32_t)(b.w0 >> 32) >> ((xl >> 5) & 31)) &
+                         ((uint32_t)b.w1 >> ((xl >> 10) & 31)) & ((uint32_t)(b.w1 >> 32) >> ((xl >> 15) & 31)) &
+                         ((uint32_t)b.w2 >> ((xl >> 20) & 31)) & ((uint32_t)(b.w2 >> 32) >> ((xl >> 25) & 31)) &
+                         ((uint32_t)b.w3 >> (xh & 31)) & ((uint32_t)(b.w3 >> 32) >> ((xh >> 5) & 31));
+    return (hit & 1u) != 0;
 }
 
 struct ProbeStats {  // sequential-equivalent event counts of one dictionary probe
