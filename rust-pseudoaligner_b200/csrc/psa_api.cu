@@ -860,7 +860,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
         if ((rc = m->novel.ensure(m->novel_cap * 4))) return rc;
     }
     if ((rc = m->nlist.ensure((n + 1) * 4)) || (rc = m->nslot.ensure((n + 1) * 4))) return rc;
-    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 128, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] [7] lane kernel's, [8] novel reads listed, [9] list length when k_map's first launch began, [10] claim counter of its second launch
+    CU(cudaMemsetAsync(m->novel_cursor.p, 0, 128, st));  // [0] novel, [1] pool, [2] deferred, [3] to scan, [4] seeded, [5] k_map's claim counter, [6] second pass's claim counter, [7] unused, [8] novel reads listed, [9] list length when k_map's first launch began, [10] claim counter of its second launch
     CU(cudaMemsetAsync(m->status.p, 0, 4, st));
 
     MapParams p{};
@@ -905,6 +905,7 @@ static int enqueue_device_batch(psa_mapper* m, const DeviceBatch& b, bool want_c
             p.list = m->deferred.as<uint32_t>();
             p.list_count = m->novel_cursor.as<unsigned long long>() + 2;
             p.work_cursor = m->novel_cursor.as<unsigned long long>() + 5;
+            p.hint_cursor = m->novel_cursor.as<unsigned long long>() + 6;
             p.max_probes = m->fast_probes;
             p.max_small = m->fast_max_small;
             if (m->scan_width) {

@@ -386,6 +386,7 @@ struct MapParams {
     uint32_t* list;
     unsigned long long* list_count;
     unsigned long long* work_cursor;  // k_map over the list: next entry to claim (zeroed per batch), or nullptr
+    unsigned long long* hint_cursor;  // second pass of k_map_thread: next 32 entries of `seeded` to claim (zeroed per batch)
     // k_map in two launches (the first one overlaps k_seed_scan and the second pass of the thread kernel on another stream):
     const unsigned long long* list_first;  // first entry of this launch (nullptr: 0)
     const unsigned long long* list_end;    // one past its last entry (nullptr: *list_count)
@@ -944,9 +945,16 @@ __global__ void __launch_bounds__(kThreadBlock, PSA_THREAD_MIN_BLOCKS) k_map_thr
     }
     DevSink sink{p};
     const uint64_t n_todo = HINT ? (uint64_t)*p.seeded_count : p.reads.n;
-    const uint64_t stride = HINT ? gridDim.x * (uint64_t)blockDim.x : ~0ULL >> 1;
-    // warp-uniform trip count: the hand-over below uses full-warp votes
-    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); base < n_todo; base += stride) {
+    // Second pass: persistent warps that CLAIM their next 32 entries from a counter (the entries differ widely in cost;
+    // striding over the list left the slowest warp several entries behind).  Warp-uniform trip count either way: the
+    // hand-over below uses full-warp votes.
+    auto next_base = [&](uint64_t) -> uint64_t {
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(p.hint_cursor, 32ULL);
+        return __shfl_sync(kFull, at, 0);
+    };
+    for (uint64_t base = HINT ? next_base(0) : blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); base < n_todo;
+         base = HINT ? next_base(base) : ~0ULL >> 1) {
         const uint64_t it = base + lane;
         const bool live = it < n_todo;
         bool defer = false;
